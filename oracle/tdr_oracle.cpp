@@ -1,0 +1,694 @@
+// =============================================================================
+// tdr_oracle.cpp — CPU restatement of the top_down_render localization hot path.
+//
+// TEST INFRASTRUCTURE ONLY.  Nothing in the product path (the package
+// top_down_renderer_b200/ or libtdr_b200.so) may include, link or call this
+// file.  Only tests/, __graft_entry__.smoke() and bench.py's cpu_baseline /
+// --impl reference legs use it, and only as the checker / CPU baseline.
+//
+// PARITY UNPINNED: the reference (KumarRobotics/top_down_renderer) ships no
+// tests, golden vectors or fixtures, and it cannot be compiled in this image
+// (every header needs ROS, Eigen, OpenCV C++, PCL, TBB — none installed, no
+// network).  This restatement is therefore pinned only by
+//   * cv2.distanceTransform / cv2.threshold (the real third-party routine the
+//     reference calls, top_down_map.cpp:312,315) — tests/test_oracle_edt.py,
+//   * glibc 2.39 libm (atan2f/sqrtf/roundf — the reference's own libm calls),
+//   * libstdc++ <random> (the reference's own RNG),
+//   * a deliberately naive numpy twin (oracle/numpy_twin.py) and hand KATs.
+// Build contract being restated: g++ -O2, no -march (x86-64 baseline, SSE2
+// 4-float Eigen packets, no FMA, no SSE3 hadd), -ffp-contract=off, Eigen
+// 3.3/3.4 reduction orders where an order must be chosen.
+//
+// Citations are file:line relative to the reference checkout.
+// Conventions: Eigen::ArrayXXf(rows, cols) is column-major, element (r, c) at
+// c*rows + r.  Images/layers here are plain float arrays in that layout.
+// =============================================================================
+#include <math.h>   // global float overloads, as in the reference TU (ros.h pulls <math.h>)
+#include <cmath>
+#include <cstdint>
+#include <cstring>
+#include <cfloat>
+#include <climits>
+#include <vector>
+#include <algorithm>
+#include <thread>
+#include <random>
+#include <limits>
+
+#define ORC_API extern "C" __attribute__((visibility("default")))
+
+namespace {
+
+// x86-64 cvttss2si semantics: NaN / out-of-range -> INT_MIN ("integer indefinite").
+// The reference relies on this implicitly (float -> int assignments).
+inline int f2i_x86(float v) {
+  if (!(v > -2147483904.0f && v < 2147483648.0f)) return INT_MIN;
+  return (int)v;
+}
+inline int d2i_x86(double v) {
+  if (!(v > -2147483649.0 && v < 2147483648.0)) return INT_MIN;
+  return (int)v;
+}
+
+// Eigen SSE2 predux<Packet4f>: (a0+a2)+(a1+a3)  (no SSE3 hadd in a flag-less build)
+inline float predux4(const float p[4]) { return (p[0] + p[2]) + (p[1] + p[3]); }
+
+// Eigen redux_impl<LinearVectorizedTraversal, NoUnrolling> for a sum over a
+// 16-byte-aligned contiguous float vector (Eigen/src/Core/Redux.h).  Used by
+// weights_.sum() (particle_filter.cpp:135,142).
+float eigen_linear_sum(const float* x, long size) {
+  if (size == 0) return 0.f;  // DenseBase::sum() special-cases empty
+  const long ps = 4;
+  const long alignedSize2 = (size / (2 * ps)) * (2 * ps);
+  const long alignedSize = (size / ps) * ps;
+  float res;
+  if (alignedSize) {
+    float p0[4] = {x[0], x[1], x[2], x[3]};
+    if (alignedSize > ps) {
+      float p1[4] = {x[4], x[5], x[6], x[7]};
+      for (long i = 2 * ps; i < alignedSize2; i += 2 * ps) {
+        for (int k = 0; k < 4; k++) p0[k] = p0[k] + x[i + k];
+        for (int k = 0; k < 4; k++) p1[k] = p1[k] + x[i + ps + k];
+      }
+      for (int k = 0; k < 4; k++) p0[k] = p0[k] + p1[k];
+      if (alignedSize > alignedSize2)
+        for (int k = 0; k < 4; k++) p0[k] = p0[k] + x[alignedSize2 + k];
+    }
+    res = predux4(p0);
+    for (long i = alignedSize; i < size; i++) res = res + x[i];
+  } else {
+    res = x[0];
+    for (long i = 1; i < size; i++) res = res + x[i];
+  }
+  return res;
+}
+
+// Eigen redux_impl<SliceVectorizedTraversal> for (A.block * B.block).sum() where
+// both blocks are `inner` consecutive rows of column-major arrays with `outer`
+// columns and column stride `ld` (state_particle.cpp:136-142).
+float eigen_slice_prod_sum(const float* a, const float* b, long inner, long outer, long ld) {
+  if (inner == 0 || outer == 0) return 0.f;  // DenseBase::sum() on an empty expression
+  const long ps = 4;
+  const long pin = (inner / ps) * ps;
+  float res;
+  if (pin) {
+    float p[4];
+    for (int k = 0; k < 4; k++) p[k] = a[k] * b[k];
+    for (long j = 0; j < outer; j++)
+      for (long i = (j == 0 ? ps : 0); i < pin; i += ps)
+        for (int k = 0; k < 4; k++) p[k] = p[k] + a[j * ld + i + k] * b[j * ld + i + k];
+    res = predux4(p);
+    for (long j = 0; j < outer; j++)
+      for (long i = pin; i < inner; i++) res = res + a[j * ld + i] * b[j * ld + i];
+  } else {
+    // DefaultTraversal: coeff(0,0) then column-major order
+    res = a[0] * b[0];
+    for (long i = 1; i < inner; i++) res = res + a[i] * b[i];
+    for (long j = 1; j < outer; j++)
+      for (long i = 0; i < inner; i++) res = res + a[j * ld + i] * b[j * ld + i];
+  }
+  return res;
+}
+
+}  // namespace
+
+// -----------------------------------------------------------------------------
+// a1  ScanRendererPolar::renderSemanticTopDown   src/scan_renderer_polar.cpp:83-109
+// pts: AoS, x,y at byte offsets 0,4, intensity at byte offset `intensity_off`
+// (pcl::PointXYZI: 16).  imgs: C images, each n_theta x n_r column-major.
+// Deviation: the reference indexes flatten_lut_[pt_class] unchecked (UB when
+// out of range); here an out-of-range class drops the point.
+// -----------------------------------------------------------------------------
+ORC_API void orc_render_polar(const uint8_t* pts, int stride, int intensity_off, long n,
+                              float res, float ang_res, int n_theta, int n_r,
+                              const int* lut, int n_lut, int C, float* imgs) {
+  if (C < 1) return;                                      // :85
+  std::memset(imgs, 0, sizeof(float) * (size_t)C * n_theta * n_r);  // :88-90
+  for (long idx = 0; idx < n; idx++) {                    // :93
+    float x, y, inten;
+    std::memcpy(&x, pts + idx * stride + 0, 4);
+    std::memcpy(&y, pts + idx * stride + 4, 4);
+    std::memcpy(&inten, pts + idx * stride + intensity_off, 4);
+    if (x == 0 && y == 0) continue;                       // :95
+    float theta = atan2(x, y);                            // :97 (float overload -> atan2f)
+    float r = sqrt(x * x + y * y);                        // :98
+    int theta_ind = f2i_x86(std::round(theta / ang_res) + n_theta / 2);  // :100
+    int r_ind = f2i_x86(std::round(r / res));             // :101
+    if (theta_ind >= 0 && theta_ind < n_theta && r_ind >= 0 && r_ind < n_r) {  // :102
+      int pt_class = f2i_x86(inten);                      // :103
+      if (pt_class < 0 || pt_class >= n_lut) continue;    // (UB in the reference)
+      int f = lut[pt_class];
+      if (f >= 0 && f < C) imgs[(size_t)f * n_theta * n_r + (size_t)r_ind * n_theta + theta_ind] += 1;  // :104-105
+    }
+  }
+}
+
+// a2  ScanRenderer::renderSemanticTopDown   src/scan_renderer.cpp:55-78
+// imgs: C images rows x cols column-major; (y_ind, x_ind) -> x_ind*rows + y_ind.
+ORC_API void orc_render_cart(const uint8_t* pts, int stride, int intensity_off, long n, float res,
+                             int rows, int cols, const int* lut, int n_lut, int C, float* imgs) {
+  if (C < 1) return;
+  std::memset(imgs, 0, sizeof(float) * (size_t)C * rows * cols);
+  for (long idx = 0; idx < n; idx++) {
+    float x, y, inten;
+    std::memcpy(&x, pts + idx * stride + 0, 4);
+    std::memcpy(&y, pts + idx * stride + 4, 4);
+    std::memcpy(&inten, pts + idx * stride + intensity_off, 4);
+    if (x == 0 && y == 0) continue;                                   // :67
+    int x_ind = f2i_x86(std::round(x / res) + cols / 2);              // :69  img_size[0] = cols
+    int y_ind = f2i_x86(std::round(y / res) + rows / 2);              // :70
+    if (x_ind >= 0 && x_ind < cols && y_ind >= 0 && y_ind < rows) {   // :71
+      int pt_class = f2i_x86(inten);
+      if (pt_class < 0 || pt_class >= n_lut) continue;
+      int f = lut[pt_class];
+      if (f >= 0 && f < C) imgs[(size_t)f * rows * cols + (size_t)x_ind * rows + y_ind] += 1;  // :74
+    }
+  }
+}
+
+// -----------------------------------------------------------------------------
+// a3  TopDownMap::loadCompressedRasterMap   src/top_down_map.cpp:116-144
+// img: row-major uint8 (cv::Mat) h_img x w_img with row stride `stride`.
+// layers: C layers rows x cols column-major, rows=(int)(h_img/res), cols=(int)(w_img/res).
+// Deviation: flatten_lut is indexed unchecked in the reference; here an index
+// beyond n_lut means "no class" (the adapters pad the LUT to 256 x -1).
+// -----------------------------------------------------------------------------
+ORC_API void orc_map_dims(int h_img, int w_img, float res, int* rows, int* cols) {
+  *rows = (int)(h_img / res);  // :121
+  *cols = (int)(w_img / res);  // :122
+}
+
+ORC_API void orc_class_image_to_layers(const uint8_t* img, int h_img, int w_img, int stride,
+                                       const int* lut, int n_lut, int C, float res, float* layers) {
+  int rows, cols;
+  orc_map_dims(h_img, w_img, res, &rows, &cols);
+  const size_t L = (size_t)rows * cols;
+  for (size_t i = 0; i < L * C; i++) layers[i] = 1.0f;   // :120-123
+  for (size_t xi = 0; xi < (size_t)cols; xi++) {         // :135
+    for (size_t yi = 0; yi < (size_t)rows; yi++) {       // :136
+      // :137  map.size().height - yi*resolution - 1  : int - (size_t->float * float) - int, in float
+      int src_row = std::max<int>(f2i_x86((float)h_img - (float)yi * res - 1), 0);
+      int src_col = std::min<int>(f2i_x86((float)xi * res), w_img - 1);      // :138
+      uint8_t v = img[(size_t)src_row * stride + src_col];
+      int cls = (v < n_lut) ? lut[v] : -1;
+      if (cls >= 0 && cls < C) layers[(size_t)cls * L + xi * rows + yi] = 0;  // :139-141
+    }
+  }
+}
+
+// -----------------------------------------------------------------------------
+// a4  TopDownMap::computeDists   src/top_down_map.cpp:289-326
+// In place over C column-major layers (rows x cols); mask out: rows x cols uint8.
+// EDT: exact integer squared distance (two-pass lower envelope, integer
+// arithmetic) then sqrtf((float)d2) — what cv::distanceTransform(DIST_L2,
+// DIST_MASK_PRECISE) returns (verified against cv2 in tests/test_oracle_edt.py).
+// -----------------------------------------------------------------------------
+namespace {
+const int64_t EDT_INF = (int64_t)1 << 40;
+
+// 1D squared-distance transform of f (Felzenszwalb & Huttenlocher), integer-exact.
+void dt1d(const int64_t* f, int n, int64_t* d, int* v, double* z) {
+  int k = -1;
+  for (int q = 0; q < n; q++) {
+    if (f[q] >= EDT_INF) continue;
+    while (true) {
+      if (k < 0) { k = 0; v[0] = q; z[0] = -1e30; z[1] = 1e30; break; }
+      int p = v[k];
+      // intersection of parabolas rooted at p and q
+      double s = ((double)(f[q] + (int64_t)q * q) - (double)(f[p] + (int64_t)p * p)) / (2.0 * (q - p));
+      if (s <= z[k]) { k--; continue; }
+      k++; v[k] = q; z[k] = s; z[k + 1] = 1e30; break;
+    }
+  }
+  if (k < 0) { for (int q = 0; q < n; q++) d[q] = EDT_INF; return; }
+  int j = 0;
+  for (int q = 0; q < n; q++) {
+    while (z[j + 1] < q) j++;
+    // exactness guard: the envelope search uses doubles; re-check neighbours in integers
+    int64_t best = (int64_t)(q - v[j]) * (q - v[j]) + f[v[j]];
+    if (j > 0) best = std::min(best, (int64_t)(q - v[j - 1]) * (q - v[j - 1]) + f[v[j - 1]]);
+    if (j < k) best = std::min(best, (int64_t)(q - v[j + 1]) * (q - v[j + 1]) + f[v[j + 1]]);
+    d[q] = best;
+  }
+}
+}  // namespace
+
+// exact squared EDT of a binary image (seed where bin==0); out d2 (int64), col-major agnostic:
+// treats the buffer as an n0 (fast) x n1 (slow) grid.
+ORC_API void orc_edt_sq(const uint8_t* bin, int n0, int n1, int64_t* d2) {
+  std::vector<int64_t> tmp((size_t)n0 * n1);
+  // pass 1: along the fast axis
+  {
+    int n = std::max(n0, n1);
+    std::vector<int64_t> f(n), d(n); std::vector<int> v(n + 1); std::vector<double> z(n + 2);
+    for (int j = 0; j < n1; j++) {
+      for (int i = 0; i < n0; i++) f[i] = bin[(size_t)j * n0 + i] == 0 ? 0 : EDT_INF;
+      dt1d(f.data(), n0, d.data(), v.data(), z.data());
+      for (int i = 0; i < n0; i++) tmp[(size_t)j * n0 + i] = d[i];
+    }
+    for (int i = 0; i < n0; i++) {
+      for (int j = 0; j < n1; j++) f[j] = tmp[(size_t)j * n0 + i];
+      dt1d(f.data(), n1, d.data(), v.data(), z.data());
+      for (int j = 0; j < n1; j++) d2[(size_t)j * n0 + i] = d[j];
+    }
+  }
+}
+
+ORC_API void orc_compute_dists(float* layers, int rows, int cols, int C, float resolution, uint8_t* mask) {
+  const size_t L = (size_t)rows * cols;
+  // :294-299  mask = sum_c (uint8)layer_c ; threshold(mask, C-1, 255, BINARY)
+  for (size_t i = 0; i < L; i++) {
+    uint8_t m = 0;
+    for (int c = 0; c < C; c++) m = (uint8_t)(m + (uint8_t)layers[(size_t)c * L + i]);  // Eigen cast<uint8_t>: truncation
+    mask[i] = (m > C - 1) ? 255 : 0;
+  }
+  std::vector<uint8_t> bin(L);
+  std::vector<int64_t> d2(L);
+  for (int c = 0; c < C; c++) {
+    float* lay = layers + (size_t)c * L;
+    // :306 convertTo(CV_8UC1): saturate_cast<uchar>(cvRound(v)) — round half to even
+    for (size_t i = 0; i < L; i++) {
+      float v = lay[i];
+      long r = lrintf(v);  // default rounding mode = nearest-even = cvRound
+      bin[i] = (uint8_t)std::min<long>(std::max<long>(r, 0), 255);
+    }
+    orc_edt_sq(bin.data(), rows, cols, d2.data());   // :312
+    for (size_t i = 0; i < L; i++) {
+      float d = (d2[i] >= EDT_INF) ? 65536.0f : sqrtf((float)d2[i]);
+      d = d * resolution;                            // :314
+      d = (d > 50.0f) ? 50.0f : d;                   // :315 THRESH_TRUNC
+      if (mask[i]) d = 0;                            // :317
+      lay[i] = d;
+    }
+  }
+  for (size_t i = 0; i < L; i++) mask[i] /= 255;     // :321
+}
+
+// a5  TopDownMap::getGeoRasterMap   src/top_down_map.cpp:410-427 (binary class layers in, 2 geo layers out)
+ORC_API void orc_geo_raster(const float* class_layers, int rows, int cols, int C, float* geo) {
+  const size_t L = (size_t)rows * cols;
+  for (size_t i = 0; i < 2 * L; i++) geo[i] = 0;                       // :413-415
+  for (int c = 3; c < C; c++)
+    for (size_t i = 0; i < L; i++) geo[L + i] += 1 - class_layers[(size_t)c * L + i];  // :417-419
+  for (int g = 0; g < 2; g++)
+    for (size_t i = 0; i < L; i++) { float v = std::min(geo[g * L + i], 1.0f); geo[g * L + i] = 1 - v; }  // :422-425
+  for (size_t i = 0; i < L; i++) geo[i] = 1 - geo[L + i];              // :426
+}
+
+// -----------------------------------------------------------------------------
+// a6  polar offset table: TopDownMap::samplePts (:367-389, NDEBUG semantics) +
+// TopDownMapPolar::samplePtsPolar (src/top_down_map_polar.cpp:7-19).
+// tab: 2 x P (tab[2*p+0] = cos*rho -> row offset, tab[2*p+1] = sin*rho -> col offset).
+// NOTE: the reference evaluates Eigen's packet cos/sin; libm cosf/sinf is used
+// here.  The table is an INPUT to both the oracle and the device library, so
+// this choice does not enter any parity comparison.
+// -----------------------------------------------------------------------------
+ORC_API void orc_polar_table(int n_theta, int n_r, float ang_res, float resolution, float* tab) {
+  const int P = n_theta * n_r;
+  // LinSpaced(rows, -res*(rows-1)/2., res*(rows-1)/2.) with res = 1, step == 1 exactly
+  const float lo0 = (float)(-1.0f * (n_theta - 1) / 2.);
+  const float lo1 = (float)(-1.0f * (n_r - 1) / 2.);
+  const float inv_res = (float)(1. / resolution);          // row(1) *= 1./resolution (scalar cast to float)
+  for (int p = 0; p < P; p++) {
+    float a0 = lo0 + (float)(p % n_theta) * 1.0f;          // :376 (rot = 0: rotation is exact identity)
+    float a1 = lo1 + (float)(p / n_theta) * 1.0f;          // :378
+    a1 = a1 + (-lo1);                                      // polar :11 shift radius to start at 0
+    a0 = a0 * ang_res;                                     // :13
+    a1 = a1 * inv_res;                                     // :14
+    tab[2 * p + 0] = cosf(a0) * a1;                        // :17
+    tab[2 * p + 1] = sinf(a0) * a1;                        // :18
+  }
+}
+
+// -----------------------------------------------------------------------------
+// a7  TopDownMapPolar::getLocalMap   src/top_down_map_polar.cpp:21-53
+// layers: C col-major rows x cols (post-computeDists), mask rows x cols.
+// dists: C x P, mask_out: P.
+// -----------------------------------------------------------------------------
+ORC_API void orc_local_map_polar(const float* layers, const uint8_t* mask, int rows, int cols, int C,
+                                 float resolution, const float* tab, int P, float cx, float cy,
+                                 float scale, float res, float* dists, uint8_t* mask_out) {
+  if (C < 1) return;
+  const size_t L = (size_t)rows * cols;
+  const float oy = cy / resolution, ox = cx / resolution;
+  for (int p = 0; p < P; p++) {
+    float q0 = tab[2 * p + 0] * scale * res;   // :28 (ang_sample_pts_*scale)*res
+    float q1 = tab[2 * p + 1] * scale * res;
+    q0 = q0 + oy;                              // :29 row(0) += center[1]/resolution
+    q1 = q1 + ox;                              // :30
+    int r = f2i_x86(std::round(q0));           // :31 round half away, cast<int>
+    int c = f2i_x86(std::round(q1));
+    bool in = r >= 0 && r < rows && c >= 0 && c < cols;
+    for (int k = 0; k < C; k++) dists[(size_t)k * P + p] = in ? layers[(size_t)k * L + (size_t)c * rows + r] : 0.f;  // :33-42
+    mask_out[p] = in ? mask[(size_t)c * rows + r] : 1;  // :44-52
+  }
+}
+
+// a8  TopDownMap::getLocalMap (Cartesian)   src/top_down_map.cpp:429-459 with samplePts :367-389
+ORC_API void orc_local_map_cart(const float* layers, const uint8_t* mask, int rows, int cols, int C,
+                                float resolution, float cx, float cy, float rot, float res,
+                                int out_rows, int out_cols, float* dists, uint8_t* mask_out) {
+  if (C < 1) return;
+  const size_t L = (size_t)rows * cols;
+  const int P = out_rows * out_cols;
+  const float sres = res / resolution;                       // :434
+  const float c0 = cx / resolution, c1 = cy / resolution;
+  // LinSpaced(rows, -res*(rows-1)/2., res*(rows-1)/2.) : float*int -> float, /2. -> double, -> float
+  auto linsp = [](int size, float sres_, int i) -> float {
+    float low = (float)(-sres_ * (size - 1) / 2.);
+    float high = (float)(sres_ * (size - 1) / 2.);
+    if (size == 1) return low;  // Eigen: m_size1 = 1, step = 0 -> i==m_size1 never for i=0 -> low + 0
+    float step = (high - low) / (float)(size - 1);
+    bool flip = std::abs(high) < std::abs(low);
+    int size1 = size - 1;
+    if (flip) return (i == 0) ? low : (high - (float)(size1 - i) * step);
+    return (i == size1) ? high : (low + (float)i * step);
+  };
+  const float cr = cosf(rot), sr = sinf(rot);                // :383 cos(rot) float overload
+  for (int p = 0; p < P; p++) {
+    float x = linsp(out_rows, sres, p % out_rows);           // pts(0,p)
+    float y = linsp(out_cols, sres, p / out_rows);           // pts(1,p)
+    // rotm * pts : [c -s; s c]   (2x2 * 2xN product, no FMA in a baseline build)
+    float xr = cr * x + (-sr) * y;
+    float yr = sr * x + cr * y;
+    xr = xr + c1;                                            // :387 x_vals += center[1]
+    yr = yr + c0;                                            // :388 y_vals += center[0]
+    int r = f2i_x86(std::round(xr));                         // :437
+    int c = f2i_x86(std::round(yr));
+    bool in = r >= 0 && r < rows && c >= 0 && c < cols;
+    for (int k = 0; k < C; k++) dists[(size_t)k * P + p] = in ? layers[(size_t)k * L + (size_t)c * rows + r] : 0.f;
+    mask_out[p] = in ? mask[(size_t)c * rows + r] : 1;
+  }
+}
+
+// -----------------------------------------------------------------------------
+// State / FilterParams mirrors   include/top_down_render/state_particle.h:9-38
+// -----------------------------------------------------------------------------
+struct OrcState {
+  float init_x_px, init_y_px, dx_m, dy_m, theta, scale;
+  uint8_t have_init; uint8_t pad[3];
+};
+static_assert(sizeof(OrcState) == 28, "State is 28 bytes");
+
+struct OrcFilterParams {
+  float regularization;
+  int force_on_map;
+  float fixed_scale, scale_log_min, scale_log_max;
+  float map_width, map_height;     // StateParticle::width_/height_ (state_particle.cpp:46-47)
+  int num_classes;
+  float class_weights[16];
+};
+
+// rot -> row shift   state_particle.cpp:123-128
+ORC_API int orc_rot_to_shift(float rot, int num_bins) {
+  int rot_shift = d2i_x86(std::round((double)(rot * num_bins / 2) / M_PI));
+  if (rot_shift == INT_MIN) return 0;  // NaN/inf rot: reference loops forever; not reachable with finite theta
+  while (rot_shift >= num_bins) rot_shift -= num_bins;
+  while (rot_shift < 0) rot_shift += num_bins;
+  return rot_shift;
+}
+
+// theta-search candidate list   state_particle.cpp:197   for (float t=0; t<2*M_PI; t+=2*M_PI/40)
+ORC_API int orc_search_list(int num_bins, float* thetas, int* shifts, int cap) {
+  int n = 0;
+  for (float t = 0; t < 2 * M_PI; t += 2 * M_PI / 40) {
+    if (n < cap) { thetas[n] = t; shifts[n] = orc_rot_to_shift(t, num_bins); }
+    n++;
+  }
+  return n;
+}
+
+// a10  StateParticle::getCostForRot   src/state_particle.cpp:112-155
+// scan: C x (n_theta x n_r) col-major; classes likewise (the gathered local map);
+// known = 1 - mask (float, n_theta x n_r).
+ORC_API float orc_cost_for_shift(const float* scan, const float* classes, const float* known,
+                                 int n_theta, int n_r, int C, const float* class_weights, int rot_shift) {
+  const int P = n_theta * n_r;
+  // :117  static_cast<float>(mask.sum())/mask.size() < 0.5   (integer-valued float sum: exact in any order)
+  float ksum = eigen_linear_sum(known, P);
+  if ((double)(ksum / (float)(long)P) < 0.5) return std::numeric_limits<float>::quiet_NaN();
+  float cost = 0, normalization = 0;
+  const int s = rot_shift, t = n_theta - rot_shift;
+  for (int i = 0; i < C; i++) {
+    const float* sc = scan + (size_t)i * P;
+    const float* cl = classes + (size_t)i * P;
+    // :136  scan.topRows(s) * classes.bottomRows(s)
+    float S1 = eigen_slice_prod_sum(sc, cl + t, s, n_r, n_theta);
+    cost = (float)((double)cost + (double)S1 * 0.01 * (double)class_weights[i]);
+    // :138  scan.bottomRows(N-s) * classes.topRows(N-s)
+    float S2 = eigen_slice_prod_sum(sc + s, cl, t, n_r, n_theta);
+    cost = (float)((double)cost + (double)S2 * 0.01 * (double)class_weights[i]);
+    normalization += eigen_slice_prod_sum(sc, known + t, s, n_r, n_theta);      // :141
+    normalization += eigen_slice_prod_sum(sc + s, known, t, n_r, n_theta);      // :142
+  }
+  return cost / normalization;   // :154
+}
+
+// a9  StateParticle::computeWeight   src/state_particle.cpp:157-219
+// Returns the weight; updates st->theta / st->have_init as the reference does.
+// geo_layers may be null; if non-null the (unused) geo gather of :189 is performed ("literal" cost).
+static float compute_weight_impl(OrcState* st, const OrcFilterParams* fp, const float* layers,
+                                 const uint8_t* mask, const float* geo_layers, int rows, int cols,
+                                 float resolution, const float* tab, int n_theta, int n_r,
+                                 const float* scan, float res, const float* search_thetas,
+                                 const int* search_shifts, int n_search) {
+  const int C = fp->num_classes, P = n_theta * n_r;
+  float cx = st->dx_m * st->scale + st->init_x_px;   // :161
+  float cy = st->dy_m * st->scale + st->init_y_px;   // :162
+  if (fp->force_on_map) {                            // :163-168
+    if (cx < 0 || cy < 0 || cx > fp->map_width || cy > fp->map_height) return 0;
+  }
+  if (fp->fixed_scale < 0) {                         // :169-176
+    if ((double)st->scale < std::pow(10, fp->scale_log_min) || (double)st->scale > std::pow(10, fp->scale_log_max)) return 0;
+  }
+  // :178-186 per-particle allocations, kept literally
+  std::vector<float> classes((size_t)C * P);
+  std::vector<uint8_t> m(P);
+  orc_local_map_polar(layers, mask, rows, cols, C, resolution, tab, P, cx, cy, st->scale, res, classes.data(), m.data());  // :188
+  if (geo_layers) {                                  // :189 result unused (:145-152 commented out)
+    std::vector<float> geo((size_t)2 * P);
+    std::vector<uint8_t> gm(P);
+    orc_local_map_polar(geo_layers, mask, rows, cols, 2, resolution, tab, P, cx, cy, st->scale, res, geo.data(), gm.data());
+  }
+  std::vector<float> known(P);
+  float best_cost = std::numeric_limits<float>::max();   // :193
+  float best_theta = 0;
+  if (!st->have_init) {                                  // :195-206
+    for (int k = 0; k < n_search; k++) {
+      for (int p = 0; p < P; p++) known[p] = 1 - (float)m[p];   // :199 temp rebuilt per call
+      float cost = orc_cost_for_shift(scan, classes.data(), known.data(), n_theta, n_r, C, fp->class_weights, search_shifts[k]);
+      if (cost < best_cost) { best_cost = cost; best_theta = search_thetas[k]; }
+    }
+    st->theta = best_theta;
+    st->have_init = 1;
+  } else {
+    for (int p = 0; p < P; p++) known[p] = 1 - (float)m[p];
+    best_cost = orc_cost_for_shift(scan, classes.data(), known.data(), n_theta, n_r, C, fp->class_weights,
+                                   orc_rot_to_shift(st->theta, n_theta));   // :208-209
+  }
+  return (float)(1. / (double)(best_cost + fp->regularization));   // :212
+}
+
+ORC_API float orc_compute_weight(OrcState* st, const OrcFilterParams* fp, const float* layers,
+                                 const uint8_t* mask, const float* geo_layers, int rows, int cols,
+                                 float resolution, const float* tab, int n_theta, int n_r,
+                                 const float* scan, float res, const float* search_thetas,
+                                 const int* search_shifts, int n_search) {
+  return compute_weight_impl(st, fp, layers, mask, geo_layers, rows, cols, resolution, tab, n_theta, n_r,
+                             scan, res, search_thetas, search_shifts, n_search);
+}
+
+// ParticleFilter::update :104-105 — the for_each(par) region; threads stand in for TBB.
+ORC_API void orc_score_all(OrcState* states, long n, const OrcFilterParams* fp, const float* layers,
+                           const uint8_t* mask, const float* geo_layers, int rows, int cols, float resolution,
+                           const float* tab, int n_theta, int n_r, const float* scan, float res,
+                           const float* search_thetas, const int* search_shifts, int n_search,
+                           float* weights, int n_threads) {
+  if (n_threads < 1) n_threads = 1;
+  auto work = [&](int t) {
+    long lo = n * t / n_threads, hi = n * (t + 1) / n_threads;
+    for (long i = lo; i < hi; i++)
+      weights[i] = compute_weight_impl(&states[i], fp, layers, mask, geo_layers, rows, cols, resolution, tab,
+                                       n_theta, n_r, scan, res, search_thetas, search_shifts, n_search);
+  };
+  if (n_threads == 1) { work(0); return; }
+  std::vector<std::thread> th;
+  for (int t = 0; t < n_threads; t++) th.emplace_back(work, t);
+  for (auto& x : th) x.join();
+}
+
+// Exhaustive grid (BASELINE cfg4): value of getCostForRot at every (centre, shift).
+// costs: n_centres x n_shifts.  No counterpart function in the reference; composition of a7 + a10.
+ORC_API void orc_cost_grid(const float* centers_xy, long n, float scale, const OrcFilterParams* fp,
+                           const float* layers, const uint8_t* mask, int rows, int cols, float resolution,
+                           const float* tab, int n_theta, int n_r, const float* scan, float res,
+                           const int* shifts, int n_shifts, float* costs, int n_threads) {
+  const int C = fp->num_classes, P = n_theta * n_r;
+  if (n_threads < 1) n_threads = 1;
+  auto work = [&](int t) {
+    std::vector<float> classes((size_t)C * P), known(P);
+    std::vector<uint8_t> m(P);
+    long lo = n * t / n_threads, hi = n * (t + 1) / n_threads;
+    for (long i = lo; i < hi; i++) {
+      orc_local_map_polar(layers, mask, rows, cols, C, resolution, tab, P, centers_xy[2 * i], centers_xy[2 * i + 1],
+                          scale, res, classes.data(), m.data());
+      for (int p = 0; p < P; p++) known[p] = 1 - (float)m[p];
+      for (int k = 0; k < n_shifts; k++)
+        costs[i * n_shifts + k] = orc_cost_for_shift(scan, classes.data(), known.data(), n_theta, n_r, C,
+                                                     fp->class_weights, shifts[k]);
+    }
+  };
+  std::vector<std::thread> th;
+  for (int t = 0; t < n_threads; t++) th.emplace_back(work, t);
+  for (auto& x : th) x.join();
+}
+
+// -----------------------------------------------------------------------------
+// a11  ParticleFilter::update — weights   src/particle_filter.cpp:107-147
+// The three `int i;` loop counters are uninitialised in the reference (UB); the
+// intended i = 0 is used.  w: in raw weights, out normalised.  Returns arg-max.
+// stats (optional, 6 floats): sum, num_valid, mean, bottom_stddev, num_under, fallback
+// -----------------------------------------------------------------------------
+ORC_API long orc_normalize(float* w, const float* last_dist, long n, float* stats) {
+  float sum = 0; int num_valid = 0;
+  for (long i = 0; i < n; i++) {                       // :110-116
+    if (!std::isnan(w[i])) { sum += w[i]; ++num_valid; }
+  }
+  float mean = sum / num_valid;                        // :117
+  float bottom_stddev = 0; int num_under = 0;
+  for (long i = 0; i < n; i++) {                       // :120-125
+    if (!std::isnan(w[i]) && w[i] < mean) {
+      bottom_stddev += std::pow(w[i] - mean, 2);       // pow(float,int) -> double; float += double
+      ++num_under;
+    }
+  }
+  bottom_stddev = std::sqrt(bottom_stddev / num_under);  // :126 (float)
+  int fallback = 0;
+  if (sum == 0 || num_under < 1) {                     // :129-131
+    for (long i = 0; i < n; i++) w[i] = 1;
+    fallback = 1;
+  } else {
+    float rep = mean - bottom_stddev;                  // :133
+    for (long i = 0; i < n; i++) if (std::isnan(w[i])) w[i] = rep;
+  }
+  float s1 = eigen_linear_sum(w, n);                   // :135
+  for (long i = 0; i < n; i++) w[i] = w[i] / s1;
+  for (long i = 0; i < n; i++) {                       // :138-141
+    float d = std::min<float>(last_dist[i] * 5, 1);
+    w[i] = d * w[i] + (1 - d) / (float)(size_t)n;
+  }
+  float s2 = eigen_linear_sum(w, n);                   // :142
+  for (long i = 0; i < n; i++) w[i] = w[i] / s2;
+  long arg = 0; float best = w[0];                     // :145-146 maxCoeff: first maximum
+  for (long i = 1; i < n; i++) if (w[i] > best) { best = w[i]; arg = i; }
+  if (stats) { stats[0] = sum; stats[1] = (float)num_valid; stats[2] = mean; stats[3] = bottom_stddev;
+               stats[4] = (float)num_under; stats[5] = (float)fallback; }
+  return arg;
+}
+
+// a12  systematic resample   src/particle_filter.cpp:172-185
+// literal O(N*M) form.
+ORC_API void orc_resample_literal(const float* w, long n, float shift, int M, int* idx) {
+  for (int i = 0; i < M; i++) {
+    float running_sum = 0;
+    float sample = ((float)i + shift) / M;   // float / int -> float
+    long j = 0;
+    for (; j < n; j++) {
+      running_sum += w[j];
+      if (running_sum > sample || j == n - 1) break;
+    }
+    idx[i] = (int)j;
+  }
+}
+
+// Same indices in one pass: the float prefix is the same sequence for every i (it restarts
+// from 0 and adds the same terms in the same order), so "first j with prefix_j > sample" is
+// a search over ONE sequence; a running maximum makes the search monotone even if some
+// weights are negative (first j with prefix_j > x == first j with max_{k<=j} prefix_k > x).
+ORC_API void orc_resample_fast(const float* w, long n, float shift, int M, int* idx, float* prefix_out) {
+  std::vector<float> rmax(n);
+  float run = 0, mx = -std::numeric_limits<float>::infinity();
+  for (long j = 0; j < n; j++) {
+    run += w[j];
+    if (run > mx) mx = run;
+    rmax[j] = mx;
+    if (prefix_out) prefix_out[j] = run;
+  }
+  long j = 0;
+  for (int i = 0; i < M; i++) {
+    float sample = ((float)i + shift) / M;
+    // samples are non-decreasing in i (RN is monotone), so j never moves back
+    while (j < n - 1 && !(rmax[j] > sample)) j++;
+    idx[i] = (int)j;
+  }
+}
+
+// the single uniform draw of :172-173 from a seeded engine (libstdc++ generate_canonical<float,24>)
+ORC_API float orc_uniform_draw(uint32_t seed) {
+  std::mt19937 gen(seed);
+  std::uniform_real_distribution<float> shift_dist(0., 1.);
+  return shift_dist(gen);
+}
+
+// -----------------------------------------------------------------------------
+// a13  pose   src/state_particle.cpp:98-102, src/particle_filter.cpp:191-236
+// -----------------------------------------------------------------------------
+static inline void ml_state(const OrcState& s, float out[4]) {
+  out[0] = s.dx_m * s.scale + s.init_x_px;
+  out[1] = s.dy_m * s.scale + s.init_y_px;
+  out[2] = s.theta;
+  out[3] = s.scale;
+}
+
+ORC_API void orc_mean_likelihood(const OrcState* st, long n, float mean[4]) {
+  float acc[4] = {0, 0, 0, 0}; float cos_sum = 0, sin_sum = 0;
+  for (long i = 0; i < n; i++) {                       // :195-200
+    float s[4]; ml_state(st[i], s);
+    for (int k = 0; k < 4; k++) acc[k] = acc[k] + s[k];
+    cos_sum += cos(s[2]);
+    sin_sum += sin(s[2]);
+  }
+  for (int k = 0; k < 4; k++) mean[k] = acc[k] / (float)(size_t)n;   // :201
+  mean[2] = atan2(sin_sum / (float)(size_t)n, cos_sum / (float)(size_t)n);  // :202
+}
+
+static void cov_about(const OrcState* st, long n, const float ref[4], float cov[16]) {
+  for (int k = 0; k < 16; k++) cov[k] = 0;
+  for (long i = 0; i < n; i++) {
+    float s[4]; ml_state(st[i], s);
+    for (int k = 0; k < 4; k++) s[k] = s[k] - ref[k];
+    while (s[2] > M_PI) s[2] -= 2 * M_PI;              // float compared/updated through double
+    while (s[2] < -M_PI) s[2] += 2 * M_PI;
+    for (int c = 0; c < 4; c++) for (int r = 0; r < 4; r++) cov[c * 4 + r] = cov[c * 4 + r] + s[r] * s[c];
+  }
+  float den = (float)(size_t)(n - 1);
+  for (int k = 0; k < 16; k++) cov[k] = cov[k] / den;  // :219
+}
+
+ORC_API void orc_mean_cov(const OrcState* st, long n, float mean[4], float cov[16]) {   // :205-220
+  orc_mean_likelihood(st, n, mean);
+  cov_about(st, n, mean, cov);
+}
+ORC_API void orc_ml_cov(const OrcState* st, long n, long argmax, float ml[4], float cov[16]) {  // :222-236
+  ml_state(st[argmax], ml);
+  cov_about(st, n, ml, cov);
+}
+
+// -----------------------------------------------------------------------------
+// refine_map-style binning rule (BASELINE cfg5)   src/refine_map.cpp:76-94
+// points (x,y) double-free restatement on floats: ind = floor(pt/res) + (int)(centre/res)
+// counts saturate like the reference's uint8 "+= 1" (wraps mod 256) — kept as wrap.
+// -----------------------------------------------------------------------------
+ORC_API void orc_refine_bin(const float* xy, const int* cls, long n, float res, float cx, float cy,
+                            int width, int height, int C, uint8_t* maps /* C x height x width row-major */) {
+  std::memset(maps, 0, (size_t)C * width * height);
+  for (long i = 0; i < n; i++) {
+    int ix = (int)std::floor((double)xy[2 * i] / res) + (int)(cx / res);
+    int iy = (int)std::floor((double)xy[2 * i + 1] / res) + (int)(cy / res);
+    if (ix < 0 || ix >= width || iy < 0 || iy >= height) continue;
+    if (cls[i] < 0 || cls[i] >= C) continue;
+    maps[(size_t)cls[i] * width * height + (size_t)iy * width + ix] += 1;
+  }
+}
+
+ORC_API int orc_abi_version() { return 1; }
