@@ -1,0 +1,167 @@
+/* =============================================================================
+ * tdr.h — C ABI of libtdr_b200: the B200-native (sm_100a) localization hot path
+ * of KumarRobotics/top_down_renderer.
+ *
+ * This is the drop-in boundary: the reference's TopDownMap / TopDownMapPolar /
+ * ScanRenderer / ScanRendererPolar / ParticleFilter classes keep their
+ * declarations and become thin adapters over these entry points (see
+ * INTEGRATION.md and top_down_renderer_b200/adapters/).  Plain pointers and
+ * sizes only; caller-owned host buffers, library-owned device buffers.
+ *
+ * Conventions
+ *   - every function returns 0 on success, a negative TDR_E* code otherwise;
+ *     tdr_last_error() returns a thread-local message.  No exceptions cross.
+ *   - "col-major rows x cols" = Eigen::ArrayXXf layout, element (r, c) at c*rows + r.
+ *   - one context = one CUDA device + one stream; not re-entrant (the reference
+ *     serialises all calls on the ROS spinner thread under particle_lock_).
+ *   - there is NO CPU fallback: every entry point fails with TDR_ENOGPU when no
+ *     CUDA device is usable.
+ *
+ * reference citations are file:line in the reference checkout.
+ * ========================================================================== */
+#ifndef TDR_H_
+#define TDR_H_
+
+#include <stdint.h>
+
+#ifdef __cplusplus
+extern "C" {
+#endif
+
+#define TDR_ABI_VERSION 1
+#define TDR_MAX_CLASSES 7   /* device pixel = 8 fp32 slots: <=7 class distances + known flag */
+#define TDR_MAX_SHIFTS 128
+
+enum {
+  TDR_OK = 0,
+  TDR_EINVAL = -1,      /* bad argument / shape */
+  TDR_ENOGPU = -2,      /* no usable CUDA device */
+  TDR_ECUDA = -3,       /* CUDA runtime error (message in tdr_last_error) */
+  TDR_ESTATE = -4,      /* call order (e.g. score before a map / table / states exist) */
+  TDR_EUNSUPPORTED = -5
+};
+
+typedef struct tdr_ctx tdr_ctx;
+
+/* State — include/top_down_render/state_particle.h:9-17 (28 bytes, same layout) */
+typedef struct tdr_state {
+  float init_x_px, init_y_px, dx_m, dy_m, theta, scale;
+  uint8_t have_init;
+  uint8_t pad_[3];
+} tdr_state;
+
+/* the FilterParams fields that reach the hot path — state_particle.h:19-38, used at
+ * state_particle.cpp:163-176,212 and :137,139 */
+typedef struct tdr_filter_params {
+  float regularization;
+  int32_t force_on_map;
+  float fixed_scale;
+  float scale_log_min, scale_log_max;
+  int32_t num_classes;
+  float class_weights[16];
+} tdr_filter_params;
+
+/* ---- context ------------------------------------------------------------- */
+int tdr_abi_version(void);
+const char* tdr_last_error(void);
+int tdr_create(tdr_ctx** out, int device);       /* device = CUDA ordinal (LOCAL_RANK) */
+void tdr_destroy(tdr_ctx* ctx);
+int tdr_sync(tdr_ctx* ctx);                      /* cudaStreamSynchronize on the context stream */
+void* tdr_stream(tdr_ctx* ctx);                  /* the cudaStream_t every kernel is launched on */
+int tdr_launch_count(tdr_ctx* ctx, int64_t* n);  /* kernels launched by this context so far */
+
+/* ---- map: TopDownMap / TopDownMapPolar ------------------------------------ */
+/* a3+a4: TopDownMap::updateMap = loadCompressedRasterMap + computeDists
+ * (top_down_map.cpp:116-157, 289-326).  img: row-major uint8 class-index image
+ * (cv::Mat), flatten_lut[n_lut] (index >= n_lut means "no class"). */
+int tdr_map_set_class_image(tdr_ctx* ctx, const uint8_t* img, int h_img, int w_img, int stride,
+                            const int32_t* flatten_lut, int n_lut, int num_classes, float resolution);
+/* a4 alone: computeDists over caller-supplied binary class layers (the svg / raster-cache
+ * constructor path, top_down_map.cpp:56).  layers: C col-major rows x cols, values 0/1. */
+int tdr_map_set_binary_layers(tdr_ctx* ctx, const float* layers, int rows, int cols, int num_classes,
+                              float resolution);
+/* precomputed distance layers + mask (the ~/.ros/xview_cache *.eig path, top_down_map.cpp:244-261) */
+int tdr_map_set_dist_layers(tdr_ctx* ctx, const float* layers, const uint8_t* mask, int rows, int cols,
+                            int num_classes, float resolution);
+/* class_maps_ / class_mask_ as the reference holds them after computeDists (for the .eig cache,
+ * getClassesAtPoint (top_down_map.cpp:159-175) and parity tests).  layers: C col-major rows x cols. */
+int tdr_map_get_layers(tdr_ctx* ctx, float* layers, uint8_t* mask);
+int tdr_map_info(tdr_ctx* ctx, int* rows, int* cols, int* num_classes, float* resolution);
+/* a5: geo layers (getGeoRasterMap + computeDists, top_down_map.cpp:410-427, :58) from the
+ * current binary class seeds; 2 col-major rows x cols layers out.  Interface completeness only. */
+int tdr_map_get_geo_layers(tdr_ctx* ctx, float* geo_layers);
+/* a6: ang_sample_pts_ (top_down_map_polar.cpp:7-19), computed by the caller exactly as the
+ * reference does (Eigen cos/sin) and handed over: tab[2*p+0] -> row offset, tab[2*p+1] -> col offset */
+int tdr_map_set_polar_table(tdr_ctx* ctx, const float* tab2xP, int n_theta, int n_r);
+/* a7: TopDownMapPolar::getLocalMap (top_down_map_polar.cpp:21-53) for n centres.
+ * centers: n x (x, y); dists: n x C x P; mask: n x P */
+int tdr_map_local_polar(tdr_ctx* ctx, const float* centers_xy, int n, float scale, float res, float* dists,
+                        uint8_t* mask);
+/* a8: TopDownMap::getLocalMap (Cartesian, top_down_map.cpp:429-459); dists C x rows x cols col-major */
+int tdr_map_local_cart(tdr_ctx* ctx, float cx, float cy, float rot, float res, int rows, int cols,
+                       float* dists, uint8_t* mask);
+
+/* ---- scan: ScanRenderer / ScanRendererPolar ------------------------------- */
+/* H2D of one scan (pcl::PointCloud<PointXYZI>::points): AoS, x/y at byte 0/4, intensity at
+ * intensity_off (16 for PointXYZI).  The lut is flatten_lut_ (scan_renderer.cpp:3-5). */
+int tdr_scan_set_points(tdr_ctx* ctx, const void* pts, int stride_bytes, int intensity_off, int64_t n);
+int tdr_scan_set_lut(tdr_ctx* ctx, const int32_t* lut, int n_lut, int num_classes);
+/* a1: ScanRendererPolar::renderSemanticTopDown (scan_renderer_polar.cpp:83-109) over the resident
+ * points; the class images stay on the device (input of tdr_pf_score) and, if imgs != NULL, are
+ * copied out: C col-major n_theta x n_r images. */
+int tdr_scan_render_polar(tdr_ctx* ctx, float res, float ang_res, int n_theta, int n_r, float* imgs);
+/* a2: ScanRenderer::renderSemanticTopDown (scan_renderer.cpp:55-78); C col-major rows x cols */
+int tdr_scan_render_cart(tdr_ctx* ctx, float res, int rows, int cols, float* imgs);
+/* upload externally rendered polar class images instead (ParticleFilter::update takes them
+ * as an argument, particle_filter.cpp:94) */
+int tdr_scan_set_polar_images(tdr_ctx* ctx, const float* imgs, int n_theta, int n_r, int num_classes);
+
+/* ---- filter: ParticleFilter / StateParticle -------------------------------- */
+int tdr_pf_set_params(tdr_ctx* ctx, const tdr_filter_params* p);
+/* theta-search candidates (state_particle.cpp:197), generated by the caller with the
+ * reference's own float loop: thetas[k], shifts[k] */
+int tdr_pf_set_search(tdr_ctx* ctx, const float* thetas, const int32_t* shifts, int n);
+int tdr_pf_set_states(tdr_ctx* ctx, const tdr_state* states, const float* last_dist, int64_t n);
+int tdr_pf_get_states(tdr_ctx* ctx, tdr_state* states, int64_t n);
+int tdr_pf_count(tdr_ctx* ctx, int64_t* n);
+/* a9+a10: StateParticle::computeWeight for every particle (the for_each(par) region,
+ * particle_filter.cpp:104-105) against the resident polar scan images.  Updates theta /
+ * have_init on the device like the reference.  weights_out may be NULL. */
+int tdr_pf_score(tdr_ctx* ctx, float res, float* weights_out);
+int tdr_pf_set_weights(tdr_ctx* ctx, const float* weights, int64_t n);   /* stage-wise parity entry */
+int tdr_pf_get_weights(tdr_ctx* ctx, float* weights, int64_t n);
+/* a11: particle_filter.cpp:107-147 on the resident raw weights. stats: sum, num_valid, mean,
+ * bottom_stddev, num_under, fallback (6 floats, may be NULL) */
+int tdr_pf_normalize(tdr_ctx* ctx, int64_t* argmax_out, float* stats);
+/* a12: particle_filter.cpp:172-187 on the resident normalised weights: M outputs, one uniform u.
+ * Gathers the states (new particle i = old particle idx[i]); idx_out may be NULL. */
+int tdr_pf_resample(tdr_ctx* ctx, float u, int64_t M, int32_t* idx_out);
+/* a13: mean / covariance / max-likelihood pose (particle_filter.cpp:191-236).  ml uses the arg-max
+ * of the last tdr_pf_normalize (max_likelihood_particle_, :145-147).  Any pointer may be NULL. */
+int tdr_pf_pose(tdr_ctx* ctx, float mean[4], float cov_mean[16], float ml[4], float cov_ml[16]);
+/* the whole ParticleFilter::update (:94-189) on resident data, asynchronous on the context
+ * stream: score -> normalise -> resample.  Outputs are read with the getters + tdr_sync. */
+int tdr_pf_update(tdr_ctx* ctx, float res, float u, int64_t M);
+/* render (a1) + update, the per-scan step of TopDownRender::takeStep (top_down_render.cpp:505-572)
+ * minus ROS: H2D of the scan is tdr_scan_set_points. */
+int tdr_step(tdr_ctx* ctx, float res, float ang_res, int n_theta, int n_r, float u, int64_t M);
+
+/* exhaustive grid (BASELINE cfg4): getCostForRot at every (centre, shift); costs n x n_shifts.
+ * costs_out (host) may be NULL: results stay resident, see tdr_grid_best. */
+int tdr_grid_costs(tdr_ctx* ctx, const float* centers_xy, int64_t n, float scale, float res,
+                   const int32_t* shifts, int n_shifts, float* costs_out);
+/* (min cost, flat index) over the resident grid costs — what a rank contributes to the
+ * multi-GPU reduction */
+int tdr_grid_best(tdr_ctx* ctx, float* best_cost, int64_t* best_index);
+/* device pointers of resident buffers for collectives issued by the host layer (NCCL through
+ * torch.distributed): weights (n floats) / grid costs (n*n_shifts floats) */
+int tdr_dev_ptr(tdr_ctx* ctx, int which, void** ptr, int64_t* n_elems);
+enum { TDR_BUF_WEIGHTS = 0, TDR_BUF_GRID_COSTS = 1, TDR_BUF_STATES_SOA = 2, TDR_BUF_SCAN_IMAGES = 3 };
+/* replace the resident weights by an externally gathered vector living on the device
+ * (all-gather output), n floats */
+int tdr_pf_set_weights_dev(tdr_ctx* ctx, const void* dev_weights, int64_t n);
+
+#ifdef __cplusplus
+}
+#endif
+#endif /* TDR_H_ */

@@ -1,0 +1,262 @@
+"""numpy-facing wrapper of the C ABI (include/tdr.h): one Context = one tdr_ctx.
+
+Array conventions follow the reference's Eigen types:
+  * class / distance layers: numpy (C, cols, rows) C-contiguous == C column-major rows x cols arrays
+  * polar images: (C, n_r, n_theta) C-contiguous == C column-major n_theta x n_r images
+  * states: structured array of STATE_DTYPE (28-byte State records)
+"""
+from __future__ import annotations
+
+import ctypes as C
+
+import numpy as np
+
+from . import _lib
+from ._lib import TdrFilterParams, check
+
+STATE_DTYPE = np.dtype([("init_x_px", "<f4"), ("init_y_px", "<f4"), ("dx_m", "<f4"), ("dy_m", "<f4"),
+                        ("theta", "<f4"), ("scale", "<f4"), ("have_init", "u1"), ("pad", "u1", (3,))])
+
+_f = C.POINTER(C.c_float)
+_i = C.POINTER(C.c_int32)
+_b = C.POINTER(C.c_uint8)
+
+
+def _pf(a):
+    return a.ctypes.data_as(_f)
+
+
+def _pi(a):
+    return a.ctypes.data_as(_i)
+
+
+def _pb(a):
+    return a.ctypes.data_as(_b)
+
+
+class Context:
+    def __init__(self, device: int = 0):
+        self._lib = _lib.load()
+        h = C.c_void_p()
+        check(self._lib.tdr_create(C.byref(h), int(device)))
+        self._h = h
+        self.device = int(device)
+
+    def close(self):
+        if getattr(self, "_h", None):
+            self._lib.tdr_destroy(self._h)
+            self._h = None
+
+    def __del__(self):
+        try:
+            self.close()
+        except Exception:
+            pass
+
+    # ---- context
+    def sync(self):
+        check(self._lib.tdr_sync(self._h))
+
+    @property
+    def stream(self) -> int:
+        return int(self._lib.tdr_stream(self._h) or 0)
+
+    def launch_count(self) -> int:
+        n = C.c_int64()
+        check(self._lib.tdr_launch_count(self._h, C.byref(n)))
+        return n.value
+
+    # ---- map
+    def map_set_class_image(self, img, flatten_lut, num_classes, resolution=1.0):
+        img = np.ascontiguousarray(img, dtype=np.uint8)
+        lut = np.ascontiguousarray(flatten_lut, dtype=np.int32)
+        check(self._lib.tdr_map_set_class_image(self._h, _pb(img), img.shape[0], img.shape[1], C.c_int(img.strides[0]),
+                                                _pi(lut), len(lut), int(num_classes), C.c_float(resolution)))
+
+    def map_set_binary_layers(self, layers, resolution=1.0):
+        layers = np.ascontiguousarray(layers, dtype=np.float32)
+        c, cols, rows = layers.shape
+        check(self._lib.tdr_map_set_binary_layers(self._h, _pf(layers), rows, cols, c, C.c_float(resolution)))
+
+    def map_set_dist_layers(self, layers, mask, resolution=1.0):
+        layers = np.ascontiguousarray(layers, dtype=np.float32)
+        mask = np.ascontiguousarray(mask, dtype=np.uint8)
+        c, cols, rows = layers.shape
+        check(self._lib.tdr_map_set_dist_layers(self._h, _pf(layers), _pb(mask), rows, cols, c, C.c_float(resolution)))
+
+    def map_info(self):
+        r, c, k, res = C.c_int(), C.c_int(), C.c_int(), C.c_float()
+        check(self._lib.tdr_map_info(self._h, C.byref(r), C.byref(c), C.byref(k), C.byref(res)))
+        return r.value, c.value, k.value, res.value
+
+    def map_get_layers(self):
+        rows, cols, k, _ = self.map_info()
+        layers = np.empty((k, cols, rows), dtype=np.float32)
+        mask = np.empty((cols, rows), dtype=np.uint8)
+        check(self._lib.tdr_map_get_layers(self._h, _pf(layers), _pb(mask)))
+        return layers, mask
+
+    def map_get_geo_layers(self):
+        rows, cols, _, _ = self.map_info()
+        geo = np.empty((2, cols, rows), dtype=np.float32)
+        check(self._lib.tdr_map_get_geo_layers(self._h, _pf(geo)))
+        return geo
+
+    def map_set_polar_table(self, tab, n_theta, n_r):
+        tab = np.ascontiguousarray(tab, dtype=np.float32)
+        assert tab.size == 2 * n_theta * n_r
+        check(self._lib.tdr_map_set_polar_table(self._h, _pf(tab), int(n_theta), int(n_r)))
+        self._P = n_theta * n_r
+
+    def map_local_polar(self, centers_xy, scale, res):
+        centers = np.ascontiguousarray(centers_xy, dtype=np.float32).reshape(-1, 2)
+        n = centers.shape[0]
+        _, _, k, _ = self.map_info()
+        d = np.empty((n, k, self._P), dtype=np.float32)
+        m = np.empty((n, self._P), dtype=np.uint8)
+        check(self._lib.tdr_map_local_polar(self._h, _pf(centers), n, C.c_float(scale), C.c_float(res), _pf(d), _pb(m)))
+        return d, m
+
+    def map_local_cart(self, cx, cy, rot, res, rows, cols):
+        _, _, k, _ = self.map_info()
+        d = np.empty((k, rows * cols), dtype=np.float32)
+        m = np.empty((rows * cols,), dtype=np.uint8)
+        check(self._lib.tdr_map_local_cart(self._h, C.c_float(cx), C.c_float(cy), C.c_float(rot), C.c_float(res),
+                                           int(rows), int(cols), _pf(d), _pb(m)))
+        return d, m
+
+    # ---- scan
+    def scan_set_points(self, pts, intensity_off=16):
+        """pts: (n, k) float32 AoS (PointXYZI: k = 8).  Asynchronous: keep `pts` alive until sync()."""
+        assert pts.dtype == np.float32 and pts.flags.c_contiguous
+        self._pts_keepalive = pts
+        check(self._lib.tdr_scan_set_points(self._h, C.c_void_p(pts.ctypes.data), C.c_int(pts.strides[0]),
+                                            C.c_int(intensity_off), C.c_int64(pts.shape[0])))
+
+    def scan_set_points_ptr(self, ptr, stride, intensity_off, n):
+        check(self._lib.tdr_scan_set_points(self._h, C.c_void_p(ptr), C.c_int(stride), C.c_int(intensity_off), C.c_int64(n)))
+
+    def scan_set_lut(self, lut, num_classes):
+        lut = np.ascontiguousarray(lut, dtype=np.int32)
+        check(self._lib.tdr_scan_set_lut(self._h, _pi(lut), len(lut), int(num_classes)))
+        self._scan_C = int(num_classes)
+
+    def scan_render_polar(self, res, ang_res, n_theta, n_r, want=True):
+        out = np.empty((self._scan_C, n_r, n_theta), dtype=np.float32) if want else None
+        check(self._lib.tdr_scan_render_polar(self._h, C.c_float(res), C.c_float(ang_res), int(n_theta), int(n_r),
+                                              _pf(out) if want else None))
+        return out
+
+    def scan_render_cart(self, res, rows, cols):
+        out = np.empty((self._scan_C, cols, rows), dtype=np.float32)
+        check(self._lib.tdr_scan_render_cart(self._h, C.c_float(res), int(rows), int(cols), _pf(out)))
+        return out
+
+    def scan_set_polar_images(self, imgs):
+        imgs = np.ascontiguousarray(imgs, dtype=np.float32)
+        c, n_r, n_theta = imgs.shape
+        check(self._lib.tdr_scan_set_polar_images(self._h, _pf(imgs), n_theta, n_r, c))
+
+    # ---- filter
+    def pf_set_params(self, num_classes, regularization=0.7, class_weights=None, force_on_map=False, fixed_scale=2.0,
+                      scale_log_min=-0.1, scale_log_max=1.0):
+        p = TdrFilterParams()
+        p.regularization = regularization
+        p.force_on_map = int(bool(force_on_map))
+        p.fixed_scale = fixed_scale
+        p.scale_log_min = scale_log_min
+        p.scale_log_max = scale_log_max
+        p.num_classes = int(num_classes)
+        cw = list(class_weights) if class_weights is not None else [1.0] * num_classes
+        for k, v in enumerate(cw):
+            p.class_weights[k] = v
+        check(self._lib.tdr_pf_set_params(self._h, C.byref(p)))
+
+    def pf_set_search(self, thetas, shifts):
+        th = np.ascontiguousarray(thetas, dtype=np.float32)
+        sh = np.ascontiguousarray(shifts, dtype=np.int32)
+        check(self._lib.tdr_pf_set_search(self._h, _pf(th), _pi(sh), len(sh)))
+
+    def pf_set_states(self, states, last_dist=None):
+        assert states.dtype == STATE_DTYPE
+        states = np.ascontiguousarray(states)
+        ld = np.ascontiguousarray(last_dist, dtype=np.float32) if last_dist is not None else None
+        check(self._lib.tdr_pf_set_states(self._h, C.c_void_p(states.ctypes.data), _pf(ld) if ld is not None else None,
+                                          C.c_int64(len(states))))
+
+    def pf_count(self):
+        n = C.c_int64()
+        check(self._lib.tdr_pf_count(self._h, C.byref(n)))
+        return n.value
+
+    def pf_get_states(self, n=None):
+        n = self.pf_count() if n is None else n
+        st = np.zeros(n, dtype=STATE_DTYPE)
+        check(self._lib.tdr_pf_get_states(self._h, C.c_void_p(st.ctypes.data), C.c_int64(n)))
+        return st
+
+    def pf_score(self, res, want=True):
+        n = self.pf_count()
+        w = np.empty(n, dtype=np.float32) if want else None
+        check(self._lib.tdr_pf_score(self._h, C.c_float(res), _pf(w) if want else None))
+        return w
+
+    def pf_set_weights(self, w):
+        w = np.ascontiguousarray(w, dtype=np.float32)
+        check(self._lib.tdr_pf_set_weights(self._h, _pf(w), C.c_int64(len(w))))
+
+    def pf_get_weights(self, n):
+        w = np.empty(n, dtype=np.float32)
+        check(self._lib.tdr_pf_get_weights(self._h, _pf(w), C.c_int64(n)))
+        return w
+
+    def pf_normalize(self):
+        arg = C.c_int64()
+        stats = np.zeros(6, dtype=np.float32)
+        check(self._lib.tdr_pf_normalize(self._h, C.byref(arg), _pf(stats)))
+        return arg.value, stats
+
+    def pf_resample(self, u, M, want=True):
+        idx = np.empty(M, dtype=np.int32) if want else None
+        check(self._lib.tdr_pf_resample(self._h, C.c_float(u), C.c_int64(M), _pi(idx) if want else None))
+        return idx
+
+    def pf_pose(self, want_ml=True):
+        mean = np.zeros(4, dtype=np.float32)
+        cov = np.zeros(16, dtype=np.float32)
+        ml = np.zeros(4, dtype=np.float32)
+        cov_ml = np.zeros(16, dtype=np.float32)
+        check(self._lib.tdr_pf_pose(self._h, _pf(mean), _pf(cov), _pf(ml) if want_ml else None,
+                                    _pf(cov_ml) if want_ml else None))
+        return mean, cov.reshape(4, 4), ml, cov_ml.reshape(4, 4)
+
+    def pf_update(self, res, u, M):
+        check(self._lib.tdr_pf_update(self._h, C.c_float(res), C.c_float(u), C.c_int64(M)))
+
+    def step(self, res, ang_res, n_theta, n_r, u, M):
+        check(self._lib.tdr_step(self._h, C.c_float(res), C.c_float(ang_res), int(n_theta), int(n_r), C.c_float(u),
+                                 C.c_int64(M)))
+
+    # ---- grid
+    def grid_costs(self, centers_xy, scale, res, shifts, want=True):
+        centers = np.ascontiguousarray(centers_xy, dtype=np.float32).reshape(-1, 2)
+        sh = np.ascontiguousarray(shifts, dtype=np.int32)
+        out = np.empty((centers.shape[0], len(sh)), dtype=np.float32) if want else None
+        check(self._lib.tdr_grid_costs(self._h, _pf(centers), C.c_int64(centers.shape[0]), C.c_float(scale),
+                                       C.c_float(res), _pi(sh), len(sh), _pf(out) if want else None))
+        return out
+
+    def grid_best(self):
+        c = C.c_float()
+        i = C.c_int64()
+        check(self._lib.tdr_grid_best(self._h, C.byref(c), C.byref(i)))
+        return c.value, i.value
+
+    def dev_ptr(self, which):
+        p = C.c_void_p()
+        n = C.c_int64()
+        check(self._lib.tdr_dev_ptr(self._h, int(which), C.byref(p), C.byref(n)))
+        return (p.value or 0), n.value
+
+    def pf_set_weights_dev(self, ptr, n):
+        check(self._lib.tdr_pf_set_weights_dev(self._h, C.c_void_p(ptr), C.c_int64(n)))

@@ -1,0 +1,452 @@
+// api.cu — the extern "C" surface declared in include/tdr.h.
+#include <stdarg.h>
+#include <string.h>
+
+#include "tdr_ctx.cuh"
+#include "tdr_math.cuh"
+
+namespace tdr {
+
+static thread_local char g_err[512] = "";
+void set_error(const char* fmt, ...) {
+  va_list ap; va_start(ap, fmt);
+  vsnprintf(g_err, sizeof(g_err), fmt, ap);
+  va_end(ap);
+}
+
+int Particles::reserve(int64_t cap) {
+  size_t b = (size_t)cap * 4;
+  if (int e = init_x.reserve(b)) return e;
+  if (int e = init_y.reserve(b)) return e;
+  if (int e = dx.reserve(b)) return e;
+  if (int e = dy.reserve(b)) return e;
+  if (int e = theta.reserve(b)) return e;
+  if (int e = scale.reserve(b)) return e;
+  if (int e = last_dist.reserve(b)) return e;
+  if (int e = have_init.reserve((size_t)cap)) return e;
+  return TDR_OK;
+}
+void Particles::release() {
+  init_x.release(); init_y.release(); dx.release(); dy.release(); theta.release(); scale.release();
+  last_dist.release(); have_init.release(); n = 0;
+}
+
+struct SoA { float *ix, *iy, *dx, *dy, *th, *sc; uint8_t* hi; };
+static SoA soa_of(Particles& p) {
+  SoA s; s.ix = p.init_x.as<float>(); s.iy = p.init_y.as<float>(); s.dx = p.dx.as<float>(); s.dy = p.dy.as<float>();
+  s.th = p.theta.as<float>(); s.sc = p.scale.as<float>(); s.hi = p.have_init.as<uint8_t>();
+  return s;
+}
+
+// 28-byte State records <-> SoA (7 words per record; have_init is byte 24)
+__global__ void k_aos_to_soa(const uint32_t* __restrict__ aos, long long n, SoA s) {
+  for (long long i = (long long)blockIdx.x * blockDim.x + threadIdx.x; i < n; i += (long long)gridDim.x * blockDim.x) {
+    const uint32_t* r = aos + i * 7;
+    s.ix[i] = __uint_as_float(r[0]); s.iy[i] = __uint_as_float(r[1]); s.dx[i] = __uint_as_float(r[2]);
+    s.dy[i] = __uint_as_float(r[3]); s.th[i] = __uint_as_float(r[4]); s.sc[i] = __uint_as_float(r[5]);
+    s.hi[i] = (uint8_t)((r[6] & 0xffu) ? 1 : 0);
+  }
+}
+__global__ void k_soa_to_aos(SoA s, long long n, uint32_t* __restrict__ aos) {
+  for (long long i = (long long)blockIdx.x * blockDim.x + threadIdx.x; i < n; i += (long long)gridDim.x * blockDim.x) {
+    uint32_t* r = aos + i * 7;
+    r[0] = __float_as_uint(s.ix[i]); r[1] = __float_as_uint(s.iy[i]); r[2] = __float_as_uint(s.dx[i]);
+    r[3] = __float_as_uint(s.dy[i]); r[4] = __float_as_uint(s.th[i]); r[5] = __float_as_uint(s.sc[i]);
+    r[6] = s.hi[i] ? 1u : 0u;
+  }
+}
+
+static int grid_for(tdr_ctx* ctx, long long n, int threads = 256) {
+  long long b = (n + threads - 1) / threads;
+  long long cap = (long long)ctx->sm_count * 8;
+  return (int)(b < cap ? (b < 1 ? 1 : b) : cap);
+}
+
+}  // namespace tdr
+
+using namespace tdr;
+
+#define CTX_CHECK(ctx)                                                           \
+  do {                                                                           \
+    if (!(ctx)) { tdr::set_error("null context"); return TDR_EINVAL; }           \
+    cudaError_t e__ = cudaSetDevice((ctx)->device);                              \
+    if (e__ != cudaSuccess) { tdr::set_error("cudaSetDevice: %s", cudaGetErrorString(e__)); return TDR_ECUDA; } \
+  } while (0)
+
+extern "C" {
+
+int tdr_abi_version(void) { return TDR_ABI_VERSION; }
+const char* tdr_last_error(void) { return tdr::g_err; }
+
+int tdr_create(tdr_ctx** out, int device) {
+  TDR_REQUIRE(out, TDR_EINVAL, "null out pointer");
+  *out = nullptr;
+  int count = 0;
+  cudaError_t e = cudaGetDeviceCount(&count);
+  if (e != cudaSuccess || count <= 0) {
+    tdr::set_error("no usable CUDA device (%s); libtdr_b200 has no CPU fallback",
+                   e != cudaSuccess ? cudaGetErrorString(e) : "device count 0");
+    return TDR_ENOGPU;
+  }
+  TDR_REQUIRE(device >= 0 && device < count, TDR_EINVAL, "device %d out of range (%d devices)", device, count);
+  TDR_CUDA(cudaSetDevice(device));
+  tdr_ctx* c = new tdr_ctx();
+  c->device = device;
+  cudaDeviceProp prop;
+  TDR_CUDA(cudaGetDeviceProperties(&prop, device));
+  c->sm_count = prop.multiProcessorCount;
+  if (prop.major < 10) {
+    tdr::set_error("device %d is sm_%d%d; this library is built for sm_100a only", device, prop.major, prop.minor);
+    delete c;
+    return TDR_ENOGPU;
+  }
+  TDR_CUDA(cudaStreamCreateWithFlags(&c->stream, cudaStreamNonBlocking));
+  if (int r = c->scal.reserve(SC_TOTAL * 4)) { delete c; return r; }
+  TDR_CUDA(cudaMemsetAsync(c->scal.p, 0, SC_TOTAL * 4, c->stream));
+  if (int r = c->d_cw.reserve(64)) { delete c; return r; }
+  *out = c;
+  return TDR_OK;
+}
+
+void tdr_destroy(tdr_ctx* c) {
+  if (!c) return;
+  cudaSetDevice(c->device);
+  if (c->stream) { cudaStreamSynchronize(c->stream); }
+  tdr::DevBuf* bufs[] = {&c->map_px, &c->seedbits, &c->edt_g, &c->scratch, &c->scratch2, &c->tab, &c->pts, &c->lut,
+                         &c->scan_img, &c->scan_pack, &c->hist, &c->d_search_thetas, &c->d_search_shifts, &c->weights,
+                         &c->prefix, &c->idx, &c->scal, &c->pose_tmp, &c->grid_centers, &c->grid_costs,
+                         &c->grid_shifts, &c->d_cw};
+  for (auto* b : bufs) b->release();
+  c->part[0].release(); c->part[1].release();
+  c->pin.release();
+  if (c->stream) cudaStreamDestroy(c->stream);
+  delete c;
+}
+
+int tdr_sync(tdr_ctx* ctx) { CTX_CHECK(ctx); TDR_CUDA(cudaStreamSynchronize(ctx->stream)); return TDR_OK; }
+void* tdr_stream(tdr_ctx* ctx) { return ctx ? (void*)ctx->stream : nullptr; }
+int tdr_launch_count(tdr_ctx* ctx, int64_t* n) { TDR_REQUIRE(ctx && n, TDR_EINVAL, "null argument"); *n = ctx->launches; return TDR_OK; }
+
+// ---- map ------------------------------------------------------------------------------------------
+int tdr_map_set_class_image(tdr_ctx* ctx, const uint8_t* img, int h_img, int w_img, int stride,
+                            const int32_t* flatten_lut, int n_lut, int num_classes, float resolution) {
+  CTX_CHECK(ctx);
+  return map_set_class_image(ctx, img, h_img, w_img, stride, flatten_lut, n_lut, num_classes, resolution);
+}
+int tdr_map_set_binary_layers(tdr_ctx* ctx, const float* layers, int rows, int cols, int num_classes, float resolution) {
+  CTX_CHECK(ctx);
+  return map_set_binary_layers(ctx, layers, rows, cols, num_classes, resolution);
+}
+int tdr_map_set_dist_layers(tdr_ctx* ctx, const float* layers, const uint8_t* mask, int rows, int cols, int num_classes,
+                            float resolution) {
+  CTX_CHECK(ctx);
+  return map_set_dist_layers(ctx, layers, mask, rows, cols, num_classes, resolution);
+}
+int tdr_map_get_layers(tdr_ctx* ctx, float* layers, uint8_t* mask) { CTX_CHECK(ctx); return map_get_layers(ctx, layers, mask); }
+int tdr_map_get_geo_layers(tdr_ctx* ctx, float* geo) { CTX_CHECK(ctx); return map_get_geo_layers(ctx, geo); }
+int tdr_map_info(tdr_ctx* ctx, int* rows, int* cols, int* num_classes, float* resolution) {
+  TDR_REQUIRE(ctx, TDR_EINVAL, "null context");
+  TDR_REQUIRE(ctx->have_map, TDR_ESTATE, "no map");
+  if (rows) *rows = ctx->rows;
+  if (cols) *cols = ctx->cols;
+  if (num_classes) *num_classes = ctx->C;
+  if (resolution) *resolution = ctx->resolution;
+  return TDR_OK;
+}
+
+int tdr_map_set_polar_table(tdr_ctx* ctx, const float* tab, int n_theta, int n_r) {
+  CTX_CHECK(ctx);
+  TDR_REQUIRE(tab && n_theta > 0 && n_r > 0, TDR_EINVAL, "bad polar table");
+  TDR_REQUIRE((long long)n_theta * n_r <= 65535 && n_theta <= 65535, TDR_EUNSUPPORTED, "polar table too large");
+  size_t bytes = (size_t)n_theta * n_r * 2 * 4;
+  if (int e = ctx->tab.reserve(bytes)) return e;
+  TDR_CUDA(cudaMemcpyAsync(ctx->tab.p, tab, bytes, cudaMemcpyHostToDevice, ctx->stream));
+  TDR_CUDA(cudaStreamSynchronize(ctx->stream));
+  ctx->n_theta = n_theta; ctx->n_r = n_r; ctx->have_tab = true;
+  return TDR_OK;
+}
+
+int tdr_map_local_polar(tdr_ctx* ctx, const float* centers_xy, int n, float scale, float res, float* dists, uint8_t* mask) {
+  CTX_CHECK(ctx);
+  TDR_REQUIRE(ctx->have_map && ctx->have_tab, TDR_ESTATE, "map / polar table missing");
+  TDR_REQUIRE(centers_xy && n > 0 && n <= 65535 && dists && mask, TDR_EINVAL, "bad arguments");
+  const int P = ctx->n_theta * ctx->n_r;
+  size_t db = (size_t)n * ctx->C * P * 4, mb = (size_t)n * P;
+  if (int e = ctx->scratch.reserve(db + mb + 256)) return e;
+  if (int e = ctx->scratch2.reserve((size_t)n * 8)) return e;
+  TDR_CUDA(cudaMemcpyAsync(ctx->scratch2.p, centers_xy, (size_t)n * 8, cudaMemcpyHostToDevice, ctx->stream));
+  float* dd = ctx->scratch.as<float>();
+  uint8_t* dm = ctx->scratch.as<uint8_t>() + db;
+  if (int e = local_polar(ctx, ctx->scratch2.as<float>(), n, scale, res, dd, dm)) return e;
+  TDR_CUDA(cudaMemcpyAsync(dists, dd, db, cudaMemcpyDeviceToHost, ctx->stream));
+  TDR_CUDA(cudaMemcpyAsync(mask, dm, mb, cudaMemcpyDeviceToHost, ctx->stream));
+  TDR_CUDA(cudaStreamSynchronize(ctx->stream));
+  return TDR_OK;
+}
+
+int tdr_map_local_cart(tdr_ctx* ctx, float cx, float cy, float rot, float res, int rows, int cols, float* dists, uint8_t* mask) {
+  CTX_CHECK(ctx);
+  TDR_REQUIRE(ctx->have_map, TDR_ESTATE, "no map");
+  TDR_REQUIRE(rows > 0 && cols > 0 && dists && mask, TDR_EINVAL, "bad arguments");
+  const size_t P = (size_t)rows * cols;
+  size_t db = P * ctx->C * 4;
+  if (int e = ctx->scratch.reserve(db + P + 256)) return e;
+  float* dd = ctx->scratch.as<float>();
+  uint8_t* dm = ctx->scratch.as<uint8_t>() + db;
+  if (int e = local_cart(ctx, cx, cy, rot, res, rows, cols, dd, dm)) return e;
+  TDR_CUDA(cudaMemcpyAsync(dists, dd, db, cudaMemcpyDeviceToHost, ctx->stream));
+  TDR_CUDA(cudaMemcpyAsync(mask, dm, P, cudaMemcpyDeviceToHost, ctx->stream));
+  TDR_CUDA(cudaStreamSynchronize(ctx->stream));
+  return TDR_OK;
+}
+
+// ---- scan -----------------------------------------------------------------------------------------
+int tdr_scan_set_points(tdr_ctx* ctx, const void* pts, int stride_bytes, int intensity_off, int64_t n) {
+  CTX_CHECK(ctx);
+  TDR_REQUIRE(n >= 0 && (n == 0 || pts), TDR_EINVAL, "null points");
+  TDR_REQUIRE(stride_bytes >= 8 && stride_bytes % 4 == 0 && intensity_off % 4 == 0 && intensity_off >= 0 &&
+                  intensity_off + 4 <= stride_bytes, TDR_EINVAL, "bad point layout (stride %d, intensity offset %d)", stride_bytes, intensity_off);
+  size_t bytes = (size_t)n * stride_bytes;
+  if (int e = ctx->pts.reserve(bytes + 16)) return e;
+  if (n) TDR_CUDA(cudaMemcpyAsync(ctx->pts.p, pts, bytes, cudaMemcpyHostToDevice, ctx->stream));
+  ctx->pts_stride = stride_bytes; ctx->pts_ioff = intensity_off; ctx->n_pts = n;
+  return TDR_OK;   // asynchronous: the caller keeps `pts` alive until the next tdr_sync (pinned memory recommended)
+}
+
+int tdr_scan_set_lut(tdr_ctx* ctx, const int32_t* lut, int n_lut, int num_classes) {
+  CTX_CHECK(ctx);
+  TDR_REQUIRE(lut && n_lut > 0 && num_classes >= 1 && num_classes <= TDR_MAX_CLASSES, TDR_EINVAL, "bad lut");
+  if (int e = ctx->lut.reserve((size_t)n_lut * 4)) return e;
+  TDR_CUDA(cudaMemcpyAsync(ctx->lut.p, lut, (size_t)n_lut * 4, cudaMemcpyHostToDevice, ctx->stream));
+  TDR_CUDA(cudaStreamSynchronize(ctx->stream));
+  ctx->n_lut = n_lut; ctx->lut_classes = num_classes;
+  return TDR_OK;
+}
+
+static int render_polar_resident(tdr_ctx* ctx, float res, float ang_res, int n_theta, int n_r) {
+  const int C = ctx->lut_classes;
+  if (int e = ctx->scan_img.reserve((size_t)C * n_theta * n_r * 4)) return e;
+  if (int e = scan_render(ctx, true, res, ang_res, n_theta, n_r, ctx->scan_img.as<float>())) return e;
+  ctx->scan_theta = n_theta; ctx->scan_r = n_r; ctx->scan_C = C; ctx->have_scan = true;
+  return TDR_OK;
+}
+
+int tdr_scan_render_polar(tdr_ctx* ctx, float res, float ang_res, int n_theta, int n_r, float* imgs) {
+  CTX_CHECK(ctx);
+  if (int e = render_polar_resident(ctx, res, ang_res, n_theta, n_r)) return e;
+  if (imgs) {
+    TDR_CUDA(cudaMemcpyAsync(imgs, ctx->scan_img.p, (size_t)ctx->scan_C * n_theta * n_r * 4, cudaMemcpyDeviceToHost, ctx->stream));
+    TDR_CUDA(cudaStreamSynchronize(ctx->stream));
+  }
+  return TDR_OK;
+}
+
+int tdr_scan_render_cart(tdr_ctx* ctx, float res, int rows, int cols, float* imgs) {
+  CTX_CHECK(ctx);
+  TDR_REQUIRE(imgs, TDR_EINVAL, "null output");
+  const int C = ctx->lut_classes;
+  size_t bytes = (size_t)C * rows * cols * 4;
+  if (int e = ctx->scratch2.reserve(bytes)) return e;
+  if (int e = scan_render(ctx, false, res, 0.f, rows, cols, ctx->scratch2.as<float>())) return e;
+  TDR_CUDA(cudaMemcpyAsync(imgs, ctx->scratch2.p, bytes, cudaMemcpyDeviceToHost, ctx->stream));
+  TDR_CUDA(cudaStreamSynchronize(ctx->stream));
+  return TDR_OK;
+}
+
+int tdr_scan_set_polar_images(tdr_ctx* ctx, const float* imgs, int n_theta, int n_r, int num_classes) {
+  CTX_CHECK(ctx);
+  TDR_REQUIRE(imgs && n_theta > 0 && n_r > 0 && num_classes >= 1 && num_classes <= TDR_MAX_CLASSES, TDR_EINVAL, "bad images");
+  size_t bytes = (size_t)num_classes * n_theta * n_r * 4;
+  if (int e = ctx->scan_img.reserve(bytes)) return e;
+  TDR_CUDA(cudaMemcpyAsync(ctx->scan_img.p, imgs, bytes, cudaMemcpyHostToDevice, ctx->stream));
+  TDR_CUDA(cudaStreamSynchronize(ctx->stream));
+  ctx->scan_theta = n_theta; ctx->scan_r = n_r; ctx->scan_C = num_classes; ctx->have_scan = true;
+  return TDR_OK;
+}
+
+// ---- filter ---------------------------------------------------------------------------------------
+int tdr_pf_set_params(tdr_ctx* ctx, const tdr_filter_params* p) {
+  CTX_CHECK(ctx);
+  TDR_REQUIRE(p && p->num_classes >= 1 && p->num_classes <= TDR_MAX_CLASSES, TDR_EINVAL, "bad filter params");
+  ctx->fp = *p;
+  TDR_CUDA(cudaMemcpyAsync(ctx->d_cw.p, ctx->fp.class_weights, 64, cudaMemcpyHostToDevice, ctx->stream));
+  TDR_CUDA(cudaStreamSynchronize(ctx->stream));
+  ctx->have_params = true;
+  return TDR_OK;
+}
+
+int tdr_pf_set_search(tdr_ctx* ctx, const float* thetas, const int32_t* shifts, int n) {
+  CTX_CHECK(ctx);
+  TDR_REQUIRE(thetas && shifts && n > 0 && n <= TDR_MAX_SHIFTS, TDR_EINVAL, "bad search list");
+  ctx->search_thetas.assign(thetas, thetas + n);
+  ctx->search_shifts.assign(shifts, shifts + n);
+  if (int e = ctx->d_search_thetas.reserve((size_t)n * 4)) return e;
+  if (int e = ctx->d_search_shifts.reserve((size_t)n * 4)) return e;
+  TDR_CUDA(cudaMemcpyAsync(ctx->d_search_thetas.p, thetas, (size_t)n * 4, cudaMemcpyHostToDevice, ctx->stream));
+  TDR_CUDA(cudaMemcpyAsync(ctx->d_search_shifts.p, shifts, (size_t)n * 4, cudaMemcpyHostToDevice, ctx->stream));
+  TDR_CUDA(cudaStreamSynchronize(ctx->stream));
+  return TDR_OK;
+}
+
+int tdr_pf_set_states(tdr_ctx* ctx, const tdr_state* states, const float* last_dist, int64_t n) {
+  CTX_CHECK(ctx);
+  TDR_REQUIRE(states && n > 0 && n < (1ll << 31), TDR_EINVAL, "bad states");
+  static_assert(sizeof(tdr_state) == 28, "State must be 28 bytes");
+  Particles& pt = ctx->part[ctx->cur];
+  if (int e = pt.reserve(n)) return e;
+  if (int e = ctx->scratch.reserve((size_t)n * 28)) return e;
+  TDR_CUDA(cudaMemcpyAsync(ctx->scratch.p, states, (size_t)n * 28, cudaMemcpyHostToDevice, ctx->stream));
+  k_aos_to_soa<<<grid_for(ctx, n), 256, 0, ctx->stream>>>(ctx->scratch.as<uint32_t>(), n, soa_of(pt));
+  count_launch(ctx);
+  TDR_CUDA(cudaGetLastError());
+  if (last_dist) TDR_CUDA(cudaMemcpyAsync(pt.last_dist.p, last_dist, (size_t)n * 4, cudaMemcpyHostToDevice, ctx->stream));
+  else TDR_CUDA(cudaMemsetAsync(pt.last_dist.p, 0, (size_t)n * 4, ctx->stream));
+  TDR_CUDA(cudaStreamSynchronize(ctx->stream));
+  int64_t un = 0;
+  for (int64_t i = 0; i < n; i++) un += states[i].have_init ? 0 : 1;
+  pt.n = n; ctx->n_uninit = un; ctx->have_argmax = false;
+  return TDR_OK;
+}
+
+int tdr_pf_get_states(tdr_ctx* ctx, tdr_state* states, int64_t n) {
+  CTX_CHECK(ctx);
+  Particles& pt = ctx->part[ctx->cur];
+  TDR_REQUIRE(states && n > 0 && n <= pt.n, TDR_EINVAL, "bad state count %lld (have %lld)", (long long)n, (long long)pt.n);
+  if (int e = ctx->scratch.reserve((size_t)n * 28)) return e;
+  k_soa_to_aos<<<grid_for(ctx, n), 256, 0, ctx->stream>>>(soa_of(pt), n, ctx->scratch.as<uint32_t>());
+  count_launch(ctx);
+  TDR_CUDA(cudaGetLastError());
+  TDR_CUDA(cudaMemcpyAsync(states, ctx->scratch.p, (size_t)n * 28, cudaMemcpyDeviceToHost, ctx->stream));
+  TDR_CUDA(cudaStreamSynchronize(ctx->stream));
+  return TDR_OK;
+}
+
+int tdr_pf_count(tdr_ctx* ctx, int64_t* n) { TDR_REQUIRE(ctx && n, TDR_EINVAL, "null argument"); *n = ctx->part[ctx->cur].n; return TDR_OK; }
+
+static int copy_out_floats(tdr_ctx* ctx, float* dst, const void* src, int64_t n) {
+  TDR_CUDA(cudaMemcpyAsync(dst, src, (size_t)n * 4, cudaMemcpyDeviceToHost, ctx->stream));
+  TDR_CUDA(cudaStreamSynchronize(ctx->stream));
+  return TDR_OK;
+}
+
+int tdr_pf_score(tdr_ctx* ctx, float res, float* weights_out) {
+  CTX_CHECK(ctx);
+  if (int e = scan_pack(ctx)) return e;
+  if (int e = score_particles(ctx, res)) return e;
+  ctx->ld_override = nullptr;
+  if (weights_out) return copy_out_floats(ctx, weights_out, ctx->weights.p, ctx->n_weights);
+  return TDR_OK;
+}
+
+int tdr_pf_set_weights(tdr_ctx* ctx, const float* weights, int64_t n) {
+  CTX_CHECK(ctx);
+  TDR_REQUIRE(weights && n > 0, TDR_EINVAL, "bad weights");
+  if (int e = ctx->weights.reserve((size_t)n * 4)) return e;
+  TDR_CUDA(cudaMemcpyAsync(ctx->weights.p, weights, (size_t)n * 4, cudaMemcpyHostToDevice, ctx->stream));
+  TDR_CUDA(cudaStreamSynchronize(ctx->stream));
+  ctx->n_weights = n;
+  return TDR_OK;
+}
+
+int tdr_pf_set_weights_dev(tdr_ctx* ctx, const void* dev_weights, int64_t n) {
+  CTX_CHECK(ctx);
+  TDR_REQUIRE(dev_weights && n > 0, TDR_EINVAL, "bad weights");
+  if (int e = ctx->weights.reserve((size_t)n * 4)) return e;
+  TDR_CUDA(cudaMemcpyAsync(ctx->weights.p, dev_weights, (size_t)n * 4, cudaMemcpyDeviceToDevice, ctx->stream));
+  ctx->n_weights = n;
+  return TDR_OK;
+}
+
+int tdr_pf_get_weights(tdr_ctx* ctx, float* weights, int64_t n) {
+  CTX_CHECK(ctx);
+  TDR_REQUIRE(weights && n > 0 && n <= ctx->n_weights, TDR_EINVAL, "bad weight count");
+  return copy_out_floats(ctx, weights, ctx->weights.p, n);
+}
+
+int tdr_pf_normalize(tdr_ctx* ctx, int64_t* argmax_out, float* stats) {
+  CTX_CHECK(ctx);
+  TDR_REQUIRE(ctx->ld_override || ctx->n_weights == ctx->part[ctx->cur].n, TDR_ESTATE,
+              "weights (%lld) and particles (%lld) differ", (long long)ctx->n_weights, (long long)ctx->part[ctx->cur].n);
+  if (int e = normalize(ctx)) return e;
+  ctx->argmax_buf = ctx->cur;
+  if (argmax_out || stats) {
+    float host[16];
+    TDR_CUDA(cudaMemcpyAsync(host, ctx->scal.p, 16 * 4, cudaMemcpyDeviceToHost, ctx->stream));
+    TDR_CUDA(cudaStreamSynchronize(ctx->stream));
+    int a; memcpy(&a, &host[SC_ARGMAX], 4);
+    ctx->argmax = a;
+    if (argmax_out) *argmax_out = a;
+    if (stats) for (int k = 0; k < 6; k++) stats[k] = host[k];
+  }
+  return TDR_OK;
+}
+
+int tdr_pf_resample(tdr_ctx* ctx, float u, int64_t M, int32_t* idx_out) {
+  CTX_CHECK(ctx);
+  if (int e = resample(ctx, u, M, 0, M, true)) return e;
+  if (idx_out) {
+    TDR_CUDA(cudaMemcpyAsync(idx_out, ctx->idx.p, (size_t)M * 4, cudaMemcpyDeviceToHost, ctx->stream));
+    TDR_CUDA(cudaStreamSynchronize(ctx->stream));
+  }
+  return TDR_OK;
+}
+
+int tdr_pf_pose(tdr_ctx* ctx, float mean[4], float cov_mean[16], float ml[4], float cov_ml[16]) {
+  CTX_CHECK(ctx);
+  return pose(ctx, mean, cov_mean, ml, cov_ml);
+}
+
+int tdr_pf_update(tdr_ctx* ctx, float res, float u, int64_t M) {
+  CTX_CHECK(ctx);
+  if (int e = scan_pack(ctx)) return e;
+  if (int e = score_particles(ctx, res)) return e;
+  ctx->ld_override = nullptr;
+  if (int e = normalize(ctx)) return e;
+  ctx->argmax_buf = ctx->cur;
+  return resample(ctx, u, M, 0, M, true);
+}
+
+int tdr_step(tdr_ctx* ctx, float res, float ang_res, int n_theta, int n_r, float u, int64_t M) {
+  CTX_CHECK(ctx);
+  if (int e = render_polar_resident(ctx, res, ang_res, n_theta, n_r)) return e;
+  return tdr_pf_update(ctx, res, u, M);
+}
+
+// ---- exhaustive grid --------------------------------------------------------------------------------
+int tdr_grid_costs(tdr_ctx* ctx, const float* centers_xy, int64_t n, float scale, float res, const int32_t* shifts,
+                   int n_shifts, float* costs_out) {
+  CTX_CHECK(ctx);
+  TDR_REQUIRE(centers_xy && n > 0 && shifts && n_shifts > 0 && n_shifts <= TDR_MAX_SHIFTS, TDR_EINVAL, "bad grid arguments");
+  if (int e = ctx->grid_centers.reserve((size_t)n * 8)) return e;
+  if (int e = ctx->grid_costs.reserve((size_t)n * n_shifts * 4)) return e;
+  if (int e = ctx->grid_shifts.reserve((size_t)n_shifts * 4)) return e;
+  TDR_CUDA(cudaMemcpyAsync(ctx->grid_centers.p, centers_xy, (size_t)n * 8, cudaMemcpyHostToDevice, ctx->stream));
+  TDR_CUDA(cudaMemcpyAsync(ctx->grid_shifts.p, shifts, (size_t)n_shifts * 4, cudaMemcpyHostToDevice, ctx->stream));
+  ctx->grid_n = n; ctx->grid_shifts_n = n_shifts;
+  if (int e = scan_pack(ctx)) return e;
+  if (int e = score_grid(ctx, n, scale, res)) return e;
+  if (costs_out) TDR_CUDA(cudaMemcpyAsync(costs_out, ctx->grid_costs.p, (size_t)n * n_shifts * 4, cudaMemcpyDeviceToHost, ctx->stream));
+  TDR_CUDA(cudaStreamSynchronize(ctx->stream));
+  return TDR_OK;
+}
+
+int tdr_grid_best(tdr_ctx* ctx, float* best_cost, int64_t* best_index) {
+  CTX_CHECK(ctx);
+  long long idx = -1;
+  int e = grid_best(ctx, best_cost, &idx);
+  if (best_index) *best_index = idx;
+  return e;
+}
+
+int tdr_dev_ptr(tdr_ctx* ctx, int which, void** ptr, int64_t* n_elems) {
+  TDR_REQUIRE(ctx && ptr, TDR_EINVAL, "null argument");
+  switch (which) {
+    case TDR_BUF_WEIGHTS: *ptr = ctx->weights.p; if (n_elems) *n_elems = ctx->n_weights; break;
+    case TDR_BUF_GRID_COSTS: *ptr = ctx->grid_costs.p; if (n_elems) *n_elems = ctx->grid_n * ctx->grid_shifts_n; break;
+    case TDR_BUF_SCAN_IMAGES: *ptr = ctx->scan_img.p; if (n_elems) *n_elems = (int64_t)ctx->scan_C * ctx->scan_theta * ctx->scan_r; break;
+    default: tdr::set_error("unknown buffer id %d", which); return TDR_EINVAL;
+  }
+  return TDR_OK;
+}
+
+}  // extern "C"

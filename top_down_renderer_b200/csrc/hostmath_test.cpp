@@ -1,0 +1,112 @@
+// hostmath_test.cpp — host build of tdr_math.cuh for CPU unit tests (tests/test_host_math.py).
+// It exercises the SAME inline functions the kernels use (index arithmetic, fdlibm atan2f, the
+// exact-sum pair algebra).  Not part of the product path: the product library is libtdr_b200.so.
+#include <vector>
+#include "tdr_math.cuh"
+
+using namespace tdr;
+
+extern "C" {
+
+float hm_atan2f(float y, float x) { return fdlibm_atan2f(y, x); }
+
+// bulk compare against libm: returns the number of mismatching bit patterns
+long hm_atan2f_mismatches(const float* y, const float* x, long n) {
+  long bad = 0;
+  for (long i = 0; i < n; i++) {
+    float a = fdlibm_atan2f(y[i], x[i]);
+    float b = atan2f(y[i], x[i]);
+    if (f2u(a) != f2u(b) && !(a != a && b != b)) bad++;
+  }
+  return bad;
+}
+
+int hm_polar_bin(float x, float y, float res, float ang_res, int n_theta, int n_r, int* ti, int* ri) {
+  return polar_bin(x, y, res, ang_res, n_theta, n_r, ti, ri) ? 1 : 0;
+}
+int hm_cart_bin(float x, float y, float res, int rows, int cols, int* xi, int* yi) {
+  return cart_bin(x, y, res, rows, cols, xi, yi) ? 1 : 0;
+}
+int hm_lattice_index(float tab, float scale, float res, float off) { return lattice_index(tab, scale, res, off); }
+int hm_rot_to_shift(float rot, int n_theta) { return rot_to_shift(rot, n_theta); }
+float hm_round(float x) { return round_half_away(x); }
+int hm_f2i(float x) { return f2i_x86(x); }
+float hm_dist_value(unsigned d2, float res) { return dist_value(d2, res); }
+
+// CPU emulation of k_exact_seq: identical control flow (binade segments, crossing adds, irregular
+// tail), with the block scan replaced by a left-to-right composition of the same IncPairs.
+void hm_exact_prefix(const float* x, long n, int chunk, int skip_nan, float* runmax_out, float* total_out,
+                     long* n_segments) {
+  float S = 0.f, rmax = -INFINITY;
+  long pos = 0, segs = 0;
+  int mode = 0;
+  std::vector<IncPair> pref(chunk);
+  while (pos < n) {
+    if (mode == 1) {
+      for (long j = pos; j < n; j++) {
+        float w = x[j];
+        if (skip_nan && w != w) w = 0.f;
+        S = S + w;
+        if (S > rmax) rmax = S;
+        if (runmax_out) runmax_out[j] = rmax;
+      }
+      pos = n;
+      break;
+    }
+    segs++;
+    const int E = binade_of(S);
+    const uint32_t m_in = mant_of(S), limit = binade_limit(E);
+    const int len = (int)((n - pos) < chunk ? (n - pos) : chunk);
+    IncPair agg; agg.a = agg.b = 0;
+    for (int j = 0; j < len; j++) {
+      float w = x[pos + j];
+      if (skip_nan && w != w) w = 0.f;
+      bool irr;
+      agg = pair_compose(agg, inc_pair(w, E, &irr));
+      pref[j] = agg;
+    }
+    const bool odd = (m_in & 1u) != 0;
+    int cross = len;
+    uint32_t mprev = m_in;
+    for (int j = 0; j < len; j++) {
+      uint32_t m = m_in + (odd ? pref[j].b : pref[j].a);
+      if (m >= limit) { cross = j; break; }
+      float Sj = from_binade(E, m);
+      if (runmax_out) runmax_out[pos + j] = Sj > rmax ? Sj : rmax;
+      mprev = m;
+    }
+    if (cross > 0) { S = from_binade(E, mprev); if (S > rmax) rmax = S; }
+    pos += cross;
+    if (cross < len) {
+      float w = x[pos];
+      if (skip_nan && w != w) w = 0.f;
+      S = S + w;
+      if (S > rmax) rmax = S;
+      if (runmax_out) runmax_out[pos] = rmax;
+      pos++;
+      if (!(S >= 0.f) || S == INFINITY) mode = 1;
+    }
+  }
+  if (total_out) *total_out = S;
+  if (n_segments) *n_segments = segs;
+}
+
+// associativity probe: compose pairs in a balanced tree instead of left-to-right and compare
+int hm_pair_tree_equals_chain(const float* x, int n, int E) {
+  std::vector<IncPair> v(n);
+  bool irr;
+  for (int i = 0; i < n; i++) v[i] = inc_pair(x[i], E, &irr);
+  IncPair chain; chain.a = chain.b = 0;
+  for (int i = 0; i < n; i++) chain = pair_compose(chain, v[i]);
+  std::vector<IncPair> t = v;
+  int len = n;
+  while (len > 1) {
+    int o = 0;
+    for (int i = 0; i + 1 < len; i += 2) t[o++] = pair_compose(t[i], t[i + 1]);
+    if (len & 1) t[o++] = t[len - 1];
+    len = o;
+  }
+  return (n == 0) || (t[0].a == chain.a && t[0].b == chain.b);
+}
+
+}  // extern "C"

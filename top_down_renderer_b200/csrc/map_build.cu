@@ -1,0 +1,298 @@
+// map_build.cu — a3/a4/a5: class image -> seeds -> exact truncated EDT -> device map pixels.
+//
+// Reference: TopDownMap::loadCompressedRasterMap (src/top_down_map.cpp:116-144),
+// TopDownMap::computeDists (:289-326), getGeoRasterMap (:410-427).
+//
+// The distance fields are min(sqrtf(d2) * resolution, 50) with d2 the exact integer squared
+// distance to the nearest class pixel (what cv::distanceTransform(DIST_L2, DIST_MASK_PRECISE)
+// returns).  Because of the truncation at 50 only seeds within rcap = ceil(50/resolution) px
+// can matter, so the separable search is windowed and trivially parallel:
+//   pass V: g_c(y, x)  = vertical distance to the nearest class-c seed in column x (<= rcap, else 255)
+//   pass H: d2_c(y, x) = min_{|dx| <= rcap} dx^2 + g_c(y, x+dx)^2        (early exit once dx^2 >= best)
+// Everything is integer until the final sqrtf/mul, hence bit-exact.
+#include "tdr_ctx.cuh"
+#include "tdr_math.cuh"
+
+namespace tdr {
+
+// seed byte: bit c (c < 7) = class c present at the pixel (binary layer == 0); bit 7 = unknown (class_mask_)
+__global__ void k_class_image_to_seeds(const uint8_t* __restrict__ img, int h_img, int w_img, int stride,
+                                       const int32_t* __restrict__ lut, int n_lut, int C, float res, int rows,
+                                       int cols, uint8_t* __restrict__ seed) {
+  int xi = blockIdx.x * blockDim.x + threadIdx.x;
+  int yi = blockIdx.y * blockDim.y + threadIdx.y;
+  if (xi >= cols || yi >= rows) return;
+  // top_down_map.cpp:137-138   max<int>(height - yi*res - 1, 0), min<int>(xi*res, width-1)
+  int src_row = f2i_x86(TDR_FSUB(TDR_FSUB((float)h_img, TDR_FMUL((float)yi, res)), 1.0f));
+  src_row = src_row > 0 ? src_row : 0;
+  int src_col = f2i_x86(TDR_FMUL((float)xi, res));
+  src_col = src_col < w_img - 1 ? src_col : w_img - 1;
+  int v = img[(size_t)src_row * stride + src_col];
+  int cls = (v < n_lut) ? lut[v] : -1;
+  uint8_t s = (cls >= 0 && cls < C) ? (uint8_t)(1u << cls) : (uint8_t)0x80;  // no class -> every layer stays 1 -> unknown
+  seed[(size_t)yi * cols + xi] = s;
+}
+
+// binary float layers (col-major) -> seed bytes.  EDT seed: convertTo(CV_8U) == 0 i.e. cvRound(v) <= 0
+// (top_down_map.cpp:306); mask: sum_c (uint8)trunc(v_c) > C-1 (:294-299).
+__global__ void k_layers_to_seeds(const float* __restrict__ layers, int rows, int cols, int C,
+                                  uint8_t* __restrict__ seed) {
+  int yi = blockIdx.x * blockDim.x + threadIdx.x;   // y fastest in the col-major input
+  int xi = blockIdx.y * blockDim.y + threadIdx.y;
+  if (xi >= cols || yi >= rows) return;
+  size_t L = (size_t)rows * cols;
+  uint32_t bits = 0, msum = 0;
+  for (int c = 0; c < C; c++) {
+    float v = layers[(size_t)c * L + (size_t)xi * rows + yi];
+    float r = rintf(v);                       // cvRound: nearest-even
+    if (!(r >= 1.0f)) bits |= (1u << c);      // saturate_cast<uchar> of <= 0 (or NaN -> 0) is 0 -> seed
+    int t = (int)v;                           // Eigen cast<uint8_t>: truncation
+    msum = (msum + (uint32_t)(t & 0xff)) & 0xffu;
+  }
+  if ((int)msum > C - 1) bits |= 0x80u;
+  seed[(size_t)yi * cols + xi] = (uint8_t)bits;
+}
+
+// geo seeds from class seeds: geo[1] is 0 where any class >= 3 is present, geo[0] = 1 - geo[1]
+// (top_down_map.cpp:417-426).  bit0 = geo0 seed, bit1 = geo1 seed; mask never set (geo0 + geo1 == 1).
+__global__ void k_geo_seeds(const uint8_t* __restrict__ seed, size_t n, int C, uint8_t* __restrict__ gseed) {
+  size_t i = (size_t)blockIdx.x * blockDim.x + threadIdx.x;
+  if (i >= n) return;
+  uint32_t hi = (C > 3) ? (((1u << C) - 1u) & ~7u) : 0u;
+  bool obstacle = (seed[i] & hi) != 0;
+  gseed[i] = obstacle ? 2 : 1;
+}
+
+__global__ void k_edt_vertical(const uint8_t* __restrict__ seed, int rows, int cols, int C, int rcap,
+                               uint8_t* __restrict__ g) {
+  int x = blockIdx.x * blockDim.x + threadIdx.x;
+  int y = blockIdx.y * blockDim.y + threadIdx.y;
+  if (x >= cols || y >= rows) return;
+  const uint32_t all = (1u << C) - 1u;
+  uint32_t found = 0;
+  uint32_t gd[7];
+#pragma unroll
+  for (int c = 0; c < 7; c++) gd[c] = 255;
+  for (int d = 0; d <= rcap; d++) {
+    uint32_t bits = 0;
+    if (y - d >= 0) bits |= seed[(size_t)(y - d) * cols + x];
+    if (y + d < rows) bits |= seed[(size_t)(y + d) * cols + x];
+    bits &= all;
+    uint32_t nw = bits & ~found;
+#pragma unroll
+    for (int c = 0; c < 7; c++)
+      if ((nw >> c) & 1u) gd[c] = d;
+    found |= bits;
+    if (found == all) break;
+  }
+  size_t L = (size_t)rows * cols;
+#pragma unroll
+  for (int c = 0; c < 7; c++)
+    if (c < C) g[(size_t)c * L + (size_t)y * cols + x] = (uint8_t)gd[c];
+}
+
+// TO_MAP: write MapPixel records (class layers + known).  else: planar col-major float layers.
+template <bool TO_MAP>
+__global__ void k_edt_horizontal(const uint8_t* __restrict__ seed, const uint8_t* __restrict__ g, int rows, int cols,
+                                 int C, int rcap, uint32_t capcode, float resolution, MapPixel* __restrict__ map_px,
+                                 float* __restrict__ planar) {
+  int x = blockIdx.x * blockDim.x + threadIdx.x;
+  int y = blockIdx.y * blockDim.y + threadIdx.y;
+  if (x >= cols || y >= rows) return;
+  const size_t L = (size_t)rows * cols;
+  const bool unknown = (seed[(size_t)y * cols + x] & 0x80u) != 0;
+  float out[8];
+#pragma unroll
+  for (int c = 0; c < 8; c++) out[c] = 0.f;
+#pragma unroll
+  for (int c = 0; c < 7; c++) {
+    if (c < C) {
+      const uint8_t* gr = g + (size_t)c * L + (size_t)y * cols;
+      uint32_t g0 = gr[x];
+      uint32_t best = (g0 == 255u) ? 0x3fffffffu : g0 * g0;
+      for (int dx = 1; dx <= rcap && (uint32_t)(dx * dx) < best; dx++) {
+        uint32_t dx2 = (uint32_t)(dx * dx);
+        if (x - dx >= 0) { uint32_t gv = gr[x - dx]; if (gv != 255u) { uint32_t cand = dx2 + gv * gv; best = cand < best ? cand : best; } }
+        if (x + dx < cols) { uint32_t gv = gr[x + dx]; if (gv != 255u) { uint32_t cand = dx2 + gv * gv; best = cand < best ? cand : best; } }
+      }
+      uint32_t d2 = best < capcode ? best : capcode;       // every d2 >= capcode is worth exactly 50
+      out[c] = unknown ? 0.f : dist_value(d2, resolution);  // top_down_map.cpp:312-317
+    }
+  }
+  if (TO_MAP) {
+    out[7] = unknown ? 0.f : 1.f;
+    float4* dst = reinterpret_cast<float4*>(map_px + (size_t)y * cols + x);
+    dst[0] = make_float4(out[0], out[1], out[2], out[3]);
+    dst[1] = make_float4(out[4], out[5], out[6], out[7]);
+  } else {
+#pragma unroll
+    for (int c = 0; c < 7; c++)
+      if (c < C) planar[(size_t)c * L + (size_t)x * rows + y] = out[c];
+  }
+}
+
+// cached distance layers (col-major) + mask -> MapPixel
+__global__ void k_dist_layers_to_map(const float* __restrict__ layers, const uint8_t* __restrict__ mask, int rows,
+                                     int cols, int C, MapPixel* __restrict__ map_px) {
+  int y = blockIdx.x * blockDim.x + threadIdx.x;
+  int x = blockIdx.y * blockDim.y + threadIdx.y;
+  if (x >= cols || y >= rows) return;
+  size_t L = (size_t)rows * cols;
+  float out[8];
+#pragma unroll
+  for (int c = 0; c < 8; c++) out[c] = 0.f;
+  for (int c = 0; c < C; c++) out[c] = layers[(size_t)c * L + (size_t)x * rows + y];
+  out[7] = mask[(size_t)x * rows + y] ? 0.f : 1.f;
+  float4* dst = reinterpret_cast<float4*>(map_px + (size_t)y * cols + x);
+  dst[0] = make_float4(out[0], out[1], out[2], out[3]);
+  dst[1] = make_float4(out[4], out[5], out[6], out[7]);
+}
+
+// MapPixel -> the reference's col-major layers + mask
+__global__ void k_map_to_layers(const MapPixel* __restrict__ map_px, int rows, int cols, int C,
+                                float* __restrict__ layers, uint8_t* __restrict__ mask) {
+  int y = blockIdx.x * blockDim.x + threadIdx.x;
+  int x = blockIdx.y * blockDim.y + threadIdx.y;
+  if (x >= cols || y >= rows) return;
+  size_t L = (size_t)rows * cols;
+  const float4* src = reinterpret_cast<const float4*>(map_px + (size_t)y * cols + x);
+  float4 a = src[0], b = src[1];
+  float v[8] = {a.x, a.y, a.z, a.w, b.x, b.y, b.z, b.w};
+  for (int c = 0; c < C; c++) layers[(size_t)c * L + (size_t)x * rows + y] = v[c];
+  if (mask) mask[(size_t)x * rows + y] = v[7] != 0.f ? 0 : 1;
+}
+
+// smallest d2 whose value is already 50 (host, same IEEE ops as dist_value)
+static uint32_t compute_capcode(float resolution) {
+  for (uint32_t d2 = 0; d2 < (1u << 24); d2++) {
+    float d = sqrtf((float)d2) * resolution;
+    if (d >= 50.0f) return d2;
+  }
+  return 1u << 24;
+}
+
+static int run_edt(tdr_ctx* ctx, const uint8_t* seed, int rows, int cols, int C, float resolution, bool to_map,
+                   float* planar_out) {
+  uint32_t capcode = compute_capcode(resolution);
+  int rcap = (int)ceil(sqrt((double)capcode)) + 1;
+  TDR_REQUIRE(rcap <= 254, TDR_EUNSUPPORTED, "resolution %g needs an EDT window of %d px (> 254)", resolution, rcap);
+  size_t L = (size_t)rows * cols;
+  if (int e = ctx->edt_g.reserve(L * (size_t)C)) return e;
+  dim3 blk(32, 8), grd((cols + 31) / 32, (rows + 7) / 8);
+  k_edt_vertical<<<grd, blk, 0, ctx->stream>>>(seed, rows, cols, C, rcap, ctx->edt_g.as<uint8_t>());
+  if (to_map)
+    k_edt_horizontal<true><<<grd, blk, 0, ctx->stream>>>(seed, ctx->edt_g.as<uint8_t>(), rows, cols, C, rcap, capcode,
+                                                         resolution, ctx->map_px.as<MapPixel>(), nullptr);
+  else
+    k_edt_horizontal<false><<<grd, blk, 0, ctx->stream>>>(seed, ctx->edt_g.as<uint8_t>(), rows, cols, C, rcap, capcode,
+                                                          resolution, nullptr, planar_out);
+  count_launch(ctx, 2);
+  TDR_CUDA(cudaGetLastError());
+  return TDR_OK;
+}
+
+static int map_alloc(tdr_ctx* ctx, int rows, int cols, int C, float resolution) {
+  TDR_REQUIRE(rows > 0 && cols > 0, TDR_EINVAL, "empty map %d x %d", rows, cols);
+  TDR_REQUIRE(C >= 1 && C <= TDR_MAX_CLASSES, TDR_EUNSUPPORTED, "num_classes %d not in [1, %d]", C, TDR_MAX_CLASSES);
+  TDR_REQUIRE(resolution > 0.f, TDR_EINVAL, "resolution must be positive");
+  size_t L = (size_t)rows * cols;
+  if (int e = ctx->map_px.reserve(L * sizeof(MapPixel))) return e;
+  if (int e = ctx->seedbits.reserve(L)) return e;
+  ctx->rows = rows; ctx->cols = cols; ctx->C = C; ctx->resolution = resolution;
+  return TDR_OK;
+}
+
+int map_set_class_image(tdr_ctx* ctx, const uint8_t* img, int h_img, int w_img, int stride, const int32_t* lut,
+                        int n_lut, int C, float resolution) {
+  TDR_REQUIRE(img && lut && h_img > 0 && w_img > 0 && stride >= w_img && n_lut > 0, TDR_EINVAL, "bad class image arguments");
+  TDR_REQUIRE(resolution > 0.f, TDR_EINVAL, "resolution must be positive");
+  int rows = (int)(h_img / resolution), cols = (int)(w_img / resolution);   // top_down_map.cpp:121-122
+  if (int e = map_alloc(ctx, rows, cols, C, resolution)) return e;
+  size_t img_bytes = (size_t)h_img * stride;
+  if (int e = ctx->scratch.reserve(img_bytes)) return e;
+  if (int e = ctx->scratch2.reserve((size_t)n_lut * 4)) return e;
+  TDR_CUDA(cudaMemcpyAsync(ctx->scratch.p, img, img_bytes, cudaMemcpyHostToDevice, ctx->stream));
+  TDR_CUDA(cudaMemcpyAsync(ctx->scratch2.p, lut, (size_t)n_lut * 4, cudaMemcpyHostToDevice, ctx->stream));
+  dim3 blk(32, 8), grd((cols + 31) / 32, (rows + 7) / 8);
+  k_class_image_to_seeds<<<grd, blk, 0, ctx->stream>>>(ctx->scratch.as<uint8_t>(), h_img, w_img, stride,
+                                                       ctx->scratch2.as<int32_t>(), n_lut, C, resolution, rows, cols,
+                                                       ctx->seedbits.as<uint8_t>());
+  count_launch(ctx);
+  TDR_CUDA(cudaGetLastError());
+  if (int e = run_edt(ctx, ctx->seedbits.as<uint8_t>(), rows, cols, C, resolution, true, nullptr)) return e;
+  TDR_CUDA(cudaStreamSynchronize(ctx->stream));  // img / lut are caller-owned pageable buffers
+  ctx->have_map = true; ctx->have_seeds = true;
+  return TDR_OK;
+}
+
+int map_set_binary_layers(tdr_ctx* ctx, const float* layers, int rows, int cols, int C, float resolution) {
+  TDR_REQUIRE(layers, TDR_EINVAL, "null layers");
+  if (int e = map_alloc(ctx, rows, cols, C, resolution)) return e;
+  size_t L = (size_t)rows * cols;
+  if (int e = ctx->scratch.reserve(L * C * 4)) return e;
+  TDR_CUDA(cudaMemcpyAsync(ctx->scratch.p, layers, L * C * 4, cudaMemcpyHostToDevice, ctx->stream));
+  dim3 blk(32, 8), grd((rows + 31) / 32, (cols + 7) / 8);
+  k_layers_to_seeds<<<grd, blk, 0, ctx->stream>>>(ctx->scratch.as<float>(), rows, cols, C, ctx->seedbits.as<uint8_t>());
+  count_launch(ctx);
+  TDR_CUDA(cudaGetLastError());
+  if (int e = run_edt(ctx, ctx->seedbits.as<uint8_t>(), rows, cols, C, resolution, true, nullptr)) return e;
+  TDR_CUDA(cudaStreamSynchronize(ctx->stream));
+  ctx->have_map = true; ctx->have_seeds = true;
+  return TDR_OK;
+}
+
+int map_set_dist_layers(tdr_ctx* ctx, const float* layers, const uint8_t* mask, int rows, int cols, int C,
+                        float resolution) {
+  TDR_REQUIRE(layers && mask, TDR_EINVAL, "null layers / mask");
+  if (int e = map_alloc(ctx, rows, cols, C, resolution)) return e;
+  size_t L = (size_t)rows * cols;
+  if (int e = ctx->scratch.reserve(L * C * 4)) return e;
+  if (int e = ctx->scratch2.reserve(L)) return e;
+  TDR_CUDA(cudaMemcpyAsync(ctx->scratch.p, layers, L * C * 4, cudaMemcpyHostToDevice, ctx->stream));
+  TDR_CUDA(cudaMemcpyAsync(ctx->scratch2.p, mask, L, cudaMemcpyHostToDevice, ctx->stream));
+  dim3 blk(32, 8), grd((rows + 31) / 32, (cols + 7) / 8);
+  k_dist_layers_to_map<<<grd, blk, 0, ctx->stream>>>(ctx->scratch.as<float>(), ctx->scratch2.as<uint8_t>(), rows, cols,
+                                                     C, ctx->map_px.as<MapPixel>());
+  count_launch(ctx);
+  TDR_CUDA(cudaGetLastError());
+  TDR_CUDA(cudaStreamSynchronize(ctx->stream));
+  ctx->have_map = true; ctx->have_seeds = false;   // class presence is not recoverable from distances under the mask
+  return TDR_OK;
+}
+
+int map_get_layers(tdr_ctx* ctx, float* layers, uint8_t* mask) {
+  TDR_REQUIRE(ctx->have_map, TDR_ESTATE, "no map");
+  TDR_REQUIRE(layers, TDR_EINVAL, "null layers");
+  size_t L = (size_t)ctx->rows * ctx->cols;
+  if (int e = ctx->scratch.reserve(L * ctx->C * 4)) return e;
+  if (int e = ctx->scratch2.reserve(L)) return e;
+  dim3 blk(32, 8), grd((ctx->rows + 31) / 32, (ctx->cols + 7) / 8);
+  k_map_to_layers<<<grd, blk, 0, ctx->stream>>>(ctx->map_px.as<MapPixel>(), ctx->rows, ctx->cols, ctx->C,
+                                                ctx->scratch.as<float>(), ctx->scratch2.as<uint8_t>());
+  count_launch(ctx);
+  TDR_CUDA(cudaGetLastError());
+  TDR_CUDA(cudaMemcpyAsync(layers, ctx->scratch.p, L * ctx->C * 4, cudaMemcpyDeviceToHost, ctx->stream));
+  if (mask) TDR_CUDA(cudaMemcpyAsync(mask, ctx->scratch2.p, L, cudaMemcpyDeviceToHost, ctx->stream));
+  TDR_CUDA(cudaStreamSynchronize(ctx->stream));
+  return TDR_OK;
+}
+
+int map_get_geo_layers(tdr_ctx* ctx, float* geo_layers) {
+  TDR_REQUIRE(ctx->have_map && ctx->have_seeds, TDR_ESTATE, "geo layers need a map built from class seeds");
+  TDR_REQUIRE(geo_layers, TDR_EINVAL, "null output");
+  size_t L = (size_t)ctx->rows * ctx->cols;
+  if (int e = ctx->scratch2.reserve(L)) return e;
+  if (int e = ctx->scratch.reserve(L * 2 * 4)) return e;
+  k_geo_seeds<<<(unsigned)((L + 255) / 256), 256, 0, ctx->stream>>>(ctx->seedbits.as<uint8_t>(), L, ctx->C,
+                                                                     ctx->scratch2.as<uint8_t>());
+  count_launch(ctx);
+  TDR_CUDA(cudaGetLastError());
+  if (int e = run_edt(ctx, ctx->scratch2.as<uint8_t>(), ctx->rows, ctx->cols, 2, ctx->resolution, false,
+                      ctx->scratch.as<float>()))
+    return e;
+  TDR_CUDA(cudaMemcpyAsync(geo_layers, ctx->scratch.p, L * 2 * 4, cudaMemcpyDeviceToHost, ctx->stream));
+  TDR_CUDA(cudaStreamSynchronize(ctx->stream));
+  return TDR_OK;
+}
+
+}  // namespace tdr

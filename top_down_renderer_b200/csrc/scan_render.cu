@@ -1,0 +1,185 @@
+// scan_render.cu — a1/a2: semantic scan rasterisers.
+//
+// Reference: ScanRendererPolar::renderSemanticTopDown (src/scan_renderer_polar.cpp:83-109) and
+// ScanRenderer::renderSemanticTopDown (src/scan_renderer.cpp:55-78).
+//
+// The images are integer histograms (the reference's float "+= 1" is exact below 2^24), so the
+// result is order-independent and bit-exact as soon as the bin index is (tdr_math.cuh).
+// Small images (the live 100 x 25 polar image): ATOMIC-FREE.  Every warp owns a private uint16
+// histogram in shared memory; inside a warp, lanes that hit the same bin are aggregated with
+// match.any so exactly one lane per distinct bin updates the warp's histogram; the per-warp
+// histograms are summed per CTA into a partial in global memory and a second kernel folds the
+// partials.  No atomics anywhere, bit-reproducible.
+// Large images (refine_map-style batch rasterisation, BASELINE cfg5): warp-aggregated integer
+// red.global (still exact, order-independent).
+#include "tdr_ctx.cuh"
+#include "tdr_math.cuh"
+
+namespace tdr {
+
+struct ScanParams {
+  const uint8_t* pts; int stride; int ioff; long long n;
+  const int32_t* lut; int n_lut; int C;
+  float res; float ang_res;   // polar
+  int d0, d1;                 // polar: n_theta, n_r ; cart: rows, cols
+  int polar;
+};
+
+__device__ __forceinline__ int scan_key(const ScanParams& sp, long long i) {
+  const uint8_t* p = sp.pts + i * sp.stride;
+  float x = *reinterpret_cast<const float*>(p);
+  float y = *reinterpret_cast<const float*>(p + 4);
+  int a, b;
+  bool ok = sp.polar ? polar_bin(x, y, sp.res, sp.ang_res, sp.d0, sp.d1, &a, &b)
+                     : cart_bin(x, y, sp.res, sp.d0, sp.d1, &a, &b);
+  if (!ok) return -1;
+  float inten = *reinterpret_cast<const float*>(p + sp.ioff);
+  int cls = f2i_x86(inten);                       // int pt_class = intensity (:103)
+  if (cls < 0 || cls >= sp.n_lut) return -1;      // unchecked in the reference (UB); dropped here
+  int f = sp.lut[cls];
+  if (f < 0 || f >= sp.C) return -1;
+  // polar: img(theta_ind, r_ind) -> r*n_theta + theta ; cart: img(y_ind, x_ind) -> x*rows + y  (a = x_ind, b = y_ind)
+  int cell = sp.polar ? (b * sp.d0 + a) : (a * sp.d0 + b);
+  return f * (sp.d0 * sp.d1) + cell;
+}
+
+// grid.x CTAs x W warps; warp g handles points [g*per_warp, (g+1)*per_warp)
+__global__ void k_scan_bin_private(ScanParams sp, int bins, long long per_warp, int32_t* __restrict__ partial) {
+  extern __shared__ uint16_t sh_hist[];
+  const int W = blockDim.x >> 5, warp = threadIdx.x >> 5, lane = threadIdx.x & 31;
+  for (int i = threadIdx.x; i < W * bins; i += blockDim.x) sh_hist[i] = 0;
+  __syncthreads();
+  uint16_t* mine = sh_hist + (size_t)warp * bins;
+  long long g = (long long)blockIdx.x * W + warp;
+  long long lo = g * per_warp, hi = lo + per_warp;
+  if (hi > sp.n) hi = sp.n;
+  for (long long base = lo; base < hi; base += 32) {
+    long long i = base + lane;
+    int key = (i < hi) ? scan_key(sp, i) : -1;
+    unsigned peers = __match_any_sync(0xffffffffu, key);
+    if (key >= 0 && lane == (__ffs(peers) - 1)) mine[key] = (uint16_t)(mine[key] + __popc(peers));
+    __syncwarp();
+  }
+  __syncthreads();
+  for (int b = threadIdx.x; b < bins; b += blockDim.x) {
+    int s = 0;
+    for (int w = 0; w < W; w++) s += sh_hist[(size_t)w * bins + b];
+    partial[(size_t)blockIdx.x * bins + b] = s;
+  }
+}
+
+__global__ void k_hist_fold(const int32_t* __restrict__ partial, int nparts, int bins, int accumulate,
+                            int32_t* __restrict__ hist) {
+  int b = blockIdx.x * blockDim.x + threadIdx.x;
+  if (b >= bins) return;
+  int s = accumulate ? hist[b] : 0;
+  for (int p = 0; p < nparts; p++) s += partial[(size_t)p * bins + b];
+  hist[b] = s;
+}
+
+__global__ void k_scan_bin_global(ScanParams sp, int32_t* __restrict__ hist) {
+  long long i = (long long)blockIdx.x * blockDim.x + threadIdx.x;
+  int lane = threadIdx.x & 31;
+  int key = (i < sp.n) ? scan_key(sp, i) : -1;
+  unsigned peers = __match_any_sync(0xffffffffu, key);
+  if (key >= 0 && lane == (__ffs(peers) - 1)) atomicAdd(hist + key, __popc(peers));
+}
+
+// counts -> the reference's float images ("+= 1" on a float saturates at 2^24)
+__global__ void k_hist_to_float(const int32_t* __restrict__ hist, int bins, float* __restrict__ img) {
+  int b = blockIdx.x * blockDim.x + threadIdx.x;
+  if (b >= bins) return;
+  int v = hist[b];
+  img[b] = (float)(v > 16777216 ? 16777216 : v);
+}
+
+// scan_pack[p][c] = count_c[p] * 0.01 * w_c (c < C), slot 7 = sum_c count_c[p]
+// (state_particle.cpp:136-142: cost += S*0.01*w_c ; normalization += sum scan_c*known)
+__global__ void k_scan_pack(const float* __restrict__ img, int P, int C, const float* __restrict__ cw,
+                            float* __restrict__ pack) {
+  int p = blockIdx.x * blockDim.x + threadIdx.x;
+  if (p >= P) return;
+  float out[8];
+#pragma unroll
+  for (int c = 0; c < 8; c++) out[c] = 0.f;
+  float tot = 0.f;
+  for (int c = 0; c < C; c++) {
+    float v = img[(size_t)c * P + p];
+    out[c] = (float)((double)v * 0.01 * (double)cw[c]);
+    tot += v;
+  }
+  out[7] = tot;
+  float4* dst = reinterpret_cast<float4*>(pack + (size_t)p * 8);
+  dst[0] = make_float4(out[0], out[1], out[2], out[3]);
+  dst[1] = make_float4(out[4], out[5], out[6], out[7]);
+}
+
+static const int kSmemBudget = 200 * 1024;
+
+int scan_render(tdr_ctx* ctx, bool polar, float res, float ang_res, int d0, int d1, float* dev_img_out) {
+  TDR_REQUIRE(ctx->n_lut > 0, TDR_ESTATE, "tdr_scan_set_lut has not been called");
+  TDR_REQUIRE(res > 0.f && d0 > 0 && d1 > 0, TDR_EINVAL, "bad raster arguments");
+  const int C = ctx->lut_classes;
+  const long long cells = (long long)d0 * d1;
+  TDR_REQUIRE(cells * C < (1ll << 30), TDR_EINVAL, "image too large");
+  const int bins = (int)(cells * C);
+  ScanParams sp;
+  sp.pts = ctx->pts.as<uint8_t>(); sp.stride = ctx->pts_stride; sp.ioff = ctx->pts_ioff; sp.n = ctx->n_pts;
+  sp.lut = ctx->lut.as<int32_t>(); sp.n_lut = ctx->n_lut; sp.C = C;
+  sp.res = res; sp.ang_res = ang_res; sp.d0 = d0; sp.d1 = d1; sp.polar = polar ? 1 : 0;
+  if (int e = ctx->hist.reserve((size_t)bins * 4)) return e;
+  int W = kSmemBudget / (2 * bins);
+  if (W > 8) W = 8;
+  if (W >= 2 && ctx->n_pts > 0) {
+    // atomic-free path
+    static bool attr_set = false;
+    if (!attr_set) {
+      TDR_CUDA(cudaFuncSetAttribute(k_scan_bin_private, cudaFuncAttributeMaxDynamicSharedMemorySize, kSmemBudget + 8192));
+      attr_set = true;
+    }
+    long long done = 0;
+    int round = 0;
+    while (done < ctx->n_pts) {
+      long long n_here = ctx->n_pts - done;
+      // every warp handles at most 65504 points (uint16 counters), aim for >= 512 per warp
+      long long warps_needed = (n_here + 511) / 512;
+      int ctas = (int)((warps_needed + W - 1) / W);
+      if (ctas > ctx->sm_count) ctas = ctx->sm_count;
+      if (ctas < 1) ctas = 1;
+      long long per_warp = (n_here + (long long)ctas * W - 1) / ((long long)ctas * W);
+      per_warp = (per_warp + 31) / 32 * 32;
+      if (per_warp > 65504) { per_warp = 65504; n_here = per_warp * ctas * W; }
+      ScanParams s2 = sp; s2.pts = sp.pts + done * sp.stride; s2.n = n_here;
+      if (int e = ctx->scratch.reserve((size_t)ctas * bins * 4)) return e;
+      k_scan_bin_private<<<ctas, W * 32, (size_t)W * bins * 2, ctx->stream>>>(s2, bins, per_warp, ctx->scratch.as<int32_t>());
+      k_hist_fold<<<(bins + 255) / 256, 256, 0, ctx->stream>>>(ctx->scratch.as<int32_t>(), ctas, bins, round > 0,
+                                                               ctx->hist.as<int32_t>());
+      count_launch(ctx, 2);
+      done += n_here; round++;
+    }
+  } else {
+    TDR_CUDA(cudaMemsetAsync(ctx->hist.p, 0, (size_t)bins * 4, ctx->stream));
+    if (ctx->n_pts > 0) {
+      long long blocks = (ctx->n_pts + 255) / 256;
+      k_scan_bin_global<<<(unsigned)blocks, 256, 0, ctx->stream>>>(sp, ctx->hist.as<int32_t>());
+      count_launch(ctx);
+    }
+  }
+  k_hist_to_float<<<(bins + 255) / 256, 256, 0, ctx->stream>>>(ctx->hist.as<int32_t>(), bins, dev_img_out);
+  count_launch(ctx);
+  TDR_CUDA(cudaGetLastError());
+  return TDR_OK;
+}
+
+int scan_pack(tdr_ctx* ctx) {
+  TDR_REQUIRE(ctx->have_scan && ctx->have_params, TDR_ESTATE, "scan images / filter params missing");
+  int P = ctx->scan_theta * ctx->scan_r;
+  if (int e = ctx->scan_pack.reserve((size_t)P * 8 * 4)) return e;
+  k_scan_pack<<<(P + 127) / 128, 128, 0, ctx->stream>>>(ctx->scan_img.as<float>(), P, ctx->scan_C,
+                                                        ctx->d_cw.as<float>(), ctx->scan_pack.as<float>());
+  count_launch(ctx);
+  TDR_CUDA(cudaGetLastError());
+  return TDR_OK;
+}
+
+}  // namespace tdr

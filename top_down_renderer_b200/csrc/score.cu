@@ -1,0 +1,401 @@
+// score.cu — a7/a9/a10: polar local-map gather + circular shift-correlation + weight.
+//
+// Reference: TopDownMapPolar::getLocalMap (src/top_down_map_polar.cpp:21-53),
+// StateParticle::getCostForRot (src/state_particle.cpp:112-155),
+// StateParticle::computeWeight (:157-219).
+//
+// Data layout: the map is one 32-byte record per pixel (MapPixel: <=7 class distances + known),
+// so ONE sector serves every class layer and the mask of a lattice point (the reference's planar
+// col-major layers need C+1 sectors).  A lane pair fetches the two 16-byte halves of a record.
+// The scan is pre-packed per lattice cell as 8 floats (class counts scaled by 0.01*w_c, and the
+// class-summed count for the normalisation) and staged in shared memory once per CTA.
+//
+//   k_score_track : one warp per particle, one row shift (tracking; have_init == true)
+//   k_score_search: one CTA per hypothesis centre, n_shifts row shifts evaluated against the SAME
+//                   gathered local map held in registers (theta search; also the exhaustive grid)
+#include "tdr_ctx.cuh"
+#include "tdr_math.cuh"
+
+namespace tdr {
+
+struct ScoreParams {
+  const MapPixel* map; int rows, cols; float resolution;
+  const float* tab; int n_theta, n_r, P;
+  const float* scan_pack;
+  float res;
+  // particles
+  const float *init_x, *init_y, *dx, *dy; float* theta; const float* scale; uint8_t* have_init;
+  long long n;
+  // gates / weight
+  int force_on_map; float map_w, map_h; int scale_gate; double scale_lo, scale_hi; float regularization;
+  // search list
+  const float* thetas; const int32_t* shifts; int n_shifts;
+  // outputs
+  float* weights;
+  // grid mode
+  const float* centers; float grid_scale; float* costs;
+};
+
+__device__ __forceinline__ float4 ldg4(const void* p) { return __ldg(reinterpret_cast<const float4*>(p)); }
+
+__device__ __forceinline__ float weight_from_cost(float cost, float reg) {
+  return (float)(1.0 / (double)TDR_FADD(cost, reg));   // state_particle.cpp:212
+}
+
+// centre + gates (state_particle.cpp:161-176).  returns false when the particle is gated (weight 0).
+__device__ __forceinline__ bool particle_centre(const ScoreParams& sp, long long i, float* cx, float* cy, float* sc) {
+  float s = sp.scale[i];
+  float x = TDR_FADD(TDR_FMUL(sp.dx[i], s), sp.init_x[i]);
+  float y = TDR_FADD(TDR_FMUL(sp.dy[i], s), sp.init_y[i]);
+  *cx = x; *cy = y; *sc = s;
+  if (sp.force_on_map && (x < 0.f || y < 0.f || x > sp.map_w || y > sp.map_h)) return false;
+  if (sp.scale_gate && ((double)s < sp.scale_lo || (double)s > sp.scale_hi)) return false;
+  return true;
+}
+
+// ------------------------------------------------------------------------------------------------
+// tracking: warp per particle
+// shared: scan_pack (P*8 floats) | tab (2P floats) | cellpos (P x ushort2: theta, n_theta*r)
+// ------------------------------------------------------------------------------------------------
+__global__ void __launch_bounds__(256) k_score_track(ScoreParams sp) {
+  extern __shared__ __align__(16) unsigned char smem[];
+  float* s_scan = reinterpret_cast<float*>(smem);
+  float* s_tab = s_scan + (size_t)sp.P * 8;
+  ushort2* s_cell = reinterpret_cast<ushort2*>(s_tab + (size_t)sp.P * 2);
+  for (int i = threadIdx.x; i < sp.P * 2; i += blockDim.x) {   // float4 copies of the packed scan
+    reinterpret_cast<float4*>(s_scan)[i] = ldg4(sp.scan_pack + (size_t)i * 4);
+  }
+  for (int i = threadIdx.x; i < sp.P * 2; i += blockDim.x) s_tab[i] = sp.tab[i];
+  for (int i = threadIdx.x; i < sp.P; i += blockDim.x) {
+    int r = i / sp.n_theta;
+    s_cell[i] = make_ushort2((unsigned short)(i - r * sp.n_theta), (unsigned short)(r * sp.n_theta));
+  }
+  __syncthreads();
+
+  const int lane = threadIdx.x & 31, half = lane & 1;
+  const long long warps_total = (long long)gridDim.x * (blockDim.x >> 5);
+  const char* map_bytes = reinterpret_cast<const char*>(sp.map);
+  const int n_iter = (sp.P + 31) / 32;
+  for (long long i = (long long)blockIdx.x * (blockDim.x >> 5) + (threadIdx.x >> 5); i < sp.n; i += warps_total) {
+    if (!sp.have_init[i]) continue;                       // searched by k_score_search
+    float cx, cy, sc;
+    if (!particle_centre(sp, i, &cx, &cy, &sc)) { if (lane == 0) sp.weights[i] = 0.f; continue; }
+    const float oy = TDR_FDIV(cy, sp.resolution), ox = TDR_FDIV(cx, sp.resolution);   // top_down_map_polar.cpp:29-30
+    const int shift = rot_to_shift(sp.theta[i], sp.n_theta);
+    float acc_c = 0.f, acc_n = 0.f, acc_k = 0.f;
+    for (int it = 0; it < n_iter; it++) {
+      int p = it * 32 + lane;
+      long long pix = -1;
+      if (p < sp.P) {
+        int r = lattice_index(s_tab[2 * p], sc, sp.res, oy);
+        int c = lattice_index(s_tab[2 * p + 1], sc, sp.res, ox);
+        if (r >= 0 && r < sp.rows && c >= 0 && c < sp.cols) pix = (long long)r * sp.cols + c;
+      }
+#pragma unroll
+      for (int j = 0; j < 2; j++) {
+        int src = (lane >> 1) + 16 * j;
+        long long pj = __shfl_sync(0xffffffffu, pix, src);
+        int pp = it * 32 + src;
+        if (pj >= 0) {                                     // out of bounds: value 0, mask 1 -> contributes nothing
+          float4 v = ldg4(map_bytes + pj * 32 + half * 16);
+          ushort2 cell = s_cell[pp];
+          int th = cell.x + shift;                         // scan row (m + s) mod n_theta pairs with map row m
+          if (th >= sp.n_theta) th -= sp.n_theta;
+          float4 sv = *reinterpret_cast<const float4*>(s_scan + ((size_t)(cell.y + th)) * 8 + half * 4);
+          if (half == 0) {
+            acc_c = fmaf(v.x, sv.x, acc_c); acc_c = fmaf(v.y, sv.y, acc_c);
+            acc_c = fmaf(v.z, sv.z, acc_c); acc_c = fmaf(v.w, sv.w, acc_c);
+          } else {
+            acc_c = fmaf(v.x, sv.x, acc_c); acc_c = fmaf(v.y, sv.y, acc_c); acc_c = fmaf(v.z, sv.z, acc_c);
+            acc_n = fmaf(v.w, sv.w, acc_n);
+            acc_k += v.w;
+          }
+        }
+      }
+    }
+#pragma unroll
+    for (int o = 16; o > 0; o >>= 1) {
+      acc_c += __shfl_xor_sync(0xffffffffu, acc_c, o);
+      acc_n += __shfl_xor_sync(0xffffffffu, acc_n, o);
+      acc_k += __shfl_xor_sync(0xffffffffu, acc_k, o);
+    }
+    if (lane == 0) {
+      float cost;
+      if ((double)TDR_FDIV(acc_k, (float)sp.P) < 0.5) cost = __int_as_float(0x7fc00000);   // :117-120
+      else cost = TDR_FDIV(acc_c, acc_n);                                                 // :154
+      sp.weights[i] = weight_from_cost(cost, sp.regularization);
+    }
+  }
+}
+
+// ------------------------------------------------------------------------------------------------
+// theta search / exhaustive grid: CTA per centre, the gathered local map lives in registers
+// shared: scan_pack (P*8 floats) | partial sums [n_shifts][warps][2] | misc
+// ------------------------------------------------------------------------------------------------
+template <int THREADS, int JMAX>
+__global__ void __launch_bounds__(THREADS) k_score_search(ScoreParams sp, int grid_mode) {
+  extern __shared__ __align__(16) unsigned char smem[];
+  constexpr int WARPS = THREADS / 32;
+  float* s_scan = reinterpret_cast<float*>(smem);
+  float* s_part = s_scan + (size_t)sp.P * 8;               // [n_shifts][WARPS][2]
+  float* s_kc = s_part + (size_t)sp.n_shifts * WARPS * 2;   // [WARPS]
+  for (int i = threadIdx.x; i < sp.P * 2; i += THREADS)
+    reinterpret_cast<float4*>(s_scan)[i] = ldg4(sp.scan_pack + (size_t)i * 4);
+
+  // this thread's lattice points never change: p = tid + THREADS*j
+  float ty[JMAX], tx[JMAX];
+  int cth[JMAX], crb[JMAX];
+#pragma unroll
+  for (int j = 0; j < JMAX; j++) {
+    int p = threadIdx.x + THREADS * j;
+    if (p < sp.P) {
+      ty[j] = sp.tab[2 * p]; tx[j] = sp.tab[2 * p + 1];
+      int r = p / sp.n_theta;
+      cth[j] = p - r * sp.n_theta; crb[j] = r * sp.n_theta;
+    } else { ty[j] = 0.f; tx[j] = 0.f; cth[j] = -1; crb[j] = 0; }
+  }
+  __syncthreads();
+  const int lane = threadIdx.x & 31, warp = threadIdx.x >> 5;
+  const char* map_bytes = reinterpret_cast<const char*>(sp.map);
+
+  for (long long i = blockIdx.x; i < sp.n; i += gridDim.x) {
+    float cx, cy, sc;
+    if (grid_mode) { cx = sp.centers[2 * i]; cy = sp.centers[2 * i + 1]; sc = sp.grid_scale; }
+    else {
+      if (sp.have_init[i]) continue;                       // block-uniform
+      if (!particle_centre(sp, i, &cx, &cy, &sc)) { if (threadIdx.x == 0) sp.weights[i] = 0.f; continue; }
+    }
+    const float oy = TDR_FDIV(cy, sp.resolution), ox = TDR_FDIV(cx, sp.resolution);
+    float4 ma[JMAX], mb[JMAX];
+    float kc = 0.f;
+#pragma unroll
+    for (int j = 0; j < JMAX; j++) {
+      ma[j] = make_float4(0.f, 0.f, 0.f, 0.f); mb[j] = ma[j];
+      if (cth[j] >= 0) {
+        int r = lattice_index(ty[j], sc, sp.res, oy);
+        int c = lattice_index(tx[j], sc, sp.res, ox);
+        if (r >= 0 && r < sp.rows && c >= 0 && c < sp.cols) {
+          const char* px = map_bytes + ((long long)r * sp.cols + c) * 32;
+          ma[j] = ldg4(px); mb[j] = ldg4(px + 16);
+        }
+      }
+    }
+#pragma unroll
+    for (int j = 0; j < JMAX; j++) kc += mb[j].w;
+#pragma unroll
+    for (int o = 16; o > 0; o >>= 1) kc += __shfl_xor_sync(0xffffffffu, kc, o);
+    if (lane == 0) s_kc[warp] = kc;
+
+    for (int k = 0; k < sp.n_shifts; k++) {
+      const int shift = sp.shifts[k];
+      float acc_c = 0.f, acc_n = 0.f;
+#pragma unroll
+      for (int j = 0; j < JMAX; j++) {
+        if (cth[j] >= 0) {
+          int th = cth[j] + shift;
+          if (th >= sp.n_theta) th -= sp.n_theta;
+          const float4* sv = reinterpret_cast<const float4*>(s_scan + ((size_t)(crb[j] + th)) * 8);
+          float4 s0 = sv[0], s1 = sv[1];
+          acc_c = fmaf(ma[j].x, s0.x, acc_c); acc_c = fmaf(ma[j].y, s0.y, acc_c);
+          acc_c = fmaf(ma[j].z, s0.z, acc_c); acc_c = fmaf(ma[j].w, s0.w, acc_c);
+          acc_c = fmaf(mb[j].x, s1.x, acc_c); acc_c = fmaf(mb[j].y, s1.y, acc_c);
+          acc_c = fmaf(mb[j].z, s1.z, acc_c);
+          acc_n = fmaf(mb[j].w, s1.w, acc_n);
+        }
+      }
+#pragma unroll
+      for (int o = 16; o > 0; o >>= 1) {
+        acc_c += __shfl_xor_sync(0xffffffffu, acc_c, o);
+        acc_n += __shfl_xor_sync(0xffffffffu, acc_n, o);
+      }
+      if (lane == 0) { s_part[((size_t)k * WARPS + warp) * 2] = acc_c; s_part[((size_t)k * WARPS + warp) * 2 + 1] = acc_n; }
+    }
+    __syncthreads();
+    // finalise: thread k owns shift k (fixed summation order -> deterministic)
+    float known = 0.f;
+    for (int w = 0; w < WARPS; w++) known += s_kc[w];
+    const bool unknown = (double)TDR_FDIV(known, (float)sp.P) < 0.5;
+    for (int k = threadIdx.x; k < sp.n_shifts; k += THREADS) {
+      float c = 0.f, nrm = 0.f;
+      for (int w = 0; w < WARPS; w++) { c += s_part[((size_t)k * WARPS + w) * 2]; nrm += s_part[((size_t)k * WARPS + w) * 2 + 1]; }
+      float cost = unknown ? __int_as_float(0x7fc00000) : TDR_FDIV(c, nrm);
+      if (grid_mode) sp.costs[i * sp.n_shifts + k] = cost;
+      s_part[(size_t)k * WARPS * 2] = cost;               // slot (k, warp 0, 0) is only read by thread k above
+    }
+    __syncthreads();
+    if (!grid_mode && threadIdx.x == 0) {
+      float best = 3.402823466e+38f, best_theta = 0.f;      // state_particle.cpp:193-204
+      for (int k = 0; k < sp.n_shifts; k++) {
+        float c = s_part[(size_t)k * WARPS * 2];
+        if (c < best) { best = c; best_theta = sp.thetas[k]; }
+      }
+      sp.theta[i] = best_theta;
+      sp.have_init[i] = 1;
+      sp.weights[i] = weight_from_cost(best, sp.regularization);
+    }
+    __syncthreads();
+  }
+}
+
+// a7 as a stand-alone operator (ActiveLocalizer / debug / parity): n centres -> dists n x C x P, mask n x P
+__global__ void k_local_polar(const MapPixel* __restrict__ map, int rows, int cols, int C, float resolution,
+                              const float* __restrict__ tab, int P, const float* __restrict__ centers, int n,
+                              float scale, float res, float* __restrict__ dists, uint8_t* __restrict__ mask) {
+  int p = blockIdx.x * blockDim.x + threadIdx.x;
+  int i = blockIdx.y;
+  if (p >= P || i >= n) return;
+  float oy = TDR_FDIV(centers[2 * i + 1], resolution), ox = TDR_FDIV(centers[2 * i], resolution);
+  int r = lattice_index(tab[2 * p], scale, res, oy);
+  int c = lattice_index(tab[2 * p + 1], scale, res, ox);
+  float v[8] = {0, 0, 0, 0, 0, 0, 0, 0};
+  if (r >= 0 && r < rows && c >= 0 && c < cols) {
+    const float4* px = reinterpret_cast<const float4*>(map + (size_t)r * cols + c);
+    float4 a = px[0], b = px[1];
+    v[0] = a.x; v[1] = a.y; v[2] = a.z; v[3] = a.w; v[4] = b.x; v[5] = b.y; v[6] = b.z; v[7] = b.w;
+  }
+  for (int k = 0; k < C; k++) dists[((size_t)i * C + k) * P + p] = v[k];
+  mask[(size_t)i * P + p] = v[7] != 0.f ? 0 : 1;
+}
+
+// a8: Cartesian local map (top_down_map.cpp:429-459 with samplePts :367-389)
+__device__ __forceinline__ float linspaced(int size, float sres, int i) {
+  float low = (float)((double)TDR_FMUL(-sres, (float)(size - 1)) / 2.);
+  float high = (float)((double)TDR_FMUL(sres, (float)(size - 1)) / 2.);
+  if (size == 1) return low;
+  float step = TDR_FDIV(TDR_FSUB(high, low), (float)(size - 1));
+  bool flip = fabsf(high) < fabsf(low);
+  int size1 = size - 1;
+  if (flip) return (i == 0) ? low : TDR_FSUB(high, TDR_FMUL((float)(size1 - i), step));
+  return (i == size1) ? high : TDR_FADD(low, TDR_FMUL((float)i, step));
+}
+
+__global__ void k_local_cart(const MapPixel* __restrict__ map, int rows, int cols, int C, float resolution, float cx,
+                             float cy, float cr, float sr, float res, int out_rows, int out_cols,
+                             float* __restrict__ dists, uint8_t* __restrict__ mask) {
+  int p = blockIdx.x * blockDim.x + threadIdx.x;
+  int P = out_rows * out_cols;
+  if (p >= P) return;
+  float sres = TDR_FDIV(res, resolution);
+  float c0 = TDR_FDIV(cx, resolution), c1 = TDR_FDIV(cy, resolution);
+  float x = linspaced(out_rows, sres, p % out_rows);
+  float y = linspaced(out_cols, sres, p / out_rows);
+  float xr = TDR_FADD(TDR_FMUL(cr, x), TDR_FMUL(-sr, y));
+  float yr = TDR_FADD(TDR_FMUL(sr, x), TDR_FMUL(cr, y));
+  xr = TDR_FADD(xr, c1); yr = TDR_FADD(yr, c0);
+  int r = f2i_x86(round_half_away(xr)), c = f2i_x86(round_half_away(yr));
+  float v[8] = {0, 0, 0, 0, 0, 0, 0, 0};
+  if (r >= 0 && r < rows && c >= 0 && c < cols) {
+    const float4* px = reinterpret_cast<const float4*>(map + (size_t)r * cols + c);
+    float4 a = px[0], b = px[1];
+    v[0] = a.x; v[1] = a.y; v[2] = a.z; v[3] = a.w; v[4] = b.x; v[5] = b.y; v[6] = b.z; v[7] = b.w;
+  }
+  for (int k = 0; k < C; k++) dists[(size_t)k * P + p] = v[k];
+  mask[p] = v[7] != 0.f ? 0 : 1;
+}
+
+// ------------------------------------------------------------------------------------------------
+static const int SEARCH_THREADS = 512;
+static const int SEARCH_JMAX = 5;     // 512 * 5 = 2560 >= P = 2500
+
+static int fill_params(tdr_ctx* ctx, float res, ScoreParams* sp) {
+  TDR_REQUIRE(ctx->have_map, TDR_ESTATE, "no map");
+  TDR_REQUIRE(ctx->have_tab, TDR_ESTATE, "no polar table");
+  TDR_REQUIRE(ctx->have_scan, TDR_ESTATE, "no scan images");
+  TDR_REQUIRE(ctx->have_params, TDR_ESTATE, "no filter params");
+  TDR_REQUIRE(ctx->scan_theta == ctx->n_theta && ctx->scan_r == ctx->n_r, TDR_EINVAL,
+              "scan image %dx%d does not match the polar table %dx%d", ctx->scan_theta, ctx->scan_r, ctx->n_theta, ctx->n_r);
+  TDR_REQUIRE(ctx->scan_C == ctx->C && ctx->fp.num_classes == ctx->C, TDR_EINVAL,
+              "class counts differ: scan %d, map %d, params %d", ctx->scan_C, ctx->C, ctx->fp.num_classes);
+  sp->map = ctx->map_px.as<MapPixel>(); sp->rows = ctx->rows; sp->cols = ctx->cols; sp->resolution = ctx->resolution;
+  sp->tab = ctx->tab.as<float>(); sp->n_theta = ctx->n_theta; sp->n_r = ctx->n_r; sp->P = ctx->n_theta * ctx->n_r;
+  sp->scan_pack = ctx->scan_pack.as<float>();
+  sp->res = res;
+  sp->force_on_map = ctx->fp.force_on_map;
+  // StateParticle::width_/height_ = map->size().cast<float>() * map->resolution()  (state_particle.cpp:11,46-47)
+  sp->map_w = (float)ctx->cols * ctx->resolution; sp->map_h = (float)ctx->rows * ctx->resolution;
+  sp->scale_gate = ctx->fp.fixed_scale < 0 ? 1 : 0;                                   // :169
+  sp->scale_lo = pow(10.0, (double)ctx->fp.scale_log_min); sp->scale_hi = pow(10.0, (double)ctx->fp.scale_log_max);
+  sp->regularization = ctx->fp.regularization;
+  sp->thetas = ctx->d_search_thetas.as<float>(); sp->shifts = ctx->d_search_shifts.as<int32_t>();
+  sp->n_shifts = (int)ctx->search_shifts.size();
+  sp->centers = nullptr; sp->grid_scale = 1.f; sp->costs = nullptr;
+  return TDR_OK;
+}
+
+int score_particles(tdr_ctx* ctx, float res) {
+  ScoreParams sp;
+  if (int e = fill_params(ctx, res, &sp)) return e;
+  tdr::Particles& pt = ctx->part[ctx->cur];
+  TDR_REQUIRE(pt.n > 0, TDR_ESTATE, "no particles");
+  sp.init_x = pt.init_x.as<float>(); sp.init_y = pt.init_y.as<float>(); sp.dx = pt.dx.as<float>(); sp.dy = pt.dy.as<float>();
+  sp.theta = pt.theta.as<float>(); sp.scale = pt.scale.as<float>(); sp.have_init = pt.have_init.as<uint8_t>();
+  sp.n = pt.n;
+  if (int e = ctx->weights.reserve((size_t)pt.n * 4)) return e;
+  sp.weights = ctx->weights.as<float>();
+  ctx->n_weights = pt.n;
+  const int P = sp.P;
+  TDR_REQUIRE(P <= 65535 && P <= SEARCH_THREADS * SEARCH_JMAX, TDR_EUNSUPPORTED, "polar image of %d cells is too large (max %d)", P, SEARCH_THREADS * SEARCH_JMAX);
+  static bool attr_set = false;
+  if (!attr_set) {
+    TDR_CUDA(cudaFuncSetAttribute(k_score_track, cudaFuncAttributeMaxDynamicSharedMemorySize, 200 * 1024));
+    TDR_CUDA(cudaFuncSetAttribute(k_score_search<SEARCH_THREADS, SEARCH_JMAX>, cudaFuncAttributeMaxDynamicSharedMemorySize, 200 * 1024));
+    attr_set = true;
+  }
+  // particles that already have a heading are tracked (one shift); the rest run the theta search,
+  // which sets theta / have_init (state_particle.cpp:195-206).  Track first: it only READS have_init.
+  const size_t track_smem = (size_t)P * 32 + (size_t)P * 8 + (size_t)P * 4;
+  if (ctx->n_uninit < pt.n) {
+    k_score_track<<<ctx->sm_count * 2, 256, track_smem, ctx->stream>>>(sp);
+    count_launch(ctx);
+  }
+  if (ctx->n_uninit > 0) {
+    TDR_REQUIRE(sp.n_shifts > 0, TDR_ESTATE, "theta-search list not set (tdr_pf_set_search)");
+    size_t smem = (size_t)P * 32 + (size_t)sp.n_shifts * (SEARCH_THREADS / 32) * 8 + 256;
+    long long ctas = sp.n < (long long)ctx->sm_count * 8 ? sp.n : (long long)ctx->sm_count * 8;
+    k_score_search<SEARCH_THREADS, SEARCH_JMAX><<<(unsigned)ctas, SEARCH_THREADS, smem, ctx->stream>>>(sp, 0);
+    count_launch(ctx);
+    ctx->n_uninit = 0;
+  }
+  TDR_CUDA(cudaGetLastError());
+  return TDR_OK;
+}
+
+int score_grid(tdr_ctx* ctx, long long n, float scale, float res) {
+  ScoreParams sp;
+  if (int e = fill_params(ctx, res, &sp)) return e;
+  sp.n = n; sp.centers = ctx->grid_centers.as<float>(); sp.grid_scale = scale; sp.costs = ctx->grid_costs.as<float>();
+  sp.shifts = ctx->grid_shifts.as<int32_t>(); sp.n_shifts = ctx->grid_shifts_n; sp.thetas = nullptr;
+  sp.init_x = sp.init_y = sp.dx = sp.dy = nullptr; sp.theta = nullptr; sp.scale = nullptr; sp.have_init = nullptr; sp.weights = nullptr;
+  const int P = sp.P;
+  TDR_REQUIRE(P <= SEARCH_THREADS * SEARCH_JMAX, TDR_EUNSUPPORTED, "polar image too large");
+  TDR_CUDA(cudaFuncSetAttribute(k_score_search<SEARCH_THREADS, SEARCH_JMAX>, cudaFuncAttributeMaxDynamicSharedMemorySize, 200 * 1024));
+  size_t smem = (size_t)P * 32 + (size_t)sp.n_shifts * (SEARCH_THREADS / 32) * 8 + 256;
+  long long ctas = n < (long long)ctx->sm_count * 8 ? n : (long long)ctx->sm_count * 8;
+  k_score_search<SEARCH_THREADS, SEARCH_JMAX><<<(unsigned)ctas, SEARCH_THREADS, smem, ctx->stream>>>(sp, 1);
+  count_launch(ctx);
+  TDR_CUDA(cudaGetLastError());
+  return TDR_OK;
+}
+
+int local_polar(tdr_ctx* ctx, const float* dev_centers, int n, float scale, float res, float* dev_dists, uint8_t* dev_mask) {
+  int P = ctx->n_theta * ctx->n_r;
+  dim3 grd((P + 127) / 128, n);
+  k_local_polar<<<grd, 128, 0, ctx->stream>>>(ctx->map_px.as<MapPixel>(), ctx->rows, ctx->cols, ctx->C, ctx->resolution,
+                                              ctx->tab.as<float>(), P, dev_centers, n, scale, res, dev_dists, dev_mask);
+  count_launch(ctx);
+  TDR_CUDA(cudaGetLastError());
+  return TDR_OK;
+}
+
+int local_cart(tdr_ctx* ctx, float cx, float cy, float rot, float res, int out_rows, int out_cols, float* dev_dists,
+               uint8_t* dev_mask) {
+  int P = out_rows * out_cols;
+  k_local_cart<<<(P + 127) / 128, 128, 0, ctx->stream>>>(ctx->map_px.as<MapPixel>(), ctx->rows, ctx->cols, ctx->C,
+                                                         ctx->resolution, cx, cy, cosf(rot), sinf(rot), res, out_rows,
+                                                         out_cols, dev_dists, dev_mask);
+  count_launch(ctx);
+  TDR_CUDA(cudaGetLastError());
+  return TDR_OK;
+}
+
+}  // namespace tdr

@@ -1,0 +1,177 @@
+// tdr_ctx.cuh — internal context of libtdr_b200 (not part of the ABI).
+#pragma once
+#include <cuda_runtime.h>
+#include <stdint.h>
+#include <stdio.h>
+#include <string>
+#include <vector>
+
+#include "../../include/tdr.h"
+
+namespace tdr {
+
+void set_error(const char* fmt, ...);
+
+#define TDR_CUDA(call)                                                                       \
+  do {                                                                                       \
+    cudaError_t e__ = (call);                                                                \
+    if (e__ != cudaSuccess) {                                                                \
+      tdr::set_error("%s failed at %s:%d: %s", #call, __FILE__, __LINE__, cudaGetErrorString(e__)); \
+      return TDR_ECUDA;                                                                      \
+    }                                                                                        \
+  } while (0)
+
+#define TDR_REQUIRE(cond, code, ...)        \
+  do {                                      \
+    if (!(cond)) {                          \
+      tdr::set_error(__VA_ARGS__);          \
+      return (code);                        \
+    }                                       \
+  } while (0)
+
+// growable device buffer
+struct DevBuf {
+  void* p = nullptr;
+  size_t cap = 0;
+  int reserve(size_t bytes) {
+    if (bytes <= cap) return TDR_OK;
+    if (p) cudaFree(p);
+    p = nullptr; cap = 0;
+    cudaError_t e = cudaMalloc(&p, bytes);
+    if (e != cudaSuccess) { set_error("cudaMalloc(%zu) failed: %s", bytes, cudaGetErrorString(e)); return TDR_ECUDA; }
+    cap = bytes;
+    return TDR_OK;
+  }
+  void release() { if (p) cudaFree(p); p = nullptr; cap = 0; }
+  template <typename T> T* as() const { return reinterpret_cast<T*>(p); }
+};
+
+// pinned host staging buffer (H2D / D2H without a pageable bounce)
+struct PinBuf {
+  void* p = nullptr;
+  size_t cap = 0;
+  int reserve(size_t bytes) {
+    if (bytes <= cap) return TDR_OK;
+    if (p) cudaFreeHost(p);
+    p = nullptr; cap = 0;
+    cudaError_t e = cudaMallocHost(&p, bytes);
+    if (e != cudaSuccess) { set_error("cudaMallocHost(%zu) failed: %s", bytes, cudaGetErrorString(e)); return TDR_ECUDA; }
+    cap = bytes;
+    return TDR_OK;
+  }
+  void release() { if (p) cudaFreeHost(p); p = nullptr; cap = 0; }
+};
+
+// Device map pixel: 8 fp32 slots (32 B = one sector): slots [0, C) hold the class distance
+// fields exactly as the reference's class_maps_ hold them after computeDists, slot 7 holds
+// known = 1 - class_mask_ (1.0f / 0.0f).  Row-major over (row = y, col = x), x fastest.
+struct MapPixel { float v[8]; };
+
+struct Particles {   // SoA mirror of State (+ last_dist_, weight_)
+  DevBuf init_x, init_y, dx, dy, theta, scale, have_init /*u8*/, last_dist;
+  int64_t n = 0;
+  int reserve(int64_t cap);
+  void release();
+};
+
+}  // namespace tdr
+
+struct tdr_ctx {
+  int device = 0;
+  int sm_count = 148;
+  cudaStream_t stream = nullptr;
+  int64_t launches = 0;
+
+  // ---- map
+  int rows = 0, cols = 0, C = 0;
+  float resolution = 1.f;
+  bool have_map = false;
+  tdr::DevBuf map_px;        // rows*cols MapPixel
+  tdr::DevBuf seedbits;      // rows*cols uint8: bit c set where class c is present (binary layer == 0)
+  bool have_seeds = false;
+  tdr::DevBuf edt_g;         // C planes rows*cols uint8 vertical distances (scratch)
+  tdr::DevBuf scratch;       // generic scratch (layer staging, partial histograms, ...)
+  tdr::DevBuf scratch2;
+
+  // ---- polar table
+  int n_theta = 0, n_r = 0;
+  tdr::DevBuf tab;           // 2*P floats
+  bool have_tab = false;
+
+  // ---- scan
+  tdr::DevBuf pts;           // raw AoS copy
+  int pts_stride = 0, pts_ioff = 0;
+  int64_t n_pts = 0;
+  tdr::DevBuf lut;           // int32[n_lut]
+  int n_lut = 0, lut_classes = 0;
+  tdr::DevBuf scan_img;      // C x P floats (col-major n_theta x n_r per class)
+  int scan_theta = 0, scan_r = 0, scan_C = 0;
+  bool have_scan = false;
+  tdr::DevBuf scan_pack;     // P x 8 floats: per lattice cell (w_c*0.01*count_c for c<C, ..., slot7 = sum_c count_c)
+  tdr::DevBuf hist;          // int32 bin counts
+
+  // ---- filter
+  tdr_filter_params fp{};
+  bool have_params = false;
+  std::vector<float> search_thetas;
+  std::vector<int32_t> search_shifts;
+  tdr::DevBuf d_search_thetas, d_search_shifts;
+  tdr::Particles part[2];    // ping-pong (particles_ / new_particles_, particle_filter.cpp:187)
+  int cur = 0;
+  int64_t n_uninit = 0;      // particles still without a heading (have_init == false)
+  tdr::DevBuf d_cw;          // class weights (16 floats)
+  int argmax_buf = 0;        // particle buffer the last arg-max indexes into (max_likelihood_particle_)
+  tdr::DevBuf weights;       // raw -> normalised in place
+  int64_t n_weights = 0;
+  const float* ld_override = nullptr;  // device last_dist aligned with an all-gathered weight vector (multi-GPU)
+  tdr::DevBuf prefix;        // running max of the order-exact prefix
+  tdr::DevBuf idx;           // resampled indices
+  tdr::DevBuf scal;          // small device scalars (sums, stats, argmax, pose)
+  tdr::DevBuf pose_tmp;      // 4 x n floats (ml-state columns)
+  tdr::PinBuf pin;           // pinned staging
+  int64_t argmax = 0;
+  bool have_argmax = false;
+
+  // ---- grid (cfg4)
+  tdr::DevBuf grid_centers, grid_costs, grid_shifts;
+  int64_t grid_n = 0;
+  int grid_shifts_n = 0;
+};
+
+namespace tdr {
+// scalar slots in ctx->scal (floats unless noted)
+enum {
+  SC_SUM = 0, SC_NVALID, SC_MEAN, SC_BS, SC_NUNDER, SC_FALLBACK,     // stats (6 floats, ABI order)
+  SC_S1, SC_S2, SC_REP, SC_ARGMAX /*int*/, SC_ARGVAL,
+  SC_CHAIN = 16,            // 8 chain totals
+  SC_DBL = 32,              // doubles from here (8-byte aligned): sumsq, count_valid, count_under ...
+  SC_POSE = 64,             // pose scalars
+  SC_TOTAL = 256
+};
+
+
+inline void count_launch(tdr_ctx* c, int k = 1) { c->launches += k; }
+
+// map_build.cu
+int map_set_class_image(tdr_ctx*, const uint8_t*, int, int, int, const int32_t*, int, int, float);
+int map_set_binary_layers(tdr_ctx*, const float*, int, int, int, float);
+int map_set_dist_layers(tdr_ctx*, const float*, const uint8_t*, int, int, int, float);
+int map_get_layers(tdr_ctx*, float*, uint8_t*);
+int map_get_geo_layers(tdr_ctx*, float*);
+// scan_render.cu
+int scan_render(tdr_ctx*, bool polar, float res, float ang_res, int d0, int d1, float* dev_img_out);
+int scan_pack(tdr_ctx*);
+// score.cu
+int score_particles(tdr_ctx*, float res);
+int score_grid(tdr_ctx*, long long n, float scale, float res);
+int local_polar(tdr_ctx*, const float* dev_centers, int n, float scale, float res, float* dev_dists, uint8_t* dev_mask);
+int local_cart(tdr_ctx*, float cx, float cy, float rot, float res, int out_rows, int out_cols, float* dev_dists, uint8_t* dev_mask);
+// weights.cu
+int normalize(tdr_ctx*);
+int build_prefix(tdr_ctx*);
+int resample(tdr_ctx*, float u, long long M, long long i0, long long i1, bool gather);
+int exact_sums(tdr_ctx*, const float* const* cols, long long n, int ncols, float* totals_dev);
+// pose.cu
+int pose(tdr_ctx*, float* mean, float* cov_mean, float* ml, float* cov_ml);
+int grid_best(tdr_ctx*, float* best_cost, long long* best_index);
+}

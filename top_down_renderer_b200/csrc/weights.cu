@@ -1,0 +1,418 @@
+// weights.cu — a11/a12: weight normalisation and systematic resampling.
+//
+// Reference: ParticleFilter::update (src/particle_filter.cpp:107-147 weights, :172-187 resample).
+//
+// The reference's sums are SEQUENTIAL fp32 accumulations and its resampler compares samples with
+// a sequential fp32 prefix, so bit-exact indices need the same prefix VALUES.  k_exact_seq
+// reproduces a sequential fp32 accumulation exactly, in parallel, with the binade algebra of
+// tdr_math.cuh (IncPair scan), restarting at the ~20-30 binade crossings of a run.
+#include "tdr_ctx.cuh"
+#include "tdr_math.cuh"
+
+namespace tdr {
+
+// One job = one sequential accumulation chain  s_j = RN(s_{j-1} + x[start + j*stride]), j < count.
+struct SeqJob {
+  const float* x; long long start, stride, count;
+  float* runmax_out;   // optional: max_{k<=j} s_k per element (contiguous, length count)
+  float* total_out;    // final s
+  int skip_nan;        // NaN elements are skipped (== add +0), particle_filter.cpp:112
+};
+#define TDR_MAX_JOBS 8
+struct SeqJobs { SeqJob j[TDR_MAX_JOBS]; };
+
+static const int SEQ_THREADS = 1024;
+static const int SEQ_ITEMS = 4;
+static const int SEQ_CHUNK = SEQ_THREADS * SEQ_ITEMS;
+
+__device__ __forceinline__ IncPair shfl_up_pair(IncPair v, int d) {
+  IncPair r;
+  r.a = __shfl_up_sync(0xffffffffu, v.a, d);
+  r.b = __shfl_up_sync(0xffffffffu, v.b, d);
+  return r;
+}
+
+// grid.x = number of jobs; one CTA walks its chain chunk by chunk.
+__global__ void __launch_bounds__(SEQ_THREADS) k_exact_seq(SeqJobs jobs) {
+  const SeqJob job = jobs.j[blockIdx.x];
+  __shared__ IncPair s_warp[32];
+  __shared__ int s_cross;          // first crossing position inside the chunk (relative), or chunk_len
+  __shared__ uint32_t s_mprev;     // m of the element just before the crossing
+  __shared__ float s_S, s_rmax;    // chain state
+  __shared__ long long s_pos;
+  __shared__ int s_mode;           // 0 = binade scan, 1 = plain sequential tail (irregular state)
+  const int tid = threadIdx.x, lane = tid & 31, warp = tid >> 5;
+  if (tid == 0) { s_S = 0.f; s_rmax = -INFINITY; s_pos = 0; s_mode = 0; }
+  __syncthreads();
+
+  while (true) {
+    const long long pos = s_pos;
+    if (pos >= job.count) break;
+    if (s_mode == 1) {
+      // irregular accumulator (negative / inf / NaN): finish with real adds, one thread.
+      if (tid == 0) {
+        float S = s_S, rm = s_rmax;
+        for (long long j = pos; j < job.count; j++) {
+          float w = job.x[job.start + j * job.stride];
+          if (job.skip_nan && w != w) w = 0.f;
+          S = TDR_FADD(S, w);
+          if (S > rm) rm = S;
+          if (job.runmax_out) job.runmax_out[j] = rm;
+        }
+        s_S = S; s_rmax = rm; s_pos = job.count;
+      }
+      __syncthreads();
+      continue;
+    }
+    const float S_in = s_S;
+    const float rmax_in = s_rmax;
+    const int E = binade_of(S_in);
+    const uint32_t m_in = mant_of(S_in);
+    const uint32_t limit = binade_limit(E);
+    long long remaining = job.count - pos;
+    const int chunk_len = remaining < SEQ_CHUNK ? (int)remaining : SEQ_CHUNK;
+    if (tid == 0) s_cross = chunk_len;
+
+    // ---- per-thread pairs (blocked: thread owns SEQ_ITEMS consecutive elements)
+    IncPair loc[SEQ_ITEMS];
+    float wv[SEQ_ITEMS];
+    IncPair agg; agg.a = agg.b = 0;
+#pragma unroll
+    for (int k = 0; k < SEQ_ITEMS; k++) {
+      int j = tid * SEQ_ITEMS + k;
+      float w = 0.f;
+      if (j < chunk_len) {
+        w = job.x[job.start + (pos + j) * job.stride];
+        if (job.skip_nan && w != w) w = 0.f;
+      }
+      wv[k] = w;
+      bool irr;
+      IncPair pr = inc_pair(w, E, &irr);
+      agg = pair_compose(agg, pr);
+      loc[k] = agg;                       // inclusive within the thread
+    }
+    // ---- block exclusive scan of thread aggregates (pair_compose is associative, not commutative)
+    IncPair incl = agg;
+#pragma unroll
+    for (int d = 1; d < 32; d <<= 1) {
+      IncPair o = shfl_up_pair(incl, d);
+      if (lane >= d) incl = pair_compose(o, incl);
+    }
+    if (lane == 31) s_warp[warp] = incl;
+    __syncthreads();
+    if (warp == 0) {
+      IncPair v = s_warp[lane];
+#pragma unroll
+      for (int d = 1; d < 32; d <<= 1) {
+        IncPair o = shfl_up_pair(v, d);
+        if (lane >= d) v = pair_compose(o, v);
+      }
+      s_warp[lane] = v;                   // inclusive over warps
+    }
+    __syncthreads();
+    IncPair excl_thread = shfl_up_pair(incl, 1);
+    if (lane == 0) { excl_thread.a = 0; excl_thread.b = 0; }
+    if (warp > 0) excl_thread = pair_compose(s_warp[warp - 1], excl_thread);
+
+    // ---- element values and the first crossing
+    const bool odd = (m_in & 1u) != 0;
+    uint32_t mv[SEQ_ITEMS];
+    int my_cross = chunk_len;
+#pragma unroll
+    for (int k = 0; k < SEQ_ITEMS; k++) {
+      int j = tid * SEQ_ITEMS + k;
+      IncPair t = pair_compose(excl_thread, loc[k]);
+      uint32_t inc = odd ? t.b : t.a;
+      uint32_t m = m_in + inc;            // <= 2^24 + 2^30, no overflow
+      mv[k] = m;
+      if (j < chunk_len && m >= limit && j < my_cross) my_cross = j;
+    }
+    if (my_cross < chunk_len) atomicMin(&s_cross, my_cross);
+    __syncthreads();
+    const int cross = s_cross;
+    // ---- emit the valid part [0, cross)
+#pragma unroll
+    for (int k = 0; k < SEQ_ITEMS; k++) {
+      int j = tid * SEQ_ITEMS + k;
+      if (j < cross) {
+        if (job.runmax_out) {
+          float S = from_binade(E, mv[k]);
+          job.runmax_out[pos + j] = S > rmax_in ? S : rmax_in;   // non-decreasing inside a segment
+        }
+        if (j == cross - 1) s_mprev = mv[k];
+      }
+    }
+    __syncthreads();
+    // ---- advance the chain state (one thread; the crossing add is a real fp32 add)
+    if (tid == 0) {
+      float S = (cross > 0) ? from_binade(E, s_mprev) : S_in;
+      float rm = rmax_in;
+      if (cross > 0 && S > rm) rm = S;
+      long long np = pos + cross;
+      if (cross < chunk_len) {
+        float w = job.x[job.start + (pos + cross) * job.stride];
+        if (job.skip_nan && w != w) w = 0.f;
+        S = TDR_FADD(S, w);
+        if (S > rm) rm = S;
+        if (job.runmax_out) job.runmax_out[pos + cross] = rm;
+        np += 1;
+        if (!(S >= 0.f) || S == INFINITY) s_mode = 1;   // negative / NaN / inf accumulator
+      }
+      s_S = S; s_rmax = rm; s_pos = np;
+    }
+    __syncthreads();
+  }
+  if (tid == 0 && job.total_out) *job.total_out = s_S;
+}
+
+// ------------------------------------------------------------------------------------------------
+// count of non-NaN weights
+__global__ void k_count_valid(const float* __restrict__ w, long long n, unsigned long long* __restrict__ out) {
+  unsigned long long c = 0;
+  for (long long i = (long long)blockIdx.x * blockDim.x + threadIdx.x; i < n; i += (long long)gridDim.x * blockDim.x)
+    c += (w[i] == w[i]) ? 1ull : 0ull;
+  for (int o = 16; o > 0; o >>= 1) c += __shfl_xor_sync(0xffffffffu, c, o);
+  if ((threadIdx.x & 31) == 0 && c) atomicAdd(out, c);
+}
+
+__global__ void k_mean(float* scal, const unsigned long long* nvalid) {
+  // mean = sum / num_valid   (int -> float conversion of num_valid, particle_filter.cpp:117)
+  scal[SC_NVALID] = (float)(long long)*nvalid;
+  scal[SC_MEAN] = TDR_FDIV(scal[SC_SUM], (float)(int)*nvalid);
+}
+
+// lower-half squared deviations (particle_filter.cpp:120-125).  The reference accumulates
+// (float)((double)acc + (double)(w-mean)^2) sequentially; here the squares are summed in double
+// (integer-free but order-insensitive to ~1e-16) and rounded once — see DESIGN.md "normalise".
+__global__ void k_under(const float* __restrict__ w, long long n, const float* __restrict__ scal, double* sumsq,
+                        unsigned long long* nunder) {
+  const float mean = scal[SC_MEAN];
+  double s = 0.0; unsigned long long c = 0;
+  for (long long i = (long long)blockIdx.x * blockDim.x + threadIdx.x; i < n; i += (long long)gridDim.x * blockDim.x) {
+    float v = w[i];
+    if (v == v && v < mean) { double d = (double)TDR_FSUB(v, mean); s += d * d; c++; }
+  }
+  for (int o = 16; o > 0; o >>= 1) { s += __shfl_xor_sync(0xffffffffu, s, o); c += __shfl_xor_sync(0xffffffffu, c, o); }
+  if ((threadIdx.x & 31) == 0 && c) { atomicAdd(sumsq, s); atomicAdd(nunder, c); }
+}
+
+__global__ void k_stats(float* scal, const double* sumsq, const unsigned long long* nunder) {
+  int nu = (int)*nunder;
+  float bs = (float)*sumsq;
+  bs = TDR_FSQRT(TDR_FDIV(bs, (float)nu));                       // :126
+  scal[SC_BS] = bs; scal[SC_NUNDER] = (float)nu;
+  bool fallback = (scal[SC_SUM] == 0.f) || (nu < 1);             // :129
+  scal[SC_FALLBACK] = fallback ? 1.f : 0.f;
+  scal[SC_REP] = TDR_FSUB(scal[SC_MEAN], bs);                    // :133
+}
+
+__global__ void k_fill_nan(float* __restrict__ w, long long n, const float* __restrict__ scal) {
+  const bool fallback = scal[SC_FALLBACK] != 0.f;
+  const float rep = scal[SC_REP];
+  for (long long i = (long long)blockIdx.x * blockDim.x + threadIdx.x; i < n; i += (long long)gridDim.x * blockDim.x) {
+    float v = w[i];
+    if (fallback) w[i] = 1.f;               // :130
+    else if (v != v) w[i] = rep;            // :133
+  }
+}
+
+// Eigen's vectorised weights_.sum() (SSE2 packets, 2x unrolled; Eigen/src/Core/Redux.h): combine the 8
+// exact chain totals in Eigen's order.  Small n is summed directly.
+__global__ void k_eigen_sum_finish(const float* __restrict__ x, long long n, const float* __restrict__ chain,
+                                   float* __restrict__ out) {
+  const long long ps = 4;
+  const long long aS2 = (n / (2 * ps)) * (2 * ps), aS = (n / ps) * ps;
+  float res;
+  if (n == 0) { *out = 0.f; return; }
+  if (aS == 0) { res = x[0]; for (long long i = 1; i < n; i++) res = TDR_FADD(res, x[i]); *out = res; return; }
+  float p0[4], p1[4];
+  if (aS2 >= 2 * ps) {
+    for (int k = 0; k < 4; k++) { p0[k] = chain[k]; p1[k] = chain[4 + k]; }
+    for (int k = 0; k < 4; k++) p0[k] = TDR_FADD(p0[k], p1[k]);
+    if (aS > aS2) for (int k = 0; k < 4; k++) p0[k] = TDR_FADD(p0[k], x[aS2 + k]);
+  } else {
+    for (int k = 0; k < 4; k++) p0[k] = x[k];      // exactly one packet (4 <= n < 8)
+  }
+  res = TDR_FADD(TDR_FADD(p0[0], p0[2]), TDR_FADD(p0[1], p0[3]));
+  for (long long i = aS; i < n; i++) res = TDR_FADD(res, x[i]);
+  *out = res;
+}
+
+// w /= s1 ; w = d*w + (1-d)/N   (:135-141)
+__global__ void k_regularize(float* __restrict__ w, const float* __restrict__ last_dist, long long n,
+                             const float* __restrict__ scal) {
+  const float s1 = scal[SC_S1];
+  const float fn = (float)(unsigned long long)n;
+  for (long long i = (long long)blockIdx.x * blockDim.x + threadIdx.x; i < n; i += (long long)gridDim.x * blockDim.x) {
+    float v = TDR_FDIV(w[i], s1);
+    float d = TDR_FMUL(last_dist[i], 5.0f);
+    d = (1.0f < d) ? 1.0f : d;               // std::min<float>(a, 1) == (1 < a) ? 1 : a  (a NaN stays NaN)
+    w[i] = TDR_FADD(TDR_FMUL(d, v), TDR_FDIV(TDR_FSUB(1.0f, d), fn));
+  }
+}
+
+// w /= s2 and first arg-max (:142-147)
+__global__ void k_final_div_argmax(float* __restrict__ w, long long n, const float* __restrict__ scal,
+                                   unsigned long long* __restrict__ best) {
+  const float s2 = scal[SC_S2];
+  unsigned long long loc = 0ull;   // key: (ordered float bits << 32) | (0xffffffff - index): max key = max value, then smallest index
+  for (long long i = (long long)blockIdx.x * blockDim.x + threadIdx.x; i < n; i += (long long)gridDim.x * blockDim.x) {
+    float v = TDR_FDIV(w[i], s2);
+    w[i] = v;
+    if (v == v) {
+      uint32_t u = __float_as_uint(v);
+      u = (u & 0x80000000u) ? ~u : (u | 0x80000000u);
+      unsigned long long key = ((unsigned long long)u << 32) | (unsigned long long)(0xffffffffu - (uint32_t)i);
+      if (key > loc) loc = key;
+    }
+  }
+  for (int o = 16; o > 0; o >>= 1) { unsigned long long t = __shfl_xor_sync(0xffffffffu, loc, o); if (t > loc) loc = t; }
+  if ((threadIdx.x & 31) == 0 && loc) atomicMax(best, loc);
+}
+
+__global__ void k_argmax_store(const unsigned long long* best, float* scal) {
+  unsigned long long k = *best;
+  int idx = k ? (int)(0xffffffffu - (uint32_t)(k & 0xffffffffull)) : 0;
+  reinterpret_cast<int*>(scal)[SC_ARGMAX] = idx;
+}
+
+// ------------------------------------------------------------------------------------------------
+// resample (:172-185): idx[i] = first j with runmax[j] > sample_i, else n-1;  new state i = old state idx[i]
+struct GatherPtrs {
+  const float *ix, *iy, *dx, *dy, *th, *sc, *ld; const uint8_t* hi;
+  float *oix, *oiy, *odx, *ody, *oth, *osc, *old; uint8_t* ohi;
+};
+
+__global__ void k_resample(const float* __restrict__ runmax, long long n, float u, long long M, long long i0,
+                           long long i1, int32_t* __restrict__ idx, GatherPtrs g, long long src_n) {
+  const float fM = (float)(int)M;
+  for (long long i = i0 + (long long)blockIdx.x * blockDim.x + threadIdx.x; i < i1; i += (long long)gridDim.x * blockDim.x) {
+    float sample = TDR_FDIV(TDR_FADD((float)(int)i, u), fM);    // (static_cast<float>(i)+shift)/num_particles_
+    long long lo = 0, hi = n - 1;                               // first j in [0, n-1] with runmax[j] > sample, default n-1
+    while (lo < hi) {
+      long long mid = (lo + hi) >> 1;
+      if (runmax[mid] > sample) hi = mid; else lo = mid + 1;
+    }
+    idx[i - i0] = (int32_t)lo;
+    if (g.ix && lo < src_n) {
+      long long o = i - i0;
+      g.oix[o] = g.ix[lo]; g.oiy[o] = g.iy[lo]; g.odx[o] = g.dx[lo]; g.ody[o] = g.dy[lo];
+      g.oth[o] = g.th[lo]; g.osc[o] = g.sc[lo]; g.ohi[o] = g.hi[lo];
+      g.old[o] = g.ld[lo];
+    }
+  }
+}
+
+// ------------------------------------------------------------------------------------------------
+static int launch_seq(tdr_ctx* ctx, const SeqJobs& jobs, int njobs) {
+  k_exact_seq<<<njobs, SEQ_THREADS, 0, ctx->stream>>>(jobs);
+  count_launch(ctx);
+  TDR_CUDA(cudaGetLastError());
+  return TDR_OK;
+}
+
+// Eigen linear-vectorised sum of x[0..n) into scal[slot]
+static int eigen_sum(tdr_ctx* ctx, const float* x, long long n, int slot) {
+  float* scal = ctx->scal.as<float>();
+  const long long aS2 = (n / 8) * 8;
+  if (aS2 >= 8) {
+    SeqJobs jobs;
+    for (int k = 0; k < 8; k++) {
+      jobs.j[k].x = x; jobs.j[k].start = k; jobs.j[k].stride = 8; jobs.j[k].count = aS2 / 8;
+      jobs.j[k].runmax_out = nullptr; jobs.j[k].total_out = scal + SC_CHAIN + k; jobs.j[k].skip_nan = 0;
+    }
+    if (int e = launch_seq(ctx, jobs, 8)) return e;
+  }
+  k_eigen_sum_finish<<<1, 1, 0, ctx->stream>>>(x, n, scal + SC_CHAIN, scal + slot);
+  count_launch(ctx);
+  TDR_CUDA(cudaGetLastError());
+  return TDR_OK;
+}
+
+int normalize(tdr_ctx* ctx) {
+  const long long n = ctx->n_weights;
+  TDR_REQUIRE(n > 0, TDR_ESTATE, "no weights");
+  TDR_REQUIRE(n < (1ll << 31), TDR_EUNSUPPORTED, "too many weights");
+  float* w = ctx->weights.as<float>();
+  const float* ld = ctx->ld_override ? ctx->ld_override : ctx->part[ctx->cur].last_dist.as<float>();
+  if (int e = ctx->scal.reserve(SC_TOTAL * 4)) return e;
+  float* scal = ctx->scal.as<float>();
+  double* dbl = reinterpret_cast<double*>(scal + SC_DBL);
+  unsigned long long* u64 = reinterpret_cast<unsigned long long*>(dbl);
+  TDR_CUDA(cudaMemsetAsync(dbl, 0, 8 * 8, ctx->stream));   // [0]=sumsq [1]=nvalid [2]=nunder [3]=argmax key
+  const int blocks = (int)((n + 1023) / 1024 < ctx->sm_count * 4 ? (n + 1023) / 1024 : ctx->sm_count * 4);
+  // sum / num_valid (:108-116): sequential fp32 over non-NaN weights
+  SeqJobs jobs;
+  jobs.j[0].x = w; jobs.j[0].start = 0; jobs.j[0].stride = 1; jobs.j[0].count = n; jobs.j[0].runmax_out = nullptr;
+  jobs.j[0].total_out = scal + SC_SUM; jobs.j[0].skip_nan = 1;
+  if (int e = launch_seq(ctx, jobs, 1)) return e;
+  k_count_valid<<<blocks, 256, 0, ctx->stream>>>(w, n, u64 + 1);
+  k_mean<<<1, 1, 0, ctx->stream>>>(scal, u64 + 1);
+  k_under<<<blocks, 256, 0, ctx->stream>>>(w, n, scal, dbl, u64 + 2);
+  k_stats<<<1, 1, 0, ctx->stream>>>(scal, dbl, u64 + 2);
+  k_fill_nan<<<blocks, 256, 0, ctx->stream>>>(w, n, scal);
+  count_launch(ctx, 5);
+  if (int e = eigen_sum(ctx, w, n, SC_S1)) return e;
+  k_regularize<<<blocks, 256, 0, ctx->stream>>>(w, ld, n, scal);
+  count_launch(ctx);
+  if (int e = eigen_sum(ctx, w, n, SC_S2)) return e;
+  k_final_div_argmax<<<blocks, 256, 0, ctx->stream>>>(w, n, scal, u64 + 3);
+  k_argmax_store<<<1, 1, 0, ctx->stream>>>(u64 + 3, scal);
+  count_launch(ctx, 2);
+  TDR_CUDA(cudaGetLastError());
+  ctx->have_argmax = true;
+  return TDR_OK;
+}
+
+// order-exact sequential fp32 totals of up to 8 columns (pose sums, particle_filter.cpp:195-197)
+int exact_sums(tdr_ctx* ctx, const float* const* cols, long long n, int ncols, float* totals_dev) {
+  TDR_REQUIRE(ncols >= 1 && ncols <= TDR_MAX_JOBS, TDR_EINVAL, "bad column count");
+  SeqJobs jobs;
+  for (int k = 0; k < ncols; k++) {
+    jobs.j[k].x = cols[k]; jobs.j[k].start = 0; jobs.j[k].stride = 1; jobs.j[k].count = n;
+    jobs.j[k].runmax_out = nullptr; jobs.j[k].total_out = totals_dev + k; jobs.j[k].skip_nan = 0;
+  }
+  return launch_seq(ctx, jobs, ncols);
+}
+
+// prefix (running max of the exact sequential prefix) over the resident weights
+int build_prefix(tdr_ctx* ctx) {
+  const long long n = ctx->n_weights;
+  TDR_REQUIRE(n > 0, TDR_ESTATE, "no weights");
+  if (int e = ctx->prefix.reserve((size_t)n * 4)) return e;
+  if (int e = ctx->scal.reserve(SC_TOTAL * 4)) return e;
+  SeqJobs jobs;
+  jobs.j[0].x = ctx->weights.as<float>(); jobs.j[0].start = 0; jobs.j[0].stride = 1; jobs.j[0].count = n;
+  jobs.j[0].runmax_out = ctx->prefix.as<float>(); jobs.j[0].total_out = ctx->scal.as<float>() + SC_CHAIN + 8;
+  jobs.j[0].skip_nan = 0;
+  return launch_seq(ctx, jobs, 1);
+}
+
+// outputs [i0, i1) of the M systematic samples; gathers states from the current particle set into the
+// other buffer when `gather` (single-GPU: i0 = 0, i1 = M)
+int resample(tdr_ctx* ctx, float u, long long M, long long i0, long long i1, bool gather) {
+  const long long n = ctx->n_weights;
+  TDR_REQUIRE(M > 0 && M < (1ll << 31) && i0 >= 0 && i1 <= M && i0 < i1, TDR_EINVAL, "bad resample range");
+  if (int e = build_prefix(ctx)) return e;
+  const long long cnt = i1 - i0;
+  if (int e = ctx->idx.reserve((size_t)cnt * 4)) return e;
+  GatherPtrs g; memset(&g, 0, sizeof(g));
+  tdr::Particles& src = ctx->part[ctx->cur];
+  tdr::Particles& dst = ctx->part[ctx->cur ^ 1];
+  if (gather) {
+    TDR_REQUIRE(src.n > 0, TDR_ESTATE, "no particles to gather");
+    if (int e = dst.reserve(cnt)) return e;
+    g.ix = src.init_x.as<float>(); g.iy = src.init_y.as<float>(); g.dx = src.dx.as<float>(); g.dy = src.dy.as<float>();
+    g.th = src.theta.as<float>(); g.sc = src.scale.as<float>(); g.ld = src.last_dist.as<float>(); g.hi = src.have_init.as<uint8_t>();
+    g.oix = dst.init_x.as<float>(); g.oiy = dst.init_y.as<float>(); g.odx = dst.dx.as<float>(); g.ody = dst.dy.as<float>();
+    g.oth = dst.theta.as<float>(); g.osc = dst.scale.as<float>(); g.old = dst.last_dist.as<float>(); g.ohi = dst.have_init.as<uint8_t>();
+  }
+  int blocks = (int)((cnt + 255) / 256 < ctx->sm_count * 8 ? (cnt + 255) / 256 : ctx->sm_count * 8);
+  k_resample<<<blocks, 256, 0, ctx->stream>>>(ctx->prefix.as<float>(), n, u, M, i0, i1, ctx->idx.as<int32_t>(), g, src.n);
+  count_launch(ctx);
+  TDR_CUDA(cudaGetLastError());
+  if (gather) { dst.n = cnt; ctx->cur ^= 1; }
+  return TDR_OK;
+}
+
+}  // namespace tdr
