@@ -130,7 +130,7 @@ class Context:
         """pts: (n, k) float32 AoS (PointXYZI: k = 8).  Asynchronous: keep `pts` alive until sync()."""
         assert pts.dtype == np.float32 and pts.flags.c_contiguous
         self._pts_keepalive = pts
-        check(self._lib.tdr_scan_set_points(self._h, C.c_void_p(pts.ctypes.data), C.c_int(pts.strides[0]),
+        check(self._lib.tdr_scan_set_points(self._h, C.c_void_p(pts.ctypes.data), C.c_int(pts.shape[1] * 4),
                                             C.c_int(intensity_off), C.c_int64(pts.shape[0])))
 
     def scan_set_points_ptr(self, ptr, stride, intensity_off, n):
