@@ -1,0 +1,382 @@
+#!/usr/bin/env python
+"""bench.py — the localization hot path (rasterise + score + normalise + resample) on N B200s.
+
+    python bench.py [--gpus N] [--steps K] [--warmup W] [--impl reference] [--workload global|tracking|grid]
+
+One "step" = one whole ParticleFilter update on one synthetic scan (TopDownRender::takeStep minus ROS,
+top_down_render.cpp:505-572): polar rasterise of a 65 536-point semantic scan, score of every particle
+(40-shift polar theta search while the heading is unknown), weight normalisation, systematic resample.
+Metric (BASELINE.json): particle scores/sec — one score = one getCostForRot evaluation, i.e. one
+(x, y, theta) hypothesis (state_particle.cpp:112-155).
+
+Default workload = BASELINE cfg3 "global localization": 1M particles per GPU over a 4000 x 4000 px map
+(4 km^2 at 0.5 m/px), 6 classes, heading unknown.  N > 1: particles are sharded (weak scaling, 1M per
+GPU), the map / scan are replicated, and ONE all-gather of (weights + states) per step over NCCL feeds a
+normalise + order-exact prefix done redundantly on every rank (bit-exact indices independent of N).
+
+Rank 0 prints ONE JSON line (see the driver contract).  `--impl reference` times the CPU restatement of
+the reference (oracle/, all host threads) on bounded samples of the same workload instead.
+"""
+from __future__ import annotations
+
+import argparse
+import json
+import math
+import os
+import subprocess
+import sys
+import threading
+import time
+
+import numpy as np
+
+ROOT = os.path.dirname(os.path.abspath(__file__))
+if ROOT not in sys.path:
+    sys.path.insert(0, ROOT)
+
+N_THETA, N_R = 100, 25
+P = N_THETA * N_R
+ANG_RES = np.float32(2 * math.pi / 100)
+SEED = 1234
+
+WORKLOADS = {
+    # name: (map side px, classes, particles per GPU, res m/bin, shifts per particle, description)
+    "global": dict(side=4000, C=6, n=1_000_000, res=4.0, shifts=40,
+                   desc="cfg3 global localization: 1M particles/GPU x 40-shift polar theta search, 4000x4000 px map "
+                        "(4 km^2 @0.5 m/px), 6 classes, 65536-pt scan; rasterise+score+normalise+resample"),
+    "tracking": dict(side=2000, C=6, n=10_000, res=0.5, shifts=1,
+                     desc="cfg2 tracking: 10k particles, 2000x2000 px map, 6 classes, 65536-pt scan; "
+                          "rasterise+score+normalise+resample"),
+}
+
+
+def peaks():
+    try:
+        with open(os.path.join(ROOT, "MEASURED_PEAKS.json")) as f:
+            return float(json.load(f)["hbm_gbs"]), "measured (MEASURED_PEAKS.json hbm_gbs)"
+    except Exception:
+        return 6650.0, "fallback (B200_PROFILING.md)"
+
+
+def b_score(C):
+    """algorithmic bytes per scored particle, SURVEY.md section 8d: P*(4C+1) + 28 B state + 4 B weight"""
+    return P * (4 * C + 1) + 32
+
+
+# ------------------------------------------------------------------------------------------------
+# synthetic world
+# ------------------------------------------------------------------------------------------------
+def make_inputs(wl, rank=0):
+    from top_down_renderer_b200 import synth
+    side, C, n = wl["side"], wl["C"], wl["n"]
+    cm = synth.make_class_map(side, side, C, seed=SEED)
+    img, lut = synth.to_cv_image(cm), synth.identity_lut(C)
+    pose, heading = synth.default_pose(cm, seed=SEED)
+    pts = synth.make_scan(cm, pose, heading, seed=SEED)
+    if wl["shifts"] == 1:
+        st, ld = synth.particles_tracking(n, pose, heading, seed=SEED + 101 * rank)
+    else:
+        st, ld = synth.particles_global(n, cm, seed=SEED + 101 * rank)
+    return dict(cm=cm, img=img, lut=lut, pose=pose, heading=heading, pts=pts, st=st, ld=ld)
+
+
+# ------------------------------------------------------------------------------------------------
+# clocks
+# ------------------------------------------------------------------------------------------------
+class ClockSampler:
+    Q = ("clocks.sm,clocks.max.sm,clocks_event_reasons.hw_slowdown,clocks_event_reasons.hw_thermal_slowdown,"
+         "clocks_event_reasons.sw_thermal_slowdown,clocks_event_reasons.sw_power_cap")
+
+    def __init__(self, index):
+        self.index, self.proc, self.lines = index, None, []
+
+    def start(self):
+        try:
+            self.proc = subprocess.Popen(["nvidia-smi", f"--query-gpu={self.Q}", "--format=csv,noheader,nounits",
+                                          "-i", str(self.index), "-lms", "100"], stdout=subprocess.PIPE,
+                                         stderr=subprocess.DEVNULL, text=True)
+            self.t = threading.Thread(target=self._read, daemon=True)
+            self.t.start()
+        except Exception:
+            self.proc = None
+
+    def _read(self):
+        for line in self.proc.stdout:
+            self.lines.append(line.strip())
+
+    def stop(self):
+        if not self.proc:
+            return {"sm_mhz": None, "sm_max_mhz": None, "reasons": ["nvidia-smi unavailable"]}
+        self.proc.terminate()
+        try:
+            self.proc.wait(timeout=5)
+        except Exception:
+            self.proc.kill()
+        sm, mx, reasons = [], [], set()
+        names = ["hw_slowdown", "hw_thermal_slowdown", "sw_thermal_slowdown", "sw_power_cap"]
+        for ln in self.lines:
+            f = [x.strip() for x in ln.split(",")]
+            if len(f) < 6:
+                continue
+            try:
+                sm.append(float(f[0])); mx.append(float(f[1]))
+            except ValueError:
+                continue
+            for k, nm in enumerate(names):
+                if f[2 + k].lower().startswith("active"):
+                    reasons.add(nm)
+        return {"sm_mhz": float(np.median(sm)) if sm else None, "sm_max_mhz": max(mx) if mx else None,
+                "reasons": sorted(reasons), "samples": len(sm)}
+
+
+# ------------------------------------------------------------------------------------------------
+# CPU arm: the oracle restatement of the reference (cpu_baseline / --impl reference)
+# ------------------------------------------------------------------------------------------------
+class CpuArm:
+    def __init__(self, wl, inp):
+        from oracle import oracle as orc
+        self.orc, self.wl, self.inp = orc, wl, inp
+        orc.build()
+        C = wl["C"]
+        self.cores = os.cpu_count() or 1
+        bl = orc.class_image_to_layers(inp["img"], inp["lut"], C, 1.0)
+        self.layers, self.mask = orc.compute_dists(bl, 1.0)        # set-up, not timed (map precompute)
+        self.tab = orc.polar_table(N_THETA, N_R, ANG_RES, 1.0)
+        self.thetas, self.shifts = orc.search_list(N_THETA)
+        self.fp = orc.make_params(C, regularization=0.7, map_width=wl["side"], map_height=wl["side"])
+        self.u = orc.uniform_draw(SEED)
+
+    def step(self, lo, n):
+        """one reference update on particles [lo, lo+n): render + score (all host threads) + normalise + resample"""
+        orc, wl, inp = self.orc, self.wl, self.inp
+        st = inp["st"][lo:lo + n].copy()
+        ld = inp["ld"][lo:lo + n]
+        t0 = time.perf_counter()
+        scan = orc.render_polar(inp["pts"], wl["res"], ANG_RES, N_THETA, N_R, inp["lut"], wl["C"])
+        w = orc.score_all(st, self.fp, self.layers, self.mask, 1.0, self.tab, N_THETA, N_R, scan, wl["res"],
+                          self.thetas, self.shifts, n_threads=self.cores)
+        wn, _, _ = orc.normalize(w, ld)
+        orc.resample_fast(wn, self.u, n)
+        return time.perf_counter() - t0
+
+
+def run_reference(args, wl):
+    rank = int(os.environ.get("RANK", "0"))
+    if rank != 0:
+        return
+    inp = make_inputs(wl)
+    arm = CpuArm(wl, inp)
+    n_s = min(wl["n"], 8192 if wl["shifts"] > 1 else wl["n"])
+    for i in range(args.warmup):
+        arm.step((i * n_s) % max(1, wl["n"] - n_s), n_s)
+    ts = []
+    for i in range(args.steps):
+        ts.append(arm.step(((i + args.warmup) * n_s) % max(1, wl["n"] - n_s), n_s))
+    total = float(np.sum(ts))
+    value = n_s * wl["shifts"] * args.steps / total
+    sample = (f"{n_s} of the workload's {wl['n']} particles per step (x{wl['shifts']} shifts), full scan render + "
+              f"normalise + O(N) resample; oracle/tdr_oracle.cpp g++ -O2, {arm.cores} std::threads")
+    out = {"impl": "reference", "metric": "particle_scores_per_sec", "value": value, "unit": "scores/s",
+           "n_gpus": args.gpus, "steps": args.steps, "warmup": args.warmup, "ms_per_step": 1e3 * total / args.steps,
+           "higher_is_better": True, "scaling": "weak", "vs_baseline": None, "dtype": "f32", "data": "synthetic",
+           "config": {"workload": wl["desc"], "particles_per_step_sampled": n_s},
+           "cpu_baseline": {"value": value, "unit": "scores/s", "cores": arm.cores, "kind": "port", "sample": sample},
+           "e2e": {"value": value, "unit": "scores/s", "h2d_bytes_per_step": 0, "d2h_bytes_per_step": 0},
+           "gpu_launches": 0}
+    print(json.dumps(out), flush=True)
+
+
+# ------------------------------------------------------------------------------------------------
+# GPU arm
+# ------------------------------------------------------------------------------------------------
+def setup_ctx(wl, inp, device):
+    from top_down_renderer_b200 import hostmath
+    from top_down_renderer_b200.core import Context
+    ctx = Context(device)
+    C = wl["C"]
+    ctx.map_set_class_image(inp["img"], inp["lut"], C, 1.0)
+    ctx.map_set_polar_table(hostmath.polar_table(N_THETA, N_R, ANG_RES, 1.0), N_THETA, N_R)
+    ctx.scan_set_lut(inp["lut"], C)
+    ctx.pf_set_params(C, regularization=0.7)
+    th, sh = hostmath.search_list(N_THETA)
+    ctx.pf_set_search(th, sh)
+    ctx.pf_set_states(inp["st"], inp["ld"])
+    ctx.pf_checkpoint()
+    return ctx
+
+
+def run_gpu(args, wl):
+    import torch
+    import torch.distributed as dist
+    rank = int(os.environ.get("RANK", "0"))
+    world = int(os.environ.get("WORLD_SIZE", "1"))
+    local = int(os.environ.get("LOCAL_RANK", "0"))
+    if not torch.cuda.is_available():
+        raise SystemExit("bench.py: no CUDA device — the product path has no CPU fallback "
+                         "(use --impl reference for the CPU arm)")
+    torch.cuda.set_device(local)
+    if world > 1:
+        os.environ.setdefault("MASTER_ADDR", "127.0.0.1")
+        dist.init_process_group("nccl", device_id=torch.device("cuda", local))
+    from top_down_renderer_b200 import sharded
+
+    inp = make_inputs(wl, rank)
+    ctx = setup_ctx(wl, inp, local)
+    ctx.profile_enable(True)
+    stream = torch.cuda.ExternalStream(ctx.stream, device=local)
+    flt = sharded.ShardedFilter(ctx, stream, rank, world) if world > 1 else None
+    n, C, res = wl["n"], wl["C"], wl["res"]
+    M = n                                   # resample back to the same particle count (per GPU)
+    u = float(np.random.default_rng(SEED).random(dtype=np.float32))
+    pts_pinned = torch.from_numpy(inp["pts"]).pin_memory()
+    flush = torch.empty(256 << 20, dtype=torch.uint8, device=f"cuda:{local}")
+
+    def one_step():
+        if flt is not None:
+            flt.step(res, float(ANG_RES), N_THETA, N_R, u, M * world)
+        else:
+            ctx.step(res, float(ANG_RES), N_THETA, N_R, u, M)
+
+    def barrier():
+        if world > 1:
+            dist.barrier()
+        torch.cuda.synchronize()
+
+    # ---- resident run: scan points already in HBM
+    ctx.scan_set_points_ptr(pts_pinned.data_ptr(), 32, 16, pts_pinned.shape[0])
+    ctx.sync()
+    launches0 = None
+    evs, stage = [], []
+    sampler = ClockSampler(local)
+    total_steps = args.warmup + args.steps
+    for i in range(total_steps):
+        if i == args.warmup:
+            barrier()
+            sampler.start()
+            launches0 = ctx.launch_count()
+            t_wall0 = time.perf_counter()
+        with torch.cuda.stream(stream):
+            ctx.pf_restore()                 # same prior every step (outside the timed events)
+            flush.zero_()                    # L2 flush: 256 MiB write > 126 MB L2
+            e0, e1 = torch.cuda.Event(enable_timing=True), torch.cuda.Event(enable_timing=True)
+            e0.record(stream)
+            one_step()
+            e1.record(stream)
+        if i >= args.warmup:
+            evs.append((e0, e1))
+            stage.append(ctx.profile_stage_ms())
+    barrier()
+    t_wall = time.perf_counter() - t_wall0
+    clocks = sampler.stop()
+    launches = ctx.launch_count() - launches0
+    step_ms = np.array([a.elapsed_time(b) for a, b in evs])
+    total_ms = float(step_ms.sum())
+    stage = np.array(stage)
+    if world > 1:
+        t = torch.tensor([total_ms], device=f"cuda:{local}", dtype=torch.float64)
+        dist.all_reduce(t, op=dist.ReduceOp.MAX)
+        total_ms = float(t.item())
+    scores_per_step = n * wl["shifts"] * world
+    value = scores_per_step * args.steps / (total_ms * 1e-3)
+
+    # ---- end to end: host scan in pinned memory -> H2D -> step -> pose D2H, wall clock around the public calls
+    e2e_t = []
+    for i in range(args.warmup + args.steps):
+        with torch.cuda.stream(stream):
+            ctx.pf_restore()
+            flush.zero_()
+        barrier()
+        t0 = time.perf_counter()
+        ctx.scan_set_points_ptr(pts_pinned.data_ptr(), 32, 16, pts_pinned.shape[0])     # H2D 2 MiB
+        with torch.cuda.stream(stream):
+            one_step()
+        if flt is not None:
+            mean, cov, _, _ = flt.pose(want_ml=False)                                    # 2nd all-gather + D2H pose
+        else:
+            mean, cov, _, _ = ctx.pf_pose(want_ml=False)                                 # D2H pose (synchronises)
+        dt = time.perf_counter() - t0
+        if i >= args.warmup:
+            e2e_t.append(dt)
+    e2e_total = float(np.sum(e2e_t))
+    if world > 1:
+        t = torch.tensor([e2e_total], device=f"cuda:{local}", dtype=torch.float64)
+        dist.all_reduce(t, op=dist.ReduceOp.MAX)
+        e2e_total = float(t.item())
+    e2e_value = scores_per_step * args.steps / e2e_total
+
+    out = None
+    if rank == 0:
+        peak, peak_src = peaks()
+        score_ms = float(stage[:, 1].mean())
+        achieved = n * b_score(C) / (score_ms * 1e-3) / 1e9
+        traffic = None
+        try:
+            with open(os.path.join(ROOT, "profiles", "score_kernel_traffic.json")) as f:
+                traffic = json.load(f).get(args.workload, {}).get("dram_bytes_per_launch")
+        except Exception:
+            pass
+        out = {"metric": "particle_scores_per_sec", "value": value, "unit": "scores/s", "n_gpus": world,
+               "steps": args.steps, "warmup": args.warmup, "ms_per_step": total_ms / args.steps,
+               "higher_is_better": True, "scaling": "weak", "vs_baseline": None, "dtype": "f32", "data": "synthetic",
+               "config": {"workload": wl["desc"], "particles_per_gpu": n, "shifts_per_particle": wl["shifts"],
+                          "map_px": [wl["side"], wl["side"]], "classes": C, "polar_image": [N_THETA, N_R],
+                          "res_m_per_bin": res, "parallelism": f"particle shards x{world}, map replicated"
+                          + (", 1 all-gather(weights+states)/step" if world > 1 else ""),
+                          "l2": "flushed (256 MiB write) and particle set rolled back between steps, outside the timed events"},
+               "clocks": clocks,
+               "p50_update_ms": float(np.median(step_ms)),
+               "stage_ms": {"render": float(stage[:, 0].mean()), "score": score_ms,
+                            "normalize": float(stage[:, 2].mean()), "resample": float(stage[:, 3].mean())},
+               "e2e": {"value": e2e_value, "unit": "scores/s", "h2d_bytes_per_step": int(inp["pts"].nbytes),
+                       "d2h_bytes_per_step": 20 * 4, "ms_per_step": 1e3 * e2e_total / args.steps,
+                       "p50_ms": 1e3 * float(np.median(e2e_t)), "timer": "host wall clock around set_points+step+pose"},
+               "gpu_launches": int(launches),
+               "wall_s_timed_region": t_wall,
+               "roofline": {"bound": "hbm", "kernel": "k_score_search" if wl["shifts"] > 1 else "k_score_track",
+                            "achieved": achieved, "peak": peak, "unit": "GB/s", "frac": achieved / peak,
+                            "traffic": traffic, "peak_source": peak_src,
+                            "algorithmic_bytes_per_launch": n * b_score(C), "kernel_ms": score_ms}}
+    # ---- CPU baseline (rank 0, N = 1 only): bounded sample of the same workload on the host cores
+    if rank == 0 and world == 1 and not args.no_cpu:
+        arm = CpuArm(wl, inp)
+        n_s = min(n, 32768 if wl["shifts"] > 1 else n)
+        arm.step(0, min(n_s, 2048))
+        reps = 1 if wl["shifts"] > 1 else 20
+        tt = sum(arm.step(0, n_s) for _ in range(reps))
+        out["cpu_baseline"] = {"value": n_s * wl["shifts"] * reps / tt, "unit": "scores/s", "cores": arm.cores,
+                               "kind": "port",
+                               "sample": f"{reps} update(s) of {n_s} of the {n} particles (x{wl['shifts']} shifts) incl. scan render, "
+                                         f"normalise, O(N) resample; oracle/tdr_oracle.cpp (g++ -O2, no -march), "
+                                         f"{arm.cores} std::threads"}
+    elif rank == 0:
+        out["cpu_baseline"] = None
+    if rank == 0:
+        print(json.dumps(out), flush=True)
+    ctx.close()
+    if world > 1:
+        dist.barrier()
+        dist.destroy_process_group()
+
+
+def main():
+    ap = argparse.ArgumentParser()
+    ap.add_argument("--gpus", type=int, default=1)
+    ap.add_argument("--steps", type=int, default=20)
+    ap.add_argument("--warmup", type=int, default=3)
+    ap.add_argument("--impl", default="b200", choices=["b200", "reference"])
+    ap.add_argument("--workload", default="global", choices=sorted(WORKLOADS))
+    ap.add_argument("--particles", type=int, default=0, help="override particles per GPU")
+    ap.add_argument("--no-cpu", action="store_true", help="skip the cpu_baseline leg")
+    args = ap.parse_args()
+    args.warmup = max(args.warmup, 0)
+    wl = dict(WORKLOADS[args.workload])
+    if args.particles:
+        wl["n"] = args.particles
+    if args.impl == "reference":
+        run_reference(args, wl)
+    else:
+        run_gpu(args, wl)
+
+
+if __name__ == "__main__":
+    main()

@@ -69,6 +69,14 @@ void tdr_destroy(tdr_ctx* ctx);
 int tdr_sync(tdr_ctx* ctx);                      /* cudaStreamSynchronize on the context stream */
 void* tdr_stream(tdr_ctx* ctx);                  /* the cudaStream_t every kernel is launched on */
 int tdr_launch_count(tdr_ctx* ctx, int64_t* n);  /* kernels launched by this context so far */
+/* stage stopwatches (the reference's "Render took / Filter update N ms" prints, top_down_render.cpp:416-428,
+ * 513-548, as CUDA events on the context stream).  When enabled, tdr_step / tdr_pf_update bracket
+ * render, score, normalise and resample; tdr_profile_stage_ms synchronises and returns the last step's
+ * device time per stage in ms. */
+#define TDR_N_STAGES 4
+enum { TDR_STAGE_RENDER = 0, TDR_STAGE_SCORE = 1, TDR_STAGE_NORMALIZE = 2, TDR_STAGE_RESAMPLE = 3 };
+int tdr_profile_enable(tdr_ctx* ctx, int on);
+int tdr_profile_stage_ms(tdr_ctx* ctx, float ms[TDR_N_STAGES]);
 
 /* ---- map: TopDownMap / TopDownMapPolar ------------------------------------ */
 /* a3+a4: TopDownMap::updateMap = loadCompressedRasterMap + computeDists
@@ -124,6 +132,11 @@ int tdr_pf_set_search(tdr_ctx* ctx, const float* thetas, const int32_t* shifts, 
 int tdr_pf_set_states(tdr_ctx* ctx, const tdr_state* states, const float* last_dist, int64_t n);
 int tdr_pf_get_states(tdr_ctx* ctx, tdr_state* states, int64_t n);
 int tdr_pf_count(tdr_ctx* ctx, int64_t* n);
+/* device-side snapshot / roll-back of the resident particle set (asynchronous, D2D).  No reference
+ * counterpart: lets a supervisor (or bench.py) replay an update from the same prior without a
+ * 28 B/particle H2D. */
+int tdr_pf_checkpoint(tdr_ctx* ctx);
+int tdr_pf_restore(tdr_ctx* ctx);
 /* a9+a10: StateParticle::computeWeight for every particle (the for_each(par) region,
  * particle_filter.cpp:104-105) against the resident polar scan images.  Updates theta /
  * have_init on the device like the reference.  weights_out may be NULL. */
@@ -157,6 +170,21 @@ int tdr_grid_best(tdr_ctx* ctx, float* best_cost, int64_t* best_index);
  * torch.distributed): weights (n floats) / grid costs (n*n_shifts floats) */
 int tdr_dev_ptr(tdr_ctx* ctx, int which, void** ptr, int64_t* n_elems);
 enum { TDR_BUF_WEIGHTS = 0, TDR_BUF_GRID_COSTS = 1, TDR_BUF_STATES_SOA = 2, TDR_BUF_SCAN_IMAGES = 3 };
+/* ---- multi-GPU: particle shards, map replicated.  The collective itself (ONE all-gather per step) is
+ * issued by the host layer on tdr_stream() — torch.distributed / NCCL; the library packs and consumes.
+ * Shard block = TDR_SHARD_ROWS rows of n_local floats: weight, init_x, init_y, dx, dy, theta, scale,
+ * have_init (0/1), last_dist. */
+#define TDR_SHARD_ROWS 9
+/* pack the resident particle set (+ its raw weights from tdr_pf_score when with_weights) into dev_out */
+int tdr_pf_export_shard(tdr_ctx* ctx, void* dev_out, int64_t capacity_floats, int with_weights);
+/* dev_all = n_ranks shard blocks in rank order (the all-gather output).  Normalises the N = n_ranks*n_local
+ * weights in global order (redundantly on every rank, so the result does not depend on n_ranks), then
+ * draws outputs [i0, i1) of the M systematic samples and gathers their states into the resident set. */
+int tdr_pf_update_gathered(tdr_ctx* ctx, const void* dev_all, int n_ranks, int64_t n_local, float u, int64_t M,
+                           int64_t i0, int64_t i1);
+/* pose over the all-gathered resampled set (same result on every rank and for every n_ranks) */
+int tdr_pf_pose_gathered(tdr_ctx* ctx, const void* dev_all, int n_ranks, int64_t n_local, float mean[4],
+                         float cov_mean[16], float ml[4], float cov_ml[16]);
 /* replace the resident weights by an externally gathered vector living on the device
  * (all-gather output), n floats */
 int tdr_pf_set_weights_dev(tdr_ctx* ctx, const void* dev_weights, int64_t n);

@@ -1,0 +1,155 @@
+"""A second, deliberately naive restatement of the hot path in numpy / pure Python (TEST INFRASTRUCTURE ONLY).
+
+It exists to cross-check oracle/tdr_oracle.cpp on small inputs with *different code*: explicit np.roll for
+the shift-correlation, brute-force nearest-seed search for the distance transform, a literal O(N*M)
+resampler.  Citations are file:line in the reference checkout.
+"""
+from __future__ import annotations
+
+import ctypes as C
+import math
+
+import numpy as np
+
+_libm = C.CDLL("libm.so.6")
+_libm.atan2f.restype = C.c_float
+_libm.atan2f.argtypes = [C.c_float, C.c_float]
+_libm.roundf.restype = C.c_float
+_libm.roundf.argtypes = [C.c_float]
+f32 = np.float32
+
+
+def render_polar(pts, res, ang_res, n_theta, n_r, lut, num_classes):
+    """scan_renderer_polar.cpp:83-109; returns (C, n_r, n_theta)"""
+    img = np.zeros((num_classes, n_r, n_theta), dtype=np.float32)
+    for p in pts:
+        x, y, inten = f32(p[0]), f32(p[1]), p[4]
+        if x == 0 and y == 0:
+            continue
+        theta = f32(_libm.atan2f(x, y))
+        r = np.sqrt(f32(f32(x * x) + f32(y * y)), dtype=np.float32)
+        ti = int(f32(_libm.roundf(f32(theta / f32(ang_res))) + f32(n_theta // 2)))
+        ri = int(_libm.roundf(f32(r / f32(res))))
+        if 0 <= ti < n_theta and 0 <= ri < n_r:
+            cls = lut[int(inten)]
+            if cls >= 0:
+                img[cls, ri, ti] += 1
+    return img
+
+
+def edt_layers_bruteforce(bin_layers, resolution):
+    """top_down_map.cpp:289-326 with a brute-force nearest-zero search; layers (C, cols, rows) of 0/1"""
+    Cn, cols, rows = bin_layers.shape
+    mask = (bin_layers.astype(np.uint8).sum(axis=0) > Cn - 1).astype(np.uint8)
+    out = np.empty_like(bin_layers, dtype=np.float32)
+    xs, ys = np.meshgrid(np.arange(cols), np.arange(rows), indexing="ij")
+    for c in range(Cn):
+        seeds = np.argwhere(bin_layers[c] == 0)
+        if len(seeds) == 0:
+            d = np.full((cols, rows), 50.0, dtype=np.float32)
+        else:
+            d2 = np.min((xs[..., None] - seeds[:, 0]) ** 2 + (ys[..., None] - seeds[:, 1]) ** 2, axis=-1)
+            d = np.minimum(np.sqrt(d2.astype(np.float32), dtype=np.float32) * f32(resolution), f32(50.0))
+        d[mask != 0] = 0
+        out[c] = d
+    return out, mask
+
+
+def local_map_polar(layers, mask, resolution, tab, cx, cy, scale, res):
+    """top_down_map_polar.cpp:21-53; layers (C, cols, rows); returns (C, P), (P,)"""
+    Cn, cols, rows = layers.shape
+    P = tab.shape[0]
+    d = np.zeros((Cn, P), dtype=np.float32)
+    m = np.ones(P, dtype=np.uint8)
+    oy, ox = f32(f32(cy) / f32(resolution)), f32(f32(cx) / f32(resolution))
+    for p in range(P):
+        r = int(_libm.roundf(f32(f32(f32(tab[p, 0] * f32(scale)) * f32(res)) + oy)))
+        c = int(_libm.roundf(f32(f32(f32(tab[p, 1] * f32(scale)) * f32(res)) + ox)))
+        if 0 <= r < rows and 0 <= c < cols:
+            d[:, p] = layers[:, c, r]
+            m[p] = mask[c, r]
+    return d, m
+
+
+def cost_for_shift(scan, classes, known, n_theta, n_r, class_weights, shift):
+    """state_particle.cpp:112-155 with an explicit roll: scan row r pairs with map row (r - s) mod n_theta.
+    float64 accumulation (the reference's fp32 SIMD order is not part of the contract; 1e-5 is)."""
+    known = known.reshape(n_r, n_theta).astype(np.float64)
+    if known.sum() / known.size < 0.5:
+        return float("nan")
+    cost = norm = 0.0
+    for c in range(scan.shape[0]):
+        sc = scan[c].reshape(n_r, n_theta).astype(np.float64)
+        mp = classes[c].reshape(n_r, n_theta).astype(np.float64)
+        cost += (sc * np.roll(mp, shift, axis=1)).sum() * 0.01 * float(class_weights[c])
+        norm += (sc * np.roll(known, shift, axis=1)).sum()
+    return cost / norm if norm != 0 else float("nan")
+
+
+def normalize(w, last_dist):
+    """particle_filter.cpp:107-147 (loop counters read as i = 0), scalar Python, sequential fp32"""
+    w = np.array(w, dtype=np.float32)
+    n = len(w)
+    s, nv = f32(0), 0
+    for v in w:
+        if v == v:
+            s = f32(s + v); nv += 1
+    with np.errstate(all="ignore"):
+        mean = f32(s / f32(nv)) if nv else f32(np.nan)
+    bs, nu = f32(0), 0
+    for v in w:
+        if v == v and v < mean:
+            bs = f32(float(bs) + float(f32(v - mean)) ** 2); nu += 1
+    with np.errstate(all="ignore"):
+        bs = np.sqrt(f32(bs / f32(nu)), dtype=np.float32) if nu else f32(np.nan)
+    if s == 0 or nu < 1:
+        w[:] = 1
+    else:
+        w[np.isnan(w)] = f32(mean - bs)
+    w = (w / _eigen_sum(w)).astype(np.float32)
+    d = np.minimum(last_dist.astype(np.float32) * f32(5), f32(1))
+    w = (d * w).astype(np.float32) + ((f32(1) - d) / f32(n)).astype(np.float32)
+    w = (w / _eigen_sum(w)).astype(np.float32)
+    return w, int(np.argmax(w))
+
+
+def _eigen_sum(x):
+    """Eigen linear-vectorised float sum, SSE2 packets of 4, 2x unrolled (Eigen/src/Core/Redux.h)"""
+    x = np.asarray(x, dtype=np.float32)
+    n = len(x)
+    a4, a8 = (n // 4) * 4, (n // 8) * 8
+    if a4 == 0:
+        r = x[0]
+        for v in x[1:]:
+            r = f32(r + v)
+        return r
+    p0 = x[0:4].copy()
+    if a4 > 4:
+        p1 = x[4:8].copy()
+        for i in range(8, a8, 8):
+            p0 = (p0 + x[i:i + 4]).astype(np.float32)
+            p1 = (p1 + x[i + 4:i + 8]).astype(np.float32)
+        p0 = (p0 + p1).astype(np.float32)
+        if a4 > a8:
+            p0 = (p0 + x[a8:a8 + 4]).astype(np.float32)
+    r = f32(f32(p0[0] + p0[2]) + f32(p0[1] + p0[3]))
+    for v in x[a4:]:
+        r = f32(r + v)
+    return r
+
+
+def resample_literal(w, u, M):
+    """particle_filter.cpp:172-185, the O(N*M) double loop"""
+    n = len(w)
+    idx = np.empty(M, dtype=np.int32)
+    for i in range(M):
+        sample = f32(f32(f32(i) + f32(u)) / f32(M))
+        run = f32(0)
+        j = 0
+        while True:
+            run = f32(run + w[j])
+            if run > sample or j == n - 1:
+                break
+            j += 1
+        idx[i] = j
+    return idx

@@ -333,3 +333,123 @@ def test_full_update_cfg1(world, ctx):
     got_idx_from_states = got_states["init_x_px"]
     mism = np.count_nonzero(got_idx_from_states != st_o["init_x_px"][idx])
     assert mism <= 10, mism
+
+
+# ---- committed golden fixtures (tests/golden/*.npz travel to the GPU box; /root/reference and cv2 need not exist) ---
+def _gold(name):
+    import os
+    return np.load(os.path.join(os.path.dirname(os.path.abspath(__file__)), "golden", name))
+
+
+@pytest.mark.parametrize("resolution", [1.0, 0.5, 2.0])
+def test_distance_fields_equal_opencv_fixture(resolution):
+    """the CUDA EDT against OpenCV's own answer (cv2.distanceTransform PRECISE + TRUNC 50, top_down_map.cpp:312-317)"""
+    g = _gold("edt_cv2.npz")
+    from top_down_renderer_b200.core import Context
+    c = Context(0)
+    c.map_set_class_image(g["img"], g["lut"], int(g["num_classes"]), resolution)
+    layers, mask = c.map_get_layers()
+    c.close()
+    assert np.array_equal(mask, g[f"mask_{resolution}"])
+    assert np.array_equal(layers.view(np.uint32), g[f"layers_{resolution}"].view(np.uint32))
+
+
+def test_cfg1_mini_fixture_through_the_c_abi():
+    import zlib
+    g = _gold("cfg1_mini.npz")
+    Cn, n = int(g["num_classes"]), len(g["states"])
+    from top_down_renderer_b200.core import Context
+    c = Context(0)
+    c.map_set_class_image(g["img"], g["lut"], Cn, 1.0)
+    c.map_set_polar_table(g["tab"], N_THETA, N_R)
+    c.scan_set_lut(g["lut"], Cn)
+    c.pf_set_params(Cn, regularization=0.7)
+    c.pf_set_search(g["thetas"], g["shifts"])
+    layers, mask = c.map_get_layers()
+    assert zlib.crc32(layers.tobytes()) == int(g["layers_crc"]) and zlib.crc32(mask.tobytes()) == int(g["mask_crc"])
+    c.scan_set_points(np.ascontiguousarray(g["pts"]))
+    scan = c.scan_render_polar(float(g["res"]), g["ang_res"], N_THETA, N_R)
+    assert np.array_equal(scan, g["scan"])                                           # class images: bit-exact
+    c.pf_set_states(g["states"].copy(), g["last_dist"])
+    w = c.pf_score(float(g["res"]))
+    assert rel_err(w, g["weights"]).max() <= WEIGHT_RTOL                             # weights: 1e-5
+    # stage-wise from here on (SURVEY section 8 parity contract): feed the oracle's raw weights
+    c.pf_set_weights(g["weights"])
+    arg, _ = c.pf_normalize()
+    wn = c.pf_get_weights(n)
+    assert np.array_equal(wn.view(np.uint32), g["weights_norm"].view(np.uint32)) and arg == int(g["argmax"])
+    idx = c.pf_resample(float(g["u"]), n)
+    assert np.array_equal(idx, g["idx"])                                             # indices: bit-exact
+    mean, cov, ml, _ = c.pf_pose()
+    c.close()
+    assert abs(mean[0] - g["mean"][0]) <= POSE_TOL_PX and abs(mean[1] - g["mean"][1]) <= POSE_TOL_PX
+    assert abs(mean[2] - g["mean"][2]) <= POSE_TOL_RAD
+    assert abs(ml[0] - g["ml"][0]) <= POSE_TOL_PX and abs(ml[1] - g["ml"][1]) <= POSE_TOL_PX
+
+
+# ---- multi-GPU path, ranks emulated one after another on one device (no kernel waits on another) -----------------
+@pytest.mark.parametrize("world_size", [2, 4])
+def test_sharded_update_is_independent_of_world_size(world, world_size):
+    import torch
+    from top_down_renderer_b200 import sharded
+    n_local = 500
+    n_total = n_local * world_size
+    st, ld = synth.particles_tracking(n_total, world.pose, world.heading, seed=3)
+    st["have_init"][::5] = 0
+    u, M = orc.uniform_draw(3), n_total
+    # single context, whole set
+    one = make_ctx(world)
+    one.scan_set_points(world.pts)
+    one.pf_set_states(st, ld)
+    one.step(4.0, ANG_RES, N_THETA, N_R, u, M)
+    one.sync()
+    w_one, st_one = one.pf_get_weights(n_total), one.pf_get_states()
+    mean_one, cov_one, ml_one, _ = one.pf_pose()
+    one.close()
+    # world_size contexts, one shard each
+    ranks = []
+    blocks = torch.empty(world_size * sharded.SHARD_ROWS * n_local, dtype=torch.float32, device="cuda:0")
+    for g in range(world_size):
+        c = make_ctx(world)
+        lo, hi = sharded.shard_range(n_total, g, world_size)
+        c.scan_set_points(world.pts)
+        c.pf_set_states(st[lo:hi].copy(), ld[lo:hi])
+        c.scan_render_polar(4.0, ANG_RES, N_THETA, N_R, want=False)
+        c.pf_score(4.0, want=False)
+        c.pf_export_shard(blocks.data_ptr() + 4 * g * sharded.SHARD_ROWS * n_local, sharded.SHARD_ROWS * n_local, True)
+        c.sync()
+        ranks.append(c)
+    got_states, blocks2 = [], torch.empty_like(blocks)
+    for g, c in enumerate(ranks):
+        i0, i1 = sharded.sample_slice(M, g, world_size)
+        c.pf_update_gathered(blocks.data_ptr(), world_size, n_local, u, M, i0, i1)
+        c.sync()
+        assert np.array_equal(c.pf_get_weights(n_total).view(np.uint32), w_one.view(np.uint32))
+        got_states.append(c.pf_get_states())
+        c.pf_export_shard(blocks2.data_ptr() + 4 * g * sharded.SHARD_ROWS * n_local, sharded.SHARD_ROWS * n_local, False)
+        c.sync()
+    assert np.array_equal(np.concatenate(got_states), st_one)
+    mean, cov, ml, _ = ranks[0].pf_pose_gathered(blocks2.data_ptr(), world_size, n_local)
+    for c in ranks:
+        c.close()
+    assert np.array_equal(mean, mean_one) and np.array_equal(ml, ml_one) and np.allclose(cov, cov_one, rtol=1e-6)
+
+
+def test_checkpoint_restore_and_stage_timers(world):
+    c = make_ctx(world)
+    st, ld = synth.particles_tracking(2000, world.pose, world.heading, seed=8)
+    st["have_init"][::2] = 0
+    c.scan_set_points(world.pts)
+    c.pf_set_states(st, ld)
+    c.pf_checkpoint()
+    c.profile_enable(True)
+    u = orc.uniform_draw(8)
+    c.step(4.0, ANG_RES, N_THETA, N_R, u, 2000)
+    a = c.pf_get_states()
+    ms = c.profile_stage_ms()
+    assert len(ms) == 4 and all(m >= 0 for m in ms) and ms[1] > 0
+    c.pf_restore()
+    assert np.array_equal(c.pf_get_states(), st)
+    c.step(4.0, ANG_RES, N_THETA, N_R, u, 2000)
+    assert np.array_equal(c.pf_get_states(), a)          # replay from the same prior is deterministic
+    c.close()

@@ -1,0 +1,170 @@
+"""Host build of the kernels' shared index math (csrc/tdr_math.cuh) against glibc and plain sequential loops.
+
+The same inline functions are compiled into the CUDA kernels (with _rn intrinsics instead of
+-ffp-contract=off), so these CPU tests pin the arithmetic the GPU parity tests then confirm."""
+import ctypes as C
+import math
+
+import numpy as np
+import pytest
+
+import top_down_renderer_b200 as tdr
+
+fp = C.POINTER(C.c_float)
+
+
+@pytest.fixture(scope="module")
+def hm():
+    lib = C.CDLL(tdr.build_hostmath())
+    lib.hm_atan2f.restype = C.c_float
+    lib.hm_atan2f.argtypes = [C.c_float, C.c_float]
+    lib.hm_atan2f_mismatches.restype = C.c_long
+    lib.hm_round.restype = C.c_float
+    lib.hm_round.argtypes = [C.c_float]
+    lib.hm_f2i.argtypes = [C.c_float]
+    lib.hm_dist_value.restype = C.c_float
+    lib.hm_dist_value.argtypes = [C.c_uint, C.c_float]
+    lib.hm_rot_to_shift.argtypes = [C.c_float, C.c_int]
+    lib.hm_lattice_index.argtypes = [C.c_float] * 4
+    lib.hm_polar_bin.argtypes = [C.c_float] * 4 + [C.c_int, C.c_int, C.POINTER(C.c_int), C.POINTER(C.c_int)]
+    return lib
+
+
+def test_atan2f_is_glibc_bit_for_bit(hm):
+    rng = np.random.default_rng(1)
+    n = 2_000_000
+    for scale in (1.0, 100.0, 1e-3, 1e6):
+        y = (rng.standard_normal(n) * scale).astype(np.float32)
+        x = (rng.standard_normal(n) * scale).astype(np.float32)
+        assert hm.hm_atan2f_mismatches(y.ctypes.data_as(fp), x.ctypes.data_as(fp), C.c_long(n)) == 0
+    # ratios that land on the argument-reduction thresholds, axes, zeros, infinities, NaN, denormals
+    sp = np.array([0.0, -0.0, 1.0, -1.0, 0.4375, 0.6875, 1.1875, 2.4375, 1e-38, 1e-45, 3e38, np.inf, -np.inf, np.nan,
+                   2.0 ** 25, 2.0 ** -29, 7.0 / 16, 11.0 / 16, 19.0 / 16, 39.0 / 16], dtype=np.float32)
+    yy, xx = [a.reshape(-1).copy() for a in np.meshgrid(sp, sp)]
+    assert hm.hm_atan2f_mismatches(yy.ctypes.data_as(fp), xx.ctypes.data_as(fp), C.c_long(len(yy))) == 0
+
+
+def test_round_and_float_to_int(hm):
+    libm = C.CDLL("libm.so.6")
+    libm.roundf.restype = C.c_float
+    libm.roundf.argtypes = [C.c_float]
+    rng = np.random.default_rng(0)
+    vals = [0.5, -0.5, 1.5, 2.5, -2.5, 0.49999997, -0.49999997, 8388607.5, 8388608.0, 1e10, -1e10, 3.0, -0.0]
+    vals += list((rng.standard_normal(20000) * 100).astype(np.float32)) + list(rng.integers(-500, 500, 2000) + 0.5)
+    for v in vals:
+        assert hm.hm_round(float(v)) == libm.roundf(float(v)), v        # std::round: half away from zero
+    assert hm.hm_f2i(float("nan")) == -2 ** 31 and hm.hm_f2i(3e9) == -2 ** 31 and hm.hm_f2i(-3e9) == -2 ** 31
+    assert hm.hm_f2i(-7.9) == -7 and hm.hm_f2i(7.9) == 7
+
+
+def test_polar_bin_matches_independent_numpy(hm):
+    """scan_renderer_polar.cpp:95-102 restated with numpy float32 ops + glibc atan2f via ctypes libm"""
+    libm = C.CDLL("libm.so.6")
+    libm.atan2f.restype = C.c_float
+    libm.atan2f.argtypes = [C.c_float, C.c_float]
+    rng = np.random.default_rng(2)
+    ang = np.float32(2 * math.pi / 100)
+    ti, ri = C.c_int(), C.c_int()
+    for res in (4.0, 0.5, 1.7):
+        pts = (rng.standard_normal((4000, 2)) * 40).astype(np.float32)
+        for x, y in pts:
+            th = np.float32(libm.atan2f(x, y))
+            r = np.sqrt(np.float32(np.float32(x * x) + np.float32(y * y)), dtype=np.float32)
+            q = np.float32(th / ang)
+            t = int(math.copysign(math.floor(abs(q) + np.float32(0.5)), q)) + 50
+            rq = np.float32(r / np.float32(res))
+            rr = int(math.floor(rq + np.float32(0.5)))
+            ok = 0 <= t < 100 and 0 <= rr < 25
+            got = hm.hm_polar_bin(x, y, res, ang, 100, 25, C.byref(ti), C.byref(ri))
+            assert bool(got) == ok
+            if ok:
+                assert (ti.value, ri.value) == (t, rr)
+    assert hm.hm_polar_bin(0.0, 0.0, 4.0, ang, 100, 25, C.byref(ti), C.byref(ri)) == 0       # skipped point (:95)
+    assert hm.hm_polar_bin(float("nan"), 1.0, 4.0, ang, 100, 25, C.byref(ti), C.byref(ri)) == 0
+
+
+def test_rot_to_shift_and_search_list(hm):
+    from top_down_renderer_b200 import hostmath
+    th, sh = hostmath.search_list(100)
+    assert len(th) == 40                                  # the loop runs exactly 40 times
+    assert list(sh) == [0, 3, 5, 8, 10, 13, 15, 17, 20, 22, 25, 27, 30, 32, 35, 37, 40, 42, 45, 47, 50, 53, 55, 58, 60,
+                        63, 65, 68, 70, 73, 75, 78, 80, 83, 85, 88, 90, 93, 95, 98]
+    for t, s in zip(th, sh):
+        assert hm.hm_rot_to_shift(float(t), 100) == s
+    for rot in (-0.1, -3.2, 7.0, 100.0, -100.0, 0.0314, 6.2831):
+        assert hm.hm_rot_to_shift(rot, 100) == hostmath.rot_to_shift(rot, 100)
+        assert 0 <= hm.hm_rot_to_shift(rot, 100) < 100
+
+
+def test_dist_value_is_sqrt_mul_min(hm):
+    for res in (1.0, 0.5, 2.0, 1.3):
+        for d2 in (0, 1, 2, 5, 624, 625, 2499, 2500, 2501, 10000, 65536):
+            want = min(np.float32(np.sqrt(np.float32(d2), dtype=np.float32) * np.float32(res)), np.float32(50.0))
+            assert hm.hm_dist_value(d2, res) == want
+
+
+def _seq_prefix(x, skip_nan=False):
+    s = np.float32(0)
+    out = np.empty(len(x), dtype=np.float32)
+    rm = -np.inf
+    for i, w in enumerate(x):
+        if skip_nan and w != w:
+            w = np.float32(0)
+        s = np.float32(s + w)
+        rm = max(rm, s) if s == s else rm
+        out[i] = rm
+    return out, s
+
+
+def _cases(rng, n):
+    w = rng.random(n).astype(np.float32)
+    yield "uniform_normalised", (w / w.sum()).astype(np.float32)
+    yield "raw_weights", (1.0 / (rng.random(n) * 2 + 0.7)).astype(np.float32)
+    yield "dyadic_ties", (rng.integers(0, 8, n) * 2.0 ** -20).astype(np.float32)
+    sp = np.full(n, 1e-9, dtype=np.float32)
+    sp[rng.integers(0, n, max(1, n // 50))] = 1.0
+    yield "spiky", (sp / sp.sum()).astype(np.float32)
+    yield "denormals", np.where(rng.random(n) < 0.9, 2.93874e-39, 1e-3).astype(np.float32)
+    z = rng.random(n).astype(np.float32)
+    z[: n // 3] = 0
+    yield "leading_zeros", z
+    yield "equal_small", np.full(n, 1e-6, dtype=np.float32)
+
+
+@pytest.mark.parametrize("n", [1, 33, 4096, 50_000])
+def test_exact_prefix_equals_sequential_fp32(hm, n):
+    """the binade / IncPair algebra of k_exact_seq reproduces s = RN(s + w) bit for bit"""
+    rng = np.random.default_rng(n)
+    for name, x in _cases(rng, n):
+        want, tot = _seq_prefix(x)
+        got = np.empty(n, dtype=np.float32)
+        total = C.c_float()
+        segs = C.c_long()
+        for chunk in (4096, 64):
+            hm.hm_exact_prefix(x.ctypes.data_as(fp), C.c_long(n), chunk, 0, got.ctypes.data_as(fp), C.byref(total),
+                               C.byref(segs))
+            assert np.array_equal(got.view(np.uint32), want.view(np.uint32)), (name, chunk)
+            assert np.float32(total.value).view(np.uint32) == np.float32(tot).view(np.uint32), name
+
+
+def test_exact_prefix_irregular_inputs(hm):
+    rng = np.random.default_rng(5)
+    n = 3000
+    x = rng.random(n).astype(np.float32)
+    x[rng.integers(0, n, 30)] = -0.5                     # negative weights: falls back to real adds
+    x[rng.integers(0, n, 10)] = np.nan
+    want, tot = _seq_prefix(x, skip_nan=True)
+    got = np.empty(n, dtype=np.float32)
+    total = C.c_float()
+    hm.hm_exact_prefix(x.ctypes.data_as(fp), C.c_long(n), 256, 1, got.ctypes.data_as(fp), C.byref(total), None)
+    assert np.array_equal(got.view(np.uint32), want.view(np.uint32))
+    assert np.float32(total.value).view(np.uint32) == np.float32(tot).view(np.uint32)
+
+
+def test_pair_composition_is_associative(hm):
+    rng = np.random.default_rng(6)
+    for E in (-1, -5, -20, 0, 3, -127):
+        for _ in range(20):
+            n = int(rng.integers(1, 300))
+            x = (rng.random(n) * 2.0 ** (E - rng.integers(0, 30, n))).astype(np.float32)
+            assert hm.hm_pair_tree_equals_chain(x.ctypes.data_as(fp), n, E) == 1

@@ -1,0 +1,289 @@
+"""The oracle (oracle/tdr_oracle.cpp) against everything that can pin it WITHOUT the reference's own tests
+(it has none): OpenCV's real routine (live cv2 and the committed cv2 fixture), a naive numpy
+twin, hand-computed known answers, and domain properties."""
+import math
+import os
+import zlib
+
+import numpy as np
+import pytest
+
+from oracle import numpy_twin as twin
+from oracle import oracle as orc
+from top_down_renderer_b200 import synth
+
+GOLD = os.path.join(os.path.dirname(os.path.abspath(__file__)), "golden")
+ANG = np.float32(2 * math.pi / 100)
+
+
+# ---- distance fields (a3/a4) ------------------------------------------------------------------------
+def test_edt_matches_committed_cv2_fixture():
+    g = np.load(os.path.join(GOLD, "edt_cv2.npz"))
+    Cn = int(g["num_classes"])
+    for resolution in (1.0, 0.5, 2.0):
+        bl = orc.class_image_to_layers(g["img"], g["lut"], Cn, resolution)
+        layers, mask = orc.compute_dists(bl, resolution)
+        assert np.array_equal(mask, g[f"mask_{resolution}"])
+        assert np.array_equal(layers.view(np.uint32), g[f"layers_{resolution}"].view(np.uint32)), resolution
+
+
+@pytest.mark.parametrize("shape,p", [((200, 300), 1e-3), ((257, 131), 0.2), ((64, 64), 0.0)])
+def test_edt_matches_live_cv2(shape, p):
+    cv2 = pytest.importorskip("cv2")
+    cv2.ipp.setUseIPP(False)      # OpenCV's own trueDistTrans (see test_small_image_ipp_path_is_within_2ulp)
+    rng = np.random.default_rng(shape[0])
+    b = (rng.random(shape) >= p).astype(np.uint8)          # 0 = seed
+    d2 = orc.edt_sq(b)
+    got = np.sqrt(d2.astype(np.float32), dtype=np.float32)
+    want = cv2.distanceTransform(b, cv2.DIST_L2, cv2.DIST_MASK_PRECISE)
+    if p == 0.0:                                           # no seed: OpenCV returns a large sentinel -> truncates to 50
+        assert (want > 50).all() and (np.minimum(got, 50) == 50).all()
+    else:
+        assert np.array_equal(got.view(np.uint32), want.view(np.uint32))
+
+
+def test_small_image_ipp_path_is_within_2ulp():
+    """pip's cv2 sends images under 16384 px to Intel IPP, whose sqrt is not correctly rounded; the oracle
+    follows OpenCV's own code path (bit-exact above), and the IPP deviation is characterised here."""
+    cv2 = pytest.importorskip("cv2")
+    if not hasattr(cv2, "ipp"):
+        pytest.skip("no IPP switch in this cv2")
+    rng = np.random.default_rng(1)
+    b = (rng.random((96, 72)) >= 0.01).astype(np.uint8)
+    want = np.sqrt(orc.edt_sq(b).astype(np.float32), dtype=np.float32)
+    cv2.ipp.setUseIPP(True)
+    got = cv2.distanceTransform(b, cv2.DIST_L2, cv2.DIST_MASK_PRECISE)
+    cv2.ipp.setUseIPP(False)
+    ulp = np.abs(got.view(np.int32).astype(np.int64) - want.view(np.int32).astype(np.int64))
+    assert ulp.max() <= 2
+
+
+def test_compute_dists_equals_bruteforce_twin():
+    cm = synth.make_class_map(40, 56, 4, seed=5)
+    img, lut = synth.to_cv_image(cm), synth.identity_lut(4)
+    for resolution in (1.0, 0.5):
+        bl = orc.class_image_to_layers(img, lut, 4, resolution)
+        layers, mask = orc.compute_dists(bl, resolution)
+        tl, tm = twin.edt_layers_bruteforce(bl, resolution)
+        assert np.array_equal(mask, tm) and np.array_equal(layers.view(np.uint32), tl.view(np.uint32))
+
+
+def test_edt_known_answer_3x3():
+    # class 0 only at the centre, class 1 everywhere else -> no unknown pixel.
+    bl = np.ones((2, 3, 3), dtype=np.float32)
+    bl[0, 1, 1] = 0
+    bl[1] = 0
+    bl[1, 1, 1] = 1
+    layers, mask = orc.compute_dists(bl, 1.0)
+    r2 = np.float32(np.sqrt(np.float32(2)))
+    assert np.array_equal(layers[0], np.array([[r2, 1, r2], [1, 0, 1], [r2, 1, r2]], dtype=np.float32))
+    assert np.array_equal(layers[1], np.array([[0, 0, 0], [0, 1, 0], [0, 0, 0]], dtype=np.float32))
+    assert not mask.any()
+    # a pixel with no class at all is unknown: every layer is zeroed there and the mask is 1
+    bl[1, 0, 0] = 1
+    layers, mask = orc.compute_dists(bl, 1.0)
+    assert mask[0, 0] == 1 and mask.sum() == 1 and layers[0, 0, 0] == 0 and layers[1, 0, 0] == 0
+    # truncation at 50 and the class-absent layer (top_down_map.cpp:315; OpenCV's no-seed sentinel)
+    big = np.ones((2, 1, 120), dtype=np.float32)
+    big[0, 0, 0] = 0
+    big[1] = 1
+    big[1, 0, 1:] = 1
+    big[0, 0, 1:] = 1
+    layers, mask = orc.compute_dists(np.stack([big[0], np.zeros_like(big[0])]), 1.0)
+    assert layers[0, 0, 49] == 49 and layers[0, 0, 50] == 50 and layers[0, 0, 119] == 50
+
+
+def test_edt_commutes_with_transpose():
+    rng = np.random.default_rng(3)
+    b = (rng.random((90, 70)) > 0.01).astype(np.uint8)
+    assert np.array_equal(orc.edt_sq(b).T, orc.edt_sq(np.ascontiguousarray(b.T)))
+
+
+def test_class_image_flip_and_lut():
+    # image row 0 is the TOP of the map (top_down_map.cpp:137): class at image (row 0, col 2) lands in map row H-1
+    img = np.full((4, 5), 255, dtype=np.uint8)
+    img[0, 2] = 1
+    bl = orc.class_image_to_layers(img, synth.identity_lut(2), 2, 1.0)
+    assert bl.shape == (2, 5, 4)
+    assert bl[1, 2, 3] == 0 and bl[1].sum() == 19 and bl[0].sum() == 20
+
+
+# ---- rasterisers (a1/a2) ----------------------------------------------------------------------------
+def test_polar_render_known_answers():
+    lut = synth.identity_lut(2)
+    pts = np.zeros((6, 8), dtype=np.float32)
+    pts[0, :2] = (0, 4)        # theta = atan2(x=0, y=4) = 0      -> bin 50, r bin 1
+    pts[1, :2] = (4, 0)        # +pi/2 -> 25 bins                 -> bin 75
+    pts[2, :2] = (-4, 0)       # -pi/2                            -> bin 25
+    pts[3, :2] = (0, -4)       # +pi -> bin 100: dropped (scan_renderer_polar.cpp:102)
+    pts[4, :2] = (-1e-4, -4)   # just below -pi... rounds to -50  -> bin 0
+    pts[5, :2] = (0, 0)        # invalid return, skipped (:95)
+    pts[:, 4] = 1
+    img = orc.render_polar(pts, 4.0, ANG, 100, 25, lut, 2)
+    nz = {(int(c), int(r), int(t)): int(img[c, r, t]) for c, r, t in np.argwhere(img)}
+    assert nz == {(1, 1, 50): 1, (1, 1, 75): 1, (1, 1, 25): 1, (1, 1, 0): 1}
+
+
+def test_render_polar_equals_twin_and_counts_points():
+    cm = synth.make_class_map(300, 300, 4, seed=9)
+    pose, heading = synth.default_pose(cm, seed=9)
+    pts = synth.make_scan(cm, pose, heading, seed=9, n_rings=16, n_az=128)
+    lut = synth.identity_lut(4)
+    for res in (4.0, 0.7):
+        a = orc.render_polar(pts, res, ANG, 100, 25, lut, 4)
+        b = twin.render_polar(pts, res, ANG, 100, 25, lut, 4)
+        assert np.array_equal(a, b)
+    # property: the images sum to the number of valid, in-range, known-class points
+    assert a.sum() == b.sum() > 0
+    cart = orc.render_cart(pts, 1.0, 64, 48, lut, 4)
+    x, y = pts[:, 0], pts[:, 1]
+    xi = np.array([twin._libm.roundf(float(v)) for v in x]) + 24
+    yi = np.array([twin._libm.roundf(float(v)) for v in y]) + 32
+    ok = ~((x == 0) & (y == 0)) & (xi >= 0) & (xi < 48) & (yi >= 0) & (yi < 64) & (pts[:, 4] < 4)
+    assert cart.sum() == ok.sum()
+
+
+# ---- gather + shift-correlation (a6/a7/a10) -----------------------------------------------------------
+@pytest.fixture(scope="module")
+def small_world():
+    cm = synth.make_class_map(260, 300, 4, seed=21)
+    img, lut = synth.to_cv_image(cm), synth.identity_lut(4)
+    layers, mask = orc.compute_dists(orc.class_image_to_layers(img, lut, 4, 1.0), 1.0)
+    pose, heading = synth.default_pose(cm, seed=21)
+    pts = synth.make_scan(cm, pose, heading, seed=21, n_rings=32, n_az=256)
+    scan = orc.render_polar(pts, 1.5, ANG, 100, 25, lut, 4)
+    tab = orc.polar_table(100, 25, ANG, 1.0)
+    return dict(cm=cm, layers=layers, mask=mask, pose=pose, heading=heading, scan=scan, tab=tab, lut=lut)
+
+
+def test_local_map_equals_twin(small_world):
+    w = small_world
+    for cx, cy in [(150.3, 120.8), (2.0, 3.0), (299.6, 259.4), (-40.0, 100.0)]:
+        d, m = orc.local_map_polar(w["layers"], w["mask"], 1.0, w["tab"], cx, cy, 2.0, 1.5)
+        td, tm = twin.local_map_polar(w["layers"], w["mask"], 1.0, w["tab"], cx, cy, 2.0, 1.5)
+        assert np.array_equal(m, tm) and np.array_equal(d.view(np.uint32), td.view(np.uint32))
+    # fully off the map: everything masked, zeros
+    d, m = orc.local_map_polar(w["layers"], w["mask"], 1.0, w["tab"], -5000.0, -5000.0, 2.0, 1.5)
+    assert m.all() and not d.any()
+
+
+def test_shift_correlation_is_a_roll(small_world):
+    w = small_world
+    d, m = orc.local_map_polar(w["layers"], w["mask"], 1.0, w["tab"], w["pose"][0], w["pose"][1], 2.0, 1.5)
+    known = (1 - m).astype(np.float32)
+    cw = np.array([1.0, 0.5, 2.0, 1.25], dtype=np.float32)
+    for s in (0, 1, 3, 50, 98, 99):
+        a = orc.cost_for_shift(w["scan"], d, known, 100, 25, cw, s)
+        b = twin.cost_for_shift(w["scan"], d, known, 100, 25, cw, s)
+        assert abs(a - b) <= 1e-5 * abs(b), (s, a, b)
+
+
+def test_cost_known_answer_4x2():
+    # 4 angular x 2 radial bins, one class, one scan count at (theta=1, r=1): cost(s) = 0.01*w*m[(1-s)%4, 1]
+    scan = np.zeros((1, 2, 4), dtype=np.float32)
+    scan[0, 1, 1] = 3
+    m = np.arange(8, dtype=np.float32).reshape(1, 2, 4) + 1          # map value at (r, theta) = 1 + 4r + theta
+    known = np.ones(8, dtype=np.float32)
+    for s in range(4):
+        want = 0.01 * 2.0 * 3 * m[0, 1, (1 - s) % 4] / 3.0
+        got = orc.cost_for_shift(scan, m.reshape(1, 8), known, 4, 2, np.array([2.0], dtype=np.float32), s)
+        assert abs(got - want) < 1e-6 * want
+    known[:5] = 0                                                     # < half known -> NaN (state_particle.cpp:117-120)
+    assert math.isnan(orc.cost_for_shift(scan, m.reshape(1, 8), known, 4, 2, np.array([2.0], dtype=np.float32), 0))
+
+
+def test_search_picks_first_strict_minimum(small_world):
+    w = small_world
+    thetas, shifts = orc.search_list(100)
+    fp = orc.make_params(4, regularization=0.7, map_width=300, map_height=260)
+    st = np.zeros(3, dtype=synth.STATE_DTYPE)
+    st["init_x_px"], st["init_y_px"], st["scale"] = [w["pose"][0], 40.0, -900.0], [w["pose"][1], 200.0, 50.0], 2.0
+    st0 = st.copy()
+    wt = orc.score_all(st, fp, w["layers"], w["mask"], 1.0, w["tab"], 100, 25, w["scan"], 1.5, thetas, shifts)
+    for i in range(3):
+        d, m = orc.local_map_polar(w["layers"], w["mask"], 1.0, w["tab"], st0["init_x_px"][i], st0["init_y_px"][i], 2.0, 1.5)
+        costs = [twin.cost_for_shift(w["scan"], d, (1 - m).astype(np.float32), 100, 25, np.ones(4), s) for s in shifts]
+        if np.all(np.isnan(costs)):
+            assert st["theta"][i] == 0 and wt[i] == np.float32(1.0 / (np.float32(3.402823466e38) + np.float32(0.7)))
+            assert 0 < wt[i] < 1.2e-38                                  # the denormal weight (Appendix A.5)
+        else:
+            k = int(np.nanargmin(costs))
+            assert abs(wt[i] - 1.0 / (costs[k] + 0.7)) <= 1e-5 * wt[i]
+        assert st["have_init"][i] == 1
+
+
+# ---- normalise / resample / pose (a11-a13) --------------------------------------------------------------
+def test_normalize_known_answer():
+    w = np.array([1, 2, 3, np.nan], dtype=np.float32)
+    wn, arg, stats = orc.normalize(w, np.full(4, 0.2, dtype=np.float32))        # d = min(0.2*5, 1) = 1
+    assert np.allclose(wn, np.array([1, 2, 3, 1]) / 7.0, rtol=1e-6) and arg == 2
+    assert stats[0] == 6 and stats[1] == 3 and stats[2] == 2 and stats[3] == 1   # sum, num_valid, mean, lower std
+    wn, arg, _ = orc.normalize(w, np.zeros(4, dtype=np.float32))                 # d = 0 -> uniform
+    assert np.array_equal(wn, np.full(4, 0.25, dtype=np.float32)) and arg == 0
+    wn, _, stats = orc.normalize(np.zeros(5, dtype=np.float32), np.ones(5, dtype=np.float32))
+    assert stats[5] == 1 and np.array_equal(wn, np.full(5, 0.2, dtype=np.float32))  # all-ones fallback (:129-131)
+
+
+@pytest.mark.parametrize("n", [1, 3, 4, 7, 8, 9, 64, 1001])
+def test_normalize_equals_twin(n):
+    rng = np.random.default_rng(n)
+    w = (1.0 / (rng.random(n) * 2 + 0.7)).astype(np.float32)
+    if n > 3:
+        w[rng.integers(0, n, n // 4)] = np.nan
+    ld = rng.uniform(0, 0.4, n).astype(np.float32)
+    a, arg, _ = orc.normalize(w, ld)
+    b, targ = twin.normalize(w, ld)
+    assert np.array_equal(a.view(np.uint32), b.view(np.uint32)) and arg == targ
+
+
+def test_resample_known_answer_and_properties():
+    w = np.array([0.1, 0.2, 0.3, 0.4], dtype=np.float32)
+    assert list(orc.resample_literal(w, 0.5, 4)) == [1, 2, 3, 3]
+    assert list(orc.resample_fast(w, 0.5, 4)) == [1, 2, 3, 3]
+    rng = np.random.default_rng(8)
+    for n, M in [(1, 5), (50, 50), (300, 123), (257, 1024)]:
+        w = rng.random(n).astype(np.float32)
+        w /= w.sum()
+        u = orc.uniform_draw(n)
+        assert 0 <= u < 1
+        a, b, c = orc.resample_literal(w, u, M), orc.resample_fast(w, u, M), twin.resample_literal(w, u, M)
+        assert np.array_equal(a, b) and np.array_equal(a, c)
+        assert (np.diff(a) >= 0).all() and a.max() <= n - 1
+    # weights that sum to less than the last sample: the index clamps to N-1 (:180)
+    w = np.full(10, 0.05, dtype=np.float32)
+    assert orc.resample_fast(w, 0.9, 10)[-1] == 9 and orc.resample_literal(w, 0.9, 10)[-1] == 9
+
+
+def test_uniform_draw_is_libstdcxx_mt19937():
+    # mt19937(seed)() first output for seed 5489 is 3499211612; generate_canonical<float,24> = that / 2^32
+    assert abs(orc.uniform_draw(5489) - 3499211612 / 2 ** 32) < 1e-7
+
+
+def test_pose_known_answer():
+    st = np.zeros(4, dtype=synth.STATE_DTYPE)
+    st["init_x_px"], st["init_y_px"] = [10, 20, 30, 40], [1, 1, 3, 3]
+    st["dx_m"], st["scale"] = 1.0, 2.0                      # ml x = dx*scale + init_x
+    st["theta"] = [0.1, -0.1, 0.1, -0.1]
+    mean, cov = orc.mean_cov(st)
+    assert mean[0] == 27 and mean[1] == 2 and abs(mean[2]) < 1e-7 and mean[3] == 2
+    assert abs(cov[0, 0] - 500 / 3) < 1e-4 and abs(cov[1, 1] - 4 / 3) < 1e-6 and cov[3, 3] == 0
+    ml, _ = orc.ml_cov(st, 2)
+    assert list(ml) == [32, 3, np.float32(0.1), 2]
+
+
+# ---- regression pin ---------------------------------------------------------------------------------
+def test_cfg1_mini_fixture_reproduces():
+    g = np.load(os.path.join(GOLD, "cfg1_mini.npz"))
+    Cn = int(g["num_classes"])
+    layers, mask = orc.compute_dists(orc.class_image_to_layers(g["img"], g["lut"], Cn, 1.0), 1.0)
+    assert zlib.crc32(layers.tobytes()) == int(g["layers_crc"]) and zlib.crc32(mask.tobytes()) == int(g["mask_crc"])
+    scan = orc.render_polar(g["pts"], float(g["res"]), g["ang_res"], 100, 25, g["lut"], Cn)
+    assert np.array_equal(scan, g["scan"])
+    assert np.array_equal(orc.polar_table(100, 25, g["ang_res"], 1.0), g["tab"])
+    st = g["states"].copy()
+    fp = orc.make_params(Cn, regularization=0.7, map_width=layers.shape[1], map_height=layers.shape[2])
+    w = orc.score_all(st, fp, layers, mask, 1.0, g["tab"], 100, 25, scan, float(g["res"]), g["thetas"], g["shifts"])
+    assert np.array_equal(w.view(np.uint32), g["weights"].view(np.uint32))
+    wn, arg, _ = orc.normalize(w, g["last_dist"])
+    assert np.array_equal(wn.view(np.uint32), g["weights_norm"].view(np.uint32)) and arg == int(g["argmax"])
+    assert np.array_equal(orc.resample_fast(wn, float(g["u"]), len(st)), g["idx"])

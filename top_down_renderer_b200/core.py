@@ -66,6 +66,15 @@ class Context:
         check(self._lib.tdr_launch_count(self._h, C.byref(n)))
         return n.value
 
+    def profile_enable(self, on=True):
+        check(self._lib.tdr_profile_enable(self._h, int(bool(on))))
+
+    def profile_stage_ms(self):
+        """device ms of the last step's stages: render, score, normalise, resample (synchronises)."""
+        ms = (C.c_float * 4)()
+        check(self._lib.tdr_profile_stage_ms(self._h, ms))
+        return [float(v) for v in ms]
+
     # ---- map
     def map_set_class_image(self, img, flatten_lut, num_classes, resolution=1.0):
         img = np.ascontiguousarray(img, dtype=np.uint8)
@@ -189,6 +198,12 @@ class Context:
         check(self._lib.tdr_pf_count(self._h, C.byref(n)))
         return n.value
 
+    def pf_checkpoint(self):
+        check(self._lib.tdr_pf_checkpoint(self._h))
+
+    def pf_restore(self):
+        check(self._lib.tdr_pf_restore(self._h))
+
     def pf_get_states(self, n=None):
         n = self.pf_count() if n is None else n
         st = np.zeros(n, dtype=STATE_DTYPE)
@@ -236,6 +251,23 @@ class Context:
     def step(self, res, ang_res, n_theta, n_r, u, M):
         check(self._lib.tdr_step(self._h, C.c_float(res), C.c_float(ang_res), int(n_theta), int(n_r), C.c_float(u),
                                  C.c_int64(M)))
+
+    # ---- multi-GPU shards (device pointers; the host layer issues the all-gather)
+    def pf_export_shard(self, dev_ptr, capacity_floats, with_weights=True):
+        check(self._lib.tdr_pf_export_shard(self._h, C.c_void_p(dev_ptr), C.c_int64(capacity_floats), int(with_weights)))
+
+    def pf_update_gathered(self, dev_ptr, n_ranks, n_local, u, M, i0, i1):
+        check(self._lib.tdr_pf_update_gathered(self._h, C.c_void_p(dev_ptr), int(n_ranks), C.c_int64(n_local),
+                                               C.c_float(u), C.c_int64(M), C.c_int64(i0), C.c_int64(i1)))
+
+    def pf_pose_gathered(self, dev_ptr, n_ranks, n_local, want_ml=True):
+        mean = np.zeros(4, dtype=np.float32)
+        cov = np.zeros(16, dtype=np.float32)
+        ml = np.zeros(4, dtype=np.float32)
+        cov_ml = np.zeros(16, dtype=np.float32)
+        check(self._lib.tdr_pf_pose_gathered(self._h, C.c_void_p(dev_ptr), int(n_ranks), C.c_int64(n_local), _pf(mean),
+                                             _pf(cov), _pf(ml) if want_ml else None, _pf(cov_ml) if want_ml else None))
+        return mean, cov.reshape(4, 4), ml, cov_ml.reshape(4, 4)
 
     # ---- grid
     def grid_costs(self, centers_xy, scale, res, shifts, want=True):

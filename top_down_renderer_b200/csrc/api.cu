@@ -56,6 +56,29 @@ __global__ void k_soa_to_aos(SoA s, long long n, uint32_t* __restrict__ aos) {
   }
 }
 
+// multi-GPU shard block: TDR_SHARD_ROWS rows of n floats — weight, init_x, init_y, dx, dy, theta, scale,
+// have_init (0/1 as float), last_dist.  One block per rank is what the all-gather moves.
+struct ShardSrc { const float *w, *ix, *iy, *dx, *dy, *th, *sc, *ld; const uint8_t* hi; };
+__global__ void k_pack_shard(ShardSrc s, long long n, float* __restrict__ out) {
+  for (long long i = (long long)blockIdx.x * blockDim.x + threadIdx.x; i < n; i += (long long)gridDim.x * blockDim.x) {
+    out[i] = s.w ? s.w[i] : 0.f;
+    out[n + i] = s.ix[i]; out[2 * n + i] = s.iy[i]; out[3 * n + i] = s.dx[i]; out[4 * n + i] = s.dy[i];
+    out[5 * n + i] = s.th[i]; out[6 * n + i] = s.sc[i]; out[7 * n + i] = s.hi[i] ? 1.f : 0.f; out[8 * n + i] = s.ld[i];
+  }
+}
+struct ShardDst { float *w, *ix, *iy, *dx, *dy, *th, *sc, *ld; uint8_t* hi; };
+__global__ void k_unpack_all(const float* __restrict__ in, int ranks, long long n_local, ShardDst d) {
+  const long long N = (long long)ranks * n_local;
+  for (long long j = (long long)blockIdx.x * blockDim.x + threadIdx.x; j < N; j += (long long)gridDim.x * blockDim.x) {
+    const long long g = j / n_local, i = j - g * n_local;
+    const float* b = in + g * TDR_SHARD_ROWS * n_local;
+    if (d.w) d.w[j] = b[i];
+    d.ix[j] = b[n_local + i]; d.iy[j] = b[2 * n_local + i]; d.dx[j] = b[3 * n_local + i]; d.dy[j] = b[4 * n_local + i];
+    d.th[j] = b[5 * n_local + i]; d.sc[j] = b[6 * n_local + i]; d.hi[j] = b[7 * n_local + i] != 0.f ? 1 : 0;
+    d.ld[j] = b[8 * n_local + i];
+  }
+}
+
 static int grid_for(tdr_ctx* ctx, long long n, int threads = 256) {
   long long b = (n + threads - 1) / threads;
   long long cap = (long long)ctx->sm_count * 8;
@@ -117,8 +140,9 @@ void tdr_destroy(tdr_ctx* c) {
                          &c->prefix, &c->idx, &c->scal, &c->pose_tmp, &c->grid_centers, &c->grid_costs,
                          &c->grid_shifts, &c->d_cw};
   for (auto* b : bufs) b->release();
-  c->part[0].release(); c->part[1].release();
+  c->part[0].release(); c->part[1].release(); c->ckpt.release();
   c->pin.release();
+  for (int k = 0; k <= TDR_N_STAGES; k++) if (c->stage_ev[k]) cudaEventDestroy(c->stage_ev[k]);
   if (c->stream) cudaStreamDestroy(c->stream);
   delete c;
 }
@@ -126,6 +150,22 @@ void tdr_destroy(tdr_ctx* c) {
 int tdr_sync(tdr_ctx* ctx) { CTX_CHECK(ctx); TDR_CUDA(cudaStreamSynchronize(ctx->stream)); return TDR_OK; }
 void* tdr_stream(tdr_ctx* ctx) { return ctx ? (void*)ctx->stream : nullptr; }
 int tdr_launch_count(tdr_ctx* ctx, int64_t* n) { TDR_REQUIRE(ctx && n, TDR_EINVAL, "null argument"); *n = ctx->launches; return TDR_OK; }
+
+int tdr_profile_enable(tdr_ctx* ctx, int on) {
+  CTX_CHECK(ctx);
+  if (on && !ctx->stage_ev[0])
+    for (int k = 0; k <= TDR_N_STAGES; k++) TDR_CUDA(cudaEventCreate(&ctx->stage_ev[k]));
+  ctx->profiling = on != 0; ctx->stage_valid = false;
+  return TDR_OK;
+}
+int tdr_profile_stage_ms(tdr_ctx* ctx, float ms[TDR_N_STAGES]) {
+  CTX_CHECK(ctx);
+  TDR_REQUIRE(ms, TDR_EINVAL, "null output");
+  TDR_REQUIRE(ctx->profiling && ctx->stage_valid, TDR_ESTATE, "no profiled step (tdr_profile_enable, then tdr_step / tdr_pf_update)");
+  TDR_CUDA(cudaStreamSynchronize(ctx->stream));
+  for (int k = 0; k < TDR_N_STAGES; k++) TDR_CUDA(cudaEventElapsedTime(&ms[k], ctx->stage_ev[k], ctx->stage_ev[k + 1]));
+  return TDR_OK;
+}
 
 // ---- map ------------------------------------------------------------------------------------------
 int tdr_map_set_class_image(tdr_ctx* ctx, const uint8_t* img, int h_img, int w_img, int stride,
@@ -233,6 +273,7 @@ static int render_polar_resident(tdr_ctx* ctx, float res, float ang_res, int n_t
 
 int tdr_scan_render_polar(tdr_ctx* ctx, float res, float ang_res, int n_theta, int n_r, float* imgs) {
   CTX_CHECK(ctx);
+  stage_mark(ctx, TDR_STAGE_RENDER);
   if (int e = render_polar_resident(ctx, res, ang_res, n_theta, n_r)) return e;
   if (imgs) {
     TDR_CUDA(cudaMemcpyAsync(imgs, ctx->scan_img.p, (size_t)ctx->scan_C * n_theta * n_r * 4, cudaMemcpyDeviceToHost, ctx->stream));
@@ -321,6 +362,34 @@ int tdr_pf_get_states(tdr_ctx* ctx, tdr_state* states, int64_t n) {
   return TDR_OK;
 }
 
+static int copy_particles(tdr_ctx* ctx, Particles& dst, Particles& src) {
+  if (int e = dst.reserve(src.n)) return e;
+  DevBuf* d[] = {&dst.init_x, &dst.init_y, &dst.dx, &dst.dy, &dst.theta, &dst.scale, &dst.last_dist};
+  DevBuf* s[] = {&src.init_x, &src.init_y, &src.dx, &src.dy, &src.theta, &src.scale, &src.last_dist};
+  for (int k = 0; k < 7; k++)
+    TDR_CUDA(cudaMemcpyAsync(d[k]->p, s[k]->p, (size_t)src.n * 4, cudaMemcpyDeviceToDevice, ctx->stream));
+  TDR_CUDA(cudaMemcpyAsync(dst.have_init.p, src.have_init.p, (size_t)src.n, cudaMemcpyDeviceToDevice, ctx->stream));
+  dst.n = src.n;
+  return TDR_OK;
+}
+
+int tdr_pf_checkpoint(tdr_ctx* ctx) {
+  CTX_CHECK(ctx);
+  Particles& pt = ctx->part[ctx->cur];
+  TDR_REQUIRE(pt.n > 0, TDR_ESTATE, "no particles");
+  if (int e = copy_particles(ctx, ctx->ckpt, pt)) return e;
+  ctx->ckpt_uninit = ctx->n_uninit;
+  return TDR_OK;
+}
+
+int tdr_pf_restore(tdr_ctx* ctx) {
+  CTX_CHECK(ctx);
+  TDR_REQUIRE(ctx->ckpt.n > 0, TDR_ESTATE, "no checkpoint");
+  if (int e = copy_particles(ctx, ctx->part[ctx->cur], ctx->ckpt)) return e;
+  ctx->n_uninit = ctx->ckpt_uninit; ctx->have_argmax = false;
+  return TDR_OK;
+}
+
 int tdr_pf_count(tdr_ctx* ctx, int64_t* n) { TDR_REQUIRE(ctx && n, TDR_EINVAL, "null argument"); *n = ctx->part[ctx->cur].n; return TDR_OK; }
 
 static int copy_out_floats(tdr_ctx* ctx, float* dst, const void* src, int64_t n) {
@@ -332,6 +401,7 @@ static int copy_out_floats(tdr_ctx* ctx, float* dst, const void* src, int64_t n)
 int tdr_pf_score(tdr_ctx* ctx, float res, float* weights_out) {
   CTX_CHECK(ctx);
   if (int e = scan_pack(ctx)) return e;
+  stage_mark(ctx, TDR_STAGE_SCORE);
   if (int e = score_particles(ctx, res)) return e;
   ctx->ld_override = nullptr;
   if (weights_out) return copy_out_floats(ctx, weights_out, ctx->weights.p, ctx->n_weights);
@@ -368,7 +438,7 @@ int tdr_pf_normalize(tdr_ctx* ctx, int64_t* argmax_out, float* stats) {
   TDR_REQUIRE(ctx->ld_override || ctx->n_weights == ctx->part[ctx->cur].n, TDR_ESTATE,
               "weights (%lld) and particles (%lld) differ", (long long)ctx->n_weights, (long long)ctx->part[ctx->cur].n);
   if (int e = normalize(ctx)) return e;
-  ctx->argmax_buf = ctx->cur;
+  if (!ctx->ld_override) { if (int e = cache_ml_state(ctx, ctx->part[ctx->cur])) return e; }
   if (argmax_out || stats) {
     float host[16];
     TDR_CUDA(cudaMemcpyAsync(host, ctx->scal.p, 16 * 4, cudaMemcpyDeviceToHost, ctx->stream));
@@ -383,7 +453,8 @@ int tdr_pf_normalize(tdr_ctx* ctx, int64_t* argmax_out, float* stats) {
 
 int tdr_pf_resample(tdr_ctx* ctx, float u, int64_t M, int32_t* idx_out) {
   CTX_CHECK(ctx);
-  if (int e = resample(ctx, u, M, 0, M, true)) return e;
+  if (int e = resample(ctx, u, M, 0, M, &ctx->part[ctx->cur], &ctx->part[ctx->cur ^ 1])) return e;
+  ctx->cur ^= 1;
   if (idx_out) {
     TDR_CUDA(cudaMemcpyAsync(idx_out, ctx->idx.p, (size_t)M * 4, cudaMemcpyDeviceToHost, ctx->stream));
     TDR_CUDA(cudaStreamSynchronize(ctx->stream));
@@ -393,23 +464,95 @@ int tdr_pf_resample(tdr_ctx* ctx, float u, int64_t M, int32_t* idx_out) {
 
 int tdr_pf_pose(tdr_ctx* ctx, float mean[4], float cov_mean[16], float ml[4], float cov_ml[16]) {
   CTX_CHECK(ctx);
-  return pose(ctx, mean, cov_mean, ml, cov_ml);
+  return pose_of(ctx, ctx->part[ctx->cur], mean, cov_mean, ml, cov_ml);
+}
+
+static int update_resident(tdr_ctx* ctx, float res, float u, int64_t M) {
+  if (int e = scan_pack(ctx)) return e;
+  stage_mark(ctx, TDR_STAGE_SCORE);
+  if (int e = score_particles(ctx, res)) return e;
+  ctx->ld_override = nullptr;
+  stage_mark(ctx, TDR_STAGE_NORMALIZE);
+  if (int e = normalize(ctx)) return e;
+  if (int e = cache_ml_state(ctx, ctx->part[ctx->cur])) return e;
+  stage_mark(ctx, TDR_STAGE_RESAMPLE);
+  if (int e = resample(ctx, u, M, 0, M, &ctx->part[ctx->cur], &ctx->part[ctx->cur ^ 1])) return e;
+  ctx->cur ^= 1;
+  stage_mark(ctx, TDR_N_STAGES);
+  ctx->stage_valid = ctx->profiling;
+  return TDR_OK;
 }
 
 int tdr_pf_update(tdr_ctx* ctx, float res, float u, int64_t M) {
   CTX_CHECK(ctx);
-  if (int e = scan_pack(ctx)) return e;
-  if (int e = score_particles(ctx, res)) return e;
-  ctx->ld_override = nullptr;
-  if (int e = normalize(ctx)) return e;
-  ctx->argmax_buf = ctx->cur;
-  return resample(ctx, u, M, 0, M, true);
+  stage_mark(ctx, TDR_STAGE_RENDER);   // empty render stage
+  return update_resident(ctx, res, u, M);
 }
 
 int tdr_step(tdr_ctx* ctx, float res, float ang_res, int n_theta, int n_r, float u, int64_t M) {
   CTX_CHECK(ctx);
+  stage_mark(ctx, TDR_STAGE_RENDER);
   if (int e = render_polar_resident(ctx, res, ang_res, n_theta, n_r)) return e;
-  return tdr_pf_update(ctx, res, u, M);
+  return update_resident(ctx, res, u, M);
+}
+
+// ---- multi-GPU (particle shards; the collective itself is issued by the host layer) ---------------------
+int tdr_pf_export_shard(tdr_ctx* ctx, void* dev_out, int64_t capacity_floats, int with_weights) {
+  CTX_CHECK(ctx);
+  Particles& pt = ctx->part[ctx->cur];
+  TDR_REQUIRE(pt.n > 0, TDR_ESTATE, "no particles");
+  TDR_REQUIRE(dev_out && capacity_floats >= pt.n * TDR_SHARD_ROWS, TDR_EINVAL, "shard buffer too small");
+  TDR_REQUIRE(!with_weights || ctx->n_weights == pt.n, TDR_ESTATE, "weights (%lld) and particles (%lld) differ",
+              (long long)ctx->n_weights, (long long)pt.n);
+  ShardSrc s; s.w = with_weights ? ctx->weights.as<float>() : nullptr;
+  s.ix = pt.init_x.as<float>(); s.iy = pt.init_y.as<float>(); s.dx = pt.dx.as<float>(); s.dy = pt.dy.as<float>();
+  s.th = pt.theta.as<float>(); s.sc = pt.scale.as<float>(); s.ld = pt.last_dist.as<float>(); s.hi = pt.have_init.as<uint8_t>();
+  k_pack_shard<<<grid_for(ctx, pt.n), 256, 0, ctx->stream>>>(s, pt.n, reinterpret_cast<float*>(dev_out));
+  count_launch(ctx);
+  TDR_CUDA(cudaGetLastError());
+  return TDR_OK;
+}
+
+static int unpack_all(tdr_ctx* ctx, const void* dev_all, int n_ranks, int64_t n_local, bool weights) {
+  const int64_t N = (int64_t)n_ranks * n_local;
+  TDR_REQUIRE(dev_all && n_ranks >= 1 && n_local > 0 && N < (1ll << 31), TDR_EINVAL, "bad gathered block");
+  if (int e = ctx->all.reserve(N)) return e;
+  if (weights) { if (int e = ctx->weights.reserve((size_t)N * 4)) return e; }
+  Particles& a = ctx->all;
+  ShardDst d; d.w = weights ? ctx->weights.as<float>() : nullptr;
+  d.ix = a.init_x.as<float>(); d.iy = a.init_y.as<float>(); d.dx = a.dx.as<float>(); d.dy = a.dy.as<float>();
+  d.th = a.theta.as<float>(); d.sc = a.scale.as<float>(); d.ld = a.last_dist.as<float>(); d.hi = a.have_init.as<uint8_t>();
+  k_unpack_all<<<grid_for(ctx, N), 256, 0, ctx->stream>>>(reinterpret_cast<const float*>(dev_all), n_ranks, n_local, d);
+  count_launch(ctx);
+  TDR_CUDA(cudaGetLastError());
+  a.n = N;
+  if (weights) ctx->n_weights = N;
+  return TDR_OK;
+}
+
+int tdr_pf_update_gathered(tdr_ctx* ctx, const void* dev_all, int n_ranks, int64_t n_local, float u, int64_t M,
+                           int64_t i0, int64_t i1) {
+  CTX_CHECK(ctx);
+  stage_mark(ctx, TDR_STAGE_NORMALIZE);
+  if (int e = unpack_all(ctx, dev_all, n_ranks, n_local, true)) return e;
+  ctx->ld_override = ctx->all.last_dist.as<float>();
+  int e = normalize(ctx);
+  ctx->ld_override = nullptr;
+  if (e) return e;
+  if (int e2 = cache_ml_state(ctx, ctx->all)) return e2;
+  stage_mark(ctx, TDR_STAGE_RESAMPLE);
+  if (int e2 = resample(ctx, u, M, i0, i1, &ctx->all, &ctx->part[ctx->cur ^ 1])) return e2;
+  ctx->cur ^= 1;
+  stage_mark(ctx, TDR_N_STAGES);
+  ctx->stage_valid = ctx->profiling;
+  return TDR_OK;
+}
+
+int tdr_pf_pose_gathered(tdr_ctx* ctx, const void* dev_all, int n_ranks, int64_t n_local, float mean[4],
+                         float cov_mean[16], float ml[4], float cov_ml[16]) {
+  CTX_CHECK(ctx);
+  if (int e = unpack_all(ctx, dev_all, n_ranks, n_local, false)) return e;
+  return pose_of(ctx, ctx->all, mean, cov_mean, ml, cov_ml);
 }
 
 // ---- exhaustive grid --------------------------------------------------------------------------------

@@ -96,8 +96,17 @@ static PartPtrs ptrs_of(const Particles& p) {
   return q;
 }
 
-int pose(tdr_ctx* ctx, float* mean, float* cov_mean, float* ml, float* cov_ml) {
-  Particles& pt = ctx->part[ctx->cur];
+// max_likelihood_particle_->mlState() (particle_filter.cpp:145-147,222-224): cached when the arg-max is
+// taken, because the particle it points at belongs to the pre-resample set.
+int cache_ml_state(tdr_ctx* ctx, const Particles& src) {
+  k_pose_ml<<<1, 1, 0, ctx->stream>>>(ctx->scal.as<float>(), ptrs_of(src), src.n);
+  count_launch(ctx);
+  TDR_CUDA(cudaGetLastError());
+  ctx->have_argmax = true;
+  return TDR_OK;
+}
+
+int pose_of(tdr_ctx* ctx, Particles& pt, float* mean, float* cov_mean, float* ml, float* cov_ml) {
   const long long n = pt.n;
   TDR_REQUIRE(n > 0, TDR_ESTATE, "no particles");
   if (int e = ctx->scal.reserve(SC_TOTAL * 4)) return e;
@@ -121,9 +130,6 @@ int pose(tdr_ctx* ctx, float* mean, float* cov_mean, float* ml, float* cov_ml) {
   }
   if (ml || cov_ml) {
     TDR_REQUIRE(ctx->have_argmax, TDR_ESTATE, "max-likelihood pose needs a previous tdr_pf_normalize");
-    Particles& mlp = ctx->part[ctx->argmax_buf];
-    k_pose_ml<<<1, 1, 0, ctx->stream>>>(scal, ptrs_of(mlp), mlp.n);
-    count_launch(ctx);
     if (cov_ml) {
       k_cov_accum<<<blocks, 256, 0, ctx->stream>>>(p, n, scal, SC_POSE + 4, dacc + 12);
       k_cov_finish<<<1, 1, 0, ctx->stream>>>(dacc + 12, n, scal, SC_POSE + 32);

@@ -118,9 +118,11 @@ struct tdr_ctx {
   tdr::DevBuf d_search_thetas, d_search_shifts;
   tdr::Particles part[2];    // ping-pong (particles_ / new_particles_, particle_filter.cpp:187)
   int cur = 0;
+  tdr::Particles ckpt;       // device-side snapshot of the particle set (tdr_pf_checkpoint / tdr_pf_restore)
+  int64_t ckpt_uninit = 0;
   int64_t n_uninit = 0;      // particles still without a heading (have_init == false)
   tdr::DevBuf d_cw;          // class weights (16 floats)
-  int argmax_buf = 0;        // particle buffer the last arg-max indexes into (max_likelihood_particle_)
+  tdr::Particles all;        // multi-GPU: the all-gathered particle set (N = ranks * n_local) in global order
   tdr::DevBuf weights;       // raw -> normalised in place
   int64_t n_weights = 0;
   const float* ld_override = nullptr;  // device last_dist aligned with an all-gathered weight vector (multi-GPU)
@@ -131,6 +133,11 @@ struct tdr_ctx {
   tdr::PinBuf pin;           // pinned staging
   int64_t argmax = 0;
   bool have_argmax = false;
+
+  // ---- stage timers (tdr_profile_enable): events bracket render / score / normalise / resample
+  bool profiling = false;
+  cudaEvent_t stage_ev[TDR_N_STAGES + 1] = {};
+  bool stage_valid = false;
 
   // ---- grid (cfg4)
   tdr::DevBuf grid_centers, grid_costs, grid_shifts;
@@ -151,6 +158,7 @@ enum {
 
 
 inline void count_launch(tdr_ctx* c, int k = 1) { c->launches += k; }
+inline void stage_mark(tdr_ctx* c, int k) { if (c->profiling) cudaEventRecord(c->stage_ev[k], c->stream); }
 
 // map_build.cu
 int map_set_class_image(tdr_ctx*, const uint8_t*, int, int, int, const int32_t*, int, int, float);
@@ -169,9 +177,10 @@ int local_cart(tdr_ctx*, float cx, float cy, float rot, float res, int out_rows,
 // weights.cu
 int normalize(tdr_ctx*);
 int build_prefix(tdr_ctx*);
-int resample(tdr_ctx*, float u, long long M, long long i0, long long i1, bool gather);
+int resample(tdr_ctx*, float u, long long M, long long i0, long long i1, Particles* src, Particles* dst);
+int cache_ml_state(tdr_ctx*, const Particles& src);
 int exact_sums(tdr_ctx*, const float* const* cols, long long n, int ncols, float* totals_dev);
 // pose.cu
-int pose(tdr_ctx*, float* mean, float* cov_mean, float* ml, float* cov_ml);
+int pose_of(tdr_ctx*, Particles& pt, float* mean, float* cov_mean, float* ml, float* cov_ml);
 int grid_best(tdr_ctx*, float* best_cost, long long* best_index);
 }

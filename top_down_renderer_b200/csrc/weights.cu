@@ -360,7 +360,6 @@ int normalize(tdr_ctx* ctx) {
   k_argmax_store<<<1, 1, 0, ctx->stream>>>(u64 + 3, scal);
   count_launch(ctx, 2);
   TDR_CUDA(cudaGetLastError());
-  ctx->have_argmax = true;
   return TDR_OK;
 }
 
@@ -388,30 +387,31 @@ int build_prefix(tdr_ctx* ctx) {
   return launch_seq(ctx, jobs, 1);
 }
 
-// outputs [i0, i1) of the M systematic samples; gathers states from the current particle set into the
-// other buffer when `gather` (single-GPU: i0 = 0, i1 = M)
-int resample(tdr_ctx* ctx, float u, long long M, long long i0, long long i1, bool gather) {
+// outputs [i0, i1) of the M systematic samples over the resident weights; when src/dst are given the
+// states of the drawn particles are gathered from *src into *dst (dst->n = i1 - i0).
+// Single GPU: i0 = 0, i1 = M, src = particles_, dst = new_particles_ (particle_filter.cpp:185-187).
+int resample(tdr_ctx* ctx, float u, long long M, long long i0, long long i1, Particles* src, Particles* dst) {
   const long long n = ctx->n_weights;
   TDR_REQUIRE(M > 0 && M < (1ll << 31) && i0 >= 0 && i1 <= M && i0 < i1, TDR_EINVAL, "bad resample range");
   if (int e = build_prefix(ctx)) return e;
   const long long cnt = i1 - i0;
   if (int e = ctx->idx.reserve((size_t)cnt * 4)) return e;
   GatherPtrs g; memset(&g, 0, sizeof(g));
-  tdr::Particles& src = ctx->part[ctx->cur];
-  tdr::Particles& dst = ctx->part[ctx->cur ^ 1];
-  if (gather) {
-    TDR_REQUIRE(src.n > 0, TDR_ESTATE, "no particles to gather");
-    if (int e = dst.reserve(cnt)) return e;
-    g.ix = src.init_x.as<float>(); g.iy = src.init_y.as<float>(); g.dx = src.dx.as<float>(); g.dy = src.dy.as<float>();
-    g.th = src.theta.as<float>(); g.sc = src.scale.as<float>(); g.ld = src.last_dist.as<float>(); g.hi = src.have_init.as<uint8_t>();
-    g.oix = dst.init_x.as<float>(); g.oiy = dst.init_y.as<float>(); g.odx = dst.dx.as<float>(); g.ody = dst.dy.as<float>();
-    g.oth = dst.theta.as<float>(); g.osc = dst.scale.as<float>(); g.old = dst.last_dist.as<float>(); g.ohi = dst.have_init.as<uint8_t>();
+  long long src_n = 0;
+  if (src && dst) {
+    TDR_REQUIRE(src->n > 0, TDR_ESTATE, "no particles to gather");
+    if (int e = dst->reserve(cnt)) return e;
+    g.ix = src->init_x.as<float>(); g.iy = src->init_y.as<float>(); g.dx = src->dx.as<float>(); g.dy = src->dy.as<float>();
+    g.th = src->theta.as<float>(); g.sc = src->scale.as<float>(); g.ld = src->last_dist.as<float>(); g.hi = src->have_init.as<uint8_t>();
+    g.oix = dst->init_x.as<float>(); g.oiy = dst->init_y.as<float>(); g.odx = dst->dx.as<float>(); g.ody = dst->dy.as<float>();
+    g.oth = dst->theta.as<float>(); g.osc = dst->scale.as<float>(); g.old = dst->last_dist.as<float>(); g.ohi = dst->have_init.as<uint8_t>();
+    src_n = src->n;
   }
   int blocks = (int)((cnt + 255) / 256 < ctx->sm_count * 8 ? (cnt + 255) / 256 : ctx->sm_count * 8);
-  k_resample<<<blocks, 256, 0, ctx->stream>>>(ctx->prefix.as<float>(), n, u, M, i0, i1, ctx->idx.as<int32_t>(), g, src.n);
+  k_resample<<<blocks, 256, 0, ctx->stream>>>(ctx->prefix.as<float>(), n, u, M, i0, i1, ctx->idx.as<int32_t>(), g, src_n);
   count_launch(ctx);
   TDR_CUDA(cudaGetLastError());
-  if (gather) { dst.n = cnt; ctx->cur ^= 1; }
+  if (src && dst) dst->n = cnt;
   return TDR_OK;
 }
 

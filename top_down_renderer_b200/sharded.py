@@ -1,0 +1,101 @@
+"""Particle shards across the GPUs of one box.
+
+One process per GPU (torch.distributed, NCCL over NVLink/NVSwitch).  Rank g owns particles
+[g*n_local, (g+1)*n_local); the map, the polar table and the scan are replicated (the scan is
+rasterised redundantly on every rank — cheaper than a broadcast).  Per step there is exactly ONE
+collective: an all-gather of each rank's shard block (raw weight + the 8 state rows per particle,
+36 B/particle).  Every rank then normalises the N weights in GLOBAL order and builds the order-exact
+prefix redundantly, so weights and resampled indices are bit-identical for every world size, draws its
+own slice [i0, i1) of the M systematic samples and gathers those states out of the gathered block.
+
+The reference has no counterpart (its only parallelism is for_each(par) over particles,
+particle_filter.cpp:104); the semantics are those of ParticleFilter::update (:94-189) on the
+concatenated particle set.
+"""
+from __future__ import annotations
+
+SHARD_ROWS = 9   # TDR_SHARD_ROWS (include/tdr.h)
+
+
+def shard_range(n_total: int, rank: int, world: int):
+    """particles owned by `rank` when n_total particles are dealt in contiguous, near-equal shards"""
+    base, rem = divmod(n_total, world)
+    lo = rank * base + min(rank, rem)
+    return lo, lo + base + (1 if rank < rem else 0)
+
+
+def sample_slice(M: int, rank: int, world: int):
+    """outputs [i0, i1) of the M systematic samples drawn by `rank` (contiguous; systematic resampling is
+    monotone, so a contiguous output slice reads a contiguous source range)"""
+    return shard_range(M, rank, world)
+
+
+class ShardedFilter:
+    """ParticleFilter::update over particle shards.  `ctx` holds this rank's shard; `stream` is the
+    torch.cuda.ExternalStream wrapping ctx.stream so the NCCL collective is ordered with the kernels."""
+
+    def __init__(self, ctx, stream, rank: int, world: int, group=None):
+        import torch
+        self.torch, self.ctx, self.stream, self.rank, self.world, self.group = torch, ctx, stream, rank, world, group
+        self.send = self.recv = None
+
+    def _buffers(self, n_local):
+        torch = self.torch
+        if self.send is None or self.send.numel() != SHARD_ROWS * n_local:
+            dev = torch.device("cuda", self.ctx.device)
+            self.send = torch.empty(SHARD_ROWS * n_local, dtype=torch.float32, device=dev)
+            self.recv = torch.empty(self.world * SHARD_ROWS * n_local, dtype=torch.float32, device=dev)
+
+    def _all_gather(self, n_local, with_weights):
+        import torch.distributed as dist
+        self._buffers(n_local)
+        self.ctx.pf_export_shard(self.send.data_ptr(), self.send.numel(), with_weights)
+        dist.all_gather_into_tensor(self.recv, self.send, group=self.group)
+
+    def step(self, res, ang_res, n_theta, n_r, u, M_total):
+        """render + score the local shard, all-gather, normalise globally, resample this rank's slice"""
+        ctx = self.ctx
+        n_local = ctx.pf_count()
+        i0, i1 = sample_slice(M_total, self.rank, self.world)
+        with self.torch.cuda.stream(self.stream):
+            ctx.scan_render_polar(res, ang_res, n_theta, n_r, want=False)
+            ctx.pf_score(res, want=False)
+            self._all_gather(n_local, True)
+            ctx.pf_update_gathered(self.recv.data_ptr(), self.world, n_local, u, M_total, i0, i1)
+
+    def pose(self, want_ml=True):
+        """mean / covariance / ML pose over the whole (all-gathered) resampled set; needs equal shards"""
+        ctx = self.ctx
+        n_local = ctx.pf_count()
+        with self.torch.cuda.stream(self.stream):
+            self._all_gather(n_local, False)
+            return ctx.pf_pose_gathered(self.recv.data_ptr(), self.world, n_local, want_ml)
+
+
+# ---- layout helpers (numpy): the shard block exactly as k_pack_shard / k_unpack_all lay it out.
+# Used by the CPU (gloo) tests of the protocol and as executable documentation of the wire format.
+_ROWS = ("weight", "init_x_px", "init_y_px", "dx_m", "dy_m", "theta", "scale", "have_init", "last_dist")
+
+
+def pack_block_numpy(states, last_dist, weights):
+    import numpy as np
+    n = len(states)
+    blk = np.empty((SHARD_ROWS, n), dtype=np.float32)
+    blk[0] = weights if weights is not None else 0
+    for k, name in enumerate(_ROWS[1:7], start=1):
+        blk[k] = states[name]
+    blk[7] = (states["have_init"] != 0).astype(np.float32)
+    blk[8] = last_dist
+    return blk.reshape(-1)
+
+
+def unpack_blocks_numpy(gathered, world, n_local, state_dtype):
+    """gathered: world blocks in rank order -> (states[N], last_dist[N], weights[N]) in global particle order"""
+    import numpy as np
+    g = np.asarray(gathered, dtype=np.float32).reshape(world, SHARD_ROWS, n_local)
+    N = world * n_local
+    st = np.zeros(N, dtype=state_dtype)
+    for k, name in enumerate(_ROWS[1:7], start=1):
+        st[name] = g[:, k, :].reshape(N)
+    st["have_init"] = (g[:, 7, :].reshape(N) != 0).astype(np.uint8)
+    return st, g[:, 8, :].reshape(N).copy(), g[:, 0, :].reshape(N).copy()
