@@ -73,6 +73,10 @@ int tdr_launch_count(tdr_ctx* ctx, int64_t* n);  /* kernels launched by this con
  * 513-548, as CUDA events on the context stream).  When enabled, tdr_step / tdr_pf_update bracket
  * render, score, normalise and resample; tdr_profile_stage_ms synchronises and returns the last step's
  * device time per stage in ms. */
+/* theta-search / grid implementation: 0 = auto (tensor cores from 4096 hypotheses up), 1 = CUDA cores only,
+ * 2 = tcgen05 gather-GEMM whenever its preconditions hold (<= 111 shifts, scan counts <= 2048, class weights
+ * within fp16 range); both implement state_particle.cpp:112-219 to the same 1e-5 bar. */
+int tdr_set_score_impl(tdr_ctx* ctx, int impl);
 #define TDR_N_STAGES 4
 enum { TDR_STAGE_RENDER = 0, TDR_STAGE_SCORE = 1, TDR_STAGE_NORMALIZE = 2, TDR_STAGE_RESAMPLE = 3 };
 int tdr_profile_enable(tdr_ctx* ctx, int on);

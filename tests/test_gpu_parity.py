@@ -453,3 +453,81 @@ def test_checkpoint_restore_and_stage_timers(world):
     c.step(4.0, ANG_RES, N_THETA, N_R, u, 2000)
     assert np.array_equal(c.pf_get_states(), a)          # replay from the same prior is deterministic
     c.close()
+
+
+# ---- tcgen05 gather-GEMM score path (score_mma.cu): same bars as the CUDA-core kernels ---------------------------
+@pytest.fixture()
+def mma_ctx(world):
+    c = make_ctx(world)
+    c.set_score_impl(2)
+    yield c
+    c.close()
+
+
+def test_mma_theta_search_weights_and_headings(world, mma_ctx):
+    st, ld = synth.particles_global(3000, world.class_map)
+    st["init_x_px"][:7] = -900                       # far off the map: every cell masked -> all-NaN -> denormal weight
+    got, want, st_o = _score_both(world, mma_ctx, st, ld, 4.0)
+    e = rel_err(got, want)
+    assert np.isfinite(e).all()
+    assert e.max() <= WEIGHT_RTOL, e.max()
+    st_g = mma_ctx.pf_get_states()
+    assert (st_g["have_init"] == 1).all()
+    same = st_g["theta"] == st_o["theta"]
+    assert same.mean() > 0.995, same.mean()
+    assert (got[:7] > 0).all() and (got[:7] < 1.2e-38).all()
+
+
+@pytest.mark.parametrize("res", [0.5, 1.7])
+def test_mma_other_radial_resolutions(world, mma_ctx, res):
+    st, ld = synth.particles_global(700, world.class_map, seed=int(res * 10))
+    got, want, _ = _score_both(world, mma_ctx, st, ld, res)
+    e = rel_err(got, want)
+    assert np.isfinite(e).all() and e.max() <= WEIGHT_RTOL, e.max()
+
+
+def test_mma_mixed_init_flags_and_gates(world):
+    wd = world
+    c = make_ctx(wd)
+    c.set_score_impl(2)
+    c.pf_set_params(wd.C, regularization=0.15, class_weights=[1.0, 0.5, 2.0, 1.25], force_on_map=True, fixed_scale=-1.0)
+    st, ld = synth.particles_tracking(900, wd.pose, wd.heading)
+    st["have_init"][::3] = 0
+    st["init_x_px"][:30] = -10
+    st["scale"][30:60] = 0.5
+    c.scan_set_polar_images(wd.scan)
+    c.pf_set_states(st, ld)
+    got = c.pf_score(4.0)
+    fp = orc.make_params(wd.C, regularization=0.15, class_weights=[1.0, 0.5, 2.0, 1.25], force_on_map=True,
+                         fixed_scale=-1.0, map_width=wd.cols, map_height=wd.rows)
+    st_o = st.copy()
+    want = orc.score_all(st_o, fp, wd.layers, wd.mask, 1.0, wd.tab, N_THETA, N_R, wd.scan, 4.0, wd.thetas, wd.shifts)
+    st_g = c.pf_get_states()
+    c.close()
+    assert (got[:60] == 0).all() and (want[:60] == 0).all()
+    assert rel_err(got, want).max() <= WEIGHT_RTOL
+    assert np.array_equal(st_g["have_init"], st_o["have_init"])
+
+
+def test_mma_grid_costs_100_shifts(world, mma_ctx):
+    centers = synth.grid_centers(world.h, world.w, 25)[:1000]
+    shifts = np.arange(100, dtype=np.int32)
+    mma_ctx.scan_set_polar_images(world.scan)
+    got = mma_ctx.grid_costs(centers, 2.0, 4.0, shifts)
+    want = orc.cost_grid(centers, 2.0, world.fp, world.layers, world.mask, 1.0, world.tab, N_THETA, N_R, world.scan, 4.0, shifts)
+    e = rel_err(got, want)
+    assert np.isfinite(e).all() and e.max() <= WEIGHT_RTOL, e.max()
+
+
+def test_mma_matches_cuda_core_path(world):
+    st, ld = synth.particles_global(5000, world.class_map, seed=99)
+    out = []
+    for impl in (1, 2):
+        c = make_ctx(world)
+        c.set_score_impl(impl)
+        c.scan_set_polar_images(world.scan)
+        c.pf_set_states(st.copy(), ld)
+        out.append((c.pf_score(4.0), c.pf_get_states()))
+        c.close()
+    assert rel_err(out[1][0], out[0][0]).max() <= WEIGHT_RTOL
+    assert (out[0][1]["theta"] == out[1][1]["theta"]).mean() > 0.995

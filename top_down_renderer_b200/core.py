@@ -66,6 +66,10 @@ class Context:
         check(self._lib.tdr_launch_count(self._h, C.byref(n)))
         return n.value
 
+    def set_score_impl(self, impl):
+        """0 auto, 1 CUDA cores only, 2 tensor cores whenever usable"""
+        check(self._lib.tdr_set_score_impl(self._h, int(impl)))
+
     def profile_enable(self, on=True):
         check(self._lib.tdr_profile_enable(self._h, int(bool(on))))
 

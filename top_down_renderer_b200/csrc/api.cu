@@ -138,9 +138,9 @@ void tdr_destroy(tdr_ctx* c) {
   tdr::DevBuf* bufs[] = {&c->map_px, &c->seedbits, &c->edt_g, &c->scratch, &c->scratch2, &c->tab, &c->pts, &c->lut,
                          &c->scan_img, &c->scan_pack, &c->hist, &c->d_search_thetas, &c->d_search_shifts, &c->weights,
                          &c->prefix, &c->idx, &c->scal, &c->pose_tmp, &c->grid_centers, &c->grid_costs,
-                         &c->grid_shifts, &c->d_cw};
+                         &c->grid_shifts, &c->d_cw, &c->map16, &c->scan_op, &c->bin_counts, &c->perm};
   for (auto* b : bufs) b->release();
-  c->part[0].release(); c->part[1].release(); c->ckpt.release();
+  c->part[0].release(); c->part[1].release(); c->ckpt.release(); c->all.release();
   c->pin.release();
   for (int k = 0; k <= TDR_N_STAGES; k++) if (c->stage_ev[k]) cudaEventDestroy(c->stage_ev[k]);
   if (c->stream) cudaStreamDestroy(c->stream);
@@ -150,6 +150,12 @@ void tdr_destroy(tdr_ctx* c) {
 int tdr_sync(tdr_ctx* ctx) { CTX_CHECK(ctx); TDR_CUDA(cudaStreamSynchronize(ctx->stream)); return TDR_OK; }
 void* tdr_stream(tdr_ctx* ctx) { return ctx ? (void*)ctx->stream : nullptr; }
 int tdr_launch_count(tdr_ctx* ctx, int64_t* n) { TDR_REQUIRE(ctx && n, TDR_EINVAL, "null argument"); *n = ctx->launches; return TDR_OK; }
+
+int tdr_set_score_impl(tdr_ctx* ctx, int impl) {
+  TDR_REQUIRE(ctx && impl >= 0 && impl <= 2, TDR_EINVAL, "score impl must be 0 (auto), 1 (CUDA cores) or 2 (tensor cores)");
+  ctx->score_impl = impl;
+  return TDR_OK;
+}
 
 int tdr_profile_enable(tdr_ctx* ctx, int on) {
   CTX_CHECK(ctx);
@@ -312,7 +318,7 @@ int tdr_pf_set_params(tdr_ctx* ctx, const tdr_filter_params* p) {
   ctx->fp = *p;
   TDR_CUDA(cudaMemcpyAsync(ctx->d_cw.p, ctx->fp.class_weights, 64, cudaMemcpyHostToDevice, ctx->stream));
   TDR_CUDA(cudaStreamSynchronize(ctx->stream));
-  ctx->have_params = true;
+  ctx->have_params = true; ctx->map16_valid = false;   // class weights are folded into the fp16 map copy
   return TDR_OK;
 }
 

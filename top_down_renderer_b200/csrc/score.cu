@@ -350,6 +350,12 @@ int score_particles(tdr_ctx* ctx, float res) {
   }
   if (ctx->n_uninit > 0) {
     TDR_REQUIRE(sp.n_shifts > 0, TDR_ESTATE, "theta-search list not set (tdr_pf_set_search)");
+    // large searches go to the tensor cores (score_mma.cu); small ones stay on the CUDA cores
+    bool used = false;
+    if (ctx->score_impl == 2 || (ctx->score_impl == 0 && ctx->n_uninit >= 4096)) {
+      if (int e = score_mma(ctx, res, false, pt.n, 1.f, sp.shifts, sp.n_shifts, &used)) return e;
+    }
+    if (used) { ctx->n_uninit = 0; TDR_CUDA(cudaGetLastError()); return TDR_OK; }
     size_t smem = (size_t)P * 32 + (size_t)sp.n_shifts * (SEARCH_THREADS / 32) * 8 + 256;
     long long ctas = sp.n < (long long)ctx->sm_count * 8 ? sp.n : (long long)ctx->sm_count * 8;
     k_score_search<SEARCH_THREADS, SEARCH_JMAX><<<(unsigned)ctas, SEARCH_THREADS, smem, ctx->stream>>>(sp, 0);
@@ -367,6 +373,11 @@ int score_grid(tdr_ctx* ctx, long long n, float scale, float res) {
   sp.shifts = ctx->grid_shifts.as<int32_t>(); sp.n_shifts = ctx->grid_shifts_n; sp.thetas = nullptr;
   sp.init_x = sp.init_y = sp.dx = sp.dy = nullptr; sp.theta = nullptr; sp.scale = nullptr; sp.have_init = nullptr; sp.weights = nullptr;
   const int P = sp.P;
+  bool used = false;
+  if (ctx->score_impl == 2 || (ctx->score_impl == 0 && n >= 4096)) {
+    if (int e = score_mma(ctx, res, true, n, scale, sp.shifts, sp.n_shifts, &used)) return e;
+  }
+  if (used) return TDR_OK;
   TDR_REQUIRE(P <= SEARCH_THREADS * SEARCH_JMAX, TDR_EUNSUPPORTED, "polar image too large");
   TDR_CUDA(cudaFuncSetAttribute(k_score_search<SEARCH_THREADS, SEARCH_JMAX>, cudaFuncAttributeMaxDynamicSharedMemorySize, 200 * 1024));
   size_t smem = (size_t)P * 32 + (size_t)sp.n_shifts * (SEARCH_THREADS / 32) * 8 + 256;

@@ -93,6 +93,13 @@ struct tdr_ctx {
   tdr::DevBuf scratch;       // generic scratch (layer staging, partial histograms, ...)
   tdr::DevBuf scratch2;
 
+  // tensor-core score path (score_mma.cu): class-weighted fp16 hi/lo copy of the map, scan operand, binning
+  tdr::DevBuf map16;         // rows*cols x 32 B
+  bool map16_valid = false;
+  tdr::DevBuf scan_op;       // P_pad x N x 32 B
+  tdr::DevBuf bin_counts, perm;
+  int score_impl = 0;        // 0 auto, 1 CUDA cores only, 2 tensor cores whenever usable
+
   // ---- polar table
   int n_theta = 0, n_r = 0;
   tdr::DevBuf tab;           // 2*P floats
@@ -150,6 +157,7 @@ namespace tdr {
 enum {
   SC_SUM = 0, SC_NVALID, SC_MEAN, SC_BS, SC_NUNDER, SC_FALLBACK,     // stats (6 floats, ABI order)
   SC_S1, SC_S2, SC_REP, SC_ARGMAX /*int*/, SC_ARGVAL,
+  SC_MMA_MAXCOUNT = 12,     // int: max class-summed scan count (fp16 exactness check of the tensor-core path)
   SC_CHAIN = 16,            // 8 chain totals
   SC_DBL = 32,              // doubles from here (8-byte aligned): sumsq, count_valid, count_under ...
   SC_POSE = 64,             // pose scalars
@@ -174,6 +182,9 @@ int score_particles(tdr_ctx*, float res);
 int score_grid(tdr_ctx*, long long n, float scale, float res);
 int local_polar(tdr_ctx*, const float* dev_centers, int n, float scale, float res, float* dev_dists, uint8_t* dev_mask);
 int local_cart(tdr_ctx*, float cx, float cy, float rot, float res, int out_rows, int out_cols, float* dev_dists, uint8_t* dev_mask);
+// score_mma.cu
+int score_mma(tdr_ctx*, float res, bool grid_mode, long long n_items, float grid_scale, const int32_t* dev_shifts,
+              int n_shifts, bool* used);
 // weights.cu
 int normalize(tdr_ctx*);
 int build_prefix(tdr_ctx*);
