@@ -1,5 +1,6 @@
 // api.cu — the extern "C" surface declared in include/tdr.h.
 #include <stdarg.h>
+#include <stdlib.h>
 #include <string.h>
 
 #include "tdr_ctx.cuh"
@@ -123,6 +124,8 @@ int tdr_create(tdr_ctx** out, int device) {
     delete c;
     return TDR_ENOGPU;
   }
+  if (const char* e = getenv("TDR_MMA_TILES")) { int v = atoi(e); if (v == 1 || v == 2 || v == 4) c->mma_tiles = v; }
+  if (const char* e = getenv("TDR_MMA_ST_SHIFT")) { int v = atoi(e); if (v >= 5 && v <= 16) c->mma_st_shift = v; }
   TDR_CUDA(cudaStreamCreateWithFlags(&c->stream, cudaStreamNonBlocking));
   if (int r = c->scal.reserve(SC_TOTAL * 4)) { delete c; return r; }
   TDR_CUDA(cudaMemsetAsync(c->scal.p, 0, SC_TOTAL * 4, c->stream));

@@ -95,6 +95,11 @@ __device__ __forceinline__ uint32_t tmem_ld1(uint32_t taddr) {
   asm volatile("tcgen05.ld.sync.aligned.32x32b.x1.b32 {%0}, [%1];" : "=r"(v) : "r"(taddr));
   return v;
 }
+__device__ __forceinline__ void ldg256(const void* p, uint4& a, uint4& b) {
+  asm("ld.global.nc.v8.b32 {%0, %1, %2, %3, %4, %5, %6, %7}, [%8];"
+      : "=r"(a.x), "=r"(a.y), "=r"(a.z), "=r"(a.w), "=r"(b.x), "=r"(b.y), "=r"(b.z), "=r"(b.w)
+      : "l"(p));
+}
 __device__ __forceinline__ void tmem_wait_ld() { asm volatile("tcgen05.wait::ld.sync.aligned;" ::: "memory"); }
 
 // K-major, no swizzle (cute UMMA "INTERLEAVE"): core matrix = 8 rows x 16 B contiguous;
@@ -181,7 +186,7 @@ __global__ void k_build_scan_operand(const float* __restrict__ img, int C, int n
 struct BinParams {
   const float *init_x, *init_y, *dx, *dy, *scale; const uint8_t* have_init;   // particle mode
   const float* centers;                                                       // grid mode
-  long long n; float resolution; int rows, cols, tile_shift, tiles_x, n_bins;
+  long long n; float resolution; int rows, cols, st_shift, super_x, per_super, n_bins;
 };
 __device__ __forceinline__ int bin_of(const BinParams& b, long long i) {
   float x, y;
@@ -193,7 +198,10 @@ __device__ __forceinline__ int bin_of(const BinParams& b, long long i) {
   }
   int c = f2i_x86(TDR_FDIV(x, b.resolution)), r = f2i_x86(TDR_FDIV(y, b.resolution));
   if (c < 0 || r < 0 || c >= b.cols || r >= b.rows) return b.n_bins - 1;      // off-map: last bin
-  return (r >> b.tile_shift) * b.tiles_x + (c >> b.tile_shift);
+  // super-tile (2^st_shift px square, row-major over the map), then pixel row, then 32-px column segment
+  const int S = 1 << b.st_shift, m = S - 1;
+  const int sup = (r >> b.st_shift) * b.super_x + (c >> b.st_shift);
+  return sup * b.per_super + (r & m) * (S >> 5) + ((c & m) >> 5);
 }
 __global__ void k_bin_count(BinParams b, int* __restrict__ counts) {
   for (long long i = (long long)blockIdx.x * blockDim.x + threadIdx.x; i < b.n; i += (long long)gridDim.x * blockDim.x) {
@@ -201,32 +209,58 @@ __global__ void k_bin_count(BinParams b, int* __restrict__ counts) {
     if (k >= 0) atomicAdd(counts + k, 1);
   }
 }
-// single CTA exclusive scan of counts -> cursor (in place)
-__global__ void __launch_bounds__(1024) k_bin_scan(int* __restrict__ counts, int n_bins) {
+// exclusive scan of the bin counts (in place): per-block local scan + block sums, scan of the sums, add back
+static const int SCAN_ITEMS = 4, SCAN_BLOCK = 1024, SCAN_TILE = SCAN_ITEMS * SCAN_BLOCK;
+__device__ __forceinline__ int block_excl_scan(int v, int* s_w, int* total) {
+  const int lane = threadIdx.x & 31, warp = threadIdx.x >> 5;
+  int inc = v;
+  for (int d = 1; d < 32; d <<= 1) { int o = __shfl_up_sync(0xffffffffu, inc, d); if (lane >= d) inc += o; }
+  if (lane == 31) s_w[warp] = inc;
+  __syncthreads();
+  if (warp == 0) {
+    int w = s_w[lane];
+    for (int d = 1; d < 32; d <<= 1) { int o = __shfl_up_sync(0xffffffffu, w, d); if (lane >= d) w += o; }
+    s_w[lane] = w;
+  }
+  __syncthreads();
+  const int excl = inc - v + (warp > 0 ? s_w[warp - 1] : 0);
+  if (total) *total = s_w[31];
+  __syncthreads();
+  return excl;
+}
+__global__ void __launch_bounds__(SCAN_BLOCK) k_scan_local(int* __restrict__ a, int n, int* __restrict__ sums) {
+  __shared__ int s_w[32];
+  const int base = blockIdx.x * SCAN_TILE + threadIdx.x * SCAN_ITEMS;
+  int v[SCAN_ITEMS], t = 0;
+#pragma unroll
+  for (int k = 0; k < SCAN_ITEMS; k++) { v[k] = base + k < n ? a[base + k] : 0; t += v[k]; }
+  int total;
+  int excl = block_excl_scan(t, s_w, &total);
+#pragma unroll
+  for (int k = 0; k < SCAN_ITEMS; k++) { if (base + k < n) a[base + k] = excl; excl += v[k]; }
+  if (threadIdx.x == 0) sums[blockIdx.x] = total;
+}
+__global__ void __launch_bounds__(SCAN_BLOCK) k_scan_sums(int* __restrict__ sums, int nb) {
   __shared__ int s_w[32];
   __shared__ int s_carry;
-  const int tid = threadIdx.x, lane = tid & 31, warp = tid >> 5;
-  if (tid == 0) s_carry = 0;
+  if (threadIdx.x == 0) s_carry = 0;
   __syncthreads();
-  for (int base = 0; base < n_bins; base += 1024) {
-    int i = base + tid;
-    int v = i < n_bins ? counts[i] : 0;
-    int inc = v;
-    for (int d = 1; d < 32; d <<= 1) { int o = __shfl_up_sync(0xffffffffu, inc, d); if (lane >= d) inc += o; }
-    if (lane == 31) s_w[warp] = inc;
+  for (int base = 0; base < nb; base += SCAN_BLOCK) {
+    const int i = base + threadIdx.x;
+    const int v = i < nb ? sums[i] : 0;
+    int total;
+    const int excl = block_excl_scan(v, s_w, &total) + s_carry;
+    if (i < nb) sums[i] = excl;
     __syncthreads();
-    if (warp == 0) {
-      int w = s_w[lane];
-      for (int d = 1; d < 32; d <<= 1) { int o = __shfl_up_sync(0xffffffffu, w, d); if (lane >= d) w += o; }
-      s_w[lane] = w;
-    }
-    __syncthreads();
-    int excl = inc - v + (warp > 0 ? s_w[warp - 1] : 0) + s_carry;
-    if (i < n_bins) counts[i] = excl;
-    __syncthreads();
-    if (tid == 1023) s_carry = excl + v;
+    if (threadIdx.x == 0) s_carry += total;
     __syncthreads();
   }
+}
+__global__ void __launch_bounds__(SCAN_BLOCK) k_scan_add(int* __restrict__ a, int n, const int* __restrict__ sums) {
+  const int base = blockIdx.x * SCAN_TILE + threadIdx.x * SCAN_ITEMS;
+  const int add = sums[blockIdx.x];
+#pragma unroll
+  for (int k = 0; k < SCAN_ITEMS; k++) if (base + k < n) a[base + k] += add;
 }
 __global__ void k_bin_scatter(BinParams b, int* __restrict__ cursor, int* __restrict__ perm) {
   for (long long i = (long long)blockIdx.x * blockDim.x + threadIdx.x; i < b.n; i += (long long)gridDim.x * blockDim.x) {
@@ -252,29 +286,37 @@ struct MmaParams {
 };
 
 static const int MMA_G = 2;        // lattice cells per pipeline stage
+// A tile (128 hypotheses x 16 fp16, K-major, no swizzle): K chunk 0 at [0, 2048), K chunk 1 at [A_LBO, A_LBO + 2048).
+// A_LBO is 64 bytes past a multiple of 128 so that a quarter-warp's 4 rows x 2 chunks hit 8 different 16-byte
+// bank groups (conflict-free STS.128).
+static const int A_LBO = 2048 + 64;
+static const int A_TILE = 4224;
 template <int N, int T> struct MmaCfg {
   static const int kThreads = 128 * T + 64;
-  static const int kABytes = MMA_G * T * 4096;           // per stage
-  static const int kBBytes = MMA_G * N * 32;             // per stage
+  static const int kTmemCols = T * N <= 128 ? 128 : (T * N <= 256 ? 256 : 512);
+  static const int kCtasPerSm = 512 / kTmemCols;           // TMEM is the co-residency limit
+  static const int kABytes = MMA_G * T * A_TILE;          // per stage
+  static const int kBBytes = MMA_G * N * 32;              // per stage
   static const int kStageBytes = kABytes + kBBytes;
-  static const int kStages = (200 * 1024) / kStageBytes > 8 ? 8 : (200 * 1024) / kStageBytes;
+  static const int kBudget = (216 * 1024) / kCtasPerSm - 1280;
+  static const int kStages = kBudget / kStageBytes > 8 ? 8 : kBudget / kStageBytes;
   static const int kSmem = kStages * kStageBytes + 256;
 };
 
 template <int N, int T>
-__global__ void __launch_bounds__(128 * T + 64, 1) k_score_mma(MmaParams sp) {
+__global__ void __launch_bounds__(128 * T + 64, MmaCfg<N, T>::kCtasPerSm) k_score_mma(MmaParams sp) {
   using Cfg = MmaCfg<N, T>;
   constexpr int NS = Cfg::kStages;
   constexpr int S_PAD = N / 2;
   extern __shared__ __align__(128) unsigned char smem[];
-  unsigned char* sA = smem;                                  // [NS][G][T][kc 2][128][16 B]
+  unsigned char* sA = smem;                                  // [NS][G][T] tiles of A_TILE bytes
   unsigned char* sB = smem + (size_t)NS * Cfg::kABytes;       // [NS][G][kc 2][N][16 B]
   uint64_t* bars = reinterpret_cast<uint64_t*>(smem + (size_t)NS * Cfg::kStageBytes);   // full[NS] empty[NS] accum
   uint32_t* s_tmem = reinterpret_cast<uint32_t*>(bars + 2 * NS + 1);
   const int tid = threadIdx.x, warp = tid >> 5, lane = tid & 31;
   const uint32_t bar_full = smem_u32(bars), bar_empty = smem_u32(bars + NS), bar_accum = smem_u32(bars + 2 * NS);
 
-  if (warp == 4 * T + 1) tmem_alloc(smem_u32(s_tmem), 512);
+  if (warp == 4 * T + 1) tmem_alloc(smem_u32(s_tmem), Cfg::kTmemCols);
   if (tid == 0) {
     for (int s = 0; s < NS; s++) { mbar_init(bar_full + 8 * s, 4 * T + 1); mbar_init(bar_empty + 8 * s, 1); }
     mbar_init(bar_accum, 1);
@@ -314,30 +356,30 @@ __global__ void __launch_bounds__(128 * T + 64, 1) k_score_mma(MmaParams sp) {
       }
       const float oy = TDR_FDIV(cy, sp.resolution), ox = TDR_FDIV(cx, sp.resolution);
 
+      // Each thread pulls the whole 32-byte record of ITS hypothesis with one 256-bit load (one sector, one L1
+      // wavefront; measured 0.95 records/clk/SM from L2 against 0.42 for 2 x LDG.128 — tools/gather_bench.cu).
       auto load_stage = [&](int k, uint4 (&rec)[MMA_G][2]) {
 #pragma unroll
         for (int g = 0; g < MMA_G; g++) {
-          rec[g][0] = make_uint4(0, 0, 0, 0); rec[g][1] = rec[g][0];
           const int p = k * MMA_G + g;
+          rec[g][0] = make_uint4(0, 0, 0, 0); rec[g][1] = rec[g][0];
           if (active && p < sp.P) {
             const float2 tb = __ldg(sp.tab + p);
             const int r = lattice_index(tb.x, sc, sp.res, oy);
             const int c = lattice_index(tb.y, sc, sp.res, ox);
-            if (r >= 0 && r < sp.rows && c >= 0 && c < sp.cols) {
-              const uint4* px = reinterpret_cast<const uint4*>(map_bytes + ((size_t)r * sp.cols + c) * 32);
-              rec[g][0] = __ldg(px); rec[g][1] = __ldg(px + 1);
-            }
+            if (r >= 0 && r < sp.rows && c >= 0 && c < sp.cols)
+              ldg256(map_bytes + ((size_t)r * sp.cols + c) * 32, rec[g][0], rec[g][1]);
           }
         }
       };
       auto store_stage = [&](uint32_t iter, const uint4 (&rec)[MMA_G][2]) {
         const uint32_t st = iter % NS, ph = (iter / NS) & 1u;
         mbar_wait(bar_empty + 8 * st, ph ^ 1u);
-        unsigned char* base = sA + (size_t)st * Cfg::kABytes + (size_t)t * 4096 + (size_t)m * 16;
+        unsigned char* base = sA + (size_t)st * Cfg::kABytes + (size_t)t * A_TILE + (size_t)m * 16;
 #pragma unroll
         for (int g = 0; g < MMA_G; g++) {
-          *reinterpret_cast<uint4*>(base + (size_t)g * T * 4096) = rec[g][0];
-          *reinterpret_cast<uint4*>(base + (size_t)g * T * 4096 + 2048) = rec[g][1];
+          *reinterpret_cast<uint4*>(base + (size_t)g * T * A_TILE) = rec[g][0];            // K chunk 0: hi halves
+          *reinterpret_cast<uint4*>(base + (size_t)g * T * A_TILE + A_LBO) = rec[g][1];    // K chunk 1: lo halves
         }
         fence_proxy_async();
         __syncwarp();
@@ -421,7 +463,7 @@ __global__ void __launch_bounds__(128 * T + 64, 1) k_score_mma(MmaParams sp) {
             const uint64_t bdesc = umma_desc(b0 + g * (N * 32), N * 16, 128);
 #pragma unroll
             for (int tt = 0; tt < T; tt++) {
-              const uint64_t adesc = umma_desc(a0 + (g * T + tt) * 4096, 2048, 128);
+              const uint64_t adesc = umma_desc(a0 + (g * T + tt) * A_TILE, A_LBO, 128);
               umma_f16(tmem_base + (uint32_t)(tt * N), adesc, bdesc, idesc, (k > 0 || g > 0) ? 1u : 0u);
             }
           }
@@ -433,7 +475,7 @@ __global__ void __launch_bounds__(128 * T + 64, 1) k_score_mma(MmaParams sp) {
   }
   tc_fence_before();
   __syncthreads();
-  if (warp == 4 * T + 1) tmem_dealloc(tmem_base, 512);
+  if (warp == 4 * T + 1) tmem_dealloc(tmem_base, Cfg::kTmemCols);
 }
 
 // ------------------------------------------------------------------------------------------------
@@ -497,18 +539,31 @@ int score_mma(tdr_ctx* ctx, float res, bool grid_mode, long long n_items, float 
     bp.scale = pt.scale.as<float>(); bp.have_init = pt.have_init.as<uint8_t>();
   }
   bp.n = n_items; bp.resolution = ctx->resolution; bp.rows = ctx->rows; bp.cols = ctx->cols;
-  bp.tile_shift = 5;
-  while ((((long long)(ctx->rows >> bp.tile_shift) + 1) * ((ctx->cols >> bp.tile_shift) + 1)) > 60000) bp.tile_shift++;
-  bp.tiles_x = (ctx->cols >> bp.tile_shift) + 1;
-  bp.n_bins = ((ctx->rows >> bp.tile_shift) + 1) * bp.tiles_x + 1;
-  if (int e = ctx->bin_counts.reserve((size_t)bp.n_bins * 4)) return e;
+  // bins = (super-tile, pixel row, 32-px column segment).  The super-tile keeps the hypotheses that are in
+  // flight together (sm_count x 128T of them) inside one compact region so that its dilated footprint stays
+  // L2-resident; row + segment order puts warp neighbours on the same map row a few pixels apart (shared lines).
+  bp.st_shift = ctx->mma_st_shift;
+  while ((1 << bp.st_shift) < 32) bp.st_shift++;
+  bp.super_x = (ctx->cols >> bp.st_shift) + 1;
+  bp.per_super = (1 << bp.st_shift) * ((1 << bp.st_shift) >> 5);
+  {
+    long long nb = (long long)((ctx->rows >> bp.st_shift) + 1) * bp.super_x * bp.per_super + 1;
+    TDR_REQUIRE(nb < (1ll << 28), TDR_EUNSUPPORTED, "map too large for the hypothesis binning (%lld bins)", nb);
+    bp.n_bins = (int)nb;
+  }
+  const int scan_blocks = (bp.n_bins + SCAN_TILE - 1) / SCAN_TILE;
+  if (int e = ctx->bin_counts.reserve((size_t)bp.n_bins * 4 + (size_t)scan_blocks * 4 + 64)) return e;
   if (int e = ctx->perm.reserve((size_t)n_items * 4)) return e;
-  TDR_CUDA(cudaMemsetAsync(ctx->bin_counts.p, 0, (size_t)bp.n_bins * 4, ctx->stream));
+  int* d_counts = ctx->bin_counts.as<int>();
+  int* d_sums = d_counts + bp.n_bins;
+  TDR_CUDA(cudaMemsetAsync(d_counts, 0, (size_t)bp.n_bins * 4, ctx->stream));
   const int blocks = (int)((n_items + 255) / 256 < ctx->sm_count * 8 ? (n_items + 255) / 256 : ctx->sm_count * 8);
-  k_bin_count<<<blocks, 256, 0, ctx->stream>>>(bp, ctx->bin_counts.as<int>());
-  k_bin_scan<<<1, 1024, 0, ctx->stream>>>(ctx->bin_counts.as<int>(), bp.n_bins);
-  k_bin_scatter<<<blocks, 256, 0, ctx->stream>>>(bp, ctx->bin_counts.as<int>(), ctx->perm.as<int>());
-  count_launch(ctx, 3);
+  k_bin_count<<<blocks, 256, 0, ctx->stream>>>(bp, d_counts);
+  k_scan_local<<<scan_blocks, SCAN_BLOCK, 0, ctx->stream>>>(d_counts, bp.n_bins, d_sums);
+  k_scan_sums<<<1, SCAN_BLOCK, 0, ctx->stream>>>(d_sums, scan_blocks);
+  k_scan_add<<<scan_blocks, SCAN_BLOCK, 0, ctx->stream>>>(d_counts, bp.n_bins, d_sums);
+  k_bin_scatter<<<blocks, 256, 0, ctx->stream>>>(bp, d_counts, ctx->perm.as<int>());
+  count_launch(ctx, 5);
   TDR_CUDA(cudaGetLastError());
 
   MmaParams sp; memset(&sp, 0, sizeof(sp));
@@ -532,20 +587,25 @@ int score_mma(tdr_ctx* ctx, float res, bool grid_mode, long long n_items, float 
     sp.regularization = ctx->fp.regularization;
     sp.thetas = ctx->d_search_thetas.as<float>();
   }
-  const long long n_batches48 = (sp.n_work + 511) / 512, n_batches112 = (sp.n_work + 255) / 256;
+#define TDR_LAUNCH_MMA(NN, TT)                                                                                       \
+  do {                                                                                                                \
+    using Cfg = MmaCfg<NN, TT>;                                                                                       \
+    static bool attr = false;                                                                                         \
+    if (!attr) { TDR_CUDA(cudaFuncSetAttribute(k_score_mma<NN, TT>, cudaFuncAttributeMaxDynamicSharedMemorySize, Cfg::kSmem)); attr = true; } \
+    const long long nb = (sp.n_work + 128 * TT - 1) / (128 * TT);                                                     \
+    const long long cap = (long long)ctx->sm_count * Cfg::kCtasPerSm;                                                 \
+    const int grid = (int)(nb < cap ? nb : cap);                                                                      \
+    k_score_mma<NN, TT><<<grid, Cfg::kThreads, Cfg::kSmem, ctx->stream>>>(sp);                                        \
+  } while (0)
   if (S_pad == 48) {
-    using Cfg = MmaCfg<96, 4>;
-    static bool attr = false;
-    if (!attr) { TDR_CUDA(cudaFuncSetAttribute(k_score_mma<96, 4>, cudaFuncAttributeMaxDynamicSharedMemorySize, Cfg::kSmem)); attr = true; }
-    int grid = (int)(n_batches48 < ctx->sm_count ? n_batches48 : ctx->sm_count);
-    k_score_mma<96, 4><<<grid, Cfg::kThreads, Cfg::kSmem, ctx->stream>>>(sp);
+    if (ctx->mma_tiles == 4) TDR_LAUNCH_MMA(96, 4);
+    else if (ctx->mma_tiles == 2) TDR_LAUNCH_MMA(96, 2);
+    else TDR_LAUNCH_MMA(96, 1);
   } else {
-    using Cfg = MmaCfg<224, 2>;
-    static bool attr = false;
-    if (!attr) { TDR_CUDA(cudaFuncSetAttribute(k_score_mma<224, 2>, cudaFuncAttributeMaxDynamicSharedMemorySize, Cfg::kSmem)); attr = true; }
-    int grid = (int)(n_batches112 < ctx->sm_count ? n_batches112 : ctx->sm_count);
-    k_score_mma<224, 2><<<grid, Cfg::kThreads, Cfg::kSmem, ctx->stream>>>(sp);
+    if (ctx->mma_tiles >= 2) TDR_LAUNCH_MMA(224, 2);
+    else TDR_LAUNCH_MMA(224, 1);
   }
+#undef TDR_LAUNCH_MMA
   count_launch(ctx);
   TDR_CUDA(cudaGetLastError());
   *used = true;

@@ -99,6 +99,8 @@ struct tdr_ctx {
   tdr::DevBuf scan_op;       // P_pad x N x 32 B
   tdr::DevBuf bin_counts, perm;
   int score_impl = 0;        // 0 auto, 1 CUDA cores only, 2 tensor cores whenever usable
+  int mma_tiles = 2;         // 128-hypothesis tiles per CTA; 2 tiles x 2 CTAs/SM measured best (tuning: TDR_MMA_TILES)
+  int mma_st_shift = 10;     // log2 of the binning super-tile side in px (tuning: TDR_MMA_ST_SHIFT)
 
   // ---- polar table
   int n_theta = 0, n_r = 0;
