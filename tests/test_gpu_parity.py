@@ -531,3 +531,47 @@ def test_mma_matches_cuda_core_path(world):
         c.close()
     assert rel_err(out[1][0], out[0][0]).max() <= WEIGHT_RTOL
     assert (out[0][1]["theta"] == out[1][1]["theta"]).mean() > 0.995
+
+
+# ---- long chains: the tiled (multi-CTA) order-exact accumulation ------------------------------------------------
+@pytest.mark.parametrize("kind", ["scored", "nan", "gated", "denormal"])
+@pytest.mark.parametrize("n", [40000, 1_000_000])
+def test_normalize_long(ctx, kind, n):
+    rng = np.random.default_rng(n + len(kind))
+    w = _weights_case(kind, n, rng)
+    ld = rng.uniform(0, 0.4, n).astype(np.float32)
+    st = np.zeros(n, dtype=synth.STATE_DTYPE)
+    st["scale"] = 2
+    ctx.pf_set_states(st, ld)
+    ctx.pf_set_weights(w)
+    arg, stats = ctx.pf_normalize()
+    got = ctx.pf_get_weights(n)
+    want, warg, wstats = orc.normalize(w, ld)
+    assert rel_err(got, want).max() <= WEIGHT_RTOL
+    # sums, the lower-half deviation and hence every normalised weight are order-exact: bit for bit, NaNs included
+    assert np.array_equal(got.view(np.uint32), want.view(np.uint32)) and arg == warg
+    assert stats[0] == wstats[0] and stats[3] == wstats[3]
+
+
+@pytest.mark.parametrize("kind", ["normalized", "ties", "spiky", "zeros_lead", "equal"])
+@pytest.mark.parametrize("n,M", [(33000, 33000), (1_000_000, 1_000_000), (3_000_001, 1_000_000)])
+def test_resample_long_chains_bit_exact(ctx, n, M, kind):
+    rng = np.random.default_rng(n + M)
+    if kind == "normalized":
+        w = rng.random(n).astype(np.float32); w /= w.sum()
+    elif kind == "ties":
+        w = (rng.integers(0, 8, n) * 2.0 ** -24).astype(np.float32)
+    elif kind == "spiky":
+        w = np.full(n, 1e-10, dtype=np.float32); w[rng.integers(0, n, max(1, n // 50))] = 1.0; w /= w.sum()
+    elif kind == "equal":
+        w = np.full(n, 1.0 / n, dtype=np.float32)        # worst case for rounding bias: every add rounds the same way
+    else:
+        w = rng.random(n).astype(np.float32); w[: n // 3] = 0; w /= max(w.sum(), 1e-30)
+    st = np.zeros(n, dtype=synth.STATE_DTYPE)
+    st["init_x_px"] = np.arange(n) % 4096
+    u = orc.uniform_draw(n)
+    ctx.pf_set_states(st, None)
+    ctx.pf_set_weights(w)
+    got = ctx.pf_resample(u, M)
+    want = orc.resample_fast(w, u, M)
+    assert np.array_equal(got, want), np.count_nonzero(got != want)

@@ -168,3 +168,24 @@ def test_pair_composition_is_associative(hm):
             n = int(rng.integers(1, 300))
             x = (rng.random(n) * 2.0 ** (E - rng.integers(0, 30, n))).astype(np.float32)
             assert hm.hm_pair_tree_equals_chain(x.ctypes.data_as(fp), n, E) == 1
+
+
+def test_double_addend_chain_is_exact(hm):
+    """s = (float)((double)s + d) with double addends (the lower-deviation sum, particle_filter.cpp:123) through
+    inc_pair_d equals the sequential loop bit for bit"""
+    hm.hm_exact_sum_double_addends.restype = C.c_long
+    dp = C.POINTER(C.c_double)
+    rng = np.random.default_rng(11)
+    cases = {
+        "squares": (rng.random(200_000).astype(np.float32) * np.float32(1e-3)).astype(np.float64) ** 2,
+        "float_valued": rng.random(100_000).astype(np.float32).astype(np.float64),
+        "tiny_then_big": np.concatenate([np.full(1000, 1e-50), (rng.random(50_000).astype(np.float32) ** 2).astype(np.float64)]),
+        "ties": (rng.integers(0, 16, 100_000) * 2.0 ** -30).astype(np.float64) + 2.0 ** -31,
+        "zeros": np.zeros(1000),
+    }
+    for name, d in cases.items():
+        d = np.ascontiguousarray(d, dtype=np.float64)
+        a, b = C.c_float(), C.c_float()
+        real = hm.hm_exact_sum_double_addends(d.ctypes.data_as(dp), C.c_long(len(d)), C.byref(a), C.byref(b))
+        assert np.float32(a.value).view(np.uint32) == np.float32(b.value).view(np.uint32), (name, a.value, b.value)
+        assert real < 2000 + 64, (name, real)      # only binade crossings (and the denormal head) take real adds

@@ -124,6 +124,7 @@ int tdr_create(tdr_ctx** out, int device) {
     delete c;
     return TDR_ENOGPU;
   }
+  if (const char* e = getenv("TDR_SEQ_IMPL")) c->seq_impl = atoi(e) == 1 ? 1 : 0;
   if (const char* e = getenv("TDR_MMA_TILES")) { int v = atoi(e); if (v == 1 || v == 2 || v == 4) c->mma_tiles = v; }
   if (const char* e = getenv("TDR_MMA_ST_SHIFT")) { int v = atoi(e); if (v >= 5 && v <= 16) c->mma_st_shift = v; }
   TDR_CUDA(cudaStreamCreateWithFlags(&c->stream, cudaStreamNonBlocking));
@@ -141,7 +142,7 @@ void tdr_destroy(tdr_ctx* c) {
   tdr::DevBuf* bufs[] = {&c->map_px, &c->seedbits, &c->edt_g, &c->scratch, &c->scratch2, &c->tab, &c->pts, &c->lut,
                          &c->scan_img, &c->scan_pack, &c->hist, &c->d_search_thetas, &c->d_search_shifts, &c->weights,
                          &c->prefix, &c->idx, &c->scal, &c->pose_tmp, &c->grid_centers, &c->grid_costs,
-                         &c->grid_shifts, &c->d_cw, &c->map16, &c->scan_op, &c->bin_counts, &c->perm};
+                         &c->grid_shifts, &c->d_cw, &c->map16, &c->seq_ws, &c->scan_op, &c->bin_counts, &c->perm};
   for (auto* b : bufs) b->release();
   c->part[0].release(); c->part[1].release(); c->ckpt.release(); c->all.release();
   c->pin.release();

@@ -91,6 +91,33 @@ void hm_exact_prefix(const float* x, long n, int chunk, int skip_nan, float* run
   if (n_segments) *n_segments = segs;
 }
 
+// sequential  s = (float)((double)s + d[i])  vs the inc_pair_d algebra (one binade segment at a time)
+long hm_exact_sum_double_addends(const double* d, long n, float* total_seq, float* total_alg) {
+  float s = 0.f;
+  for (long i = 0; i < n; i++) s = (float)((double)s + d[i]);
+  *total_seq = s;
+  float S = 0.f;
+  long real_adds = 0;
+  long i = 0;
+  while (i < n) {
+    const int E = binade_of(S);
+    uint32_t m = mant_of(S);
+    const uint32_t limit = binade_limit(E);
+    bool crossed = false;
+    while (i < n) {
+      bool irr;
+      IncPair pr = inc_pair_d(d[i], E, true, &irr);
+      uint32_t inc = (m & 1u) ? pr.b : pr.a;
+      if (m + inc >= limit || inc >= TDR_INC_SAT) { crossed = true; break; }
+      m += inc; i++;
+    }
+    S = from_binade(E, m);
+    if (crossed) { S = (float)((double)S + d[i]); i++; real_adds++; }
+  }
+  *total_alg = S;
+  return real_adds;
+}
+
 // associativity probe: compose pairs in a balanced tree instead of left-to-right and compare
 int hm_pair_tree_equals_chain(const float* x, int n, int E) {
   std::vector<IncPair> v(n);

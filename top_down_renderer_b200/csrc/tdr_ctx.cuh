@@ -136,6 +136,8 @@ struct tdr_ctx {
   int64_t n_weights = 0;
   const float* ld_override = nullptr;  // device last_dist aligned with an all-gathered weight vector (multi-GPU)
   tdr::DevBuf prefix;        // running max of the order-exact prefix
+  tdr::DevBuf seq_ws;        // workspace of the tiled order-exact accumulation
+  int seq_impl = 0;          // 0 auto (tiled for long chains), 1 single-CTA kernel only (TDR_SEQ_IMPL)
   tdr::DevBuf idx;           // resampled indices
   tdr::DevBuf scal;          // small device scalars (sums, stats, argmax, pose)
   tdr::DevBuf pose_tmp;      // 4 x n floats (ml-state columns)
@@ -158,7 +160,7 @@ namespace tdr {
 // scalar slots in ctx->scal (floats unless noted)
 enum {
   SC_SUM = 0, SC_NVALID, SC_MEAN, SC_BS, SC_NUNDER, SC_FALLBACK,     // stats (6 floats, ABI order)
-  SC_S1, SC_S2, SC_REP, SC_ARGMAX /*int*/, SC_ARGVAL,
+  SC_S1, SC_S2, SC_REP, SC_ARGMAX /*int*/, SC_ARGVAL, SC_BSRAW /* sequential sum of lower squared deviations */,
   SC_MMA_MAXCOUNT = 12,     // int: max class-summed scan count (fp16 exactness check of the tensor-core path)
   SC_CHAIN = 16,            // 8 chain totals
   SC_DBL = 32,              // doubles from here (8-byte aligned): sumsq, count_valid, count_under ...

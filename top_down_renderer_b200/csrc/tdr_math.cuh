@@ -293,6 +293,54 @@ TDR_HD IncPair inc_pair(float w, int E, bool* irregular) {
   return r;
 }
 
+// The same pair for an accumulation whose addend is a DOUBLE:  s = (float)((double)s + d), d >= 0
+// (particle_filter.cpp:123: bottom_stddev += std::pow(w - mean, 2) with a float accumulator).  The sum is first
+// rounded to double: inside binade E that grid is 2^(E-52), and because s is a multiple of 2^(E-23) the rounded
+// addend d' does not depend on s; the float rounding of s + d' then follows the usual rule.  For a float-valued
+// d this reduces to inc_pair.  strict_denormal: in the denormal binade a double addend can carry bits below the
+// double grid assumed here, so every nonzero addend forces a real add (never more than a handful of elements).
+TDR_HD IncPair inc_pair_d(double d, int E, bool strict_denormal, bool* irregular) {
+  IncPair r; r.a = r.b = 0; *irregular = false;
+  uint64_t u;
+#if defined(__CUDA_ARCH__)
+  u = (uint64_t)__double_as_longlong(d);
+#else
+  memcpy(&u, &d, 8);
+#endif
+  if ((u << 1) == 0) return r;                                   // +-0
+  const uint32_t ex = (uint32_t)((u >> 52) & 0x7ff);
+  if ((u >> 63) || ex == 0x7ff) { *irregular = true; r.a = r.b = TDR_INC_SAT; return r; }
+  if (E == -127 && strict_denormal) { r.a = r.b = TDR_INC_SAT; return r; }
+  const int E_eff = E == -127 ? -126 : E;
+  // d = md * 2^ed
+  const uint64_t md = ex ? ((u & 0xfffffffffffffull) | (1ull << 52)) : (u & 0xfffffffffffffull);
+  const int ed = (ex ? (int)ex : 1) - 1075;
+  // d >= 2^(E_eff+1) certainly leaves the binade
+  const int msb = 63 - (int)
+#if defined(__CUDA_ARCH__)
+      __clzll((long long)md);
+#else
+      __builtin_clzll(md);
+#endif
+  if (msb + ed >= E_eff + 1) { r.a = r.b = TDR_INC_SAT; return r; }
+  // D = RN_even(d / 2^(E_eff - 52)), the double-rounded addend in units of the double grid
+  const int shift = (E_eff - 52) - ed;
+  uint64_t D;
+  if (shift <= 0) D = md << (-shift);                            // fits: d < 2^(E_eff+1)  ->  D < 2^53
+  else if (shift > 54) D = 0;
+  else {
+    const uint64_t q0 = md >> shift, rem0 = md & ((1ull << shift) - 1ull), half0 = 1ull << (shift - 1);
+    D = q0 + ((rem0 > half0 || (rem0 == half0 && (q0 & 1ull))) ? 1ull : 0ull);
+  }
+  // float grid = 2^29 double-grid units
+  const uint32_t q = (uint32_t)(D >> 29);
+  const uint32_t rem = (uint32_t)(D & ((1u << 29) - 1u)), half = 1u << 28;
+  if (rem > half) { r.a = r.b = q + 1u; }
+  else if (rem < half) { r.a = r.b = q; }
+  else { r.a = q + (q & 1u); r.b = q + 1u - (q & 1u); }
+  return r;
+}
+
 // upper limit of m inside binade E (exclusive)
 TDR_HD uint32_t binade_limit(int E) { return E == -127 ? 0x800000u : 0x1000000u; }
 

@@ -17,6 +17,9 @@ struct SeqJob {
   float* runmax_out;   // optional: max_{k<=j} s_k per element (contiguous, length count)
   float* total_out;    // final s
   int skip_nan;        // NaN elements are skipped (== add +0), particle_filter.cpp:112
+  int mode;            // 0: addend = x (float).  1: addend = (double)(x - param)^2 for non-NaN x < param, else 0
+                       //    (lower-half squared deviations, particle_filter.cpp:120-125; float accumulator, double adds)
+  const float* param;  // device scalar (mode 1: the mean, scal[SC_MEAN])
 };
 #define TDR_MAX_JOBS 8
 struct SeqJobs { SeqJob j[TDR_MAX_JOBS]; };
@@ -24,6 +27,19 @@ struct SeqJobs { SeqJob j[TDR_MAX_JOBS]; };
 static const int SEQ_THREADS = 1024;
 static const int SEQ_ITEMS = 4;
 static const int SEQ_CHUNK = SEQ_THREADS * SEQ_ITEMS;
+
+// addend j of a chain as a double (exact for float chains)
+__device__ __forceinline__ double seq_elem(const SeqJob& job, long long j) {
+  float w = job.x[job.start + j * job.stride];
+  if (job.mode == 0) {
+    if (job.skip_nan && w != w) w = 0.f;
+    return (double)w;
+  }
+  const float mean = __ldg(job.param);
+  if (w == w && w < mean) { float dv = TDR_FSUB(w, mean); return (double)dv * (double)dv; }
+  return 0.0;
+}
+__device__ __forceinline__ float seq_add(float S, double d) { return (float)((double)S + d); }
 
 __device__ __forceinline__ IncPair shfl_up_pair(IncPair v, int d) {
   IncPair r;
@@ -33,8 +49,11 @@ __device__ __forceinline__ IncPair shfl_up_pair(IncPair v, int d) {
 }
 
 // grid.x = number of jobs; one CTA walks its chain chunk by chunk.
-__global__ void __launch_bounds__(SEQ_THREADS) k_exact_seq(SeqJobs jobs) {
+// only_flagged != nullptr: run a job only when its flag is set (fallback of the tiled path for chains with
+// negative / NaN / inf elements)
+__global__ void __launch_bounds__(SEQ_THREADS) k_exact_seq(SeqJobs jobs, const int* __restrict__ only_flagged) {
   const SeqJob job = jobs.j[blockIdx.x];
+  if (only_flagged && only_flagged[blockIdx.x] == 0) return;
   __shared__ IncPair s_warp[32];
   __shared__ int s_cross;          // first crossing position inside the chunk (relative), or chunk_len
   __shared__ uint32_t s_mprev;     // m of the element just before the crossing
@@ -53,9 +72,7 @@ __global__ void __launch_bounds__(SEQ_THREADS) k_exact_seq(SeqJobs jobs) {
       if (tid == 0) {
         float S = s_S, rm = s_rmax;
         for (long long j = pos; j < job.count; j++) {
-          float w = job.x[job.start + j * job.stride];
-          if (job.skip_nan && w != w) w = 0.f;
-          S = TDR_FADD(S, w);
+          S = seq_add(S, seq_elem(job, j));
           if (S > rm) rm = S;
           if (job.runmax_out) job.runmax_out[j] = rm;
         }
@@ -75,19 +92,14 @@ __global__ void __launch_bounds__(SEQ_THREADS) k_exact_seq(SeqJobs jobs) {
 
     // ---- per-thread pairs (blocked: thread owns SEQ_ITEMS consecutive elements)
     IncPair loc[SEQ_ITEMS];
-    float wv[SEQ_ITEMS];
     IncPair agg; agg.a = agg.b = 0;
 #pragma unroll
     for (int k = 0; k < SEQ_ITEMS; k++) {
       int j = tid * SEQ_ITEMS + k;
-      float w = 0.f;
-      if (j < chunk_len) {
-        w = job.x[job.start + (pos + j) * job.stride];
-        if (job.skip_nan && w != w) w = 0.f;
-      }
-      wv[k] = w;
+      double w = 0.0;
+      if (j < chunk_len) w = seq_elem(job, pos + j);
       bool irr;
-      IncPair pr = inc_pair(w, E, &irr);
+      IncPair pr = inc_pair_d(w, E, job.mode != 0, &irr);
       agg = pair_compose(agg, pr);
       loc[k] = agg;                       // inclusive within the thread
     }
@@ -150,9 +162,7 @@ __global__ void __launch_bounds__(SEQ_THREADS) k_exact_seq(SeqJobs jobs) {
       if (cross > 0 && S > rm) rm = S;
       long long np = pos + cross;
       if (cross < chunk_len) {
-        float w = job.x[job.start + (pos + cross) * job.stride];
-        if (job.skip_nan && w != w) w = 0.f;
-        S = TDR_FADD(S, w);
+        S = seq_add(S, seq_elem(job, pos + cross));
         if (S > rm) rm = S;
         if (job.runmax_out) job.runmax_out[pos + cross] = rm;
         np += 1;
@@ -163,6 +173,324 @@ __global__ void __launch_bounds__(SEQ_THREADS) k_exact_seq(SeqJobs jobs) {
     __syncthreads();
   }
   if (tid == 0 && job.total_out) *job.total_out = s_S;
+}
+
+
+// ================================================================================================
+// Tiled (multi-CTA) order-exact accumulation for long chains.
+//
+// The chain is cut into tiles of SQ_TILE elements.  (0) per-tile double sums give an approximate prefix, hence
+// for every tile a small window of binades the exact running sum can be in; (1) every tile reduces its
+// elements to one IncPair per candidate binade (grid-parallel); (2) ONE CTA per chain walks the tiles: a block
+// scan over the tile pairs of the current binade finds the tile in which the sum leaves the binade (or whose
+// window does not contain it), that tile alone is resolved element-wise, and the walk continues in the new
+// binade — ~25 iterations for 1e6 normalised weights instead of n/4096 dependent chunk steps; (3) with the
+// exact sum at every tile start known, all tiles emit their prefix values in parallel.  The window only affects
+// speed: a tile outside its window is resolved element-wise, so the result is exact regardless.
+// Chains with negative / NaN / inf elements fall back to k_exact_seq (flag set by step 0).
+// ================================================================================================
+static const int SQ_THREADS = 512;
+static const int SQ_ITEMS = 4;
+static const int SQ_TILE = SQ_THREADS * SQ_ITEMS;     // 2048
+static const int SQ_KMAX = 4;                         // candidate binades per tile
+
+struct SeqWs {            // per-job workspace (device pointers)
+  double* tile_sum;       // [n_tiles]   approximate sums, then exclusive approximate prefix
+  int* win_lo;            // [n_tiles]   first candidate binade
+  IncPair* agg;           // [n_tiles][SQ_KMAX]
+  float* tile_start;      // [n_tiles]   exact running sum at the tile start
+  int* flag;              // [1] irregular elements seen
+};
+struct SeqWsAll { SeqWs w[TDR_MAX_JOBS]; };
+
+
+// ordered block reduction / scan of IncPairs (SQ_THREADS threads).  Returns the inclusive scan value of this
+// thread; *total = composition of all threads.
+__device__ __forceinline__ IncPair block_scan_pairs(IncPair v, IncPair* s_warp, IncPair* total) {
+  const int lane = threadIdx.x & 31, warp = threadIdx.x >> 5;
+  IncPair incl = v;
+#pragma unroll
+  for (int d = 1; d < 32; d <<= 1) {
+    IncPair o = shfl_up_pair(incl, d);
+    if (lane >= d) incl = pair_compose(o, incl);
+  }
+  if (lane == 31) s_warp[warp] = incl;
+  __syncthreads();
+  if (warp == 0) {
+    IncPair w; w.a = w.b = 0;
+    if (lane < SQ_THREADS / 32) w = s_warp[lane];
+#pragma unroll
+    for (int d = 1; d < 32; d <<= 1) {
+      IncPair o = shfl_up_pair(w, d);
+      if (lane >= d) w = pair_compose(o, w);
+    }
+    if (lane < SQ_THREADS / 32) s_warp[lane] = w;
+  }
+  __syncthreads();
+  if (warp > 0) incl = pair_compose(s_warp[warp - 1], incl);
+  if (total) *total = s_warp[SQ_THREADS / 32 - 1];
+  __syncthreads();
+  return incl;
+}
+
+// (0) approximate tile sums + irregular flag
+__global__ void __launch_bounds__(SQ_THREADS) k_seq_tile_sums(SeqJobs jobs, SeqWsAll ws) {
+  const SeqJob job = jobs.j[blockIdx.y];
+  const long long base = (long long)blockIdx.x * SQ_TILE;
+  if (base >= job.count) return;
+  __shared__ double s_d[SQ_THREADS / 32];
+  double acc = 0.0; bool irr = false;
+#pragma unroll
+  for (int k = 0; k < SQ_ITEMS; k++) {
+    long long j = base + threadIdx.x * SQ_ITEMS + k;
+    if (j < job.count) {
+      double w = seq_elem(job, j);
+      if (!(w >= 0.0) || w > 1e30) irr = true;              // negative / NaN / inf / huge: sequential fallback
+      acc += w;
+    }
+  }
+  for (int o = 16; o > 0; o >>= 1) acc += __shfl_xor_sync(0xffffffffu, acc, o);
+  if ((threadIdx.x & 31) == 0) s_d[threadIdx.x >> 5] = acc;
+  if (irr) atomicOr(ws.w[blockIdx.y].flag, 1);
+  __syncthreads();
+  if (threadIdx.x == 0) {
+    double t = 0.0;
+    for (int w = 0; w < SQ_THREADS / 32; w++) t += s_d[w];
+    ws.w[blockIdx.y].tile_sum[blockIdx.x] = t;
+  }
+}
+
+// (0b) one CTA per job: exclusive scan of the tile sums (double) -> candidate binade window per tile
+__global__ void __launch_bounds__(SQ_THREADS) k_seq_plan(SeqJobs jobs, SeqWsAll ws) {
+  const SeqJob job = jobs.j[blockIdx.x];
+  SeqWs w = ws.w[blockIdx.x];
+  if (*w.flag) return;
+  const int n_tiles = (int)((job.count + SQ_TILE - 1) / SQ_TILE);
+  __shared__ double s_w[SQ_THREADS / 32];
+  __shared__ double s_carry;
+  if (threadIdx.x == 0) s_carry = 0.0;
+  __syncthreads();
+  const int lane = threadIdx.x & 31, warp = threadIdx.x >> 5;
+  for (int base = 0; base < n_tiles; base += SQ_THREADS) {
+    const int t = base + threadIdx.x;
+    const double v = t < n_tiles ? w.tile_sum[t] : 0.0;
+    double inc = v;
+    for (int d = 1; d < 32; d <<= 1) { double o = __shfl_up_sync(0xffffffffu, inc, d); if (lane >= d) inc += o; }
+    if (lane == 31) s_w[warp] = inc;
+    __syncthreads();
+    double pre = s_carry;
+    for (int k = 0; k < warp; k++) pre += s_w[k];
+    const double start = pre + inc - v, end = pre + inc;
+    if (t < n_tiles) {
+      // the exact fp32 running sum differs from the real sum by at most ~n * 2^-24 relative: one binade of
+      // margin on the low side covers it (and a wrong window is only slower, never wrong)
+      int e_lo = binade_of((float)(start * 0.7));
+      int e_hi = binade_of((float)(end * 1.4));
+      if (start <= 0.0) e_lo = -127;
+      if (e_hi - e_lo + 1 > SQ_KMAX) e_lo = 1000;          // too many binades inside the tile: resolve element-wise
+      w.win_lo[t] = e_lo;
+    }
+    __syncthreads();
+    if (threadIdx.x == SQ_THREADS - 1) s_carry = end;
+    __syncthreads();
+  }
+}
+
+// (1) per tile: one IncPair per candidate binade
+__global__ void __launch_bounds__(SQ_THREADS) k_seq_tile_aggs(SeqJobs jobs, SeqWsAll ws) {
+  const SeqJob job = jobs.j[blockIdx.y];
+  SeqWs w = ws.w[blockIdx.y];
+  const long long base = (long long)blockIdx.x * SQ_TILE;
+  if (base >= job.count || *w.flag) return;
+  const int e_lo = w.win_lo[blockIdx.x];
+  if (e_lo > 500) return;
+  __shared__ IncPair s_warp[SQ_THREADS / 32];
+  double x[SQ_ITEMS];
+#pragma unroll
+  for (int k = 0; k < SQ_ITEMS; k++) {
+    long long j = base + threadIdx.x * SQ_ITEMS + k;
+    x[k] = j < job.count ? seq_elem(job, j) : 0.0;
+  }
+  for (int c = 0; c < SQ_KMAX; c++) {
+    const int E = e_lo + c;
+    IncPair agg; agg.a = agg.b = 0;
+    if (E <= 127) {
+#pragma unroll
+      for (int k = 0; k < SQ_ITEMS; k++) { bool irr; agg = pair_compose(agg, inc_pair_d(x[k], E, job.mode != 0, &irr)); }
+    }
+    IncPair total;
+    block_scan_pairs(agg, s_warp, &total);
+    if (threadIdx.x == 0) w.agg[(size_t)blockIdx.x * SQ_KMAX + c] = total;
+  }
+}
+
+// element-wise exact processing of ONE tile from the exact running sum S at its start (any number of binade
+// crossings inside).  Elements live in x[] (thread owns SQ_ITEMS consecutive ones, tile_len valid in total).
+// Optionally emits the prefix values.  Returns the exact running sum at the tile end (all threads).
+__device__ float seq_resolve_tile(const double (&x)[SQ_ITEMS], bool strict, int tile_len, float S, float* __restrict__ out,
+                                  IncPair* s_warp, int* s_cross, uint32_t* s_mprev, float* s_S) {
+  int first = 0;                       // elements [0, first) are already consumed
+  while (true) {
+    const int E = binade_of(S);
+    const uint32_t m_in = mant_of(S), limit = binade_limit(E);
+    const bool odd = (m_in & 1u) != 0;
+    if (threadIdx.x == 0) *s_cross = tile_len;
+    IncPair loc[SQ_ITEMS];
+    IncPair agg; agg.a = agg.b = 0;
+#pragma unroll
+    for (int k = 0; k < SQ_ITEMS; k++) {
+      const int j = threadIdx.x * SQ_ITEMS + k;
+      IncPair pr; pr.a = pr.b = 0;
+      if (j >= first && j < tile_len) { bool irr; pr = inc_pair_d(x[k], E, strict, &irr); }
+      agg = pair_compose(agg, pr);
+      loc[k] = agg;
+    }
+    IncPair incl = block_scan_pairs(agg, s_warp, nullptr);      // contains a __syncthreads after s_cross init
+    // exclusive value of this thread = inclusive of the previous thread
+    IncPair excl = shfl_up_pair(incl, 1);
+    if ((threadIdx.x & 31) == 0) {
+      if (threadIdx.x == 0) { excl.a = 0; excl.b = 0; }
+      else excl = s_warp[(threadIdx.x >> 5) - 1];               // s_warp holds inclusive warp aggregates
+    }
+    uint32_t mv[SQ_ITEMS];
+    int my_cross = tile_len;
+#pragma unroll
+    for (int k = 0; k < SQ_ITEMS; k++) {
+      const int j = threadIdx.x * SQ_ITEMS + k;
+      IncPair t = pair_compose(excl, loc[k]);
+      mv[k] = m_in + (odd ? t.b : t.a);
+      if (j >= first && j < tile_len && mv[k] >= limit && j < my_cross) my_cross = j;
+    }
+    if (my_cross < tile_len) atomicMin(s_cross, my_cross);
+    __syncthreads();
+    const int cross = *s_cross;
+#pragma unroll
+    for (int k = 0; k < SQ_ITEMS; k++) {
+      const int j = threadIdx.x * SQ_ITEMS + k;
+      if (j >= first && j < cross) {
+        if (out) out[j] = from_binade(E, mv[k]);
+        if (j == cross - 1) *s_mprev = mv[k];
+      }
+    }
+    __syncthreads();
+    if (threadIdx.x == 0) {
+      float Sn = (cross > first) ? from_binade(E, *s_mprev) : S;
+      if (cross < tile_len) {
+        // the crossing add is a real fp32 add; x of element `cross` is fetched through shared memory below
+        *s_S = Sn;
+      } else *s_S = Sn;
+    }
+    __syncthreads();
+    if (cross >= tile_len) return *s_S;
+    // the thread owning element `cross` performs the real add and publishes it
+    if (threadIdx.x == cross / SQ_ITEMS) {
+      double wv = 0.0;
+#pragma unroll
+      for (int k = 0; k < SQ_ITEMS; k++) if (k == cross % SQ_ITEMS) wv = x[k];
+      float Sn = seq_add(*s_S, wv);
+      if (out) out[cross] = Sn;
+      *s_S = Sn;
+    }
+    __syncthreads();
+    S = *s_S;
+    first = cross + 1;
+    __syncthreads();
+    if (first >= tile_len) return S;
+  }
+}
+
+// (2) one CTA per job walks the tiles
+__global__ void __launch_bounds__(SQ_THREADS) k_seq_walk(SeqJobs jobs, SeqWsAll ws) {
+  const SeqJob job = jobs.j[blockIdx.x];
+  SeqWs w = ws.w[blockIdx.x];
+  if (*w.flag) return;
+  const int n_tiles = (int)((job.count + SQ_TILE - 1) / SQ_TILE);
+  __shared__ IncPair s_warp[SQ_THREADS / 32];
+  __shared__ int s_cross, s_first_bad;
+  __shared__ uint32_t s_mprev;
+  __shared__ float s_S;
+  __shared__ uint32_t s_mlast;
+  float S = 0.f;
+  int t0 = 0;
+  while (t0 < n_tiles) {
+    const int E = binade_of(S);
+    const uint32_t m_in = mant_of(S), limit = binade_limit(E);
+    const bool odd = (m_in & 1u) != 0;
+    const int t = t0 + threadIdx.x;
+    IncPair pr; pr.a = pr.b = 0;
+    if (t < n_tiles) {
+      const int e_lo = w.win_lo[t];
+      if (E >= e_lo && E < e_lo + SQ_KMAX) pr = w.agg[(size_t)t * SQ_KMAX + (E - e_lo)];
+      else pr.a = pr.b = TDR_INC_SAT;                       // outside the window: resolve this tile element-wise
+    }
+    if (threadIdx.x == 0) s_first_bad = SQ_THREADS;
+    IncPair incl = block_scan_pairs(pr, s_warp, nullptr);
+    IncPair excl = shfl_up_pair(incl, 1);
+    if ((threadIdx.x & 31) == 0) {
+      if (threadIdx.x == 0) { excl.a = 0; excl.b = 0; }
+      else excl = s_warp[(threadIdx.x >> 5) - 1];
+    }
+    const uint32_t m_start = m_in + (odd ? excl.b : excl.a);   // running mantissa at the start of tile t
+    const uint32_t m_end = m_in + (odd ? incl.b : incl.a);
+    const bool in_range = t < n_tiles;
+    const bool bad = in_range && m_end >= limit;               // the sum leaves the binade inside (or before) tile t
+    if (bad) atomicMin(&s_first_bad, (int)threadIdx.x);
+    __syncthreads();
+    const int fb = s_first_bad;
+    // tiles before the first bad one (and the bad one itself) start inside binade E
+    if (in_range && (int)threadIdx.x <= fb) w.tile_start[t] = from_binade(E, m_start);
+    if ((int)threadIdx.x == (fb < SQ_THREADS ? fb : SQ_THREADS - 1)) { s_mlast = (fb < SQ_THREADS) ? m_start : m_end; }
+    __syncthreads();
+    if (fb >= SQ_THREADS || t0 + fb >= n_tiles) {
+      // no crossing in this window of tiles
+      const int adv = (n_tiles - t0) < SQ_THREADS ? (n_tiles - t0) : SQ_THREADS;
+      // m after the last valid tile: thread adv-1 holds it
+      if ((int)threadIdx.x == adv - 1) s_mlast = m_end;
+      __syncthreads();
+      S = from_binade(E, s_mlast);
+      t0 += adv;
+      __syncthreads();
+      continue;
+    }
+    // resolve tile t0 + fb element-wise from its exact start
+    const int tb = t0 + fb;
+    float Sb = from_binade(E, s_mlast);
+    const long long base = (long long)tb * SQ_TILE;
+    const long long rem = job.count - base;
+    const int tile_len = rem < SQ_TILE ? (int)rem : SQ_TILE;
+    double x[SQ_ITEMS];
+#pragma unroll
+    for (int k = 0; k < SQ_ITEMS; k++) {
+      const int j = threadIdx.x * SQ_ITEMS + k;
+      x[k] = j < tile_len ? seq_elem(job, base + j) : 0.0;
+    }
+    __syncthreads();
+    S = seq_resolve_tile(x, job.mode != 0, tile_len, Sb, nullptr, s_warp, &s_cross, &s_mprev, &s_S);
+    t0 = tb + 1;
+    __syncthreads();
+  }
+  if (threadIdx.x == 0 && job.total_out) *job.total_out = S;
+}
+
+// (3) all tiles emit their prefix values from their exact start
+__global__ void __launch_bounds__(SQ_THREADS) k_seq_emit(SeqJobs jobs, SeqWsAll ws) {
+  const SeqJob job = jobs.j[blockIdx.y];
+  SeqWs w = ws.w[blockIdx.y];
+  const long long base = (long long)blockIdx.x * SQ_TILE;
+  if (base >= job.count || *w.flag || !job.runmax_out) return;
+  __shared__ IncPair s_warp[SQ_THREADS / 32];
+  __shared__ int s_cross;
+  __shared__ uint32_t s_mprev;
+  __shared__ float s_S;
+  const long long rem = job.count - base;
+  const int tile_len = rem < SQ_TILE ? (int)rem : SQ_TILE;
+  double x[SQ_ITEMS];
+#pragma unroll
+  for (int k = 0; k < SQ_ITEMS; k++) {
+    const int j = threadIdx.x * SQ_ITEMS + k;
+    x[k] = j < tile_len ? seq_elem(job, base + j) : 0.0;
+  }
+  seq_resolve_tile(x, job.mode != 0, tile_len, w.tile_start[blockIdx.x], job.runmax_out + base, s_warp, &s_cross, &s_mprev, &s_S);
 }
 
 // ------------------------------------------------------------------------------------------------
@@ -181,24 +509,23 @@ __global__ void k_mean(float* scal, const unsigned long long* nvalid) {
   scal[SC_MEAN] = TDR_FDIV(scal[SC_SUM], (float)(int)*nvalid);
 }
 
-// lower-half squared deviations (particle_filter.cpp:120-125).  The reference accumulates
-// (float)((double)acc + (double)(w-mean)^2) sequentially; here the squares are summed in double
-// (integer-free but order-insensitive to ~1e-16) and rounded once — see DESIGN.md "normalise".
-__global__ void k_under(const float* __restrict__ w, long long n, const float* __restrict__ scal, double* sumsq,
+// number of weights below the mean (particle_filter.cpp:120-125); the squared deviations themselves are an
+// order-exact chain of mode 1 (float accumulator, double addends)
+__global__ void k_under(const float* __restrict__ w, long long n, const float* __restrict__ scal,
                         unsigned long long* nunder) {
   const float mean = scal[SC_MEAN];
-  double s = 0.0; unsigned long long c = 0;
+  unsigned long long c = 0;
   for (long long i = (long long)blockIdx.x * blockDim.x + threadIdx.x; i < n; i += (long long)gridDim.x * blockDim.x) {
     float v = w[i];
-    if (v == v && v < mean) { double d = (double)TDR_FSUB(v, mean); s += d * d; c++; }
+    if (v == v && v < mean) c++;
   }
-  for (int o = 16; o > 0; o >>= 1) { s += __shfl_xor_sync(0xffffffffu, s, o); c += __shfl_xor_sync(0xffffffffu, c, o); }
-  if ((threadIdx.x & 31) == 0 && c) { atomicAdd(sumsq, s); atomicAdd(nunder, c); }
+  for (int o = 16; o > 0; o >>= 1) c += __shfl_xor_sync(0xffffffffu, c, o);
+  if ((threadIdx.x & 31) == 0 && c) atomicAdd(nunder, c);
 }
 
-__global__ void k_stats(float* scal, const double* sumsq, const unsigned long long* nunder) {
+__global__ void k_stats(float* scal, const unsigned long long* nunder) {
   int nu = (int)*nunder;
-  float bs = (float)*sumsq;
+  float bs = scal[SC_BSRAW];
   bs = TDR_FSQRT(TDR_FDIV(bs, (float)nu));                       // :126
   scal[SC_BS] = bs; scal[SC_NUNDER] = (float)nu;
   bool fallback = (scal[SC_SUM] == 0.f) || (nu < 1);             // :129
@@ -304,9 +631,44 @@ __global__ void k_resample(const float* __restrict__ runmax, long long n, float 
 }
 
 // ------------------------------------------------------------------------------------------------
+static const long long SQ_MIN_COUNT = 32768;    // shorter chains: the single-CTA kernel (fewer launches)
+
 static int launch_seq(tdr_ctx* ctx, const SeqJobs& jobs, int njobs) {
-  k_exact_seq<<<njobs, SEQ_THREADS, 0, ctx->stream>>>(jobs);
-  count_launch(ctx);
+  long long maxc = 0;
+  for (int k = 0; k < njobs; k++) maxc = jobs.j[k].count > maxc ? jobs.j[k].count : maxc;
+  if (maxc < SQ_MIN_COUNT || ctx->seq_impl == 1) {
+    k_exact_seq<<<njobs, SEQ_THREADS, 0, ctx->stream>>>(jobs, nullptr);
+    count_launch(ctx);
+    TDR_CUDA(cudaGetLastError());
+    return TDR_OK;
+  }
+  const int n_tiles = (int)((maxc + SQ_TILE - 1) / SQ_TILE);
+  // workspace: per job  tile_sum (8) + win_lo (4) + agg (8*KMAX) + tile_start (4) per tile, + one flag word
+  const size_t per_job = (size_t)n_tiles * (8 + 4 + 8 * SQ_KMAX + 4) + 256;
+  if (int e = ctx->seq_ws.reserve(per_job * njobs + 256)) return e;
+  SeqWsAll ws;
+  unsigned char* p = ctx->seq_ws.as<unsigned char>();
+  TDR_CUDA(cudaMemsetAsync(p, 0, 256, ctx->stream));              // the flags live in the first 256 bytes
+  int* flags = reinterpret_cast<int*>(p);
+  p += 256;
+  for (int k = 0; k < njobs; k++) {
+    ws.w[k].flag = flags + k;
+    ws.w[k].tile_sum = reinterpret_cast<double*>(p); p += (size_t)n_tiles * 8;
+    ws.w[k].agg = reinterpret_cast<IncPair*>(p); p += (size_t)n_tiles * 8 * SQ_KMAX;
+    ws.w[k].win_lo = reinterpret_cast<int*>(p); p += (size_t)n_tiles * 4;
+    ws.w[k].tile_start = reinterpret_cast<float*>(p); p += (size_t)n_tiles * 4;
+    p += (256 - ((size_t)n_tiles * 8 * (1 + SQ_KMAX) + (size_t)n_tiles * 8) % 256) % 256;
+  }
+  bool any_out = false;
+  for (int k = 0; k < njobs; k++) any_out |= jobs.j[k].runmax_out != nullptr;
+  dim3 grid(n_tiles, njobs);
+  k_seq_tile_sums<<<grid, SQ_THREADS, 0, ctx->stream>>>(jobs, ws);
+  k_seq_plan<<<njobs, SQ_THREADS, 0, ctx->stream>>>(jobs, ws);
+  k_seq_tile_aggs<<<grid, SQ_THREADS, 0, ctx->stream>>>(jobs, ws);
+  k_seq_walk<<<njobs, SQ_THREADS, 0, ctx->stream>>>(jobs, ws);
+  if (any_out) { k_seq_emit<<<grid, SQ_THREADS, 0, ctx->stream>>>(jobs, ws); count_launch(ctx); }
+  k_exact_seq<<<njobs, SEQ_THREADS, 0, ctx->stream>>>(jobs, flags);   // only chains flagged irregular
+  count_launch(ctx, 5);
   TDR_CUDA(cudaGetLastError());
   return TDR_OK;
 }
@@ -316,7 +678,7 @@ static int eigen_sum(tdr_ctx* ctx, const float* x, long long n, int slot) {
   float* scal = ctx->scal.as<float>();
   const long long aS2 = (n / 8) * 8;
   if (aS2 >= 8) {
-    SeqJobs jobs;
+    SeqJobs jobs; memset(&jobs, 0, sizeof(jobs));
     for (int k = 0; k < 8; k++) {
       jobs.j[k].x = x; jobs.j[k].start = k; jobs.j[k].stride = 8; jobs.j[k].count = aS2 / 8;
       jobs.j[k].runmax_out = nullptr; jobs.j[k].total_out = scal + SC_CHAIN + k; jobs.j[k].skip_nan = 0;
@@ -342,14 +704,17 @@ int normalize(tdr_ctx* ctx) {
   TDR_CUDA(cudaMemsetAsync(dbl, 0, 8 * 8, ctx->stream));   // [0]=sumsq [1]=nvalid [2]=nunder [3]=argmax key
   const int blocks = (int)((n + 1023) / 1024 < ctx->sm_count * 4 ? (n + 1023) / 1024 : ctx->sm_count * 4);
   // sum / num_valid (:108-116): sequential fp32 over non-NaN weights
-  SeqJobs jobs;
+  SeqJobs jobs; memset(&jobs, 0, sizeof(jobs));
   jobs.j[0].x = w; jobs.j[0].start = 0; jobs.j[0].stride = 1; jobs.j[0].count = n; jobs.j[0].runmax_out = nullptr;
   jobs.j[0].total_out = scal + SC_SUM; jobs.j[0].skip_nan = 1;
   if (int e = launch_seq(ctx, jobs, 1)) return e;
   k_count_valid<<<blocks, 256, 0, ctx->stream>>>(w, n, u64 + 1);
   k_mean<<<1, 1, 0, ctx->stream>>>(scal, u64 + 1);
-  k_under<<<blocks, 256, 0, ctx->stream>>>(w, n, scal, dbl, u64 + 2);
-  k_stats<<<1, 1, 0, ctx->stream>>>(scal, dbl, u64 + 2);
+  k_under<<<blocks, 256, 0, ctx->stream>>>(w, n, scal, u64 + 2);
+  // bottom_stddev (:120-125): float accumulator, double addends, sequential -> order-exact chain of mode 1
+  jobs.j[0].total_out = scal + SC_BSRAW; jobs.j[0].skip_nan = 0; jobs.j[0].mode = 1; jobs.j[0].param = scal + SC_MEAN;
+  if (int e = launch_seq(ctx, jobs, 1)) return e;
+  k_stats<<<1, 1, 0, ctx->stream>>>(scal, u64 + 2);
   k_fill_nan<<<blocks, 256, 0, ctx->stream>>>(w, n, scal);
   count_launch(ctx, 5);
   if (int e = eigen_sum(ctx, w, n, SC_S1)) return e;
@@ -366,7 +731,7 @@ int normalize(tdr_ctx* ctx) {
 // order-exact sequential fp32 totals of up to 8 columns (pose sums, particle_filter.cpp:195-197)
 int exact_sums(tdr_ctx* ctx, const float* const* cols, long long n, int ncols, float* totals_dev) {
   TDR_REQUIRE(ncols >= 1 && ncols <= TDR_MAX_JOBS, TDR_EINVAL, "bad column count");
-  SeqJobs jobs;
+  SeqJobs jobs; memset(&jobs, 0, sizeof(jobs));
   for (int k = 0; k < ncols; k++) {
     jobs.j[k].x = cols[k]; jobs.j[k].start = 0; jobs.j[k].stride = 1; jobs.j[k].count = n;
     jobs.j[k].runmax_out = nullptr; jobs.j[k].total_out = totals_dev + k; jobs.j[k].skip_nan = 0;
@@ -380,7 +745,7 @@ int build_prefix(tdr_ctx* ctx) {
   TDR_REQUIRE(n > 0, TDR_ESTATE, "no weights");
   if (int e = ctx->prefix.reserve((size_t)n * 4)) return e;
   if (int e = ctx->scal.reserve(SC_TOTAL * 4)) return e;
-  SeqJobs jobs;
+  SeqJobs jobs; memset(&jobs, 0, sizeof(jobs));
   jobs.j[0].x = ctx->weights.as<float>(); jobs.j[0].start = 0; jobs.j[0].stride = 1; jobs.j[0].count = n;
   jobs.j[0].runmax_out = ctx->prefix.as<float>(); jobs.j[0].total_out = ctx->scal.as<float>() + SC_CHAIN + 8;
   jobs.j[0].skip_nan = 0;
