@@ -332,7 +332,7 @@ def run_gpu(args, wl):
                        "p50_ms": 1e3 * float(np.median(e2e_t)), "timer": "host wall clock around set_points+step+pose"},
                "gpu_launches": int(launches),
                "wall_s_timed_region": t_wall,
-               "roofline": {"bound": "hbm", "kernel": "k_score_search" if wl["shifts"] > 1 else "k_score_track",
+               "roofline": {"bound": "hbm", "kernel": "k_score_mma (tcgen05 gather-GEMM)" if wl["shifts"] > 1 else "k_score_track",
                             "achieved": achieved, "peak": peak, "unit": "GB/s", "frac": achieved / peak,
                             "traffic": traffic, "peak_source": peak_src,
                             "algorithmic_bytes_per_launch": n * b_score(C), "kernel_ms": score_ms}}

@@ -126,6 +126,9 @@ int tdr_create(tdr_ctx** out, int device) {
   }
   if (const char* e = getenv("TDR_SEQ_IMPL")) c->seq_impl = atoi(e) == 1 ? 1 : 0;
   if (const char* e = getenv("TDR_MMA_TILES")) { int v = atoi(e); if (v == 1 || v == 2 || v == 4) c->mma_tiles = v; }
+  if (const char* e = getenv("TDR_MMA_SPLIT")) { int v = atoi(e); if (v == 1 || v == 2 || v == 4) c->mma_split = v; }
+  if (const char* e = getenv("TDR_MMA_SEG_SHIFT")) { int v = atoi(e); if (v >= 0 && v <= 5) c->mma_seg_shift = v; }
+  if (const char* e = getenv("TDR_MMA_CTAS")) c->mma_ctas = atoi(e);
   if (const char* e = getenv("TDR_MMA_ST_SHIFT")) { int v = atoi(e); if (v >= 5 && v <= 16) c->mma_st_shift = v; }
   TDR_CUDA(cudaStreamCreateWithFlags(&c->stream, cudaStreamNonBlocking));
   if (int r = c->scal.reserve(SC_TOTAL * 4)) { delete c; return r; }
@@ -212,7 +215,7 @@ int tdr_map_set_polar_table(tdr_ctx* ctx, const float* tab, int n_theta, int n_r
   if (int e = ctx->tab.reserve(bytes)) return e;
   TDR_CUDA(cudaMemcpyAsync(ctx->tab.p, tab, bytes, cudaMemcpyHostToDevice, ctx->stream));
   TDR_CUDA(cudaStreamSynchronize(ctx->stream));
-  ctx->n_theta = n_theta; ctx->n_r = n_r; ctx->have_tab = true;
+  ctx->n_theta = n_theta; ctx->n_r = n_r; ctx->have_tab = true; ctx->tab_dirty = true;
   return TDR_OK;
 }
 

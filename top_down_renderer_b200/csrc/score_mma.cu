@@ -186,7 +186,7 @@ __global__ void k_build_scan_operand(const float* __restrict__ img, int C, int n
 struct BinParams {
   const float *init_x, *init_y, *dx, *dy, *scale; const uint8_t* have_init;   // particle mode
   const float* centers;                                                       // grid mode
-  long long n; float resolution; int rows, cols, st_shift, super_x, per_super, n_bins;
+  long long n; float resolution; int rows, cols, st_shift, seg_shift, super_x, per_super, n_bins;
 };
 __device__ __forceinline__ int bin_of(const BinParams& b, long long i) {
   float x, y;
@@ -201,7 +201,7 @@ __device__ __forceinline__ int bin_of(const BinParams& b, long long i) {
   // super-tile (2^st_shift px square, row-major over the map), then pixel row, then 32-px column segment
   const int S = 1 << b.st_shift, m = S - 1;
   const int sup = (r >> b.st_shift) * b.super_x + (c >> b.st_shift);
-  return sup * b.per_super + (r & m) * (S >> 5) + ((c & m) >> 5);
+  return sup * b.per_super + (r & m) * (S >> b.seg_shift) + ((c & m) >> b.seg_shift);
 }
 __global__ void k_bin_count(BinParams b, int* __restrict__ counts) {
   for (long long i = (long long)blockIdx.x * blockDim.x + threadIdx.x; i < b.n; i += (long long)gridDim.x * blockDim.x) {
@@ -272,6 +272,13 @@ __global__ void k_bin_scatter(BinParams b, int* __restrict__ cursor, int* __rest
 // ------------------------------------------------------------------------------------------------
 // the gather-GEMM
 // ------------------------------------------------------------------------------------------------
+// The polar offset table is read with a warp-uniform index once per cell by every gather thread.  As a global
+// load it queued behind the record loads in the L1 pipe and a quarter of all stall samples sat on the first
+// FMUL of the index math; from constant memory (uniform LDC through the constant cache) it is off that path.
+static const int MMA_TAB_MAX = 4096;
+__constant__ float2 c_tab[MMA_TAB_MAX];
+static const void* g_tab_owner = nullptr;     // device table currently mirrored in c_tab
+
 struct MmaParams {
   const uint4* map16; int rows, cols; float resolution;
   const float2* tab; int P, P_pad; float res;
@@ -291,10 +298,14 @@ static const int MMA_G = 2;        // lattice cells per pipeline stage
 // bank groups (conflict-free STS.128).
 static const int A_LBO = 2048 + 64;
 static const int A_TILE = 4224;
-template <int N, int T> struct MmaCfg {
-  static const int kThreads = 128 * T + 64;
+// T = 128-hypothesis tiles per CTA; R = gather threads per hypothesis row (the R threads of a row take turns
+// stage by stage, so the loads in flight per SM double without doubling the hypotheses — and their map
+// footprint — that are in flight together)
+template <int N, int T, int R> struct MmaCfg {
+  static const int kThreads = 128 * T * R + 64;
   static const int kTmemCols = T * N <= 128 ? 128 : (T * N <= 256 ? 256 : 512);
-  static const int kCtasPerSm = 512 / kTmemCols;           // TMEM is the co-residency limit
+  static const int kByTmem = 512 / kTmemCols, kByRegs = 65536 / (kThreads * 88) < 1 ? 1 : 65536 / (kThreads * 88);
+  static const int kCtasPerSm = kByTmem < kByRegs ? kByTmem : kByRegs;
   static const int kABytes = MMA_G * T * A_TILE;          // per stage
   static const int kBBytes = MMA_G * N * 32;              // per stage
   static const int kStageBytes = kABytes + kBBytes;
@@ -303,9 +314,10 @@ template <int N, int T> struct MmaCfg {
   static const int kSmem = kStages * kStageBytes + 256;
 };
 
-template <int N, int T>
-__global__ void __launch_bounds__(128 * T + 64, MmaCfg<N, T>::kCtasPerSm) k_score_mma(MmaParams sp) {
-  using Cfg = MmaCfg<N, T>;
+template <int N, int T, int R>
+__global__ void __launch_bounds__(128 * T * R + 64, MmaCfg<N, T, R>::kCtasPerSm) k_score_mma(MmaParams sp) {
+  using Cfg = MmaCfg<N, T, R>;
+  constexpr int GW = 4 * T * R;        // gather warps
   constexpr int NS = Cfg::kStages;
   constexpr int S_PAD = N / 2;
   extern __shared__ __align__(128) unsigned char smem[];
@@ -316,7 +328,7 @@ __global__ void __launch_bounds__(128 * T + 64, MmaCfg<N, T>::kCtasPerSm) k_scor
   const int tid = threadIdx.x, warp = tid >> 5, lane = tid & 31;
   const uint32_t bar_full = smem_u32(bars), bar_empty = smem_u32(bars + NS), bar_accum = smem_u32(bars + 2 * NS);
 
-  if (warp == 4 * T + 1) tmem_alloc(smem_u32(s_tmem), Cfg::kTmemCols);
+  if (warp == GW + 1) tmem_alloc(smem_u32(s_tmem), Cfg::kTmemCols);
   if (tid == 0) {
     for (int s = 0; s < NS; s++) { mbar_init(bar_full + 8 * s, 4 * T + 1); mbar_init(bar_empty + 8 * s, 1); }
     mbar_init(bar_accum, 1);
@@ -333,12 +345,13 @@ __global__ void __launch_bounds__(128 * T + 64, MmaCfg<N, T>::kCtasPerSm) k_scor
   uint32_t it = 0;                 // pipeline iteration counter, continues across batches (same sequence in every role)
   uint32_t local_batch = 0;
 
-  if (warp < 4 * T) {
+  if (warp < GW) {
     // =========================== gather + epilogue ===========================
-    const int t = warp >> 2, m = tid & 127;
+    const int sub = warp / (4 * T);                      // which of the R threads of a row this is
+    const int t = (warp % (4 * T)) >> 2, m = tid & 127;
     const unsigned char* map_bytes = reinterpret_cast<const unsigned char*>(sp.map16);
     for (long long batch = blockIdx.x; batch < n_batches; batch += gridDim.x, local_batch++) {
-      const long long slot = batch * per_batch + tid;
+      const long long slot = batch * per_batch + (tid % (128 * T));
       long long i = -1;
       if (slot < sp.n_work) i = sp.perm ? (long long)sp.perm[slot] : slot;
       float cx = 0.f, cy = 0.f, sc = 1.f;
@@ -364,7 +377,7 @@ __global__ void __launch_bounds__(128 * T + 64, MmaCfg<N, T>::kCtasPerSm) k_scor
           const int p = k * MMA_G + g;
           rec[g][0] = make_uint4(0, 0, 0, 0); rec[g][1] = rec[g][0];
           if (active && p < sp.P) {
-            const float2 tb = __ldg(sp.tab + p);
+            const float2 tb = c_tab[p];
             const int r = lattice_index(tb.x, sc, sp.res, oy);
             const int c = lattice_index(tb.y, sc, sp.res, ox);
             if (r >= 0 && r < sp.rows && c >= 0 && c < sp.cols)
@@ -387,15 +400,16 @@ __global__ void __launch_bounds__(128 * T + 64, MmaCfg<N, T>::kCtasPerSm) k_scor
       };
 
       uint4 ra[MMA_G][2], rb[MMA_G][2];
-      load_stage(0, ra);
+      if (sub < K_ITERS) load_stage(sub, ra);
 #pragma unroll 1
-      for (int k = 0; k < K_ITERS; k += 2) {
-        if (k + 1 < K_ITERS) load_stage(k + 1, rb);
+      for (int k = sub; k < K_ITERS; k += 2 * R) {       // this thread's stages: sub, sub + R, ... (two in flight)
+        if (k + R < K_ITERS) load_stage(k + R, rb);
         store_stage(it + k, ra);
-        if (k + 2 < K_ITERS) load_stage(k + 2, ra);
-        if (k + 1 < K_ITERS) store_stage(it + k + 1, rb);
+        if (k + 2 * R < K_ITERS) load_stage(k + 2 * R, ra);
+        if (k + R < K_ITERS) store_stage(it + k + R, rb);
       }
       it += K_ITERS;
+      if (sub != 0) continue;                            // the first thread of each row owns the epilogue
 
       // ---- epilogue: this thread's accumulator row
       mbar_wait(bar_accum, local_batch & 1u);
@@ -433,7 +447,7 @@ __global__ void __launch_bounds__(128 * T + 64, MmaCfg<N, T>::kCtasPerSm) k_scor
       }
       tc_fence_before();           // TMEM reads are done before the next batch's first full-barrier arrive
     }
-  } else if (warp == 4 * T) {
+  } else if (warp == GW) {
     // =========================== scan-operand loader ===========================
     if (lane == 0) {
       for (long long batch = blockIdx.x; batch < n_batches; batch += gridDim.x) {
@@ -475,7 +489,7 @@ __global__ void __launch_bounds__(128 * T + 64, MmaCfg<N, T>::kCtasPerSm) k_scor
   }
   tc_fence_before();
   __syncthreads();
-  if (warp == 4 * T + 1) tmem_dealloc(tmem_base, Cfg::kTmemCols);
+  if (warp == GW + 1) tmem_dealloc(tmem_base, Cfg::kTmemCols);
 }
 
 // ------------------------------------------------------------------------------------------------
@@ -509,6 +523,7 @@ int score_mma(tdr_ctx* ctx, float res, bool grid_mode, long long n_items, float 
   *used = false;
   if (!mma_usable(ctx, n_shifts)) return TDR_OK;
   const int P = ctx->n_theta * ctx->n_r;
+  if (P > MMA_TAB_MAX) return TDR_OK;
   const int S_pad = n_shifts + 1 <= 48 ? 48 : 112;
   const int N = 2 * S_pad;
   const int P_pad = (P + 2 * MMA_G - 1) / (2 * MMA_G) * (2 * MMA_G);     // even number of stages keeps the 2x unroll simple
@@ -545,7 +560,8 @@ int score_mma(tdr_ctx* ctx, float res, bool grid_mode, long long n_items, float 
   bp.st_shift = ctx->mma_st_shift;
   while ((1 << bp.st_shift) < 32) bp.st_shift++;
   bp.super_x = (ctx->cols >> bp.st_shift) + 1;
-  bp.per_super = (1 << bp.st_shift) * ((1 << bp.st_shift) >> 5);
+  bp.seg_shift = ctx->mma_seg_shift;
+  bp.per_super = (1 << bp.st_shift) * ((1 << bp.st_shift) >> bp.seg_shift);
   {
     long long nb = (long long)((ctx->rows >> bp.st_shift) + 1) * bp.super_x * bp.per_super + 1;
     TDR_REQUIRE(nb < (1ll << 28), TDR_EUNSUPPORTED, "map too large for the hypothesis binning (%lld bins)", nb);
@@ -566,6 +582,10 @@ int score_mma(tdr_ctx* ctx, float res, bool grid_mode, long long n_items, float 
   count_launch(ctx, 5);
   TDR_CUDA(cudaGetLastError());
 
+  if (g_tab_owner != ctx->tab.p || ctx->tab_dirty) {
+    TDR_CUDA(cudaMemcpyToSymbolAsync(c_tab, ctx->tab.p, (size_t)P * 8, 0, cudaMemcpyDeviceToDevice, ctx->stream));
+    g_tab_owner = ctx->tab.p; ctx->tab_dirty = false;
+  }
   MmaParams sp; memset(&sp, 0, sizeof(sp));
   sp.map16 = ctx->map16.as<uint4>(); sp.rows = ctx->rows; sp.cols = ctx->cols; sp.resolution = ctx->resolution;
   sp.tab = ctx->tab.as<float2>(); sp.P = P; sp.P_pad = P_pad; sp.res = res;
@@ -587,23 +607,32 @@ int score_mma(tdr_ctx* ctx, float res, bool grid_mode, long long n_items, float 
     sp.regularization = ctx->fp.regularization;
     sp.thetas = ctx->d_search_thetas.as<float>();
   }
-#define TDR_LAUNCH_MMA(NN, TT)                                                                                       \
+#define TDR_LAUNCH_MMA(NN, TT, RR)                                                                                   \
   do {                                                                                                                \
-    using Cfg = MmaCfg<NN, TT>;                                                                                       \
+    using Cfg = MmaCfg<NN, TT, RR>;                                                                                   \
     static bool attr = false;                                                                                         \
-    if (!attr) { TDR_CUDA(cudaFuncSetAttribute(k_score_mma<NN, TT>, cudaFuncAttributeMaxDynamicSharedMemorySize, Cfg::kSmem)); attr = true; } \
+    if (!attr) { TDR_CUDA(cudaFuncSetAttribute(k_score_mma<NN, TT, RR>, cudaFuncAttributeMaxDynamicSharedMemorySize, Cfg::kSmem)); attr = true; } \
     const long long nb = (sp.n_work + 128 * TT - 1) / (128 * TT);                                                     \
-    const long long cap = (long long)ctx->sm_count * Cfg::kCtasPerSm;                                                 \
+    const long long cap = (long long)ctx->sm_count * (ctx->mma_ctas > 0 && ctx->mma_ctas < Cfg::kCtasPerSm ? ctx->mma_ctas : Cfg::kCtasPerSm); \
     const int grid = (int)(nb < cap ? nb : cap);                                                                      \
-    k_score_mma<NN, TT><<<grid, Cfg::kThreads, Cfg::kSmem, ctx->stream>>>(sp);                                        \
+    k_score_mma<NN, TT, RR><<<grid, Cfg::kThreads, Cfg::kSmem, ctx->stream>>>(sp);                                    \
   } while (0)
+  const int cfg = ctx->mma_tiles * 10 + ctx->mma_split;
   if (S_pad == 48) {
-    if (ctx->mma_tiles == 4) TDR_LAUNCH_MMA(96, 4);
-    else if (ctx->mma_tiles == 2) TDR_LAUNCH_MMA(96, 2);
-    else TDR_LAUNCH_MMA(96, 1);
+    switch (cfg) {
+      case 41: TDR_LAUNCH_MMA(96, 4, 1); break;
+      case 21: TDR_LAUNCH_MMA(96, 2, 1); break;
+      case 22: TDR_LAUNCH_MMA(96, 2, 2); break;
+      case 11: TDR_LAUNCH_MMA(96, 1, 1); break;
+      case 14: TDR_LAUNCH_MMA(96, 1, 4); break;
+      default: TDR_LAUNCH_MMA(96, 1, 2); break;
+    }
   } else {
-    if (ctx->mma_tiles >= 2) TDR_LAUNCH_MMA(224, 2);
-    else TDR_LAUNCH_MMA(224, 1);
+    switch (cfg) {
+      case 21: case 41: TDR_LAUNCH_MMA(224, 2, 1); break;
+      case 11: TDR_LAUNCH_MMA(224, 1, 1); break;
+      default: TDR_LAUNCH_MMA(224, 1, 2); break;
+    }
   }
 #undef TDR_LAUNCH_MMA
   count_launch(ctx);

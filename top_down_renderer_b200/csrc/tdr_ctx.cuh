@@ -99,13 +99,18 @@ struct tdr_ctx {
   tdr::DevBuf scan_op;       // P_pad x N x 32 B
   tdr::DevBuf bin_counts, perm;
   int score_impl = 0;        // 0 auto, 1 CUDA cores only, 2 tensor cores whenever usable
-  int mma_tiles = 2;         // 128-hypothesis tiles per CTA; 2 tiles x 2 CTAs/SM measured best (tuning: TDR_MMA_TILES)
+  int mma_tiles = 1;         // 128-hypothesis tiles per CTA (tuning: TDR_MMA_TILES); 1 tile x 4 threads/row keeps the
+                             // in-flight footprint L2-resident (96 % L2 hits) at the speed of 2 tiles x 2 CTAs/SM
+  int mma_seg_shift = 2;     // log2 of the column-segment width of a bin (tuning: TDR_MMA_SEG_SHIFT)
+  int mma_split = 4;         // gather threads per hypothesis row (tuning: TDR_MMA_SPLIT)
+  int mma_ctas = 0;          // cap on co-resident CTAs per SM (0 = as many as TMEM allows; tuning: TDR_MMA_CTAS)
   int mma_st_shift = 10;     // log2 of the binning super-tile side in px (tuning: TDR_MMA_ST_SHIFT)
 
   // ---- polar table
   int n_theta = 0, n_r = 0;
   tdr::DevBuf tab;           // 2*P floats
   bool have_tab = false;
+  bool tab_dirty = true;     // the constant-memory mirror used by score_mma.cu needs a refresh
 
   // ---- scan
   tdr::DevBuf pts;           // raw AoS copy
