@@ -44,6 +44,10 @@ WORKLOADS = {
     "global": dict(side=4000, C=6, n=1_000_000, res=4.0, shifts=40,
                    desc="cfg3 global localization: 1M particles/GPU x 40-shift polar theta search, 4000x4000 px map "
                         "(4 km^2 @0.5 m/px), 6 classes, 65536-pt scan; rasterise+score+normalise+resample"),
+    "grid": dict(side=4000, C=6, n=1_000_000, res=4.0, shifts=100, grid=True,
+                 desc="cfg4 exhaustive grid: 1000x1000 centres (stride 4 px over 4000x4000 px, 6 classes) x 100 row shifts = "
+                      "1e8 (x, y, theta) hypotheses in total, sharded over the GPUs; rasterise + all costs + weight all-gather "
+                      "+ arg-min"),
     "tracking": dict(side=2000, C=6, n=10_000, res=0.5, shifts=1,
                      desc="cfg2 tracking: 10k particles, 2000x2000 px map, 6 classes, 65536-pt scan; "
                           "rasterise+score+normalise+resample"),
@@ -149,6 +153,16 @@ class CpuArm:
     def step(self, lo, n):
         """one reference update on particles [lo, lo+n): render + score (all host threads) + normalise + resample"""
         orc, wl, inp = self.orc, self.wl, self.inp
+        if wl.get("grid"):
+            from top_down_renderer_b200 import synth
+            if not hasattr(self, "centers"):
+                self.centers = synth.grid_centers(wl["side"], wl["side"], 4)
+            t0 = time.perf_counter()
+            scan = orc.render_polar(inp["pts"], wl["res"], ANG_RES, N_THETA, N_R, inp["lut"], wl["C"])
+            costs = orc.cost_grid(self.centers[lo:lo + n], 2.0, self.fp, self.layers, self.mask, 1.0, self.tab, N_THETA, N_R,
+                                  scan, wl["res"], np.arange(N_THETA, dtype=np.int32), n_threads=self.cores)
+            np.nanargmin(costs)
+            return time.perf_counter() - t0
         st = inp["st"][lo:lo + n].copy()
         ld = inp["ld"][lo:lo + n]
         t0 = time.perf_counter()
@@ -164,9 +178,9 @@ def run_reference(args, wl):
     rank = int(os.environ.get("RANK", "0"))
     if rank != 0:
         return
-    inp = make_inputs(wl)
+    inp = make_inputs(dict(wl, n=16, shifts=1) if wl.get("grid") else wl)
     arm = CpuArm(wl, inp)
-    n_s = min(wl["n"], 8192 if wl["shifts"] > 1 else wl["n"])
+    n_s = min(wl["n"], (2048 if wl.get("grid") else 8192) if wl["shifts"] > 1 else wl["n"])
     for i in range(args.warmup):
         arm.step((i * n_s) % max(1, wl["n"] - n_s), n_s)
     ts = []
@@ -178,8 +192,8 @@ def run_reference(args, wl):
               f"normalise + O(N) resample; oracle/tdr_oracle.cpp g++ -O2, {arm.cores} std::threads")
     out = {"impl": "reference", "metric": "particle_scores_per_sec", "value": value, "unit": "scores/s",
            "n_gpus": args.gpus, "steps": args.steps, "warmup": args.warmup, "ms_per_step": 1e3 * total / args.steps,
-           "higher_is_better": True, "scaling": "weak", "vs_baseline": None, "dtype": "f32", "data": "synthetic",
-           "config": {"workload": wl["desc"], "particles_per_step_sampled": n_s},
+           "higher_is_better": True, "scaling": "strong" if wl.get("grid") else "weak", "vs_baseline": None, "dtype": "f32",
+           "data": "synthetic", "config": {"workload": wl["desc"], "particles_per_step_sampled": n_s},
            "cpu_baseline": {"value": value, "unit": "scores/s", "cores": arm.cores, "kind": "port", "sample": sample},
            "e2e": {"value": value, "unit": "scores/s", "h2d_bytes_per_step": 0, "d2h_bytes_per_step": 0},
            "gpu_launches": 0}
@@ -358,6 +372,129 @@ def run_gpu(args, wl):
         dist.destroy_process_group()
 
 
+def run_grid(args, wl):
+    """cfg4: exhaustive (x, y, theta) grid, STRONG scaling: the lattice of centres is split over the ranks; one
+    all-gather of the costs ("weight all-gather") per step, then the arg-min on every rank."""
+    import torch
+    import torch.distributed as dist
+    from top_down_renderer_b200 import hostmath, sharded, synth
+    from top_down_renderer_b200.core import Context
+    rank = int(os.environ.get("RANK", "0"))
+    world = int(os.environ.get("WORLD_SIZE", "1"))
+    local = int(os.environ.get("LOCAL_RANK", "0"))
+    if not torch.cuda.is_available():
+        raise SystemExit("bench.py: no CUDA device — the product path has no CPU fallback")
+    torch.cuda.set_device(local)
+    if world > 1:
+        os.environ.setdefault("MASTER_ADDR", "127.0.0.1")
+        dist.init_process_group("nccl", device_id=torch.device("cuda", local))
+    side, C, res = wl["side"], wl["C"], wl["res"]
+    inp = make_inputs(dict(wl, n=16, shifts=1), rank)
+    centers_all = synth.grid_centers(side, side, 4)                       # 1000 x 1000 centres
+    n_total = centers_all.shape[0]
+    assert n_total % world == 0
+    lo, hi = sharded.shard_range(n_total, rank, world)
+    centers = np.ascontiguousarray(centers_all[lo:hi])
+    n_local = hi - lo
+    shifts = np.arange(N_THETA, dtype=np.int32)
+    S = len(shifts)
+    ctx = Context(local)
+    ctx.map_set_class_image(inp["img"], inp["lut"], C, 1.0)
+    ctx.map_set_polar_table(hostmath.polar_table(N_THETA, N_R, ANG_RES, 1.0), N_THETA, N_R)
+    ctx.scan_set_lut(inp["lut"], C)
+    ctx.pf_set_params(C, regularization=0.7)
+    stream = torch.cuda.ExternalStream(ctx.stream, device=local)
+    dev = f"cuda:{local}"
+    send = torch.empty(n_local * S, dtype=torch.float32, device=dev)
+    recv = torch.empty(world * n_local * S, dtype=torch.float32, device=dev) if world > 1 else send
+    ctx.grid_set_costs_buffer(send.data_ptr(), send.numel())
+    pts_pinned = torch.from_numpy(inp["pts"]).pin_memory()
+    flush = torch.empty(256 << 20, dtype=torch.uint8, device=dev)
+    ctx.scan_set_points_ptr(pts_pinned.data_ptr(), 32, 16, pts_pinned.shape[0])
+    ctx.scan_render_polar(res, float(ANG_RES), N_THETA, N_R, want=False)
+    ctx.grid_costs(centers, 2.0, res, shifts, want=False)                  # uploads the centres once
+    ctx.sync()
+    ctx.profile_enable(True)
+
+    def one_step():
+        with torch.cuda.stream(stream):
+            ctx.scan_render_polar(res, float(ANG_RES), N_THETA, N_R, want=False)
+            ctx.grid_run_resident(n_local, 2.0, res, shifts)
+            if world > 1:
+                dist.all_gather_into_tensor(recv, send)
+            return ctx.grid_best_dev(recv.data_ptr(), recv.numel())        # D2H of (cost, index): synchronises
+
+    def barrier():
+        if world > 1:
+            dist.barrier()
+        torch.cuda.synchronize()
+
+    evs, kern_ms, best = [], [], None
+    sampler = ClockSampler(local)
+    for i in range(args.warmup + args.steps):
+        if i == args.warmup:
+            barrier()
+            sampler.start()
+            launches0 = ctx.launch_count()
+        with torch.cuda.stream(stream):
+            flush.zero_()
+            e0, e1 = torch.cuda.Event(enable_timing=True), torch.cuda.Event(enable_timing=True)
+            e0.record(stream)
+        best = one_step()
+        e1.record(stream)
+        if i >= args.warmup:
+            evs.append((e0, e1))
+            kern_ms.append(ctx.profile_stage_ms()[1])
+    barrier()
+    clocks = sampler.stop()
+    launches = ctx.launch_count() - launches0
+    total_ms = float(sum(a.elapsed_time(b) for a, b in evs))
+    e2e_t = []
+    for i in range(args.warmup + args.steps):
+        with torch.cuda.stream(stream):
+            flush.zero_()
+        barrier()
+        t0 = time.perf_counter()
+        ctx.scan_set_points_ptr(pts_pinned.data_ptr(), 32, 16, pts_pinned.shape[0])
+        one_step()
+        if i >= args.warmup:
+            e2e_t.append(time.perf_counter() - t0)
+    e2e_total = float(np.sum(e2e_t))
+    if world > 1:
+        t = torch.tensor([total_ms, e2e_total], device=dev, dtype=torch.float64)
+        dist.all_reduce(t, op=dist.ReduceOp.MAX)
+        total_ms, e2e_total = float(t[0].item()), float(t[1].item())
+    if rank == 0:
+        peak, peak_src = peaks()
+        scores = n_total * S
+        k_ms = float(np.mean(kern_ms))
+        achieved = n_local * b_score(C) / (k_ms * 1e-3) / 1e9
+        out = {"metric": "particle_scores_per_sec", "value": scores * args.steps / (total_ms * 1e-3), "unit": "scores/s",
+               "n_gpus": world, "steps": args.steps, "warmup": args.warmup, "ms_per_step": total_ms / args.steps,
+               "higher_is_better": True, "scaling": "strong", "vs_baseline": None, "dtype": "f32", "data": "synthetic",
+               "config": {"workload": wl["desc"], "centres_total": n_total, "centres_per_gpu": n_local, "shifts": S,
+                          "map_px": [side, side], "classes": C, "polar_image": [N_THETA, N_R], "res_m_per_bin": res,
+                          "parallelism": f"centre shards x{world}, map replicated"
+                          + (", 1 all-gather(costs)/step" if world > 1 else ""),
+                          "l2": "flushed (256 MiB write) between steps, outside the timed events"},
+               "clocks": clocks, "best": {"cost": best[0], "flat_index": best[1]},
+               "stage_ms": {"score": k_ms},
+               "e2e": {"value": scores * args.steps / e2e_total, "unit": "scores/s",
+                       "h2d_bytes_per_step": int(inp["pts"].nbytes), "d2h_bytes_per_step": 12,
+                       "ms_per_step": 1e3 * e2e_total / args.steps,
+                       "timer": "host wall clock around set_points+render+grid(+all-gather)+arg-min"},
+               "gpu_launches": int(launches),
+               "roofline": {"bound": "hbm", "kernel": "k_score_mma (tcgen05 gather-GEMM)", "achieved": achieved, "peak": peak,
+                            "unit": "GB/s", "frac": achieved / peak, "traffic": None, "peak_source": peak_src,
+                            "algorithmic_bytes_per_launch": n_local * b_score(C), "kernel_ms": k_ms},
+               "cpu_baseline": None}
+        print(json.dumps(out), flush=True)
+    ctx.close()
+    if world > 1:
+        dist.barrier()
+        dist.destroy_process_group()
+
+
 def main():
     ap = argparse.ArgumentParser()
     ap.add_argument("--gpus", type=int, default=1)
@@ -374,6 +511,8 @@ def main():
         wl["n"] = args.particles
     if args.impl == "reference":
         run_reference(args, wl)
+    elif wl.get("grid"):
+        run_grid(args, wl)
     else:
         run_gpu(args, wl)
 

@@ -167,9 +167,15 @@ int tdr_step(tdr_ctx* ctx, float res, float ang_res, int n_theta, int n_r, float
  * costs_out (host) may be NULL: results stay resident, see tdr_grid_best. */
 int tdr_grid_costs(tdr_ctx* ctx, const float* centers_xy, int64_t n, float scale, float res,
                    const int32_t* shifts, int n_shifts, float* costs_out);
-/* (min cost, flat index) over the resident grid costs — what a rank contributes to the
- * multi-GPU reduction */
+/* centers_xy == NULL reuses the resident centres of the previous call (same n); then, with costs_out == NULL, the
+ * call is asynchronous on the context stream.
+ * (min cost, flat index) over the resident grid costs — what a rank contributes to the multi-GPU reduction */
 int tdr_grid_best(tdr_ctx* ctx, float* best_cost, int64_t* best_index);
+/* multi-GPU: let the grid kernel write its costs into a caller-owned device buffer (the send half of the weight
+ * all-gather; NULL restores the internal buffer), and take the arg-min over an arbitrary device array of n costs
+ * (the all-gather output; first index wins on ties, NaN never wins) */
+int tdr_grid_set_costs_buffer(tdr_ctx* ctx, void* dev_costs, int64_t capacity_floats);
+int tdr_grid_best_dev(tdr_ctx* ctx, const void* dev_costs, int64_t n, float* best_cost, int64_t* best_index);
 /* device pointers of resident buffers for collectives issued by the host layer (NCCL through
  * torch.distributed): weights (n floats) / grid costs (n*n_shifts floats) */
 int tdr_dev_ptr(tdr_ctx* ctx, int which, void** ptr, int64_t* n_elems);

@@ -575,3 +575,23 @@ def test_resample_long_chains_bit_exact(ctx, n, M, kind):
     got = ctx.pf_resample(u, M)
     want = orc.resample_fast(w, u, M)
     assert np.array_equal(got, want), np.count_nonzero(got != want)
+
+
+def test_ring_kernel_on_the_search_list_matches_list_kernel(world, monkeypatch):
+    """the all-shifts ring kernel (used for long lists / grids) run on the 40-candidate search: same weights"""
+    st, ld = synth.particles_global(4500, world.class_map, seed=5)
+    out = []
+    for kernel in ("1", "2"):
+        monkeypatch.setenv("TDR_MMA_KERNEL", kernel)
+        c = make_ctx(world)
+        c.set_score_impl(2)
+        c.scan_set_polar_images(world.scan)
+        c.pf_set_states(st.copy(), ld)
+        out.append((c.pf_score(4.0), c.pf_get_states()))
+        c.close()
+    st_o = st.copy()
+    want = orc.score_all(st_o, world.fp, world.layers, world.mask, 1.0, world.tab, N_THETA, N_R, world.scan, 4.0,
+                         world.thetas, world.shifts)
+    for w, s in out:
+        assert rel_err(w, want).max() <= WEIGHT_RTOL
+        assert (s["theta"] == st_o["theta"]).mean() > 0.995

@@ -1,8 +1,16 @@
-timeout 200 python -m pytest tests/test_gpu_parity.py -m gpu -x -q -k "mma or sharded" 2>&1 | tail -2
-for cfg in "2 1 2" "1 4 2" "1 2 2" "4 1 2"; do set -- $cfg
-  echo "T=$1 R=$2 SEG=$3"; TDR_MMA_TILES=$1 TDR_MMA_SPLIT=$2 TDR_MMA_SEG_SHIFT=$3 timeout 200 python bench.py --steps 5 --warmup 3 --no-cpu 2>&1 | python -c "
+timeout 400 python -m pytest tests -m gpu -x -q 2>&1 | tail -4
+timeout 200 python bench.py --steps 10 --warmup 3 --no-cpu 2>&1 | python -c "
 import json,sys
 for l in sys.stdin:
     if l.startswith('{'):
-        d=json.loads(l); print(d['ms_per_step'], d['stage_ms']['score'])"
-done
+        d=json.loads(l); print('global', d['ms_per_step'], d['stage_ms'])"
+timeout 300 python bench.py --workload grid --steps 5 --warmup 3 2>&1 | python -c "
+import json,sys
+for l in sys.stdin:
+    if l.startswith('{'):
+        d=json.loads(l); print('grid', d['ms_per_step'], d['stage_ms'], d['value'], d['best'])"
+TDR_MMA_KERNEL=1 timeout 300 python bench.py --workload grid --steps 3 --warmup 3 2>&1 | python -c "
+import json,sys
+for l in sys.stdin:
+    if l.startswith('{'):
+        d=json.loads(l); print('grid(list kernel)', d['ms_per_step'], d['stage_ms'], d['value'], d['best'])"

@@ -282,6 +282,20 @@ class Context:
                                        C.c_float(res), _pi(sh), len(sh), _pf(out) if want else None))
         return out
 
+    def grid_run_resident(self, n, scale, res, shifts):
+        """asynchronous re-run over the resident centres (no H2D / D2H)"""
+        sh = np.ascontiguousarray(shifts, dtype=np.int32)
+        check(self._lib.tdr_grid_costs(self._h, None, C.c_int64(n), C.c_float(scale), C.c_float(res), _pi(sh), len(sh), None))
+
+    def grid_set_costs_buffer(self, dev_ptr, capacity_floats):
+        check(self._lib.tdr_grid_set_costs_buffer(self._h, C.c_void_p(dev_ptr), C.c_int64(capacity_floats)))
+
+    def grid_best_dev(self, dev_ptr, n):
+        c = C.c_float()
+        i = C.c_int64()
+        check(self._lib.tdr_grid_best_dev(self._h, C.c_void_p(dev_ptr), C.c_int64(n), C.byref(c), C.byref(i)))
+        return c.value, i.value
+
     def grid_best(self):
         c = C.c_float()
         i = C.c_int64()

@@ -128,6 +128,8 @@ int tdr_create(tdr_ctx** out, int device) {
   if (const char* e = getenv("TDR_MMA_TILES")) { int v = atoi(e); if (v == 1 || v == 2 || v == 4) c->mma_tiles = v; }
   if (const char* e = getenv("TDR_MMA_SPLIT")) { int v = atoi(e); if (v == 1 || v == 2 || v == 4) c->mma_split = v; }
   if (const char* e = getenv("TDR_MMA_SEG_SHIFT")) { int v = atoi(e); if (v >= 0 && v <= 5) c->mma_seg_shift = v; }
+  if (const char* e = getenv("TDR_MMA_RING_CFG")) c->mma_ring_cfg = atoi(e);
+  if (const char* e = getenv("TDR_MMA_KERNEL")) c->mma_kernel = atoi(e);
   if (const char* e = getenv("TDR_MMA_CTAS")) c->mma_ctas = atoi(e);
   if (const char* e = getenv("TDR_MMA_ST_SHIFT")) { int v = atoi(e); if (v >= 5 && v <= 16) c->mma_st_shift = v; }
   TDR_CUDA(cudaStreamCreateWithFlags(&c->stream, cudaStreamNonBlocking));
@@ -215,7 +217,7 @@ int tdr_map_set_polar_table(tdr_ctx* ctx, const float* tab, int n_theta, int n_r
   if (int e = ctx->tab.reserve(bytes)) return e;
   TDR_CUDA(cudaMemcpyAsync(ctx->tab.p, tab, bytes, cudaMemcpyHostToDevice, ctx->stream));
   TDR_CUDA(cudaStreamSynchronize(ctx->stream));
-  ctx->n_theta = n_theta; ctx->n_r = n_r; ctx->have_tab = true; ctx->tab_dirty = true;
+  ctx->n_theta = n_theta; ctx->n_r = n_r; ctx->have_tab = true; ctx->tab_version++;
   return TDR_OK;
 }
 
@@ -572,24 +574,49 @@ int tdr_pf_pose_gathered(tdr_ctx* ctx, const void* dev_all, int n_ranks, int64_t
 int tdr_grid_costs(tdr_ctx* ctx, const float* centers_xy, int64_t n, float scale, float res, const int32_t* shifts,
                    int n_shifts, float* costs_out) {
   CTX_CHECK(ctx);
-  TDR_REQUIRE(centers_xy && n > 0 && shifts && n_shifts > 0 && n_shifts <= TDR_MAX_SHIFTS, TDR_EINVAL, "bad grid arguments");
-  if (int e = ctx->grid_centers.reserve((size_t)n * 8)) return e;
-  if (int e = ctx->grid_costs.reserve((size_t)n * n_shifts * 4)) return e;
+  TDR_REQUIRE(n > 0 && shifts && n_shifts > 0 && n_shifts <= TDR_MAX_SHIFTS, TDR_EINVAL, "bad grid arguments");
+  TDR_REQUIRE(centers_xy || ctx->grid_n == n, TDR_ESTATE, "no resident centres for a grid of %lld", (long long)n);
+  if (centers_xy) {
+    if (int e = ctx->grid_centers.reserve((size_t)n * 8)) return e;
+    TDR_CUDA(cudaMemcpyAsync(ctx->grid_centers.p, centers_xy, (size_t)n * 8, cudaMemcpyHostToDevice, ctx->stream));
+  }
+  if (!ctx->grid_costs_ext) { if (int e = ctx->grid_costs.reserve((size_t)n * n_shifts * 4)) return e; }
+  else TDR_REQUIRE(ctx->grid_costs_ext_cap >= n * n_shifts, TDR_EINVAL, "external cost buffer too small");
   if (int e = ctx->grid_shifts.reserve((size_t)n_shifts * 4)) return e;
-  TDR_CUDA(cudaMemcpyAsync(ctx->grid_centers.p, centers_xy, (size_t)n * 8, cudaMemcpyHostToDevice, ctx->stream));
   TDR_CUDA(cudaMemcpyAsync(ctx->grid_shifts.p, shifts, (size_t)n_shifts * 4, cudaMemcpyHostToDevice, ctx->stream));
-  ctx->grid_n = n; ctx->grid_shifts_n = n_shifts;
+  ctx->grid_n = n; ctx->grid_shifts_n = n_shifts; ctx->grid_shifts_host.assign(shifts, shifts + n_shifts);
   if (int e = scan_pack(ctx)) return e;
+  stage_mark(ctx, TDR_STAGE_SCORE);
   if (int e = score_grid(ctx, n, scale, res)) return e;
-  if (costs_out) TDR_CUDA(cudaMemcpyAsync(costs_out, ctx->grid_costs.p, (size_t)n * n_shifts * 4, cudaMemcpyDeviceToHost, ctx->stream));
-  TDR_CUDA(cudaStreamSynchronize(ctx->stream));
+  stage_mark(ctx, TDR_STAGE_NORMALIZE); stage_mark(ctx, TDR_STAGE_RESAMPLE); stage_mark(ctx, TDR_N_STAGES);
+  ctx->stage_valid = ctx->profiling;
+  if (centers_xy || costs_out) {      // caller-owned pageable buffers: finish before returning
+    if (costs_out) TDR_CUDA(cudaMemcpyAsync(costs_out, grid_costs_ptr(ctx), (size_t)n * n_shifts * 4, cudaMemcpyDeviceToHost, ctx->stream));
+    TDR_CUDA(cudaStreamSynchronize(ctx->stream));
+  }
+  return TDR_OK;
+}
+
+int tdr_grid_set_costs_buffer(tdr_ctx* ctx, void* dev_costs, int64_t capacity_floats) {
+  TDR_REQUIRE(ctx, TDR_EINVAL, "null context");
+  ctx->grid_costs_ext = reinterpret_cast<float*>(dev_costs);
+  ctx->grid_costs_ext_cap = dev_costs ? capacity_floats : 0;
   return TDR_OK;
 }
 
 int tdr_grid_best(tdr_ctx* ctx, float* best_cost, int64_t* best_index) {
   CTX_CHECK(ctx);
   long long idx = -1;
-  int e = grid_best(ctx, best_cost, &idx);
+  int e = grid_best(ctx, grid_costs_ptr(ctx), ctx->grid_n * ctx->grid_shifts_n, best_cost, &idx);
+  if (best_index) *best_index = idx;
+  return e;
+}
+
+int tdr_grid_best_dev(tdr_ctx* ctx, const void* dev_costs, int64_t n, float* best_cost, int64_t* best_index) {
+  CTX_CHECK(ctx);
+  TDR_REQUIRE(dev_costs && n > 0, TDR_EINVAL, "bad arguments");
+  long long idx = -1;
+  int e = grid_best(ctx, reinterpret_cast<const float*>(dev_costs), n, best_cost, &idx);
   if (best_index) *best_index = idx;
   return e;
 }
@@ -598,7 +625,7 @@ int tdr_dev_ptr(tdr_ctx* ctx, int which, void** ptr, int64_t* n_elems) {
   TDR_REQUIRE(ctx && ptr, TDR_EINVAL, "null argument");
   switch (which) {
     case TDR_BUF_WEIGHTS: *ptr = ctx->weights.p; if (n_elems) *n_elems = ctx->n_weights; break;
-    case TDR_BUF_GRID_COSTS: *ptr = ctx->grid_costs.p; if (n_elems) *n_elems = ctx->grid_n * ctx->grid_shifts_n; break;
+    case TDR_BUF_GRID_COSTS: *ptr = grid_costs_ptr(ctx); if (n_elems) *n_elems = ctx->grid_n * ctx->grid_shifts_n; break;
     case TDR_BUF_SCAN_IMAGES: *ptr = ctx->scan_img.p; if (n_elems) *n_elems = (int64_t)ctx->scan_C * ctx->scan_theta * ctx->scan_r; break;
     default: tdr::set_error("unknown buffer id %d", which); return TDR_EINVAL;
   }

@@ -163,15 +163,14 @@ __global__ void k_grid_best(const float* __restrict__ costs, long long n, unsign
   if ((threadIdx.x & 31) == 0) atomicMin(best, loc);
 }
 
-int grid_best(tdr_ctx* ctx, float* best_cost, long long* best_index) {
-  const long long n = ctx->grid_n * ctx->grid_shifts_n;
-  TDR_REQUIRE(n > 0, TDR_ESTATE, "no grid costs");
+int grid_best(tdr_ctx* ctx, const float* dev_costs, long long n, float* best_cost, long long* best_index) {
+  TDR_REQUIRE(n > 0 && dev_costs, TDR_ESTATE, "no grid costs");
   TDR_REQUIRE(n < (1ll << 32), TDR_EUNSUPPORTED, "grid too large for tdr_grid_best");
   if (int e = ctx->scal.reserve(SC_TOTAL * 4)) return e;
   unsigned long long* key = reinterpret_cast<unsigned long long*>(ctx->scal.as<float>() + SC_DBL) + 6;
   TDR_CUDA(cudaMemsetAsync(key, 0xff, 8, ctx->stream));
   const int blocks = (int)((n + 255) / 256 < ctx->sm_count * 8 ? (n + 255) / 256 : ctx->sm_count * 8);
-  k_grid_best<<<blocks, 256, 0, ctx->stream>>>(ctx->grid_costs.as<float>(), n, key);
+  k_grid_best<<<blocks, 256, 0, ctx->stream>>>(dev_costs, n, key);
   count_launch(ctx);
   TDR_CUDA(cudaGetLastError());
   unsigned long long h = 0;

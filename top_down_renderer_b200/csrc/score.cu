@@ -353,7 +353,9 @@ int score_particles(tdr_ctx* ctx, float res) {
     // large searches go to the tensor cores (score_mma.cu); small ones stay on the CUDA cores
     bool used = false;
     if (ctx->score_impl == 2 || (ctx->score_impl == 0 && ctx->n_uninit >= 4096)) {
-      if (int e = score_mma(ctx, res, false, pt.n, 1.f, sp.shifts, sp.n_shifts, &used)) return e;
+      // short candidate lists: streamed-operand kernel (two pipelines per SM); long ones: all-shifts ring kernel
+      if (ctx->mma_kernel != 2) { if (int e = score_mma_list(ctx, res, false, pt.n, 1.f, sp.shifts, sp.n_shifts, &used)) return e; }
+      if (!used) { if (int e = score_mma(ctx, res, false, pt.n, 1.f, sp.shifts, ctx->search_shifts.data(), sp.n_shifts, &used)) return e; }
     }
     if (used) { ctx->n_uninit = 0; TDR_CUDA(cudaGetLastError()); return TDR_OK; }
     size_t smem = (size_t)P * 32 + (size_t)sp.n_shifts * (SEARCH_THREADS / 32) * 8 + 256;
@@ -369,13 +371,15 @@ int score_particles(tdr_ctx* ctx, float res) {
 int score_grid(tdr_ctx* ctx, long long n, float scale, float res) {
   ScoreParams sp;
   if (int e = fill_params(ctx, res, &sp)) return e;
-  sp.n = n; sp.centers = ctx->grid_centers.as<float>(); sp.grid_scale = scale; sp.costs = ctx->grid_costs.as<float>();
+  sp.n = n; sp.centers = ctx->grid_centers.as<float>(); sp.grid_scale = scale; sp.costs = grid_costs_ptr(ctx);
   sp.shifts = ctx->grid_shifts.as<int32_t>(); sp.n_shifts = ctx->grid_shifts_n; sp.thetas = nullptr;
   sp.init_x = sp.init_y = sp.dx = sp.dy = nullptr; sp.theta = nullptr; sp.scale = nullptr; sp.have_init = nullptr; sp.weights = nullptr;
   const int P = sp.P;
   bool used = false;
   if (ctx->score_impl == 2 || (ctx->score_impl == 0 && n >= 4096)) {
-    if (int e = score_mma(ctx, res, true, n, scale, sp.shifts, sp.n_shifts, &used)) return e;
+    if (ctx->mma_kernel == 1) { if (int e = score_mma_list(ctx, res, true, n, scale, sp.shifts, sp.n_shifts, &used)) return e; }
+    if (!used) { if (int e = score_mma(ctx, res, true, n, scale, sp.shifts, ctx->grid_shifts_host.data(), sp.n_shifts, &used)) return e; }
+    if (!used && ctx->mma_kernel != 1) { if (int e = score_mma_list(ctx, res, true, n, scale, sp.shifts, sp.n_shifts, &used)) return e; }
   }
   if (used) return TDR_OK;
   TDR_REQUIRE(P <= SEARCH_THREADS * SEARCH_JMAX, TDR_EUNSUPPORTED, "polar image too large");

@@ -103,6 +103,8 @@ struct tdr_ctx {
                              // in-flight footprint L2-resident (96 % L2 hits) at the speed of 2 tiles x 2 CTAs/SM
   int mma_seg_shift = 2;     // log2 of the column-segment width of a bin (tuning: TDR_MMA_SEG_SHIFT)
   int mma_split = 4;         // gather threads per hypothesis row (tuning: TDR_MMA_SPLIT)
+  int mma_ring_cfg = 12;     // ring kernel: tiles * 10 + threads per row (tuning: TDR_MMA_RING_CFG)
+  int mma_kernel = 0;        // 0 auto, 1 streamed-operand kernel only, 2 ring kernel only (tuning: TDR_MMA_KERNEL)
   int mma_ctas = 0;          // cap on co-resident CTAs per SM (0 = as many as TMEM allows; tuning: TDR_MMA_CTAS)
   int mma_st_shift = 10;     // log2 of the binning super-tile side in px (tuning: TDR_MMA_ST_SHIFT)
 
@@ -110,7 +112,7 @@ struct tdr_ctx {
   int n_theta = 0, n_r = 0;
   tdr::DevBuf tab;           // 2*P floats
   bool have_tab = false;
-  bool tab_dirty = true;     // the constant-memory mirror used by score_mma.cu needs a refresh
+  uint64_t tab_version = 1;  // bumped by tdr_map_set_polar_table: the score kernels mirror the table in constant memory
 
   // ---- scan
   tdr::DevBuf pts;           // raw AoS copy
@@ -159,6 +161,9 @@ struct tdr_ctx {
   tdr::DevBuf grid_centers, grid_costs, grid_shifts;
   int64_t grid_n = 0;
   int grid_shifts_n = 0;
+  std::vector<int32_t> grid_shifts_host;
+  float* grid_costs_ext = nullptr;       // caller-provided device buffer for the costs (tdr_grid_set_costs_buffer)
+  int64_t grid_costs_ext_cap = 0;
 };
 
 namespace tdr {
@@ -193,7 +198,10 @@ int local_polar(tdr_ctx*, const float* dev_centers, int n, float scale, float re
 int local_cart(tdr_ctx*, float cx, float cy, float rot, float res, int out_rows, int out_cols, float* dev_dists, uint8_t* dev_mask);
 // score_mma.cu
 int score_mma(tdr_ctx*, float res, bool grid_mode, long long n_items, float grid_scale, const int32_t* dev_shifts,
-              int n_shifts, bool* used);
+              const int32_t* host_shifts, int n_shifts, bool* used);
+// score_mma_list.cu
+int score_mma_list(tdr_ctx*, float res, bool grid_mode, long long n_items, float grid_scale, const int32_t* dev_shifts,
+                   int n_shifts, bool* used);
 // weights.cu
 int normalize(tdr_ctx*);
 int build_prefix(tdr_ctx*);
@@ -202,5 +210,6 @@ int cache_ml_state(tdr_ctx*, const Particles& src);
 int exact_sums(tdr_ctx*, const float* const* cols, long long n, int ncols, float* totals_dev);
 // pose.cu
 int pose_of(tdr_ctx*, Particles& pt, float* mean, float* cov_mean, float* ml, float* cov_ml);
-int grid_best(tdr_ctx*, float* best_cost, long long* best_index);
+int grid_best(tdr_ctx*, const float* dev_costs, long long n, float* best_cost, long long* best_index);
+inline float* grid_costs_ptr(tdr_ctx* c) { return c->grid_costs_ext ? c->grid_costs_ext : c->grid_costs.as<float>(); }
 }
