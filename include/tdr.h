@@ -153,6 +153,9 @@ int tdr_pf_normalize(tdr_ctx* ctx, int64_t* argmax_out, float* stats);
 /* a12: particle_filter.cpp:172-187 on the resident normalised weights: M outputs, one uniform u.
  * Gathers the states (new particle i = old particle idx[i]); idx_out may be NULL. */
 int tdr_pf_resample(tdr_ctx* ctx, float u, int64_t M, int32_t* idx_out);
+/* a11 + a12 back to back on the resident raw weights (what tdr_pf_update runs after scoring); particle sets up
+ * to 32768 take one fused single-CTA kernel.  argmax_out / idx_out may be NULL. */
+int tdr_pf_normalize_resample(tdr_ctx* ctx, float u, int64_t M, int64_t* argmax_out, int32_t* idx_out);
 /* a13: mean / covariance / max-likelihood pose (particle_filter.cpp:191-236).  ml uses the arg-max
  * of the last tdr_pf_normalize (max_likelihood_particle_, :145-147).  Any pointer may be NULL. */
 int tdr_pf_pose(tdr_ctx* ctx, float mean[4], float cov_mean[16], float ml[4], float cov_ml[16]);

@@ -595,3 +595,27 @@ def test_ring_kernel_on_the_search_list_matches_list_kernel(world, monkeypatch):
     for w, s in out:
         assert rel_err(w, want).max() <= WEIGHT_RTOL
         assert (s["theta"] == st_o["theta"]).mean() > 0.995
+
+
+# ---- the fused single-CTA normalise + resample kernel (particle sets up to 32768) -------------------------------
+@pytest.mark.parametrize("kind", ["scored", "nan", "zeros", "allnan", "gated", "denormal"])
+@pytest.mark.parametrize("n,M", [(1, 1), (5, 9), (8, 8), (37, 20), (1000, 1000), (10000, 10000), (20000, 7000), (32768, 32768)])
+def test_fused_small_update_bit_exact(ctx, kind, n, M):
+    rng = np.random.default_rng(n * 7 + M + len(kind))
+    w = _weights_case(kind, n, rng)
+    ld = rng.uniform(0, 0.4, n).astype(np.float32)
+    st = np.zeros(n, dtype=synth.STATE_DTYPE)
+    st["init_x_px"] = np.arange(n)
+    st["scale"] = 2
+    u = orc.uniform_draw(n + M)
+    ctx.pf_set_states(st, ld)
+    ctx.pf_set_weights(w)
+    arg, idx = ctx.pf_normalize_resample(u, M)
+    got_w = ctx.pf_get_weights(n)
+    new = ctx.pf_get_states()
+    want_w, warg, _ = orc.normalize(w, ld)
+    want_idx = orc.resample_fast(want_w, u, M)
+    assert np.array_equal(got_w.view(np.uint32), want_w.view(np.uint32)), rel_err(got_w, want_w).max()
+    assert arg == warg or np.isnan(want_w).all()
+    assert np.array_equal(idx, want_idx)
+    assert len(new) == M and np.array_equal(new["init_x_px"], st["init_x_px"][want_idx])

@@ -240,6 +240,12 @@ class Context:
         check(self._lib.tdr_pf_resample(self._h, C.c_float(u), C.c_int64(M), _pi(idx) if want else None))
         return idx
 
+    def pf_normalize_resample(self, u, M):
+        arg = C.c_int64()
+        idx = np.empty(M, dtype=np.int32)
+        check(self._lib.tdr_pf_normalize_resample(self._h, C.c_float(u), C.c_int64(M), C.byref(arg), _pi(idx)))
+        return arg.value, idx
+
     def pf_pose(self, want_ml=True):
         mean = np.zeros(4, dtype=np.float32)
         cov = np.zeros(16, dtype=np.float32)

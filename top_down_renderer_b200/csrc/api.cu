@@ -482,17 +482,50 @@ int tdr_pf_pose(tdr_ctx* ctx, float mean[4], float cov_mean[16], float ml[4], fl
   return pose_of(ctx, ctx->part[ctx->cur], mean, cov_mean, ml, cov_ml);
 }
 
+// a11 + a12 on the resident raw weights: one fused single-CTA kernel for small sets, the tiled kernels otherwise
+static int normalize_resample(tdr_ctx* ctx, float u, int64_t M) {
+  bool used = false;
+  if (int e = small_update(ctx, u, M, true, &used)) return e;
+  if (used) {
+    if (int e = cache_ml_state(ctx, ctx->part[ctx->cur])) return e;
+    stage_mark(ctx, TDR_STAGE_RESAMPLE);
+    ctx->cur ^= 1;
+    return TDR_OK;
+  }
+  if (int e = normalize(ctx)) return e;
+  if (int e = cache_ml_state(ctx, ctx->part[ctx->cur])) return e;
+  stage_mark(ctx, TDR_STAGE_RESAMPLE);
+  if (int e = resample(ctx, u, M, 0, M, &ctx->part[ctx->cur], &ctx->part[ctx->cur ^ 1])) return e;
+  ctx->cur ^= 1;
+  return TDR_OK;
+}
+
+int tdr_pf_normalize_resample(tdr_ctx* ctx, float u, int64_t M, int64_t* argmax_out, int32_t* idx_out) {
+  CTX_CHECK(ctx);
+  TDR_REQUIRE(ctx->n_weights == ctx->part[ctx->cur].n, TDR_ESTATE, "weights (%lld) and particles (%lld) differ",
+              (long long)ctx->n_weights, (long long)ctx->part[ctx->cur].n);
+  ctx->ld_override = nullptr;
+  if (int e = normalize_resample(ctx, u, M)) return e;
+  if (argmax_out) {
+    int a = 0;
+    TDR_CUDA(cudaMemcpyAsync(&a, ctx->scal.as<float>() + SC_ARGMAX, 4, cudaMemcpyDeviceToHost, ctx->stream));
+    TDR_CUDA(cudaStreamSynchronize(ctx->stream));
+    *argmax_out = a;
+  }
+  if (idx_out) {
+    TDR_CUDA(cudaMemcpyAsync(idx_out, ctx->idx.p, (size_t)M * 4, cudaMemcpyDeviceToHost, ctx->stream));
+    TDR_CUDA(cudaStreamSynchronize(ctx->stream));
+  }
+  return TDR_OK;
+}
+
 static int update_resident(tdr_ctx* ctx, float res, float u, int64_t M) {
   if (int e = scan_pack(ctx)) return e;
   stage_mark(ctx, TDR_STAGE_SCORE);
   if (int e = score_particles(ctx, res)) return e;
   ctx->ld_override = nullptr;
   stage_mark(ctx, TDR_STAGE_NORMALIZE);
-  if (int e = normalize(ctx)) return e;
-  if (int e = cache_ml_state(ctx, ctx->part[ctx->cur])) return e;
-  stage_mark(ctx, TDR_STAGE_RESAMPLE);
-  if (int e = resample(ctx, u, M, 0, M, &ctx->part[ctx->cur], &ctx->part[ctx->cur ^ 1])) return e;
-  ctx->cur ^= 1;
+  if (int e = normalize_resample(ctx, u, M)) return e;
   stage_mark(ctx, TDR_N_STAGES);
   ctx->stage_valid = ctx->profiling;
   return TDR_OK;

@@ -54,62 +54,73 @@ __device__ __forceinline__ bool particle_centre(const ScoreParams& sp, long long
 }
 
 // ------------------------------------------------------------------------------------------------
-// tracking: warp per particle
-// shared: scan_pack (P*8 floats) | tab (2P floats) | cellpos (P x ushort2: theta, n_theta*r)
+// tracking: warp per particle, lane per lattice cell.
+// shared: scan_pack (P*8 floats) | tab (P float2) | cell (P x ushort2: theta, n_theta*r).  Every record is ONE
+// 256-bit load (one sector, one L1 wavefront: tools/gather_bench.cu) and four cells per lane are in flight.
 // ------------------------------------------------------------------------------------------------
-__global__ void __launch_bounds__(256) k_score_track(ScoreParams sp) {
+
+__device__ __forceinline__ void ldg256f(const void* p, float4& a, float4& b) {
+  asm("ld.global.nc.v8.f32 {%0, %1, %2, %3, %4, %5, %6, %7}, [%8];"
+      : "=f"(a.x), "=f"(a.y), "=f"(a.z), "=f"(a.w), "=f"(b.x), "=f"(b.y), "=f"(b.z), "=f"(b.w)
+      : "l"(p));
+}
+
+__global__ void __launch_bounds__(512, 2) k_score_track(ScoreParams sp) {
   extern __shared__ __align__(16) unsigned char smem[];
   float* s_scan = reinterpret_cast<float*>(smem);
-  float* s_tab = s_scan + (size_t)sp.P * 8;
-  ushort2* s_cell = reinterpret_cast<ushort2*>(s_tab + (size_t)sp.P * 2);
-  for (int i = threadIdx.x; i < sp.P * 2; i += blockDim.x) {   // float4 copies of the packed scan
+  float2* s_tab = reinterpret_cast<float2*>(s_scan + (size_t)sp.P * 8);
+  ushort2* s_cell = reinterpret_cast<ushort2*>(s_tab + sp.P);
+  for (int i = threadIdx.x; i < sp.P * 2; i += blockDim.x)       // float4 copies of the packed scan
     reinterpret_cast<float4*>(s_scan)[i] = ldg4(sp.scan_pack + (size_t)i * 4);
-  }
-  for (int i = threadIdx.x; i < sp.P * 2; i += blockDim.x) s_tab[i] = sp.tab[i];
   for (int i = threadIdx.x; i < sp.P; i += blockDim.x) {
-    int r = i / sp.n_theta;
+    s_tab[i] = reinterpret_cast<const float2*>(sp.tab)[i];
+    const int r = i / sp.n_theta;
     s_cell[i] = make_ushort2((unsigned short)(i - r * sp.n_theta), (unsigned short)(r * sp.n_theta));
   }
   __syncthreads();
 
-  const int lane = threadIdx.x & 31, half = lane & 1;
+  const int lane = threadIdx.x & 31;
   const long long warps_total = (long long)gridDim.x * (blockDim.x >> 5);
   const char* map_bytes = reinterpret_cast<const char*>(sp.map);
-  const int n_iter = (sp.P + 31) / 32;
+  const int n_theta = sp.n_theta;
   for (long long i = (long long)blockIdx.x * (blockDim.x >> 5) + (threadIdx.x >> 5); i < sp.n; i += warps_total) {
-    if (!sp.have_init[i]) continue;                       // searched by k_score_search
+    if (!sp.have_init[i]) continue;                       // searched by the theta-search kernels
     float cx, cy, sc;
     if (!particle_centre(sp, i, &cx, &cy, &sc)) { if (lane == 0) sp.weights[i] = 0.f; continue; }
     const float oy = TDR_FDIV(cy, sp.resolution), ox = TDR_FDIV(cx, sp.resolution);   // top_down_map_polar.cpp:29-30
-    const int shift = rot_to_shift(sp.theta[i], sp.n_theta);
+    const int shift = rot_to_shift(sp.theta[i], n_theta);
     float acc_c = 0.f, acc_n = 0.f, acc_k = 0.f;
-    for (int it = 0; it < n_iter; it++) {
-      int p = it * 32 + lane;
-      long long pix = -1;
-      if (p < sp.P) {
-        int r = lattice_index(s_tab[2 * p], sc, sp.res, oy);
-        int c = lattice_index(s_tab[2 * p + 1], sc, sp.res, ox);
-        if (r >= 0 && r < sp.rows && c >= 0 && c < sp.cols) pix = (long long)r * sp.cols + c;
+#pragma unroll 1
+    for (int p0 = 0; p0 < sp.P; p0 += 128) {              // 4 cells per lane in flight
+      float4 va[4], vb[4];
+      int cellidx[4];
+#pragma unroll
+      for (int q = 0; q < 4; q++) {
+        const int p = p0 + q * 32 + lane;
+        va[q] = make_float4(0.f, 0.f, 0.f, 0.f); vb[q] = va[q];
+        cellidx[q] = -1;
+        if (p < sp.P) {
+          const float2 tb = s_tab[p];
+          const int r = lattice_index(tb.x, sc, sp.res, oy);
+          const int c = lattice_index(tb.y, sc, sp.res, ox);
+          const ushort2 cell = s_cell[p];
+          int th = cell.x + shift;                         // scan row (m + s) mod n_theta pairs with map row m
+          if (th >= n_theta) th -= n_theta;
+          cellidx[q] = cell.y + th;
+          if (r >= 0 && r < sp.rows && c >= 0 && c < sp.cols)      // out of bounds: value 0, mask 1
+            ldg256f(map_bytes + ((long long)r * sp.cols + c) * 32, va[q], vb[q]);
+        }
       }
 #pragma unroll
-      for (int j = 0; j < 2; j++) {
-        int src = (lane >> 1) + 16 * j;
-        long long pj = __shfl_sync(0xffffffffu, pix, src);
-        int pp = it * 32 + src;
-        if (pj >= 0) {                                     // out of bounds: value 0, mask 1 -> contributes nothing
-          float4 v = ldg4(map_bytes + pj * 32 + half * 16);
-          ushort2 cell = s_cell[pp];
-          int th = cell.x + shift;                         // scan row (m + s) mod n_theta pairs with map row m
-          if (th >= sp.n_theta) th -= sp.n_theta;
-          float4 sv = *reinterpret_cast<const float4*>(s_scan + ((size_t)(cell.y + th)) * 8 + half * 4);
-          if (half == 0) {
-            acc_c = fmaf(v.x, sv.x, acc_c); acc_c = fmaf(v.y, sv.y, acc_c);
-            acc_c = fmaf(v.z, sv.z, acc_c); acc_c = fmaf(v.w, sv.w, acc_c);
-          } else {
-            acc_c = fmaf(v.x, sv.x, acc_c); acc_c = fmaf(v.y, sv.y, acc_c); acc_c = fmaf(v.z, sv.z, acc_c);
-            acc_n = fmaf(v.w, sv.w, acc_n);
-            acc_k += v.w;
-          }
+      for (int q = 0; q < 4; q++) {
+        if (cellidx[q] >= 0) {
+          const float4* sv = reinterpret_cast<const float4*>(s_scan + (size_t)cellidx[q] * 8);
+          const float4 s0 = sv[0], s1 = sv[1];
+          acc_c = fmaf(va[q].x, s0.x, acc_c); acc_c = fmaf(va[q].y, s0.y, acc_c);
+          acc_c = fmaf(va[q].z, s0.z, acc_c); acc_c = fmaf(va[q].w, s0.w, acc_c);
+          acc_c = fmaf(vb[q].x, s1.x, acc_c); acc_c = fmaf(vb[q].y, s1.y, acc_c); acc_c = fmaf(vb[q].z, s1.z, acc_c);
+          acc_n = fmaf(vb[q].w, s1.w, acc_n);
+          acc_k += vb[q].w;
         }
       }
     }
@@ -345,7 +356,10 @@ int score_particles(tdr_ctx* ctx, float res) {
   // which sets theta / have_init (state_particle.cpp:195-206).  Track first: it only READS have_init.
   const size_t track_smem = (size_t)P * 32 + (size_t)P * 8 + (size_t)P * 4;
   if (ctx->n_uninit < pt.n) {
-    k_score_track<<<ctx->sm_count * 2, 256, track_smem, ctx->stream>>>(sp);
+    const long long warps = pt.n;
+    long long ctas = (warps + 15) / 16;
+    if (ctas > (long long)ctx->sm_count * 2) ctas = (long long)ctx->sm_count * 2;
+    k_score_track<<<(unsigned)ctas, 512, track_smem, ctx->stream>>>(sp);
     count_launch(ctx);
   }
   if (ctx->n_uninit > 0) {

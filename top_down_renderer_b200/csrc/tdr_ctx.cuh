@@ -207,6 +207,7 @@ int normalize(tdr_ctx*);
 int build_prefix(tdr_ctx*);
 int resample(tdr_ctx*, float u, long long M, long long i0, long long i1, Particles* src, Particles* dst);
 int cache_ml_state(tdr_ctx*, const Particles& src);
+int small_update(tdr_ctx*, float u, long long M, bool do_resample, bool* used);
 int exact_sums(tdr_ctx*, const float* const* cols, long long n, int ncols, float* totals_dev);
 // pose.cu
 int pose_of(tdr_ctx*, Particles& pt, float* mean, float* cov_mean, float* ml, float* cov_ml);

@@ -48,47 +48,71 @@ __device__ __forceinline__ IncPair shfl_up_pair(IncPair v, int d) {
   return r;
 }
 
-// grid.x = number of jobs; one CTA walks its chain chunk by chunk.
-// only_flagged != nullptr: run a job only when its flag is set (fallback of the tiled path for chains with
-// negative / NaN / inf elements)
-__global__ void __launch_bounds__(SEQ_THREADS) k_exact_seq(SeqJobs jobs, const int* __restrict__ only_flagged) {
-  const SeqJob job = jobs.j[blockIdx.x];
-  if (only_flagged && only_flagged[blockIdx.x] == 0) return;
-  __shared__ IncPair s_warp[32];
-  __shared__ int s_cross;          // first crossing position inside the chunk (relative), or chunk_len
-  __shared__ uint32_t s_mprev;     // m of the element just before the crossing
-  __shared__ float s_S, s_rmax;    // chain state
-  __shared__ long long s_pos;
-  __shared__ int s_mode;           // 0 = binade scan, 1 = plain sequential tail (irregular state)
-  const int tid = threadIdx.x, lane = tid & 31, warp = tid >> 5;
-  if (tid == 0) { s_S = 0.f; s_rmax = -INFINITY; s_pos = 0; s_mode = 0; }
-  __syncthreads();
+// One CTA walks a chain chunk by chunk (the order-exact emulation described at the top of this file).
+// elem(j) returns addend j as a double; strict: see inc_pair_d.  runmax_out (may alias the storage elem reads
+// from: every element is read before its slot is written) receives max_{k<=j} s_k.  Returns the final sum to
+// every thread.  All SEQ_THREADS threads must call it.
+struct CtaSeqShared {
+  IncPair warp[32];
+  int cross;            // first crossing position inside the chunk (relative), or chunk_len
+  uint32_t mprev;       // m of the element just before the crossing
+  float S, rmax;        // chain state
+  long long pos;
+  int mode;             // 0 = binade scan, 1 = plain sequential tail (irregular state)
+};
 
+// GT = threads cooperating on the chain (SEQ_THREADS: the whole CTA; 128: one of 8 groups running 8 chains side by
+// side, each with its own named barrier and CtaSeqShared).  Every thread of the group must call it.
+template <int GT> __device__ __forceinline__ void group_sync() {
+  if (GT == SEQ_THREADS) __syncthreads();
+  else asm volatile("bar.sync %0, %1;" ::"r"(1 + (int)(threadIdx.x / GT)), "r"(GT) : "memory");
+}
+static const int SEQ_HEAD = 96;   // elements added one by one by a single thread before the scan machinery starts:
+                                  // the running sum doubles (changes binade) at elements 1, 2, 4, ... so the head
+                                  // absorbs the first ~7 binade crossings, each of which would cost a whole chunk pass
+
+template <int GT, class Elem>
+__device__ float cta_exact_chain(Elem elem, long long count, bool strict, float* runmax_out, CtaSeqShared& sh) {
+  constexpr int CHUNK = GT * SEQ_ITEMS;
+  const int tid = threadIdx.x % GT, lane = tid & 31, warp = tid >> 5;
+  group_sync<GT>();
+  if (tid == 0) {
+    float S = 0.f, rm = -INFINITY;
+    const long long head = count < SEQ_HEAD ? count : SEQ_HEAD;
+    for (long long j = 0; j < head; j++) {
+      S = seq_add(S, elem(j));
+      if (S > rm) rm = S;
+      if (runmax_out) runmax_out[j] = rm;
+    }
+    sh.S = S; sh.rmax = rm; sh.pos = head;
+    sh.mode = (!(S >= 0.f) || S == INFINITY) ? 1 : 0;
+  }
+  group_sync<GT>();
   while (true) {
-    const long long pos = s_pos;
-    if (pos >= job.count) break;
-    if (s_mode == 1) {
+    const long long pos = sh.pos;
+    if (pos >= count) break;
+    if (sh.mode == 1) {
       // irregular accumulator (negative / inf / NaN): finish with real adds, one thread.
       if (tid == 0) {
-        float S = s_S, rm = s_rmax;
-        for (long long j = pos; j < job.count; j++) {
-          S = seq_add(S, seq_elem(job, j));
+        float S = sh.S, rm = sh.rmax;
+        for (long long j = pos; j < count; j++) {
+          S = seq_add(S, elem(j));
           if (S > rm) rm = S;
-          if (job.runmax_out) job.runmax_out[j] = rm;
+          if (runmax_out) runmax_out[j] = rm;
         }
-        s_S = S; s_rmax = rm; s_pos = job.count;
+        sh.S = S; sh.rmax = rm; sh.pos = count;
       }
-      __syncthreads();
+      group_sync<GT>();
       continue;
     }
-    const float S_in = s_S;
-    const float rmax_in = s_rmax;
+    const float S_in = sh.S;
+    const float rmax_in = sh.rmax;
     const int E = binade_of(S_in);
     const uint32_t m_in = mant_of(S_in);
     const uint32_t limit = binade_limit(E);
-    long long remaining = job.count - pos;
-    const int chunk_len = remaining < SEQ_CHUNK ? (int)remaining : SEQ_CHUNK;
-    if (tid == 0) s_cross = chunk_len;
+    long long remaining = count - pos;
+    const int chunk_len = remaining < CHUNK ? (int)remaining : CHUNK;
+    if (tid == 0) sh.cross = chunk_len;
 
     // ---- per-thread pairs (blocked: thread owns SEQ_ITEMS consecutive elements)
     IncPair loc[SEQ_ITEMS];
@@ -97,34 +121,35 @@ __global__ void __launch_bounds__(SEQ_THREADS) k_exact_seq(SeqJobs jobs, const i
     for (int k = 0; k < SEQ_ITEMS; k++) {
       int j = tid * SEQ_ITEMS + k;
       double w = 0.0;
-      if (j < chunk_len) w = seq_elem(job, pos + j);
+      if (j < chunk_len) w = elem(pos + j);
       bool irr;
-      IncPair pr = inc_pair_d(w, E, job.mode != 0, &irr);
+      IncPair pr = inc_pair_d(w, E, strict, &irr);
       agg = pair_compose(agg, pr);
       loc[k] = agg;                       // inclusive within the thread
     }
-    // ---- block exclusive scan of thread aggregates (pair_compose is associative, not commutative)
+    // ---- group exclusive scan of thread aggregates (pair_compose is associative, not commutative)
     IncPair incl = agg;
 #pragma unroll
     for (int d = 1; d < 32; d <<= 1) {
       IncPair o = shfl_up_pair(incl, d);
       if (lane >= d) incl = pair_compose(o, incl);
     }
-    if (lane == 31) s_warp[warp] = incl;
-    __syncthreads();
+    if (lane == 31) sh.warp[warp] = incl;
+    group_sync<GT>();
     if (warp == 0) {
-      IncPair v = s_warp[lane];
+      IncPair v; v.a = v.b = 0;
+      if (lane < GT / 32) v = sh.warp[lane];
 #pragma unroll
       for (int d = 1; d < 32; d <<= 1) {
         IncPair o = shfl_up_pair(v, d);
         if (lane >= d) v = pair_compose(o, v);
       }
-      s_warp[lane] = v;                   // inclusive over warps
+      if (lane < GT / 32) sh.warp[lane] = v;    // inclusive over warps
     }
-    __syncthreads();
+    group_sync<GT>();
     IncPair excl_thread = shfl_up_pair(incl, 1);
     if (lane == 0) { excl_thread.a = 0; excl_thread.b = 0; }
-    if (warp > 0) excl_thread = pair_compose(s_warp[warp - 1], excl_thread);
+    if (warp > 0) excl_thread = pair_compose(sh.warp[warp - 1], excl_thread);
 
     // ---- element values and the first crossing
     const bool odd = (m_in & 1u) != 0;
@@ -139,42 +164,57 @@ __global__ void __launch_bounds__(SEQ_THREADS) k_exact_seq(SeqJobs jobs, const i
       mv[k] = m;
       if (j < chunk_len && m >= limit && j < my_cross) my_cross = j;
     }
-    if (my_cross < chunk_len) atomicMin(&s_cross, my_cross);
-    __syncthreads();
-    const int cross = s_cross;
+    if (my_cross < chunk_len) atomicMin(&sh.cross, my_cross);
+    group_sync<GT>();
+    const int cross = sh.cross;
+    // the crossing element is read BEFORE anything is emitted (runmax_out may alias the element storage)
+    double w_cross = 0.0;
+    if (tid == 0 && cross < chunk_len) w_cross = elem(pos + cross);
     // ---- emit the valid part [0, cross)
 #pragma unroll
     for (int k = 0; k < SEQ_ITEMS; k++) {
       int j = tid * SEQ_ITEMS + k;
       if (j < cross) {
-        if (job.runmax_out) {
+        if (runmax_out) {
           float S = from_binade(E, mv[k]);
-          job.runmax_out[pos + j] = S > rmax_in ? S : rmax_in;   // non-decreasing inside a segment
+          runmax_out[pos + j] = S > rmax_in ? S : rmax_in;   // non-decreasing inside a segment
         }
-        if (j == cross - 1) s_mprev = mv[k];
+        if (j == cross - 1) sh.mprev = mv[k];
       }
     }
-    __syncthreads();
+    group_sync<GT>();
     // ---- advance the chain state (one thread; the crossing add is a real fp32 add)
     if (tid == 0) {
-      float S = (cross > 0) ? from_binade(E, s_mprev) : S_in;
+      float S = (cross > 0) ? from_binade(E, sh.mprev) : S_in;
       float rm = rmax_in;
       if (cross > 0 && S > rm) rm = S;
       long long np = pos + cross;
       if (cross < chunk_len) {
-        S = seq_add(S, seq_elem(job, pos + cross));
+        S = seq_add(S, w_cross);
         if (S > rm) rm = S;
-        if (job.runmax_out) job.runmax_out[pos + cross] = rm;
+        if (runmax_out) runmax_out[pos + cross] = rm;
         np += 1;
-        if (!(S >= 0.f) || S == INFINITY) s_mode = 1;   // negative / NaN / inf accumulator
+        if (!(S >= 0.f) || S == INFINITY) sh.mode = 1;   // negative / NaN / inf accumulator
       }
-      s_S = S; s_rmax = rm; s_pos = np;
+      sh.S = S; sh.rmax = rm; sh.pos = np;
     }
-    __syncthreads();
+    group_sync<GT>();
   }
-  if (tid == 0 && job.total_out) *job.total_out = s_S;
+  const float total = sh.S;
+  group_sync<GT>();
+  return total;
 }
 
+// grid.x = number of jobs.  only_flagged != nullptr: run a job only when its flag is set (fallback of the tiled
+// path for chains with negative / NaN / inf elements)
+__global__ void __launch_bounds__(SEQ_THREADS) k_exact_seq(SeqJobs jobs, const int* __restrict__ only_flagged) {
+  const SeqJob job = jobs.j[blockIdx.x];
+  if (only_flagged && only_flagged[blockIdx.x] == 0) return;
+  __shared__ CtaSeqShared sh;
+  const float total = cta_exact_chain<SEQ_THREADS>([&](long long j) { return seq_elem(job, j); }, job.count, job.mode != 0,
+                                      job.runmax_out, sh);
+  if (threadIdx.x == 0 && job.total_out) *job.total_out = total;
+}
 
 // ================================================================================================
 // Tiled (multi-CTA) order-exact accumulation for long chains.
@@ -545,13 +585,12 @@ __global__ void k_fill_nan(float* __restrict__ w, long long n, const float* __re
 
 // Eigen's vectorised weights_.sum() (SSE2 packets, 2x unrolled; Eigen/src/Core/Redux.h): combine the 8
 // exact chain totals in Eigen's order.  Small n is summed directly.
-__global__ void k_eigen_sum_finish(const float* __restrict__ x, long long n, const float* __restrict__ chain,
-                                   float* __restrict__ out) {
+__device__ float eigen_sum_finish_dev(const float* x, long long n, const float* chain) {
   const long long ps = 4;
   const long long aS2 = (n / (2 * ps)) * (2 * ps), aS = (n / ps) * ps;
   float res;
-  if (n == 0) { *out = 0.f; return; }
-  if (aS == 0) { res = x[0]; for (long long i = 1; i < n; i++) res = TDR_FADD(res, x[i]); *out = res; return; }
+  if (n == 0) return 0.f;
+  if (aS == 0) { res = x[0]; for (long long i = 1; i < n; i++) res = TDR_FADD(res, x[i]); return res; }
   float p0[4], p1[4];
   if (aS2 >= 2 * ps) {
     for (int k = 0; k < 4; k++) { p0[k] = chain[k]; p1[k] = chain[4 + k]; }
@@ -562,7 +601,11 @@ __global__ void k_eigen_sum_finish(const float* __restrict__ x, long long n, con
   }
   res = TDR_FADD(TDR_FADD(p0[0], p0[2]), TDR_FADD(p0[1], p0[3]));
   for (long long i = aS; i < n; i++) res = TDR_FADD(res, x[i]);
-  *out = res;
+  return res;
+}
+__global__ void k_eigen_sum_finish(const float* __restrict__ x, long long n, const float* __restrict__ chain,
+                                   float* __restrict__ out) {
+  *out = eigen_sum_finish_dev(x, n, chain);
 }
 
 // w /= s1 ; w = d*w + (1-d)/N   (:135-141)
@@ -626,6 +669,124 @@ __global__ void k_resample(const float* __restrict__ runmax, long long n, float 
       g.oix[o] = g.ix[lo]; g.oiy[o] = g.iy[lo]; g.odx[o] = g.dx[lo]; g.ody[o] = g.dy[lo];
       g.oth[o] = g.th[lo]; g.osc[o] = g.sc[lo]; g.ohi[o] = g.hi[lo];
       g.old[o] = g.ld[lo];
+    }
+  }
+}
+
+// ------------------------------------------------------------------------------------------------
+// Small particle sets (tracking): the whole of particle_filter.cpp:107-187 in ONE single-CTA kernel with the
+// weights in shared memory — the same arithmetic as the kernel sequence of normalize() + resample(), without the
+// ~20 launches and their dependent round trips (the 10 k-particle update is latency-bound, not bandwidth-bound).
+// ------------------------------------------------------------------------------------------------
+static const int SMALL_MAX = 32768;
+
+__device__ __forceinline__ float block_bcast(float v, float* slot) {
+  __syncthreads();
+  if (threadIdx.x == 0) *slot = v;
+  __syncthreads();
+  return *slot;
+}
+
+__global__ void __launch_bounds__(SEQ_THREADS) k_small_update(float* __restrict__ w_g, const float* __restrict__ last_dist,
+                                                             int n, float* __restrict__ scal, float u, int M,
+                                                             int32_t* __restrict__ idx, GatherPtrs g, int do_resample) {
+  extern __shared__ float w_s[];
+  __shared__ CtaSeqShared sh;
+  __shared__ CtaSeqShared sh8[8];
+  __shared__ float s_chain[8];
+  __shared__ float s_slot;
+  __shared__ int s_cnt[2];
+  __shared__ unsigned long long s_key;
+  const int tid = threadIdx.x;
+  for (int i = tid; i < n; i += SEQ_THREADS) w_s[i] = w_g[i];
+  if (tid == 0) { s_cnt[0] = 0; s_cnt[1] = 0; s_key = 0ull; }
+  // ---- sum / num_valid / mean (:108-117)
+  const float sum = cta_exact_chain<SEQ_THREADS>([&](long long j) { float w = w_s[j]; return (double)(w != w ? 0.f : w); }, n, false, nullptr, sh);
+  int c = 0;
+  for (int i = tid; i < n; i += SEQ_THREADS) c += (w_s[i] == w_s[i]) ? 1 : 0;
+  for (int o = 16; o > 0; o >>= 1) c += __shfl_xor_sync(0xffffffffu, c, o);
+  if ((tid & 31) == 0 && c) atomicAdd(&s_cnt[0], c);
+  __syncthreads();
+  const int nvalid = s_cnt[0];
+  const float mean = TDR_FDIV(sum, (float)nvalid);
+  // ---- lower-half deviation (:120-126)
+  c = 0;
+  for (int i = tid; i < n; i += SEQ_THREADS) { float v = w_s[i]; c += (v == v && v < mean) ? 1 : 0; }
+  for (int o = 16; o > 0; o >>= 1) c += __shfl_xor_sync(0xffffffffu, c, o);
+  if ((tid & 31) == 0 && c) atomicAdd(&s_cnt[1], c);
+  const float bsraw = cta_exact_chain<SEQ_THREADS>([&](long long j) {
+    float w = w_s[j];
+    if (w == w && w < mean) { float dv = TDR_FSUB(w, mean); return (double)dv * (double)dv; }
+    return 0.0; }, n, true, nullptr, sh);
+  const int nunder = s_cnt[1];
+  const float bs = TDR_FSQRT(TDR_FDIV(bsraw, (float)nunder));
+  const bool fallback = (sum == 0.f) || (nunder < 1);                  // :129
+  const float rep = TDR_FSUB(mean, bs);                                // :133
+  if (tid == 0) {
+    scal[SC_SUM] = sum; scal[SC_NVALID] = (float)nvalid; scal[SC_MEAN] = mean; scal[SC_BS] = bs; scal[SC_BSRAW] = bsraw;
+    scal[SC_NUNDER] = (float)nunder; scal[SC_FALLBACK] = fallback ? 1.f : 0.f; scal[SC_REP] = rep;
+  }
+  for (int i = tid; i < n; i += SEQ_THREADS) {
+    float v = w_s[i];
+    if (fallback) w_s[i] = 1.f; else if (v != v) w_s[i] = rep;
+  }
+  // ---- weights_.sum() (Eigen order), regularisation, second sum (:135-142)
+  const long long aS2 = ((long long)n / 8) * 8;
+  for (int pass = 0; pass < 2; pass++) {
+    if (aS2 >= 8) {
+      // the 8 interleaved chains of Eigen's packet sum side by side: 128 threads and one named barrier each
+      __syncthreads();
+      const int k = tid >> 7;
+      const float t = cta_exact_chain<128>([&](long long j) { return (double)w_s[k + 8 * j]; }, aS2 / 8, false, nullptr, sh8[k]);
+      if ((tid & 127) == 0) s_chain[k] = t;
+    }
+    __syncthreads();
+    float tot = 0.f;
+    if (tid == 0) tot = eigen_sum_finish_dev(w_s, n, s_chain);
+    tot = block_bcast(tot, &s_slot);
+    if (pass == 0) {
+      if (tid == 0) scal[SC_S1] = tot;
+      const float fn = (float)(unsigned long long)n;
+      for (int i = tid; i < n; i += SEQ_THREADS) {
+        float v = TDR_FDIV(w_s[i], tot);
+        float d = TDR_FMUL(last_dist[i], 5.0f);
+        d = (1.0f < d) ? 1.0f : d;
+        w_s[i] = TDR_FADD(TDR_FMUL(d, v), TDR_FDIV(TDR_FSUB(1.0f, d), fn));
+      }
+    } else {
+      if (tid == 0) scal[SC_S2] = tot;
+      unsigned long long loc = 0ull;
+      for (int i = tid; i < n; i += SEQ_THREADS) {
+        float v = TDR_FDIV(w_s[i], tot);
+        w_s[i] = v; w_g[i] = v;
+        if (v == v) {
+          uint32_t ub = __float_as_uint(v);
+          ub = (ub & 0x80000000u) ? ~ub : (ub | 0x80000000u);
+          unsigned long long key = ((unsigned long long)ub << 32) | (unsigned long long)(0xffffffffu - (uint32_t)i);
+          if (key > loc) loc = key;
+        }
+      }
+      for (int o = 16; o > 0; o >>= 1) { unsigned long long t2 = __shfl_xor_sync(0xffffffffu, loc, o); if (t2 > loc) loc = t2; }
+      if ((tid & 31) == 0 && loc) atomicMax(&s_key, loc);
+    }
+    __syncthreads();
+  }
+  if (tid == 0) {
+    const unsigned long long k = s_key;
+    reinterpret_cast<int*>(scal)[SC_ARGMAX] = k ? (int)(0xffffffffu - (uint32_t)(k & 0xffffffffull)) : 0;
+  }
+  if (!do_resample) return;
+  // ---- prefix in place, then the systematic draw (:172-187)
+  cta_exact_chain<SEQ_THREADS>([&](long long j) { return (double)w_s[j]; }, n, false, w_s, sh);
+  const float fM = (float)M;
+  for (int i = tid; i < M; i += SEQ_THREADS) {
+    const float sample = TDR_FDIV(TDR_FADD((float)i, u), fM);
+    int lo = 0, hi = n - 1;
+    while (lo < hi) { int mid = (lo + hi) >> 1; if (w_s[mid] > sample) hi = mid; else lo = mid + 1; }
+    idx[i] = lo;
+    if (g.ix) {
+      g.oix[i] = g.ix[lo]; g.oiy[i] = g.iy[lo]; g.odx[i] = g.dx[lo]; g.ody[i] = g.dy[lo];
+      g.oth[i] = g.th[lo]; g.osc[i] = g.sc[lo]; g.ohi[i] = g.hi[lo]; g.old[i] = g.ld[lo];
     }
   }
 }
@@ -777,6 +938,36 @@ int resample(tdr_ctx* ctx, float u, long long M, long long i0, long long i1, Par
   count_launch(ctx);
   TDR_CUDA(cudaGetLastError());
   if (src && dst) dst->n = cnt;
+  return TDR_OK;
+}
+
+// a11 + a12 fused for small particle sets; returns *used = false when the set is too large (caller falls back)
+int small_update(tdr_ctx* ctx, float u, long long M, bool do_resample, bool* used) {
+  *used = false;
+  const long long n = ctx->n_weights;
+  tdr::Particles& src = ctx->part[ctx->cur];
+  tdr::Particles& dst = ctx->part[ctx->cur ^ 1];
+  if (n <= 0 || n > SMALL_MAX || ctx->ld_override || src.n != n || ctx->seq_impl == 1) return TDR_OK;
+  if (do_resample && (M <= 0 || M >= (1ll << 31))) return TDR_OK;
+  if (int e = ctx->scal.reserve(SC_TOTAL * 4)) return e;
+  GatherPtrs g; memset(&g, 0, sizeof(g));
+  if (do_resample) {
+    if (int e = dst.reserve(M)) return e;
+    if (int e = ctx->idx.reserve((size_t)M * 4)) return e;
+    g.ix = src.init_x.as<float>(); g.iy = src.init_y.as<float>(); g.dx = src.dx.as<float>(); g.dy = src.dy.as<float>();
+    g.th = src.theta.as<float>(); g.sc = src.scale.as<float>(); g.ld = src.last_dist.as<float>(); g.hi = src.have_init.as<uint8_t>();
+    g.oix = dst.init_x.as<float>(); g.oiy = dst.init_y.as<float>(); g.odx = dst.dx.as<float>(); g.ody = dst.dy.as<float>();
+    g.oth = dst.theta.as<float>(); g.osc = dst.scale.as<float>(); g.old = dst.last_dist.as<float>(); g.ohi = dst.have_init.as<uint8_t>();
+  }
+  static bool attr = false;
+  if (!attr) { TDR_CUDA(cudaFuncSetAttribute(k_small_update, cudaFuncAttributeMaxDynamicSharedMemorySize, SMALL_MAX * 4)); attr = true; }
+  k_small_update<<<1, SEQ_THREADS, (size_t)n * 4, ctx->stream>>>(ctx->weights.as<float>(), src.last_dist.as<float>(), (int)n,
+                                                                ctx->scal.as<float>(), u, (int)M, ctx->idx.as<int32_t>(), g,
+                                                                do_resample ? 1 : 0);
+  count_launch(ctx);
+  TDR_CUDA(cudaGetLastError());
+  if (do_resample) dst.n = M;
+  *used = true;
   return TDR_OK;
 }
 
