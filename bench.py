@@ -197,7 +197,7 @@ def run_reference(args, wl):
            "cpu_baseline": {"value": value, "unit": "scores/s", "cores": arm.cores, "kind": "port", "sample": sample},
            "e2e": {"value": value, "unit": "scores/s", "h2d_bytes_per_step": 0, "d2h_bytes_per_step": 0},
            "gpu_launches": 0}
-    print(json.dumps(out), flush=True)
+    emit(out)
 
 
 # ------------------------------------------------------------------------------------------------
@@ -217,6 +217,20 @@ def setup_ctx(wl, inp, device):
     ctx.pf_set_states(inp["st"], inp["ld"])
     ctx.pf_checkpoint()
     return ctx
+
+
+def more_warmup(t0, world, local, need_s=1.5):
+    """True while the clock sampler has not yet seen need_s seconds of load (decided collectively: every rank
+    must run the same number of steps)."""
+    import torch
+    torch.cuda.synchronize()
+    more = 1.0 if time.perf_counter() - t0 < need_s else 0.0
+    if world > 1:
+        import torch.distributed as dist
+        t = torch.tensor([more], device=f"cuda:{local}")
+        dist.all_reduce(t, op=dist.ReduceOp.MAX)
+        more = float(t.item())
+    return more > 0
 
 
 def run_gpu(args, wl):
@@ -262,11 +276,20 @@ def run_gpu(args, wl):
     launches0 = None
     evs, stage = [], []
     sampler = ClockSampler(local)
+    sampler.start()                          # nvidia-smi needs ~1 s to produce its first sample: start it before the
+    t_load0 = time.perf_counter()            # warm-up and keep warming up (same load, untimed) until it has samples
+    n_warm = args.warmup
     total_steps = args.warmup + args.steps
-    for i in range(total_steps):
-        if i == args.warmup:
+    i = -1
+    while True:
+        i += 1
+        if i == n_warm and more_warmup(t_load0, world, local) and n_warm < args.warmup + 5000:
+            n_warm += 1
+            total_steps += 1
+        if i >= total_steps:
+            break
+        if i == n_warm:
             barrier()
-            sampler.start()
             launches0 = ctx.launch_count()
             t_wall0 = time.perf_counter()
         with torch.cuda.stream(stream):
@@ -276,7 +299,7 @@ def run_gpu(args, wl):
             e0.record(stream)
             one_step()
             e1.record(stream)
-        if i >= args.warmup:
+        if i >= n_warm:
             evs.append((e0, e1))
             stage.append(ctx.profile_stage_ms())
     barrier()
@@ -365,7 +388,7 @@ def run_gpu(args, wl):
     elif rank == 0:
         out["cpu_baseline"] = None
     if rank == 0:
-        print(json.dumps(out), flush=True)
+        emit(out)
     ctx.close()
     if world > 1:
         dist.barrier()
@@ -431,10 +454,18 @@ def run_grid(args, wl):
 
     evs, kern_ms, best = [], [], None
     sampler = ClockSampler(local)
-    for i in range(args.warmup + args.steps):
-        if i == args.warmup:
+    sampler.start()
+    t_load0 = time.perf_counter()
+    n_warm, total_steps, i = args.warmup, args.warmup + args.steps, -1
+    while True:
+        i += 1
+        if i == n_warm and more_warmup(t_load0, world, local) and n_warm < args.warmup + 5000:
+            n_warm += 1
+            total_steps += 1
+        if i >= total_steps:
+            break
+        if i == n_warm:
             barrier()
-            sampler.start()
             launches0 = ctx.launch_count()
         with torch.cuda.stream(stream):
             flush.zero_()
@@ -442,7 +473,7 @@ def run_grid(args, wl):
             e0.record(stream)
         best = one_step()
         e1.record(stream)
-        if i >= args.warmup:
+        if i >= n_warm:
             evs.append((e0, e1))
             kern_ms.append(ctx.profile_stage_ms()[1])
     barrier()
@@ -488,14 +519,34 @@ def run_grid(args, wl):
                             "unit": "GB/s", "frac": achieved / peak, "traffic": None, "peak_source": peak_src,
                             "algorithmic_bytes_per_launch": n_local * b_score(C), "kernel_ms": k_ms},
                "cpu_baseline": None}
-        print(json.dumps(out), flush=True)
+        emit(out)
     ctx.close()
     if world > 1:
         dist.barrier()
         dist.destroy_process_group()
 
 
+_REAL_STDOUT = None
+
+
+def claim_stdout():
+    """Rank 0 must print exactly ONE line on stdout, but NCCL / torch write banners to fd 1: point fd 1 at stderr
+    for the whole run and keep a private handle on the real stdout for the JSON line."""
+    global _REAL_STDOUT
+    if _REAL_STDOUT is None:
+        sys.stdout.flush()
+        _REAL_STDOUT = os.fdopen(os.dup(1), "w")
+        os.dup2(2, 1)
+
+
+def emit(obj):
+    claim_stdout()
+    _REAL_STDOUT.write(json.dumps(obj) + "\n")
+    _REAL_STDOUT.flush()
+
+
 def main():
+    claim_stdout()
     ap = argparse.ArgumentParser()
     ap.add_argument("--gpus", type=int, default=1)
     ap.add_argument("--steps", type=int, default=20)

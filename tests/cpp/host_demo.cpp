@@ -1,0 +1,68 @@
+// host_demo.cpp — drives the C++ host mirror (top_down_renderer_b200/host/tdr_host.hpp) through one scan step the
+// way TopDownRender::takeStep does (top_down_render.cpp:505-572): map update, polar rasterise, particle init,
+// propagate, update, pose.  Inputs / outputs are raw little-endian files in argv[1] so that tests/test_host_cpp.py
+// can check them against the oracle.
+#include <fstream>
+#include <iostream>
+
+#include "../../top_down_renderer_b200/host/tdr_host.hpp"
+
+using namespace tdrhost;
+
+template <typename T> static std::vector<T> rd(const std::string& p) {
+  std::ifstream f(p, std::ios::binary | std::ios::ate);
+  if (!f) { std::cerr << "cannot read " << p << "\n"; exit(2); }
+  size_t n = f.tellg(); f.seekg(0);
+  std::vector<T> v(n / sizeof(T));
+  f.read(reinterpret_cast<char*>(v.data()), n);
+  return v;
+}
+template <typename T> static void wr(const std::string& p, const T* d, size_t n) {
+  std::ofstream f(p, std::ios::binary);
+  f.write(reinterpret_cast<const char*>(d), n * sizeof(T));
+}
+
+int main(int argc, char** argv) {
+  if (argc < 2) { std::cerr << "usage: host_demo <dir>\n"; return 2; }
+  const std::string dir = std::string(argv[1]) + "/";
+  auto meta = rd<int32_t>(dir + "meta.i32");       // H, W, C, N, seed, n_theta, n_r
+  auto fmeta = rd<float>(dir + "meta.f32");        // res, init_x, init_y, init_cov, init_theta_deg, init_theta_cov
+  const int H = meta[0], W = meta[1], C = meta[2], N = meta[3], seed = meta[4], n_theta = meta[5], n_r = meta[6];
+  auto img = rd<uint8_t>(dir + "class_image.u8");
+  auto pts = rd<PointXYZI>(dir + "points.f32");
+  if (!ctx()) return 3;                             // no GPU: nothing to demonstrate (and no CPU fallback)
+
+  std::vector<int> lut(256, -1);
+  for (int c = 0; c < C; c++) lut[c] = c;
+  TopDownMapPolar::Params mp; mp.flatten_lut = lut; mp.num_classes = C; mp.resolution = 1;
+  TopDownMapPolar map(mp);
+  map.samplePtsPolar(n_theta, n_r, (float)(2 * M_PI / n_theta));
+  map.updateMap(img.data(), H, W, W, Vector2i{W / 2, H / 2});
+  if (!map.haveMap()) return 4;
+
+  ScanRendererPolar renderer(lut);
+  std::vector<ArrayXXf> top_down(C, ArrayXXf(n_theta, n_r)), geo;
+  renderer.renderSemanticTopDown(pts, fmeta[0], (float)(2 * M_PI / n_theta), top_down);
+  for (int c = 0; c < C; c++) wr(dir + "scan_" + std::to_string(c) + ".f32", top_down[c].data(), (size_t)n_theta * n_r);
+
+  FilterParams fp; fp.regularization = 0.7f; fp.pos_cov = 0.15f; fp.theta_cov = 0.004f; fp.fixed_scale = 2.0f;
+  fp.init_pos_px_x = fmeta[1]; fp.init_pos_px_y = fmeta[2]; fp.init_pos_px_cov = fmeta[3];
+  fp.init_pos_deg_theta = fmeta[4]; fp.init_pos_deg_cov = fmeta[5];
+  fp.class_weights.assign(C, 1.f);
+  ParticleFilter filter(N, &map, fp, (uint32_t)seed);
+  Vector2f trans; trans.x = 0.4f; trans.y = 0.05f;
+  filter.propagate(trans, 0.01f);
+  wr(dir + "states_before.bin", filter.states().data(), filter.states().size());
+  wr(dir + "last_dist.f32", filter.lastDist().data(), filter.lastDist().size());
+  filter.update(top_down, geo, fmeta[0]);
+  const float u = filter.lastUniform();
+  wr(dir + "u.f32", &u, 1);
+  auto w = filter.weights();
+  wr(dir + "weights_norm.f32", w.data(), w.size());
+  wr(dir + "states_after.bin", filter.states().data(), filter.states().size());
+  float mean[4], cov[16], ml[4];
+  filter.meanLikelihood(mean); filter.computeMeanCov(cov); filter.maxLikelihood(ml);
+  wr(dir + "mean.f32", mean, 4); wr(dir + "cov.f32", cov, 16); wr(dir + "ml.f32", ml, 4);
+  std::cout << "host_demo ok: " << filter.numParticles() << " particles, mean (" << mean[0] << ", " << mean[1] << ", " << mean[2] << ")\n";
+  return 0;
+}

@@ -1,0 +1,87 @@
+"""The C++ host mirror of the reference's class interfaces (top_down_renderer_b200/host/tdr_host.hpp):
+it compiles and links against the C ABI on the CPU box, and on a GPU one scan step driven through
+ScanRendererPolar / TopDownMapPolar / ParticleFilter agrees with the oracle."""
+import math
+import os
+import subprocess
+
+import numpy as np
+import pytest
+
+import top_down_renderer_b200 as tdr
+from oracle import oracle as orc
+from top_down_renderer_b200 import synth
+
+ROOT = os.path.dirname(os.path.dirname(os.path.abspath(__file__)))
+DEMO = os.path.join(ROOT, "tests", "cpp", "host_demo")
+
+
+def build_demo():
+    tdr.build()
+    src = os.path.join(ROOT, "tests", "cpp", "host_demo.cpp")
+    hdr = os.path.join(ROOT, "top_down_renderer_b200", "host", "tdr_host.hpp")
+    if not os.path.exists(DEMO) or os.path.getmtime(DEMO) < max(os.path.getmtime(src), os.path.getmtime(hdr)):
+        subprocess.check_call(["g++", "-O2", "-std=c++17", "-Wall", "-o", DEMO, src, "-L", os.path.join(ROOT, "top_down_renderer_b200"),
+                               "-l:libtdr_b200.so", "-Wl,-rpath," + os.path.join(ROOT, "top_down_renderer_b200")])
+    return DEMO
+
+
+def write_inputs(d, N=800, seed=5):
+    C, H, W = 4, 400, 480
+    cm = synth.make_class_map(H, W, C, seed=seed)
+    img = synth.to_cv_image(cm)
+    pose, heading = synth.default_pose(cm, seed=seed)
+    pts = synth.make_scan(cm, pose, heading, seed=seed, n_rings=32, n_az=512)
+    np.array([H, W, C, N, seed, 100, 25], dtype=np.int32).tofile(os.path.join(d, "meta.i32"))
+    np.array([2.0, pose[0], pose[1], 6.0, math.degrees(heading), 3.0], dtype=np.float32).tofile(os.path.join(d, "meta.f32"))
+    img.tofile(os.path.join(d, "class_image.u8"))
+    pts.tofile(os.path.join(d, "points.f32"))
+    return cm, img, pts
+
+
+def test_host_mirror_compiles_and_refuses_to_run_without_gpu(tmp_path):
+    demo = build_demo()
+    import torch
+    if torch.cuda.is_available():
+        pytest.skip("a GPU is present")
+    write_inputs(str(tmp_path), N=16)
+    r = subprocess.run([demo, str(tmp_path)], capture_output=True, text=True)
+    assert r.returncode == 3 and "no CPU fallback" in r.stderr
+
+
+@pytest.mark.gpu
+def test_host_mirror_step_matches_oracle(tmp_path):
+    demo = build_demo()
+    d = str(tmp_path)
+    cm, img, pts = write_inputs(d)
+    r = subprocess.run([demo, d], capture_output=True, text=True, timeout=120)
+    assert r.returncode == 0, r.stdout + r.stderr
+    C, H, W = 4, cm.shape[0], cm.shape[1]
+    lut = synth.identity_lut(C)
+    ang = np.float32(2 * math.pi / 100)
+    # class images: bit-exact
+    scan_o = orc.render_polar(pts, 2.0, ang, 100, 25, lut, C)
+    scan = np.stack([np.fromfile(os.path.join(d, f"scan_{c}.f32"), dtype=np.float32).reshape(25, 100) for c in range(C)])
+    assert np.array_equal(scan, scan_o)
+    # particles: initialised on road pixels (state_particle.cpp:20-32), heading known
+    st = np.fromfile(os.path.join(d, "states_before.bin"), dtype=synth.STATE_DTYPE)
+    ld = np.fromfile(os.path.join(d, "last_dist.f32"), dtype=np.float32)
+    assert len(st) == 800 and (st["have_init"] == 1).all() and (st["scale"] == 2.0).all()
+    assert (cm[st["init_y_px"].astype(int), st["init_x_px"].astype(int)] == synth.ROAD).all()
+    assert (ld > 0).all()
+    # update: weights within 1e-5 of the oracle's on the same particle set, resampled states consistent
+    layers, mask = orc.compute_dists(orc.class_image_to_layers(img, lut, C, 1.0), 1.0)
+    tab = orc.polar_table(100, 25, ang, 1.0)
+    thetas, shifts = orc.search_list(100)
+    fp = orc.make_params(C, regularization=0.7, map_width=W, map_height=H)
+    w = orc.score_all(st.copy(), fp, layers, mask, 1.0, tab, 100, 25, scan_o, 2.0, thetas, shifts)
+    wn, arg, _ = orc.normalize(w, ld)
+    got = np.fromfile(os.path.join(d, "weights_norm.f32"), dtype=np.float32)
+    assert np.max(np.abs(got - wn) / wn) <= 1e-5
+    u = float(np.fromfile(os.path.join(d, "u.f32"), dtype=np.float32)[0])
+    after = np.fromfile(os.path.join(d, "states_after.bin"), dtype=synth.STATE_DTYPE)
+    idx = orc.resample_fast(got, u, len(st))                 # stage-wise: the device's own normalised weights
+    assert np.array_equal(after, st[idx])
+    mean = np.fromfile(os.path.join(d, "mean.f32"), dtype=np.float32)
+    wm, _ = orc.mean_cov(after)
+    assert abs(mean[0] - wm[0]) <= 0.002 and abs(mean[1] - wm[1]) <= 0.002 and abs(mean[2] - wm[2]) <= math.radians(0.01)

@@ -1,0 +1,322 @@
+// tdr_host.hpp — C++ host side above the C ABI (include/tdr.h): the reference's class interfaces for the hot path,
+// with the SAME names, argument meaning and (silent) error behaviour, on dependency-free types.
+//
+// The reference's classes use Eigen / PCL / OpenCV / ROS types, none of which exist in this image, so
+// this mirror swaps them for layout-compatible plain types (column-major ArrayXXf, 32-byte PointXYZI, raw uint8
+// image); INTEGRATION.md shows the one-line conversions the real adapters add.  Everything with arithmetic lives
+// behind the C ABI on the device; what stays here is what the reference also keeps on the host: particle
+// initialisation and propagation (libstdc++ RNG), the polar offset table and the theta-search list.
+//
+//   ScanRendererPolar   include/top_down_render/scan_renderer_polar.h:15-22
+//   TopDownMapPolar     include/top_down_render/top_down_map_polar.h:6-22 (+ top_down_map.h:52-101)
+//   ParticleFilter      include/top_down_render/particle_filter.h:22-41
+#pragma once
+#include <math.h>
+#include <algorithm>
+#include <cmath>
+#include <cstdint>
+#include <cstdio>
+#include <cstdlib>
+#include <limits>
+#include <random>
+#include <string>
+#include <vector>
+
+#include "../../include/tdr.h"
+
+namespace tdrhost {
+
+// Eigen::ArrayXXf / ArrayXXc stand-ins: column-major, element (r, c) at c*rows + r
+template <typename T> struct Array2D {
+  int rows_ = 0, cols_ = 0;
+  std::vector<T> d;
+  Array2D() {}
+  Array2D(int r, int c) : rows_(r), cols_(c), d((size_t)r * c, T(0)) {}
+  int rows() const { return rows_; }
+  int cols() const { return cols_; }
+  T* data() { return d.data(); }
+  const T* data() const { return d.data(); }
+  T& operator()(int r, int c) { return d[(size_t)c * rows_ + r]; }
+  const T& operator()(int r, int c) const { return d[(size_t)c * rows_ + r]; }
+};
+using ArrayXXf = Array2D<float>;
+using ArrayXXc = Array2D<uint8_t>;
+struct Vector2f { float x = 0, y = 0; };
+struct Vector2i { int x = 0, y = 0; };
+
+// pcl::PointXYZI layout (32 bytes; intensity at byte 16)
+struct PointXYZI { float x, y, z, pad0, intensity, pad1, pad2, pad3; };
+static_assert(sizeof(PointXYZI) == 32, "PointXYZI must be 32 bytes");
+
+using State = tdr_state;   // state_particle.h:9-17, identical layout
+
+// state_particle.h:19-38
+struct FilterParams {
+  float pos_cov = 0.3f, theta_cov = 0.0314f, regularization = 0.15f;
+  float init_pos_px_x = -1, init_pos_px_y = -1, init_pos_px_cov = -1;
+  float init_pos_m_x = -1, init_pos_m_y = -1, init_pos_deg_theta = -1, init_pos_deg_cov = -1;
+  bool force_on_map = false;
+  float fixed_scale = -1, scale_log_min = -0.1f, scale_log_max = 1;
+  std::vector<float> class_weights;
+};
+
+// one process-wide device context, like the reference's single ROS-thread ownership
+inline tdr_ctx* ctx() {
+  static tdr_ctx* c = nullptr;
+  if (!c) {
+    const char* dev = getenv("TDR_DEVICE");
+    if (tdr_create(&c, dev ? atoi(dev) : 0) != TDR_OK) {
+      fprintf(stderr, "[XView] libtdr_b200: %s\n", tdr_last_error());   // the reference logs and carries on
+      c = nullptr;
+    }
+  }
+  return c;
+}
+inline bool ok(int rc) {
+  if (rc != TDR_OK) fprintf(stderr, "[XView] libtdr_b200: %s\n", tdr_last_error());
+  return rc == TDR_OK;
+}
+
+class ScanRendererPolar {
+ public:
+  explicit ScanRendererPolar(const std::vector<int>& flatten_lut) : flatten_lut_(flatten_lut) {}
+  // scan_renderer_polar.cpp:83-109.  imgs: C pre-sized (n_theta x n_r) images; their size defines the raster.
+  void renderSemanticTopDown(const std::vector<PointXYZI>& cloud, float res, float ang_res, std::vector<ArrayXXf>& imgs) {
+    int max_cls = -1;
+    for (int v : flatten_lut_) max_cls = std::max(max_cls, v);
+    if ((int)imgs.size() < max_cls + 1 || !ctx()) return;                   // the reference's silent early-out (:85)
+    const int C = (int)imgs.size(), n_theta = imgs[0].rows(), n_r = imgs[0].cols();
+    if (!ok(tdr_scan_set_lut(ctx(), flatten_lut_.data(), (int)flatten_lut_.size(), C))) return;
+    if (!ok(tdr_scan_set_points(ctx(), cloud.data(), sizeof(PointXYZI), 16, (int64_t)cloud.size()))) return;
+    stage_.resize((size_t)C * n_theta * n_r);
+    if (!ok(tdr_scan_render_polar(ctx(), res, ang_res, n_theta, n_r, stage_.data()))) return;
+    for (int c = 0; c < C; c++)
+      std::copy(stage_.begin() + (size_t)c * n_theta * n_r, stage_.begin() + (size_t)(c + 1) * n_theta * n_r, imgs[c].d.begin());
+  }
+
+ private:
+  std::vector<int> flatten_lut_;
+  std::vector<float> stage_;
+};
+
+class TopDownMapPolar {
+ public:
+  struct Params {                       // top_down_map.h:54-62 (the dynamic-map fields)
+    std::vector<int> flatten_lut;
+    int num_classes = 0;
+    float resolution = 1;
+  };
+  explicit TopDownMapPolar(const Params& params) : params_(params) { samplePtsPolar(100, 50, (float)(2 * M_PI / 100)); }
+
+  // top_down_map.cpp:146-157: class-index image (row-major, row 0 = top) -> layers -> distance fields
+  void updateMap(const uint8_t* img, int rows, int cols, int stride, const Vector2i& map_center) {
+    if (!ctx()) return;
+    map_center_ = map_center;
+    std::vector<int32_t> lut(256, -1);                                     // padded like top_down_render.cpp:57
+    std::copy(params_.flatten_lut.begin(), params_.flatten_lut.end(), lut.begin());
+    if (!ok(tdr_map_set_class_image(ctx(), img, rows, cols, stride, lut.data(), 256, params_.num_classes, params_.resolution))) return;
+    int r = 0, c = 0, k = 0; float res = 1;
+    tdr_map_info(ctx(), &r, &c, &k, &res);
+    rows_ = r; cols_ = c;
+    layers_.resize((size_t)k * r * c); mask_.resize((size_t)r * c);
+    ok(tdr_map_get_layers(ctx(), layers_.data(), mask_.data()));           // host mirror for getClassesAtPoint
+    // have_map_ unless layer 1 is entirely zero (the isZero(0) quirk, :150)
+    have_map_ = true;
+    if (k > 1) {
+      bool all_zero = true;
+      for (size_t i = 0; i < (size_t)r * c && all_zero; i++) all_zero = layers_[(size_t)r * c + i] == 0.f;
+      have_map_ = !all_zero;
+    }
+    ok(tdr_map_set_polar_table(ctx(), tab_.data(), n_theta_, n_r_));
+  }
+  // top_down_map.cpp:159-170 (integer point)
+  void getClassesAtPoint(const Vector2i& center_ind, std::vector<int>& classes) const {
+    classes.clear();
+    const int cx = (int)((float)center_ind.x / params_.resolution), cy = (int)((float)center_ind.y / params_.resolution);
+    for (int cls = 0; cls < params_.num_classes; cls++)
+      if (cx < cols_ && cy < rows_ && cx >= 0 && cy >= 0 && layers_[(size_t)cls * rows_ * cols_ + (size_t)cx * rows_ + cy] < 1)
+        classes.push_back(cls);
+  }
+  // top_down_map_polar.cpp:21-53
+  void getLocalMap(Vector2f center, float scale, float res, std::vector<ArrayXXf>& dists, ArrayXXc& mask) {
+    if ((int)dists.size() < params_.num_classes || !ctx()) return;         // :25
+    const int P = n_theta_ * n_r_;
+    stage_.resize((size_t)params_.num_classes * P);
+    float cxy[2] = {center.x, center.y};
+    if (!ok(tdr_map_local_polar(ctx(), cxy, 1, scale, res, stage_.data(), mask.data()))) return;
+    for (int c = 0; c < params_.num_classes; c++) std::copy(stage_.begin() + (size_t)c * P, stage_.begin() + (size_t)(c + 1) * P, dists[c].d.begin());
+  }
+  void getLocalMap(Vector2f center, float res, std::vector<ArrayXXf>& dists, ArrayXXc& mask) { getLocalMap(center, 1, res, dists, mask); }   // :78-82
+  // top_down_map_polar.cpp:7-19 (+ samplePts, top_down_map.cpp:367-389): the offset table is computed on the host
+  void samplePtsPolar(int n_theta, int n_r, float ang_res) {
+    n_theta_ = n_theta; n_r_ = n_r;
+    tab_.resize((size_t)2 * n_theta * n_r);
+    for (int p = 0; p < n_theta * n_r; p++) {
+      const int row = p % n_theta, col = p / n_theta;
+      const float a0 = ((float)row - (float)(n_theta - 1) / 2.f) * ang_res;
+      const float a1 = (float)col * (1.f / params_.resolution);
+      tab_[2 * p] = cosf(a0) * a1;
+      tab_[2 * p + 1] = sinf(a0) * a1;
+    }
+    if (have_map_ && ctx()) ok(tdr_map_set_polar_table(ctx(), tab_.data(), n_theta, n_r));
+  }
+  Vector2i size() const { return Vector2i{cols_, rows_}; }
+  Vector2i mapCenter() const { return map_center_; }
+  int numClasses() const { return params_.num_classes; }
+  float resolution() const { return params_.resolution; }
+  bool haveMap() const { return have_map_; }
+  int nTheta() const { return n_theta_; }
+  int nR() const { return n_r_; }
+
+ private:
+  Params params_;
+  bool have_map_ = false;
+  Vector2i map_center_;
+  int rows_ = 0, cols_ = 0, n_theta_ = 0, n_r_ = 0;
+  std::vector<float> layers_, tab_, stage_;
+  std::vector<uint8_t> mask_;
+};
+
+class ParticleFilter {
+ public:
+  // particle_filter.cpp:3-17.  seed: the reference seeds from std::random_device; a fixed seed makes runs repeatable.
+  ParticleFilter(int N, TopDownMapPolar* map, FilterParams& params, uint32_t seed = std::random_device{}())
+      : gen_(seed), map_(map), params_(params), max_num_particles_(N) {
+    if (map_->haveMap()) initializeParticles();
+  }
+  // particle_filter.cpp:86-92 + StateParticle::propagate (state_particle.cpp:57-78): host RNG, as in the reference
+  void propagate(const Vector2f& trans, float omega) {
+    pull();
+    for (size_t i = 0; i < states_.size(); i++) {
+      State& s = states_[i];
+      const float c = cosf(s.theta), sn = sinf(s.theta);
+      const float gx = c * trans.x - sn * trans.y, gy = sn * trans.x + c * trans.y;
+      const float lx = s.dx_m, ly = s.dy_m;
+      s.dx_m += gx; s.dy_m += gy;
+      const float dist = sqrtf(gx * gx + gy * gy);
+      std::normal_distribution<float> disp_dist{0, params_.pos_cov * dist};
+      std::normal_distribution<float> theta_dist{0, params_.theta_cov * dist};
+      s.theta += theta_dist(gen_) + omega;
+      s.dx_m += disp_dist(gen_);
+      s.dy_m += disp_dist(gen_);
+      if (!scale_frozen_) {
+        std::normal_distribution<float> scale_dist{1, static_cast<float>(std::min(2. / dist, 0.02))};
+        s.scale *= scale_dist(gen_);
+      }
+      const float mx = lx - s.dx_m, my = ly - s.dy_m;
+      last_dist_[i] = sqrtf(mx * mx + my * my);
+    }
+    push();
+  }
+  // particle_filter.cpp:94-189.  top_down_geo is accepted and ignored, as in the reference's cost (F10).
+  void update(std::vector<ArrayXXf>& top_down_scan, std::vector<ArrayXXf>& /*top_down_geo*/, float res) {
+    if (num_particles_ == 0 || !ctx()) return;                             // :96-99
+    const int C = (int)top_down_scan.size(), n_theta = top_down_scan[0].rows(), n_r = top_down_scan[0].cols();
+    stage_.resize((size_t)C * n_theta * n_r);
+    for (int c = 0; c < C; c++) std::copy(top_down_scan[c].d.begin(), top_down_scan[c].d.end(), stage_.begin() + (size_t)c * n_theta * n_r);
+    if (!ok(tdr_scan_set_polar_images(ctx(), stage_.data(), n_theta, n_r, C))) return;
+    std::uniform_real_distribution<float> dist(0., 1.);
+    const float u = last_u_ = dist(gen_);                                  // the ONE draw of :172-173
+    if (!ok(tdr_pf_update(ctx(), res, u, num_particles_))) return;
+    host_dirty_ = true;
+  }
+  void meanLikelihood(float state[4]) { if (ctx()) ok(tdr_pf_pose(ctx(), state, nullptr, nullptr, nullptr)); }
+  void computeMeanCov(float cov[16]) { float m[4]; if (ctx()) ok(tdr_pf_pose(ctx(), m, cov, nullptr, nullptr)); }
+  void maxLikelihood(float state[4]) { if (ctx()) ok(tdr_pf_pose(ctx(), nullptr, nullptr, state, nullptr)); }
+  void computeCov(float cov[16]) { float m[4]; if (ctx()) ok(tdr_pf_pose(ctx(), nullptr, nullptr, m, cov)); }
+  int numParticles() const { return num_particles_; }
+  float scale() { pull(); return states_.empty() ? 1.f : states_[0].scale; }
+  bool isScaleFrozen() const { return scale_frozen_; }
+  // host views (the reference's visualize / GMM thread read the particles on the host)
+  const std::vector<State>& states() { pull(); return states_; }
+  const std::vector<float>& lastDist() const { return last_dist_; }
+  float lastUniform() const { return last_u_; }
+  std::vector<float> weights() {
+    std::vector<float> w(num_particles_);
+    if (ctx() && num_particles_) ok(tdr_pf_get_weights(ctx(), w.data(), num_particles_));
+    return w;
+  }
+
+ private:
+  // StateParticle::StateParticle(gen, map, params, init = true)  state_particle.cpp:3-49
+  State randomState() {
+    std::uniform_real_distribution<float> uniform_dist(0., 1.);
+    std::normal_distribution<float> normal_dist(0., 1.);
+    State s{};
+    const Vector2i sz = map_->size();
+    const float mw = (float)sz.x * map_->resolution(), mh = (float)sz.y * map_->resolution();
+    if (params_.fixed_scale < 0) s.scale = (float)std::pow(10, (uniform_dist(gen_) - 0.5) * 2);
+    else s.scale = params_.fixed_scale;
+    std::vector<int> cls_vec;
+    while (true) {
+      if (params_.init_pos_px_x > 0) {
+        s.init_x_px = std::clamp<float>(normal_dist(gen_) * params_.init_pos_px_cov + params_.init_pos_px_x, 0, mw);
+        s.init_y_px = std::clamp<float>(normal_dist(gen_) * params_.init_pos_px_cov + params_.init_pos_px_y, 0, mh);
+      } else {
+        s.init_x_px = uniform_dist(gen_) * mw;
+        s.init_y_px = uniform_dist(gen_) * mh;
+      }
+      map_->getClassesAtPoint(Vector2i{(int)s.init_x_px, (int)s.init_y_px}, cls_vec);
+      if (std::find(cls_vec.begin(), cls_vec.end(), 1) != cls_vec.end()) break;   // particle is on the road
+    }
+    if (params_.init_pos_deg_theta != std::numeric_limits<float>::infinity()) {
+      s.theta = normal_dist(gen_) * params_.init_pos_deg_cov + params_.init_pos_deg_theta;
+      s.theta *= M_PI / 180;
+      s.have_init = 1;
+    } else { s.theta = 0; s.have_init = 0; }
+    return s;
+  }
+  // particle_filter.cpp:19-84 (the GMM thread and visualisation are out of scope)
+  void initializeParticles() {
+    size_t num_at_scale = 1;
+    if (params_.fixed_scale < 0) num_at_scale = 10; else scale_frozen_ = true;
+    for (int i = 0; i < max_num_particles_ / (int)num_at_scale; i++) {
+      State proto = randomState();
+      for (float scale = 0; scale < 1; scale += 1. / num_at_scale) {
+        State p = randomState();                                            // the reference constructs (and draws) again
+        if (params_.fixed_scale < 0) { p = proto; p.scale = (float)std::pow(10., scale); }
+        states_.push_back(p);
+        (void)randomState();                                                // new_particles_ entry: same RNG consumption
+      }
+    }
+    num_particles_ = (int)states_.size();
+    last_dist_.assign(states_.size(), 0.f);
+    tdr_filter_params fp{};
+    fp.regularization = params_.regularization; fp.force_on_map = params_.force_on_map ? 1 : 0;
+    fp.fixed_scale = params_.fixed_scale; fp.scale_log_min = params_.scale_log_min; fp.scale_log_max = params_.scale_log_max;
+    fp.num_classes = map_->numClasses();
+    for (int c = 0; c < fp.num_classes && c < 16; c++) fp.class_weights[c] = c < (int)params_.class_weights.size() ? params_.class_weights[c] : 1.f;
+    if (!ctx() || !ok(tdr_pf_set_params(ctx(), &fp))) return;
+    // theta-search candidates with the reference's own float loop (state_particle.cpp:197, :123-128)
+    std::vector<float> thetas; std::vector<int32_t> shifts;
+    const int nb = map_->nTheta();
+    for (float t = 0; t < 2 * M_PI; t += 2 * M_PI / 40) {
+      thetas.push_back(t);
+      int s = (int)std::round((double)(t * nb / 2) / M_PI);
+      while (s >= nb) s -= nb;
+      while (s < 0) s += nb;
+      shifts.push_back(s);
+    }
+    ok(tdr_pf_set_search(ctx(), thetas.data(), shifts.data(), (int)thetas.size()));
+    push();
+  }
+  void push() { if (ctx() && !states_.empty()) ok(tdr_pf_set_states(ctx(), states_.data(), last_dist_.data(), (int64_t)states_.size())); host_dirty_ = false; }
+  void pull() {
+    if (!host_dirty_ || !ctx()) return;
+    int64_t n = 0; tdr_pf_count(ctx(), &n);
+    states_.resize((size_t)n); last_dist_.resize((size_t)n, 0.f);
+    if (n) ok(tdr_pf_get_states(ctx(), states_.data(), n));
+    num_particles_ = (int)n; host_dirty_ = false;
+  }
+
+  std::mt19937 gen_;
+  TopDownMapPolar* map_;
+  FilterParams params_;
+  int max_num_particles_ = 0, num_particles_ = 0;
+  bool scale_frozen_ = false, host_dirty_ = false;
+  float last_u_ = 0.f;
+  std::vector<State> states_;
+  std::vector<float> last_dist_, stage_;
+};
+
+}  // namespace tdrhost
