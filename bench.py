@@ -428,9 +428,16 @@ def run_grid(args, wl):
     ctx.pf_set_params(C, regularization=0.7)
     stream = torch.cuda.ExternalStream(ctx.stream, device=local)
     dev = f"cuda:{local}"
-    send = torch.empty(n_local * S, dtype=torch.float32, device=dev)
-    recv = torch.empty(world * n_local * S, dtype=torch.float32, device=dev) if world > 1 else send
-    ctx.grid_set_costs_buffer(send.data_ptr(), send.numel())
+    fused = world > 1 and args.grid_collective == "fused"
+    tiny = torch.zeros(1, device=dev)
+    if fused:
+        gather = sharded.FusedGridGather(ctx, rank, world, n_total, S)     # peers map each other's full arrays
+        full_ptr, full_numel = gather.full_ptr, gather.numel()
+    else:
+        send = torch.empty(n_local * S, dtype=torch.float32, device=dev)
+        recv = torch.empty(world * n_local * S, dtype=torch.float32, device=dev) if world > 1 else send
+        ctx.grid_set_costs_buffer(send.data_ptr(), send.numel())
+        full_ptr, full_numel = recv.data_ptr(), recv.numel()
     pts_pinned = torch.from_numpy(inp["pts"]).pin_memory()
     flush = torch.empty(256 << 20, dtype=torch.uint8, device=dev)
     ctx.scan_set_points_ptr(pts_pinned.data_ptr(), 32, 16, pts_pinned.shape[0])
@@ -443,9 +450,11 @@ def run_grid(args, wl):
         with torch.cuda.stream(stream):
             ctx.scan_render_polar(res, float(ANG_RES), N_THETA, N_R, want=False)
             ctx.grid_run_resident(n_local, 2.0, res, shifts)
-            if world > 1:
+            if fused:
+                dist.all_reduce(tiny)                                      # barrier: every rank's kernel (and its peer stores) is done
+            elif world > 1:
                 dist.all_gather_into_tensor(recv, send)
-            return ctx.grid_best_dev(recv.data_ptr(), recv.numel())        # D2H of (cost, index): synchronises
+            return ctx.grid_best_dev(full_ptr, full_numel)                 # D2H of (cost, index): synchronises
 
     def barrier():
         if world > 1:
@@ -506,7 +515,8 @@ def run_grid(args, wl):
                "config": {"workload": wl["desc"], "centres_total": n_total, "centres_per_gpu": n_local, "shifts": S,
                           "map_px": [side, side], "classes": C, "polar_image": [N_THETA, N_R], "res_m_per_bin": res,
                           "parallelism": f"centre shards x{world}, map replicated"
-                          + (", 1 all-gather(costs)/step" if world > 1 else ""),
+                          + ((", weight all-gather fused into the score kernel (NVLink peer stores) + 1 barrier all-reduce/step"
+                              if fused else ", 1 NCCL all-gather(costs)/step") if world > 1 else ""),
                           "l2": "flushed (256 MiB write) between steps, outside the timed events"},
                "clocks": clocks, "best": {"cost": best[0], "flat_index": best[1]},
                "stage_ms": {"score": k_ms},
@@ -520,6 +530,9 @@ def run_grid(args, wl):
                             "algorithmic_bytes_per_launch": n_local * b_score(C), "kernel_ms": k_ms},
                "cpu_baseline": None}
         emit(out)
+    if fused:
+        dist.barrier()
+        gather.close()
     ctx.close()
     if world > 1:
         dist.barrier()
@@ -555,6 +568,8 @@ def main():
     ap.add_argument("--workload", default="global", choices=sorted(WORKLOADS))
     ap.add_argument("--particles", type=int, default=0, help="override particles per GPU")
     ap.add_argument("--no-cpu", action="store_true", help="skip the cpu_baseline leg")
+    ap.add_argument("--grid-collective", default="fused", choices=["fused", "nccl"],
+                    help="grid workload, N > 1: all-gather fused into the score kernel over peer memory, or NCCL")
     args = ap.parse_args()
     args.warmup = max(args.warmup, 0)
     wl = dict(WORKLOADS[args.workload])

@@ -179,6 +179,19 @@ int tdr_grid_best(tdr_ctx* ctx, float* best_cost, int64_t* best_index);
  * (the all-gather output; first index wins on ties, NaN never wins) */
 int tdr_grid_set_costs_buffer(tdr_ctx* ctx, void* dev_costs, int64_t capacity_floats);
 int tdr_grid_best_dev(tdr_ctx* ctx, const void* dev_costs, int64_t n, float* best_cost, int64_t* best_index);
+/* ---- fused weight all-gather over NVLink peer memory (cfg4: the exhaustive grid sharded over the GPUs of a box).
+ * Every rank allocates the FULL cost array (n_total x n_shifts floats) with tdr_grid_peer_alloc, exports it as a
+ * CUDA IPC handle, opens the other ranks' handles (tdr_grid_peer_open) and registers all mapped pointers in rank
+ * order, its own included (tdr_grid_peer_set).  From then on tdr_grid_costs makes the score kernel store every
+ * cost of this rank's shard into ALL ranks' arrays at row_offset — the all-gather happens in the kernel's
+ * epilogue, overlapped tile by tile with the gather / MMA pipeline, instead of as a separate NCCL call.  The
+ * caller issues one cross-rank barrier (a tiny all-reduce on tdr_stream()) before any rank reads its array. */
+#define TDR_IPC_HANDLE_BYTES 64
+#define TDR_MAX_PEERS 8
+int tdr_grid_peer_alloc(tdr_ctx* ctx, int64_t n_floats, void** dev_ptr, uint8_t handle[TDR_IPC_HANDLE_BYTES]);
+int tdr_grid_peer_open(tdr_ctx* ctx, const uint8_t handle[TDR_IPC_HANDLE_BYTES], void** dev_ptr);
+int tdr_grid_peer_set(tdr_ctx* ctx, void* const* peer_ptrs, int n_peers, int64_t row_offset);
+int tdr_grid_peer_clear(tdr_ctx* ctx);   /* forgets the registration and closes the opened mappings */
 /* device pointers of resident buffers for collectives issued by the host layer (NCCL through
  * torch.distributed): weights (n floats) / grid costs (n*n_shifts floats) */
 int tdr_dev_ptr(tdr_ctx* ctx, int which, void** ptr, int64_t* n_elems);

@@ -619,3 +619,57 @@ def test_fused_small_update_bit_exact(ctx, kind, n, M):
     assert arg == warg or np.isnan(want_w).all()
     assert np.array_equal(idx, want_idx)
     assert len(new) == M and np.array_equal(new["init_x_px"], st["init_x_px"][want_idx])
+
+
+# ---- fused weight all-gather over peer memory: two ranks (processes) sharing this one GPU -------------------------
+def _fused_rank(rank, world_size, port, q):
+    import os
+    import torch.distributed as dist
+    os.environ.update(MASTER_ADDR="127.0.0.1", MASTER_PORT=str(port))
+    dist.init_process_group("gloo", rank=rank, world_size=world_size)
+    try:
+        from top_down_renderer_b200 import sharded
+        wd = make_world()
+        c = make_ctx(wd)
+        centers = synth.grid_centers(wd.h, wd.w, 25)[:1200]
+        shifts = np.arange(100, dtype=np.int32)
+        n_total = len(centers)
+        g = sharded.FusedGridGather(c, rank, world_size, n_total, len(shifts))
+        c.scan_set_polar_images(wd.scan)
+        c.grid_costs(centers[g.lo:g.hi], 2.0, 4.0, shifts, want=False)       # kernel stores into BOTH ranks' arrays
+        c.sync()
+        dist.barrier()                                                         # every rank's kernel has finished
+        full = c.copy_from_device(g.full_ptr, g.numel()).reshape(n_total, len(shifts))
+        best = c.grid_best_dev(g.full_ptr, g.numel())
+        q.put((rank, full, best))
+        dist.barrier()
+        g.close()
+        c.close()
+    finally:
+        dist.destroy_process_group()
+
+
+def test_fused_peer_allgather_two_ranks_one_gpu(world):
+    import socket
+    import torch.multiprocessing as mp
+    s = socket.socket(); s.bind(("127.0.0.1", 0)); port = s.getsockname()[1]; s.close()
+    mpc = mp.get_context("spawn")
+    q = mpc.Queue()
+    procs = [mpc.Process(target=_fused_rank, args=(r, 2, port, q)) for r in range(2)]
+    for p in procs:
+        p.start()
+    res = sorted([q.get(timeout=300) for _ in range(2)], key=lambda t: t[0])
+    for p in procs:
+        p.join(timeout=120)
+        assert p.exitcode == 0
+    centers = synth.grid_centers(world.h, world.w, 25)[:1200]
+    shifts = np.arange(100, dtype=np.int32)
+    c = make_ctx(world)
+    c.set_score_impl(2)                       # the peer path always runs the tensor-core ring kernel
+    c.scan_set_polar_images(world.scan)
+    want = c.grid_costs(centers, 2.0, 4.0, shifts)
+    wbest = c.grid_best()
+    c.close()
+    for rank, full, best in res:
+        assert np.array_equal(full.view(np.uint32), want.view(np.uint32)), rank     # same kernel, same bits, on every rank
+        assert best == wbest

@@ -302,6 +302,36 @@ class Context:
         check(self._lib.tdr_grid_best_dev(self._h, C.c_void_p(dev_ptr), C.c_int64(n), C.byref(c), C.byref(i)))
         return c.value, i.value
 
+    # fused weight all-gather over peer memory
+    def grid_peer_alloc(self, n_floats):
+        p = C.c_void_p()
+        h = (C.c_uint8 * 64)()
+        check(self._lib.tdr_grid_peer_alloc(self._h, C.c_int64(n_floats), C.byref(p), h))
+        return p.value, bytes(h)
+
+    def grid_peer_open(self, handle: bytes):
+        p = C.c_void_p()
+        h = (C.c_uint8 * 64).from_buffer_copy(handle)
+        check(self._lib.tdr_grid_peer_open(self._h, h, C.byref(p)))
+        return p.value
+
+    def grid_peer_set(self, ptrs, row_offset):
+        arr = (C.c_void_p * len(ptrs))(*ptrs)
+        check(self._lib.tdr_grid_peer_set(self._h, arr, len(ptrs), C.c_int64(row_offset)))
+
+    def grid_peer_clear(self):
+        check(self._lib.tdr_grid_peer_clear(self._h))
+
+    def copy_from_device(self, dev_ptr, n_floats):
+        """debug / test helper: D2H of n floats from a raw device pointer (synchronises the context stream first)"""
+        self.sync()
+        out = np.empty(n_floats, dtype=np.float32)
+        libcudart = C.CDLL("libcudart.so.12")
+        rc = libcudart.cudaMemcpy(C.c_void_p(out.ctypes.data), C.c_void_p(dev_ptr), C.c_size_t(n_floats * 4), C.c_int(2))
+        if rc != 0:
+            raise RuntimeError(f"cudaMemcpy D2H failed: {rc}")
+        return out
+
     def grid_best(self):
         c = C.c_float()
         i = C.c_int64()

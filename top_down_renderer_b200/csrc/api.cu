@@ -149,6 +149,8 @@ void tdr_destroy(tdr_ctx* c) {
                          &c->prefix, &c->idx, &c->scal, &c->pose_tmp, &c->grid_centers, &c->grid_costs,
                          &c->grid_shifts, &c->d_cw, &c->map16, &c->seq_ws, &c->scan_op, &c->bin_counts, &c->perm};
   for (auto* b : bufs) b->release();
+  for (void* p : c->grid_opened) cudaIpcCloseMemHandle(p);
+  c->grid_full.release();
   c->part[0].release(); c->part[1].release(); c->ckpt.release(); c->all.release();
   c->pin.release();
   for (int k = 0; k <= TDR_N_STAGES; k++) if (c->stage_ev[k]) cudaEventDestroy(c->stage_ev[k]);
@@ -613,7 +615,8 @@ int tdr_grid_costs(tdr_ctx* ctx, const float* centers_xy, int64_t n, float scale
     if (int e = ctx->grid_centers.reserve((size_t)n * 8)) return e;
     TDR_CUDA(cudaMemcpyAsync(ctx->grid_centers.p, centers_xy, (size_t)n * 8, cudaMemcpyHostToDevice, ctx->stream));
   }
-  if (!ctx->grid_costs_ext) { if (int e = ctx->grid_costs.reserve((size_t)n * n_shifts * 4)) return e; }
+  if (ctx->grid_n_peers) { /* costs go straight into the peer-mapped full arrays */ }
+  else if (!ctx->grid_costs_ext) { if (int e = ctx->grid_costs.reserve((size_t)n * n_shifts * 4)) return e; }
   else TDR_REQUIRE(ctx->grid_costs_ext_cap >= n * n_shifts, TDR_EINVAL, "external cost buffer too small");
   if (int e = ctx->grid_shifts.reserve((size_t)n_shifts * 4)) return e;
   TDR_CUDA(cudaMemcpyAsync(ctx->grid_shifts.p, shifts, (size_t)n_shifts * 4, cudaMemcpyHostToDevice, ctx->stream));
@@ -624,6 +627,7 @@ int tdr_grid_costs(tdr_ctx* ctx, const float* centers_xy, int64_t n, float scale
   stage_mark(ctx, TDR_STAGE_NORMALIZE); stage_mark(ctx, TDR_STAGE_RESAMPLE); stage_mark(ctx, TDR_N_STAGES);
   ctx->stage_valid = ctx->profiling;
   if (centers_xy || costs_out) {      // caller-owned pageable buffers: finish before returning
+    TDR_REQUIRE(!(costs_out && ctx->grid_n_peers), TDR_ESTATE, "with peer buffers registered the costs live in the full arrays");
     if (costs_out) TDR_CUDA(cudaMemcpyAsync(costs_out, grid_costs_ptr(ctx), (size_t)n * n_shifts * 4, cudaMemcpyDeviceToHost, ctx->stream));
     TDR_CUDA(cudaStreamSynchronize(ctx->stream));
   }
@@ -652,6 +656,42 @@ int tdr_grid_best_dev(tdr_ctx* ctx, const void* dev_costs, int64_t n, float* bes
   int e = grid_best(ctx, reinterpret_cast<const float*>(dev_costs), n, best_cost, &idx);
   if (best_index) *best_index = idx;
   return e;
+}
+
+int tdr_grid_peer_alloc(tdr_ctx* ctx, int64_t n_floats, void** dev_ptr, uint8_t handle[TDR_IPC_HANDLE_BYTES]) {
+  CTX_CHECK(ctx);
+  static_assert(sizeof(cudaIpcMemHandle_t) == TDR_IPC_HANDLE_BYTES, "IPC handle size");
+  TDR_REQUIRE(n_floats > 0 && dev_ptr && handle, TDR_EINVAL, "bad arguments");
+  if (int e = ctx->grid_full.reserve((size_t)n_floats * 4)) return e;
+  cudaIpcMemHandle_t h;
+  TDR_CUDA(cudaIpcGetMemHandle(&h, ctx->grid_full.p));
+  memcpy(handle, &h, TDR_IPC_HANDLE_BYTES);
+  *dev_ptr = ctx->grid_full.p;
+  return TDR_OK;
+}
+int tdr_grid_peer_open(tdr_ctx* ctx, const uint8_t handle[TDR_IPC_HANDLE_BYTES], void** dev_ptr) {
+  CTX_CHECK(ctx);
+  TDR_REQUIRE(handle && dev_ptr, TDR_EINVAL, "bad arguments");
+  cudaIpcMemHandle_t h;
+  memcpy(&h, handle, TDR_IPC_HANDLE_BYTES);
+  void* p = nullptr;
+  TDR_CUDA(cudaIpcOpenMemHandle(&p, h, cudaIpcMemLazyEnablePeerAccess));
+  ctx->grid_opened.push_back(p);
+  *dev_ptr = p;
+  return TDR_OK;
+}
+int tdr_grid_peer_set(tdr_ctx* ctx, void* const* peer_ptrs, int n_peers, int64_t row_offset) {
+  TDR_REQUIRE(ctx && peer_ptrs && n_peers >= 1 && n_peers <= TDR_MAX_PEERS && row_offset >= 0, TDR_EINVAL, "bad peer registration");
+  for (int k = 0; k < n_peers; k++) { TDR_REQUIRE(peer_ptrs[k], TDR_EINVAL, "null peer pointer %d", k); ctx->grid_peers[k] = reinterpret_cast<float*>(peer_ptrs[k]); }
+  ctx->grid_n_peers = n_peers; ctx->grid_peer_row0 = row_offset;
+  return TDR_OK;
+}
+int tdr_grid_peer_clear(tdr_ctx* ctx) {
+  CTX_CHECK(ctx);
+  cudaStreamSynchronize(ctx->stream);
+  for (void* p : ctx->grid_opened) cudaIpcCloseMemHandle(p);
+  ctx->grid_opened.clear(); ctx->grid_n_peers = 0;
+  return TDR_OK;
 }
 
 int tdr_dev_ptr(tdr_ctx* ctx, int which, void** ptr, int64_t* n_elems) {

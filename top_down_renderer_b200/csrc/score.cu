@@ -390,12 +390,13 @@ int score_grid(tdr_ctx* ctx, long long n, float scale, float res) {
   sp.init_x = sp.init_y = sp.dx = sp.dy = nullptr; sp.theta = nullptr; sp.scale = nullptr; sp.have_init = nullptr; sp.weights = nullptr;
   const int P = sp.P;
   bool used = false;
-  if (ctx->score_impl == 2 || (ctx->score_impl == 0 && n >= 4096)) {
-    if (ctx->mma_kernel == 1) { if (int e = score_mma_list(ctx, res, true, n, scale, sp.shifts, sp.n_shifts, &used)) return e; }
+  if (ctx->score_impl == 2 || ctx->grid_n_peers || (ctx->score_impl == 0 && n >= 4096)) {
+    if (ctx->mma_kernel == 1 && !ctx->grid_n_peers) { if (int e = score_mma_list(ctx, res, true, n, scale, sp.shifts, sp.n_shifts, &used)) return e; }
     if (!used) { if (int e = score_mma(ctx, res, true, n, scale, sp.shifts, ctx->grid_shifts_host.data(), sp.n_shifts, &used)) return e; }
-    if (!used && ctx->mma_kernel != 1) { if (int e = score_mma_list(ctx, res, true, n, scale, sp.shifts, sp.n_shifts, &used)) return e; }
+    if (!used && ctx->mma_kernel != 1 && !ctx->grid_n_peers) { if (int e = score_mma_list(ctx, res, true, n, scale, sp.shifts, sp.n_shifts, &used)) return e; }
   }
   if (used) return TDR_OK;
+  TDR_REQUIRE(ctx->grid_n_peers == 0, TDR_EUNSUPPORTED, "the fused peer all-gather needs the tensor-core ring kernel (n_theta <= 112 and even, distinct shifts)");
   TDR_REQUIRE(P <= SEARCH_THREADS * SEARCH_JMAX, TDR_EUNSUPPORTED, "polar image too large");
   TDR_CUDA(cudaFuncSetAttribute(k_score_search<SEARCH_THREADS, SEARCH_JMAX>, cudaFuncAttributeMaxDynamicSharedMemorySize, 200 * 1024));
   size_t smem = (size_t)P * 32 + (size_t)sp.n_shifts * (SEARCH_THREADS / 32) * 8 + 256;

@@ -102,6 +102,9 @@ struct MmaParams {
   const float* thetas; const int32_t* shifts; int n_shifts;
   // grid mode
   const float* centers; float grid_scale; float* costs;
+  // fused all-gather: every cost is stored into all ranks' full arrays (NVLink peer mappings) at this rank's rows
+  float* cost_peers[TDR_MAX_PEERS]; int n_cost_peers; long long cost_row0;
+  int identity_shifts;      // shifts[k] == k for all k and n_shifts % 4 == 0: vector stores of the cost rows
 };
 
 static const int MAX_RING_ROWS = 2 * RING_N;                  // n_theta <= RING_N
@@ -118,7 +121,7 @@ template <int T, int R> struct MmaCfg {
   static const int kByTmem = 512 / kTmemCols, kByRegs = 65536 / (kThreads * 96) < 1 ? 1 : 65536 / (kThreads * 96);
   static const int kCtasPerSm = kByTmem < kByRegs ? kByTmem : kByRegs;
   static const int kStageBytes = MMA_G * T * A_TILE;
-  static const int kFixed = 2 * RING_SLOT_BYTES + NB2 * B2_BYTES + NA2 * T * A2_TILE + 128 * T * R * 4 + 1024;
+  static const int kFixed = 2 * RING_SLOT_BYTES + NB2 * B2_BYTES + NA2 * T * A2_TILE + 128 * T * R * 4 + 1024 + 4 * T * 32 * 17 * 4;
   static const int kBudget = (216 * 1024) / kCtasPerSm - 1280 - kFixed;
   // every gather thread keeps two of ITS stages in flight, i.e. spans 2R stages: leave twice that as slack
   static const int kStagesMax = 4 * R < 8 ? 8 : 4 * R;
@@ -142,6 +145,7 @@ __global__ void __launch_bounds__(128 * T * R + 64, MmaCfg<T, R>::kCtasPerSm) k_
   uint64_t* bars = reinterpret_cast<uint64_t*>(s_known + 128 * T * R);
   uint32_t* s_tmem = reinterpret_cast<uint32_t*>(bars + 2 * NS + 5 + 2 * NB2);
   short* s_inv = reinterpret_cast<short*>(s_tmem + 2);                  // [RING_N] shift -> first position in the list
+  float* s_tile = reinterpret_cast<float*>(s_inv + RING_N + 8);         // [4T warps][32][17] epilogue transpose tiles
   const int tid = threadIdx.x, warp = tid >> 5, lane = tid & 31;
   const uint32_t bar_full = smem_u32(bars), bar_empty = smem_u32(bars + NS);
   const uint32_t bar_rfull = smem_u32(bars + 2 * NS), bar_rempty = smem_u32(bars + 2 * NS + 2), bar_accum = smem_u32(bars + 2 * NS + 4);
@@ -274,16 +278,53 @@ __global__ void __launch_bounds__(128 * T * R + 64, MmaCfg<T, R>::kCtasPerSm) k_
         tmem_ld16(trow + (uint32_t)(ch * 16), vc);
         tmem_ld16(trow + (uint32_t)(RING_N + ch * 16), vn);
         tmem_wait_ld();
+        float cst[16];
 #pragma unroll
         for (int j = 0; j < 16; j++) {
           const int s = ch * 16 + j;
           const int k = s < n_theta ? s_inv[s] : -1;       // position of shift s in the candidate list (-1: not asked)
-          if (k >= 0) {
-            float cost = unknown ? __int_as_float(0x7fc00000)
-                                 : TDR_FDIV(TDR_FMUL(__uint_as_float(vc[j]), 0.01f), __uint_as_float(vn[j]));   // :137,154
-            if (sp.costs && i >= 0) sp.costs[i * sp.n_shifts + k] = cost;
-            // first strict minimum in LIST order == lexicographic minimum of (cost, list position)
-            if (cost < best || (cost == best && k < best_k)) { best = cost; best_k = k; }
+          cst[j] = unknown ? __int_as_float(0x7fc00000)
+                           : TDR_FDIV(TDR_FMUL(__uint_as_float(vc[j]), 0.01f), __uint_as_float(vn[j]));   // :137,154
+          // first strict minimum in LIST order == lexicographic minimum of (cost, list position)
+          if (k >= 0 && (cst[j] < best || (cst[j] == best && k < best_k))) { best = cst[j]; best_k = k; }
+        }
+        if (sp.costs || sp.n_cost_peers) {          // warp-uniform
+          const int n_dst = sp.n_cost_peers ? sp.n_cost_peers : 1;
+          const long long row = (sp.n_cost_peers ? sp.cost_row0 + i : i) * sp.n_shifts;
+          if (sp.identity_shifts) {
+            // all shifts in order: column s is list position s.  The warp's 32 rows x 16 columns go through a
+            // shared-memory tile so that four lanes write one row's 64 contiguous bytes (8 rows per store
+            // instruction) — the difference between usable and useless NVLink packets for the peer copies.
+            float* tile = s_tile + (size_t)(warp % (4 * T)) * (32 * 17);
+#pragma unroll
+            for (int j = 0; j < 16; j++) tile[lane * 17 + j] = cst[j];
+            __syncwarp();
+            const int piece = lane & 3;
+            const bool col_ok = ch * 16 + piece * 4 + 3 < sp.n_shifts;
+#pragma unroll
+            for (int q = 0; q < 4; q++) {
+              const int r = q * 8 + (lane >> 2);
+              const long long ir = __shfl_sync(0xffffffffu, i, r);
+              const float* src = tile + r * 17 + piece * 4;
+              const float4 v = make_float4(src[0], src[1], src[2], src[3]);
+              if (ir >= 0 && col_ok) {
+                const long long at = (sp.n_cost_peers ? sp.cost_row0 + ir : ir) * sp.n_shifts + ch * 16 + piece * 4;
+#pragma unroll 1
+                for (int d = 0; d < n_dst; d++)
+                  *reinterpret_cast<float4*>((sp.n_cost_peers ? sp.cost_peers[d] : sp.costs) + at) = v;
+              }
+            }
+            __syncwarp();
+          } else {
+#pragma unroll
+            for (int j = 0; j < 16; j++) {
+              const int s = ch * 16 + j;
+              const int k = s < n_theta ? s_inv[s] : -1;
+              if (k >= 0 && i >= 0) {
+#pragma unroll 1
+                for (int d = 0; d < n_dst; d++) (sp.n_cost_peers ? sp.cost_peers[d] : sp.costs)[row + k] = cst[j];
+              }
+            }
           }
         }
       }
@@ -441,6 +482,10 @@ int score_mma(tdr_ctx* ctx, float res, bool grid_mode, long long n_items, float 
   if (grid_mode) {
     sp.n_work = n_items; sp.centers = ctx->grid_centers.as<float>(); sp.grid_scale = grid_scale;
     sp.costs = grid_costs_ptr(ctx);
+    sp.n_cost_peers = ctx->grid_n_peers; sp.cost_row0 = ctx->grid_peer_row0;
+    sp.identity_shifts = (n_shifts % 4 == 0) ? 1 : 0;
+    for (int k = 0; k < n_shifts; k++) if (host_shifts[k] != k) sp.identity_shifts = 0;
+    for (int d = 0; d < ctx->grid_n_peers; d++) sp.cost_peers[d] = ctx->grid_peers[d];
   } else {
     sp.n_work = ctx->n_uninit;
     sp.init_x = pt.init_x.as<float>(); sp.init_y = pt.init_y.as<float>(); sp.dx = pt.dx.as<float>(); sp.dy = pt.dy.as<float>();

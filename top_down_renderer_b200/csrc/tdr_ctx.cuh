@@ -162,6 +162,12 @@ struct tdr_ctx {
   int64_t grid_n = 0;
   int grid_shifts_n = 0;
   std::vector<int32_t> grid_shifts_host;
+  // fused all-gather: peer-mapped full cost arrays (rank order), this rank's row offset
+  float* grid_peers[TDR_MAX_PEERS] = {};
+  int grid_n_peers = 0;
+  int64_t grid_peer_row0 = 0;
+  tdr::DevBuf grid_full;                 // this rank's full array (IPC-exported)
+  std::vector<void*> grid_opened;        // mappings to close
   float* grid_costs_ext = nullptr;       // caller-provided device buffer for the costs (tdr_grid_set_costs_buffer)
   int64_t grid_costs_ext_cap = 0;
 };

@@ -72,6 +72,31 @@ class ShardedFilter:
             return ctx.pf_pose_gathered(self.recv.data_ptr(), self.world, n_local, want_ml)
 
 
+class FusedGridGather:
+    """cfg4: the exhaustive grid sharded over the GPUs of one box with the weight all-gather FUSED into the score
+    kernel.  Every rank owns a full (n_total x n_shifts) cost array that its peers have mapped through CUDA IPC
+    over NVLink; the kernel's epilogue stores each cost of the local shard into all of them, so when the kernels
+    have finished every rank holds every cost — no NCCL all-gather, the transfer overlaps the gather / MMA pipeline
+    tile by tile.  One tiny all-reduce on the context stream is the cross-rank barrier."""
+
+    def __init__(self, ctx, rank: int, world: int, n_total: int, n_shifts: int, group=None):
+        import torch.distributed as dist
+        self.ctx, self.rank, self.world, self.group = ctx, rank, world, group
+        self.n_total, self.n_shifts = n_total, n_shifts
+        self.full_ptr, handle = ctx.grid_peer_alloc(n_total * n_shifts)
+        handles = [None] * world
+        dist.all_gather_object(handles, handle, group=group)
+        ptrs = [self.full_ptr if r == rank else ctx.grid_peer_open(handles[r]) for r in range(world)]
+        self.lo, self.hi = shard_range(n_total, rank, world)
+        ctx.grid_peer_set(ptrs, self.lo)
+
+    def numel(self):
+        return self.n_total * self.n_shifts
+
+    def close(self):
+        self.ctx.grid_peer_clear()
+
+
 # ---- layout helpers (numpy): the shard block exactly as k_pack_shard / k_unpack_all lay it out.
 # Used by the CPU (gloo) tests of the protocol and as executable documentation of the wire format.
 _ROWS = ("weight", "init_x_px", "init_y_px", "dx_m", "dy_m", "theta", "scale", "have_init", "last_dist")
