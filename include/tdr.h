@@ -124,6 +124,11 @@ int tdr_scan_set_lut(tdr_ctx* ctx, const int32_t* lut, int n_lut, int num_classe
 int tdr_scan_render_polar(tdr_ctx* ctx, float res, float ang_res, int n_theta, int n_r, float* imgs);
 /* a2: ScanRenderer::renderSemanticTopDown (scan_renderer.cpp:55-78); C col-major rows x cols */
 int tdr_scan_render_cart(tdr_ctx* ctx, float res, int rows, int cols, float* imgs);
+/* BASELINE cfg5 (refine_map-style batch rasterisation): MapRefiner::loadSemOccGrid's binning rule
+ * (src/refine_map.cpp:76-94) over n points (x, y) with class indices: ind = floor(pt/res) + (int)(centre/res), one
+ * uint8 counter per (class, y, x), wrapping mod 256 like the reference's "+= 1".  maps_out: C x height x width. */
+int tdr_refine_bin(tdr_ctx* ctx, const float* xy, const int32_t* cls, int64_t n, float res, float center_x, float center_y,
+                   int width, int height, int num_classes, uint8_t* maps_out);
 /* upload externally rendered polar class images instead (ParticleFilter::update takes them
  * as an argument, particle_filter.cpp:94) */
 int tdr_scan_set_polar_images(tdr_ctx* ctx, const float* imgs, int n_theta, int n_r, int num_classes);

@@ -673,3 +673,26 @@ def test_fused_peer_allgather_two_ranks_one_gpu(world):
     for rank, full, best in res:
         assert np.array_equal(full.view(np.uint32), want.view(np.uint32)), rank     # same kernel, same bits, on every rank
         assert best == wbest
+
+
+def test_refine_map_binning_and_distance_rebuild():
+    """BASELINE cfg5 as a composition: refine_map's binning rule over a batch of points, then the distance fields of
+    the binned class maps (computeDists) — both bit-exact"""
+    rng = np.random.default_rng(55)
+    n, Cn, Wd, Hd = 400_000, 5, 300, 260
+    xy = (rng.standard_normal((n, 2)) * 60).astype(np.float32)
+    cls = rng.integers(-1, Cn + 1, n).astype(np.int32)           # includes classes outside [0, C): dropped
+    xy[:3000] = (3.3, -7.1)                                      # 3000 hits in one cell: the uint8 counter wraps to 184
+    cls[:3000] = 2
+    from top_down_renderer_b200.core import Context
+    c = Context(0)
+    got = c.refine_bin(xy, cls, 0.5, 70.0, 61.0, Wd, Hd, Cn)
+    want = orc.refine_bin(xy, cls, 0.5, 70.0, 61.0, Wd, Hd, Cn)
+    assert np.array_equal(got, want) and got.max() >= 184
+    # rebuild: a class is present where its counter is non-zero -> binary layers (col-major rows x cols) -> EDT
+    layers = np.ascontiguousarray((got == 0).astype(np.float32).transpose(0, 2, 1))
+    c.map_set_binary_layers(layers, 1.0)
+    d, m = c.map_get_layers()
+    c.close()
+    d_o, m_o = orc.compute_dists(layers, 1.0)
+    assert np.array_equal(d.view(np.uint32), d_o.view(np.uint32)) and np.array_equal(m, m_o)

@@ -165,6 +165,14 @@ class Context:
         check(self._lib.tdr_scan_render_cart(self._h, C.c_float(res), int(rows), int(cols), _pf(out)))
         return out
 
+    def refine_bin(self, xy, cls, res, cx, cy, width, height, num_classes):
+        xy = np.ascontiguousarray(xy, dtype=np.float32).reshape(-1, 2)
+        cls = np.ascontiguousarray(cls, dtype=np.int32)
+        out = np.empty((num_classes, height, width), dtype=np.uint8)
+        check(self._lib.tdr_refine_bin(self._h, _pf(xy), _pi(cls), C.c_int64(len(cls)), C.c_float(res), C.c_float(cx),
+                                       C.c_float(cy), int(width), int(height), int(num_classes), _pb(out)))
+        return out
+
     def scan_set_polar_images(self, imgs):
         imgs = np.ascontiguousarray(imgs, dtype=np.float32)
         c, n_r, n_theta = imgs.shape

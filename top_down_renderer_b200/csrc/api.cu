@@ -311,6 +311,13 @@ int tdr_scan_render_cart(tdr_ctx* ctx, float res, int rows, int cols, float* img
   return TDR_OK;
 }
 
+int tdr_refine_bin(tdr_ctx* ctx, const float* xy, const int32_t* cls, int64_t n, float res, float center_x, float center_y,
+                   int width, int height, int num_classes, uint8_t* maps_out) {
+  CTX_CHECK(ctx);
+  TDR_REQUIRE(n == 0 || (xy && cls), TDR_EINVAL, "null points");
+  return refine_bin(ctx, xy, cls, n, res, center_x, center_y, width, height, num_classes, maps_out);
+}
+
 int tdr_scan_set_polar_images(tdr_ctx* ctx, const float* imgs, int n_theta, int n_r, int num_classes) {
   CTX_CHECK(ctx);
   TDR_REQUIRE(imgs && n_theta > 0 && n_r > 0 && num_classes >= 1 && num_classes <= TDR_MAX_CLASSES, TDR_EINVAL, "bad images");

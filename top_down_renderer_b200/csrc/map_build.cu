@@ -63,37 +63,56 @@ __global__ void k_geo_seeds(const uint8_t* __restrict__ seed, size_t n, int C, u
   gseed[i] = obstacle ? 2 : 1;
 }
 
-__global__ void k_edt_vertical(const uint8_t* __restrict__ seed, int rows, int cols, int C, int rcap,
-                               uint8_t* __restrict__ g) {
-  int x = blockIdx.x * blockDim.x + threadIdx.x;
-  int y = blockIdx.y * blockDim.y + threadIdx.y;
-  if (x >= cols || y >= rows) return;
-  const uint32_t all = (1u << C) - 1u;
-  uint32_t found = 0;
-  uint32_t gd[7];
+// pass V as two column sweeps per band of EDT_BAND rows (thread = column x band): a counter per class holds the
+// distance to the last seed seen, so the cost does not depend on how rare a class is (a window scan per pixel only
+// stops when EVERY class has been found).  Down sweep writes the partial result, up sweep takes the minimum.
+// The band starts rcap rows early so that its counters are exact where they are used.  segmin[c][y][x/32] = min of
+// the final g over a 32-pixel segment lets pass H skip classes that have no seed anywhere near.
+static const int EDT_BAND = 128;
+__global__ void __launch_bounds__(128) k_edt_vsweep(const uint8_t* __restrict__ seed, int rows, int cols, int C, int rcap,
+                                                    uint8_t* __restrict__ g, uint8_t* __restrict__ segmin, int segs) {
+  const int x = blockIdx.x * blockDim.x + threadIdx.x;
+  const int y_lo = blockIdx.y * EDT_BAND, y_hi = min(rows, y_lo + EDT_BAND) - 1;
+  const bool live = x < cols;
+  const int xc = live ? x : cols - 1;
+  const size_t L = (size_t)rows * cols;
+  uint32_t cnt[7];
 #pragma unroll
-  for (int c = 0; c < 7; c++) gd[c] = 255;
-  for (int d = 0; d <= rcap; d++) {
-    uint32_t bits = 0;
-    if (y - d >= 0) bits |= seed[(size_t)(y - d) * cols + x];
-    if (y + d < rows) bits |= seed[(size_t)(y + d) * cols + x];
-    bits &= all;
-    uint32_t nw = bits & ~found;
+  for (int c = 0; c < 7; c++) cnt[c] = 255;
+  for (int y = max(0, y_lo - rcap); y <= y_hi; y++) {
+    const uint32_t bits = seed[(size_t)y * cols + xc];
 #pragma unroll
-    for (int c = 0; c < 7; c++)
-      if ((nw >> c) & 1u) gd[c] = d;
-    found |= bits;
-    if (found == all) break;
+    for (int c = 0; c < 7; c++) {
+      cnt[c] = ((bits >> c) & 1u) ? 0u : (cnt[c] >= 254u ? 255u : cnt[c] + 1u);
+      if (c < C && y >= y_lo && live) g[(size_t)c * L + (size_t)y * cols + x] = (uint8_t)cnt[c];
+    }
   }
-  size_t L = (size_t)rows * cols;
 #pragma unroll
-  for (int c = 0; c < 7; c++)
-    if (c < C) g[(size_t)c * L + (size_t)y * cols + x] = (uint8_t)gd[c];
+  for (int c = 0; c < 7; c++) cnt[c] = 255;
+  for (int y = min(rows - 1, y_hi + rcap); y >= y_lo; y--) {
+    const uint32_t bits = seed[(size_t)y * cols + xc];
+#pragma unroll
+    for (int c = 0; c < 7; c++) {
+      cnt[c] = ((bits >> c) & 1u) ? 0u : (cnt[c] >= 254u ? 255u : cnt[c] + 1u);
+      if (c < C && y <= y_hi) {                          // warp-uniform
+        uint32_t v = 255u;
+        if (live) {
+          const size_t at = (size_t)c * L + (size_t)y * cols + x;
+          v = min((uint32_t)g[at], cnt[c]);
+          if (v > (uint32_t)rcap) v = 255u;              // beyond the truncation window: "no seed"
+          g[at] = (uint8_t)v;
+        }
+        const uint32_t m = __reduce_min_sync(0xffffffffu, v);
+        if ((threadIdx.x & 31) == 0 && x < cols) segmin[((size_t)c * rows + y) * segs + (x >> 5)] = (uint8_t)m;
+      }
+    }
+  }
 }
 
 // TO_MAP: write MapPixel records (class layers + known).  else: planar col-major float layers.
 template <bool TO_MAP>
-__global__ void k_edt_horizontal(const uint8_t* __restrict__ seed, const uint8_t* __restrict__ g, int rows, int cols,
+__global__ void k_edt_horizontal(const uint8_t* __restrict__ seed, const uint8_t* __restrict__ g,
+                                 const uint8_t* __restrict__ segmin, int segs, int rows, int cols,
                                  int C, int rcap, uint32_t capcode, float resolution, MapPixel* __restrict__ map_px,
                                  float* __restrict__ planar) {
   int x = blockIdx.x * blockDim.x + threadIdx.x;
@@ -101,19 +120,28 @@ __global__ void k_edt_horizontal(const uint8_t* __restrict__ seed, const uint8_t
   if (x >= cols || y >= rows) return;
   const size_t L = (size_t)rows * cols;
   const bool unknown = (seed[(size_t)y * cols + x] & 0x80u) != 0;
+  const int s_lo = max(0, x - rcap) >> 5, s_hi = min(cols - 1, x + rcap) >> 5;
   float out[8];
 #pragma unroll
   for (int c = 0; c < 8; c++) out[c] = 0.f;
 #pragma unroll
   for (int c = 0; c < 7; c++) {
     if (c < C) {
-      const uint8_t* gr = g + (size_t)c * L + (size_t)y * cols;
-      uint32_t g0 = gr[x];
-      uint32_t best = (g0 == 255u) ? 0x3fffffffu : g0 * g0;
-      for (int dx = 1; dx <= rcap && (uint32_t)(dx * dx) < best; dx++) {
-        uint32_t dx2 = (uint32_t)(dx * dx);
-        if (x - dx >= 0) { uint32_t gv = gr[x - dx]; if (gv != 255u) { uint32_t cand = dx2 + gv * gv; best = cand < best ? cand : best; } }
-        if (x + dx < cols) { uint32_t gv = gr[x + dx]; if (gv != 255u) { uint32_t cand = dx2 + gv * gv; best = cand < best ? cand : best; } }
+      uint32_t best = 0x3fffffffu;
+      if (!unknown) {                                     // unknown pixels are zeroed anyway (top_down_map.cpp:317)
+        const uint8_t* sm = segmin + ((size_t)c * rows + y) * segs;
+        uint32_t near = 255u;
+        for (int sgi = s_lo; sgi <= s_hi; sgi++) near = min(near, (uint32_t)sm[sgi]);
+        if (near != 255u) {                               // some seed of this class within reach of the window
+          const uint8_t* gr = g + (size_t)c * L + (size_t)y * cols;
+          uint32_t g0 = gr[x];
+          best = (g0 == 255u) ? 0x3fffffffu : g0 * g0;
+          for (int dx = 1; dx <= rcap && (uint32_t)(dx * dx) < best; dx++) {
+            uint32_t dx2 = (uint32_t)(dx * dx);
+            if (x - dx >= 0) { uint32_t gv = gr[x - dx]; if (gv != 255u) { uint32_t cand = dx2 + gv * gv; best = cand < best ? cand : best; } }
+            if (x + dx < cols) { uint32_t gv = gr[x + dx]; if (gv != 255u) { uint32_t cand = dx2 + gv * gv; best = cand < best ? cand : best; } }
+          }
+        }
       }
       uint32_t d2 = best < capcode ? best : capcode;       // every d2 >= capcode is worth exactly 50
       out[c] = unknown ? 0.f : dist_value(d2, resolution);  // top_down_map.cpp:312-317
@@ -177,14 +205,19 @@ static int run_edt(tdr_ctx* ctx, const uint8_t* seed, int rows, int cols, int C,
   int rcap = (int)ceil(sqrt((double)capcode)) + 1;
   TDR_REQUIRE(rcap <= 254, TDR_EUNSUPPORTED, "resolution %g needs an EDT window of %d px (> 254)", resolution, rcap);
   size_t L = (size_t)rows * cols;
-  if (int e = ctx->edt_g.reserve(L * (size_t)C)) return e;
+  const int segs = (cols + 31) / 32;
+  const size_t seg_bytes = (size_t)C * rows * segs;
+  if (int e = ctx->edt_g.reserve(L * (size_t)C + seg_bytes + 256)) return e;
+  uint8_t* d_g = ctx->edt_g.as<uint8_t>();
+  uint8_t* d_seg = d_g + ((L * (size_t)C + 255) / 256) * 256;
+  dim3 vgrd((cols + 127) / 128, (rows + EDT_BAND - 1) / EDT_BAND);
+  k_edt_vsweep<<<vgrd, 128, 0, ctx->stream>>>(seed, rows, cols, C, rcap, d_g, d_seg, segs);
   dim3 blk(32, 8), grd((cols + 31) / 32, (rows + 7) / 8);
-  k_edt_vertical<<<grd, blk, 0, ctx->stream>>>(seed, rows, cols, C, rcap, ctx->edt_g.as<uint8_t>());
   if (to_map)
-    k_edt_horizontal<true><<<grd, blk, 0, ctx->stream>>>(seed, ctx->edt_g.as<uint8_t>(), rows, cols, C, rcap, capcode,
+    k_edt_horizontal<true><<<grd, blk, 0, ctx->stream>>>(seed, d_g, d_seg, segs, rows, cols, C, rcap, capcode,
                                                          resolution, ctx->map_px.as<MapPixel>(), nullptr);
   else
-    k_edt_horizontal<false><<<grd, blk, 0, ctx->stream>>>(seed, ctx->edt_g.as<uint8_t>(), rows, cols, C, rcap, capcode,
+    k_edt_horizontal<false><<<grd, blk, 0, ctx->stream>>>(seed, d_g, d_seg, segs, rows, cols, C, rcap, capcode,
                                                           resolution, nullptr, planar_out);
   count_launch(ctx, 2);
   TDR_CUDA(cudaGetLastError());

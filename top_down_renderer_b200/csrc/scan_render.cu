@@ -114,6 +114,31 @@ __global__ void k_scan_pack(const float* __restrict__ img, int P, int C, const f
   dst[1] = make_float4(out[4], out[5], out[6], out[7]);
 }
 
+// cfg5 / refine_map-style batch binning (src/refine_map.cpp:76-94): ind = floor(pt/res) + (int)(centre/res), one uint8
+// counter per (class, y, x) that wraps mod 256 like the reference's uint8 "+= 1".  Integer adds commute, so a
+// warp-aggregated int32 histogram followed by "& 255" is bit-exact for any point order.
+__global__ void k_refine_bin(const float2* __restrict__ xy, const int32_t* __restrict__ cls, long long n, float res,
+                             int off_x, int off_y, int width, int height, int C, int32_t* __restrict__ hist) {
+  long long i = (long long)blockIdx.x * blockDim.x + threadIdx.x;
+  const int lane = threadIdx.x & 31;
+  long long key = -1;
+  if (i < n) {
+    const float2 p = xy[i];
+    const int c = cls[i];
+    const double fx = floor((double)p.x / (double)res), fy = floor((double)p.y / (double)res);
+    if (fx > -2e9 && fx < 2e9 && fy > -2e9 && fy < 2e9 && c >= 0 && c < C) {
+      const int ix = (int)fx + off_x, iy = (int)fy + off_y;
+      if (ix >= 0 && ix < width && iy >= 0 && iy < height) key = ((long long)c * height + iy) * width + ix;
+    }
+  }
+  const unsigned peers = __match_any_sync(0xffffffffu, key);
+  if (key >= 0 && lane == (__ffs(peers) - 1)) atomicAdd(hist + key, __popc(peers));
+}
+__global__ void k_hist_to_u8(const int32_t* __restrict__ hist, size_t n, uint8_t* __restrict__ out) {
+  size_t i = (size_t)blockIdx.x * blockDim.x + threadIdx.x;
+  if (i < n) out[i] = (uint8_t)(hist[i] & 255);
+}
+
 static const int kSmemBudget = 200 * 1024;
 
 int scan_render(tdr_ctx* ctx, bool polar, float res, float ang_res, int d0, int d1, float* dev_img_out) {
@@ -168,6 +193,31 @@ int scan_render(tdr_ctx* ctx, bool polar, float res, float ang_res, int d0, int 
   k_hist_to_float<<<(bins + 255) / 256, 256, 0, ctx->stream>>>(ctx->hist.as<int32_t>(), bins, dev_img_out);
   count_launch(ctx);
   TDR_CUDA(cudaGetLastError());
+  return TDR_OK;
+}
+
+int refine_bin(tdr_ctx* ctx, const float* xy, const int32_t* cls, long long n, float res, float cx, float cy, int width,
+               int height, int C, uint8_t* maps_out) {
+  TDR_REQUIRE(n >= 0 && res > 0.f && width > 0 && height > 0 && C >= 1 && maps_out, TDR_EINVAL, "bad refine_bin arguments");
+  const size_t cells = (size_t)C * width * height;
+  if (int e = ctx->hist.reserve(cells * 4)) return e;
+  if (int e = ctx->scratch.reserve((size_t)(n > 0 ? n : 1) * 12)) return e;
+  if (int e = ctx->scratch2.reserve(cells)) return e;
+  float2* d_xy = ctx->scratch.as<float2>();
+  int32_t* d_cls = reinterpret_cast<int32_t*>(ctx->scratch.as<unsigned char>() + (size_t)n * 8);
+  TDR_CUDA(cudaMemsetAsync(ctx->hist.p, 0, cells * 4, ctx->stream));
+  if (n > 0) {
+    TDR_CUDA(cudaMemcpyAsync(d_xy, xy, (size_t)n * 8, cudaMemcpyHostToDevice, ctx->stream));
+    TDR_CUDA(cudaMemcpyAsync(d_cls, cls, (size_t)n * 4, cudaMemcpyHostToDevice, ctx->stream));
+    k_refine_bin<<<(unsigned)((n + 255) / 256), 256, 0, ctx->stream>>>(d_xy, d_cls, n, res, (int)(cx / res), (int)(cy / res), width,
+                                                                      height, C, ctx->hist.as<int32_t>());
+    count_launch(ctx);
+  }
+  k_hist_to_u8<<<(unsigned)((cells + 255) / 256), 256, 0, ctx->stream>>>(ctx->hist.as<int32_t>(), cells, ctx->scratch2.as<uint8_t>());
+  count_launch(ctx);
+  TDR_CUDA(cudaGetLastError());
+  TDR_CUDA(cudaMemcpyAsync(maps_out, ctx->scratch2.p, cells, cudaMemcpyDeviceToHost, ctx->stream));
+  TDR_CUDA(cudaStreamSynchronize(ctx->stream));
   return TDR_OK;
 }
 

@@ -197,6 +197,8 @@ int map_get_geo_layers(tdr_ctx*, float*);
 // scan_render.cu
 int scan_render(tdr_ctx*, bool polar, float res, float ang_res, int d0, int d1, float* dev_img_out);
 int scan_pack(tdr_ctx*);
+int refine_bin(tdr_ctx*, const float* xy, const int32_t* cls, long long n, float res, float cx, float cy, int width,
+               int height, int C, uint8_t* maps_out);
 // score.cu
 int score_particles(tdr_ctx*, float res);
 int score_grid(tdr_ctx*, long long n, float scale, float res);
