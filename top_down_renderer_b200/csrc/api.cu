@@ -128,6 +128,7 @@ int tdr_create(tdr_ctx** out, int device) {
   if (const char* e = getenv("TDR_MMA_TILES")) { int v = atoi(e); if (v == 1 || v == 2 || v == 4) c->mma_tiles = v; }
   if (const char* e = getenv("TDR_MMA_SPLIT")) { int v = atoi(e); if (v == 1 || v == 2 || v == 4) c->mma_split = v; }
   if (const char* e = getenv("TDR_MMA_SEG_SHIFT")) { int v = atoi(e); if (v >= 0 && v <= 5) c->mma_seg_shift = v; }
+  if (const char* e = getenv("TDR_MMA_A_TMEM")) c->mma_a_tmem = atoi(e) ? 1 : 0;
   if (const char* e = getenv("TDR_MMA_RING_CFG")) c->mma_ring_cfg = atoi(e);
   if (const char* e = getenv("TDR_MMA_KERNEL")) c->mma_kernel = atoi(e);
   if (const char* e = getenv("TDR_MMA_CTAS")) c->mma_ctas = atoi(e);

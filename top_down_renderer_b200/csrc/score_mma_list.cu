@@ -73,22 +73,28 @@ struct ListParams {
 // T = 128-hypothesis tiles per CTA; R = gather threads per hypothesis row (the R threads of a row take turns
 // stage by stage, so the loads in flight per SM double without doubling the hypotheses — and their map
 // footprint — that are in flight together)
-template <int N, int T, int R> struct ListCfg {
+// ATM = the gathered records go to TENSOR MEMORY instead of shared memory (tcgen05.st, 8 columns = 16 fp16 per row
+// and cell) and the MMA takes its A operand from there: the copy into the operand no longer costs L1 data-pipe
+// wavefronts (a quarter of the pipe that bounds this kernel), TMEM writes run at 256 B/clk beside it.
+template <int N, int T, int R, bool ATM> struct ListCfg {
   static const int kThreads = 128 * T * R + 64;
-  static const int kTmemCols = T * N <= 128 ? 128 : (T * N <= 256 ? 256 : 512);
+  static const int kTmemCols = ATM ? 512 : (T * N <= 128 ? 128 : (T * N <= 256 ? 256 : 512));
   static const int kByTmem = 512 / kTmemCols, kByRegs = 65536 / (kThreads * 88) < 1 ? 1 : 65536 / (kThreads * 88);
   static const int kCtasPerSm = kByTmem < kByRegs ? kByTmem : kByRegs;
-  static const int kABytes = MMA_G * T * A_TILE;          // per stage
+  static const int kABytes = ATM ? 0 : MMA_G * T * A_TILE;   // per stage
   static const int kBBytes = MMA_G * N * 32;              // per stage
   static const int kStageBytes = kABytes + kBBytes;
-  static const int kBudget = (216 * 1024) / kCtasPerSm - 1280;
-  static const int kStages = kBudget / kStageBytes > 8 ? 8 : kBudget / kStageBytes;
-  static const int kSmem = kStages * kStageBytes + 256;
+  static const int kBudget = (216 * 1024) / kCtasPerSm - 1536;
+  static const int kACols = MMA_G * T * 8;                // TMEM columns of one stage of A (ATM)
+  static const int kStagesTm = (512 - T * N) / kACols > 16 ? 16 : (512 - T * N) / kACols;
+  static const int kStagesSm = kBudget / kStageBytes > 8 ? 8 : kBudget / kStageBytes;
+  static const int kStages = ATM ? kStagesTm : kStagesSm;
+  static const int kSmem = kStages * kStageBytes + 512;     // + barriers (2 * kStages + 1) and the TMEM base word
 };
 
-template <int N, int T, int R>
-__global__ void __launch_bounds__(128 * T * R + 64, ListCfg<N, T, R>::kCtasPerSm) k_score_mma_list(ListParams sp) {
-  using Cfg = ListCfg<N, T, R>;
+template <int N, int T, int R, bool ATM>
+__global__ void __launch_bounds__(128 * T * R + 64, ListCfg<N, T, R, ATM>::kCtasPerSm) k_score_mma_list(ListParams sp) {
+  using Cfg = ListCfg<N, T, R, ATM>;
   constexpr int GW = 4 * T * R;        // gather warps
   constexpr int NS = Cfg::kStages;
   constexpr int S_PAD = N / 2;
@@ -160,13 +166,23 @@ __global__ void __launch_bounds__(128 * T * R + 64, ListCfg<N, T, R>::kCtasPerSm
       auto store_stage = [&](uint32_t iter, const uint4 (&rec)[MMA_G][2]) {
         const uint32_t st = iter % NS, ph = (iter / NS) & 1u;
         mbar_wait(bar_empty + 8 * st, ph ^ 1u);
-        unsigned char* base = sA + (size_t)st * Cfg::kABytes + (size_t)t * A_TILE + (size_t)m * 16;
+        if (ATM) {
+          // row m of the A tile = TMEM lane m (this warp's quarter), 8 columns = the record's 16 fp16 in K order
+          const uint32_t tcol = tmem_base + ((uint32_t)((warp & 3) * 32) << 16) + (uint32_t)(T * N) +
+                                (uint32_t)(st * Cfg::kACols + t * 8);
 #pragma unroll
-        for (int g = 0; g < MMA_G; g++) {
-          *reinterpret_cast<uint4*>(base + (size_t)g * T * A_TILE) = rec[g][0];            // K chunk 0: hi halves
-          *reinterpret_cast<uint4*>(base + (size_t)g * T * A_TILE + A_LBO) = rec[g][1];    // K chunk 1: lo halves
+          for (int g = 0; g < MMA_G; g++) tmem_st8(tcol + (uint32_t)(g * T * 8), rec[g][0], rec[g][1]);
+          tmem_wait_st();
+          tc_fence_before();
+        } else {
+          unsigned char* base = sA + (size_t)st * Cfg::kABytes + (size_t)t * A_TILE + (size_t)m * 16;
+#pragma unroll
+          for (int g = 0; g < MMA_G; g++) {
+            *reinterpret_cast<uint4*>(base + (size_t)g * T * A_TILE) = rec[g][0];            // K chunk 0: hi halves
+            *reinterpret_cast<uint4*>(base + (size_t)g * T * A_TILE + A_LBO) = rec[g][1];    // K chunk 1: lo halves
+          }
+          fence_proxy_async();
         }
-        fence_proxy_async();
         __syncwarp();
         if (lane == 0) mbar_arrive(bar_full + 8 * st);
       };
@@ -249,8 +265,13 @@ __global__ void __launch_bounds__(128 * T * R + 64, ListCfg<N, T, R>::kCtasPerSm
             const uint64_t bdesc = umma_desc(b0 + g * (N * 32), N * 16, 128);
 #pragma unroll
             for (int tt = 0; tt < T; tt++) {
-              const uint64_t adesc = umma_desc(a0 + (g * T + tt) * A_TILE, A_LBO, 128);
-              umma_f16(tmem_base + (uint32_t)(tt * N), adesc, bdesc, idesc, (k > 0 || g > 0) ? 1u : 0u);
+              if (ATM) {
+                umma_f16_ts(tmem_base + (uint32_t)(tt * N), tmem_base + (uint32_t)(T * N + st * Cfg::kACols + (g * T + tt) * 8),
+                            bdesc, idesc, (k > 0 || g > 0) ? 1u : 0u);
+              } else {
+                const uint64_t adesc = umma_desc(a0 + (g * T + tt) * A_TILE, A_LBO, 128);
+                umma_f16(tmem_base + (uint32_t)(tt * N), adesc, bdesc, idesc, (k > 0 || g > 0) ? 1u : 0u);
+              }
             }
           }
           umma_commit(bar_empty + 8 * st);        // implies tcgen05.fence::before_thread_sync
@@ -330,31 +351,32 @@ int score_mma_list(tdr_ctx* ctx, float res, bool grid_mode, long long n_items, f
     sp.regularization = ctx->fp.regularization;
     sp.thetas = ctx->d_search_thetas.as<float>();
   }
-#define TDR_LAUNCH_LIST(NN, TT, RR)                                                                                   \
+#define TDR_LAUNCH_LIST(NN, TT, RR, AA)                                                                               \
   do {                                                                                                                \
-    using Cfg = ListCfg<NN, TT, RR>;                                                                                   \
+    using Cfg = ListCfg<NN, TT, RR, AA>;                                                                               \
     static bool attr = false;                                                                                         \
-    if (!attr) { TDR_CUDA(cudaFuncSetAttribute(k_score_mma_list<NN, TT, RR>, cudaFuncAttributeMaxDynamicSharedMemorySize, Cfg::kSmem)); attr = true; } \
+    if (!attr) { TDR_CUDA(cudaFuncSetAttribute(k_score_mma_list<NN, TT, RR, AA>, cudaFuncAttributeMaxDynamicSharedMemorySize, Cfg::kSmem)); attr = true; } \
     const long long nb = (sp.n_work + 128 * TT - 1) / (128 * TT);                                                     \
     const long long cap = (long long)ctx->sm_count * (ctx->mma_ctas > 0 && ctx->mma_ctas < Cfg::kCtasPerSm ? ctx->mma_ctas : Cfg::kCtasPerSm); \
     const int grid = (int)(nb < cap ? nb : cap);                                                                      \
-    k_score_mma_list<NN, TT, RR><<<grid, Cfg::kThreads, Cfg::kSmem, ctx->stream>>>(sp);                                    \
+    k_score_mma_list<NN, TT, RR, AA><<<grid, Cfg::kThreads, Cfg::kSmem, ctx->stream>>>(sp);                              \
   } while (0)
   const int cfg = ctx->mma_tiles * 10 + ctx->mma_split;
-  if (S_pad == 48) {
+  if (ctx->mma_a_tmem) {
     switch (cfg) {
-      case 41: TDR_LAUNCH_LIST(96, 4, 1); break;
-      case 21: TDR_LAUNCH_LIST(96, 2, 1); break;
-      case 22: TDR_LAUNCH_LIST(96, 2, 2); break;
-      case 11: TDR_LAUNCH_LIST(96, 1, 1); break;
-      case 14: TDR_LAUNCH_LIST(96, 1, 4); break;
-      default: TDR_LAUNCH_LIST(96, 1, 2); break;
+      case 21: TDR_LAUNCH_LIST(96, 2, 1, true); break;
+      case 12: TDR_LAUNCH_LIST(96, 1, 2, true); break;
+      case 14: TDR_LAUNCH_LIST(96, 1, 4, true); break;
+      default: TDR_LAUNCH_LIST(96, 2, 2, true); break;     // 9.5 ms per 1e6 x 40 (T = 1, R = 4: 12.1; T = 2, R = 1: 15.6)
     }
   } else {
     switch (cfg) {
-      case 21: case 41: TDR_LAUNCH_LIST(224, 2, 1); break;
-      case 11: TDR_LAUNCH_LIST(224, 1, 1); break;
-      default: TDR_LAUNCH_LIST(224, 1, 2); break;
+      case 41: TDR_LAUNCH_LIST(96, 4, 1, false); break;
+      case 21: TDR_LAUNCH_LIST(96, 2, 1, false); break;
+      case 22: TDR_LAUNCH_LIST(96, 2, 2, false); break;
+      case 11: TDR_LAUNCH_LIST(96, 1, 1, false); break;
+      case 14: TDR_LAUNCH_LIST(96, 1, 4, false); break;
+      default: TDR_LAUNCH_LIST(96, 1, 2, false); break;
     }
   }
 #undef TDR_LAUNCH_LIST

@@ -99,10 +99,11 @@ struct tdr_ctx {
   tdr::DevBuf scan_op;       // P_pad x N x 32 B
   tdr::DevBuf bin_counts, perm;
   int score_impl = 0;        // 0 auto, 1 CUDA cores only, 2 tensor cores whenever usable
-  int mma_tiles = 1;         // 128-hypothesis tiles per CTA (tuning: TDR_MMA_TILES); 1 tile x 4 threads/row keeps the
-                             // in-flight footprint L2-resident (96 % L2 hits) at the speed of 2 tiles x 2 CTAs/SM
+  int mma_tiles = 2;         // list kernel: 128-hypothesis tiles per CTA (tuning: TDR_MMA_TILES); two tiles share one
+                             // streamed scan operand, 512 gather threads keep ~2000 records in flight per SM
   int mma_seg_shift = 2;     // log2 of the column-segment width of a bin (tuning: TDR_MMA_SEG_SHIFT)
-  int mma_split = 4;         // gather threads per hypothesis row (tuning: TDR_MMA_SPLIT)
+  int mma_split = 2;         // gather threads per hypothesis row (tuning: TDR_MMA_SPLIT)
+  int mma_a_tmem = 1;        // list kernel: gathered records to tensor memory instead of shared (tuning: TDR_MMA_A_TMEM)
   int mma_ring_cfg = 12;     // ring kernel: tiles * 10 + threads per row (tuning: TDR_MMA_RING_CFG)
   int mma_kernel = 0;        // 0 auto, 1 streamed-operand kernel only, 2 ring kernel only (tuning: TDR_MMA_KERNEL)
   int mma_ctas = 0;          // cap on co-resident CTAs per SM (0 = as many as TMEM allows; tuning: TDR_MMA_CTAS)
