@@ -4,6 +4,7 @@ Bars (BASELINE.json north_star): class images, distance fields, resampled indice
 weights within 1e-5 relative; pose within 1 mm / 0.01 deg.
 """
 import math
+import os
 
 import numpy as np
 import pytest
@@ -517,6 +518,28 @@ def test_mma_grid_costs_100_shifts(world, mma_ctx):
     want = orc.cost_grid(centers, 2.0, world.fp, world.layers, world.mask, 1.0, world.tab, N_THETA, N_R, world.scan, 4.0, shifts)
     e = rel_err(got, want)
     assert np.isfinite(e).all() and e.max() <= WEIGHT_RTOL, e.max()
+
+
+@pytest.mark.parametrize("stride,n_shifts", [(2, 100), (4, 100), (8, 100), (4, 40)])
+def test_mma_lattice_grid_uses_phase_split_map(world, mma_ctx, stride, n_shifts):
+    """a lattice of centres with an x stride of 2 / 4 / 8 px gathers from the phase-split map copy (every map row stored
+    as `stride` phase rows): same costs as the oracle, and bit-identical to the plain layout (the layout is only an
+    address permutation)."""
+    centers = synth.grid_centers(world.h, world.w, stride)
+    per_row = len(np.arange(stride // 2, world.w, stride))
+    centers = np.ascontiguousarray(centers[per_row * 7: per_row * 7 + 1500])       # rows well inside, and the wrap to the next row
+    shifts = np.arange(n_shifts, dtype=np.int32)
+    mma_ctx.scan_set_polar_images(world.scan)
+    got = mma_ctx.grid_costs(centers, 2.0, 4.0, shifts)
+    want = orc.cost_grid(centers, 2.0, world.fp, world.layers, world.mask, 1.0, world.tab, N_THETA, N_R, world.scan, 4.0, shifts)
+    e = rel_err(got, want)
+    assert np.isfinite(e).all() and e.max() <= WEIGHT_RTOL, e.max()
+    os.environ["TDR_GRID_PHASE_LOG2"] = "0"
+    try:
+        plain = mma_ctx.grid_costs(centers, 2.0, 4.0, shifts)
+    finally:
+        del os.environ["TDR_GRID_PHASE_LOG2"]
+    assert np.array_equal(got.view(np.uint32), plain.view(np.uint32))
 
 
 def test_mma_matches_cuda_core_path(world):

@@ -1,7 +1,7 @@
 // gather_bench.cu — micro-benchmark: how fast can one SM pull scattered 32-byte records (one L2 sector each)?
 // Variants: per-thread 2xLDG.128, lane pairs (l,l+16) / (2j,2j+1), 256-bit loads, cp.async (LDGSTS) 16 B x2,
 // cp.async.bulk 32 B.  Patterns: random over 512 MB (DRAM), random over 32 MB (L2), neighbours (4 per line),
-// near (distinct lines, same 4 KB).  Prints records / clk / SM.   nvcc -gencode arch=compute_100a,code=sm_100a
+// near (distinct lines, same 4 KB); 4-7: L2-resident window with 32 / 32 / 16 / 8 lines per warp load.  Prints records / clk / SM.   nvcc -gencode arch=compute_100a,code=sm_100a
 #include <cstdio>
 #include <cstdint>
 #include <cuda_runtime.h>
@@ -17,7 +17,11 @@ __device__ __forceinline__ uint32_t rec_index(int pattern, uint32_t gid, uint32_
     case 0: return hash32(gid * 9781u + it * 6271u) % n_rec;                          // random, whole array
     case 1: return hash32(gid * 9781u + it * 6271u) % (1u << 20);                     // random, 32 MB window
     case 2: return (hash32(warp * 131u + it * 7919u) % (n_rec - 64)) + lane;          // 32 consecutive records (8 lines)
-    default: return (hash32(warp * 131u + it * 7919u) % (n_rec - 4096)) + lane * 5;   // distinct lines, close by
+    case 3: return (hash32(warp * 131u + it * 7919u) % (n_rec - 4096)) + lane * 5;    // distinct lines, close by
+    case 4: return (hash32(warp * 131u + it * 7919u) % ((1u << 20) - 256)) + lane * 4;   // L2 window, 32 consecutive lines, 1 sector each (grid rows)
+    case 5: return (hash32(warp * 131u + it * 7919u) % ((1u << 20) - 256)) + lane * 4 + (hash32(gid + it) & 3u);   // same, random sector in the line
+    case 6: return (hash32(warp * 131u + it * 7919u) % ((1u << 20) - 256)) + lane * 2;   // L2 window, 16 lines x 2 sectors
+    default: return (hash32(warp * 131u + it * 7919u) % ((1u << 20) - 256)) + lane;      // L2 window, 8 full lines
   }
 }
 
@@ -112,7 +116,7 @@ static int run(const char* name, const uint4* d, uint32_t n_rec, uint32_t* sink,
   const int iters = 2048, threads = 512;
   size_t smem = (V >= 4) ? 4 * 512 * 32 : 0;
   CK(cudaFuncSetAttribute(k_gather<V>, cudaFuncAttributeMaxDynamicSharedMemorySize, 100 * 1024));
-  for (int pattern = 0; pattern < 4; pattern++) {
+  for (int pattern = (V == 3 ? 0 : 8); pattern < 8; pattern++) {
     for (int ctas_per_sm = 1; ctas_per_sm <= 2; ctas_per_sm++) {
       cudaEvent_t e0, e1;
       cudaEventCreate(&e0); cudaEventCreate(&e1);

@@ -148,7 +148,7 @@ void tdr_destroy(tdr_ctx* c) {
   tdr::DevBuf* bufs[] = {&c->map_px, &c->seedbits, &c->edt_g, &c->scratch, &c->scratch2, &c->tab, &c->pts, &c->lut,
                          &c->scan_img, &c->scan_pack, &c->hist, &c->d_search_thetas, &c->d_search_shifts, &c->weights,
                          &c->prefix, &c->idx, &c->scal, &c->pose_tmp, &c->grid_centers, &c->grid_costs,
-                         &c->grid_shifts, &c->d_cw, &c->map16, &c->seq_ws, &c->scan_op, &c->bin_counts, &c->perm};
+                         &c->grid_shifts, &c->d_cw, &c->map16, &c->map16g, &c->seq_ws, &c->scan_op, &c->bin_counts, &c->perm};
   for (auto* b : bufs) b->release();
   for (void* p : c->grid_opened) cudaIpcCloseMemHandle(p);
   c->grid_full.release();
@@ -337,7 +337,7 @@ int tdr_pf_set_params(tdr_ctx* ctx, const tdr_filter_params* p) {
   ctx->fp = *p;
   TDR_CUDA(cudaMemcpyAsync(ctx->d_cw.p, ctx->fp.class_weights, 64, cudaMemcpyHostToDevice, ctx->stream));
   TDR_CUDA(cudaStreamSynchronize(ctx->stream));
-  ctx->have_params = true; ctx->map16_valid = false;   // class weights are folded into the fp16 map copy
+  ctx->have_params = true; ctx->map16_valid = false; ctx->map16g_log2 = -1;   // class weights are folded into the fp16 map copy
   return TDR_OK;
 }
 
@@ -622,6 +622,18 @@ int tdr_grid_costs(tdr_ctx* ctx, const float* centers_xy, int64_t n, float scale
   if (centers_xy) {
     if (int e = ctx->grid_centers.reserve((size_t)n * 8)) return e;
     TDR_CUDA(cudaMemcpyAsync(ctx->grid_centers.p, centers_xy, (size_t)n * 8, cudaMemcpyHostToDevice, ctx->stream));
+    // a lattice with an x stride of 2, 4 or 8 px gathers from the phase-split map copy (a layout hint only: any
+    // value gives the same results); judged on the first pairs of centres
+    int votes[4] = {0, 0, 0, 0};
+    const int64_t probe = n - 1 < 256 ? n - 1 : 256;
+    for (int64_t i = 0; i < probe; i++) {
+      const float d = (centers_xy[2 * i + 2] - centers_xy[2 * i]) / ctx->resolution;
+      if (centers_xy[2 * i + 3] != centers_xy[2 * i + 1]) continue;
+      for (int k = 1; k <= 3; k++) if (d == (float)(1 << k)) votes[k]++;
+    }
+    ctx->grid_phase_log2 = 0;
+    for (int k = 1; k <= 3; k++) if (votes[k] * 2 > probe) ctx->grid_phase_log2 = k;
+    if (const char* e = getenv("TDR_GRID_PHASE_LOG2")) { int v = atoi(e); if (v >= 0 && v <= 3) ctx->grid_phase_log2 = v; }
   }
   if (ctx->grid_n_peers) { /* costs go straight into the peer-mapped full arrays */ }
   else if (!ctx->grid_costs_ext) { if (int e = ctx->grid_costs.reserve((size_t)n * n_shifts * 4)) return e; }

@@ -36,6 +36,15 @@ __device__ __forceinline__ void mbar_wait(uint32_t bar, uint32_t parity) {
       "}" ::"r"(bar), "r"(parity)
       : "memory");
 }
+// one lane of a CONVERGED warp (the lowest active one, the same every time).  The single-thread tcgen05 / bulk-copy
+// instructions are issued under this predicate from warp-uniform control flow: their operands then live in uniform
+// registers.  Issuing them from inside `if (lane == 0) { loop }` makes ptxas wrap every one in an elect / branch
+// waterfall, ~150 slow instructions per pipeline stage — it bounded both tensor-core kernels (ncu source view).
+__device__ __forceinline__ bool elect_one() {
+  uint32_t p;
+  asm volatile("{\n\t.reg .pred P;\n\telect.sync _|P, 0xffffffff;\n\tselp.u32 %0, 1, 0, P;\n\t}" : "=r"(p));
+  return p != 0;
+}
 __device__ __forceinline__ void fence_barrier_init() { asm volatile("fence.mbarrier_init.release.cluster;" ::: "memory"); }
 // generic-proxy shared-memory writes -> visible to the async proxy (the tensor core reads operands through it)
 __device__ __forceinline__ void fence_proxy_async() { asm volatile("fence.proxy.async.shared::cta;" ::: "memory"); }
@@ -78,6 +87,12 @@ __device__ __forceinline__ void tmem_st8(uint32_t taddr, const uint4& a, const u
                "r"(a.z), "r"(a.w), "r"(b.x), "r"(b.y), "r"(b.z), "r"(b.w)
                : "memory");
 }
+__device__ __forceinline__ void tmem_st1(uint32_t taddr, uint32_t v) {
+  asm volatile("tcgen05.st.sync.aligned.32x32b.x1.b32 [%0], {%1};" ::"r"(taddr), "r"(v) : "memory");
+}
+__device__ __forceinline__ void tmem_st2(uint32_t taddr, uint32_t v0, uint32_t v1) {
+  asm volatile("tcgen05.st.sync.aligned.32x32b.x2.b32 [%0], {%1, %2};" ::"r"(taddr), "r"(v0), "r"(v1) : "memory");
+}
 __device__ __forceinline__ void tmem_wait_st() { asm volatile("tcgen05.wait::st.sync.aligned;" ::: "memory"); }
 __device__ __forceinline__ void umma_commit(uint32_t bar) {
   asm volatile("tcgen05.commit.cta_group::1.mbarrier::arrive::one.shared::cluster.b64 [%0];" ::"r"(bar) : "memory");
@@ -112,10 +127,16 @@ __device__ __forceinline__ uint64_t umma_desc(uint32_t saddr, uint32_t lbo_bytes
 // operand builders
 // ------------------------------------------------------------------------------------------------
 // MapPixel (8 fp32) -> 16 fp16: hi[0..7] | lo[0..7];  value_c = w_c * dist_c, slot 7 = known (hi only)
+// byte offset of pixel (r, c) in the fp16 map copy; ph_log2 > 0: row r is stored as 2^ph_log2 phase rows of ph_cols records
+__device__ __forceinline__ size_t map16_offset(int r, int c, int cols, int ph_log2, int ph_cols) {
+  if (ph_log2 == 0) return ((size_t)r * cols + c) * 32;
+  return ((((size_t)r << ph_log2) + (size_t)(c & ((1 << ph_log2) - 1))) * ph_cols + (size_t)(c >> ph_log2)) * 32;
+}
 static __global__ void k_build_map16(const MapPixel* __restrict__ map, size_t n, int C, const float* __restrict__ cw,
-                              uint4* __restrict__ out) {
+                              uint4* __restrict__ out, int cols, int ph_log2, int ph_cols) {
   size_t i = (size_t)blockIdx.x * blockDim.x + threadIdx.x;
   if (i >= n) return;
+  const size_t o = map16_offset((int)(i / cols), (int)(i % cols), cols, ph_log2, ph_cols) / 16;
   const float4* src = reinterpret_cast<const float4*>(map + i);
   float4 a = src[0], b = src[1];
   float v[8] = {a.x, a.y, a.z, a.w, b.x, b.y, b.z, b.w};
@@ -137,7 +158,7 @@ static __global__ void k_build_map16(const MapPixel* __restrict__ map, size_t n,
   l.y = (uint32_t)__half_as_ushort(lo[2]) | ((uint32_t)__half_as_ushort(lo[3]) << 16);
   l.z = (uint32_t)__half_as_ushort(lo[4]) | ((uint32_t)__half_as_ushort(lo[5]) << 16);
   l.w = (uint32_t)__half_as_ushort(lo[6]) | ((uint32_t)__half_as_ushort(lo[7]) << 16);
-  out[2 * i] = h; out[2 * i + 1] = l;
+  out[o] = h; out[o + 1] = l;
 }
 
 // ------------------------------------------------------------------------------------------------
@@ -244,15 +265,24 @@ static const int MMA_G = 2;        // lattice cells per pipeline stage
 static const int A_LBO = 2048 + 64;
 static const int A_TILE = 4224;
 
-static int build_map16(tdr_ctx* ctx) {
-  if (ctx->map16_valid) return TDR_OK;
+// ph_log2 = 0: the plain row-major copy (particles); > 0: the phase-split copy for a lattice of centres
+static int build_map16(tdr_ctx* ctx, int ph_log2, const uint4** out, int* ph_cols) {
   const size_t L = (size_t)ctx->rows * ctx->cols;
-  if (int e = ctx->map16.reserve(L * 32)) return e;
-  k_build_map16<<<(unsigned)((L + 255) / 256), 256, 0, ctx->stream>>>(ctx->map_px.as<MapPixel>(), L, ctx->C,
-                                                                       ctx->d_cw.as<float>(), ctx->map16.as<uint4>());
-  count_launch(ctx);
-  TDR_CUDA(cudaGetLastError());
-  ctx->map16_valid = true;
+  *ph_cols = (ctx->cols + (1 << ph_log2) - 1) >> ph_log2;
+  tdr::DevBuf& buf = ph_log2 ? ctx->map16g : ctx->map16;
+  *out = nullptr;
+  const bool valid = ph_log2 ? ctx->map16g_log2 == ph_log2 : ctx->map16_valid;
+  if (!valid) {
+    const size_t bytes = ph_log2 ? ((size_t)ctx->rows << ph_log2) * (size_t)*ph_cols * 32 : L * 32;
+    if (int e = buf.reserve(bytes)) return e;
+    if (ph_log2) TDR_CUDA(cudaMemsetAsync(buf.p, 0, bytes, ctx->stream));     // padding records past the last column
+    k_build_map16<<<(unsigned)((L + 255) / 256), 256, 0, ctx->stream>>>(ctx->map_px.as<MapPixel>(), L, ctx->C, ctx->d_cw.as<float>(),
+                                                                         buf.as<uint4>(), ctx->cols, ph_log2, *ph_cols);
+    count_launch(ctx);
+    TDR_CUDA(cudaGetLastError());
+    if (ph_log2) ctx->map16g_log2 = ph_log2; else ctx->map16_valid = true;
+  }
+  *out = buf.as<uint4>();
   return TDR_OK;
 }
 

@@ -92,7 +92,7 @@ static __global__ void k_build_norm_op(const float* __restrict__ img, int C, int
 // the gather-GEMM
 // ------------------------------------------------------------------------------------------------
 struct MmaParams {
-  const uint4* map16; int rows, cols; float resolution;
+  const uint4* map16; int rows, cols; float resolution; int ph_log2, ph_cols;
   int n_theta, n_r, P; float res;
   const uint4* rings; const uint4* norm_op; int n_groups;
   const int* perm; long long n_work;
@@ -104,6 +104,7 @@ struct MmaParams {
   const float* centers; float grid_scale; float* costs;
   // fused all-gather: every cost is stored into all ranks' full arrays (NVLink peer mappings) at this rank's rows
   float* cost_peers[TDR_MAX_PEERS]; int n_cost_peers; long long cost_row0;
+  int dbg_nostore;
   int identity_shifts;      // shifts[k] == k for all k and n_shifts % 4 == 0: vector stores of the cost rows
 };
 
@@ -111,27 +112,40 @@ static const int MAX_RING_ROWS = 2 * RING_N;                  // n_theta <= RING
 static const int RING_SLOT_BYTES = 2 * MAX_RING_ROWS * 16;    // 2 K chunks
 static const int NB2 = 4, B2_BYTES = 2 * RING_N * 16;         // tot-block slots (one block per 16 cells)
 static const int NA2 = 3, A2_TILE = 4096;                     // known-flag operand buffers (128 rows x 16 cells)
-static const int CELLS_PER_GROUP = 16, STAGES_PER_GROUP = CELLS_PER_GROUP / MMA_G;
+static const int CELLS_PER_GROUP = 16;
 // T = 128-hypothesis tiles per CTA; R = gather threads per hypothesis row (the R threads of a row take turns
 // stage by stage, so the loads in flight per SM grow without growing the set of hypotheses — and their map
 // footprint — that are in flight together)
-template <int T, int R> struct MmaCfg {
+// ATM (T = 1 only) = the gathered records and the known-flag operand live in TENSOR MEMORY (tcgen05.st; the MMA takes A
+// from there): no operand stores through the L1 data pipe and no operand reads by the tensor core out of shared
+// memory.  TMEM columns: [0, 224) accumulators | [224, 248) NA2 flag groups | [248, 504) 16 stages x 2 cells x 8.
+// G = lattice cells per pipeline stage (2, or 4 on the tensor-memory path): the per-stage handshake of the single
+// MMA-issuing warp (~90 instructions) is what bounds this kernel once the operands are off the L1 pipe, so a stage
+// carries as many cells as the registers of the gather threads allow.
+template <int T, int R, bool ATM, int G> struct MmaCfg {
   static const int kThreads = 128 * T * R + 64;
-  static const int kTmemCols = T * 2 * RING_N <= 256 ? 256 : 512;
-  static const int kByTmem = 512 / kTmemCols, kByRegs = 65536 / (kThreads * 96) < 1 ? 1 : 65536 / (kThreads * 96);
+  static const int kTmemCols = ATM ? 512 : (T * 2 * RING_N <= 256 ? 256 : 512);
+  static const int kRegs = G == 2 ? 96 : 144;
+  static const int kByTmem = 512 / kTmemCols, kByRegs = 65536 / (kThreads * kRegs) < 1 ? 1 : 65536 / (kThreads * kRegs);
   static const int kCtasPerSm = kByTmem < kByRegs ? kByTmem : kByRegs;
-  static const int kStageBytes = MMA_G * T * A_TILE;
-  static const int kFixed = 2 * RING_SLOT_BYTES + NB2 * B2_BYTES + NA2 * T * A2_TILE + 128 * T * R * 4 + 1024 + 4 * T * 32 * 17 * 4;
+  static const int kStageBytes = ATM ? 0 : G * T * A_TILE;
+  static const int kA2Bytes = ATM ? 0 : NA2 * T * A2_TILE;
+  static const int kFixed = 2 * RING_SLOT_BYTES + NB2 * B2_BYTES + kA2Bytes + 128 * T * R * 4 + 1024 + 4 * T * 32 * 17 * 4;
   static const int kBudget = (216 * 1024) / kCtasPerSm - 1280 - kFixed;
   // every gather thread keeps two of ITS stages in flight, i.e. spans 2R stages: leave twice that as slack
   static const int kStagesMax = 4 * R < 8 ? 8 : 4 * R;
-  static const int kStages = kBudget / kStageBytes > kStagesMax ? kStagesMax : kBudget / kStageBytes;
+  static const int kA2Col = T * 2 * RING_N, kACol = kA2Col + NA2 * T * 8, kACols = G * T * 8;   // ATM column map
+  static const int kStagesSm = kBudget / (ATM ? 1 : kStageBytes) > kStagesMax ? kStagesMax : kBudget / (ATM ? 1 : kStageBytes);
+  static const int kStages = ATM ? ((512 - kACol) / kACols > 16 ? 16 : (512 - kACol) / kACols) : kStagesSm;
   static const int kSmem = kStages * kStageBytes + kFixed;
+  static_assert(!ATM || T == 1, "the tensor-memory operand path holds one tile per CTA");
+  static_assert(G == 2 || (ATM && G == 4), "4-cell stages exist on the tensor-memory path only");
 };
 
-template <int T, int R>
-__global__ void __launch_bounds__(128 * T * R + 64, MmaCfg<T, R>::kCtasPerSm) k_score_mma(MmaParams sp) {
-  using Cfg = MmaCfg<T, R>;
+template <int T, int R, bool ATM, int G>
+__global__ void __launch_bounds__(128 * T * R + 64, MmaCfg<T, R, ATM, G>::kCtasPerSm) k_score_mma(MmaParams sp) {
+  using Cfg = MmaCfg<T, R, ATM, G>;
+  constexpr int STAGES_PER_GROUP = CELLS_PER_GROUP / G;
   constexpr int GW = 4 * T * R;        // gather warps
   constexpr int NS = Cfg::kStages;
   constexpr int ACC = 2 * RING_N;      // accumulator columns per tile: cost | norm
@@ -140,7 +154,7 @@ __global__ void __launch_bounds__(128 * T * R + 64, MmaCfg<T, R>::kCtasPerSm) k_
   unsigned char* sRing = smem + (size_t)NS * Cfg::kStageBytes;       // [2] ring slots
   unsigned char* sB2 = sRing + 2 * RING_SLOT_BYTES;                  // [NB2] tot blocks
   unsigned char* sA2 = sB2 + NB2 * B2_BYTES;                         // [NA2][T] known-flag tiles
-  int* s_known = reinterpret_cast<int*>(sA2 + NA2 * T * A2_TILE);    // [R][128 * T] known-cell counts
+  int* s_known = reinterpret_cast<int*>(sA2 + Cfg::kA2Bytes);        // [R][128 * T] known-cell counts
   // barriers: full[NS] empty[NS] ring_full[2] ring_empty[2] accum b2_full[NB2] b2_empty[NB2]
   uint64_t* bars = reinterpret_cast<uint64_t*>(s_known + 128 * T * R);
   uint32_t* s_tmem = reinterpret_cast<uint32_t*>(bars + 2 * NS + 5 + 2 * NB2);
@@ -152,7 +166,7 @@ __global__ void __launch_bounds__(128 * T * R + 64, MmaCfg<T, R>::kCtasPerSm) k_
   const uint32_t bar_b2full = smem_u32(bars + 2 * NS + 5), bar_b2empty = smem_u32(bars + 2 * NS + 5 + NB2);
 
   if (warp == GW + 1) tmem_alloc(smem_u32(s_tmem), Cfg::kTmemCols);
-  for (int q = tid; q < NA2 * T * A2_TILE / 4; q += blockDim.x) reinterpret_cast<uint32_t*>(sA2)[q] = 0u;
+  for (int q = tid; q < Cfg::kA2Bytes / 4; q += blockDim.x) reinterpret_cast<uint32_t*>(sA2)[q] = 0u;
   if (tid < RING_N) {
     int k = -1;
     for (int q = sp.n_shifts - 1; q >= 0; q--) if (sp.shifts[q] == tid) k = q;     // first occurrence wins
@@ -169,17 +183,27 @@ __global__ void __launch_bounds__(128 * T * R + 64, MmaCfg<T, R>::kCtasPerSm) k_
   __syncthreads();
   tc_fence_after();
   const uint32_t tmem_base = *s_tmem;
+  if (ATM) {
+    // flag columns start at zero: the cells past the lattice in the last group meet zero tot values, and 0 x garbage
+    // must not be NaN
+    if (warp < 4) {
+      for (int q = 0; q < NA2 * T * 8; q++) tmem_st1(tmem_base + ((uint32_t)(warp * 32) << 16) + (uint32_t)(Cfg::kA2Col + q), 0u);
+      tmem_wait_st();
+    }
+    tc_fence_before();
+    __syncthreads();
+    tc_fence_after();
+  }
 
   const long long per_batch = 128 * T;
   const long long n_batches = (sp.n_work + per_batch - 1) / per_batch;
   const int n_theta = sp.n_theta;
-  const int K_ITERS = sp.P / MMA_G;                 // n_theta is even: a stage never straddles two rings
-  const int stages_per_ring = n_theta / MMA_G;
+  const int K_ITERS = sp.P / G;                     // G divides n_theta: a stage never straddles two rings
+  const int stages_per_ring = n_theta / G;
   const int ring_rows = n_theta + RING_N;
   const uint32_t ring_bytes = (uint32_t)ring_rows * 32;      // 2 planes x rows x 16 B
   uint32_t grp_it = 0;             // 16-cell group counter, continues across batches like `it`
   uint32_t it = 0;                 // pipeline iteration counter, continues across batches (same sequence in every role)
-  uint32_t ring_it = 0;            // ring counter, likewise
   uint32_t local_batch = 0;
 
   if (warp < GW) {
@@ -211,45 +235,59 @@ __global__ void __launch_bounds__(128 * T * R + 64, MmaCfg<T, R>::kCtasPerSm) k_
 
       // Each thread pulls the whole 32-byte record of ITS hypothesis with one 256-bit load (one sector, one L1
       // wavefront; measured 0.95 records/clk/SM from L2 against 0.42 for 2 x LDG.128 — tools/gather_bench.cu).
-      auto load_stage = [&](int k, uint4 (&rec)[MMA_G][2]) {
+      auto load_stage = [&](int k, uint4 (&rec)[G][2]) {
 #pragma unroll
-        for (int g = 0; g < MMA_G; g++) {
-          const int p = k * MMA_G + g;
+        for (int g = 0; g < G; g++) {
+          const int p = k * G + g;
           rec[g][0] = make_uint4(0, 0, 0, 0); rec[g][1] = rec[g][0];
           if (active) {
             const float2 tb = c_tab[p];
             const int r = lattice_index(tb.x, sc, sp.res, oy);
             const int c = lattice_index(tb.y, sc, sp.res, ox);
             if (r >= 0 && r < sp.rows && c >= 0 && c < sp.cols)
-              ldg256(map_bytes + ((size_t)r * sp.cols + c) * 32, rec[g][0], rec[g][1]);
+              ldg256(map_bytes + map16_offset(r, c, sp.cols, sp.ph_log2, sp.ph_cols), rec[g][0], rec[g][1]);
           }
         }
       };
-      auto store_stage = [&](int k, const uint4 (&rec)[MMA_G][2]) {
+      auto store_stage = [&](int k, const uint4 (&rec)[G][2]) {
         const uint32_t iter = it + (uint32_t)k;
         const uint32_t st = iter % NS, ph = (iter / NS) & 1u;
         mbar_wait(bar_empty + 8 * st, ph ^ 1u);
-        unsigned char* base = sA + (size_t)st * Cfg::kStageBytes + (size_t)t * A_TILE + (size_t)m * 16;
+        // the known flags as one K = 16 operand per 16 cells: this stage owns two adjacent halfs of row m
+        uint32_t word[G / 2];
 #pragma unroll
-        for (int g = 0; g < MMA_G; g++) {
-          *reinterpret_cast<uint4*>(base + (size_t)g * T * A_TILE) = rec[g][0];            // K chunk 0: hi halves
-          *reinterpret_cast<uint4*>(base + (size_t)g * T * A_TILE + A_LBO) = rec[g][1];    // K chunk 1: lo halves
-          known_cnt += (rec[g][0].w >> 16) != 0u ? 1 : 0;                                  // slot 7 hi = known (1.0)
-        }
-        {
-          // the same flags as one K = 16 operand per 16 cells: this stage owns two adjacent halfs of row m
-          const uint32_t word = (rec[0][0].w & 0xffff0000u ? 0x00003C00u : 0u) | (rec[MMA_G - 1][0].w & 0xffff0000u ? 0x3C000000u : 0u);
-          const uint32_t gq = (uint32_t)k / STAGES_PER_GROUP, q0 = ((uint32_t)k % STAGES_PER_GROUP) * MMA_G;
-          const uint32_t gslot = (grp_base + gq) % NA2;
-          *reinterpret_cast<uint32_t*>(sA2 + (size_t)(gslot * T + t) * A2_TILE + (q0 >> 3) * 2048 + (size_t)m * 16 + (q0 & 7) * 2) = word;
+        for (int g = 0; g < G; g += 2)
+          word[g / 2] = (rec[g][0].w & 0xffff0000u ? 0x00003C00u : 0u) | (rec[g + 1][0].w & 0xffff0000u ? 0x3C000000u : 0u);
+        const uint32_t gq = (uint32_t)k / STAGES_PER_GROUP, q0 = ((uint32_t)k % STAGES_PER_GROUP) * G;
+        const uint32_t gslot = (grp_base + gq) % NA2;
+#pragma unroll
+        for (int g = 0; g < G; g++) known_cnt += (rec[g][0].w >> 16) != 0u ? 1 : 0;    // slot 7 hi = known (1.0)
+        if (ATM) {
+          // row m = TMEM lane m (this warp's quarter); a record = 8 columns (16 fp16 in K order), a flag pair = 1 column
+          const uint32_t lane_base = tmem_base + ((uint32_t)((warp & 3) * 32) << 16);
+#pragma unroll
+          for (int g = 0; g < G; g++)
+            tmem_st8(lane_base + (uint32_t)(Cfg::kACol + st * Cfg::kACols + (g * T + t) * 8), rec[g][0], rec[g][1]);
+          if (G == 2) tmem_st1(lane_base + (uint32_t)(Cfg::kA2Col + (gslot * T + t) * 8 + (q0 >> 1)), word[0]);
+          else tmem_st2(lane_base + (uint32_t)(Cfg::kA2Col + (gslot * T + t) * 8 + (q0 >> 1)), word[0], word[G / 2 - 1]);
+          tmem_wait_st();
+          tc_fence_before();
+        } else {
+          unsigned char* base = sA + (size_t)st * Cfg::kStageBytes + (size_t)t * A_TILE + (size_t)m * 16;
+#pragma unroll
+          for (int g = 0; g < G; g++) {
+            *reinterpret_cast<uint4*>(base + (size_t)g * T * A_TILE) = rec[g][0];            // K chunk 0: hi halves
+            *reinterpret_cast<uint4*>(base + (size_t)g * T * A_TILE + A_LBO) = rec[g][1];    // K chunk 1: lo halves
+          }
+          *reinterpret_cast<uint32_t*>(sA2 + (size_t)(gslot * T + t) * A2_TILE + (q0 >> 3) * 2048 + (size_t)m * 16 + (q0 & 7) * 2) = word[0];
+          fence_proxy_async();
         }
         if (k + R >= K_ITERS) s_known[sub * 128 * T + row] = known_cnt;     // this thread's last stage of the batch
-        fence_proxy_async();
         __syncwarp();
         if (lane == 0) mbar_arrive(bar_full + 8 * st);
       };
 
-      uint4 ra[MMA_G][2], rb[MMA_G][2];
+      uint4 ra[G][2], rb[G][2];
       if (sub < K_ITERS) load_stage(sub, ra);
 #pragma unroll 1
       for (int k = sub; k < K_ITERS; k += 2 * R) {       // this thread's stages: sub, sub + R, ... (two in flight)
@@ -288,7 +326,7 @@ __global__ void __launch_bounds__(128 * T * R + 64, MmaCfg<T, R>::kCtasPerSm) k_
           // first strict minimum in LIST order == lexicographic minimum of (cost, list position)
           if (k >= 0 && (cst[j] < best || (cst[j] == best && k < best_k))) { best = cst[j]; best_k = k; }
         }
-        if (sp.costs || sp.n_cost_peers) {          // warp-uniform
+        if ((sp.costs || sp.n_cost_peers) && !sp.dbg_nostore) {          // warp-uniform
           const int n_dst = sp.n_cost_peers ? sp.n_cost_peers : 1;
           const long long row = (sp.n_cost_peers ? sp.cost_row0 + i : i) * sp.n_shifts;
           if (sp.identity_shifts) {
@@ -340,77 +378,99 @@ __global__ void __launch_bounds__(128 * T * R + 64, MmaCfg<T, R>::kCtasPerSm) k_
     }
   } else if (warp == GW) {
     // =========================== scan-ring / tot-block loader ===========================
-    if (lane == 0) {
-      for (long long batch = blockIdx.x; batch < n_batches; batch += gridDim.x) {
-        for (int k = 0; k < K_ITERS; k++) {              // same order as the MMA issuer consumes them
-          if (k % stages_per_ring == 0) {
-            const int r = k / stages_per_ring;
-            const uint32_t sl = ring_it & 1u, ph = (ring_it >> 1) & 1u;
-            mbar_wait(bar_rempty + 8 * sl, ph ^ 1u);
-            mbar_expect_tx(bar_rfull + 8 * sl, ring_bytes);
-            bulk_g2s(smem_u32(sRing + (size_t)sl * RING_SLOT_BYTES),
-                     reinterpret_cast<const unsigned char*>(sp.rings) + (size_t)r * ring_bytes, ring_bytes, bar_rfull + 8 * sl);
-            ring_it++;
+    // whole warp, warp-uniform control flow; the elected lane issues the copies.  Order = the order in which the MMA
+    // issuer consumes them: the ring of a radius bin before the tot block of the group in which its first cell lies.
+    const bool leader = elect_one();
+    uint32_t rsl = 0, rph = 0, bsl = 0, bph = 0;          // ring slot / parity, tot-block slot / parity
+    for (long long batch = blockIdx.x; batch < n_batches; batch += gridDim.x) {
+      int next_ring = 0, ring_first = 0;                  // next ring to load and its first stage
+      for (int g = 0; g < sp.n_groups; g++) {
+        while (next_ring < sp.n_r && ring_first <= g * STAGES_PER_GROUP + STAGES_PER_GROUP - 1) {
+          mbar_wait(bar_rempty + 8 * rsl, rph ^ 1u);
+          if (leader) {
+            mbar_expect_tx(bar_rfull + 8 * rsl, ring_bytes);
+            bulk_g2s(smem_u32(sRing) + rsl * RING_SLOT_BYTES,
+                     reinterpret_cast<const unsigned char*>(sp.rings) + (size_t)next_ring * ring_bytes, ring_bytes, bar_rfull + 8 * rsl);
           }
-          if (k % STAGES_PER_GROUP == 0) {
-            const int g = k / STAGES_PER_GROUP;
-            const uint32_t sl = grp_it % NB2, ph = (grp_it / NB2) & 1u;
-            mbar_wait(bar_b2empty + 8 * sl, ph ^ 1u);
-            mbar_expect_tx(bar_b2full + 8 * sl, B2_BYTES);
-            bulk_g2s(smem_u32(sB2 + (size_t)sl * B2_BYTES),
-                     reinterpret_cast<const unsigned char*>(sp.norm_op) + (size_t)g * B2_BYTES, B2_BYTES, bar_b2full + 8 * sl);
-            grp_it++;
-          }
+          __syncwarp();
+          rsl ^= 1u; if (rsl == 0) rph ^= 1u;
+          next_ring++; ring_first += stages_per_ring;
         }
+        mbar_wait(bar_b2empty + 8 * bsl, bph ^ 1u);
+        if (leader) {
+          mbar_expect_tx(bar_b2full + 8 * bsl, B2_BYTES);
+          bulk_g2s(smem_u32(sB2) + bsl * B2_BYTES, reinterpret_cast<const unsigned char*>(sp.norm_op) + (size_t)g * B2_BYTES,
+                   B2_BYTES, bar_b2full + 8 * bsl);
+        }
+        __syncwarp();
+        if (++bsl == NB2) { bsl = 0; bph ^= 1u; }
       }
     }
   } else {
     // =========================== MMA issuer ===========================
-    if (lane == 0) {
-      // instruction descriptor: D = f32, A = B = f16, both K-major, N = 112, M = 128
-      const uint32_t idesc = (1u << 4) | ((uint32_t)(RING_N >> 3) << 17) | ((uint32_t)(128 >> 4) << 24);
-      const uint32_t plane = (uint32_t)ring_rows * 16;           // LBO of the ring operand
-      for (long long batch = blockIdx.x; batch < n_batches; batch += gridDim.x) {
-        uint32_t ring0 = 0, rsl = 0;
-        for (int k = 0; k < K_ITERS; k++, it++) {
-          const int sr = k % stages_per_ring;
-          if (sr == 0) {
-            rsl = ring_it & 1u;
-            mbar_wait(bar_rfull + 8 * rsl, (ring_it >> 1) & 1u);
-            ring0 = smem_u32(sRing + (size_t)rsl * RING_SLOT_BYTES);
-            ring_it++;
-          }
-          const uint32_t st = it % NS, ph = (it / NS) & 1u;
-          mbar_wait(bar_full + 8 * st, ph);
-          tc_fence_after();
-          const uint32_t a0 = smem_u32(sA + (size_t)st * Cfg::kStageBytes);
+    // whole warp, warp-uniform control flow, incremental slot / parity counters; the elected lane issues.
+    // instruction descriptor: D = f32, A = B = f16, both K-major, N = 112, M = 128
+    const bool leader = elect_one();
+    const uint32_t idesc = (1u << 4) | ((uint32_t)(RING_N >> 3) << 17) | ((uint32_t)(128 >> 4) << 24);
+    const uint32_t plane = (uint32_t)ring_rows * 16;           // LBO of the ring operand
+    const uint32_t sA_u = smem_u32(sA), sA2_u = smem_u32(sA2), sRing_u = smem_u32(sRing), sB2_u = smem_u32(sB2);
+    uint32_t st = 0, ph = 0;                                   // stage slot / parity (continue across batches)
+    uint32_t rsl = 0, rph = 0, bsl = 0, bph = 0, asl = 0;      // ring, tot-block and flag-group slots
+    for (long long batch = blockIdx.x; batch < n_batches; batch += gridDim.x) {
+      uint64_t ring_desc = 0;
+      uint32_t cur_rsl = 0;
+      int sr = 0, sg = 0, grp = 0;                             // stage within the ring / within the 16-cell group; group
+      for (int k = 0; k < K_ITERS; k++) {
+        if (sr == 0) {
+          mbar_wait(bar_rfull + 8 * rsl, rph);
+          ring_desc = umma_desc(sRing_u + rsl * RING_SLOT_BYTES, plane, 128);
+          cur_rsl = rsl;
+          rsl ^= 1u; if (rsl == 0) rph ^= 1u;
+        }
+        mbar_wait(bar_full + 8 * st, ph);
+        const bool group_done = sg == STAGES_PER_GROUP - 1 || k == K_ITERS - 1;
+        if (group_done) mbar_wait(bar_b2full + 8 * bsl, bph);
+        tc_fence_after();
+        if (leader) {
 #pragma unroll
-          for (int g = 0; g < MMA_G; g++) {
-            const uint64_t bcnt = umma_desc(ring0 + (uint32_t)(sr * MMA_G + g) * 16, plane, 128);
+          for (int g = 0; g < G; g++) {
+            const uint64_t bcnt = ring_desc + (uint64_t)(uint32_t)(sr * G + g);      // window start advances 16 B per cell
 #pragma unroll
-            for (int tt = 0; tt < T; tt++)
-              umma_f16(tmem_base + (uint32_t)(tt * ACC), umma_desc(a0 + (g * T + tt) * A_TILE, A_LBO, 128), bcnt, idesc,
-                       (k > 0 || g > 0) ? 1u : 0u);
+            for (int tt = 0; tt < T; tt++) {
+              if (ATM)
+                umma_f16_ts(tmem_base + (uint32_t)(tt * ACC), tmem_base + (uint32_t)(Cfg::kACol + (g * T + tt) * 8) + st * Cfg::kACols,
+                            bcnt, idesc, (k > 0 || g > 0) ? 1u : 0u);
+              else
+                umma_f16(tmem_base + (uint32_t)(tt * ACC), umma_desc(sA_u + st * Cfg::kStageBytes + (g * T + tt) * A_TILE, A_LBO, 128),
+                         bcnt, idesc, (k > 0 || g > 0) ? 1u : 0u);
+            }
           }
-          const bool group_done = (k % STAGES_PER_GROUP == STAGES_PER_GROUP - 1) || k == K_ITERS - 1;
-          uint32_t bsl = 0;
           if (group_done) {
             // normalisation: the known flags of this group's cells against the tot block
-            bsl = grp_it % NB2;
-            mbar_wait(bar_b2full + 8 * bsl, (grp_it / NB2) & 1u);
-            const uint32_t a2 = smem_u32(sA2 + (size_t)((grp_it % NA2) * T) * A2_TILE);
-            const uint64_t btot = umma_desc(smem_u32(sB2 + (size_t)bsl * B2_BYTES), RING_N * 16, 128);
+            const uint64_t btot = umma_desc(sB2_u + bsl * B2_BYTES, RING_N * 16, 128);
 #pragma unroll
-            for (int tt = 0; tt < T; tt++)
-              umma_f16(tmem_base + (uint32_t)(tt * ACC + RING_N), umma_desc(a2 + tt * A2_TILE, 2048, 128), btot, idesc,
-                       (k / STAGES_PER_GROUP) > 0 ? 1u : 0u);
-            grp_it++;
+            for (int tt = 0; tt < T; tt++) {
+              if (ATM)
+                umma_f16_ts(tmem_base + (uint32_t)(tt * ACC + RING_N), tmem_base + (uint32_t)(Cfg::kA2Col + tt * 8) + asl * (T * 8),
+                            btot, idesc, grp > 0 ? 1u : 0u);
+              else
+                umma_f16(tmem_base + (uint32_t)(tt * ACC + RING_N), umma_desc(sA2_u + (asl * T + tt) * A2_TILE, 2048, 128), btot, idesc,
+                         grp > 0 ? 1u : 0u);
+            }
           }
           umma_commit(bar_empty + 8 * st);          // implies tcgen05.fence::before_thread_sync
           if (group_done) umma_commit(bar_b2empty + 8 * bsl);
-          if (sr == stages_per_ring - 1) umma_commit(bar_rempty + 8 * rsl);   // ring slot free once these MMAs retire
+          if (sr == stages_per_ring - 1) umma_commit(bar_rempty + 8 * cur_rsl);   // ring slot free once these MMAs retire
+          if (k == K_ITERS - 1) umma_commit(bar_accum);
         }
-        umma_commit(bar_accum);
+        __syncwarp();
+        if (group_done) {
+          sg = 0; grp++;
+          if (++bsl == NB2) { bsl = 0; bph ^= 1u; }
+          if (++asl == NA2) asl = 0;
+        } else sg++;
+        if (++sr == stages_per_ring) sr = 0;
+        if (++st == NS) { st = 0; ph ^= 1u; }
       }
     }
   }
@@ -425,7 +485,7 @@ __global__ void __launch_bounds__(128 * T * R + 64, MmaCfg<T, R>::kCtasPerSm) k_
 static bool mma_usable(tdr_ctx* ctx, const int32_t* host_shifts, int n_shifts) {
   if (ctx->score_impl == 1) return false;
   const int n_theta = ctx->n_theta;
-  if (n_theta > RING_N || (n_theta % MMA_G) != 0 || ctx->n_theta * ctx->n_r > MMA_TAB_MAX) return false;
+  if (n_theta > RING_N || (n_theta % 2) != 0 || ctx->n_theta * ctx->n_r > MMA_TAB_MAX) return false;
   if (n_shifts < 1 || n_shifts > TDR_MAX_SHIFTS) return false;
   bool seen[RING_N] = {};
   for (int k = 0; k < n_shifts; k++) {              // every candidate must be a distinct row shift in [0, n_theta)
@@ -467,18 +527,20 @@ int score_mma(tdr_ctx* ctx, float res, bool grid_mode, long long n_items, float 
   TDR_CUDA(cudaMemcpyAsync(&h_max, d_max, 4, cudaMemcpyDeviceToHost, ctx->stream));
   TDR_CUDA(cudaStreamSynchronize(ctx->stream));
   if (h_max > 2048) return TDR_OK;              // counts not exact in fp16: CUDA-core path
-  if (int e = build_map16(ctx)) return e;
 
   if (int e = build_perm(ctx, grid_mode, n_items)) return e;
   tdr::Particles& pt = ctx->part[ctx->cur];
   static uint64_t tab_seen = 0;
   if (int e = sync_const_tab(ctx, P, &tab_seen)) return e;
   MmaParams sp; memset(&sp, 0, sizeof(sp));
-  sp.map16 = ctx->map16.as<uint4>(); sp.rows = ctx->rows; sp.cols = ctx->cols; sp.resolution = ctx->resolution;
+  sp.ph_log2 = grid_mode ? ctx->grid_phase_log2 : 0;
+  if (int e = build_map16(ctx, sp.ph_log2, &sp.map16, &sp.ph_cols)) return e;
+  sp.rows = ctx->rows; sp.cols = ctx->cols; sp.resolution = ctx->resolution;
   sp.n_theta = ctx->n_theta; sp.n_r = ctx->n_r; sp.P = P; sp.res = res;
   sp.rings = ctx->scan_op.as<uint4>(); sp.norm_op = d_norm_op; sp.n_groups = n_groups;
   sp.perm = ctx->perm.as<int>();
   sp.shifts = dev_shifts; sp.n_shifts = n_shifts;
+  if (const char* e = getenv("TDR_DEBUG_NOSTORE")) sp.dbg_nostore = atoi(e);
   if (grid_mode) {
     sp.n_work = n_items; sp.centers = ctx->grid_centers.as<float>(); sp.grid_scale = grid_scale;
     sp.costs = grid_costs_ptr(ctx);
@@ -498,22 +560,29 @@ int score_mma(tdr_ctx* ctx, float res, bool grid_mode, long long n_items, float 
     sp.regularization = ctx->fp.regularization;
     sp.thetas = ctx->d_search_thetas.as<float>();
   }
-#define TDR_LAUNCH_MMA(TT, RR)                                                                                       \
+#define TDR_LAUNCH_MMA(TT, RR, AA, GG)                                                                               \
   do {                                                                                                                \
-    using Cfg = MmaCfg<TT, RR>;                                                                                       \
+    using Cfg = MmaCfg<TT, RR, AA, GG>;                                                                               \
     static bool attr = false;                                                                                         \
-    if (!attr) { TDR_CUDA(cudaFuncSetAttribute(k_score_mma<TT, RR>, cudaFuncAttributeMaxDynamicSharedMemorySize, Cfg::kSmem)); attr = true; } \
+    if (!attr) { TDR_CUDA(cudaFuncSetAttribute(k_score_mma<TT, RR, AA, GG>, cudaFuncAttributeMaxDynamicSharedMemorySize, Cfg::kSmem)); attr = true; } \
     const long long nb = (sp.n_work + 128 * TT - 1) / (128 * TT);                                                     \
     const long long cap = (long long)ctx->sm_count * (ctx->mma_ctas > 0 && ctx->mma_ctas < Cfg::kCtasPerSm ? ctx->mma_ctas : Cfg::kCtasPerSm); \
     const int grid = (int)(nb < cap ? nb : cap);                                                                      \
-    k_score_mma<TT, RR><<<grid, Cfg::kThreads, Cfg::kSmem, ctx->stream>>>(sp);                                        \
+    k_score_mma<TT, RR, AA, GG><<<grid, Cfg::kThreads, Cfg::kSmem, ctx->stream>>>(sp);                                \
   } while (0)
-  switch (ctx->mma_ring_cfg) {        // tiles * 10 + threads per row; 1 x 2 (two CTAs per SM) measured best
-    case 21: TDR_LAUNCH_MMA(2, 1); break;
-    case 22: TDR_LAUNCH_MMA(2, 2); break;
-    case 11: TDR_LAUNCH_MMA(1, 1); break;
-    case 14: TDR_LAUNCH_MMA(1, 4); break;
-    default: TDR_LAUNCH_MMA(1, 2); break;
+  // tiles * 10 + threads per row (+ 100: operands in tensor memory, + 400: and 4-cell stages, needs n_theta % 4 == 0)
+  int rcfg = ctx->mma_ring_cfg;
+  if (rcfg >= 400 && ctx->n_theta % 4 != 0) rcfg = 114;
+  switch (rcfg) {
+    case 21: TDR_LAUNCH_MMA(2, 1, false, 2); break;
+    case 22: TDR_LAUNCH_MMA(2, 2, false, 2); break;
+    case 11: TDR_LAUNCH_MMA(1, 1, false, 2); break;
+    case 14: TDR_LAUNCH_MMA(1, 4, false, 2); break;
+    case 12: TDR_LAUNCH_MMA(1, 2, false, 2); break;
+    case 112: TDR_LAUNCH_MMA(1, 2, true, 2); break;
+    case 114: TDR_LAUNCH_MMA(1, 4, true, 2); break;
+    case 412: TDR_LAUNCH_MMA(1, 2, true, 4); break;
+    default: TDR_LAUNCH_MMA(1, 3, true, 4); break;
   }
 #undef TDR_LAUNCH_MMA
   count_launch(ctx);

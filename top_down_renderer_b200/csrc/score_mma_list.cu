@@ -57,7 +57,7 @@ static __global__ void k_build_scan_operand(const float* __restrict__ img, int C
 
 
 struct ListParams {
-  const uint4* map16; int rows, cols; float resolution;
+  const uint4* map16; int rows, cols; float resolution; int ph_log2, ph_cols;
   const float2* tab; int P, P_pad; float res;
   const uint4* bop;
   const int* perm; long long n_work;
@@ -159,7 +159,7 @@ __global__ void __launch_bounds__(128 * T * R + 64, ListCfg<N, T, R, ATM>::kCtas
             const int r = lattice_index(tb.x, sc, sp.res, oy);
             const int c = lattice_index(tb.y, sc, sp.res, ox);
             if (r >= 0 && r < sp.rows && c >= 0 && c < sp.cols)
-              ldg256(map_bytes + ((size_t)r * sp.cols + c) * 32, rec[g][0], rec[g][1]);
+              ldg256(map_bytes + map16_offset(r, c, sp.cols, sp.ph_log2, sp.ph_cols), rec[g][0], rec[g][1]);
           }
         }
       };
@@ -237,46 +237,55 @@ __global__ void __launch_bounds__(128 * T * R + 64, ListCfg<N, T, R, ATM>::kCtas
     }
   } else if (warp == GW) {
     // =========================== scan-operand loader ===========================
-    if (lane == 0) {
-      for (long long batch = blockIdx.x; batch < n_batches; batch += gridDim.x) {
-        for (int k = 0; k < K_ITERS; k++, it++) {
-          const uint32_t st = it % NS, ph = (it / NS) & 1u;
-          mbar_wait(bar_empty + 8 * st, ph ^ 1u);
+    // whole warp, warp-uniform control flow; the elected lane issues the copies (see elect_one)
+    const bool leader = elect_one();
+    const uint32_t sB_u = smem_u32(sB);
+    uint32_t st = 0, ph = 0;
+    for (long long batch = blockIdx.x; batch < n_batches; batch += gridDim.x) {
+      const unsigned char* src = reinterpret_cast<const unsigned char*>(sp.bop);
+      for (int k = 0; k < K_ITERS; k++, src += Cfg::kBBytes) {
+        mbar_wait(bar_empty + 8 * st, ph ^ 1u);
+        if (leader) {
           mbar_expect_tx(bar_full + 8 * st, Cfg::kBBytes);
-          bulk_g2s(smem_u32(sB + (size_t)st * Cfg::kBBytes),
-                   reinterpret_cast<const unsigned char*>(sp.bop) + (size_t)k * Cfg::kBBytes, Cfg::kBBytes,
-                   bar_full + 8 * st);
+          bulk_g2s(sB_u + st * Cfg::kBBytes, src, Cfg::kBBytes, bar_full + 8 * st);
         }
+        __syncwarp();
+        if (++st == NS) { st = 0; ph ^= 1u; }
       }
     }
   } else {
     // =========================== MMA issuer ===========================
-    if (lane == 0) {
-      // instruction descriptor: D = f32, A = B = f16, both K-major, N, M = 128
-      const uint32_t idesc = (1u << 4) | ((uint32_t)(N >> 3) << 17) | ((uint32_t)(128 >> 4) << 24);
-      for (long long batch = blockIdx.x; batch < n_batches; batch += gridDim.x) {
-        for (int k = 0; k < K_ITERS; k++, it++) {
-          const uint32_t st = it % NS, ph = (it / NS) & 1u;
-          mbar_wait(bar_full + 8 * st, ph);
-          tc_fence_after();
-          const uint32_t a0 = smem_u32(sA + (size_t)st * Cfg::kABytes), b0 = smem_u32(sB + (size_t)st * Cfg::kBBytes);
+    // whole warp, warp-uniform control flow, incremental slot / parity counters; the elected lane issues.
+    // instruction descriptor: D = f32, A = B = f16, both K-major, N, M = 128
+    const bool leader = elect_one();
+    const uint32_t idesc = (1u << 4) | ((uint32_t)(N >> 3) << 17) | ((uint32_t)(128 >> 4) << 24);
+    const uint32_t sA_u = smem_u32(sA), sB_u = smem_u32(sB);
+    uint32_t st = 0, ph = 0;
+    for (long long batch = blockIdx.x; batch < n_batches; batch += gridDim.x) {
+      for (int k = 0; k < K_ITERS; k++) {
+        mbar_wait(bar_full + 8 * st, ph);
+        tc_fence_after();
+        if (leader) {
+          const uint64_t bdesc0 = umma_desc(sB_u + st * Cfg::kBBytes, N * 16, 128);
 #pragma unroll
           for (int g = 0; g < MMA_G; g++) {
-            const uint64_t bdesc = umma_desc(b0 + g * (N * 32), N * 16, 128);
+            const uint64_t bdesc = bdesc0 + (uint64_t)(g * (N * 32 / 16));
 #pragma unroll
             for (int tt = 0; tt < T; tt++) {
               if (ATM) {
-                umma_f16_ts(tmem_base + (uint32_t)(tt * N), tmem_base + (uint32_t)(T * N + st * Cfg::kACols + (g * T + tt) * 8),
+                umma_f16_ts(tmem_base + (uint32_t)(tt * N), tmem_base + (uint32_t)(T * N + (g * T + tt) * 8) + st * Cfg::kACols,
                             bdesc, idesc, (k > 0 || g > 0) ? 1u : 0u);
               } else {
-                const uint64_t adesc = umma_desc(a0 + (g * T + tt) * A_TILE, A_LBO, 128);
+                const uint64_t adesc = umma_desc(sA_u + st * Cfg::kABytes + (g * T + tt) * A_TILE, A_LBO, 128);
                 umma_f16(tmem_base + (uint32_t)(tt * N), adesc, bdesc, idesc, (k > 0 || g > 0) ? 1u : 0u);
               }
             }
           }
           umma_commit(bar_empty + 8 * st);        // implies tcgen05.fence::before_thread_sync
+          if (k == K_ITERS - 1) umma_commit(bar_accum);
         }
-        umma_commit(bar_accum);
+        __syncwarp();
+        if (++st == NS) { st = 0; ph ^= 1u; }
       }
     }
   }
@@ -324,14 +333,15 @@ int score_mma_list(tdr_ctx* ctx, float res, bool grid_mode, long long n_items, f
   TDR_CUDA(cudaMemcpyAsync(&h_max, d_max, 4, cudaMemcpyDeviceToHost, ctx->stream));
   TDR_CUDA(cudaStreamSynchronize(ctx->stream));
   if (h_max > 2048) return TDR_OK;              // counts not exact in fp16: CUDA-core path
-  if (int e = build_map16(ctx)) return e;
 
   if (int e = build_perm(ctx, grid_mode, n_items)) return e;
   tdr::Particles& pt = ctx->part[ctx->cur];
   static uint64_t tab_seen = 0;
   if (int e = sync_const_tab(ctx, P, &tab_seen)) return e;
   ListParams sp; memset(&sp, 0, sizeof(sp));
-  sp.map16 = ctx->map16.as<uint4>(); sp.rows = ctx->rows; sp.cols = ctx->cols; sp.resolution = ctx->resolution;
+  sp.ph_log2 = grid_mode ? ctx->grid_phase_log2 : 0;
+  if (int e = build_map16(ctx, sp.ph_log2, &sp.map16, &sp.ph_cols)) return e;
+  sp.rows = ctx->rows; sp.cols = ctx->cols; sp.resolution = ctx->resolution;
   sp.tab = ctx->tab.as<float2>(); sp.P = P; sp.P_pad = P_pad; sp.res = res;
   sp.bop = ctx->scan_op.as<uint4>();
   sp.perm = ctx->perm.as<int>();

@@ -96,6 +96,12 @@ struct tdr_ctx {
   // tensor-core score path (score_mma.cu): class-weighted fp16 hi/lo copy of the map, scan operand, binning
   tdr::DevBuf map16;         // rows*cols x 32 B
   bool map16_valid = false;
+  // second copy for lattices of centres (exhaustive grid): every map row split into 2^k PHASE rows (x mod 2^k), so
+  // that centres 2^k px apart read CONSECUTIVE records — 8 full 128-byte lines per warp load instead of one sector
+  // out of each of 32 lines (measured 1.67 against 0.82 records/clk/SM, tools/gather_bench.cu patterns 7 / 4)
+  tdr::DevBuf map16g;
+  int map16g_log2 = -1;      // layout of map16g (-1: not built)
+  int grid_phase_log2 = 0;   // x stride of the resident lattice of centres, if it is 2, 4 or 8 px (else 0)
   tdr::DevBuf scan_op;       // P_pad x N x 32 B
   tdr::DevBuf bin_counts, perm;
   int score_impl = 0;        // 0 auto, 1 CUDA cores only, 2 tensor cores whenever usable
@@ -104,7 +110,7 @@ struct tdr_ctx {
   int mma_seg_shift = 2;     // log2 of the column-segment width of a bin (tuning: TDR_MMA_SEG_SHIFT)
   int mma_split = 2;         // gather threads per hypothesis row (tuning: TDR_MMA_SPLIT)
   int mma_a_tmem = 1;        // list kernel: gathered records to tensor memory instead of shared (tuning: TDR_MMA_A_TMEM)
-  int mma_ring_cfg = 12;     // ring kernel: tiles * 10 + threads per row (tuning: TDR_MMA_RING_CFG)
+  int mma_ring_cfg = 413;    // ring kernel: tiles * 10 + threads per row, + 100 operands in tensor memory, + 400 and 4-cell stages (tuning: TDR_MMA_RING_CFG)
   int mma_kernel = 0;        // 0 auto, 1 streamed-operand kernel only, 2 ring kernel only (tuning: TDR_MMA_KERNEL)
   int mma_ctas = 0;          // cap on co-resident CTAs per SM (0 = as many as TMEM allows; tuning: TDR_MMA_CTAS)
   int mma_st_shift = 10;     // log2 of the binning super-tile side in px (tuning: TDR_MMA_ST_SHIFT)
