@@ -148,7 +148,7 @@ void tdr_destroy(tdr_ctx* c) {
   tdr::DevBuf* bufs[] = {&c->map_px, &c->seedbits, &c->edt_g, &c->scratch, &c->scratch2, &c->tab, &c->pts, &c->lut,
                          &c->scan_img, &c->scan_pack, &c->hist, &c->d_search_thetas, &c->d_search_shifts, &c->weights,
                          &c->prefix, &c->idx, &c->scal, &c->pose_tmp, &c->grid_centers, &c->grid_costs,
-                         &c->grid_shifts, &c->d_cw, &c->map16, &c->map16g, &c->seq_ws, &c->scan_op, &c->bin_counts, &c->perm};
+                         &c->grid_shifts, &c->d_cw, &c->map16, &c->map16g, &c->tab_scaled, &c->seq_ws, &c->scan_op, &c->bin_counts, &c->perm};
   for (auto* b : bufs) b->release();
   for (void* p : c->grid_opened) cudaIpcCloseMemHandle(p);
   c->grid_full.release();

@@ -81,6 +81,52 @@ __device__ __forceinline__ void umma_f16_ts(uint32_t d_tmem, uint32_t a_tmem, ui
       "}" ::"r"(d_tmem), "r"(a_tmem), "l"(bdesc), "r"(idesc), "r"(accumulate)
       : "memory");
 }
+// one pipeline stage of the tensor-memory path in ONE asm block: G MMAs (M = 128, K = 16 each) whose A operands sit 8
+// columns apart in tensor memory and whose B windows start `b_step` descriptor units (16 B) apart.  Keeping the
+// address arithmetic inside the block leaves ptxas nothing to re-derive per MMA (the issuing lane is the critical
+// path of the kernel: every instruction between two UTCHMMA costs a full uniform-datapath latency).
+template <int G>
+__device__ __forceinline__ void umma_stage_ts(uint32_t d_tmem, uint32_t a_tmem, uint64_t bdesc, uint32_t idesc, uint32_t acc_first,
+                                              uint32_t b_step) {
+  static_assert(G == 2 || G == 4, "cells per stage");
+  if (G == 2) {
+    asm volatile(
+        "{\n\t"
+        ".reg .pred p, t;\n\t"
+        ".reg .b32 a1;\n\t"
+        ".reg .b64 b1, bs;\n\t"
+        "setp.ne.b32 p, %4, 0;\n\t"
+        "setp.eq.b32 t, 0, 0;\n\t"
+        "cvt.u64.u32 bs, %5;\n\t"
+        "tcgen05.mma.cta_group::1.kind::f16 [%0], [%1], %2, %3, p;\n\t"
+        "add.u32 a1, %1, 8;\n\t"
+        "add.u64 b1, %2, bs;\n\t"
+        "tcgen05.mma.cta_group::1.kind::f16 [%0], [a1], b1, %3, t;\n\t"
+        "}" ::"r"(d_tmem), "r"(a_tmem), "l"(bdesc), "r"(idesc), "r"(acc_first), "r"(b_step)
+        : "memory");
+  } else {
+    asm volatile(
+        "{\n\t"
+        ".reg .pred p, t;\n\t"
+        ".reg .b32 a1, a2, a3;\n\t"
+        ".reg .b64 b1, b2, b3, bs;\n\t"
+        "setp.ne.b32 p, %4, 0;\n\t"
+        "setp.eq.b32 t, 0, 0;\n\t"
+        "cvt.u64.u32 bs, %5;\n\t"
+        "tcgen05.mma.cta_group::1.kind::f16 [%0], [%1], %2, %3, p;\n\t"
+        "add.u32 a1, %1, 8;\n\t"
+        "add.u64 b1, %2, bs;\n\t"
+        "tcgen05.mma.cta_group::1.kind::f16 [%0], [a1], b1, %3, t;\n\t"
+        "add.u32 a2, %1, 16;\n\t"
+        "add.u64 b2, b1, bs;\n\t"
+        "tcgen05.mma.cta_group::1.kind::f16 [%0], [a2], b2, %3, t;\n\t"
+        "add.u32 a3, %1, 24;\n\t"
+        "add.u64 b3, b2, bs;\n\t"
+        "tcgen05.mma.cta_group::1.kind::f16 [%0], [a3], b3, %3, t;\n\t"
+        "}" ::"r"(d_tmem), "r"(a_tmem), "l"(bdesc), "r"(idesc), "r"(acc_first), "r"(b_step)
+        : "memory");
+  }
+}
 // registers -> tensor memory: this thread's lane, 8 consecutive 32-bit columns (warp-collective)
 __device__ __forceinline__ void tmem_st8(uint32_t taddr, const uint4& a, const uint4& b) {
   asm volatile("tcgen05.st.sync.aligned.32x32b.x8.b32 [%0], {%1, %2, %3, %4, %5, %6, %7, %8};" ::"r"(taddr), "r"(a.x), "r"(a.y),
@@ -131,6 +177,29 @@ __device__ __forceinline__ uint64_t umma_desc(uint32_t saddr, uint32_t lbo_bytes
 __device__ __forceinline__ size_t map16_offset(int r, int c, int cols, int ph_log2, int ph_cols) {
   if (ph_log2 == 0) return ((size_t)r * cols + c) * 32;
   return ((((size_t)r << ph_log2) + (size_t)(c & ((1 << ph_log2) - 1))) * ph_cols + (size_t)(c >> ph_log2)) * 32;
+}
+// Everything a gather thread needs to turn a lattice coordinate pair into a record of the fp16 map copy.
+struct GatherGeom {
+  int cols, ph_log2, ph_cols;      // layout (map16_offset)
+  uint32_t zero_rec;               // index of an all-zero record past the map: what cells off the map read
+  float row_hi, col_hi;            // rows - 0.5, cols - 0.5 (exact in fp32)
+};
+// record index of the lattice point (vy, vx) = ((tab * scale) * res + centre / resolution), or zero_rec off the map.
+// Same result as f2i_x86(round_half_away(v)) followed by 0 <= index < limit (top_down_map_polar.cpp:28-37), in a third
+// of the instructions (the gather threads are issue-bound): round_half_away(v) lies in [0, limit) exactly when
+// -0.5 < v < limit - 0.5 (NaN fails both), and inside that interval it is trunc(v) + (v - trunc(v) >= 0.5).
+__device__ __forceinline__ uint32_t lattice_record(float vy, float vx, const GatherGeom& g) {
+  const bool ok = vy > -0.5f && vy < g.row_hi && vx > -0.5f && vx < g.col_hi;
+  const float ty = truncf(vy), tx = truncf(vx);
+  const int r = (int)ty + (TDR_FSUB(vy, ty) >= 0.5f ? 1 : 0);
+  const int c = (int)tx + (TDR_FSUB(vx, tx) >= 0.5f ? 1 : 0);
+  const uint32_t ur = (uint32_t)r, uc = (uint32_t)c;
+  const uint32_t rec = ((ur << g.ph_log2) + (uc & ((1u << g.ph_log2) - 1u))) * (uint32_t)g.ph_cols + (uc >> g.ph_log2);
+  return ok ? rec : g.zero_rec;
+}
+static __global__ void k_scale_tab(const float2* __restrict__ tab, int P, float scale, float res, float2* __restrict__ out) {
+  const int p = blockIdx.x * blockDim.x + threadIdx.x;
+  if (p < P) out[p] = make_float2(TDR_FMUL(TDR_FMUL(tab[p].x, scale), res), TDR_FMUL(TDR_FMUL(tab[p].y, scale), res));
 }
 static __global__ void k_build_map16(const MapPixel* __restrict__ map, size_t n, int C, const float* __restrict__ cw,
                               uint4* __restrict__ out, int cols, int ph_log2, int ph_cols) {
@@ -266,18 +335,23 @@ static const int A_LBO = 2048 + 64;
 static const int A_TILE = 4224;
 
 // ph_log2 = 0: the plain row-major copy (particles); > 0: the phase-split copy for a lattice of centres
-static int build_map16(tdr_ctx* ctx, int ph_log2, const uint4** out, int* ph_cols) {
+static int build_map16(tdr_ctx* ctx, int ph_log2, const uint4** out, GatherGeom* geom) {
   const size_t L = (size_t)ctx->rows * ctx->cols;
-  *ph_cols = (ctx->cols + (1 << ph_log2) - 1) >> ph_log2;
+  const int ph_cols = (ctx->cols + (1 << ph_log2) - 1) >> ph_log2;
+  const size_t n_rec = ((size_t)ctx->rows << ph_log2) * (size_t)ph_cols;
+  TDR_REQUIRE(n_rec < (1ull << 31), TDR_EUNSUPPORTED, "map too large for the fp16 copy (%zu records)", n_rec);
+  geom->cols = ctx->cols; geom->ph_log2 = ph_log2; geom->ph_cols = ph_cols; geom->zero_rec = (uint32_t)n_rec;
+  geom->row_hi = (float)ctx->rows - 0.5f; geom->col_hi = (float)ctx->cols - 0.5f;
   tdr::DevBuf& buf = ph_log2 ? ctx->map16g : ctx->map16;
   *out = nullptr;
   const bool valid = ph_log2 ? ctx->map16g_log2 == ph_log2 : ctx->map16_valid;
   if (!valid) {
-    const size_t bytes = ph_log2 ? ((size_t)ctx->rows << ph_log2) * (size_t)*ph_cols * 32 : L * 32;
+    const size_t bytes = (n_rec + 1) * 32;                                    // + the all-zero record
     if (int e = buf.reserve(bytes)) return e;
     if (ph_log2) TDR_CUDA(cudaMemsetAsync(buf.p, 0, bytes, ctx->stream));     // padding records past the last column
+    else TDR_CUDA(cudaMemsetAsync(buf.as<unsigned char>() + n_rec * 32, 0, 32, ctx->stream));
     k_build_map16<<<(unsigned)((L + 255) / 256), 256, 0, ctx->stream>>>(ctx->map_px.as<MapPixel>(), L, ctx->C, ctx->d_cw.as<float>(),
-                                                                         buf.as<uint4>(), ctx->cols, ph_log2, *ph_cols);
+                                                                         buf.as<uint4>(), ctx->cols, ph_log2, ph_cols);
     count_launch(ctx);
     TDR_CUDA(cudaGetLastError());
     if (ph_log2) ctx->map16g_log2 = ph_log2; else ctx->map16_valid = true;
@@ -287,6 +361,15 @@ static int build_map16(tdr_ctx* ctx, int ph_log2, const uint4** out, int* ph_col
 }
 
 // refresh this translation unit's constant-memory mirror of the polar table when it is stale
+// grid launches (one scale for every centre) mirror (tab * scale) * res instead: two FMULs less per coordinate
+static int sync_const_tab_scaled(tdr_ctx* ctx, int P, float scale, float res) {
+  if (int e = ctx->tab_scaled.reserve((size_t)P * 8)) return e;
+  k_scale_tab<<<(P + 255) / 256, 256, 0, ctx->stream>>>(ctx->tab.as<float2>(), P, scale, res, ctx->tab_scaled.as<float2>());
+  count_launch(ctx);
+  TDR_CUDA(cudaMemcpyToSymbolAsync(c_tab, ctx->tab_scaled.p, (size_t)P * 8, 0, cudaMemcpyDeviceToDevice, ctx->stream));
+  g_tab_owner = nullptr;                      // the next particle launch mirrors the plain table again
+  return TDR_OK;
+}
 static int sync_const_tab(tdr_ctx* ctx, int P, uint64_t* seen_version) {
   if (g_tab_owner != ctx->tab.p || *seen_version != ctx->tab_version) {
     TDR_CUDA(cudaMemcpyToSymbolAsync(c_tab, ctx->tab.p, (size_t)P * 8, 0, cudaMemcpyDeviceToDevice, ctx->stream));

@@ -92,7 +92,7 @@ static __global__ void k_build_norm_op(const float* __restrict__ img, int C, int
 // the gather-GEMM
 // ------------------------------------------------------------------------------------------------
 struct MmaParams {
-  const uint4* map16; int rows, cols; float resolution; int ph_log2, ph_cols;
+  const uint4* map16; GatherGeom geom; float resolution; int tab_scaled;
   int n_theta, n_r, P; float res;
   const uint4* rings; const uint4* norm_op; int n_groups;
   const int* perm; long long n_work;
@@ -239,14 +239,13 @@ __global__ void __launch_bounds__(128 * T * R + 64, MmaCfg<T, R, ATM, G>::kCtasP
 #pragma unroll
         for (int g = 0; g < G; g++) {
           const int p = k * G + g;
-          rec[g][0] = make_uint4(0, 0, 0, 0); rec[g][1] = rec[g][0];
-          if (active) {
-            const float2 tb = c_tab[p];
-            const int r = lattice_index(tb.x, sc, sp.res, oy);
-            const int c = lattice_index(tb.y, sc, sp.res, ox);
-            if (r >= 0 && r < sp.rows && c >= 0 && c < sp.cols)
-              ldg256(map_bytes + map16_offset(r, c, sp.cols, sp.ph_log2, sp.ph_cols), rec[g][0], rec[g][1]);
-          }
+          const float2 tb = c_tab[p];
+          float vy, vx;
+          if (sp.tab_scaled) { vy = TDR_FADD(tb.x, oy); vx = TDR_FADD(tb.y, ox); }            // grid: the table holds (tab * scale) * res
+          else { vy = TDR_FADD(TDR_FMUL(TDR_FMUL(tb.x, sc), sp.res), oy); vx = TDR_FADD(TDR_FMUL(TDR_FMUL(tb.y, sc), sp.res), ox); }
+          uint32_t off = lattice_record(vy, vx, sp.geom);
+          if (!active) off = sp.geom.zero_rec;
+          ldg256(map_bytes + (size_t)off * 32, rec[g][0], rec[g][1]);
         }
       };
       auto store_stage = [&](int k, const uint4 (&rec)[G][2]) {
@@ -531,11 +530,11 @@ int score_mma(tdr_ctx* ctx, float res, bool grid_mode, long long n_items, float 
   if (int e = build_perm(ctx, grid_mode, n_items)) return e;
   tdr::Particles& pt = ctx->part[ctx->cur];
   static uint64_t tab_seen = 0;
-  if (int e = sync_const_tab(ctx, P, &tab_seen)) return e;
+  if (grid_mode) { if (int e = sync_const_tab_scaled(ctx, P, grid_scale, res)) return e; }
+  else if (int e = sync_const_tab(ctx, P, &tab_seen)) return e;
   MmaParams sp; memset(&sp, 0, sizeof(sp));
-  sp.ph_log2 = grid_mode ? ctx->grid_phase_log2 : 0;
-  if (int e = build_map16(ctx, sp.ph_log2, &sp.map16, &sp.ph_cols)) return e;
-  sp.rows = ctx->rows; sp.cols = ctx->cols; sp.resolution = ctx->resolution;
+  if (int e = build_map16(ctx, grid_mode ? ctx->grid_phase_log2 : 0, &sp.map16, &sp.geom)) return e;
+  sp.resolution = ctx->resolution; sp.tab_scaled = grid_mode ? 1 : 0;
   sp.n_theta = ctx->n_theta; sp.n_r = ctx->n_r; sp.P = P; sp.res = res;
   sp.rings = ctx->scan_op.as<uint4>(); sp.norm_op = d_norm_op; sp.n_groups = n_groups;
   sp.perm = ctx->perm.as<int>();

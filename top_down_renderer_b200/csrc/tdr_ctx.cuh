@@ -100,6 +100,7 @@ struct tdr_ctx {
   // that centres 2^k px apart read CONSECUTIVE records — 8 full 128-byte lines per warp load instead of one sector
   // out of each of 32 lines (measured 1.67 against 0.82 records/clk/SM, tools/gather_bench.cu patterns 7 / 4)
   tdr::DevBuf map16g;
+  tdr::DevBuf tab_scaled;    // polar table x scale x res of a grid launch (uniform scale): staged here, mirrored in constant memory
   int map16g_log2 = -1;      // layout of map16g (-1: not built)
   int grid_phase_log2 = 0;   // x stride of the resident lattice of centres, if it is 2, 4 or 8 px (else 0)
   tdr::DevBuf scan_op;       // P_pad x N x 32 B
