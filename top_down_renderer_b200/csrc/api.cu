@@ -622,6 +622,7 @@ int tdr_grid_costs(tdr_ctx* ctx, const float* centers_xy, int64_t n, float scale
   if (centers_xy) {
     if (int e = ctx->grid_centers.reserve((size_t)n * 8)) return e;
     TDR_CUDA(cudaMemcpyAsync(ctx->grid_centers.p, centers_xy, (size_t)n * 8, cudaMemcpyHostToDevice, ctx->stream));
+    ctx->perm_grid_n = -1;
     // a lattice with an x stride of 2, 4 or 8 px gathers from the phase-split map copy (a layout hint only: any
     // value gives the same results); judged on the first pairs of centres
     int votes[4] = {0, 0, 0, 0};

@@ -380,6 +380,8 @@ static int sync_const_tab(tdr_ctx* ctx, int P, uint64_t* seen_version) {
 
 // spatial binning of the hypotheses -> ctx->perm (counting sort by super-tile, pixel row, column segment)
 static int build_perm(tdr_ctx* ctx, bool grid_mode, long long n_items) {
+  if (grid_mode && ctx->perm_grid_n == n_items) return TDR_OK;       // resident centres, same map: the order still holds
+  ctx->perm_grid_n = -1;
   tdr::Particles& pt = ctx->part[ctx->cur];
   BinParams bp; memset(&bp, 0, sizeof(bp));
   if (grid_mode) bp.centers = ctx->grid_centers.as<float>();
@@ -415,6 +417,7 @@ static int build_perm(tdr_ctx* ctx, bool grid_mode, long long n_items) {
   k_bin_scatter<<<blocks, 256, 0, ctx->stream>>>(bp, d_counts, ctx->perm.as<int>());
   count_launch(ctx, 5);
   TDR_CUDA(cudaGetLastError());
+  if (grid_mode) ctx->perm_grid_n = n_items;
   return TDR_OK;
 }
 
