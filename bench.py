@@ -349,7 +349,8 @@ def run_gpu(args, wl):
         traffic = None
         try:
             with open(os.path.join(ROOT, "profiles", "score_kernel_traffic.json")) as f:
-                traffic = json.load(f).get(args.workload, {}).get("dram_bytes_per_launch")
+                t_ = json.load(f).get(args.workload, {})
+                traffic = int(t_["captured_dram_bytes"] * n / t_["captured_particles"])      # per launch of n particles
         except Exception:
             pass
         out = {"metric": "particle_scores_per_sec", "value": value, "unit": "scores/s", "n_gpus": world,
@@ -369,7 +370,7 @@ def run_gpu(args, wl):
                        "p50_ms": 1e3 * float(np.median(e2e_t)), "timer": "host wall clock around set_points+step+pose"},
                "gpu_launches": int(launches),
                "wall_s_timed_region": t_wall,
-               "roofline": {"bound": "hbm", "kernel": "k_score_mma (tcgen05 gather-GEMM)" if wl["shifts"] > 1 else "k_score_track",
+               "roofline": {"bound": "hbm", "kernel": "k_score_mma_list (tcgen05 gather-GEMM, operands in tensor memory)" if wl["shifts"] > 1 else "k_score_track",
                             "achieved": achieved, "peak": peak, "unit": "GB/s", "frac": achieved / peak,
                             "traffic": traffic, "peak_source": peak_src,
                             "algorithmic_bytes_per_launch": n * b_score(C), "kernel_ms": score_ms}}
@@ -393,6 +394,16 @@ def run_gpu(args, wl):
     if world > 1:
         dist.barrier()
         dist.destroy_process_group()
+
+
+def grid_traffic(n_local):
+    """DRAM bytes of the grid score kernel per launch, from the committed ncu capture (scaled to this rank's share)"""
+    try:
+        with open(os.path.join(ROOT, "profiles", "score_kernel_traffic.json")) as f:
+            g = json.load(f)["grid"]
+        return int(g["captured_dram_bytes"] * n_local / g["captured_particles"])
+    except Exception:
+        return None
 
 
 def run_grid(args, wl):
@@ -525,8 +536,9 @@ def run_grid(args, wl):
                        "ms_per_step": 1e3 * e2e_total / args.steps,
                        "timer": "host wall clock around set_points+render+grid(+all-gather)+arg-min"},
                "gpu_launches": int(launches),
-               "roofline": {"bound": "hbm", "kernel": "k_score_mma (tcgen05 gather-GEMM)", "achieved": achieved, "peak": peak,
-                            "unit": "GB/s", "frac": achieved / peak, "traffic": None, "peak_source": peak_src,
+               "roofline": {"bound": "hbm", "kernel": "k_score_mma (tcgen05 gather-GEMM, sliding scan ring, operands in tensor memory)",
+                            "achieved": achieved, "peak": peak, "unit": "GB/s", "frac": achieved / peak,
+                            "traffic": grid_traffic(n_local), "peak_source": peak_src,
                             "algorithmic_bytes_per_launch": n_local * b_score(C), "kernel_ms": k_ms},
                "cpu_baseline": None}
         emit(out)
