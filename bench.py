@@ -457,15 +457,28 @@ def run_grid(args, wl):
     ctx.sync()
     ctx.profile_enable(True)
 
+    key_t = gather.key_tensor(torch, dev) if fused else None
+    checked = [False]
+
     def one_step():
         with torch.cuda.stream(stream):
             ctx.scan_render_polar(res, float(ANG_RES), N_THETA, N_R, want=False)
             ctx.grid_run_resident(n_local, 2.0, res, shifts)
             if fused:
-                dist.all_reduce(tiny)                                      # barrier: every rank's kernel (and its peer stores) is done
+                # ONE collective: MIN all-reduce of the packed (cost, global flat index) key the kernel folded — it is
+                # also the barrier after which every rank's array holds every cost (peer stores of all ranks done)
+                dist.all_reduce(key_t, op=dist.ReduceOp.MIN)
+                out = ctx.grid_key_decode(int(key_t.item()))               # D2H of the key: synchronises
             elif world > 1:
                 dist.all_gather_into_tensor(recv, send)
-            return ctx.grid_best_dev(full_ptr, full_numel)                 # D2H of (cost, index): synchronises
+                out = ctx.grid_best_dev(full_ptr, full_numel)              # D2H of (cost, index): synchronises
+            else:
+                out = ctx.grid_key_decode(ctx.grid_best_key())             # folded by the score kernel; D2H synchronises
+            if not checked[0]:                                             # first (warm-up) step: same answer as a re-scan
+                checked[0] = True
+                ref = ctx.grid_best_dev(full_ptr, full_numel)
+                assert ref == out, (ref, out)
+            return out
 
     def barrier():
         if world > 1:

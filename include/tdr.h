@@ -184,6 +184,15 @@ int tdr_grid_best(tdr_ctx* ctx, float* best_cost, int64_t* best_index);
  * (the all-gather output; first index wins on ties, NaN never wins) */
 int tdr_grid_set_costs_buffer(tdr_ctx* ctx, void* dev_costs, int64_t capacity_floats);
 int tdr_grid_best_dev(tdr_ctx* ctx, const void* dev_costs, int64_t n, float* best_cost, int64_t* best_index);
+/* The tensor-core grid kernel also folds (min cost, first flat index) of the costs IT computed into one device-resident
+ * 64-bit key (order-preserving cost bits << 32 | flat index; all ones = nothing finite) — the same answer as
+ * tdr_grid_best without re-reading n x n_shifts costs.  Multi-GPU: the index is global (row offset of
+ * tdr_grid_peer_set applied), so ONE MIN all-reduce of the key (buffer TDR_BUF_GRID_BEST_KEY, an int64 on the context's
+ * device) is both the cross-rank barrier of the fused all-gather and the reduction.  tdr_grid_best_key copies the key
+ * to the host (synchronises) and tdr_grid_key_decode unpacks a key.  TDR_ESTATE if the last grid did not run on the
+ * tensor-core kernel (CUDA-core fallback): use tdr_grid_best. */
+int tdr_grid_best_key(tdr_ctx* ctx, uint64_t* key);
+int tdr_grid_key_decode(uint64_t key, float* best_cost, int64_t* best_index);
 /* ---- fused weight all-gather over NVLink peer memory (cfg4: the exhaustive grid sharded over the GPUs of a box).
  * Every rank allocates the FULL cost array (n_total x n_shifts floats) with tdr_grid_peer_alloc, exports it as a
  * CUDA IPC handle, opens the other ranks' handles (tdr_grid_peer_open) and registers all mapped pointers in rank
@@ -200,7 +209,7 @@ int tdr_grid_peer_clear(tdr_ctx* ctx);   /* forgets the registration and closes 
 /* device pointers of resident buffers for collectives issued by the host layer (NCCL through
  * torch.distributed): weights (n floats) / grid costs (n*n_shifts floats) */
 int tdr_dev_ptr(tdr_ctx* ctx, int which, void** ptr, int64_t* n_elems);
-enum { TDR_BUF_WEIGHTS = 0, TDR_BUF_GRID_COSTS = 1, TDR_BUF_STATES_SOA = 2, TDR_BUF_SCAN_IMAGES = 3 };
+enum { TDR_BUF_WEIGHTS = 0, TDR_BUF_GRID_COSTS = 1, TDR_BUF_STATES_SOA = 2, TDR_BUF_SCAN_IMAGES = 3, TDR_BUF_GRID_BEST_KEY = 4 };
 /* ---- multi-GPU: particle shards, map replicated.  The collective itself (ONE all-gather per step) is
  * issued by the host layer on tdr_stream() — torch.distributed / NCCL; the library packs and consumes.
  * Shard block = TDR_SHARD_ROWS rows of n_local floats: weight, init_x, init_y, dx, dy, theta, scale,

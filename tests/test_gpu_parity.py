@@ -534,6 +534,8 @@ def test_mma_lattice_grid_uses_phase_split_map(world, mma_ctx, stride, n_shifts)
     want = orc.cost_grid(centers, 2.0, world.fp, world.layers, world.mask, 1.0, world.tab, N_THETA, N_R, world.scan, 4.0, shifts)
     e = rel_err(got, want)
     assert np.isfinite(e).all() and e.max() <= WEIGHT_RTOL, e.max()
+    # the kernel's folded (min cost, first flat index) key == a re-scan of the cost array
+    assert mma_ctx.grid_key_decode(mma_ctx.grid_best_key()) == mma_ctx.grid_best()
     os.environ["TDR_GRID_PHASE_LOG2"] = "0"
     try:
         plain = mma_ctx.grid_costs(centers, 2.0, 4.0, shifts)
@@ -664,6 +666,10 @@ def _fused_rank(rank, world_size, port, q):
         dist.barrier()                                                         # every rank's kernel has finished
         full = c.copy_from_device(g.full_ptr, g.numel()).reshape(n_total, len(shifts))
         best = c.grid_best_dev(g.full_ptr, g.numel())
+        import torch
+        kt = g.key_tensor(torch, "cuda:0").cpu()                               # gloo group: reduce the key on the host
+        dist.all_reduce(kt, op=dist.ReduceOp.MIN)                             # the fused reduction: global (cost, flat index)
+        assert c.grid_key_decode(int(kt.item())) == best, (c.grid_key_decode(int(kt.item())), best)
         q.put((rank, full, best))
         dist.barrier()
         g.close()

@@ -2,11 +2,6 @@ grid() { timeout 300 python bench.py --workload grid --steps 10 --warmup 3 2>gpu
 import json,sys
 for l in sys.stdin:
     if l.startswith('{'):
-        d=json.loads(l); print('grid', d['ms_per_step'], d['stage_ms'], d['value'], d['best'], d.get('e2e'))"; tail -3 gpurun_out/err.txt | cut -c1-300; }
+        d=json.loads(l); print('grid', d['ms_per_step'], d['stage_ms'], d['value'], d['best'], d['e2e']['ms_per_step'])"; tail -3 gpurun_out/err.txt | cut -c1-300; }
+timeout 600 python -m pytest tests -m gpu -q -x -k "grid or ring or mma or shift or peer" 2>&1 | tail -3
 echo "grid"; grid
-timeout 300 python -m pytest tests -m gpu -q -x -k "grid or ring or mma or shift or peer" 2>&1 | tail -3
-timeout 300 python bench.py --workload tracking --steps 200 --warmup 10 --no-cpu 2>gpurun_out/err.txt | python -c "
-import json,sys
-for l in sys.stdin:
-    if l.startswith('{'):
-        d=json.loads(l); print('tracking', d['ms_per_step'], d['p50_update_ms'], d['stage_ms'], d['gpu_launches'], d['e2e'])"

@@ -346,6 +346,18 @@ class Context:
         check(self._lib.tdr_grid_best(self._h, C.byref(c), C.byref(i)))
         return c.value, i.value
 
+    def grid_best_key(self):
+        """packed (min cost, first flat index) of the last tensor-core grid launch (synchronises)"""
+        k = C.c_uint64()
+        check(self._lib.tdr_grid_best_key(self._h, C.byref(k)))
+        return k.value
+
+    def grid_key_decode(self, key):
+        c = C.c_float()
+        i = C.c_int64()
+        check(self._lib.tdr_grid_key_decode(C.c_uint64(key & 0xFFFFFFFFFFFFFFFF), C.byref(c), C.byref(i)))
+        return c.value, i.value
+
     def dev_ptr(self, which):
         p = C.c_void_p()
         n = C.c_int64()

@@ -148,7 +148,7 @@ void tdr_destroy(tdr_ctx* c) {
   tdr::DevBuf* bufs[] = {&c->map_px, &c->seedbits, &c->edt_g, &c->scratch, &c->scratch2, &c->tab, &c->pts, &c->lut,
                          &c->scan_img, &c->scan_pack, &c->hist, &c->d_search_thetas, &c->d_search_shifts, &c->weights,
                          &c->prefix, &c->idx, &c->scal, &c->pose_tmp, &c->grid_centers, &c->grid_costs,
-                         &c->grid_shifts, &c->d_cw, &c->map16, &c->map16g, &c->tab_scaled, &c->seq_ws, &c->scan_op, &c->bin_counts, &c->perm};
+                         &c->grid_shifts, &c->d_cw, &c->map16, &c->map16g, &c->tab_scaled, &c->grid_key, &c->seq_ws, &c->scan_op, &c->bin_counts, &c->perm};
   for (auto* b : bufs) b->release();
   for (void* p : c->grid_opened) cudaIpcCloseMemHandle(p);
   c->grid_full.release();
@@ -679,6 +679,24 @@ int tdr_grid_best_dev(tdr_ctx* ctx, const void* dev_costs, int64_t n, float* bes
   return e;
 }
 
+int tdr_grid_best_key(tdr_ctx* ctx, uint64_t* key) {
+  CTX_CHECK(ctx);
+  TDR_REQUIRE(key, TDR_EINVAL, "null argument");
+  TDR_REQUIRE(ctx->grid_key_valid, TDR_ESTATE, "the last grid did not run on the tensor-core kernel: use tdr_grid_best");
+  TDR_CUDA(cudaMemcpyAsync(key, ctx->grid_key.p, 8, cudaMemcpyDeviceToHost, ctx->stream));
+  TDR_CUDA(cudaStreamSynchronize(ctx->stream));
+  return TDR_OK;
+}
+int tdr_grid_key_decode(uint64_t key, float* best_cost, int64_t* best_index) {
+  if (key == ~0ull) { if (best_cost) *best_cost = NAN; if (best_index) *best_index = -1; return TDR_OK; }
+  uint32_t u = (uint32_t)(key >> 32);
+  u = (u & 0x80000000u) ? (u & 0x7fffffffu) : ~u;
+  float v; memcpy(&v, &u, 4);
+  if (best_cost) *best_cost = v;
+  if (best_index) *best_index = (int64_t)(key & 0xffffffffull);
+  return TDR_OK;
+}
+
 int tdr_grid_peer_alloc(tdr_ctx* ctx, int64_t n_floats, void** dev_ptr, uint8_t handle[TDR_IPC_HANDLE_BYTES]) {
   CTX_CHECK(ctx);
   static_assert(sizeof(cudaIpcMemHandle_t) == TDR_IPC_HANDLE_BYTES, "IPC handle size");
@@ -720,6 +738,7 @@ int tdr_dev_ptr(tdr_ctx* ctx, int which, void** ptr, int64_t* n_elems) {
   switch (which) {
     case TDR_BUF_WEIGHTS: *ptr = ctx->weights.p; if (n_elems) *n_elems = ctx->n_weights; break;
     case TDR_BUF_GRID_COSTS: *ptr = grid_costs_ptr(ctx); if (n_elems) *n_elems = ctx->grid_n * ctx->grid_shifts_n; break;
+    case TDR_BUF_GRID_BEST_KEY: if (int e = ctx->grid_key.reserve(8)) return e; *ptr = ctx->grid_key.p; if (n_elems) *n_elems = 1; break;
     case TDR_BUF_SCAN_IMAGES: *ptr = ctx->scan_img.p; if (n_elems) *n_elems = (int64_t)ctx->scan_C * ctx->scan_theta * ctx->scan_r; break;
     default: tdr::set_error("unknown buffer id %d", which); return TDR_EINVAL;
   }

@@ -390,6 +390,7 @@ int score_grid(tdr_ctx* ctx, long long n, float scale, float res) {
   sp.init_x = sp.init_y = sp.dx = sp.dy = nullptr; sp.theta = nullptr; sp.scale = nullptr; sp.have_init = nullptr; sp.weights = nullptr;
   const int P = sp.P;
   bool used = false;
+  ctx->grid_key_valid = false;
   if (ctx->score_impl == 2 || ctx->grid_n_peers || (ctx->score_impl == 0 && n >= 4096)) {
     if (ctx->mma_kernel == 1 && !ctx->grid_n_peers) { if (int e = score_mma_list(ctx, res, true, n, scale, sp.shifts, sp.n_shifts, &used)) return e; }
     if (!used) { if (int e = score_mma(ctx, res, true, n, scale, sp.shifts, ctx->grid_shifts_host.data(), sp.n_shifts, &used)) return e; }

@@ -104,6 +104,7 @@ struct MmaParams {
   const float* centers; float grid_scale; float* costs;
   // fused all-gather: every cost is stored into all ranks' full arrays (NVLink peer mappings) at this rank's rows
   float* cost_peers[TDR_MAX_PEERS]; int n_cost_peers; long long cost_row0;
+  unsigned long long* grid_key;     // grid mode: (min cost, first global flat index) over everything this launch computes
   int dbg_nostore;
   int identity_shifts;      // shifts[k] == k for all k and n_shifts % 4 == 0: vector stores of the cost rows
 };
@@ -113,6 +114,7 @@ static const int RING_SLOT_BYTES = 2 * MAX_RING_ROWS * 16;    // 2 K chunks
 static const int NB2 = 4, B2_BYTES = 2 * RING_N * 16;         // tot-block slots (one block per 16 cells)
 static const int NA2 = 3, A2_TILE = 4096;                     // known-flag operand buffers (128 rows x 16 cells)
 static const int CELLS_PER_GROUP = 16;
+static const int OUT_STRIDE = RING_N;              // floats per staged cost row (16-byte multiple, >= n_theta)
 // T = 128-hypothesis tiles per CTA; R = gather threads per hypothesis row (the R threads of a row take turns
 // stage by stage, so the loads in flight per SM grow without growing the set of hypotheses — and their map
 // footprint — that are in flight together)
@@ -130,7 +132,10 @@ template <int T, int R, bool ATM, int G> struct MmaCfg {
   static const int kCtasPerSm = kByTmem < kByRegs ? kByTmem : kByRegs;
   static const int kStageBytes = ATM ? 0 : G * T * A_TILE;
   static const int kA2Bytes = ATM ? 0 : NA2 * T * A2_TILE;
-  static const int kFixed = 2 * RING_SLOT_BYTES + NB2 * B2_BYTES + kA2Bytes + 128 * T * R * 4 + 1024 + 4 * T * 32 * 17 * 4;
+  // tensor-memory path: the epilogue stages every cost row in shared memory (OUT_STRIDE floats per row) and hands it
+  // to the async proxy (cp.async.bulk shared -> global / peer) — the SM goes on with the next tile while rows drain
+  static const int kOutBytes = ATM ? 128 * T * OUT_STRIDE * 4 : 0;
+  static const int kFixed = 2 * RING_SLOT_BYTES + NB2 * B2_BYTES + kA2Bytes + 128 * T * R * 4 + 1024 + 4 * T * 32 * 17 * 4 + kOutBytes;
   static const int kBudget = (216 * 1024) / kCtasPerSm - 1280 - kFixed;
   // every gather thread keeps two of ITS stages in flight, i.e. spans 2R stages: leave twice that as slack
   static const int kStagesMax = 4 * R < 8 ? 8 : 4 * R;
@@ -160,6 +165,7 @@ __global__ void __launch_bounds__(128 * T * R + 64, MmaCfg<T, R, ATM, G>::kCtasP
   uint32_t* s_tmem = reinterpret_cast<uint32_t*>(bars + 2 * NS + 5 + 2 * NB2);
   short* s_inv = reinterpret_cast<short*>(s_tmem + 2);                  // [RING_N] shift -> first position in the list
   float* s_tile = reinterpret_cast<float*>(s_inv + RING_N + 8);         // [4T warps][32][17] epilogue transpose tiles
+  float* s_out = s_tile + 4 * T * 32 * 17;                              // [128 T][OUT_STRIDE] staged cost rows (ATM)
   const int tid = threadIdx.x, warp = tid >> 5, lane = tid & 31;
   const uint32_t bar_full = smem_u32(bars), bar_empty = smem_u32(bars + NS);
   const uint32_t bar_rfull = smem_u32(bars + 2 * NS), bar_rempty = smem_u32(bars + 2 * NS + 2), bar_accum = smem_u32(bars + 2 * NS + 4);
@@ -310,6 +316,8 @@ __global__ void __launch_bounds__(128 * T * R + 64, MmaCfg<T, R, ATM, G>::kCtasP
       float best = 3.402823466e+38f;                                                         // :193-204
       int best_k = 0x7fffffff;
       uint32_t vc[16], vn[16];
+      const bool async_rows = ATM && sp.identity_shifts && (sp.costs || sp.n_cost_peers) && !sp.dbg_nostore;   // CTA-uniform
+      if (async_rows) bulk_wait_read();          // the previous tile's stores have read this thread's staging row
 #pragma unroll 1
       for (int ch = 0; ch * 16 < n_theta; ch++) {
         tmem_ld16(trow + (uint32_t)(ch * 16), vc);
@@ -327,7 +335,13 @@ __global__ void __launch_bounds__(128 * T * R + 64, MmaCfg<T, R, ATM, G>::kCtasP
         }
         if ((sp.costs || sp.n_cost_peers) && !sp.dbg_nostore) {          // warp-uniform
           const int n_dst = sp.n_cost_peers ? sp.n_cost_peers : 1;
-          const long long row = (sp.n_cost_peers ? sp.cost_row0 + i : i) * sp.n_shifts;
+          const long long grow = (sp.n_cost_peers ? sp.cost_row0 + i : i) * sp.n_shifts;
+          if (ATM && sp.identity_shifts) {
+            // all shifts in order: column s is list position s.  Stage this row; the bulk stores go out after the loop.
+            float* mine = s_out + (size_t)row * OUT_STRIDE + ch * 16;
+#pragma unroll
+            for (int q = 0; q < 4; q++) *reinterpret_cast<float4*>(mine + 4 * q) = make_float4(cst[4 * q], cst[4 * q + 1], cst[4 * q + 2], cst[4 * q + 3]);
+          } else
           if (sp.identity_shifts) {
             // all shifts in order: column s is list position s.  The warp's 32 rows x 16 columns go through a
             // shared-memory tile so that four lanes write one row's 64 contiguous bytes (8 rows per store
@@ -359,11 +373,35 @@ __global__ void __launch_bounds__(128 * T * R + 64, MmaCfg<T, R, ATM, G>::kCtasP
               const int k = s < n_theta ? s_inv[s] : -1;
               if (k >= 0 && i >= 0) {
 #pragma unroll 1
-                for (int d = 0; d < n_dst; d++) (sp.n_cost_peers ? sp.cost_peers[d] : sp.costs)[row + k] = cst[j];
+                for (int d = 0; d < n_dst; d++) (sp.n_cost_peers ? sp.cost_peers[d] : sp.costs)[grow + k] = cst[j];
               }
             }
           }
         }
+      }
+      if (async_rows) {
+        // one bulk store of the whole row per destination (own array and every peer's, NVLink): issued here, executed
+        // by the async proxy while this CTA gathers the next tile
+        fence_proxy_async();
+        if (i >= 0) {
+          const long long at = (sp.n_cost_peers ? sp.cost_row0 + i : i) * sp.n_shifts;
+          const uint32_t src = smem_u32(s_out + (size_t)row * OUT_STRIDE);
+          const int n_dst = sp.n_cost_peers ? sp.n_cost_peers : 1;
+#pragma unroll 1
+          for (int d = 0; d < n_dst; d++) bulk_s2g((sp.n_cost_peers ? sp.cost_peers[d] : sp.costs) + at, src, (uint32_t)sp.n_shifts * 4u);
+        }
+        bulk_commit();
+      }
+      if (sp.grid_key) {
+        // fold this row's first minimum into the launch-wide (cost, flat index) key — k_grid_best's format
+        unsigned long long key = ~0ull;
+        if (i >= 0 && best_k != 0x7fffffff) {
+          uint32_t u = __float_as_uint(best);
+          u = (u & 0x80000000u) ? ~u : (u | 0x80000000u);
+          key = ((unsigned long long)u << 32) | (unsigned long long)(uint32_t)((sp.cost_row0 + i) * sp.n_shifts + best_k);
+        }
+        for (int o = 16; o > 0; o >>= 1) { const unsigned long long t = __shfl_xor_sync(0xffffffffu, key, o); if (t < key) key = t; }
+        if (lane == 0 && key != ~0ull) atomicMin(sp.grid_key, key);
       }
       if (i >= 0 && !sp.centers) {
         if (gated) sp.weights[i] = 0.f;
@@ -375,6 +413,7 @@ __global__ void __launch_bounds__(128 * T * R + 64, MmaCfg<T, R, ATM, G>::kCtasP
       }
       tc_fence_before();           // TMEM reads are done before the next batch's first full-barrier arrive
     }
+    if (ATM) bulk_wait_all();      // this thread's row stores have landed (own memory and peers) before the kernel ends
   } else if (warp == GW) {
     // =========================== scan-ring / tot-block loader ===========================
     // whole warp, warp-uniform control flow; the elected lane issues the copies.  Order = the order in which the MMA
@@ -543,7 +582,12 @@ int score_mma(tdr_ctx* ctx, float res, bool grid_mode, long long n_items, float 
   if (grid_mode) {
     sp.n_work = n_items; sp.centers = ctx->grid_centers.as<float>(); sp.grid_scale = grid_scale;
     sp.costs = grid_costs_ptr(ctx);
-    sp.n_cost_peers = ctx->grid_n_peers; sp.cost_row0 = ctx->grid_peer_row0;
+    sp.n_cost_peers = ctx->grid_n_peers; sp.cost_row0 = ctx->grid_n_peers ? ctx->grid_peer_row0 : 0;
+    if ((long long)(sp.cost_row0 + n_items) * n_shifts < (1ll << 32)) {
+      if (int e = ctx->grid_key.reserve(8)) return e;
+      TDR_CUDA(cudaMemsetAsync(ctx->grid_key.p, 0xff, 8, ctx->stream));
+      sp.grid_key = ctx->grid_key.as<unsigned long long>();
+    }
     sp.identity_shifts = (n_shifts % 4 == 0) ? 1 : 0;
     for (int k = 0; k < n_shifts; k++) if (host_shifts[k] != k) sp.identity_shifts = 0;
     for (int d = 0; d < ctx->grid_n_peers; d++) sp.cost_peers[d] = ctx->grid_peers[d];
@@ -586,6 +630,7 @@ int score_mma(tdr_ctx* ctx, float res, bool grid_mode, long long n_items, float 
 #undef TDR_LAUNCH_MMA
   count_launch(ctx);
   TDR_CUDA(cudaGetLastError());
+  ctx->grid_key_valid = grid_mode && sp.grid_key != nullptr;
   *used = true;
   return TDR_OK;
 }

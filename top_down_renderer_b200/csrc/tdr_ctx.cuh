@@ -105,6 +105,8 @@ struct tdr_ctx {
   int grid_phase_log2 = 0;   // x stride of the resident lattice of centres, if it is 2, 4 or 8 px (else 0)
   tdr::DevBuf scan_op;       // P_pad x N x 32 B
   tdr::DevBuf bin_counts, perm;
+  tdr::DevBuf grid_key;      // 8 bytes: (min cost, first flat index) of the last tensor-core grid launch, packed
+  bool grid_key_valid = false;
   int64_t perm_grid_n = -1;  // perm holds the binning of the RESIDENT grid centres (n of them); -1: it does not
   int score_impl = 0;        // 0 auto, 1 CUDA cores only, 2 tensor cores whenever usable
   int mma_tiles = 2;         // list kernel: 128-hypothesis tiles per CTA (tuning: TDR_MMA_TILES); two tiles share one

@@ -93,6 +93,16 @@ class FusedGridGather:
     def numel(self):
         return self.n_total * self.n_shifts
 
+    def key_tensor(self, torch, device):
+        """the context's 8-byte (min cost, first global flat index) key as a one-element int64 torch tensor (an alias,
+        no copy): `dist.all_reduce(t, op=MIN)` on the context stream is the cross-rank barrier of the fused all-gather
+        AND the arg-min reduction; decode the result with Context.grid_key_decode."""
+        ptr, _ = self.ctx.dev_ptr(4)                  # TDR_BUF_GRID_BEST_KEY
+
+        class _Alias:
+            __cuda_array_interface__ = {"shape": (1,), "typestr": "<i8", "data": (ptr, False), "version": 2}
+        return torch.as_tensor(_Alias(), device=device)
+
     def close(self):
         self.ctx.grid_peer_clear()
 
