@@ -146,6 +146,26 @@ int tdr_pf_count(tdr_ctx* ctx, int64_t* n);
  * 28 B/particle H2D. */
 int tdr_pf_checkpoint(tdr_ctx* ctx);
 int tdr_pf_restore(tdr_ctx* ctx);
+/* SURVEY 8f rank 1 — ParticleFilter::propagate (particle_filter.cpp:86-92) / StateParticle::propagate
+ * (state_particle.cpp:57-78) on the resident particle set: rotate trans by each particle's theta, add it and the
+ * motion noise, jitter the scale unless scale_freeze, record last_dist.  pos_cov / theta_cov are FilterParams'
+ * (state_particle.h:19-38).  The reference draws the noise from one shared std::mt19937 in particle order; here
+ *   tdr_pf_propagate      takes the STANDARD normal variates z[n][4] = (theta, dx, dy, scale) from the caller — what
+ *                         libstdc++'s normal_distribution<float> yields before `* stddev + mean`; drawn with the
+ *                         reference's own calls they reproduce its states (the parity path; host buffer),
+ *   tdr_pf_propagate_dev  the same with z already on the device,
+ *   tdr_pf_propagate_rng  draws them on the device (Philox-4x32-10 keyed by (seed, step), counter = particle index,
+ *                         Box-Muller): no host traffic at all; z_out (host, n*4 floats, may be NULL) returns the
+ *                         variates used (synchronises) so a run can be replayed through tdr_pf_propagate.
+ * Asynchronous on the context stream unless a host output is requested. */
+int tdr_pf_propagate(tdr_ctx* ctx, float trans_x, float trans_y, float omega, int scale_freeze, float pos_cov, float theta_cov,
+                     const float* z, int64_t n);
+int tdr_pf_propagate_dev(tdr_ctx* ctx, float trans_x, float trans_y, float omega, int scale_freeze, float pos_cov,
+                         float theta_cov, const void* dev_z, int64_t n);
+int tdr_pf_propagate_rng(tdr_ctx* ctx, float trans_x, float trans_y, float omega, int scale_freeze, float pos_cov,
+                         float theta_cov, uint64_t seed, uint64_t step, float* z_out);
+/* last_dist_ of every resident particle (StateParticle::lastDist, state_particle.cpp:108-110) */
+int tdr_pf_get_last_dist(tdr_ctx* ctx, float* last_dist, int64_t n);
 /* a9+a10: StateParticle::computeWeight for every particle (the for_each(par) region,
  * particle_filter.cpp:104-105) against the resident polar scan images.  Updates theta /
  * have_init on the device like the reference.  weights_out may be NULL. */

@@ -153,3 +153,30 @@ def resample_literal(w, u, M):
             j += 1
         idx[i] = j
     return idx
+
+
+def propagate_with_z(states, tx, ty, omega, scale_freeze, pos_cov, theta_cov, z):
+    """StateParticle::propagate (state_particle.cpp:57-78) with the noise given as standard normal variates
+    z[n, 4] = (theta, dx, dy, scale): every draw is `z * stddev + mean` in fp32, as libstdc++ forms it.  Vectorised
+    float32 numpy; cos / sin through float64 and rounded (glibc's cosf / sinf agree up to rare 1-ulp cases)."""
+    f = np.float32
+    st = states.copy()
+    z = np.asarray(z, dtype=f).reshape(-1, 4)
+    th = st["theta"].astype(f)
+    c, s = np.cos(th.astype(np.float64)).astype(f), np.sin(th.astype(np.float64)).astype(f)
+    gx = c * f(tx) - s * f(ty)
+    gy = s * f(tx) + c * f(ty)
+    lx, ly = st["dx_m"].astype(f), st["dy_m"].astype(f)
+    dx, dy = lx + gx, ly + gy
+    dist = np.sqrt(gx * gx + gy * gy)
+    sd_pos, sd_th = f(pos_cov) * dist, f(theta_cov) * dist
+    st["theta"] = th + ((z[:, 0] * sd_th + f(0)) + f(omega))
+    dx = dx + (z[:, 1] * sd_pos + f(0))
+    dy = dy + (z[:, 2] * sd_pos + f(0))
+    st["dx_m"], st["dy_m"] = dx, dy
+    if not scale_freeze:
+        with np.errstate(divide="ignore"):
+            sd_sc = np.minimum(2.0 / dist.astype(np.float64), 0.02).astype(f)
+        st["scale"] = st["scale"].astype(f) * (z[:, 3] * sd_sc + f(1))
+    mx, my = lx - dx, ly - dy
+    return st, np.sqrt(mx * mx + my * my)

@@ -282,3 +282,17 @@ def refine_bin(xy, cls, res, cx, cy, width, height, C_):
     lib().orc_refine_bin(_p(xy, c_float_p), _p(cls, c_int_p), C.c_long(len(cls)), C.c_float(res), C.c_float(cx),
                          C.c_float(cy), width, height, C_, _p(out, c_u8_p))
     return out
+
+
+def propagate(states, tx, ty, omega, scale_freeze, pos_cov, theta_cov, seed):
+    """StateParticle::propagate over a particle set with ONE shared mt19937(seed), in particle order
+    (state_particle.cpp:57-78, particle_filter.cpp:86-92).  Returns (new states, last_dist, z) where z[n, 4] are the
+    standard normal variates behind the draws (theta, dx, dy, scale)."""
+    st = np.ascontiguousarray(states.copy())
+    n = len(st)
+    last = np.empty(n, dtype=np.float32)
+    z = np.empty((n, 4), dtype=np.float32)
+    lib().orc_propagate(st.ctypes.data_as(C.c_void_p), _p(last, c_float_p), C.c_long(n), C.c_float(tx), C.c_float(ty),
+                        C.c_float(omega), int(bool(scale_freeze)), C.c_float(pos_cov), C.c_float(theta_cov),
+                        C.c_uint32(seed), _p(z, c_float_p))
+    return st, last, z

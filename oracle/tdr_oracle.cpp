@@ -691,4 +691,43 @@ ORC_API void orc_refine_bin(const float* xy, const int* cls, long n, float res, 
   }
 }
 
+// -----------------------------------------------------------------------------
+// SURVEY 8f rank 1  propagate   src/state_particle.cpp:57-78, src/particle_filter.cpp:86-92
+// -----------------------------------------------------------------------------
+// Literal restatement: one shared std::mt19937 walked in particle order, fresh normal_distribution<float> objects per
+// particle exactly as the reference constructs them (theta_dist called once, disp_dist twice — the second call
+// returns the polar method's saved value — scale_dist once unless frozen).  Eigen::Rotation2D<float>(theta) * trans
+// is [c -s; s c] * trans with std::cos / std::sin on float; Vector2f::norm() is sqrt(x*x + y*y).
+// z_out (may be NULL): the STANDARD normal variate behind every draw, 4 per particle (theta, dx, dy, scale; scale
+// = 0 when frozen), i.e. (draw - mean) / stddev as libstdc++ computes it before `* stddev + mean` — recovered by
+// running a second engine in lock step through N(0,1) objects, which consume the identical uniforms.
+ORC_API void orc_propagate(OrcState* st, float* last_dist, long n, float tx, float ty, float omega, int scale_freeze,
+                           float pos_cov, float theta_cov, uint32_t seed, float* z_out) {
+  std::mt19937 gen(seed), gen_z(seed);
+  for (long i = 0; i < n; i++) {
+    OrcState& s = st[i];
+    const float c = std::cos(s.theta), sn = std::sin(s.theta);
+    const float gx = c * tx - sn * ty, gy = sn * tx + c * ty;                  // :58
+    const float lx = s.dx_m, ly = s.dy_m;                                      // :59
+    s.dx_m += gx;                                                              // :60
+    s.dy_m += gy;                                                              // :61
+    const float dist = std::sqrt(gx * gx + gy * gy);                           // :63
+    std::normal_distribution<float> disp_dist{0, pos_cov * dist};              // :64
+    std::normal_distribution<float> theta_dist{0, theta_cov * dist};           // :65
+    s.theta += theta_dist(gen) + omega;                                        // :67
+    s.dx_m += disp_dist(gen);                                                  // :68
+    s.dy_m += disp_dist(gen);                                                  // :69
+    if (!scale_freeze) {                                                       // :71-74
+      std::normal_distribution<float> scale_dist{1, static_cast<float>(std::min(2. / dist, 0.02))};
+      s.scale *= scale_dist(gen);
+    }
+    const float mx = lx - s.dx_m, my = ly - s.dy_m;                            // :76
+    last_dist[i] = std::sqrt(mx * mx + my * my);                               // :77
+    // the standard variates, from the twin engine (same uniforms, unit distributions)
+    std::normal_distribution<float> zt{0, 1}, zd{0, 1}, zs{0, 1};
+    const float z0 = zt(gen_z), z1 = zd(gen_z), z2 = zd(gen_z), z3 = scale_freeze ? 0.f : zs(gen_z);
+    if (z_out) { z_out[4 * i] = z0; z_out[4 * i + 1] = z1; z_out[4 * i + 2] = z2; z_out[4 * i + 3] = z3; }
+  }
+}
+
 ORC_API int orc_abi_version() { return 1; }

@@ -725,3 +725,54 @@ def test_refine_map_binning_and_distance_rebuild():
     c.close()
     d_o, m_o = orc.compute_dists(layers, 1.0)
     assert np.array_equal(d.view(np.uint32), d_o.view(np.uint32)) and np.array_equal(m, m_o)
+
+
+# ---- propagate on the device (state_particle.cpp:57-78)
+@pytest.mark.parametrize("freeze", [False, True])
+def test_propagate_injected_variates(world, freeze):
+    """same standard normal variates in -> the reference's states out.  Against the numpy twin (which forms cos / sin
+    exactly like the kernel: double precision, rounded) every field is BIT-EXACT, i.e. the kernel keeps the reference's
+    fp32 operation order; against the literal libstdc++ restatement the difference is the 1 ulp of glibc's cosf / sinf."""
+    from oracle import numpy_twin as twin
+    st, ld = synth.particles_tracking(50_000, world.pose, world.heading)
+    tx, ty, omega, pos_cov, theta_cov = 0.7, -0.2, 0.03, 0.3, 0.1
+    want, last_o, z = orc.propagate(st, tx, ty, omega, freeze, pos_cov, theta_cov, 4321)
+    tw, last_t = twin.propagate_with_z(st, tx, ty, omega, freeze, pos_cov, theta_cov, z)
+    c = make_ctx(world)
+    c.pf_set_states(st, ld)
+    c.pf_propagate((tx, ty), omega, freeze, pos_cov, theta_cov, z)
+    got, last_g = c.pf_get_states(), c.pf_get_last_dist()
+    c.close()
+    for k in ("init_x_px", "init_y_px", "dx_m", "dy_m", "theta", "scale"):
+        assert np.array_equal(got[k].view(np.uint32), tw[k].view(np.uint32)), k
+    assert np.array_equal(got["have_init"], st["have_init"])
+    assert np.array_equal(last_g.view(np.uint32), last_t.view(np.uint32))
+    # 1 ulp of cos / sin on each product, carried through two fp32 additions (an ulp of the result each)
+    tol = 2.5e-7 * (abs(tx) + abs(ty)) + 2.5e-7 * max(np.abs(want["dx_m"]).max(), np.abs(want["dy_m"]).max(), 1.0)
+    assert np.abs(got["dx_m"] - want["dx_m"]).max() <= tol and np.abs(got["dy_m"] - want["dy_m"]).max() <= tol
+    assert np.abs(got["theta"].view(np.int32).astype(np.int64) - want["theta"].view(np.int32).astype(np.int64)).max() <= 1
+    assert np.array_equal(got["scale"].view(np.uint32), want["scale"].view(np.uint32))
+    assert np.abs(last_g - last_o).max() <= 1e-6
+
+
+def test_propagate_device_rng(world):
+    """Philox + Box-Muller on the device: the variates it reports replay to the same states through the injected
+    path, are standard normal, differ between steps and repeat for the same (seed, step)."""
+    st, ld = synth.particles_tracking(200_000, world.pose, world.heading)
+    args = ((0.5, 0.1), -0.02, False, 0.3, 0.1)
+    c = make_ctx(world)
+    c.pf_set_states(st, ld)
+    z = c.pf_propagate_rng(*args, seed=7, step=3, want_z=True)
+    got, last_g = c.pf_get_states(), c.pf_get_last_dist()
+    c.pf_set_states(st, ld)
+    c.pf_propagate(*args, z)
+    rep, last_r = c.pf_get_states(), c.pf_get_last_dist()
+    c.pf_set_states(st, ld)
+    z_same = c.pf_propagate_rng(*args, seed=7, step=3, want_z=True)
+    z_next = c.pf_propagate_rng(*args, seed=7, step=4, want_z=True)
+    c.close()
+    assert np.array_equal(got, rep) and np.array_equal(last_g, last_r)
+    assert np.array_equal(z, z_same) and not np.array_equal(z, z_next)
+    assert np.isfinite(z).all() and np.abs(z.mean(0)).max() < 0.01 and np.abs(z.std(0) - 1).max() < 0.01
+    assert abs(np.corrcoef(z[:, 0], z[:, 1])[0, 1]) < 0.01 and abs(np.corrcoef(z[:-1, 2], z[1:, 2])[0, 1]) < 0.01
+    assert np.abs(z).max() < 6.5                          # 8e5 draws

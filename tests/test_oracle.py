@@ -287,3 +287,44 @@ def test_cfg1_mini_fixture_reproduces():
     wn, arg, _ = orc.normalize(w, g["last_dist"])
     assert np.array_equal(wn.view(np.uint32), g["weights_norm"].view(np.uint32)) and arg == int(g["argmax"])
     assert np.array_equal(orc.resample_fast(wn, float(g["u"]), len(st)), g["idx"])
+
+
+# ---- propagate (state_particle.cpp:57-78)
+def _ulps(a, b):
+    return np.abs(a.view(np.int32).astype(np.int64) - b.view(np.int32).astype(np.int64))
+
+
+@pytest.mark.parametrize("freeze", [False, True])
+def test_propagate_literal_rng_equals_injected_variates(freeze):
+    """the literal restatement (one shared mt19937, libstdc++ normal_distribution objects built exactly as the
+    reference builds them) and the twin that applies the recorded STANDARD variates with `z * stddev + mean` agree:
+    scale bit for bit, positions / heading up to the 1-ulp differences between glibc's cosf / sinf (CPU-dispatched,
+    FMA or SSE2 variant) and a correctly rounded cos / sin — the tolerance the device path is held to as well."""
+    st, _ = synth.particles_tracking(20000, (150.0, 150.0), 0.6)
+    tx, ty, omega = 0.7, -0.2, 0.03
+    a, last, z = orc.propagate(st, tx, ty, omega, freeze, 0.3, 0.1, 99)
+    b, last_b = twin.propagate_with_z(st, tx, ty, omega, freeze, 0.3, 0.1, z)
+    assert np.array_equal(a["scale"].view(np.uint32), b["scale"].view(np.uint32))
+    if freeze:
+        assert np.array_equal(a["scale"], st["scale"]) and (z[:, 3] == 0).all()
+    # 1 ulp of cos / sin (<= 1.2e-7) on each product, carried through two fp32 additions (an ulp of the result each)
+    tol = 2.5e-7 * (abs(tx) + abs(ty)) + 2.5e-7 * max(np.abs(a["dx_m"]).max(), np.abs(a["dy_m"]).max(), 1.0)
+    assert np.abs(a["dx_m"] - b["dx_m"]).max() <= tol and np.abs(a["dy_m"] - b["dy_m"]).max() <= tol
+    assert _ulps(a["theta"], b["theta"]).max() <= 1
+    assert np.abs(last - last_b).max() <= 1e-6
+    # the variates are standard normal, and the stream is the reference's: re-running reproduces it
+    assert abs(z[:, :3].mean()) < 0.02 and abs(z[:, :3].std() - 1) < 0.02
+    a2, _, z2 = orc.propagate(st, tx, ty, omega, freeze, 0.3, 0.1, 99)
+    assert np.array_equal(z, z2) and np.array_equal(a2, a)
+
+
+def test_propagate_known_answer_without_noise():
+    """pos_cov = theta_cov = 0 and a frozen scale: pure rotation of the odometry step (hand-computed)"""
+    st = np.zeros(2, dtype=synth.STATE_DTYPE)
+    st["theta"] = [0.0, math.pi / 2]
+    st["scale"] = 2.0
+    st["dx_m"] = [1.0, 1.0]
+    a, last, _ = orc.propagate(st, 3.0, 4.0, 0.25, True, 0.0, 0.0, 1)
+    assert np.allclose(a["dx_m"], [4.0, -3.0], atol=1e-6) and np.allclose(a["dy_m"], [4.0, 3.0], atol=1e-6)
+    assert np.allclose(a["theta"], [0.25, math.pi / 2 + 0.25], atol=1e-6) and np.allclose(last, [5.0, 5.0], atol=1e-6)
+    assert np.array_equal(a["scale"], st["scale"])

@@ -346,6 +346,26 @@ class Context:
         check(self._lib.tdr_grid_best(self._h, C.byref(c), C.byref(i)))
         return c.value, i.value
 
+    # motion model (StateParticle::propagate, state_particle.cpp:57-78)
+    def pf_propagate(self, trans, omega, scale_freeze, pos_cov, theta_cov, z):
+        """z: (n, 4) standard normal variates (theta, dx, dy, scale) — the parity path"""
+        z = np.ascontiguousarray(z, dtype=np.float32).reshape(-1, 4)
+        check(self._lib.tdr_pf_propagate(self._h, C.c_float(trans[0]), C.c_float(trans[1]), C.c_float(omega), int(bool(scale_freeze)),
+                                         C.c_float(pos_cov), C.c_float(theta_cov), _pf(z), C.c_int64(z.shape[0])))
+
+    def pf_propagate_rng(self, trans, omega, scale_freeze, pos_cov, theta_cov, seed, step, want_z=False):
+        """device RNG (Philox + Box-Muller); returns the variates used when want_z"""
+        z = np.empty((self.pf_count(), 4), dtype=np.float32) if want_z else None
+        check(self._lib.tdr_pf_propagate_rng(self._h, C.c_float(trans[0]), C.c_float(trans[1]), C.c_float(omega), int(bool(scale_freeze)),
+                                             C.c_float(pos_cov), C.c_float(theta_cov), C.c_uint64(seed), C.c_uint64(step),
+                                             _pf(z) if want_z else None))
+        return z
+
+    def pf_get_last_dist(self):
+        out = np.empty(self.pf_count(), dtype=np.float32)
+        check(self._lib.tdr_pf_get_last_dist(self._h, _pf(out), C.c_int64(len(out))))
+        return out
+
     def grid_best_key(self):
         """packed (min cost, first flat index) of the last tensor-core grid launch (synchronises)"""
         k = C.c_uint64()

@@ -387,6 +387,52 @@ int tdr_pf_get_states(tdr_ctx* ctx, tdr_state* states, int64_t n) {
   return TDR_OK;
 }
 
+static int propagate_host_z(tdr_ctx* ctx, float tx, float ty, float omega, int scale_freeze, float pos_cov, float theta_cov,
+                            const float* z, bool z_on_device, int64_t n) {
+  Particles& pt = ctx->part[ctx->cur];
+  TDR_REQUIRE(z && n == pt.n, TDR_EINVAL, "need 4 variates for each of the %lld resident particles", (long long)pt.n);
+  const float* dz = z;
+  if (!z_on_device) {
+    if (int e = ctx->scratch.reserve((size_t)n * 16)) return e;
+    TDR_CUDA(cudaMemcpyAsync(ctx->scratch.p, z, (size_t)n * 16, cudaMemcpyHostToDevice, ctx->stream));
+    dz = ctx->scratch.as<float>();
+  }
+  if (int e = propagate(ctx, tx, ty, omega, scale_freeze, pos_cov, theta_cov, dz, false, 0, 0, nullptr)) return e;
+  if (!z_on_device) TDR_CUDA(cudaStreamSynchronize(ctx->stream));      // the caller's pageable buffer may go away
+  return TDR_OK;
+}
+int tdr_pf_propagate(tdr_ctx* ctx, float trans_x, float trans_y, float omega, int scale_freeze, float pos_cov, float theta_cov,
+                     const float* z, int64_t n) {
+  CTX_CHECK(ctx);
+  return propagate_host_z(ctx, trans_x, trans_y, omega, scale_freeze, pos_cov, theta_cov, z, false, n);
+}
+int tdr_pf_propagate_dev(tdr_ctx* ctx, float trans_x, float trans_y, float omega, int scale_freeze, float pos_cov,
+                         float theta_cov, const void* dev_z, int64_t n) {
+  CTX_CHECK(ctx);
+  return propagate_host_z(ctx, trans_x, trans_y, omega, scale_freeze, pos_cov, theta_cov, reinterpret_cast<const float*>(dev_z), true, n);
+}
+int tdr_pf_propagate_rng(tdr_ctx* ctx, float trans_x, float trans_y, float omega, int scale_freeze, float pos_cov,
+                         float theta_cov, uint64_t seed, uint64_t step, float* z_out) {
+  CTX_CHECK(ctx);
+  Particles& pt = ctx->part[ctx->cur];
+  float* dz = nullptr;
+  if (z_out) { if (int e = ctx->scratch.reserve((size_t)pt.n * 16)) return e; dz = ctx->scratch.as<float>(); }
+  if (int e = propagate(ctx, trans_x, trans_y, omega, scale_freeze, pos_cov, theta_cov, nullptr, true, seed, step, dz)) return e;
+  if (z_out) {
+    TDR_CUDA(cudaMemcpyAsync(z_out, dz, (size_t)pt.n * 16, cudaMemcpyDeviceToHost, ctx->stream));
+    TDR_CUDA(cudaStreamSynchronize(ctx->stream));
+  }
+  return TDR_OK;
+}
+int tdr_pf_get_last_dist(tdr_ctx* ctx, float* last_dist, int64_t n) {
+  CTX_CHECK(ctx);
+  Particles& pt = ctx->part[ctx->cur];
+  TDR_REQUIRE(last_dist && n == pt.n, TDR_EINVAL, "bad last_dist buffer");
+  TDR_CUDA(cudaMemcpyAsync(last_dist, pt.last_dist.p, (size_t)n * 4, cudaMemcpyDeviceToHost, ctx->stream));
+  TDR_CUDA(cudaStreamSynchronize(ctx->stream));
+  return TDR_OK;
+}
+
 static int copy_particles(tdr_ctx* ctx, Particles& dst, Particles& src) {
   if (int e = dst.reserve(src.n)) return e;
   DevBuf* d[] = {&dst.init_x, &dst.init_y, &dst.dx, &dst.dy, &dst.theta, &dst.scale, &dst.last_dist};

@@ -184,29 +184,26 @@ class ParticleFilter {
       : gen_(seed), map_(map), params_(params), max_num_particles_(N) {
     if (map_->haveMap()) initializeParticles();
   }
-  // particle_filter.cpp:86-92 + StateParticle::propagate (state_particle.cpp:57-78): host RNG, as in the reference
+  // particle_filter.cpp:86-92 + StateParticle::propagate (state_particle.cpp:57-78).  The noise comes from the
+  // reference's own RNG calls in particle order — per particle a fresh theta distribution drawn once, a fresh
+  // displacement distribution drawn twice (the second draw is the polar method's saved value), a fresh scale
+  // distribution unless frozen — taken as STANDARD variates (the uniforms consumed are the same for any stddev);
+  // the states stay on the device and tdr_pf_propagate applies `z * stddev + mean` and the motion there.
   void propagate(const Vector2f& trans, float omega) {
-    pull();
-    for (size_t i = 0; i < states_.size(); i++) {
-      State& s = states_[i];
-      const float c = cosf(s.theta), sn = sinf(s.theta);
-      const float gx = c * trans.x - sn * trans.y, gy = sn * trans.x + c * trans.y;
-      const float lx = s.dx_m, ly = s.dy_m;
-      s.dx_m += gx; s.dy_m += gy;
-      const float dist = sqrtf(gx * gx + gy * gy);
-      std::normal_distribution<float> disp_dist{0, params_.pos_cov * dist};
-      std::normal_distribution<float> theta_dist{0, params_.theta_cov * dist};
-      s.theta += theta_dist(gen_) + omega;
-      s.dx_m += disp_dist(gen_);
-      s.dy_m += disp_dist(gen_);
-      if (!scale_frozen_) {
-        std::normal_distribution<float> scale_dist{1, static_cast<float>(std::min(2. / dist, 0.02))};
-        s.scale *= scale_dist(gen_);
-      }
-      const float mx = lx - s.dx_m, my = ly - s.dy_m;
-      last_dist_[i] = sqrtf(mx * mx + my * my);
+    if (!ctx()) return;
+    int64_t n = 0; tdr_pf_count(ctx(), &n);
+    if (n <= 0) return;
+    z_.resize((size_t)n * 4);
+    for (int64_t i = 0; i < n; i++) {
+      std::normal_distribution<float> theta_dist{0, 1}, disp_dist{0, 1};
+      z_[4 * i] = theta_dist(gen_);
+      z_[4 * i + 1] = disp_dist(gen_);
+      z_[4 * i + 2] = disp_dist(gen_);
+      z_[4 * i + 3] = 0.f;
+      if (!scale_frozen_) { std::normal_distribution<float> scale_dist{0, 1}; z_[4 * i + 3] = scale_dist(gen_); }
     }
-    push();
+    if (ok(tdr_pf_propagate(ctx(), trans.x, trans.y, omega, scale_frozen_ ? 1 : 0, params_.pos_cov, params_.theta_cov, z_.data(), n)))
+      host_dirty_ = true;
   }
   // particle_filter.cpp:94-189.  top_down_geo is accepted and ignored, as in the reference's cost (F10).
   void update(std::vector<ArrayXXf>& top_down_scan, std::vector<ArrayXXf>& /*top_down_geo*/, float res) {
@@ -229,7 +226,7 @@ class ParticleFilter {
   bool isScaleFrozen() const { return scale_frozen_; }
   // host views (the reference's visualize / GMM thread read the particles on the host)
   const std::vector<State>& states() { pull(); return states_; }
-  const std::vector<float>& lastDist() const { return last_dist_; }
+  const std::vector<float>& lastDist() { pull(); return last_dist_; }
   float lastUniform() const { return last_u_; }
   std::vector<float> weights() {
     std::vector<float> w(num_particles_);
@@ -305,7 +302,7 @@ class ParticleFilter {
     if (!host_dirty_ || !ctx()) return;
     int64_t n = 0; tdr_pf_count(ctx(), &n);
     states_.resize((size_t)n); last_dist_.resize((size_t)n, 0.f);
-    if (n) ok(tdr_pf_get_states(ctx(), states_.data(), n));
+    if (n) { ok(tdr_pf_get_states(ctx(), states_.data(), n)); ok(tdr_pf_get_last_dist(ctx(), last_dist_.data(), n)); }
     num_particles_ = (int)n; host_dirty_ = false;
   }
 
@@ -316,7 +313,7 @@ class ParticleFilter {
   bool scale_frozen_ = false, host_dirty_ = false;
   float last_u_ = 0.f;
   std::vector<State> states_;
-  std::vector<float> last_dist_, stage_;
+  std::vector<float> last_dist_, stage_, z_;
 };
 
 }  // namespace tdrhost
