@@ -48,6 +48,9 @@ WORKLOADS = {
                  desc="cfg4 exhaustive grid: 1000x1000 centres (stride 4 px over 4000x4000 px, 6 classes) x 100 row shifts = "
                       "1e8 (x, y, theta) hypotheses in total, sharded over the GPUs; rasterise + all costs + weight all-gather "
                       "+ arg-min"),
+    "refine": dict(side=4000, C=6, n=0, res=0.5, shifts=0, refine=True, scans=10_000, chunk_scans=64, distinct_chunks=8,
+                   desc="cfg5 refine_map batch: 10k recorded scans (65536 pts each, 6.6e8 points) binned with refine_map's rule "
+                        "into a 4000x4000 px x 6-class count map + per-class distance-field rebuild"),
     "tracking": dict(side=2000, C=6, n=10_000, res=0.5, shifts=1,
                      desc="cfg2 tracking: 10k particles, 2000x2000 px map, 6 classes, 65536-pt scan; "
                           "rasterise+score+normalise+resample"),
@@ -567,6 +570,125 @@ def run_grid(args, wl):
 _REAL_STDOUT = None
 
 
+def run_refine(args, wl):
+    """cfg5 (a composition): refine_map's binning rule over a batch of recorded scans, then the
+    distance fields of the binned class maps.  One step = the WHOLE batch: zero the counters, bin every chunk, rebuild
+    the map.  value: chunks resident in HBM (tdr_refine_add_dev); e2e: every chunk copied from pinned host memory
+    inside the timed region (tdr_refine_add) + a read of the rebuilt map at one point.  Single GPU."""
+    import torch
+    from top_down_renderer_b200 import hostmath, synth
+    from top_down_renderer_b200.core import Context
+    if not torch.cuda.is_available():
+        raise SystemExit("bench.py: no CUDA device — the product path has no CPU fallback")
+    rank = int(os.environ.get("RANK", "0"))
+    if rank != 0:
+        return
+    torch.cuda.set_device(0)
+    side, C, res = wl["side"], wl["C"], wl["res"]
+    inp = make_inputs(dict(wl, n=16, shifts=1), 0)
+    rng = np.random.default_rng(SEED + 5)
+    road = synth.road_pixels(inp["cm"])
+    local_xy = inp["pts"][:, 0:2].astype(np.float32)                       # metres, sensor frame
+    local_cls = inp["pts"][:, 4].astype(np.int32)                          # raw class id (255 = unknown -> dropped)
+    keep = ~((local_xy[:, 0] == 0) & (local_xy[:, 1] == 0))
+    n_pts = local_xy.shape[0]
+    per_chunk = wl["chunk_scans"] * n_pts
+    chunks = []
+    for _ in range(wl["distinct_chunks"]):                                 # recorded scans: random road poses, world frame (metres)
+        xy = np.empty((wl["chunk_scans"], n_pts, 2), dtype=np.float32)
+        cl = np.empty((wl["chunk_scans"], n_pts), dtype=np.int32)
+        for k in range(wl["chunk_scans"]):
+            p = int(road[rng.integers(0, road.size)])
+            px, py, th = (p % side) * res, (p // side) * res, float(rng.uniform(-math.pi, math.pi))
+            c, s_ = np.float32(math.cos(th)), np.float32(math.sin(th))
+            xy[k, :, 0] = c * local_xy[:, 0] - s_ * local_xy[:, 1] + np.float32(px)
+            xy[k, :, 1] = s_ * local_xy[:, 0] + c * local_xy[:, 1] + np.float32(py)
+            cl[k] = np.where(keep, local_cls, -1)
+        chunks.append((torch.from_numpy(xy.reshape(-1, 2)).pin_memory(), torch.from_numpy(cl.reshape(-1)).pin_memory()))
+    dev_chunks = [(a.cuda(), b.cuda()) for a, b in chunks]
+    n_chunks = (wl["scans"] + wl["chunk_scans"] - 1) // wl["chunk_scans"]
+    total_pts = n_chunks * per_chunk
+    ctx = Context(0)
+    ctx.map_set_polar_table(hostmath.polar_table(N_THETA, N_R, ANG_RES, 1.0), N_THETA, N_R)
+    stream = torch.cuda.ExternalStream(ctx.stream, device=0)
+    flush = torch.empty(256 << 20, dtype=torch.uint8, device="cuda:0")
+    probe = np.array([[side / 2, side / 2]], dtype=np.float32)
+
+    def step(resident):
+        ctx.refine_begin(res, 0.0, 0.0, side, side, C)
+        for k in range(n_chunks):
+            if resident:
+                a, b = dev_chunks[k % len(dev_chunks)]
+                ctx.refine_add_dev(a.data_ptr(), b.data_ptr(), per_chunk)
+            else:
+                a, b = chunks[k % len(chunks)]
+                ctx.refine_add_ptr(a.data_ptr(), b.data_ptr(), per_chunk)
+        ctx.refine_rebuild_map(1.0)
+
+    sampler = ClockSampler(0)
+    sampler.start()
+    ms, e2e = [], []
+    l0 = None
+    for i in range(args.warmup + args.steps):
+        flush.fill_(i & 0xff)                                               # L2 flush, outside the events
+        torch.cuda.synchronize()
+        if i == args.warmup:
+            l0 = ctx.launch_count()
+        e0, e1 = torch.cuda.Event(enable_timing=True), torch.cuda.Event(enable_timing=True)
+        with torch.cuda.stream(stream):
+            e0.record(stream)
+            step(True)
+            e1.record(stream)
+        torch.cuda.synchronize()
+        if i >= args.warmup:
+            ms.append(e0.elapsed_time(e1))
+    launches = ctx.launch_count() - l0
+    for i in range(max(2, args.steps // 4)):
+        torch.cuda.synchronize()
+        t0 = time.perf_counter()
+        step(False)
+        ctx.map_local_polar(probe, 2.0, 4.0)                                # D2H read of the rebuilt map: synchronises
+        e2e.append(time.perf_counter() - t0)
+    clocks = sampler.stop()
+    counts = ctx.refine_counts()
+    ctx.close()
+    t = float(np.mean(ms))
+    peak, peak_src = peaks()
+    alg_bytes = total_pts * 12 + side * side * (4 * C + 2)                  # 12 B per point in + the EDT's map bytes (SURVEY 8d)
+    # CPU baseline: the oracle's binning on one chunk (1 thread, like refine_map) + cv2's EDT on the full map, extrapolated
+    cpu = None
+    if not args.no_cpu:
+        from oracle import oracle as orc
+        a, b = chunks[0]
+        t0 = time.perf_counter()
+        orc.refine_bin(a.numpy(), b.numpy(), res, 0.0, 0.0, side, side, C)
+        t_bin = time.perf_counter() - t0
+        layers = np.ascontiguousarray((counts == 0).astype(np.float32).transpose(0, 2, 1))
+        t0 = time.perf_counter()
+        orc.compute_dists(layers, 1.0)
+        t_edt = time.perf_counter() - t0
+        cpu = {"value": total_pts / (t_bin * n_chunks + t_edt), "unit": "points/s", "cores": 1, "kind": "port",
+               "sample": f"oracle binning of 1 of {n_chunks} chunks ({per_chunk} points, {t_bin * 1e3:.0f} ms, extrapolated) + oracle "
+                         f"distance fields of the full {side}x{side}x{C} map ({t_edt * 1e3:.0f} ms); oracle/tdr_oracle.cpp, 1 thread"}
+    out = {"metric": "refine_points_per_sec", "value": total_pts / (t * 1e-3), "unit": "points/s", "n_gpus": 1, "steps": args.steps,
+           "warmup": args.warmup, "ms_per_step": t, "higher_is_better": True, "scaling": "weak", "vs_baseline": None, "dtype": "i32",
+           "data": "synthetic",
+           "config": {"workload": wl["desc"], "scans": n_chunks * wl["chunk_scans"], "points": total_pts, "map_px": [side, side],
+                      "classes": C, "res_m_per_px": res, "chunks": n_chunks,
+                      "distinct_scans": wl["distinct_chunks"] * wl["chunk_scans"],
+                      "l2": "flushed (256 MiB write) between steps, outside the timed events"},
+           "clocks": clocks,
+           "e2e": {"value": total_pts / float(np.mean(e2e)), "unit": "points/s", "h2d_bytes_per_step": int(total_pts * 12),
+                   "d2h_bytes_per_step": int(N_THETA * N_R * (4 * C + 1)), "ms_per_step": 1e3 * float(np.mean(e2e)),
+                   "timer": "host wall clock around begin + all chunks from pinned host memory + rebuild + a read of the map"},
+           "gpu_launches": int(launches),
+           "roofline": {"bound": "hbm", "kernel": "k_refine_bin (warp-aggregated integer red) + EDT rebuild", "achieved": alg_bytes / (t * 1e-3) / 1e9,
+                        "peak": peak, "unit": "GB/s", "frac": alg_bytes / (t * 1e-3) / 1e9 / peak, "traffic": None,
+                        "peak_source": peak_src, "algorithmic_bytes_per_launch": alg_bytes, "kernel_ms": t},
+           "cpu_baseline": cpu}
+    emit(out)
+
+
 def claim_stdout():
     """Rank 0 must print exactly ONE line on stdout, but NCCL / torch write banners to fd 1: point fd 1 at stderr
     for the whole run and keep a private handle on the real stdout for the JSON line."""
@@ -602,6 +724,8 @@ def main():
         wl["n"] = args.particles
     if args.impl == "reference":
         run_reference(args, wl)
+    elif wl.get("refine"):
+        run_refine(args, wl)
     elif wl.get("grid"):
         run_grid(args, wl)
     else:

@@ -129,6 +129,16 @@ int tdr_scan_render_cart(tdr_ctx* ctx, float res, int rows, int cols, float* img
  * uint8 counter per (class, y, x), wrapping mod 256 like the reference's "+= 1".  maps_out: C x height x width. */
 int tdr_refine_bin(tdr_ctx* ctx, const float* xy, const int32_t* cls, int64_t n, float res, float center_x, float center_y,
                    int width, int height, int num_classes, uint8_t* maps_out);
+/* the same in pieces, for batches that do not fit one buffer (10k recorded scans = 6.6e8 points): begin zeroes the
+ * counters; add bins one chunk (host buffers, or device pointers with tdr_refine_add_dev — asynchronous);
+ * counts copies the uint8 maps out; rebuild_map turns the counters into a map without leaving the device: class c is
+ * present where its counter is non-zero, pixels without any class are unknown, then the per-class distance fields
+ * (computeDists, top_down_map.cpp:289-326) — cfg5's "distance-field rebuild".  Map rows = height, cols = width. */
+int tdr_refine_begin(tdr_ctx* ctx, float res, float center_x, float center_y, int width, int height, int num_classes);
+int tdr_refine_add(tdr_ctx* ctx, const float* xy, const int32_t* cls, int64_t n);
+int tdr_refine_add_dev(tdr_ctx* ctx, const void* dev_xy, const void* dev_cls, int64_t n);
+int tdr_refine_counts(tdr_ctx* ctx, uint8_t* maps_out);
+int tdr_refine_rebuild_map(tdr_ctx* ctx, float resolution);
 /* upload externally rendered polar class images instead (ParticleFilter::update takes them
  * as an argument, particle_filter.cpp:94) */
 int tdr_scan_set_polar_images(tdr_ctx* ctx, const float* imgs, int n_theta, int n_r, int num_classes);

@@ -725,6 +725,16 @@ def test_refine_map_binning_and_distance_rebuild():
     c.close()
     d_o, m_o = orc.compute_dists(layers, 1.0)
     assert np.array_equal(d.view(np.uint32), d_o.view(np.uint32)) and np.array_equal(m, m_o)
+    # the same batch in three chunks, counters and rebuild without leaving the device
+    c = Context(0)
+    c.refine_begin(0.5, 70.0, 61.0, Wd, Hd, Cn)
+    for lo, hi in ((0, 150_000), (150_000, 150_001), (150_001, n)):
+        c.refine_add(xy[lo:hi], cls[lo:hi])
+    assert np.array_equal(c.refine_counts(), want)
+    c.refine_rebuild_map(1.0)
+    d2, m2 = c.map_get_layers()
+    c.close()
+    assert np.array_equal(d2.view(np.uint32), d_o.view(np.uint32)) and np.array_equal(m2, m_o)
 
 
 # ---- propagate on the device (state_particle.cpp:57-78)

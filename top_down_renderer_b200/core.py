@@ -173,6 +173,32 @@ class Context:
                                        C.c_float(cy), int(width), int(height), int(num_classes), _pb(out)))
         return out
 
+    # the same in pieces (cfg5: batches larger than one buffer) + the distance-field rebuild on the device
+    def refine_begin(self, res, cx, cy, width, height, num_classes):
+        self._refine_shape = (int(num_classes), int(height), int(width))
+        check(self._lib.tdr_refine_begin(self._h, C.c_float(res), C.c_float(cx), C.c_float(cy), int(width), int(height), int(num_classes)))
+
+    def refine_add(self, xy, cls):
+        xy = np.ascontiguousarray(xy, dtype=np.float32).reshape(-1, 2)
+        cls = np.ascontiguousarray(cls, dtype=np.int32)
+        check(self._lib.tdr_refine_add(self._h, _pf(xy), _pi(cls), C.c_int64(len(cls))))
+
+    def refine_add_ptr(self, xy_ptr, cls_ptr, n):
+        """host pointers (e.g. pinned torch tensors)"""
+        check(self._lib.tdr_refine_add(self._h, C.cast(C.c_void_p(xy_ptr), C.POINTER(C.c_float)),
+                                       C.cast(C.c_void_p(cls_ptr), C.POINTER(C.c_int32)), C.c_int64(n)))
+
+    def refine_add_dev(self, xy_ptr, cls_ptr, n):
+        check(self._lib.tdr_refine_add_dev(self._h, C.c_void_p(xy_ptr), C.c_void_p(cls_ptr), C.c_int64(n)))
+
+    def refine_counts(self):
+        out = np.empty(self._refine_shape, dtype=np.uint8)
+        check(self._lib.tdr_refine_counts(self._h, _pb(out)))
+        return out
+
+    def refine_rebuild_map(self, resolution):
+        check(self._lib.tdr_refine_rebuild_map(self._h, C.c_float(resolution)))
+
     def scan_set_polar_images(self, imgs):
         imgs = np.ascontiguousarray(imgs, dtype=np.float32)
         c, n_r, n_theta = imgs.shape

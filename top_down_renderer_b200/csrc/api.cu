@@ -155,6 +155,8 @@ void tdr_destroy(tdr_ctx* c) {
   c->part[0].release(); c->part[1].release(); c->ckpt.release(); c->all.release();
   c->pin.release();
   for (int k = 0; k <= TDR_N_STAGES; k++) if (c->stage_ev[k]) cudaEventDestroy(c->stage_ev[k]);
+  for (int k = 0; k < 2; k++) { if (c->refine_copied[k]) cudaEventDestroy(c->refine_copied[k]); if (c->refine_binned[k]) cudaEventDestroy(c->refine_binned[k]); c->refine_stage[k].release(); }
+  if (c->copy_stream) cudaStreamDestroy(c->copy_stream);
   if (c->stream) cudaStreamDestroy(c->stream);
   delete c;
 }
@@ -318,6 +320,18 @@ int tdr_refine_bin(tdr_ctx* ctx, const float* xy, const int32_t* cls, int64_t n,
   TDR_REQUIRE(n == 0 || (xy && cls), TDR_EINVAL, "null points");
   return refine_bin(ctx, xy, cls, n, res, center_x, center_y, width, height, num_classes, maps_out);
 }
+
+int tdr_refine_begin(tdr_ctx* ctx, float res, float center_x, float center_y, int width, int height, int num_classes) {
+  CTX_CHECK(ctx);
+  return refine_begin(ctx, res, center_x, center_y, width, height, num_classes);
+}
+int tdr_refine_add(tdr_ctx* ctx, const float* xy, const int32_t* cls, int64_t n) { CTX_CHECK(ctx); return refine_add(ctx, xy, cls, n, false); }
+int tdr_refine_add_dev(tdr_ctx* ctx, const void* dev_xy, const void* dev_cls, int64_t n) {
+  CTX_CHECK(ctx);
+  return refine_add(ctx, reinterpret_cast<const float*>(dev_xy), reinterpret_cast<const int32_t*>(dev_cls), n, true);
+}
+int tdr_refine_counts(tdr_ctx* ctx, uint8_t* maps_out) { CTX_CHECK(ctx); return refine_counts(ctx, maps_out); }
+int tdr_refine_rebuild_map(tdr_ctx* ctx, float resolution) { CTX_CHECK(ctx); return refine_rebuild_map(ctx, resolution); }
 
 int tdr_scan_set_polar_images(tdr_ctx* ctx, const float* imgs, int n_theta, int n_r, int num_classes) {
   CTX_CHECK(ctx);

@@ -275,6 +275,15 @@ int map_set_binary_layers(tdr_ctx* ctx, const float* layers, int rows, int cols,
   return TDR_OK;
 }
 
+// seeds produced on the device (ctx->scratch2, rows*cols bytes, k_layers_to_seeds' bit layout) -> map + distance fields
+int map_from_seeds(tdr_ctx* ctx, int rows, int cols, int C, float resolution) {
+  if (int e = map_alloc(ctx, rows, cols, C, resolution)) return e;
+  TDR_CUDA(cudaMemcpyAsync(ctx->seedbits.p, ctx->scratch2.p, (size_t)rows * cols, cudaMemcpyDeviceToDevice, ctx->stream));
+  if (int e = run_edt(ctx, ctx->seedbits.as<uint8_t>(), rows, cols, C, resolution, true, nullptr)) return e;
+  ctx->have_map = true; ctx->have_seeds = true;
+  return TDR_OK;
+}
+
 int map_set_dist_layers(tdr_ctx* ctx, const float* layers, const uint8_t* mask, int rows, int cols, int C,
                         float resolution) {
   TDR_REQUIRE(layers && mask, TDR_EINVAL, "null layers / mask");

@@ -196,29 +196,101 @@ int scan_render(tdr_ctx* ctx, bool polar, float res, float ang_res, int d0, int 
   return TDR_OK;
 }
 
-int refine_bin(tdr_ctx* ctx, const float* xy, const int32_t* cls, long long n, float res, float cx, float cy, int width,
-               int height, int C, uint8_t* maps_out) {
-  TDR_REQUIRE(n >= 0 && res > 0.f && width > 0 && height > 0 && C >= 1 && maps_out, TDR_EINVAL, "bad refine_bin arguments");
+// counters -> class-presence seeds for the distance-field rebuild: class c is present where its (wrapped uint8)
+// counter is non-zero, i.e. the binary layer (counter == 0 ? 1 : 0) of the composition in SURVEY section 8 (cfg5);
+// a pixel with no class at all is unknown (computeDists' mask, top_down_map.cpp:294-299).  Same bit layout as
+// k_layers_to_seeds.
+__global__ void k_hist_to_seeds(const int32_t* __restrict__ hist, size_t L, int C, uint8_t* __restrict__ seed) {
+  const size_t i = (size_t)blockIdx.x * blockDim.x + threadIdx.x;
+  if (i >= L) return;
+  uint32_t bits = 0;
+  for (int c = 0; c < C; c++) if (hist[(size_t)c * L + i] & 255) bits |= 1u << c;
+  if (bits == 0) bits = 0x80u;
+  seed[i] = (uint8_t)bits;
+}
+
+int refine_begin(tdr_ctx* ctx, float res, float cx, float cy, int width, int height, int C) {
+  TDR_REQUIRE(res > 0.f && width > 0 && height > 0 && C >= 1 && C <= 7, TDR_EINVAL, "bad refine arguments");
   const size_t cells = (size_t)C * width * height;
   if (int e = ctx->hist.reserve(cells * 4)) return e;
-  if (int e = ctx->scratch.reserve((size_t)(n > 0 ? n : 1) * 12)) return e;
-  if (int e = ctx->scratch2.reserve(cells)) return e;
-  float2* d_xy = ctx->scratch.as<float2>();
-  int32_t* d_cls = reinterpret_cast<int32_t*>(ctx->scratch.as<unsigned char>() + (size_t)n * 8);
   TDR_CUDA(cudaMemsetAsync(ctx->hist.p, 0, cells * 4, ctx->stream));
-  if (n > 0) {
-    TDR_CUDA(cudaMemcpyAsync(d_xy, xy, (size_t)n * 8, cudaMemcpyHostToDevice, ctx->stream));
-    TDR_CUDA(cudaMemcpyAsync(d_cls, cls, (size_t)n * 4, cudaMemcpyHostToDevice, ctx->stream));
-    k_refine_bin<<<(unsigned)((n + 255) / 256), 256, 0, ctx->stream>>>(d_xy, d_cls, n, res, (int)(cx / res), (int)(cy / res), width,
-                                                                      height, C, ctx->hist.as<int32_t>());
-    count_launch(ctx);
+  ctx->refine_w = width; ctx->refine_h = height; ctx->refine_C = C; ctx->refine_res = res;
+  ctx->refine_off_x = (int)(cx / res); ctx->refine_off_y = (int)(cy / res);        // src/refine_map.cpp:80-81
+  return TDR_OK;
+}
+
+int refine_add(tdr_ctx* ctx, const float* xy, const int32_t* cls, long long n, bool on_device) {
+  TDR_REQUIRE(ctx->refine_w > 0, TDR_ESTATE, "tdr_refine_begin has not been called");
+  TDR_REQUIRE(n >= 0 && (n == 0 || (xy && cls)), TDR_EINVAL, "bad refine points");
+  if (n == 0) return TDR_OK;
+  const float2* d_xy = reinterpret_cast<const float2*>(xy);
+  const int32_t* d_cls = cls;
+  int slot = -1;
+  if (!on_device) {
+    // H2D on the copy stream into one of two staging slots, the kernel on the context stream behind an event: the
+    // copy of chunk k + 1 overlaps the binning of chunk k.  Returns once the copy is done (the caller may reuse its
+    // buffers); the kernel is still running.
+    if (!ctx->copy_stream) {
+      TDR_CUDA(cudaStreamCreateWithFlags(&ctx->copy_stream, cudaStreamNonBlocking));
+      for (int k = 0; k < 2; k++) {
+        TDR_CUDA(cudaEventCreateWithFlags(&ctx->refine_copied[k], cudaEventDisableTiming));
+        TDR_CUDA(cudaEventCreateWithFlags(&ctx->refine_binned[k], cudaEventDisableTiming));
+      }
+    }
+    slot = ctx->refine_slot; ctx->refine_slot ^= 1;
+    TDR_CUDA(cudaStreamWaitEvent(ctx->copy_stream, ctx->refine_binned[slot], 0));     // the kernel that read this slot is done
+    if (ctx->refine_stage[slot].cap < (size_t)n * 12) {
+      TDR_CUDA(cudaStreamSynchronize(ctx->copy_stream));
+      if (int e = ctx->refine_stage[slot].reserve((size_t)n * 12)) return e;
+    }
+    float2* sxy = ctx->refine_stage[slot].as<float2>();
+    int32_t* scl = reinterpret_cast<int32_t*>(ctx->refine_stage[slot].as<unsigned char>() + (size_t)n * 8);
+    TDR_CUDA(cudaMemcpyAsync(sxy, xy, (size_t)n * 8, cudaMemcpyHostToDevice, ctx->copy_stream));
+    TDR_CUDA(cudaMemcpyAsync(scl, cls, (size_t)n * 4, cudaMemcpyHostToDevice, ctx->copy_stream));
+    TDR_CUDA(cudaEventRecord(ctx->refine_copied[slot], ctx->copy_stream));
+    TDR_CUDA(cudaStreamWaitEvent(ctx->stream, ctx->refine_copied[slot], 0));
+    d_xy = sxy; d_cls = scl;
   }
+  k_refine_bin<<<(unsigned)((n + 255) / 256), 256, 0, ctx->stream>>>(d_xy, d_cls, n, ctx->refine_res, ctx->refine_off_x, ctx->refine_off_y,
+                                                                    ctx->refine_w, ctx->refine_h, ctx->refine_C, ctx->hist.as<int32_t>());
+  count_launch(ctx);
+  TDR_CUDA(cudaGetLastError());
+  if (slot >= 0) {
+    TDR_CUDA(cudaEventRecord(ctx->refine_binned[slot], ctx->stream));
+    TDR_CUDA(cudaEventSynchronize(ctx->refine_copied[slot]));
+  }
+  return TDR_OK;
+}
+
+int refine_counts(tdr_ctx* ctx, uint8_t* maps_out) {
+  TDR_REQUIRE(ctx->refine_w > 0 && maps_out, TDR_ESTATE, "no batch binning in progress / null output");
+  const size_t cells = (size_t)ctx->refine_C * ctx->refine_w * ctx->refine_h;
+  if (int e = ctx->scratch2.reserve(cells)) return e;
   k_hist_to_u8<<<(unsigned)((cells + 255) / 256), 256, 0, ctx->stream>>>(ctx->hist.as<int32_t>(), cells, ctx->scratch2.as<uint8_t>());
   count_launch(ctx);
   TDR_CUDA(cudaGetLastError());
   TDR_CUDA(cudaMemcpyAsync(maps_out, ctx->scratch2.p, cells, cudaMemcpyDeviceToHost, ctx->stream));
   TDR_CUDA(cudaStreamSynchronize(ctx->stream));
   return TDR_OK;
+}
+
+int refine_rebuild_map(tdr_ctx* ctx, float resolution) {
+  TDR_REQUIRE(ctx->refine_w > 0, TDR_ESTATE, "no batch binning in progress");
+  const int rows = ctx->refine_h, cols = ctx->refine_w, C = ctx->refine_C;
+  const size_t L = (size_t)rows * cols;
+  if (int e = ctx->scratch2.reserve(L)) return e;
+  k_hist_to_seeds<<<(unsigned)((L + 255) / 256), 256, 0, ctx->stream>>>(ctx->hist.as<int32_t>(), L, C, ctx->scratch2.as<uint8_t>());
+  count_launch(ctx);
+  TDR_CUDA(cudaGetLastError());
+  return map_from_seeds(ctx, rows, cols, C, resolution);     // copies the seeds into the map's own buffer, then the EDT
+}
+
+int refine_bin(tdr_ctx* ctx, const float* xy, const int32_t* cls, long long n, float res, float cx, float cy, int width,
+               int height, int C, uint8_t* maps_out) {
+  TDR_REQUIRE(n >= 0 && maps_out, TDR_EINVAL, "bad refine_bin arguments");
+  if (int e = refine_begin(ctx, res, cx, cy, width, height, C)) return e;
+  if (int e = refine_add(ctx, xy, cls, n, false)) return e;
+  return refine_counts(ctx, maps_out);
 }
 
 int scan_pack(tdr_ctx* ctx) {

@@ -136,6 +136,11 @@ struct tdr_ctx {
   bool have_scan = false;
   tdr::DevBuf scan_pack;     // P x 8 floats: per lattice cell (w_c*0.01*count_c for c<C, ..., slot7 = sum_c count_c)
   tdr::DevBuf hist;          // int32 bin counts
+  // cfg5 batch binning in progress (tdr_refine_begin .. tdr_refine_counts / tdr_refine_rebuild_map)
+  int refine_w = 0, refine_h = 0, refine_C = 0, refine_off_x = 0, refine_off_y = 0; float refine_res = 0.f;
+  // host chunks: H2D on a copy stream into one of two staging slots while the previous chunk's kernel runs
+  cudaStream_t copy_stream = nullptr; cudaEvent_t refine_copied[2] = {nullptr, nullptr}, refine_binned[2] = {nullptr, nullptr};
+  tdr::DevBuf refine_stage[2]; int refine_slot = 0;
 
   // ---- filter
   tdr_filter_params fp{};
@@ -205,9 +210,14 @@ int map_set_binary_layers(tdr_ctx*, const float*, int, int, int, float);
 int map_set_dist_layers(tdr_ctx*, const float*, const uint8_t*, int, int, int, float);
 int map_get_layers(tdr_ctx*, float*, uint8_t*);
 int map_get_geo_layers(tdr_ctx*, float*);
+int map_from_seeds(tdr_ctx*, int rows, int cols, int C, float resolution);   // seedbits already filled on the device
 // scan_render.cu
 int scan_render(tdr_ctx*, bool polar, float res, float ang_res, int d0, int d1, float* dev_img_out);
 int scan_pack(tdr_ctx*);
+int refine_begin(tdr_ctx*, float res, float cx, float cy, int width, int height, int C);
+int refine_add(tdr_ctx*, const float* xy, const int32_t* cls, long long n, bool on_device);
+int refine_counts(tdr_ctx*, uint8_t* maps_out);
+int refine_rebuild_map(tdr_ctx*, float resolution);
 int refine_bin(tdr_ctx*, const float* xy, const int32_t* cls, long long n, float res, float cx, float cy, int width,
                int height, int C, uint8_t* maps_out);
 // score.cu
