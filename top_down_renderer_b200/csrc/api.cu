@@ -562,7 +562,7 @@ static int normalize_resample(tdr_ctx* ctx, float u, int64_t M) {
     ctx->cur ^= 1;
     return TDR_OK;
   }
-  if (int e = normalize(ctx)) return e;
+  if (int e = normalize(ctx, true)) return e;
   if (int e = cache_ml_state(ctx, ctx->part[ctx->cur])) return e;
   stage_mark(ctx, TDR_STAGE_RESAMPLE);
   if (int e = resample(ctx, u, M, 0, M, &ctx->part[ctx->cur], &ctx->part[ctx->cur ^ 1])) return e;
@@ -654,7 +654,7 @@ int tdr_pf_update_gathered(tdr_ctx* ctx, const void* dev_all, int n_ranks, int64
   stage_mark(ctx, TDR_STAGE_NORMALIZE);
   if (int e = unpack_all(ctx, dev_all, n_ranks, n_local, true)) return e;
   ctx->ld_override = ctx->all.last_dist.as<float>();
-  int e = normalize(ctx);
+  int e = normalize(ctx, true);
   ctx->ld_override = nullptr;
   if (e) return e;
   if (int e2 = cache_ml_state(ctx, ctx->all)) return e2;

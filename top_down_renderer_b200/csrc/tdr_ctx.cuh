@@ -232,7 +232,7 @@ int score_mma(tdr_ctx*, float res, bool grid_mode, long long n_items, float grid
 int score_mma_list(tdr_ctx*, float res, bool grid_mode, long long n_items, float grid_scale, const int32_t* dev_shifts,
                    int n_shifts, bool* used);
 // weights.cu
-int normalize(tdr_ctx*);
+int normalize(tdr_ctx*, bool lazy_stddev = false);   // lazy: skip the lower-half deviation when no weight is NaN (stats[3] undefined then)
 int build_prefix(tdr_ctx*);
 int resample(tdr_ctx*, float u, long long M, long long i0, long long i1, Particles* src, Particles* dst);
 int cache_ml_state(tdr_ctx*, const Particles& src);

@@ -20,7 +20,11 @@ struct SeqJob {
   int mode;            // 0: addend = x (float).  1: addend = (double)(x - param)^2 for non-NaN x < param, else 0
                        //    (lower-half squared deviations, particle_filter.cpp:120-125; float accumulator, double adds)
   const float* param;  // device scalar (mode 1: the mean, scal[SC_MEAN])
+  // the whole chain is skipped (every kernel returns at once) when *skip_if == skip_val: the lower-half deviation is
+  // only ever used to replace NaN weights, so an update whose weights are all valid does not compute it
+  const unsigned long long* skip_if; unsigned long long skip_val;
 };
+__device__ __forceinline__ bool seq_skipped(const SeqJob& job) { return job.skip_if && *job.skip_if == job.skip_val; }
 #define TDR_MAX_JOBS 8
 struct SeqJobs { SeqJob j[TDR_MAX_JOBS]; };
 
@@ -209,6 +213,7 @@ __device__ float cta_exact_chain(Elem elem, long long count, bool strict, float*
 // path for chains with negative / NaN / inf elements)
 __global__ void __launch_bounds__(SEQ_THREADS) k_exact_seq(SeqJobs jobs, const int* __restrict__ only_flagged) {
   const SeqJob job = jobs.j[blockIdx.x];
+  if (seq_skipped(job)) return;
   if (only_flagged && only_flagged[blockIdx.x] == 0) return;
   __shared__ CtaSeqShared sh;
   const float total = cta_exact_chain<SEQ_THREADS>([&](long long j) { return seq_elem(job, j); }, job.count, job.mode != 0,
@@ -276,6 +281,7 @@ __device__ __forceinline__ IncPair block_scan_pairs(IncPair v, IncPair* s_warp, 
 // (0) approximate tile sums + irregular flag
 __global__ void __launch_bounds__(SQ_THREADS) k_seq_tile_sums(SeqJobs jobs, SeqWsAll ws) {
   const SeqJob job = jobs.j[blockIdx.y];
+  if (seq_skipped(job)) return;
   const long long base = (long long)blockIdx.x * SQ_TILE;
   if (base >= job.count) return;
   __shared__ double s_d[SQ_THREADS / 32];
@@ -303,6 +309,7 @@ __global__ void __launch_bounds__(SQ_THREADS) k_seq_tile_sums(SeqJobs jobs, SeqW
 // (0b) one CTA per job: exclusive scan of the tile sums (double) -> candidate binade window per tile
 __global__ void __launch_bounds__(SQ_THREADS) k_seq_plan(SeqJobs jobs, SeqWsAll ws) {
   const SeqJob job = jobs.j[blockIdx.x];
+  if (seq_skipped(job)) return;
   SeqWs w = ws.w[blockIdx.x];
   if (*w.flag) return;
   const int n_tiles = (int)((job.count + SQ_TILE - 1) / SQ_TILE);
@@ -328,7 +335,9 @@ __global__ void __launch_bounds__(SQ_THREADS) k_seq_plan(SeqJobs jobs, SeqWsAll 
       int e_hi = binade_of((float)(end * 1.4));
       if (start <= 0.0) e_lo = -127;
       if (e_hi - e_lo + 1 > SQ_KMAX) e_lo = 1000;          // too many binades inside the tile: resolve element-wise
-      w.win_lo[t] = e_lo;
+      int cnt = e_hi - e_lo + 1;                            // candidates actually needed (usually 2 of SQ_KMAX)
+      if (cnt < 1 || cnt > SQ_KMAX || start <= 0.0) cnt = SQ_KMAX;
+      w.win_lo[t] = (e_lo + 200) | (cnt << 16);
     }
     __syncthreads();
     if (threadIdx.x == SQ_THREADS - 1) s_carry = end;
@@ -339,10 +348,12 @@ __global__ void __launch_bounds__(SQ_THREADS) k_seq_plan(SeqJobs jobs, SeqWsAll 
 // (1) per tile: one IncPair per candidate binade
 __global__ void __launch_bounds__(SQ_THREADS) k_seq_tile_aggs(SeqJobs jobs, SeqWsAll ws) {
   const SeqJob job = jobs.j[blockIdx.y];
+  if (seq_skipped(job)) return;
   SeqWs w = ws.w[blockIdx.y];
   const long long base = (long long)blockIdx.x * SQ_TILE;
   if (base >= job.count || *w.flag) return;
-  const int e_lo = w.win_lo[blockIdx.x];
+  const int packed = w.win_lo[blockIdx.x];
+  const int e_lo = (packed & 0xffff) - 200, cnt = packed >> 16;
   if (e_lo > 500) return;
   __shared__ IncPair s_warp[SQ_THREADS / 32];
   double x[SQ_ITEMS];
@@ -353,6 +364,10 @@ __global__ void __launch_bounds__(SQ_THREADS) k_seq_tile_aggs(SeqJobs jobs, SeqW
   }
   for (int c = 0; c < SQ_KMAX; c++) {
     const int E = e_lo + c;
+    if (c >= cnt) {                                        // outside the planned window: the walk resolves element-wise
+      if (threadIdx.x == 0) { IncPair sat; sat.a = sat.b = TDR_INC_SAT; w.agg[(size_t)blockIdx.x * SQ_KMAX + c] = sat; }
+      continue;
+    }
     IncPair agg; agg.a = agg.b = 0;
     if (E <= 127) {
 #pragma unroll
@@ -442,6 +457,7 @@ __device__ float seq_resolve_tile(const double (&x)[SQ_ITEMS], bool strict, int 
 // (2) one CTA per job walks the tiles
 __global__ void __launch_bounds__(SQ_THREADS) k_seq_walk(SeqJobs jobs, SeqWsAll ws) {
   const SeqJob job = jobs.j[blockIdx.x];
+  if (seq_skipped(job)) return;
   SeqWs w = ws.w[blockIdx.x];
   if (*w.flag) return;
   const int n_tiles = (int)((job.count + SQ_TILE - 1) / SQ_TILE);
@@ -459,7 +475,7 @@ __global__ void __launch_bounds__(SQ_THREADS) k_seq_walk(SeqJobs jobs, SeqWsAll 
     const int t = t0 + threadIdx.x;
     IncPair pr; pr.a = pr.b = 0;
     if (t < n_tiles) {
-      const int e_lo = w.win_lo[t];
+      const int e_lo = (w.win_lo[t] & 0xffff) - 200;
       if (E >= e_lo && E < e_lo + SQ_KMAX) pr = w.agg[(size_t)t * SQ_KMAX + (E - e_lo)];
       else pr.a = pr.b = TDR_INC_SAT;                       // outside the window: resolve this tile element-wise
     }
@@ -515,6 +531,7 @@ __global__ void __launch_bounds__(SQ_THREADS) k_seq_walk(SeqJobs jobs, SeqWsAll 
 // (3) all tiles emit their prefix values from their exact start
 __global__ void __launch_bounds__(SQ_THREADS) k_seq_emit(SeqJobs jobs, SeqWsAll ws) {
   const SeqJob job = jobs.j[blockIdx.y];
+  if (seq_skipped(job)) return;
   SeqWs w = ws.w[blockIdx.y];
   const long long base = (long long)blockIdx.x * SQ_TILE;
   if (base >= job.count || *w.flag || !job.runmax_out) return;
@@ -852,7 +869,7 @@ static int eigen_sum(tdr_ctx* ctx, const float* x, long long n, int slot) {
   return TDR_OK;
 }
 
-int normalize(tdr_ctx* ctx) {
+int normalize(tdr_ctx* ctx, bool lazy_stddev) {
   const long long n = ctx->n_weights;
   TDR_REQUIRE(n > 0, TDR_ESTATE, "no weights");
   TDR_REQUIRE(n < (1ll << 31), TDR_EUNSUPPORTED, "too many weights");
@@ -874,7 +891,9 @@ int normalize(tdr_ctx* ctx) {
   k_under<<<blocks, 256, 0, ctx->stream>>>(w, n, scal, u64 + 2);
   // bottom_stddev (:120-125): float accumulator, double addends, sequential -> order-exact chain of mode 1
   jobs.j[0].total_out = scal + SC_BSRAW; jobs.j[0].skip_nan = 0; jobs.j[0].mode = 1; jobs.j[0].param = scal + SC_MEAN;
+  if (lazy_stddev) { jobs.j[0].skip_if = u64 + 1; jobs.j[0].skip_val = (unsigned long long)n; }     // num_valid == n: no NaN to replace
   if (int e = launch_seq(ctx, jobs, 1)) return e;
+  jobs.j[0].skip_if = nullptr;
   k_stats<<<1, 1, 0, ctx->stream>>>(scal, u64 + 2);
   k_fill_nan<<<blocks, 256, 0, ctx->stream>>>(w, n, scal);
   count_launch(ctx, 5);
