@@ -237,6 +237,7 @@ __global__ void __launch_bounds__(SEQ_THREADS) k_exact_seq(SeqJobs jobs, const i
 static const int SQ_THREADS = 512;
 static const int SQ_ITEMS = 4;
 static const int SQ_TILE = SQ_THREADS * SQ_ITEMS;     // 2048
+static const int SQ_HEAD = 128;         // elements at the start of a chain that one thread adds sequentially
 static const int SQ_KMAX = 4;                         // candidate binades per tile
 
 struct SeqWs {            // per-job workspace (device pointers)
@@ -385,6 +386,27 @@ __global__ void __launch_bounds__(SQ_THREADS) k_seq_tile_aggs(SeqJobs jobs, SeqW
 __device__ float seq_resolve_tile(const double (&x)[SQ_ITEMS], bool strict, int tile_len, float S, float* __restrict__ out,
                                   IncPair* s_warp, int* s_cross, uint32_t* s_mprev, float* s_S) {
   int first = 0;                       // elements [0, first) are already consumed
+  if (S == 0.f) {
+    // the start of a chain: the sum climbs a binade every element or two, and every crossing costs a round of the
+    // block-wide loop below (~2.5 us).  One thread adds the first SQ_HEAD elements one by one instead (~7 crossings).
+    __shared__ double s_head[SQ_HEAD];
+    const int H = tile_len < SQ_HEAD ? tile_len : SQ_HEAD;
+#pragma unroll
+    for (int k = 0; k < SQ_ITEMS; k++) {
+      const int j = threadIdx.x * SQ_ITEMS + k;
+      if (j < H) s_head[j] = x[k];
+    }
+    __syncthreads();
+    if (threadIdx.x == 0) {
+      float s = 0.f;
+      for (int j = 0; j < H; j++) { s = seq_add(s, s_head[j]); if (out) out[j] = s; }
+      *s_S = s;
+    }
+    __syncthreads();
+    S = *s_S; first = H;
+    __syncthreads();
+    if (H >= tile_len) return S;
+  }
   while (true) {
     const int E = binade_of(S);
     const uint32_t m_in = mant_of(S), limit = binade_limit(E);
