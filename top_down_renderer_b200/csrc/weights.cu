@@ -753,10 +753,13 @@ __global__ void __launch_bounds__(SEQ_THREADS) k_small_update(float* __restrict_
   for (int i = tid; i < n; i += SEQ_THREADS) { float v = w_s[i]; c += (v == v && v < mean) ? 1 : 0; }
   for (int o = 16; o > 0; o >>= 1) c += __shfl_xor_sync(0xffffffffu, c, o);
   if ((tid & 31) == 0 && c) atomicAdd(&s_cnt[1], c);
-  const float bsraw = cta_exact_chain<SEQ_THREADS>([&](long long j) {
+  // only ever used to replace NaN weights (:133): an update whose weights are all valid skips the chain (CTA-uniform)
+  float bsraw = 0.f;
+  if (nvalid != n) bsraw = cta_exact_chain<SEQ_THREADS>([&](long long j) {
     float w = w_s[j];
     if (w == w && w < mean) { float dv = TDR_FSUB(w, mean); return (double)dv * (double)dv; }
     return 0.0; }, n, true, nullptr, sh);
+  __syncthreads();
   const int nunder = s_cnt[1];
   const float bs = TDR_FSQRT(TDR_FDIV(bsraw, (float)nunder));
   const bool fallback = (sum == 0.f) || (nunder < 1);                  // :129
