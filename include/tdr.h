@@ -253,6 +253,16 @@ int tdr_pf_export_shard(tdr_ctx* ctx, void* dev_out, int64_t capacity_floats, in
 int tdr_pf_update_gathered(tdr_ctx* ctx, const void* dev_all, int n_ranks, int64_t n_local, float u, int64_t M,
                            int64_t i0, int64_t i1);
 /* pose over the all-gathered resampled set (same result on every rank and for every n_ranks) */
+/* The same update as TWO collectives, so that the big one hides behind compute: tdr_pf_export_split packs this
+ * rank's shard as wl[2][n] = (raw weight, last_dist) and states[7][n] = (init_x, init_y, dx, dy, theta, scale,
+ * have_init as 0/1); the caller all-gathers wl (8 B/particle), starts the all-gather of states (28 B/particle) on
+ * its communication stream, runs tdr_pf_normalize_gathered on the gathered wl blocks — the normalisation of all N
+ * weights — and, once the states have arrived, tdr_pf_resample_gathered (prefix, this rank's slice [i0, i1) of the
+ * M samples, state gather).  Bit-identical to tdr_pf_update_gathered. */
+int tdr_pf_export_split(tdr_ctx* ctx, void* dev_wl, void* dev_states);
+int tdr_pf_normalize_gathered(tdr_ctx* ctx, const void* dev_wl_all, int n_ranks, int64_t n_local);
+int tdr_pf_resample_gathered(tdr_ctx* ctx, const void* dev_states_all, int n_ranks, int64_t n_local, float u, int64_t M,
+                             int64_t i0, int64_t i1);
 int tdr_pf_pose_gathered(tdr_ctx* ctx, const void* dev_all, int n_ranks, int64_t n_local, float mean[4],
                          float cov_mean[16], float ml[4], float cov_ml[16]);
 /* replace the resident weights by an externally gathered vector living on the device

@@ -389,8 +389,9 @@ def test_cfg1_mini_fixture_through_the_c_abi():
 
 
 # ---- multi-GPU path, ranks emulated one after another on one device (no kernel waits on another) -----------------
-@pytest.mark.parametrize("world_size", [2, 4])
-def test_sharded_update_is_independent_of_world_size(world, world_size):
+@pytest.mark.parametrize("world_size,split", [(2, False), (4, False), (2, True), (3, True)])
+def test_sharded_update_is_independent_of_world_size(world, world_size, split):
+    """split: the two-collective protocol (weights + last_dist, then the states behind the normalisation)"""
     import torch
     from top_down_renderer_b200 import sharded
     n_local = 500
@@ -418,12 +419,21 @@ def test_sharded_update_is_independent_of_world_size(world, world_size):
         c.scan_render_polar(4.0, ANG_RES, N_THETA, N_R, want=False)
         c.pf_score(4.0, want=False)
         c.pf_export_shard(blocks.data_ptr() + 4 * g * sharded.SHARD_ROWS * n_local, sharded.SHARD_ROWS * n_local, True)
+        if split:
+            if g == 0:
+                wl_all = torch.empty(world_size * 2 * n_local, dtype=torch.float32, device="cuda:0")
+                st_all = torch.empty(world_size * 7 * n_local, dtype=torch.float32, device="cuda:0")
+            c.pf_export_split(wl_all.data_ptr() + 4 * g * 2 * n_local, st_all.data_ptr() + 4 * g * 7 * n_local)
         c.sync()
         ranks.append(c)
     got_states, blocks2 = [], torch.empty_like(blocks)
     for g, c in enumerate(ranks):
         i0, i1 = sharded.sample_slice(M, g, world_size)
-        c.pf_update_gathered(blocks.data_ptr(), world_size, n_local, u, M, i0, i1)
+        if split:
+            c.pf_normalize_gathered(wl_all.data_ptr(), world_size, n_local)
+            c.pf_resample_gathered(st_all.data_ptr(), world_size, n_local, u, M, i0, i1)
+        else:
+            c.pf_update_gathered(blocks.data_ptr(), world_size, n_local, u, M, i0, i1)
         c.sync()
         assert np.array_equal(c.pf_get_weights(n_total).view(np.uint32), w_one.view(np.uint32))
         got_states.append(c.pf_get_states())

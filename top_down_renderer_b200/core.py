@@ -304,6 +304,17 @@ class Context:
         check(self._lib.tdr_pf_update_gathered(self._h, C.c_void_p(dev_ptr), int(n_ranks), C.c_int64(n_local),
                                                C.c_float(u), C.c_int64(M), C.c_int64(i0), C.c_int64(i1)))
 
+    # the same update as two collectives (weights + last_dist first, the states while the normalisation runs)
+    def pf_export_split(self, wl_ptr, states_ptr):
+        check(self._lib.tdr_pf_export_split(self._h, C.c_void_p(wl_ptr), C.c_void_p(states_ptr)))
+
+    def pf_normalize_gathered(self, wl_all_ptr, n_ranks, n_local):
+        check(self._lib.tdr_pf_normalize_gathered(self._h, C.c_void_p(wl_all_ptr), int(n_ranks), C.c_int64(n_local)))
+
+    def pf_resample_gathered(self, states_all_ptr, n_ranks, n_local, u, M, i0, i1):
+        check(self._lib.tdr_pf_resample_gathered(self._h, C.c_void_p(states_all_ptr), int(n_ranks), C.c_int64(n_local),
+                                                 C.c_float(u), C.c_int64(M), C.c_int64(i0), C.c_int64(i1)))
+
     def pf_pose_gathered(self, dev_ptr, n_ranks, n_local, want_ml=True):
         mean = np.zeros(4, dtype=np.float32)
         cov = np.zeros(16, dtype=np.float32)

@@ -80,6 +80,32 @@ __global__ void k_unpack_all(const float* __restrict__ in, int ranks, long long 
   }
 }
 
+// split wire format (two all-gathers: the 8 B/particle the normalisation needs first, the states behind it)
+__global__ void k_pack_split(ShardSrc s, long long n, float* __restrict__ wl, float* __restrict__ st) {
+  for (long long i = (long long)blockIdx.x * blockDim.x + threadIdx.x; i < n; i += (long long)gridDim.x * blockDim.x) {
+    wl[i] = s.w[i]; wl[n + i] = s.ld[i];
+    st[i] = s.ix[i]; st[n + i] = s.iy[i]; st[2 * n + i] = s.dx[i]; st[3 * n + i] = s.dy[i];
+    st[4 * n + i] = s.th[i]; st[5 * n + i] = s.sc[i]; st[6 * n + i] = s.hi[i] ? 1.f : 0.f;
+  }
+}
+__global__ void k_unpack_wl(const float* __restrict__ in, int ranks, long long n_local, float* __restrict__ w, float* __restrict__ ld) {
+  const long long N = (long long)ranks * n_local;
+  for (long long j = (long long)blockIdx.x * blockDim.x + threadIdx.x; j < N; j += (long long)gridDim.x * blockDim.x) {
+    const long long g = j / n_local, i = j - g * n_local;
+    const float* b = in + g * 2 * n_local;
+    w[j] = b[i]; ld[j] = b[n_local + i];
+  }
+}
+__global__ void k_unpack_states(const float* __restrict__ in, int ranks, long long n_local, ShardDst d) {
+  const long long N = (long long)ranks * n_local;
+  for (long long j = (long long)blockIdx.x * blockDim.x + threadIdx.x; j < N; j += (long long)gridDim.x * blockDim.x) {
+    const long long g = j / n_local, i = j - g * n_local;
+    const float* b = in + g * 7 * n_local;
+    d.ix[j] = b[i]; d.iy[j] = b[n_local + i]; d.dx[j] = b[2 * n_local + i]; d.dy[j] = b[3 * n_local + i];
+    d.th[j] = b[4 * n_local + i]; d.sc[j] = b[5 * n_local + i]; d.hi[j] = b[6 * n_local + i] != 0.f ? 1 : 0;
+  }
+}
+
 static int grid_for(tdr_ctx* ctx, long long n, int threads = 256) {
   long long b = (n + threads - 1) / threads;
   long long cap = (long long)ctx->sm_count * 8;
@@ -660,6 +686,59 @@ int tdr_pf_update_gathered(tdr_ctx* ctx, const void* dev_all, int n_ranks, int64
   if (int e2 = cache_ml_state(ctx, ctx->all)) return e2;
   stage_mark(ctx, TDR_STAGE_RESAMPLE);
   if (int e2 = resample(ctx, u, M, i0, i1, &ctx->all, &ctx->part[ctx->cur ^ 1])) return e2;
+  ctx->cur ^= 1;
+  stage_mark(ctx, TDR_N_STAGES);
+  ctx->stage_valid = ctx->profiling;
+  return TDR_OK;
+}
+
+// ---- the same update as two collectives: weights + last_dist first (8 B/particle), the states (28 B/particle) while
+// the normalisation of the N weights runs
+int tdr_pf_export_split(tdr_ctx* ctx, void* dev_wl, void* dev_states) {
+  CTX_CHECK(ctx);
+  Particles& pt = ctx->part[ctx->cur];
+  TDR_REQUIRE(pt.n > 0 && dev_wl && dev_states, TDR_EINVAL, "no particles / null buffers");
+  TDR_REQUIRE(ctx->n_weights == pt.n, TDR_ESTATE, "weights (%lld) and particles (%lld) differ", (long long)ctx->n_weights, (long long)pt.n);
+  ShardSrc s; s.w = ctx->weights.as<float>();
+  s.ix = pt.init_x.as<float>(); s.iy = pt.init_y.as<float>(); s.dx = pt.dx.as<float>(); s.dy = pt.dy.as<float>();
+  s.th = pt.theta.as<float>(); s.sc = pt.scale.as<float>(); s.ld = pt.last_dist.as<float>(); s.hi = pt.have_init.as<uint8_t>();
+  k_pack_split<<<grid_for(ctx, pt.n), 256, 0, ctx->stream>>>(s, pt.n, reinterpret_cast<float*>(dev_wl), reinterpret_cast<float*>(dev_states));
+  count_launch(ctx);
+  TDR_CUDA(cudaGetLastError());
+  return TDR_OK;
+}
+int tdr_pf_normalize_gathered(tdr_ctx* ctx, const void* dev_wl_all, int n_ranks, int64_t n_local) {
+  CTX_CHECK(ctx);
+  const int64_t N = (int64_t)n_ranks * n_local;
+  TDR_REQUIRE(dev_wl_all && n_ranks >= 1 && n_local > 0 && N < (1ll << 31), TDR_EINVAL, "bad gathered block");
+  stage_mark(ctx, TDR_STAGE_NORMALIZE);
+  if (int e = ctx->all.reserve(N)) return e;
+  if (int e = ctx->weights.reserve((size_t)N * 4)) return e;
+  k_unpack_wl<<<grid_for(ctx, N), 256, 0, ctx->stream>>>(reinterpret_cast<const float*>(dev_wl_all), n_ranks, n_local,
+                                                        ctx->weights.as<float>(), ctx->all.last_dist.as<float>());
+  count_launch(ctx);
+  TDR_CUDA(cudaGetLastError());
+  ctx->all.n = N; ctx->n_weights = N;
+  ctx->ld_override = ctx->all.last_dist.as<float>();
+  const int e = normalize(ctx, true);
+  ctx->ld_override = nullptr;
+  return e;
+}
+int tdr_pf_resample_gathered(tdr_ctx* ctx, const void* dev_states_all, int n_ranks, int64_t n_local, float u, int64_t M,
+                             int64_t i0, int64_t i1) {
+  CTX_CHECK(ctx);
+  const int64_t N = (int64_t)n_ranks * n_local;
+  TDR_REQUIRE(dev_states_all && N == ctx->all.n && N == ctx->n_weights, TDR_ESTATE, "tdr_pf_normalize_gathered has not run on this set");
+  Particles& a = ctx->all;
+  ShardDst d; d.w = nullptr;
+  d.ix = a.init_x.as<float>(); d.iy = a.init_y.as<float>(); d.dx = a.dx.as<float>(); d.dy = a.dy.as<float>();
+  d.th = a.theta.as<float>(); d.sc = a.scale.as<float>(); d.ld = a.last_dist.as<float>(); d.hi = a.have_init.as<uint8_t>();
+  k_unpack_states<<<grid_for(ctx, N), 256, 0, ctx->stream>>>(reinterpret_cast<const float*>(dev_states_all), n_ranks, n_local, d);
+  count_launch(ctx);
+  TDR_CUDA(cudaGetLastError());
+  if (int e = cache_ml_state(ctx, ctx->all)) return e;
+  stage_mark(ctx, TDR_STAGE_RESAMPLE);
+  if (int e = resample(ctx, u, M, i0, i1, &ctx->all, &ctx->part[ctx->cur ^ 1])) return e;
   ctx->cur ^= 1;
   stage_mark(ctx, TDR_N_STAGES);
   ctx->stage_valid = ctx->profiling;
