@@ -451,7 +451,13 @@ __global__ void __launch_bounds__(128 * T * R + 64, MmaCfg<T, R, ATM, G>::kCtasP
     const bool leader = elect_one();
     const uint32_t idesc = (1u << 4) | ((uint32_t)(RING_N >> 3) << 17) | ((uint32_t)(128 >> 4) << 24);
     const uint32_t plane = (uint32_t)ring_rows * 16;           // LBO of the ring operand
-    const uint32_t sA_u = smem_u32(sA), sA2_u = smem_u32(sA2), sRing_u = smem_u32(sRing), sB2_u = smem_u32(sB2);
+    const uint32_t sA_u = smem_u32(sA), sA2_u = smem_u32(sA2);
+    // pin the addresses this loop lives on in registers: left to itself ptxas re-derives the shared-window base
+    // (S2R CgaCtaId + LEA) in every iteration of the critical path
+    uint32_t sRing_u = smem_u32(sRing), sB2_u = smem_u32(sB2), q_full = bar_full, q_empty = bar_empty, q_rfull = bar_rfull,
+             q_rempty = bar_rempty, q_accum = bar_accum, q_b2full = bar_b2full, q_b2empty = bar_b2empty, q_tmem = tmem_base;
+    asm volatile("" : "+r"(sRing_u), "+r"(sB2_u), "+r"(q_full), "+r"(q_empty), "+r"(q_rfull), "+r"(q_rempty), "+r"(q_accum),
+                 "+r"(q_b2full), "+r"(q_b2empty), "+r"(q_tmem));
     uint32_t st = 0, ph = 0;                                   // stage slot / parity (continue across batches)
     uint32_t rsl = 0, rph = 0, bsl = 0, bph = 0, asl = 0;      // ring, tot-block and flag-group slots
     for (long long batch = blockIdx.x; batch < n_batches; batch += gridDim.x) {
@@ -460,14 +466,14 @@ __global__ void __launch_bounds__(128 * T * R + 64, MmaCfg<T, R, ATM, G>::kCtasP
       int sr = 0, sg = 0, grp = 0;                             // stage within the ring / within the 16-cell group; group
       for (int k = 0; k < K_ITERS; k++) {
         if (sr == 0) {
-          mbar_wait(bar_rfull + 8 * rsl, rph);
+          mbar_wait(q_rfull + 8 * rsl, rph);
           ring_desc = umma_desc(sRing_u + rsl * RING_SLOT_BYTES, plane, 128);
           cur_rsl = rsl;
           rsl ^= 1u; if (rsl == 0) rph ^= 1u;
         }
-        mbar_wait(bar_full + 8 * st, ph);
+        mbar_wait(q_full + 8 * st, ph);
         const bool group_done = sg == STAGES_PER_GROUP - 1 || k == K_ITERS - 1;
-        if (group_done) mbar_wait(bar_b2full + 8 * bsl, bph);
+        if (group_done) mbar_wait(q_b2full + 8 * bsl, bph);
         tc_fence_after();
         if (leader) {
 #pragma unroll
@@ -476,10 +482,10 @@ __global__ void __launch_bounds__(128 * T * R + 64, MmaCfg<T, R, ATM, G>::kCtasP
 #pragma unroll
             for (int tt = 0; tt < T; tt++) {
               if (ATM)
-                umma_f16_ts(tmem_base + (uint32_t)(tt * ACC), tmem_base + (uint32_t)(Cfg::kACol + (g * T + tt) * 8) + st * Cfg::kACols,
+                umma_f16_ts(q_tmem + (uint32_t)(tt * ACC), q_tmem + (uint32_t)(Cfg::kACol + (g * T + tt) * 8) + st * Cfg::kACols,
                             bcnt, idesc, (k > 0 || g > 0) ? 1u : 0u);
               else
-                umma_f16(tmem_base + (uint32_t)(tt * ACC), umma_desc(sA_u + st * Cfg::kStageBytes + (g * T + tt) * A_TILE, A_LBO, 128),
+                umma_f16(q_tmem + (uint32_t)(tt * ACC), umma_desc(sA_u + st * Cfg::kStageBytes + (g * T + tt) * A_TILE, A_LBO, 128),
                          bcnt, idesc, (k > 0 || g > 0) ? 1u : 0u);
             }
           }
@@ -489,17 +495,17 @@ __global__ void __launch_bounds__(128 * T * R + 64, MmaCfg<T, R, ATM, G>::kCtasP
 #pragma unroll
             for (int tt = 0; tt < T; tt++) {
               if (ATM)
-                umma_f16_ts(tmem_base + (uint32_t)(tt * ACC + RING_N), tmem_base + (uint32_t)(Cfg::kA2Col + tt * 8) + asl * (T * 8),
+                umma_f16_ts(q_tmem + (uint32_t)(tt * ACC + RING_N), q_tmem + (uint32_t)(Cfg::kA2Col + tt * 8) + asl * (T * 8),
                             btot, idesc, grp > 0 ? 1u : 0u);
               else
-                umma_f16(tmem_base + (uint32_t)(tt * ACC + RING_N), umma_desc(sA2_u + (asl * T + tt) * A2_TILE, 2048, 128), btot, idesc,
+                umma_f16(q_tmem + (uint32_t)(tt * ACC + RING_N), umma_desc(sA2_u + (asl * T + tt) * A2_TILE, 2048, 128), btot, idesc,
                          grp > 0 ? 1u : 0u);
             }
           }
-          umma_commit(bar_empty + 8 * st);          // implies tcgen05.fence::before_thread_sync
-          if (group_done) umma_commit(bar_b2empty + 8 * bsl);
-          if (sr == stages_per_ring - 1) umma_commit(bar_rempty + 8 * cur_rsl);   // ring slot free once these MMAs retire
-          if (k == K_ITERS - 1) umma_commit(bar_accum);
+          umma_commit(q_empty + 8 * st);          // implies tcgen05.fence::before_thread_sync
+          if (group_done) umma_commit(q_b2empty + 8 * bsl);
+          if (sr == stages_per_ring - 1) umma_commit(q_rempty + 8 * cur_rsl);   // ring slot free once these MMAs retire
+          if (k == K_ITERS - 1) umma_commit(q_accum);
         }
         __syncwarp();
         if (group_done) {
