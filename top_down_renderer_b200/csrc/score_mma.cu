@@ -458,66 +458,119 @@ __global__ void __launch_bounds__(128 * T * R + 64, MmaCfg<T, R, ATM, G>::kCtasP
              q_rempty = bar_rempty, q_accum = bar_accum, q_b2full = bar_b2full, q_b2empty = bar_b2empty, q_tmem = tmem_base;
     asm volatile("" : "+r"(sRing_u), "+r"(sB2_u), "+r"(q_full), "+r"(q_empty), "+r"(q_rfull), "+r"(q_rempty), "+r"(q_accum),
                  "+r"(q_b2full), "+r"(q_b2empty), "+r"(q_tmem));
-    uint32_t st = 0, ph = 0;                                   // stage slot / parity (continue across batches)
-    uint32_t rsl = 0, rph = 0, bsl = 0, bph = 0, asl = 0;      // ring, tot-block and flag-group slots
-    for (long long batch = blockIdx.x; batch < n_batches; batch += gridDim.x) {
-      uint64_t ring_desc = 0;
-      uint32_t cur_rsl = 0;
-      int sr = 0, sg = 0, grp = 0;                             // stage within the ring / within the 16-cell group; group
-      for (int k = 0; k < K_ITERS; k++) {
-        if (sr == 0) {
-          mbar_wait(q_rfull + 8 * rsl, rph);
-          ring_desc = umma_desc(sRing_u + rsl * RING_SLOT_BYTES, plane, 128);
-          cur_rsl = rsl;
-          rsl ^= 1u; if (rsl == 0) rph ^= 1u;
-        }
-        mbar_wait(q_full + 8 * st, ph);
-        const bool group_done = sg == STAGES_PER_GROUP - 1 || k == K_ITERS - 1;
-        if (group_done) mbar_wait(q_b2full + 8 * bsl, bph);
-        tc_fence_after();
-        if (leader) {
-#pragma unroll
-          for (int g = 0; g < G; g++) {
-            const uint64_t bcnt = ring_desc + (uint64_t)(uint32_t)(sr * G + g);      // window start advances 16 B per cell
-#pragma unroll
-            for (int tt = 0; tt < T; tt++) {
-              if (ATM)
-                umma_f16_ts(q_tmem + (uint32_t)(tt * ACC), q_tmem + (uint32_t)(Cfg::kACol + (g * T + tt) * 8) + st * Cfg::kACols,
-                            bcnt, idesc, (k > 0 || g > 0) ? 1u : 0u);
-              else
-                umma_f16(q_tmem + (uint32_t)(tt * ACC), umma_desc(sA_u + st * Cfg::kStageBytes + (g * T + tt) * A_TILE, A_LBO, 128),
-                         bcnt, idesc, (k > 0 || g > 0) ? 1u : 0u);
-            }
+    if (ATM && T == 1) {
+      // the tensor-memory path: every per-stage quantity is a RUNNING value (barrier addresses, the stage's TMEM
+      // columns, the window descriptor), advanced by an add and wrapped by a compare — no multiplies, no re-derivation
+      uint32_t ph = 0, rsl = 0, rph = 0, bph = 0;
+      uint32_t full_a = q_full, empty_a = q_empty;                       // + 8 per stage, wrap after NS
+      uint32_t a_cols = q_tmem + (uint32_t)Cfg::kACol;                   // + kACols per stage, wrap after NS
+      uint32_t b2full_a = q_b2full, b2empty_a = q_b2empty, b2_addr = sB2_u;   // + 8 / + B2_BYTES per group, wrap after NB2
+      uint32_t a2_cols = q_tmem + (uint32_t)Cfg::kA2Col;                 // + 8 per group, wrap after NA2
+      const uint32_t full_end = q_full + 8 * NS, a_end = q_tmem + (uint32_t)(Cfg::kACol + NS * Cfg::kACols);
+      const uint32_t b2full_end = q_b2full + 8 * NB2, a2_end = q_tmem + (uint32_t)(Cfg::kA2Col + NA2 * 8);
+      for (long long batch = blockIdx.x; batch < n_batches; batch += gridDim.x) {
+        uint64_t bdesc = 0;                                              // window of the stage's first cell (+ G per stage)
+        uint32_t ring_empty_a = 0;
+        int sr = 0, sg = 0;
+        uint32_t acc = 0, acc_norm = 0;
+        for (int k = 0; k < K_ITERS; k++) {
+          if (sr == 0) {
+            mbar_wait(q_rfull + 8 * rsl, rph);
+            bdesc = umma_desc(sRing_u + rsl * RING_SLOT_BYTES, plane, 128);
+            ring_empty_a = q_rempty + 8 * rsl;
+            rsl ^= 1u; if (rsl == 0) rph ^= 1u;
           }
+          mbar_wait(full_a, ph);
+          const bool group_done = sg == STAGES_PER_GROUP - 1 || k == K_ITERS - 1;
+          if (group_done) mbar_wait(b2full_a, bph);
+          tc_fence_after();
+          if (leader) {
+            umma_stage_ts<G>(q_tmem, a_cols, bdesc, idesc, acc, 1u);
+            if (group_done) {
+              // normalisation: the known flags of this group's cells against the tot block
+              umma_f16_ts(q_tmem + (uint32_t)RING_N, a2_cols, umma_desc(b2_addr, RING_N * 16, 128), idesc, acc_norm);
+            }
+            umma_commit(empty_a);                   // implies tcgen05.fence::before_thread_sync
+            if (group_done) umma_commit(b2empty_a);
+            if (sr == stages_per_ring - 1) umma_commit(ring_empty_a);   // ring slot free once these MMAs retire
+            if (k == K_ITERS - 1) umma_commit(q_accum);
+          }
+          __syncwarp();
+          acc = 1u;
+          bdesc += (uint64_t)G;
           if (group_done) {
-            // normalisation: the known flags of this group's cells against the tot block
-            const uint64_t btot = umma_desc(sB2_u + bsl * B2_BYTES, RING_N * 16, 128);
-#pragma unroll
-            for (int tt = 0; tt < T; tt++) {
-              if (ATM)
-                umma_f16_ts(q_tmem + (uint32_t)(tt * ACC + RING_N), q_tmem + (uint32_t)(Cfg::kA2Col + tt * 8) + asl * (T * 8),
-                            btot, idesc, grp > 0 ? 1u : 0u);
-              else
-                umma_f16(q_tmem + (uint32_t)(tt * ACC + RING_N), umma_desc(sA2_u + (asl * T + tt) * A2_TILE, 2048, 128), btot, idesc,
-                         grp > 0 ? 1u : 0u);
-            }
-          }
-          umma_commit(q_empty + 8 * st);          // implies tcgen05.fence::before_thread_sync
-          if (group_done) umma_commit(q_b2empty + 8 * bsl);
-          if (sr == stages_per_ring - 1) umma_commit(q_rempty + 8 * cur_rsl);   // ring slot free once these MMAs retire
-          if (k == K_ITERS - 1) umma_commit(q_accum);
+            sg = 0; acc_norm = 1u;
+            b2full_a += 8; b2empty_a += 8; b2_addr += B2_BYTES;
+            if (b2full_a == b2full_end) { b2full_a = q_b2full; b2empty_a = q_b2empty; b2_addr = sB2_u; bph ^= 1u; }
+            a2_cols += 8; if (a2_cols == a2_end) a2_cols = q_tmem + (uint32_t)Cfg::kA2Col;
+          } else sg++;
+          if (++sr == stages_per_ring) sr = 0;
+          full_a += 8; empty_a += 8; a_cols += (uint32_t)Cfg::kACols;
+          if (full_a == full_end) { full_a = q_full; empty_a = q_empty; a_cols = q_tmem + (uint32_t)Cfg::kACol; ph ^= 1u; }
         }
-        __syncwarp();
-        if (group_done) {
-          sg = 0; grp++;
-          if (++bsl == NB2) { bsl = 0; bph ^= 1u; }
-          if (++asl == NA2) asl = 0;
-        } else sg++;
-        if (++sr == stages_per_ring) sr = 0;
-        if (++st == NS) { st = 0; ph ^= 1u; }
+      }
+    } else {
+    uint32_t st = 0, ph = 0;                                   // stage slot / parity (continue across batches)
+      uint32_t rsl = 0, rph = 0, bsl = 0, bph = 0, asl = 0;      // ring, tot-block and flag-group slots
+      for (long long batch = blockIdx.x; batch < n_batches; batch += gridDim.x) {
+        uint64_t ring_desc = 0;
+        uint32_t cur_rsl = 0;
+        int sr = 0, sg = 0, grp = 0;                             // stage within the ring / within the 16-cell group; group
+        for (int k = 0; k < K_ITERS; k++) {
+          if (sr == 0) {
+            mbar_wait(q_rfull + 8 * rsl, rph);
+            ring_desc = umma_desc(sRing_u + rsl * RING_SLOT_BYTES, plane, 128);
+            cur_rsl = rsl;
+            rsl ^= 1u; if (rsl == 0) rph ^= 1u;
+          }
+          mbar_wait(q_full + 8 * st, ph);
+          const bool group_done = sg == STAGES_PER_GROUP - 1 || k == K_ITERS - 1;
+          if (group_done) mbar_wait(q_b2full + 8 * bsl, bph);
+          tc_fence_after();
+          if (leader) {
+  #pragma unroll
+            for (int g = 0; g < G; g++) {
+              const uint64_t bcnt = ring_desc + (uint64_t)(uint32_t)(sr * G + g);      // window start advances 16 B per cell
+  #pragma unroll
+              for (int tt = 0; tt < T; tt++) {
+                if (ATM)
+                  umma_f16_ts(q_tmem + (uint32_t)(tt * ACC), q_tmem + (uint32_t)(Cfg::kACol + (g * T + tt) * 8) + st * Cfg::kACols,
+                              bcnt, idesc, (k > 0 || g > 0) ? 1u : 0u);
+                else
+                  umma_f16(q_tmem + (uint32_t)(tt * ACC), umma_desc(sA_u + st * Cfg::kStageBytes + (g * T + tt) * A_TILE, A_LBO, 128),
+                           bcnt, idesc, (k > 0 || g > 0) ? 1u : 0u);
+              }
+            }
+            if (group_done) {
+              // normalisation: the known flags of this group's cells against the tot block
+              const uint64_t btot = umma_desc(sB2_u + bsl * B2_BYTES, RING_N * 16, 128);
+  #pragma unroll
+              for (int tt = 0; tt < T; tt++) {
+                if (ATM)
+                  umma_f16_ts(q_tmem + (uint32_t)(tt * ACC + RING_N), q_tmem + (uint32_t)(Cfg::kA2Col + tt * 8) + asl * (T * 8),
+                              btot, idesc, grp > 0 ? 1u : 0u);
+                else
+                  umma_f16(q_tmem + (uint32_t)(tt * ACC + RING_N), umma_desc(sA2_u + (asl * T + tt) * A2_TILE, 2048, 128), btot, idesc,
+                           grp > 0 ? 1u : 0u);
+              }
+            }
+            umma_commit(q_empty + 8 * st);          // implies tcgen05.fence::before_thread_sync
+            if (group_done) umma_commit(q_b2empty + 8 * bsl);
+            if (sr == stages_per_ring - 1) umma_commit(q_rempty + 8 * cur_rsl);   // ring slot free once these MMAs retire
+            if (k == K_ITERS - 1) umma_commit(q_accum);
+          }
+          __syncwarp();
+          if (group_done) {
+            sg = 0; grp++;
+            if (++bsl == NB2) { bsl = 0; bph ^= 1u; }
+            if (++asl == NA2) asl = 0;
+          } else sg++;
+          if (++sr == stages_per_ring) sr = 0;
+          if (++st == NS) { st = 0; ph ^= 1u; }
+        }
       }
     }
-  }
+    }
   tc_fence_before();
   __syncthreads();
   if (warp == GW + 1) tmem_dealloc(tmem_base, Cfg::kTmemCols);
