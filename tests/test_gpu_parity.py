@@ -796,3 +796,99 @@ def test_propagate_device_rng(world):
     assert np.isfinite(z).all() and np.abs(z.mean(0)).max() < 0.01 and np.abs(z.std(0) - 1).max() < 0.01
     assert abs(np.corrcoef(z[:, 0], z[:, 1])[0, 1]) < 0.01 and abs(np.corrcoef(z[:-1, 2], z[1:, 2])[0, 1]) < 0.01
     assert np.abs(z).max() < 6.5                          # 8e5 draws
+
+
+# ---- edge cases of the lean lattice index, the phase-split layout, the folded arg-min, chunked binning, propagate
+def test_mma_lattice_index_at_the_map_border_and_nan_centres(world, mma_ctx):
+    """centres whose lattice coordinates fall exactly on the rounding / border boundaries (-0.5 rounds away to -1 =
+    off the map; rows - 0.5 rounds to rows = off the map; just inside stays inside), centres that are NaN / inf, and
+    centres far outside: the tensor-core path's interval test must make the reference's decisions (weights within
+    1e-5 relative of the oracle, same NaN pattern)"""
+    st, ld = synth.particles_global(6000, world.class_map, seed=21)
+    edge = [-0.5, np.nextafter(np.float32(-0.5), np.float32(0)), 0.0, 0.49999997, 0.5, world.w - 0.5,
+            np.nextafter(np.float32(world.w - 0.5), np.float32(0)), world.w - 1.0, world.w - 1.5, 1e7, -1e7, np.nan, np.inf, -np.inf]
+    k = 0
+    for ex in edge:
+        for ey in edge:
+            st["init_x_px"][k], st["init_y_px"][k] = ex, ey
+            st["dx_m"][k] = st["dy_m"][k] = 0.0
+            k += 1
+    # and rows of particles sitting right on the four borders (the whole lattice half in, half out)
+    st["init_x_px"][k:k + 200] = np.linspace(-3, 3, 200, dtype=np.float32)
+    st["init_y_px"][k + 200:k + 400] = np.linspace(world.h - 4, world.h + 2, 200, dtype=np.float32)
+    got, want, st_o = _score_both(world, mma_ctx, st, ld, 4.0)
+    e = rel_err(got, want)
+    assert np.isfinite(e).all(), "NaN pattern differs"
+    assert e.max() <= WEIGHT_RTOL, e.max()
+    got_st = mma_ctx.pf_get_states()
+    assert np.array_equal(got_st["have_init"], st_o["have_init"])
+    same = ~np.isnan(want)
+    assert np.array_equal(got_st["theta"][same], st_o["theta"][same])
+
+
+def test_phase_split_map_with_a_width_that_is_not_a_multiple_of_the_stride():
+    """1003 px wide map, lattice stride 4 and 8: the last phase rows are padded; costs equal the plain layout's bits"""
+    wd = make_world(h=300, w=1003)
+    c = make_ctx(wd)
+    c.set_score_impl(2)
+    c.scan_set_polar_images(wd.scan)
+    shifts = np.arange(100, dtype=np.int32)
+    for stride in (4, 8):
+        centers = synth.grid_centers(wd.h, wd.w, stride)
+        per_row = len(np.arange(stride // 2, wd.w, stride))
+        centers = np.ascontiguousarray(centers[per_row * 10 - 40: per_row * 10 + per_row + 40])   # a full row incl. both borders
+        got = c.grid_costs(centers, 2.0, 4.0, shifts)
+        key = c.grid_key_decode(c.grid_best_key())
+        assert key == c.grid_best()
+        os.environ["TDR_GRID_PHASE_LOG2"] = "0"
+        try:
+            plain = c.grid_costs(centers, 2.0, 4.0, shifts)
+        finally:
+            del os.environ["TDR_GRID_PHASE_LOG2"]
+        assert np.array_equal(got.view(np.uint32), plain.view(np.uint32))
+        want = orc.cost_grid(centers[:300], 2.0, wd.fp, wd.layers, wd.mask, 1.0, wd.tab, N_THETA, N_R, wd.scan, 4.0, shifts)
+        e = rel_err(got[:300], want)
+        assert np.isfinite(e).all() and e.max() <= WEIGHT_RTOL, e.max()
+    c.close()
+
+
+def test_grid_key_when_no_hypothesis_is_valid(world, mma_ctx):
+    """every centre far off the map: all costs NaN, the folded key says so (like tdr_grid_best)"""
+    centers = np.stack([np.full(4200, -5000.0, np.float32), np.linspace(0, 100, 4200, dtype=np.float32)], axis=1)
+    mma_ctx.scan_set_polar_images(world.scan)
+    got = mma_ctx.grid_costs(centers, 2.0, 4.0, np.arange(100, dtype=np.int32))
+    assert np.isnan(got).all()
+    cost, idx = mma_ctx.grid_key_decode(mma_ctx.grid_best_key())
+    ref_cost, ref_idx = mma_ctx.grid_best()
+    assert np.isnan(cost) and idx == -1 and np.isnan(ref_cost) and ref_idx == -1
+
+
+def test_refine_empty_batch_rebuilds_an_unknown_map():
+    from top_down_renderer_b200.core import Context
+    c = Context(0)
+    c.refine_begin(0.5, 10.0, 10.0, 64, 48, 3)
+    c.refine_add(np.zeros((0, 2), np.float32), np.zeros(0, np.int32))
+    cnt = c.refine_counts()
+    assert cnt.shape == (3, 48, 64) and not cnt.any()
+    c.refine_rebuild_map(1.0)
+    d, m = c.map_get_layers()
+    c.close()
+    layers = np.ones((3, 64, 48), dtype=np.float32)               # no class anywhere: every binary layer is 1
+    d_o, m_o = orc.compute_dists(layers, 1.0)
+    assert np.array_equal(d.view(np.uint32), d_o.view(np.uint32)) and np.array_equal(m, m_o)
+
+
+def test_propagate_without_motion_is_bit_exact(world):
+    """trans = 0: the rotation contributes exact zeros, so cos / sin rounding cannot matter — every field equals the
+    literal libstdc++ restatement bit for bit (stddev 0 for pose and heading, scale jitter N(1, 0.02) since 2 / 0 = inf)"""
+    st, ld = synth.particles_tracking(20_000, world.pose, world.heading, seed=77)
+    want, last_o, z = orc.propagate(st, 0.0, 0.0, 0.125, False, 0.3, 0.1, 5)
+    c = make_ctx(world)
+    c.pf_set_states(st, ld)
+    c.pf_propagate((0.0, 0.0), 0.125, False, 0.3, 0.1, z)
+    got, last_g = c.pf_get_states(), c.pf_get_last_dist()
+    c.close()
+    for k in ("dx_m", "dy_m", "theta", "scale"):
+        assert np.array_equal(got[k].view(np.uint32), want[k].view(np.uint32)), k
+    assert np.array_equal(last_g.view(np.uint32), last_o.view(np.uint32))
+    assert not np.array_equal(got["scale"], st["scale"])
