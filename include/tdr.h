@@ -97,6 +97,16 @@ int tdr_map_set_dist_layers(tdr_ctx* ctx, const float* layers, const uint8_t* ma
                             int num_classes, float resolution);
 /* class_maps_ / class_mask_ as the reference holds them after computeDists (for the .eig cache,
  * getClassesAtPoint (top_down_map.cpp:159-175) and parity tests).  layers: C col-major rows x cols. */
+/* SURVEY 8f rank 3 — the vector-map constructor path: TopDownMap::getRasterMap (top_down_map.cpp:391-408) with
+ * samplePts (:367-389) and getClasses (:328-365, even-odd rule per polygon, then "only one ground type per cell" over
+ * the exclusive classes), followed by computeDists.  verts_xy: the vertices of all polygons back to back as
+ * loadSvg (:66-114) produces them (x, svg_height - y); polygon k = vertices [poly_start[k], poly_start[k+1]) of
+ * flattened class poly_class[k]; map_w / map_h: the svg size; exclusive: Params::exclusive_classes as the node builds
+ * it (top_down_render.cpp:177-181).  layers_out (may be NULL): the C binary class maps (col-major rows x cols,
+ * rows = (int)(map_h / resolution)), what saveRasterizedMaps writes to the raster cache. */
+int tdr_map_set_polygons(tdr_ctx* ctx, const float* verts_xy, const int32_t* poly_start, const int32_t* poly_class, int n_poly,
+                         int map_w, int map_h, float rot, int num_classes, float resolution, const int32_t* exclusive,
+                         int n_exclusive, float* layers_out);
 int tdr_map_get_layers(tdr_ctx* ctx, float* layers, uint8_t* mask);
 int tdr_map_info(tdr_ctx* ctx, int* rows, int* cols, int* num_classes, float* resolution);
 /* a5: geo layers (getGeoRasterMap + computeDists, top_down_map.cpp:410-427, :58) from the

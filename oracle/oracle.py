@@ -296,3 +296,20 @@ def propagate(states, tx, ty, omega, scale_freeze, pos_cov, theta_cov, seed):
                         C.c_float(omega), int(bool(scale_freeze)), C.c_float(pos_cov), C.c_float(theta_cov),
                         C.c_uint32(seed), _p(z, c_float_p))
     return st, last, z
+
+
+def raster_polygons(polys, poly_class, map_w, map_h, rot, resolution, C_, exclusive):
+    """getRasterMap + getClasses (top_down_map.cpp:328-408): polys = list of (n_k, 2) float32 vertex arrays (x, y), their
+    flattened classes, the svg size -> C binary layers (C, cols, rows) = col-major rows x cols, 0 inside, 1 outside"""
+    start = np.zeros(len(polys) + 1, dtype=np.int32)
+    start[1:] = np.cumsum([len(p) for p in polys])
+    verts = (np.concatenate([np.asarray(p, dtype=np.float32).reshape(-1, 2) for p in polys]) if polys
+             else np.zeros((0, 2), np.float32))
+    verts = np.ascontiguousarray(verts, dtype=np.float32)
+    pc = np.ascontiguousarray(poly_class, dtype=np.int32)
+    ex = np.ascontiguousarray(exclusive, dtype=np.int32)
+    rows, cols = int(map_h / resolution), int(map_w / resolution)
+    out = np.empty((C_, cols, rows), dtype=np.float32)
+    lib().orc_raster_polygons(_p(verts, c_float_p), _p(start, c_int_p), _p(pc, c_int_p), len(polys), int(map_w), int(map_h),
+                              C.c_float(rot), C.c_float(resolution), C_, _p(ex, c_int_p), len(ex), _p(out, c_float_p))
+    return out

@@ -730,4 +730,72 @@ ORC_API void orc_propagate(OrcState* st, float* last_dist, long n, float tx, flo
   }
 }
 
+// -----------------------------------------------------------------------------
+// SURVEY 8f rank 3  vector map -> binary class layers   src/top_down_map.cpp:391-408 (getRasterMap),
+// :367-389 (samplePts), :328-365 (getClasses: even-odd rule over every polygon of a class, then "only one ground
+// type per cell" over the exclusive classes)
+// -----------------------------------------------------------------------------
+// verts: x, y pairs of all polygons back to back (y already flipped as loadSvg does, :89); polygon k owns vertices
+// [poly_start[k], poly_start[k+1]) and belongs to flattened class poly_class[k] (polygons of a class in the order
+// given).  layers: C col-major rows x cols images, 0 inside a polygon of the class, 1 elsewhere, with
+// rows = (int)(map_h / resolution), cols = (int)(map_w / resolution) (:399-400).
+ORC_API void orc_raster_polygons(const float* verts, const int* poly_start, const int* poly_class, int n_poly, int map_w,
+                                 int map_h, float rot, float resolution, int C, const int* exclusive, int n_excl,
+                                 float* layers) {
+  const int rows = (int)(map_h / resolution), cols = (int)(map_w / resolution);
+  const size_t L = (size_t)rows * cols;
+  auto linsp = [](int size, float sres_, int i) -> float {       // Eigen LinSpaced, as in orc_local_map_cart
+    float low = (float)(-sres_ * (size - 1) / 2.);
+    float high = (float)(sres_ * (size - 1) / 2.);
+    if (size == 1) return low;
+    float step = (high - low) / (float)(size - 1);
+    bool flip = std::abs(high) < std::abs(low);
+    int size1 = size - 1;
+    if (flip) return (i == 0) ? low : (high - (float)(size1 - i) * step);
+    return (i == size1) ? high : (low + (float)i * step);
+  };
+  const float cr = cosf(rot), sr = sinf(rot);
+  const float c0 = (float)map_w / 2, c1 = (float)map_h / 2;       // map_size.cast<float>() / 2  (:405)
+  std::vector<float> py(L), px(L);
+  for (size_t p = 0; p < L; p++) {
+    float a = linsp(rows, resolution, (int)(p % rows));           // pts(0, p)
+    float b = linsp(cols, resolution, (int)(p / rows));           // pts(1, p)
+    float ar = cr * a + (-sr) * b, br = sr * a + cr * b;          // rotm * pts
+    py[p] = ar + c1;                                              // x_vals += center[1]
+    px[p] = br + c0;                                              // y_vals += center[0]
+  }
+  for (int c = 0; c < C; c++) {
+    float* out = layers + (size_t)c * L;
+    for (size_t p = 0; p < L; p++) out[p] = -1.f;                 // class_fills = -1
+    std::vector<float> buf(L);
+    for (int k = 0; k < n_poly; k++) {
+      if (poly_class[k] != c) continue;
+      const float* v = verts + 2 * (size_t)poly_start[k];
+      const int n = poly_start[k + 1] - poly_start[k];
+      for (size_t p = 0; p < L; p++) buf[p] = -1.f;
+      int j = n - 1;
+      for (int i = 0; i < n; i++) {
+        const float xi = v[2 * i], yi = v[2 * i + 1], xj = v[2 * j], yj = v[2 * j + 1];
+        for (size_t p = 0; p < L; p++) {
+          const bool a = (py[p] < yi) != (py[p] < yj);
+          const bool b = px[p] < (xi + ((xj - xi) * (py[p] - yi) / (yj - yi)));
+          buf[p] *= (float)(-2 * (int)(a && b)) + 1;              // -2*cond.cast<float>() + 1   (:343-346)
+        }
+        j = i;
+      }
+      for (size_t p = 0; p < L; p++) out[p] = std::max(out[p], buf[p]);
+    }
+    for (size_t p = 0; p < L; p++) { out[p] *= -1; out[p] += 1; out[p] /= 2; }       // :351-353
+  }
+  for (int a = 0; a < n_excl; a++) {                              // :357-364
+    const int under = exclusive[a];
+    for (int b = 0; b < n_excl; b++) {
+      const int cls = exclusive[b];
+      if (under < cls)
+        for (size_t p = 0; p < L; p++) layers[(size_t)under * L + p] += 1 - layers[(size_t)cls * L + p];
+    }
+    for (size_t p = 0; p < L; p++) layers[(size_t)under * L + p] = std::min(layers[(size_t)under * L + p], 1.f);
+  }
+}
+
 ORC_API int orc_abi_version() { return 1; }

@@ -892,3 +892,52 @@ def test_propagate_without_motion_is_bit_exact(world):
         assert np.array_equal(got[k].view(np.uint32), want[k].view(np.uint32)), k
     assert np.array_equal(last_g.view(np.uint32), last_o.view(np.uint32))
     assert not np.array_equal(got["scale"], st["scale"])
+
+
+# ---- vector map (polygons) -> class layers -> distance fields
+def _random_polygons(rng, n, w, h, C):
+    polys, cls = [], []
+    for _ in range(n):
+        k = int(rng.integers(3, 12))
+        cx, cy = rng.uniform(-10, w + 10), rng.uniform(-10, h + 10)
+        ang = np.sort(rng.uniform(0, 2 * np.pi, k))
+        rad = rng.uniform(3, 60) * rng.uniform(0.3, 1.0, k)                  # star-shaped, concave as a rule
+        p = np.stack([cx + rad * np.cos(ang), cy + rad * np.sin(ang)], axis=1).astype(np.float32)
+        if rng.random() < 0.3:
+            p = np.rint(p).astype(np.float32)                                # vertices on pixel-centre ties and horizontal edges
+        polys.append(p)
+        cls.append(int(rng.integers(0, C)))
+    return polys, cls
+
+
+@pytest.mark.parametrize("rot,resolution", [(0.0, 1.0), (0.0, 0.5), (0.3, 1.0)])
+def test_polygon_map_layers_and_distance_fields(rot, resolution):
+    """TopDownMap's vector-map path (getRasterMap + getClasses + computeDists) on random concave polygons: binary class
+    layers and distance fields bit-exact against the oracle; the node's exclusive-class list (num_classes zeros, then
+    the ids, top_down_render.cpp:177-181) is taken as it is"""
+    from top_down_renderer_b200.core import Context
+    rng = np.random.default_rng(17)
+    C, W, H = 5, 330, 270
+    polys, cls = _random_polygons(rng, 120, W, H, C)
+    polys.append(np.array([[40, 40], [200, 40], [200, 180], [40, 180], [40, 40], [80, 80], [80, 140], [160, 140], [160, 80], [80, 80]],
+                          np.float32))                                        # a ring traced as one path: even-odd hole
+    cls.append(1)
+    exclusive = [0] * C + [0, 1, 2, 3]
+    want = orc.raster_polygons(polys, cls, W, H, rot, resolution, C, exclusive)
+    c = Context(0)
+    got = c.map_set_polygons(polys, cls, W, H, rot, C, resolution, exclusive)
+    d, m = c.map_get_layers()
+    c.close()
+    assert got.shape == want.shape and np.array_equal(got.view(np.uint32), want.view(np.uint32))
+    assert 0.05 < (want == 0).mean() < 0.8
+    d_o, m_o = orc.compute_dists(want.copy(), resolution)
+    assert np.array_equal(d.view(np.uint32), d_o.view(np.uint32)) and np.array_equal(m, m_o)
+
+
+def test_polygon_map_without_polygons_is_all_unknown():
+    from top_down_renderer_b200.core import Context
+    c = Context(0)
+    got = c.map_set_polygons([], [], 40, 30, 0.0, 3, 1.0, [])
+    d, m = c.map_get_layers()
+    c.close()
+    assert (got == 1).all() and (m == 1).all() and (d == 0).all()

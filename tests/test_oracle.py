@@ -328,3 +328,31 @@ def test_propagate_known_answer_without_noise():
     assert np.allclose(a["dx_m"], [4.0, -3.0], atol=1e-6) and np.allclose(a["dy_m"], [4.0, 3.0], atol=1e-6)
     assert np.allclose(a["theta"], [0.25, math.pi / 2 + 0.25], atol=1e-6) and np.allclose(last, [5.0, 5.0], atol=1e-6)
     assert np.array_equal(a["scale"], st["scale"])
+
+
+# ---- vector map -> class layers (top_down_map.cpp:328-408)
+def test_raster_polygons_known_answers():
+    """sample point of pixel (row r, col c) is (x, y) = (c + 0.5, r + 0.5) at resolution 1; a layer is 0 inside a polygon of
+    its class; overlapping polygons of one class are a union (max over polygons), a polygon traced twice in one path
+    is a hole (even-odd); exclusive classes: the lower class yields where a higher one is present"""
+    sq = np.array([[2, 2], [6, 2], [6, 5], [2, 5]], np.float32)
+    out = orc.raster_polygons([sq], [0], 10, 8, 0.0, 1.0, 2, [])
+    lay = out[0].T                                           # rows x cols
+    want = np.ones((8, 10), np.float32)
+    want[2:5, 2:6] = 0
+    assert np.array_equal(lay, want) and (out[1] == 1).all()
+    # union of two overlapping squares of the same class, and a second class on top with exclusivity
+    sq2 = sq + np.float32([2, 1])
+    out = orc.raster_polygons([sq, sq2, sq2], [0, 0, 1], 10, 8, 0.0, 1.0, 2, [0, 1])
+    want0 = want.copy(); want0[3:6, 4:8] = 0
+    want1 = np.ones((8, 10), np.float32); want1[3:6, 4:8] = 0
+    assert np.array_equal(out[1].T, want1)
+    assert np.array_equal(out[0].T, np.minimum(want0 + (1 - want1), 1))        # class 0 removed under class 1
+    # a ring: outer square and inner square in ONE path -> the inner part is outside (even-odd)
+    ring = np.array([[1, 1], [9, 1], [9, 7], [1, 7], [1, 1], [3, 3], [3, 5], [7, 5], [7, 3], [3, 3]], np.float32)
+    out = orc.raster_polygons([ring], [0], 10, 8, 0.0, 1.0, 1, [])
+    lay = out[0].T
+    assert lay[1, 1] == 0 and lay[6, 8] == 0 and lay[3, 3] == 1 and lay[4, 6] == 1 and lay[0, 0] == 1
+    # half resolution: 2 px per unit -> sample points at 0.25, 0.75, ...
+    out = orc.raster_polygons([sq], [0], 10, 8, 0.0, 0.5, 1, [])
+    assert out.shape == (1, 20, 16) and out[0].T[4:10, 4:12].sum() == 0 and out[0].sum() == 20 * 16 - 6 * 8

@@ -121,6 +121,22 @@ class Context:
         check(self._lib.tdr_map_set_polar_table(self._h, _pf(tab), int(n_theta), int(n_r)))
         self._P = n_theta * n_r
 
+    def map_set_polygons(self, polys, poly_class, map_w, map_h, rot, num_classes, resolution, exclusive, want_layers=True):
+        """vector map (getRasterMap + getClasses + computeDists); returns the binary class layers (C, cols, rows)"""
+        start = np.zeros(len(polys) + 1, dtype=np.int32)
+        start[1:] = np.cumsum([len(p) for p in polys])
+        verts = (np.concatenate([np.asarray(p, dtype=np.float32).reshape(-1, 2) for p in polys]) if len(polys)
+                 else np.zeros((0, 2), np.float32))
+        verts = np.ascontiguousarray(verts, dtype=np.float32)
+        pc = np.ascontiguousarray(poly_class, dtype=np.int32)
+        ex = np.ascontiguousarray(exclusive, dtype=np.int32)
+        rows, cols = int(map_h / resolution), int(map_w / resolution)
+        out = np.empty((num_classes, cols, rows), dtype=np.float32) if want_layers else None
+        check(self._lib.tdr_map_set_polygons(self._h, _pf(verts), _pi(start), _pi(pc), len(polys), int(map_w), int(map_h),
+                                             C.c_float(rot), int(num_classes), C.c_float(resolution), _pi(ex), len(ex),
+                                             _pf(out) if want_layers else None))
+        return out
+
     def map_local_polar(self, centers_xy, scale, res):
         centers = np.ascontiguousarray(centers_xy, dtype=np.float32).reshape(-1, 2)
         n = centers.shape[0]

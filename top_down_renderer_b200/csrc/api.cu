@@ -228,6 +228,13 @@ int tdr_map_set_dist_layers(tdr_ctx* ctx, const float* layers, const uint8_t* ma
   CTX_CHECK(ctx);
   return map_set_dist_layers(ctx, layers, mask, rows, cols, num_classes, resolution);
 }
+int tdr_map_set_polygons(tdr_ctx* ctx, const float* verts_xy, const int32_t* poly_start, const int32_t* poly_class, int n_poly,
+                         int map_w, int map_h, float rot, int num_classes, float resolution, const int32_t* exclusive,
+                         int n_exclusive, float* layers_out) {
+  CTX_CHECK(ctx);
+  return map_set_polygons(ctx, verts_xy, poly_start, poly_class, n_poly, map_w, map_h, rot, num_classes, resolution, exclusive,
+                          n_exclusive, layers_out);
+}
 int tdr_map_get_layers(tdr_ctx* ctx, float* layers, uint8_t* mask) { CTX_CHECK(ctx); return map_get_layers(ctx, layers, mask); }
 int tdr_map_get_geo_layers(tdr_ctx* ctx, float* geo) { CTX_CHECK(ctx); return map_get_geo_layers(ctx, geo); }
 int tdr_map_info(tdr_ctx* ctx, int* rows, int* cols, int* num_classes, float* resolution) {

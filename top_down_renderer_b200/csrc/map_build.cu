@@ -275,6 +275,130 @@ int map_set_binary_layers(tdr_ctx* ctx, const float* layers, int rows, int cols,
   return TDR_OK;
 }
 
+// ---- vector map -> binary class layers (getRasterMap :391-408, samplePts :367-389, getClasses :328-365)
+// Eigen LinSpaced(size, -res*(size-1)/2., res*(size-1)/2.)[i] (same as k_local_cart's)
+__device__ __forceinline__ float raster_linspaced(int size, float sres, int i) {
+  float low = (float)((double)TDR_FMUL(-sres, (float)(size - 1)) / 2.);
+  float high = (float)((double)TDR_FMUL(sres, (float)(size - 1)) / 2.);
+  if (size == 1) return low;
+  float step = TDR_FDIV(TDR_FSUB(high, low), (float)(size - 1));
+  bool flip = fabsf(high) < fabsf(low);
+  int size1 = size - 1;
+  if (flip) return (i == 0) ? low : TDR_FSUB(high, TDR_FMUL((float)(size1 - i), step));
+  return (i == size1) ? high : TDR_FADD(low, TDR_FMUL((float)i, step));
+}
+struct PolyParams {
+  const float2* verts; const int32_t* start; const int32_t* cls; const float4* bbox; int n_poly;   // bbox: xmin, xmax, ymin, ymax
+  int rows, cols, C; float resolution, cr, sr, c0, c1;
+  int excl[2 * TDR_MAX_CLASSES]; int n_excl;
+};
+// One thread per sample point (= map pixel).  The reference runs the even-odd rule edge by edge over ALL points
+// (O(pixels x edges), :339-349); a polygon can only flip points whose y lies inside its y-range and whose x is not
+// clearly to its right, and left of it the flips of a closed polygon cancel — those polygons are skipped (exactly),
+// the edges of the rest are evaluated with the reference's fp32 expression.
+__global__ void k_raster_polygons(PolyParams q, float* __restrict__ layers) {
+  const size_t L = (size_t)q.rows * q.cols;
+  const size_t p = (size_t)blockIdx.x * blockDim.x + threadIdx.x;
+  if (p >= L) return;
+  const float a = raster_linspaced(q.rows, q.resolution, (int)(p % q.rows));   // pts(0, p)
+  const float b = raster_linspaced(q.cols, q.resolution, (int)(p / q.rows));   // pts(1, p)
+  const float py = TDR_FADD(TDR_FADD(TDR_FMUL(q.cr, a), TDR_FMUL(-q.sr, b)), q.c1);   // rotm * pts, += center[1]
+  const float px = TDR_FADD(TDR_FADD(TDR_FMUL(q.sr, a), TDR_FMUL(q.cr, b)), q.c0);    // += center[0]
+  float fills[TDR_MAX_CLASSES];
+#pragma unroll
+  for (int c = 0; c < TDR_MAX_CLASSES; c++) fills[c] = -1.f;                 // class_fills = -1
+  for (int k = 0; k < q.n_poly; k++) {
+    const float4 bb = __ldg(q.bbox + k);
+    if (py < bb.z || !(py < bb.w)) continue;                                 // no edge straddles this y
+    if (!(px < bb.y + 1.0f) || px < bb.x - 1.0f) continue;                   // right of it: no flip; left of it: an even number
+    const int s0 = q.start[k], n = q.start[k + 1] - s0;
+    float buf = -1.f;                                                        // class_fills_buf = -1
+    float2 vj = __ldg(q.verts + s0 + n - 1);
+    for (int i = 0; i < n; i++) {
+      const float2 vi = __ldg(q.verts + s0 + i);
+      const bool ca = (py < vi.y) != (py < vj.y);
+      const bool cb = px < TDR_FADD(vi.x, TDR_FDIV(TDR_FMUL(TDR_FSUB(vj.x, vi.x), TDR_FSUB(py, vi.y)), TDR_FSUB(vj.y, vi.y)));
+      if (ca && cb) buf = -buf;                                              // *= -2 * cond + 1
+      vj = vi;
+    }
+    const int c = q.cls[k];
+#pragma unroll
+    for (int cc = 0; cc < TDR_MAX_CLASSES; cc++) if (cc == c) fills[cc] = fmaxf(fills[cc], buf);
+  }
+#pragma unroll
+  for (int c = 0; c < TDR_MAX_CLASSES; c++) fills[c] = TDR_FDIV(TDR_FADD(TDR_FMUL(fills[c], -1.f), 1.f), 2.f);   // :351-353
+  for (int ia = 0; ia < q.n_excl; ia++) {                                   // "only one ground type per cell" :357-364
+    const int under = q.excl[ia];
+    float u = 0.f;
+#pragma unroll
+    for (int cc = 0; cc < TDR_MAX_CLASSES; cc++) if (cc == under) u = fills[cc];
+    for (int ib = 0; ib < q.n_excl; ib++) {
+      const int cls = q.excl[ib];
+      if (under < cls) {
+        float v = 0.f;
+#pragma unroll
+        for (int cc = 0; cc < TDR_MAX_CLASSES; cc++) if (cc == cls) v = fills[cc];
+        u = TDR_FADD(u, TDR_FSUB(1.f, v));
+      }
+    }
+    u = fminf(u, 1.f);
+#pragma unroll
+    for (int cc = 0; cc < TDR_MAX_CLASSES; cc++) if (cc == under) fills[cc] = u;
+  }
+#pragma unroll
+  for (int c = 0; c < TDR_MAX_CLASSES; c++) if (c < q.C) layers[(size_t)c * L + p] = fills[c];
+}
+
+int map_set_polygons(tdr_ctx* ctx, const float* verts, const int32_t* poly_start, const int32_t* poly_class, int n_poly, int map_w,
+                     int map_h, float rot, int C, float resolution, const int32_t* exclusive, int n_excl, float* layers_out) {
+  TDR_REQUIRE(n_poly >= 0 && map_w > 0 && map_h > 0 && resolution > 0.f, TDR_EINVAL, "bad polygon map arguments");
+  TDR_REQUIRE(n_poly == 0 || (verts && poly_start && poly_class), TDR_EINVAL, "null polygon arrays");
+  TDR_REQUIRE(n_excl >= 0 && n_excl <= 2 * TDR_MAX_CLASSES && (n_excl == 0 || exclusive), TDR_EINVAL, "bad exclusive class list");
+  const int rows = (int)(map_h / resolution), cols = (int)(map_w / resolution);   // :399-400
+  if (int e = map_alloc(ctx, rows, cols, C, resolution)) return e;
+  const size_t L = (size_t)rows * cols;
+  const int n_verts = n_poly ? poly_start[n_poly] : 0;
+  std::vector<float4> bbox((size_t)(n_poly > 0 ? n_poly : 1));
+  for (int k = 0; k < n_poly; k++) {
+    TDR_REQUIRE(poly_class[k] >= 0 && poly_class[k] < C && poly_start[k + 1] > poly_start[k], TDR_EINVAL, "bad polygon %d", k);
+    float4 bb = make_float4(INFINITY, -INFINITY, INFINITY, -INFINITY);
+    for (int i = poly_start[k]; i < poly_start[k + 1]; i++) {
+      bb.x = fminf(bb.x, verts[2 * i]); bb.y = fmaxf(bb.y, verts[2 * i]);
+      bb.z = fminf(bb.z, verts[2 * i + 1]); bb.w = fmaxf(bb.w, verts[2 * i + 1]);
+    }
+    bbox[k] = bb;
+  }
+  for (int k = 0; k < n_excl; k++) TDR_REQUIRE(exclusive[k] >= 0 && exclusive[k] < C, TDR_EINVAL, "exclusive class %d out of range", exclusive[k]);
+  // device staging: layers (C*L floats) in scratch; polygon arrays in scratch2
+  const size_t off_start = (size_t)n_verts * 8, off_cls = off_start + (size_t)(n_poly + 1) * 4, off_bbox = ((off_cls + (size_t)n_poly * 4 + 15) / 16) * 16;
+  if (int e = ctx->scratch.reserve(L * C * 4)) return e;
+  if (int e = ctx->scratch2.reserve(off_bbox + (size_t)(n_poly + 1) * 16 + L)) return e;   // + L: map_get_layers' mask staging
+  unsigned char* d2 = ctx->scratch2.as<unsigned char>();
+  if (n_poly > 0) {
+    TDR_CUDA(cudaMemcpyAsync(d2, verts, (size_t)n_verts * 8, cudaMemcpyHostToDevice, ctx->stream));
+    TDR_CUDA(cudaMemcpyAsync(d2 + off_start, poly_start, (size_t)(n_poly + 1) * 4, cudaMemcpyHostToDevice, ctx->stream));
+    TDR_CUDA(cudaMemcpyAsync(d2 + off_cls, poly_class, (size_t)n_poly * 4, cudaMemcpyHostToDevice, ctx->stream));
+    TDR_CUDA(cudaMemcpyAsync(d2 + off_bbox, bbox.data(), (size_t)n_poly * 16, cudaMemcpyHostToDevice, ctx->stream));
+  }
+  PolyParams q; memset(&q, 0, sizeof(q));
+  q.verts = reinterpret_cast<const float2*>(d2); q.start = reinterpret_cast<const int32_t*>(d2 + off_start);
+  q.cls = reinterpret_cast<const int32_t*>(d2 + off_cls); q.bbox = reinterpret_cast<const float4*>(d2 + off_bbox); q.n_poly = n_poly;
+  q.rows = rows; q.cols = cols; q.C = C; q.resolution = resolution; q.cr = cosf(rot); q.sr = sinf(rot);
+  q.c0 = (float)map_w / 2; q.c1 = (float)map_h / 2;
+  q.n_excl = n_excl;
+  for (int k = 0; k < n_excl; k++) q.excl[k] = exclusive[k];
+  k_raster_polygons<<<(unsigned)((L + 255) / 256), 256, 0, ctx->stream>>>(q, ctx->scratch.as<float>());
+  dim3 blk(32, 8), grd((rows + 31) / 32, (cols + 7) / 8);
+  k_layers_to_seeds<<<grd, blk, 0, ctx->stream>>>(ctx->scratch.as<float>(), rows, cols, C, ctx->seedbits.as<uint8_t>());
+  count_launch(ctx, 2);
+  TDR_CUDA(cudaGetLastError());
+  if (layers_out) TDR_CUDA(cudaMemcpyAsync(layers_out, ctx->scratch.p, L * C * 4, cudaMemcpyDeviceToHost, ctx->stream));
+  if (int e = run_edt(ctx, ctx->seedbits.as<uint8_t>(), rows, cols, C, resolution, true, nullptr)) return e;
+  TDR_CUDA(cudaStreamSynchronize(ctx->stream));      // bbox (host vector) and the caller's arrays may go away
+  ctx->have_map = true; ctx->have_seeds = true;
+  return TDR_OK;
+}
+
 // seeds produced on the device (ctx->scratch2, rows*cols bytes, k_layers_to_seeds' bit layout) -> map + distance fields
 int map_from_seeds(tdr_ctx* ctx, int rows, int cols, int C, float resolution) {
   if (int e = map_alloc(ctx, rows, cols, C, resolution)) return e;

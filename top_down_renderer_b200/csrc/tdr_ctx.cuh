@@ -210,7 +210,9 @@ int map_set_binary_layers(tdr_ctx*, const float*, int, int, int, float);
 int map_set_dist_layers(tdr_ctx*, const float*, const uint8_t*, int, int, int, float);
 int map_get_layers(tdr_ctx*, float*, uint8_t*);
 int map_get_geo_layers(tdr_ctx*, float*);
-int map_from_seeds(tdr_ctx*, int rows, int cols, int C, float resolution);   // seedbits already filled on the device
+int map_from_seeds(tdr_ctx*, int rows, int cols, int C, float resolution);
+int map_set_polygons(tdr_ctx*, const float* verts, const int32_t* poly_start, const int32_t* poly_class, int n_poly, int map_w, int map_h,
+                     float rot, int C, float resolution, const int32_t* exclusive, int n_excl, float* layers_out);   // seedbits already filled on the device
 // scan_render.cu
 int scan_render(tdr_ctx*, bool polar, float res, float ang_res, int d0, int d1, float* dev_img_out);
 int scan_pack(tdr_ctx*);
