@@ -8,6 +8,10 @@
                       and cannot be built here (F1), so this is the only externally pinned stage.
 * kat_small.npz    — hand-checkable known-answer cases (tiny map / 4x2 polar image / 5 particles), values derived
                      in the comments of tests/test_oracle.py.
+* widen_mini.npz   — oracle outputs for the rows added beyond the first path: propagate with the reference's
+                     shared mt19937 + libstdc++ normal_distribution (states, last_dist and the standard variates behind the
+                     draws), and the vector-map path (polygons -> binary class layers); regression pins read by the CPU
+                     and the GPU tests.
 * cfg1_mini.npz    — oracle outputs on a seeded cfg1-style world (regression pin; the GPU tests compare the CUDA
                      path with the same file, so the fixture travels to the GPU box where /root/reference and
                      cv2 need not exist).
@@ -83,9 +87,34 @@ def cfg1_mini():
                         idx=idx, mean=mean, cov=cov, ml=ml)
 
 
+def widen_mini():
+    rng = np.random.default_rng(5)
+    st, _ = synth.particles_tracking(256, (120.0, 90.0), 0.4, seed=5)
+    out = {}
+    for freeze in (0, 1):
+        a, last, z = orc.propagate(st, 0.7, -0.2, 0.03, bool(freeze), 0.3, 0.1, 1234)
+        out[f"prop_states_{freeze}"], out[f"prop_last_{freeze}"], out[f"prop_z_{freeze}"] = a, last, z
+    polys, cls = [], []
+    for _ in range(24):
+        k = int(rng.integers(3, 9))
+        ang = np.sort(rng.uniform(0, 2 * np.pi, k))
+        rad = rng.uniform(4, 30) * rng.uniform(0.4, 1.0, k)
+        cx, cy = rng.uniform(0, 96), rng.uniform(0, 72)
+        polys.append(np.stack([cx + rad * np.cos(ang), cy + rad * np.sin(ang)], axis=1).astype(np.float32))
+        cls.append(int(rng.integers(0, 3)))
+    start = np.zeros(len(polys) + 1, dtype=np.int32)
+    start[1:] = np.cumsum([len(p) for p in polys])
+    excl = np.array([0, 0, 0, 0, 1], dtype=np.int32)
+    layers = orc.raster_polygons(polys, cls, 96, 72, 0.0, 1.0, 3, excl)
+    np.savez_compressed(os.path.join(HERE, "widen_mini.npz"), prop_in=st, prop_args=np.float32([0.7, -0.2, 0.03, 0.3, 0.1]),
+                        poly_verts=np.concatenate(polys), poly_start=start, poly_class=np.int32(cls), poly_excl=excl,
+                        poly_layers=layers.astype(np.uint8), **out)
+
+
 if __name__ == "__main__":
     edt_cv2()
     cfg1_mini()
+    widen_mini()
     for f in sorted(os.listdir(HERE)):
         if f.endswith(".npz"):
             print(f, os.path.getsize(os.path.join(HERE, f)))

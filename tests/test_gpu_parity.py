@@ -941,3 +941,30 @@ def test_polygon_map_without_polygons_is_all_unknown():
     d, m = c.map_get_layers()
     c.close()
     assert (got == 1).all() and (m == 1).all() and (d == 0).all()
+
+
+def test_widen_mini_fixture_through_the_c_abi(world):
+    """the committed fixture of the widened rows (propagate with the reference's RNG stream, vector map) against the
+    CUDA path: polygon layers to the bit; propagate from the fixture's variates — scale to the bit, heading 1 ulp,
+    positions within the cos / sin ulp"""
+    from top_down_renderer_b200.core import Context
+    g = _gold("widen_mini.npz")
+    tx, ty, omega, pos_cov, theta_cov = (float(v) for v in g["prop_args"])
+    c = make_ctx(world)
+    for freeze in (0, 1):
+        c.pf_set_states(g["prop_in"], None)
+        c.pf_propagate((tx, ty), omega, bool(freeze), pos_cov, theta_cov, g[f"prop_z_{freeze}"])
+        got, last = c.pf_get_states(), c.pf_get_last_dist()
+        want = g[f"prop_states_{freeze}"]
+        assert np.array_equal(got["scale"].view(np.uint32), want["scale"].view(np.uint32))
+        assert np.abs(got["theta"].view(np.int32).astype(np.int64) - want["theta"].view(np.int32).astype(np.int64)).max() <= 1
+        tol = 2.5e-7 * (abs(tx) + abs(ty)) + 2.5e-7 * max(np.abs(want["dx_m"]).max(), np.abs(want["dy_m"]).max(), 1.0)
+        assert np.abs(got["dx_m"] - want["dx_m"]).max() <= tol and np.abs(got["dy_m"] - want["dy_m"]).max() <= tol
+        assert np.abs(last - g[f"prop_last_{freeze}"]).max() <= 1e-6
+    c.close()
+    st = g["poly_start"]
+    polys = [g["poly_verts"][st[k]:st[k + 1]] for k in range(len(st) - 1)]
+    c = Context(0)
+    lay = c.map_set_polygons(polys, g["poly_class"], 96, 72, 0.0, 3, 1.0, g["poly_excl"])
+    c.close()
+    assert np.array_equal(lay.astype(np.uint8), g["poly_layers"])

@@ -356,3 +356,22 @@ def test_raster_polygons_known_answers():
     # half resolution: 2 px per unit -> sample points at 0.25, 0.75, ...
     out = orc.raster_polygons([sq], [0], 10, 8, 0.0, 0.5, 1, [])
     assert out.shape == (1, 20, 16) and out[0].T[4:10, 4:12].sum() == 0 and out[0].sum() == 20 * 16 - 6 * 8
+
+
+def test_widen_mini_fixture_reproduces():
+    """tests/golden/widen_mini.npz (make_golden.py): propagate and the vector-map path.  The polygon layers involve no
+    transcendental and must match to the bit; the propagate stream goes through glibc's logf / cosf / sinf, whose
+    CPU-dispatched variants may differ in the last place between machines, hence 2 ulp on the variates."""
+    g = np.load(os.path.join(GOLD, "widen_mini.npz"))
+    tx, ty, omega, pos_cov, theta_cov = (float(v) for v in g["prop_args"])
+    for freeze in (0, 1):
+        a, last, z = orc.propagate(g["prop_in"], tx, ty, omega, bool(freeze), pos_cov, theta_cov, 1234)
+        assert _ulps(z, g[f"prop_z_{freeze}"]).max() <= 2
+        want = g[f"prop_states_{freeze}"]
+        for k in ("dx_m", "dy_m", "theta", "scale"):
+            assert np.allclose(a[k], want[k], rtol=2e-6, atol=2e-6), k
+        assert np.allclose(last, g[f"prop_last_{freeze}"], rtol=1e-5, atol=2e-6)
+    st = g["poly_start"]
+    polys = [g["poly_verts"][st[k]:st[k + 1]] for k in range(len(st) - 1)]
+    lay = orc.raster_polygons(polys, g["poly_class"], 96, 72, 0.0, 1.0, 3, g["poly_excl"])
+    assert np.array_equal(lay.astype(np.uint8), g["poly_layers"]) and set(np.unique(lay)) <= {0.0, 1.0}
