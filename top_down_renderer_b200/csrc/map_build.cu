@@ -295,36 +295,69 @@ struct PolyParams {
 // One thread per sample point (= map pixel).  The reference runs the even-odd rule edge by edge over ALL points
 // (O(pixels x edges), :339-349); a polygon can only flip points whose y lies inside its y-range and whose x is not
 // clearly to its right, and left of it the flips of a closed polygon cancel — those polygons are skipped (exactly),
-// the edges of the rest are evaluated with the reference's fp32 expression.
-__global__ void k_raster_polygons(PolyParams q, float* __restrict__ layers) {
+// the edges of the rest are evaluated with the reference's fp32 expression.  A block (256 consecutive points of a map
+// column) first collects, cooperatively, the polygons whose padded bounding box meets the block's extent.
+static const int RASTER_THREADS = 256, RASTER_CHUNK = 2048;
+__global__ void __launch_bounds__(RASTER_THREADS) k_raster_polygons(PolyParams q, float* __restrict__ layers) {
+  __shared__ int s_list[RASTER_CHUNK];
+  __shared__ int s_n;
+  __shared__ float s_ext[4][RASTER_THREADS / 32];                            // per-warp min/max of py, px
   const size_t L = (size_t)q.rows * q.cols;
-  const size_t p = (size_t)blockIdx.x * blockDim.x + threadIdx.x;
-  if (p >= L) return;
+  const size_t p_raw = (size_t)blockIdx.x * blockDim.x + threadIdx.x;
+  const bool live = p_raw < L;
+  const size_t p = live ? p_raw : L - 1;
   const float a = raster_linspaced(q.rows, q.resolution, (int)(p % q.rows));   // pts(0, p)
   const float b = raster_linspaced(q.cols, q.resolution, (int)(p / q.rows));   // pts(1, p)
   const float py = TDR_FADD(TDR_FADD(TDR_FMUL(q.cr, a), TDR_FMUL(-q.sr, b)), q.c1);   // rotm * pts, += center[1]
   const float px = TDR_FADD(TDR_FADD(TDR_FMUL(q.sr, a), TDR_FMUL(q.cr, b)), q.c0);    // += center[0]
+  // extent of this block's sample points: only polygons whose (padded) bounding box meets it can flip any of them
+  float ylo = py, yhi = py, xlo = px, xhi = px;
+  for (int o = 16; o > 0; o >>= 1) {
+    ylo = fminf(ylo, __shfl_xor_sync(0xffffffffu, ylo, o)); yhi = fmaxf(yhi, __shfl_xor_sync(0xffffffffu, yhi, o));
+    xlo = fminf(xlo, __shfl_xor_sync(0xffffffffu, xlo, o)); xhi = fmaxf(xhi, __shfl_xor_sync(0xffffffffu, xhi, o));
+  }
+  if ((threadIdx.x & 31) == 0) {
+    const int w = threadIdx.x >> 5;
+    s_ext[0][w] = ylo; s_ext[1][w] = yhi; s_ext[2][w] = xlo; s_ext[3][w] = xhi;
+  }
+  __syncthreads();
+  for (int w = 0; w < RASTER_THREADS / 32; w++) {
+    ylo = fminf(ylo, s_ext[0][w]); yhi = fmaxf(yhi, s_ext[1][w]); xlo = fminf(xlo, s_ext[2][w]); xhi = fmaxf(xhi, s_ext[3][w]);
+  }
   float fills[TDR_MAX_CLASSES];
 #pragma unroll
   for (int c = 0; c < TDR_MAX_CLASSES; c++) fills[c] = -1.f;                 // class_fills = -1
-  for (int k = 0; k < q.n_poly; k++) {
-    const float4 bb = __ldg(q.bbox + k);
-    if (py < bb.z || !(py < bb.w)) continue;                                 // no edge straddles this y
-    if (!(px < bb.y + 1.0f) || px < bb.x - 1.0f) continue;                   // right of it: no flip; left of it: an even number
-    const int s0 = q.start[k], n = q.start[k + 1] - s0;
-    float buf = -1.f;                                                        // class_fills_buf = -1
-    float2 vj = __ldg(q.verts + s0 + n - 1);
-    for (int i = 0; i < n; i++) {
-      const float2 vi = __ldg(q.verts + s0 + i);
-      const bool ca = (py < vi.y) != (py < vj.y);
-      const bool cb = px < TDR_FADD(vi.x, TDR_FDIV(TDR_FMUL(TDR_FSUB(vj.x, vi.x), TDR_FSUB(py, vi.y)), TDR_FSUB(vj.y, vi.y)));
-      if (ca && cb) buf = -buf;                                              // *= -2 * cond + 1
-      vj = vi;
+  for (int k0 = 0; k0 < q.n_poly; k0 += RASTER_CHUNK) {
+    __syncthreads();
+    if (threadIdx.x == 0) s_n = 0;
+    __syncthreads();
+    for (int k = k0 + threadIdx.x; k < q.n_poly && k < k0 + RASTER_CHUNK; k += RASTER_THREADS) {
+      const float4 bb = __ldg(q.bbox + k);
+      if (yhi >= bb.z && ylo < bb.w && xhi >= bb.x - 1.0f && xlo < bb.y + 1.0f) s_list[atomicAdd(&s_n, 1)] = k;
     }
-    const int c = q.cls[k];
+    __syncthreads();
+    const int n_list = s_n;
+    for (int e = 0; e < n_list; e++) {
+      const int k = s_list[e];
+      const float4 bb = __ldg(q.bbox + k);
+      if (py < bb.z || !(py < bb.w)) continue;                               // no edge straddles this y
+      if (!(px < bb.y + 1.0f) || px < bb.x - 1.0f) continue;                 // right of it: no flip; left of it: an even number
+      const int s0 = q.start[k], n = q.start[k + 1] - s0;
+      float buf = -1.f;                                                      // class_fills_buf = -1
+      float2 vj = __ldg(q.verts + s0 + n - 1);
+      for (int i = 0; i < n; i++) {
+        const float2 vi = __ldg(q.verts + s0 + i);
+        const bool ca = (py < vi.y) != (py < vj.y);
+        const bool cb = px < TDR_FADD(vi.x, TDR_FDIV(TDR_FMUL(TDR_FSUB(vj.x, vi.x), TDR_FSUB(py, vi.y)), TDR_FSUB(vj.y, vi.y)));
+        if (ca && cb) buf = -buf;                                            // *= -2 * cond + 1
+        vj = vi;
+      }
+      const int c = q.cls[k];
 #pragma unroll
-    for (int cc = 0; cc < TDR_MAX_CLASSES; cc++) if (cc == c) fills[cc] = fmaxf(fills[cc], buf);
+      for (int cc = 0; cc < TDR_MAX_CLASSES; cc++) if (cc == c) fills[cc] = fmaxf(fills[cc], buf);
+    }
   }
+  if (!live) return;
 #pragma unroll
   for (int c = 0; c < TDR_MAX_CLASSES; c++) fills[c] = TDR_FDIV(TDR_FADD(TDR_FMUL(fills[c], -1.f), 1.f), 2.f);   // :351-353
   for (int ia = 0; ia < q.n_excl; ia++) {                                   // "only one ground type per cell" :357-364
@@ -387,7 +420,7 @@ int map_set_polygons(tdr_ctx* ctx, const float* verts, const int32_t* poly_start
   q.c0 = (float)map_w / 2; q.c1 = (float)map_h / 2;
   q.n_excl = n_excl;
   for (int k = 0; k < n_excl; k++) q.excl[k] = exclusive[k];
-  k_raster_polygons<<<(unsigned)((L + 255) / 256), 256, 0, ctx->stream>>>(q, ctx->scratch.as<float>());
+  k_raster_polygons<<<(unsigned)((L + RASTER_THREADS - 1) / RASTER_THREADS), RASTER_THREADS, 0, ctx->stream>>>(q, ctx->scratch.as<float>());
   dim3 blk(32, 8), grd((rows + 31) / 32, (cols + 7) / 8);
   k_layers_to_seeds<<<grd, blk, 0, ctx->stream>>>(ctx->scratch.as<float>(), rows, cols, C, ctx->seedbits.as<uint8_t>());
   count_launch(ctx, 2);
