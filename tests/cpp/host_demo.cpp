@@ -39,6 +39,11 @@ int main(int argc, char** argv) {
   map.samplePtsPolar(n_theta, n_r, (float)(2 * M_PI / n_theta));
   map.updateMap(img.data(), H, W, W, Vector2i{W / 2, H / 2});
   if (!map.haveMap()) return 4;
+  // the map cache (top_down_map.cpp:226-286): written in the reference's .eig format, then loaded back — from here on
+  // the filter runs on the CACHED distance fields (tdr_map_set_dist_layers), which must change nothing
+  map.saveCachedMaps(dir, "demo_map");
+  if (!map.loadCacheMetaData(dir, "demo_map") || map.loadCacheMetaData(dir, "another_map")) return 5;
+  if (!map.loadCachedMaps(dir) || !map.haveMap()) return 6;
 
   ScanRendererPolar renderer(lut);
   std::vector<ArrayXXf> top_down(C, ArrayXXf(n_theta, n_r)), geo;

@@ -81,6 +81,15 @@ def test_host_mirror_step_matches_oracle(tmp_path):
     wn, arg, _ = orc.normalize(w, ld)
     got = np.fromfile(os.path.join(d, "weights_norm.f32"), dtype=np.float32)
     assert np.max(np.abs(got - wn) / wn) <= 1e-5
+    # the map cache the C++ mirror wrote in the reference's .eig format (and then ran the filter from): read back with
+    # the independent Python reader — distance fields and mask to the bit, geo layers like the oracle's
+    from top_down_renderer_b200 import eigcache
+    assert eigcache.cache_is_valid(d, "demo_map", C, 1.0) and not eigcache.cache_is_valid(d, "demo_map", C + 1, 1.0)
+    c_layers, c_geo, c_mask = eigcache.load_cache(d, C)
+    assert np.array_equal(c_layers.view(np.uint32), layers.view(np.uint32)) and np.array_equal(c_mask, mask)
+    geo_o = orc.geo_raster(orc.class_image_to_layers(img, lut, C, 1.0))
+    geo_d, _ = orc.compute_dists(geo_o, 1.0)
+    assert np.array_equal(c_geo.view(np.uint32), geo_d.view(np.uint32))
     u = float(np.fromfile(os.path.join(d, "u.f32"), dtype=np.float32)[0])
     after = np.fromfile(os.path.join(d, "states_after.bin"), dtype=synth.STATE_DTYPE)
     idx = orc.resample_fast(got, u, len(st))                 # stage-wise: the device's own normalised weights

@@ -189,3 +189,31 @@ def test_double_addend_chain_is_exact(hm):
         real = hm.hm_exact_sum_double_addends(d.ctypes.data_as(dp), C.c_long(len(d)), C.byref(a), C.byref(b))
         assert np.float32(a.value).view(np.uint32) == np.float32(b.value).view(np.uint32), (name, a.value, b.value)
         assert real < 2000 + 64, (name, real)      # only binade crossings (and the denormal head) take real adds
+
+
+# ---- the reference's .eig map cache (top_down_map.h:29-50, top_down_map.cpp:226-286)
+def test_eig_cache_format_and_round_trip(tmp_path):
+    import struct
+    from top_down_renderer_b200 import eigcache
+    rng = np.random.default_rng(2)
+    rows, cols, C = 5, 3, 2
+    layers = rng.random((C, cols, rows)).astype(np.float32)
+    geo = rng.random((2, cols, rows)).astype(np.float32)
+    mask = (rng.random((cols, rows)) < 0.3).astype(np.uint8)
+    d = str(tmp_path)
+    eigcache.save_cache(d, "/maps/campus.svg", layers, geo, mask, 0.5)
+    # byte layout: int64 rows, int64 cols, then COLUMN-major scalars (element (r, c) at c*rows + r)
+    raw = open(f"{d}/class_map1.eig", "rb").read()
+    assert struct.unpack("<qq", raw[:16]) == (rows, cols) and len(raw) == 16 + rows * cols * 4
+    vals = np.frombuffer(raw[16:], dtype="<f4")
+    assert vals[2 * rows + 4] == layers[1][2, 4]                      # (row 4, col 2)
+    raw = open(f"{d}/class_mask.eig", "rb").read()
+    assert len(raw) == 16 + rows * cols and raw[16 + 1 * rows + 3] == mask[1, 3]
+    assert open(f"{d}/cached_data.txt").read() == "/maps/campus.svg\n2\n0.5\n"
+    # validity rule (:233-239): same path, same class count, resolution within 0.01
+    assert eigcache.cache_is_valid(d, "/maps/campus.svg", 2, 0.505)
+    assert not eigcache.cache_is_valid(d, "/maps/campus.svg", 2, 0.52)
+    assert not eigcache.cache_is_valid(d, "/maps/other.svg", 2, 0.5) and not eigcache.cache_is_valid(d, "/maps/campus.svg", 3, 0.5)
+    assert not eigcache.cache_is_valid(str(tmp_path / "nowhere"), "/maps/campus.svg", 2, 0.5)
+    l2, g2, m2 = eigcache.load_cache(d, C)
+    assert np.array_equal(l2, layers) and np.array_equal(g2, geo) and np.array_equal(m2, mask)

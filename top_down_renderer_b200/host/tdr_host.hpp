@@ -17,6 +17,7 @@
 #include <cstdint>
 #include <cstdio>
 #include <cstdlib>
+#include <fstream>
 #include <limits>
 #include <random>
 #include <string>
@@ -129,6 +130,50 @@ class TopDownMapPolar {
     }
     ok(tdr_map_set_polar_table(ctx(), tab_.data(), n_theta_, n_r_));
   }
+  // ---- the map cache, top_down_map.cpp:226-286 with write_binary / read_binary of top_down_map.h:29-50: same files, same
+  // bytes (Eigen::Index = int64 rows, cols, then column-major scalars), in `dir` instead of $HOME/.ros/xview_cache
+  bool loadCacheMetaData(const std::string& dir, const std::string& map_path) const {
+    std::ifstream f(dir + "/cached_data.txt");
+    if (!f) return false;
+    std::string line;
+    std::getline(f, line); if (line != map_path) return false;
+    std::getline(f, line); if (std::stoi(line) != params_.num_classes) return false;
+    std::getline(f, line); if (std::abs(std::stof(line) - params_.resolution) > 0.01) return false;
+    return true;
+  }
+  void saveCachedMaps(const std::string& dir, const std::string& map_path) {
+    if (!ctx() || rows_ == 0) return;
+    std::ofstream f(dir + "/cached_data.txt", std::ofstream::out | std::ofstream::trunc);
+    f << map_path << std::endl << params_.num_classes << std::endl << params_.resolution << std::endl;
+    const size_t L = (size_t)rows_ * cols_;
+    for (int cls = 0; cls < params_.num_classes; cls++) write_eig(dir + "/class_map" + std::to_string(cls) + ".eig", layers_.data() + cls * L, 4);
+    std::vector<float> geo(2 * L);
+    if (ok(tdr_map_get_geo_layers(ctx(), geo.data())))
+      for (int cls = 0; cls < 2; cls++) write_eig(dir + "/geo_map" + std::to_string(cls) + ".eig", geo.data() + cls * L, 4);
+    write_eig(dir + "/class_mask.eig", mask_.data(), 1);
+  }
+  // a cache hit skips the distance transform: the cached fields go straight to the device (tdr_map_set_dist_layers)
+  bool loadCachedMaps(const std::string& dir) {
+    if (!ctx()) return false;
+    std::vector<float> all;
+    int64_t r = 0, c = 0;
+    for (int cls = 0; cls < params_.num_classes; cls++) {
+      std::vector<char> raw;
+      int64_t rr = 0, cc = 0;
+      if (!read_eig(dir + "/class_map" + std::to_string(cls) + ".eig", 4, raw, rr, cc) || (cls > 0 && (rr != r || cc != c))) return false;
+      r = rr; c = cc;
+      all.insert(all.end(), reinterpret_cast<float*>(raw.data()), reinterpret_cast<float*>(raw.data()) + (size_t)r * c);
+    }
+    std::vector<char> m;
+    int64_t mr = 0, mc = 0;
+    if (!read_eig(dir + "/class_mask.eig", 1, m, mr, mc) || mr != r || mc != c) return false;
+    if (!ok(tdr_map_set_dist_layers(ctx(), all.data(), reinterpret_cast<const uint8_t*>(m.data()), (int)r, (int)c, params_.num_classes,
+                                    params_.resolution))) return false;
+    rows_ = (int)r; cols_ = (int)c; layers_ = all; mask_.assign(m.begin(), m.end());
+    have_map_ = true;
+    ok(tdr_map_set_polar_table(ctx(), tab_.data(), n_theta_, n_r_));
+    return true;
+  }
   // top_down_map.cpp:159-170 (integer point)
   void getClassesAtPoint(const Vector2i& center_ind, std::vector<int>& classes) const {
     classes.clear();
@@ -169,6 +214,24 @@ class TopDownMapPolar {
   int nR() const { return n_r_; }
 
  private:
+  // write_binary / read_binary (top_down_map.h:29-50): Eigen::Index rows, cols, then column-major scalars
+  void write_eig(const std::string& name, const void* data, size_t scalar_bytes) const {
+    std::ofstream out(name, std::ios::out | std::ios::binary | std::ios::trunc);
+    const int64_t rows = rows_, cols = cols_;
+    out.write(reinterpret_cast<const char*>(&rows), 8);
+    out.write(reinterpret_cast<const char*>(&cols), 8);
+    out.write(reinterpret_cast<const char*>(data), (std::streamsize)((size_t)rows * cols * scalar_bytes));
+  }
+  static bool read_eig(const std::string& name, size_t scalar_bytes, std::vector<char>& data, int64_t& rows, int64_t& cols) {
+    std::ifstream in(name, std::ios::in | std::ios::binary);
+    if (!in) return false;
+    in.read(reinterpret_cast<char*>(&rows), 8);
+    in.read(reinterpret_cast<char*>(&cols), 8);
+    if (!in || rows <= 0 || cols <= 0 || rows * cols > (int64_t)1 << 32) return false;
+    data.resize((size_t)rows * cols * scalar_bytes);
+    in.read(data.data(), (std::streamsize)data.size());
+    return (bool)in;
+  }
   Params params_;
   bool have_map_ = false;
   Vector2i map_center_;
