@@ -120,6 +120,17 @@ int tdr_map_set_polar_table(tdr_ctx* ctx, const float* tab2xP, int n_theta, int 
 int tdr_map_local_polar(tdr_ctx* ctx, const float* centers_xy, int n, float scale, float res, float* dists,
                         uint8_t* mask);
 /* a8: TopDownMap::getLocalMap (Cartesian, top_down_map.cpp:429-459); dists C x rows x cols col-major */
+/* SURVEY 8f rank 2 — the geometric twin, TopDownMapPolar::getLocalGeoMap (top_down_map_polar.cpp:55-76): the same
+ * gather on the two geometric distance layers (built on first use from the class seeds); geo: n x 2 x P, no mask.
+ * And ActiveLocalizer::getBestRelPos (active_localizer.cpp:45-82): for relative positions (dist = 50, 75, ... m while
+ * the best difference is under 6000; 16-17 bearings) the local maps around every prediction (x, y, theta), rotated by
+ * the prediction's heading, are compared pairwise (mean absolute difference per class pair); rel_pos = (dist, theta) of
+ * the most discriminative one, (0, 0) when nothing beats 0 (e.g. a single prediction).  n_preds <= 64. */
+int tdr_map_local_geo_polar(tdr_ctx* ctx, const float* centers_xy, int n, float scale, float res, float* geo);
+/* cached geometric distance layers (geo_map0/1.eig of the map cache, top_down_map.cpp:252-257) for a map that was set
+ * from cached distance fields: 2 col-major rows x cols images */
+int tdr_map_set_geo_dist_layers(tdr_ctx* ctx, const float* geo_layers);
+int tdr_active_best_rel_pos(tdr_ctx* ctx, const float* preds_xyt, int n_preds, float rel_pos[2], float* best_diff);
 int tdr_map_local_cart(tdr_ctx* ctx, float cx, float cy, float rot, float res, int rows, int cols,
                        float* dists, uint8_t* mask);
 

@@ -313,3 +313,15 @@ def raster_polygons(polys, poly_class, map_w, map_h, rot, resolution, C_, exclus
     lib().orc_raster_polygons(_p(verts, c_float_p), _p(start, c_int_p), _p(pc, c_int_p), len(polys), int(map_w), int(map_h),
                               C.c_float(rot), C.c_float(resolution), C_, _p(ex, c_int_p), len(ex), _p(out, c_float_p))
     return out
+
+
+def active_best_rel_pos(layers, mask, resolution, tab, n_theta, n_r, preds):
+    """ActiveLocalizer::getBestRelPos (active_localizer.cpp:45-82) -> ((dist, theta), best_diff)"""
+    C_, cols, rows = layers.shape
+    preds = np.ascontiguousarray(preds, dtype=np.float32).reshape(-1, 3)
+    rel = np.zeros(2, dtype=np.float32)
+    best = C.c_float()
+    lib().orc_active_best_rel_pos(_p(layers, c_float_p), _p(mask, c_u8_p), rows, cols, C_, C.c_float(resolution),
+                                  _p(np.ascontiguousarray(tab, dtype=np.float32), c_float_p), n_theta, n_r, _p(preds, c_float_p),
+                                  len(preds), _p(rel, c_float_p), C.byref(best))
+    return (float(rel[0]), float(rel[1])), best.value

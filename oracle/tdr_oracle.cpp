@@ -798,4 +798,58 @@ ORC_API void orc_raster_polygons(const float* verts, const int* poly_start, cons
   }
 }
 
+// -----------------------------------------------------------------------------
+// SURVEY 8f rank 2  ActiveLocalizer::getBestRelPos   src/active_localizer.cpp:7-82 (+ getLocalMap :22-42,
+// computeTotalDifference :7-20).  The geometric twin of the polar gather (top_down_map_polar.cpp:55-76) is
+// orc_local_map_polar on the two geo layers with the mask ignored.
+// -----------------------------------------------------------------------------
+// preds: n x (x, y, theta).  local maps are n_theta x n_r (the reference hard-codes 100 x 25), gathered with the
+// 4-argument getLocalMap(center, res = 2, ...) i.e. scale = 1.  rel: (dist, theta) of the best relative position.
+ORC_API void orc_active_best_rel_pos(const float* layers, const uint8_t* mask, int rows, int cols, int C, float resolution,
+                                     const float* tab, int n_theta, int n_r, const float* preds, int n, float rel[2],
+                                     float* best_diff_out) {
+  const int P = n_theta * n_r;
+  std::vector<std::vector<float>> local((size_t)n, std::vector<float>((size_t)C * P));
+  std::vector<float> orig((size_t)C * P);
+  std::vector<uint8_t> m(P);
+  float dist = 50;                                                          // :59
+  float best_diff = 0;
+  float best0 = 0, best1 = 0;
+  while (best_diff < 6000 && dist < 150) {                                  // :62
+    for (float theta = 0; theta < 2 * M_PI; theta += M_PI / 8) {            // :63 (float += double)
+      for (int idx = 0; idx < n; idx++) {
+        const float* pred = preds + 3 * idx;
+        const float px = pred[0] + dist * std::cos(theta + pred[2]);       // :67 Vector2f(cos, sin) * dist, float
+        const float py = pred[1] + dist * std::sin(theta + pred[2]);
+        orc_local_map_polar(layers, mask, rows, cols, C, resolution, tab, P, px, py, 1.f, 2.f, orig.data(), m.data());   // :29
+        const int num_bins = n_theta;
+        int rot_shift = static_cast<int>(std::round(pred[2] * num_bins / 2 / M_PI));      // :32
+        while (rot_shift >= num_bins) rot_shift -= num_bins;
+        while (rot_shift < 0) rot_shift += num_bins;
+        for (int c = 0; c < C; c++)                                         // :38-41 rows rotate down by rot_shift
+          for (int col = 0; col < n_r; col++)
+            for (int r = 0; r < num_bins; r++) {
+              const int src = r < rot_shift ? r + num_bins - rot_shift : r - rot_shift;
+              local[idx][(size_t)c * P + (size_t)col * num_bins + r] = orig[(size_t)c * P + (size_t)col * num_bins + src];
+            }
+      }
+      float total = 0;                                                      // :7-20
+      int cnt = 0;
+      for (int i = 0; i < n; i++)
+        for (int j = 0; j < i; j++)
+          for (int c = 0; c < C; c++) {
+            float sum = 0;
+            for (int p = 0; p < P; p++) sum += std::abs(local[i][(size_t)c * P + p] - local[j][(size_t)c * P + p]);
+            total += sum;
+            cnt += 1;
+          }
+      const float diff = total / cnt;
+      if (diff > best_diff) { best_diff = diff; best0 = dist; best1 = theta; }   // :74-77
+    }
+    dist += 25;                                                             // :80
+  }
+  rel[0] = best0; rel[1] = best1;
+  if (best_diff_out) *best_diff_out = best_diff;
+}
+
 ORC_API int orc_abi_version() { return 1; }

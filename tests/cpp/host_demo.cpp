@@ -68,6 +68,19 @@ int main(int argc, char** argv) {
   float mean[4], cov[16], ml[4];
   filter.meanLikelihood(mean); filter.computeMeanCov(cov); filter.maxLikelihood(ml);
   wr(dir + "mean.f32", mean, 4); wr(dir + "cov.f32", cov, 16); wr(dir + "ml.f32", ml, 4);
+  // ActiveLocalizer (dead code in the reference, kept linkable): most discriminative relative position for three guesses
+  ActiveLocalizer al(&map);
+  std::vector<Vector3f> preds(3);
+  preds[0].x = W * 0.3f; preds[0].y = H * 0.4f; preds[0].z = 0.2f;
+  preds[1].x = W * 0.6f; preds[1].y = H * 0.5f; preds[1].z = -1.1f;
+  preds[2].x = W * 0.5f; preds[2].y = H * 0.7f; preds[2].z = 2.4f;
+  const Vector2f rel = al.getBestRelPos(preds);
+  const float relv[2] = {rel.x, rel.y};
+  wr(dir + "active_rel.f32", relv, 2);
+  std::vector<ArrayXXf> geo_local(2, ArrayXXf(n_theta, n_r));
+  Vector2f gc; gc.x = W * 0.5f; gc.y = H * 0.5f;
+  map.getLocalGeoMap(gc, 2.0f, geo_local);
+  wr(dir + "geo_local0.f32", geo_local[0].data(), (size_t)n_theta * n_r);
   std::cout << "host_demo ok: " << filter.numParticles() << " particles, mean (" << mean[0] << ", " << mean[1] << ", " << mean[2] << ")\n";
   return 0;
 }

@@ -968,3 +968,34 @@ def test_widen_mini_fixture_through_the_c_abi(world):
     lay = c.map_set_polygons(polys, g["poly_class"], 96, 72, 0.0, 3, 1.0, g["poly_excl"])
     c.close()
     assert np.array_equal(lay.astype(np.uint8), g["poly_layers"])
+
+
+# ---- geometric local map and ActiveLocalizer
+def test_local_geo_map_polar(world, ctx):
+    """TopDownMapPolar::getLocalGeoMap: the polar gather on the two geometric distance layers, bit-exact (values are
+    copied); centres inside, on the border and off the map"""
+    geo_bin = orc.geo_raster(world.bin_layers)
+    geo, _ = orc.compute_dists(geo_bin, 1.0)
+    no_mask = np.zeros(geo.shape[1:], dtype=np.uint8)
+    centers = np.array([[500.2, 480.7], [3.0, 996.5], [-40.0, 500.0], [1500.0, 1500.0], [999.4, 0.4]], dtype=np.float32)
+    for scale, res in ((2.0, 4.0), (1.0, 2.0), (2.0, 0.5)):
+        got = ctx.map_local_geo_polar(centers, scale, res)
+        for i, (cx, cy) in enumerate(centers):
+            want, _ = orc.local_map_polar(geo, no_mask, 1.0, world.tab, cx, cy, scale, res)
+            assert np.array_equal(got[i].view(np.uint32), want.view(np.uint32)), (i, scale, res)
+
+
+def test_active_localizer_best_relative_position(world, ctx):
+    """ActiveLocalizer::getBestRelPos: same (dist, theta) as the literal restatement, best difference within 1e-5
+    relative (the reference sums |L_i - L_j| in fp32, the kernel in double); one prediction -> (0, 0)"""
+    rng = np.random.default_rng(9)
+    for n in (2, 3, 6):
+        preds = np.stack([rng.uniform(150, 850, n), rng.uniform(150, 850, n), rng.uniform(-3.1, 3.1, n)], axis=1).astype(np.float32)
+        (d_o, t_o), best_o = orc.active_best_rel_pos(world.layers, world.mask, 1.0, world.tab, N_THETA, N_R, preds)
+        (d_g, t_g), best_g = ctx.active_best_rel_pos(preds)
+        assert (d_g, t_g) == (d_o, t_o) and d_o >= 50
+        assert abs(best_g - best_o) <= 1e-5 * best_o
+    # predictions on top of each other in a featureless corner would need the farther rings; a single one never moves
+    (d_g, t_g), best_g = ctx.active_best_rel_pos(np.float32([[400, 400, 0.5]]))
+    assert (d_g, t_g) == (0.0, 0.0) and best_g == 0.0
+    assert orc.active_best_rel_pos(world.layers, world.mask, 1.0, world.tab, N_THETA, N_R, np.float32([[400, 400, 0.5]])) == ((0.0, 0.0), 0.0)

@@ -94,6 +94,14 @@ def test_host_mirror_step_matches_oracle(tmp_path):
     after = np.fromfile(os.path.join(d, "states_after.bin"), dtype=synth.STATE_DTYPE)
     idx = orc.resample_fast(got, u, len(st))                 # stage-wise: the device's own normalised weights
     assert np.array_equal(after, st[idx])
+    # ActiveLocalizer::getBestRelPos and getLocalGeoMap through the mirror classes
+    preds = np.float32([[W * 0.3, H * 0.4, 0.2], [W * 0.6, H * 0.5, -1.1], [W * 0.5, H * 0.7, 2.4]])
+    rel_o, _ = orc.active_best_rel_pos(layers, mask, 1.0, tab.reshape(-1), 100, 25, preds)
+    rel = np.fromfile(os.path.join(d, "active_rel.f32"), dtype=np.float32)
+    assert (float(rel[0]), float(rel[1])) == rel_o and rel_o[0] >= 50
+    g0 = np.fromfile(os.path.join(d, "geo_local0.f32"), dtype=np.float32)
+    want_g, _ = orc.local_map_polar(geo_d, np.zeros_like(mask), 1.0, tab, np.float32(W * 0.5), np.float32(H * 0.5), 1.0, 2.0)
+    assert np.array_equal(g0.view(np.uint32), want_g[0].view(np.uint32))
     mean = np.fromfile(os.path.join(d, "mean.f32"), dtype=np.float32)
     wm, _ = orc.mean_cov(after)
     assert abs(mean[0] - wm[0]) <= 0.002 and abs(mean[1] - wm[1]) <= 0.002 and abs(mean[2] - wm[2]) <= math.radians(0.01)

@@ -146,6 +146,25 @@ class Context:
         check(self._lib.tdr_map_local_polar(self._h, _pf(centers), n, C.c_float(scale), C.c_float(res), _pf(d), _pb(m)))
         return d, m
 
+    def map_set_geo_dist_layers(self, geo):
+        geo = np.ascontiguousarray(geo, dtype=np.float32)
+        check(self._lib.tdr_map_set_geo_dist_layers(self._h, _pf(geo)))
+
+    def map_local_geo_polar(self, centers_xy, scale, res):
+        centers = np.ascontiguousarray(centers_xy, dtype=np.float32).reshape(-1, 2)
+        n = centers.shape[0]
+        g = np.empty((n, 2, self._P), dtype=np.float32)
+        check(self._lib.tdr_map_local_geo_polar(self._h, _pf(centers), n, C.c_float(scale), C.c_float(res), _pf(g)))
+        return g
+
+    def active_best_rel_pos(self, preds_xyt):
+        """ActiveLocalizer::getBestRelPos -> ((dist, theta), best_diff)"""
+        preds = np.ascontiguousarray(preds_xyt, dtype=np.float32).reshape(-1, 3)
+        rel = np.zeros(2, dtype=np.float32)
+        best = C.c_float()
+        check(self._lib.tdr_active_best_rel_pos(self._h, _pf(preds), preds.shape[0], _pf(rel), C.byref(best)))
+        return (float(rel[0]), float(rel[1])), best.value
+
     def map_local_cart(self, cx, cy, rot, res, rows, cols):
         _, _, k, _ = self.map_info()
         d = np.empty((k, rows * cols), dtype=np.float32)

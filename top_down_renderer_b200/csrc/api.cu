@@ -1,4 +1,5 @@
 // api.cu — the extern "C" surface declared in include/tdr.h.
+#include <cmath>
 #include <stdarg.h>
 #include <stdlib.h>
 #include <string.h>
@@ -174,7 +175,7 @@ void tdr_destroy(tdr_ctx* c) {
   tdr::DevBuf* bufs[] = {&c->map_px, &c->seedbits, &c->edt_g, &c->scratch, &c->scratch2, &c->tab, &c->pts, &c->lut,
                          &c->scan_img, &c->scan_pack, &c->hist, &c->d_search_thetas, &c->d_search_shifts, &c->weights,
                          &c->prefix, &c->idx, &c->scal, &c->pose_tmp, &c->grid_centers, &c->grid_costs,
-                         &c->grid_shifts, &c->d_cw, &c->map16, &c->map16g, &c->tab_scaled, &c->grid_key, &c->seq_ws, &c->scan_op, &c->bin_counts, &c->perm};
+                         &c->grid_shifts, &c->d_cw, &c->map16, &c->map16g, &c->geo_planar, &c->tab_scaled, &c->grid_key, &c->seq_ws, &c->scan_op, &c->bin_counts, &c->perm};
   for (auto* b : bufs) b->release();
   for (void* p : c->grid_opened) cudaIpcCloseMemHandle(p);
   c->grid_full.release();
@@ -274,6 +275,88 @@ int tdr_map_local_polar(tdr_ctx* ctx, const float* centers_xy, int n, float scal
   TDR_CUDA(cudaMemcpyAsync(dists, dd, db, cudaMemcpyDeviceToHost, ctx->stream));
   TDR_CUDA(cudaMemcpyAsync(mask, dm, mb, cudaMemcpyDeviceToHost, ctx->stream));
   TDR_CUDA(cudaStreamSynchronize(ctx->stream));
+  return TDR_OK;
+}
+
+int tdr_map_set_geo_dist_layers(tdr_ctx* ctx, const float* geo_layers) {
+  CTX_CHECK(ctx);
+  TDR_REQUIRE(ctx->have_map && geo_layers, TDR_ESTATE, "no map / null layers");
+  const size_t bytes = (size_t)ctx->rows * ctx->cols * 2 * 4;
+  if (int e = ctx->geo_planar.reserve(bytes)) return e;
+  TDR_CUDA(cudaMemcpyAsync(ctx->geo_planar.p, geo_layers, bytes, cudaMemcpyHostToDevice, ctx->stream));
+  TDR_CUDA(cudaStreamSynchronize(ctx->stream));
+  ctx->geo_valid = true;
+  return TDR_OK;
+}
+int tdr_map_local_geo_polar(tdr_ctx* ctx, const float* centers_xy, int n, float scale, float res, float* geo) {
+  CTX_CHECK(ctx);
+  TDR_REQUIRE(ctx->have_map && ctx->have_tab, TDR_ESTATE, "map / polar table missing");
+  TDR_REQUIRE(centers_xy && n > 0 && n <= 65535 && geo, TDR_EINVAL, "bad arguments");
+  const int P = ctx->n_theta * ctx->n_r;
+  const size_t gb = (size_t)n * 2 * P * 4;
+  if (int e = map_geo_resident(ctx)) return e;            // uses scratch2 for the seeds: before the staging below
+  const size_t off_c = ((gb + 255) / 256) * 256;
+  if (int e = ctx->scratch.reserve(off_c + (size_t)n * 8)) return e;
+  float* dg = ctx->scratch.as<float>();
+  float* dc = reinterpret_cast<float*>(ctx->scratch.as<unsigned char>() + off_c);
+  TDR_CUDA(cudaMemcpyAsync(dc, centers_xy, (size_t)n * 8, cudaMemcpyHostToDevice, ctx->stream));
+  if (int e = local_geo_polar(ctx, dc, n, scale, res, dg)) return e;
+  TDR_CUDA(cudaMemcpyAsync(geo, dg, gb, cudaMemcpyDeviceToHost, ctx->stream));
+  TDR_CUDA(cudaStreamSynchronize(ctx->stream));
+  return TDR_OK;
+}
+
+// ActiveLocalizer::getBestRelPos (active_localizer.cpp:45-82): the candidate loop runs on the host exactly as written
+// (float theta += M_PI / 8, dist 50, 75, ... while best_diff < 6000), the gathers of every candidate x prediction and
+// the pairwise differences run on the device in two launches
+int tdr_active_best_rel_pos(tdr_ctx* ctx, const float* preds_xyt, int n_preds, float rel_pos[2], float* best_diff_out) {
+  CTX_CHECK(ctx);
+  TDR_REQUIRE(ctx->have_map && ctx->have_tab, TDR_ESTATE, "map / polar table missing");
+  TDR_REQUIRE(preds_xyt && n_preds >= 1 && n_preds <= 64 && rel_pos, TDR_EINVAL, "bad predictions");
+  std::vector<float> thetas, dists;
+  for (float theta = 0; theta < 2 * M_PI; theta += M_PI / 8) thetas.push_back(theta);     // :63
+  for (float dist = 50; dist < 150; dist += 25) dists.push_back(dist);                     // :59,62,80
+  const int T = (int)thetas.size(), D = (int)dists.size(), n_cfg = D * T, P = ctx->n_theta * ctx->n_r, C = ctx->C;
+  const int n_total = n_cfg * n_preds;
+  std::vector<float> centers((size_t)n_total * 2);
+  std::vector<int> shifts((size_t)n_preds);
+  for (int i = 0; i < n_preds; i++) {
+    const float th = preds_xyt[3 * i + 2];
+    int rs = static_cast<int>(std::round(th * ctx->n_theta / 2 / M_PI));                  // :32
+    while (rs >= ctx->n_theta) rs -= ctx->n_theta;
+    while (rs < 0) rs += ctx->n_theta;
+    shifts[i] = rs;
+  }
+  for (int d = 0; d < D; d++)
+    for (int t = 0; t < T; t++)
+      for (int i = 0; i < n_preds; i++) {
+        const float* pr = preds_xyt + 3 * i;
+        const size_t k = ((size_t)(d * T + t) * n_preds + i) * 2;
+        centers[k] = pr[0] + dists[d] * std::cos(thetas[t] + pr[2]);                       // :67
+        centers[k + 1] = pr[1] + dists[d] * std::sin(thetas[t] + pr[2]);
+      }
+  const size_t maps_b = (size_t)n_total * C * P * 4, mask_b = (size_t)n_total * P;
+  const size_t off_mask = ((maps_b + 255) / 256) * 256, off_cent = off_mask + ((mask_b + 255) / 256) * 256;
+  const size_t off_shift = off_cent + (size_t)n_total * 8, off_tot = off_shift + ((size_t)n_preds * 4 + 255) / 256 * 256;
+  if (int e = ctx->scratch.reserve(off_tot + (size_t)n_cfg * 4)) return e;
+  unsigned char* b = ctx->scratch.as<unsigned char>();
+  TDR_CUDA(cudaMemcpyAsync(b + off_cent, centers.data(), (size_t)n_total * 8, cudaMemcpyHostToDevice, ctx->stream));
+  TDR_CUDA(cudaMemcpyAsync(b + off_shift, shifts.data(), (size_t)n_preds * 4, cudaMemcpyHostToDevice, ctx->stream));
+  if (int e = local_polar(ctx, reinterpret_cast<float*>(b + off_cent), n_total, 1.f, 2.f, reinterpret_cast<float*>(b), b + off_mask)) return e;   // :29
+  if (int e = active_pairwise(ctx, reinterpret_cast<float*>(b), reinterpret_cast<int*>(b + off_shift), n_cfg, n_preds,
+                              reinterpret_cast<float*>(b + off_tot))) return e;
+  std::vector<float> totals((size_t)n_cfg);
+  TDR_CUDA(cudaMemcpyAsync(totals.data(), b + off_tot, (size_t)n_cfg * 4, cudaMemcpyDeviceToHost, ctx->stream));
+  TDR_CUDA(cudaStreamSynchronize(ctx->stream));
+  const int cnt = n_preds * (n_preds - 1) / 2 * C;
+  float best_diff = 0, best0 = 0, best1 = 0;
+  for (int d = 0; d < D && best_diff < 6000; d++)
+    for (int t = 0; t < T; t++) {
+      const float diff = totals[(size_t)d * T + t] / cnt;                                  // 0 / 0 = NaN for one prediction: never best
+      if (diff > best_diff) { best_diff = diff; best0 = dists[d]; best1 = thetas[t]; }
+    }
+  rel_pos[0] = best0; rel_pos[1] = best1;
+  if (best_diff_out) *best_diff_out = best_diff;
   return TDR_OK;
 }
 

@@ -232,7 +232,7 @@ static int map_alloc(tdr_ctx* ctx, int rows, int cols, int C, float resolution) 
   if (int e = ctx->map_px.reserve(L * sizeof(MapPixel))) return e;
   if (int e = ctx->seedbits.reserve(L)) return e;
   ctx->rows = rows; ctx->cols = cols; ctx->C = C; ctx->resolution = resolution;
-  ctx->map16_valid = false; ctx->map16g_log2 = -1; ctx->perm_grid_n = -1;
+  ctx->map16_valid = false; ctx->map16g_log2 = -1; ctx->perm_grid_n = -1; ctx->geo_valid = false;
   return TDR_OK;
 }
 
@@ -474,6 +474,21 @@ int map_get_layers(tdr_ctx* ctx, float* layers, uint8_t* mask) {
   TDR_CUDA(cudaMemcpyAsync(layers, ctx->scratch.p, L * ctx->C * 4, cudaMemcpyDeviceToHost, ctx->stream));
   if (mask) TDR_CUDA(cudaMemcpyAsync(mask, ctx->scratch2.p, L, cudaMemcpyDeviceToHost, ctx->stream));
   TDR_CUDA(cudaStreamSynchronize(ctx->stream));
+  return TDR_OK;
+}
+
+// the geo distance layers resident on the device (for getLocalGeoMap)
+int map_geo_resident(tdr_ctx* ctx) {
+  if (ctx->have_map && ctx->geo_valid) return TDR_OK;            // built earlier, or uploaded from the map cache
+  TDR_REQUIRE(ctx->have_map && ctx->have_seeds, TDR_ESTATE, "geo layers need a map built from class seeds (or tdr_map_set_geo_dist_layers)");
+  size_t L = (size_t)ctx->rows * ctx->cols;
+  if (int e = ctx->scratch2.reserve(L)) return e;
+  if (int e = ctx->geo_planar.reserve(L * 2 * 4)) return e;
+  k_geo_seeds<<<(unsigned)((L + 255) / 256), 256, 0, ctx->stream>>>(ctx->seedbits.as<uint8_t>(), L, ctx->C, ctx->scratch2.as<uint8_t>());
+  count_launch(ctx);
+  TDR_CUDA(cudaGetLastError());
+  if (int e = run_edt(ctx, ctx->scratch2.as<uint8_t>(), ctx->rows, ctx->cols, 2, ctx->resolution, false, ctx->geo_planar.as<float>())) return e;
+  ctx->geo_valid = true;
   return TDR_OK;
 }
 

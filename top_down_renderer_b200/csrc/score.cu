@@ -268,6 +268,54 @@ __global__ void k_local_polar(const MapPixel* __restrict__ map, int rows, int co
   mask[(size_t)i * P + p] = v[7] != 0.f ? 0 : 1;
 }
 
+// TopDownMapPolar::getLocalGeoMap (top_down_map_polar.cpp:55-76): the same gather on the two geometric
+// distance layers (col-major planar), no mask; n centres -> n x 2 x P
+__global__ void k_local_geo_polar(const float* __restrict__ geo, int rows, int cols, float resolution, const float* __restrict__ tab,
+                                  int P, const float* __restrict__ centers, int n, float scale, float res, float* __restrict__ out) {
+  int p = blockIdx.x * blockDim.x + threadIdx.x;
+  int i = blockIdx.y;
+  if (p >= P || i >= n) return;
+  float oy = TDR_FDIV(centers[2 * i + 1], resolution), ox = TDR_FDIV(centers[2 * i], resolution);
+  int r = lattice_index(tab[2 * p], scale, res, oy);
+  int c = lattice_index(tab[2 * p + 1], scale, res, ox);
+  const bool in = r >= 0 && r < rows && c >= 0 && c < cols;
+  const size_t L = (size_t)rows * cols;
+#pragma unroll
+  for (int k = 0; k < 2; k++) out[((size_t)i * 2 + k) * P + p] = in ? geo[(size_t)k * L + (size_t)c * rows + r] : 0.f;
+}
+
+// ActiveLocalizer::computeTotalDifference (active_localizer.cpp:7-20) for every candidate relative position at once:
+// maps[cfg][i][c][P] are the gathered local maps of prediction i (UN-rotated); the rows of prediction i are rotated
+// down by shifts[i] (getLocalMap :38-41) on the fly.  totals[cfg] = sum over pairs i > j, classes, cells of
+// |L_i - L_j|, accumulated in double (the reference: fp32 Eigen sums; compared at 1e-5 relative).
+__global__ void k_active_pairwise(const float* __restrict__ maps, const int* __restrict__ shifts, int n, int C, int n_theta, int n_r,
+                                  float* __restrict__ totals) {
+  const int cfg = blockIdx.x, P = n_theta * n_r;
+  const float* base = maps + (size_t)cfg * n * C * P;
+  double acc = 0.0;
+  for (int i = 1; i < n; i++) {
+    const int si = shifts[i];
+    for (int j = 0; j < i; j++) {
+      const int sj = shifts[j];
+      for (int q = threadIdx.x; q < C * P; q += blockDim.x) {
+        const int c = q / P, p = q - c * P, col = p / n_theta, r = p - col * n_theta;
+        const int ri = r < si ? r + n_theta - si : r - si, rj = r < sj ? r + n_theta - sj : r - sj;
+        const float a = base[((size_t)i * C + c) * P + col * n_theta + ri], b = base[((size_t)j * C + c) * P + col * n_theta + rj];
+        acc += (double)fabsf(TDR_FSUB(a, b));
+      }
+    }
+  }
+  __shared__ double s_acc[32];
+  for (int o = 16; o > 0; o >>= 1) acc += __shfl_xor_sync(0xffffffffu, acc, o);
+  if ((threadIdx.x & 31) == 0) s_acc[threadIdx.x >> 5] = acc;
+  __syncthreads();
+  if (threadIdx.x == 0) {
+    double t = 0.0;
+    for (int w = 0; w < (int)(blockDim.x >> 5); w++) t += s_acc[w];
+    totals[cfg] = (float)t;
+  }
+}
+
 // a8: Cartesian local map (top_down_map.cpp:429-459 with samplePts :367-389)
 __device__ __forceinline__ float linspaced(int size, float sres, int i) {
   float low = (float)((double)TDR_FMUL(-sres, (float)(size - 1)) / 2.);
@@ -413,6 +461,24 @@ int local_polar(tdr_ctx* ctx, const float* dev_centers, int n, float scale, floa
   dim3 grd((P + 127) / 128, n);
   k_local_polar<<<grd, 128, 0, ctx->stream>>>(ctx->map_px.as<MapPixel>(), ctx->rows, ctx->cols, ctx->C, ctx->resolution,
                                               ctx->tab.as<float>(), P, dev_centers, n, scale, res, dev_dists, dev_mask);
+  count_launch(ctx);
+  TDR_CUDA(cudaGetLastError());
+  return TDR_OK;
+}
+
+int local_geo_polar(tdr_ctx* ctx, const float* dev_centers, int n, float scale, float res, float* dev_geo) {
+  if (int e = map_geo_resident(ctx)) return e;
+  int P = ctx->n_theta * ctx->n_r;
+  dim3 grd((P + 127) / 128, n);
+  k_local_geo_polar<<<grd, 128, 0, ctx->stream>>>(ctx->geo_planar.as<float>(), ctx->rows, ctx->cols, ctx->resolution, ctx->tab.as<float>(), P,
+                                                  dev_centers, n, scale, res, dev_geo);
+  count_launch(ctx);
+  TDR_CUDA(cudaGetLastError());
+  return TDR_OK;
+}
+
+int active_pairwise(tdr_ctx* ctx, const float* dev_maps, const int* dev_shifts, int n_cfg, int n_preds, float* dev_totals) {
+  k_active_pairwise<<<n_cfg, 256, 0, ctx->stream>>>(dev_maps, dev_shifts, n_preds, ctx->C, ctx->n_theta, ctx->n_r, dev_totals);
   count_launch(ctx);
   TDR_CUDA(cudaGetLastError());
   return TDR_OK;

@@ -99,6 +99,8 @@ struct tdr_ctx {
   // second copy for lattices of centres (exhaustive grid): every map row split into 2^k PHASE rows (x mod 2^k), so
   // that centres 2^k px apart read CONSECUTIVE records — 8 full 128-byte lines per warp load instead of one sector
   // out of each of 32 lines (measured 1.67 against 0.82 records/clk/SM, tools/gather_bench.cu patterns 7 / 4)
+  tdr::DevBuf geo_planar;    // the 2 geometric distance layers (getGeoRasterMap + computeDists), col-major, built on demand
+  bool geo_valid = false;
   tdr::DevBuf map16g;
   tdr::DevBuf tab_scaled;    // polar table x scale x res of a grid launch (uniform scale): staged here, mirrored in constant memory
   int map16g_log2 = -1;      // layout of map16g (-1: not built)
@@ -210,6 +212,9 @@ int map_set_binary_layers(tdr_ctx*, const float*, int, int, int, float);
 int map_set_dist_layers(tdr_ctx*, const float*, const uint8_t*, int, int, int, float);
 int map_get_layers(tdr_ctx*, float*, uint8_t*);
 int map_get_geo_layers(tdr_ctx*, float*);
+int map_geo_resident(tdr_ctx*);          // builds ctx->geo_planar if stale
+int local_geo_polar(tdr_ctx*, const float* dev_centers, int n, float scale, float res, float* dev_geo);
+int active_pairwise(tdr_ctx*, const float* dev_maps, const int* dev_shifts, int n_cfg, int n_preds, float* dev_totals);
 int map_from_seeds(tdr_ctx*, int rows, int cols, int C, float resolution);
 int map_set_polygons(tdr_ctx*, const float* verts, const int32_t* poly_start, const int32_t* poly_class, int n_poly, int map_w, int map_h,
                      float rot, int C, float resolution, const int32_t* exclusive, int n_excl, float* layers_out);   // seedbits already filled on the device

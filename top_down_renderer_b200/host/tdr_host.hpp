@@ -44,6 +44,7 @@ using ArrayXXf = Array2D<float>;
 using ArrayXXc = Array2D<uint8_t>;
 struct Vector2f { float x = 0, y = 0; };
 struct Vector2i { int x = 0, y = 0; };
+struct Vector3f { float x = 0, y = 0, z = 0; };   // ActiveLocalizer's (x, y, theta) predictions
 
 // pcl::PointXYZI layout (32 bytes; intensity at byte 16)
 struct PointXYZI { float x, y, z, pad0, intensity, pad1, pad2, pad3; };
@@ -170,6 +171,14 @@ class TopDownMapPolar {
     if (!ok(tdr_map_set_dist_layers(ctx(), all.data(), reinterpret_cast<const uint8_t*>(m.data()), (int)r, (int)c, params_.num_classes,
                                     params_.resolution))) return false;
     rows_ = (int)r; cols_ = (int)c; layers_ = all; mask_.assign(m.begin(), m.end());
+    std::vector<float> geo;                                                // geo_map0/1.eig (:252-257)
+    for (int cls = 0; cls < 2; cls++) {
+      std::vector<char> raw;
+      int64_t rr = 0, cc = 0;
+      if (!read_eig(dir + "/geo_map" + std::to_string(cls) + ".eig", 4, raw, rr, cc) || rr != r || cc != c) return false;
+      geo.insert(geo.end(), reinterpret_cast<float*>(raw.data()), reinterpret_cast<float*>(raw.data()) + (size_t)r * c);
+    }
+    if (!ok(tdr_map_set_geo_dist_layers(ctx(), geo.data()))) return false;
     have_map_ = true;
     ok(tdr_map_set_polar_table(ctx(), tab_.data(), n_theta_, n_r_));
     return true;
@@ -192,6 +201,16 @@ class TopDownMapPolar {
     for (int c = 0; c < params_.num_classes; c++) std::copy(stage_.begin() + (size_t)c * P, stage_.begin() + (size_t)(c + 1) * P, dists[c].d.begin());
   }
   void getLocalMap(Vector2f center, float res, std::vector<ArrayXXf>& dists, ArrayXXc& mask) { getLocalMap(center, 1, res, dists, mask); }   // :78-82
+  // top_down_map_polar.cpp:55-76 (+ the 3-argument overload :84-87): the two geometric distance layers, no mask
+  void getLocalGeoMap(Vector2f center, float scale, float res, std::vector<ArrayXXf>& dists) {
+    if (dists.size() < 1 || !ctx()) return;                                // :58
+    const int P = n_theta_ * n_r_;
+    stage_.resize((size_t)2 * P);
+    const float c[2] = {center.x, center.y};
+    if (!ok(tdr_map_local_geo_polar(ctx(), c, 1, scale, res, stage_.data()))) return;
+    for (size_t k = 0; k < dists.size() && k < 2; k++) std::copy(stage_.begin() + k * P, stage_.begin() + (k + 1) * P, dists[k].d.begin());
+  }
+  void getLocalGeoMap(Vector2f center, float res, std::vector<ArrayXXf>& dists) { getLocalGeoMap(center, 1, res, dists); }
   // top_down_map_polar.cpp:7-19 (+ samplePts, top_down_map.cpp:367-389): the offset table is computed on the host
   void samplePtsPolar(int n_theta, int n_r, float ang_res) {
     n_theta_ = n_theta; n_r_ = n_r;
@@ -238,6 +257,22 @@ class TopDownMapPolar {
   int rows_ = 0, cols_ = 0, n_theta_ = 0, n_r_ = 0;
   std::vector<float> layers_, tab_, stage_;
   std::vector<uint8_t> mask_;
+};
+
+// active_localizer.h:7-16 / active_localizer.cpp:45-82: the whole candidate search is one call
+class ActiveLocalizer {
+ public:
+  explicit ActiveLocalizer(TopDownMapPolar* map) : map_(map) {}
+  Vector2f getBestRelPos(std::vector<Vector3f>& preds) {
+    Vector2f best;                                                          // (dist, theta); (0, 0) when nothing beats 0
+    if (!ctx() || !map_ || !map_->haveMap() || preds.empty()) return best;
+    float rel[2] = {0, 0}, diff = 0;
+    static_assert(sizeof(Vector3f) == 12, "predictions are packed (x, y, theta)");
+    if (ok(tdr_active_best_rel_pos(ctx(), &preds[0].x, (int)preds.size(), rel, &diff))) { best.x = rel[0]; best.y = rel[1]; }
+    return best;
+  }
+ private:
+  TopDownMapPolar* map_;
 };
 
 class ParticleFilter {
