@@ -195,6 +195,11 @@ int tdr_pf_propagate_dev(tdr_ctx* ctx, float trans_x, float trans_y, float omega
                          float theta_cov, const void* dev_z, int64_t n);
 int tdr_pf_propagate_rng(tdr_ctx* ctx, float trans_x, float trans_y, float omega, int scale_freeze, float pos_cov,
                          float theta_cov, uint64_t seed, uint64_t step, float* z_out);
+/* SURVEY 8f rank 4 — what the GMM thread needs from the particle set (ParticleFilter::computeGMM,
+ * particle_filter.cpp:262-272): num_samples (<= 1000 in the reference) particles taken at a stride, each as
+ * (x, y, 50 cos theta, 50 sin theta) in double — 32 B per sample over PCIe instead of the whole set; the EM fit itself
+ * (cv::ml::EM) stays on the host.  samples: num_samples x 4. */
+int tdr_pf_gmm_samples(tdr_ctx* ctx, int num_samples, double* samples);
 /* last_dist_ of every resident particle (StateParticle::lastDist, state_particle.cpp:108-110) */
 int tdr_pf_get_last_dist(tdr_ctx* ctx, float* last_dist, int64_t n);
 /* a9+a10: StateParticle::computeWeight for every particle (the for_each(par) region,

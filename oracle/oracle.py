@@ -325,3 +325,18 @@ def active_best_rel_pos(layers, mask, resolution, tab, n_theta, n_r, preds):
                                   _p(np.ascontiguousarray(tab, dtype=np.float32), c_float_p), n_theta, n_r, _p(preds, c_float_p),
                                   len(preds), _p(rel, c_float_p), C.byref(best))
     return (float(rel[0]), float(rel[1])), best.value
+
+
+def gmm_samples(states, num_samples):
+    """the num_samples x 4 double matrix computeGMM hands to cv::ml::EM (particle_filter.cpp:262-272)"""
+    st = np.ascontiguousarray(states)
+    out = np.empty((num_samples, 4), dtype=np.float64)
+    lib().orc_gmm_samples(st.ctypes.data_as(C.c_void_p), C.c_long(len(st)), int(num_samples), out.ctypes.data_as(C.c_void_p))
+    return out
+
+
+def adaptive_count(covs, last_num_particles, max_num_particles):
+    """num_particles_ of the next resampling from the GMM covariances (particle_filter.cpp:151-158); covs: (k, 4, 4)"""
+    cv = np.ascontiguousarray(covs, dtype=np.float32).reshape(-1, 16)
+    lib().orc_adaptive_count.restype = C.c_int
+    return int(lib().orc_adaptive_count(_p(cv, c_float_p), len(cv), int(last_num_particles), int(max_num_particles)))

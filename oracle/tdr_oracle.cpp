@@ -852,4 +852,32 @@ ORC_API void orc_active_best_rel_pos(const float* layers, const uint8_t* mask, i
   if (best_diff_out) *best_diff_out = best_diff;
 }
 
+// -----------------------------------------------------------------------------
+// SURVEY 8f rank 4  the sample matrix of ParticleFilter::computeGMM (src/particle_filter.cpp:262-272) and the adaptive
+// particle count of update() (:151-158)
+// -----------------------------------------------------------------------------
+ORC_API void orc_gmm_samples(const OrcState* st, long n, int num_samples, double* samples /* num_samples x 4 */) {
+  for (int i = 0; i < num_samples; i++) {
+    const long idx = std::min<long>(n - 1, (long)i * n / num_samples);      // :265-266
+    float s[4]; ml_state(st[idx], s);
+    samples[4 * i + 0] = s[0];
+    samples[4 * i + 1] = s[1];
+    samples[4 * i + 2] = 50 * std::cos(s[2]);                               // int * float(cosf) -> float -> double
+    samples[4 * i + 3] = 50 * std::sin(s[2]);
+  }
+}
+// covs: n_cov 4x4 matrices (row-major here; only the top-left 2x2 block is read).  Eigen::eigenvalues() of a real 2x2
+// matrix [[a, b], [c, d]]: (tr +- sqrt(tr^2 - 4 det)) / 2, complex when the discriminant is negative (then .real() = tr/2)
+ORC_API int orc_adaptive_count(const float* covs, int n_cov, int last_num_particles, int max_num_particles) {
+  int num = 0;
+  for (int k = 0; k < n_cov; k++) {
+    const float a = covs[16 * k + 0], b = covs[16 * k + 1], c = covs[16 * k + 4], d = covs[16 * k + 5];
+    const float tr = a + d, det = a * d - b * c, disc = tr * tr - 4 * det;
+    float e0, e1;
+    if (disc >= 0) { const float sq = std::sqrt(disc); e0 = (tr - sq) / 2; e1 = (tr + sq) / 2; } else { e0 = e1 = tr / 2; }
+    num += static_cast<int>(std::sqrt(e0) * std::sqrt(e1));                 // :155 area of the covariance ellipse
+  }
+  return std::min(std::max(num, 3 * last_num_particles / 4 + 10), max_num_particles);   // :157
+}
+
 ORC_API int orc_abi_version() { return 1; }

@@ -999,3 +999,14 @@ def test_active_localizer_best_relative_position(world, ctx):
     (d_g, t_g), best_g = ctx.active_best_rel_pos(np.float32([[400, 400, 0.5]]))
     assert (d_g, t_g) == (0.0, 0.0) and best_g == 0.0
     assert orc.active_best_rel_pos(world.layers, world.mask, 1.0, world.tab, N_THETA, N_R, np.float32([[400, 400, 0.5]])) == ((0.0, 0.0), 0.0)
+
+
+def test_gmm_sample_matrix(world, ctx):
+    """ParticleFilter::computeGMM's strided sample matrix off the device: positions to the bit, 50 cos / 50 sin within
+    the ulp of cosf / sinf"""
+    st, ld = synth.particles_tracking(23_456, world.pose, world.heading, seed=12)
+    ctx.pf_set_states(st, ld)
+    for k in (1000, 17):
+        got, want = ctx.pf_gmm_samples(k), orc.gmm_samples(st, k)
+        assert np.array_equal(got[:, :2], want[:, :2])
+        assert np.abs(got[:, 2:] - want[:, 2:]).max() <= 8e-6

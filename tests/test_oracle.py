@@ -375,3 +375,29 @@ def test_widen_mini_fixture_reproduces():
     polys = [g["poly_verts"][st[k]:st[k + 1]] for k in range(len(st) - 1)]
     lay = orc.raster_polygons(polys, g["poly_class"], 96, 72, 0.0, 1.0, 3, g["poly_excl"])
     assert np.array_equal(lay.astype(np.uint8), g["poly_layers"]) and set(np.unique(lay)) <= {0.0, 1.0}
+
+
+# ---- adaptive particle count and the GMM sample matrix
+def test_adaptive_count_known_answers():
+    """num_particles_ = clamp(sum_k floor(sqrt(l0_k) * sqrt(l1_k)), 3 * last / 4 + 10, max) (particle_filter.cpp:151-158)"""
+    cov = np.zeros((2, 4, 4), np.float32)
+    cov[0, 0, 0], cov[0, 1, 1] = 400.0, 900.0                      # eigenvalues 400, 900 -> 20 * 30 = 600
+    cov[1, :2, :2] = [[50.0, 30.0], [30.0, 50.0]]                  # eigenvalues 20, 80 -> sqrt(1600) = 40
+    assert orc.adaptive_count(cov, 100, 100000) == 640
+    assert orc.adaptive_count(cov, 2000, 100000) == 1510           # lower bound 3 * 2000 / 4 + 10
+    assert orc.adaptive_count(cov, 100, 500) == 500                # upper bound
+    rot = np.zeros((1, 4, 4), np.float32)
+    rot[0, :2, :2] = [[4.0, -9.0], [9.0, 4.0]]                     # complex pair 4 +- 9i: real parts 4 -> 2 * 2
+    assert orc.adaptive_count(rot, 0, 100) == 10                   # 4 < 0 * 3 / 4 + 10
+
+
+def test_gmm_samples_stride_and_encoding():
+    st, _ = synth.particles_tracking(2345, (100.0, 80.0), 0.5, seed=4)
+    s = orc.gmm_samples(st, 1000)
+    idx = np.minimum(len(st) - 1, np.arange(1000) * len(st) // 1000)
+    x = st["dx_m"][idx] * st["scale"][idx] + st["init_x_px"][idx]
+    assert np.array_equal(s[:, 0], x.astype(np.float64))
+    assert np.allclose(s[:, 2], 50 * np.cos(st["theta"][idx].astype(np.float64)), atol=1e-5)
+    assert np.allclose(np.hypot(s[:, 2], s[:, 3]), 50.0, atol=1e-4)
+    few = orc.gmm_samples(st[:7], 7)
+    assert np.array_equal(few[:, 1], (st["dy_m"][:7] * st["scale"][:7] + st["init_y_px"][:7]).astype(np.float64))

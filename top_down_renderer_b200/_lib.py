@@ -66,7 +66,7 @@ SYMBOLS = [
     "tdr_pf_count", "tdr_pf_checkpoint", "tdr_pf_restore", "tdr_pf_score", "tdr_pf_set_weights", "tdr_pf_get_weights", "tdr_pf_normalize", "tdr_pf_resample", "tdr_pf_normalize_resample",
     "tdr_pf_pose", "tdr_pf_update", "tdr_step", "tdr_grid_costs", "tdr_grid_best", "tdr_grid_set_costs_buffer", "tdr_grid_best_dev", "tdr_grid_best_key", "tdr_grid_key_decode", "tdr_grid_peer_alloc", "tdr_grid_peer_open",
     "tdr_grid_peer_set", "tdr_grid_peer_clear", "tdr_dev_ptr",
-    "tdr_pf_propagate", "tdr_pf_propagate_dev", "tdr_pf_propagate_rng", "tdr_pf_get_last_dist",
+    "tdr_pf_propagate", "tdr_pf_propagate_dev", "tdr_pf_propagate_rng", "tdr_pf_get_last_dist", "tdr_pf_gmm_samples",
     "tdr_pf_set_weights_dev", "tdr_pf_export_shard", "tdr_pf_update_gathered", "tdr_pf_export_split", "tdr_pf_normalize_gathered", "tdr_pf_resample_gathered", "tdr_pf_pose_gathered",
 ]
 

@@ -433,6 +433,11 @@ class Context:
                                              _pf(z) if want_z else None))
         return z
 
+    def pf_gmm_samples(self, num_samples):
+        out = np.empty((num_samples, 4), dtype=np.float64)
+        check(self._lib.tdr_pf_gmm_samples(self._h, int(num_samples), out.ctypes.data_as(C.c_void_p)))
+        return out
+
     def pf_get_last_dist(self):
         out = np.empty(self.pf_count(), dtype=np.float32)
         check(self._lib.tdr_pf_get_last_dist(self._h, _pf(out), C.c_int64(len(out))))

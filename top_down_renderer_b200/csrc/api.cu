@@ -554,6 +554,7 @@ int tdr_pf_propagate_rng(tdr_ctx* ctx, float trans_x, float trans_y, float omega
   }
   return TDR_OK;
 }
+int tdr_pf_gmm_samples(tdr_ctx* ctx, int num_samples, double* samples) { CTX_CHECK(ctx); return gmm_samples(ctx, num_samples, samples); }
 int tdr_pf_get_last_dist(tdr_ctx* ctx, float* last_dist, int64_t n) {
   CTX_CHECK(ctx);
   Particles& pt = ctx->part[ctx->cur];

@@ -147,6 +147,32 @@ int pose_of(tdr_ctx* ctx, Particles& pt, float* mean, float* cov_mean, float* ml
   return TDR_OK;
 }
 
+// ---- the strided sample matrix of ParticleFilter::computeGMM (particle_filter.cpp:262-272):
+// sample i = mlState of particle min(n - 1, i * n / num_samples) as (x, y, 50 cos theta, 50 sin theta) in double
+__global__ void k_gmm_samples(PartPtrs p, long long n, int num_samples, double* __restrict__ out) {
+  const int i = blockIdx.x * blockDim.x + threadIdx.x;
+  if (i >= num_samples) return;
+  long long idx = (long long)i * n / num_samples;
+  if (idx > n - 1) idx = n - 1;
+  float s[4]; ml_state(p, idx, s);
+  out[4 * i + 0] = (double)s[0];
+  out[4 * i + 1] = (double)s[1];
+  out[4 * i + 2] = (double)TDR_FMUL(50.f, (float)cos((double)s[2]));           // 50 * cos(float) is a float product
+  out[4 * i + 3] = (double)TDR_FMUL(50.f, (float)sin((double)s[2]));
+}
+int gmm_samples(tdr_ctx* ctx, int num_samples, double* samples_host) {
+  Particles& pt = ctx->part[ctx->cur];
+  TDR_REQUIRE(pt.n > 0 && num_samples > 0 && samples_host, TDR_EINVAL, "bad sample request");
+  if (int e = ctx->scratch.reserve((size_t)num_samples * 32)) return e;
+  PartPtrs p{pt.init_x.as<float>(), pt.init_y.as<float>(), pt.dx.as<float>(), pt.dy.as<float>(), pt.theta.as<float>(), pt.scale.as<float>()};
+  k_gmm_samples<<<(num_samples + 127) / 128, 128, 0, ctx->stream>>>(p, pt.n, num_samples, ctx->scratch.as<double>());
+  count_launch(ctx);
+  TDR_CUDA(cudaGetLastError());
+  TDR_CUDA(cudaMemcpyAsync(samples_host, ctx->scratch.p, (size_t)num_samples * 32, cudaMemcpyDeviceToHost, ctx->stream));
+  TDR_CUDA(cudaStreamSynchronize(ctx->stream));
+  return TDR_OK;
+}
+
 // ---- exhaustive grid: (min cost, first index) over n*n_shifts costs, NaN never wins
 __global__ void k_grid_best(const float* __restrict__ costs, long long n, unsigned long long* __restrict__ best) {
   unsigned long long loc = ~0ull;   // key = (ordered bits << 32 | low index bits)... index may exceed 32 bits -> two-stage

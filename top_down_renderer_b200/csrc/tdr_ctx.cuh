@@ -248,6 +248,7 @@ int exact_sums(tdr_ctx*, const float* const* cols, long long n, int ncols, float
 // pose.cu
 int pose_of(tdr_ctx*, Particles& pt, float* mean, float* cov_mean, float* ml, float* cov_ml);
 int grid_best(tdr_ctx*, const float* dev_costs, long long n, float* best_cost, long long* best_index);
+int gmm_samples(tdr_ctx*, int num_samples, double* samples_host);
 int propagate(tdr_ctx*, float tx, float ty, float omega, int scale_freeze, float pos_cov, float theta_cov, const float* z_dev, bool rng,
               unsigned long long seed, unsigned long long step, float* z_out_dev);
 inline float* grid_costs_ptr(tdr_ctx* c) { return c->grid_costs_ext ? c->grid_costs_ext : c->grid_costs.as<float>(); }

@@ -13,6 +13,7 @@
 #pragma once
 #include <math.h>
 #include <algorithm>
+#include <array>
 #include <cmath>
 #include <cstdint>
 #include <cstdio>
@@ -302,6 +303,28 @@ class ParticleFilter {
     }
     if (ok(tdr_pf_propagate(ctx(), trans.x, trans.y, omega, scale_frozen_ ? 1 : 0, params_.pos_cov, params_.theta_cov, z_.data(), n)))
       host_dirty_ = true;
+  }
+  // particle_filter.cpp:262-272: the sample matrix the GMM thread fits (num_samples x 4 doubles), straight off the device
+  std::vector<double> gmmSamples() {
+    int64_t n = 0;
+    if (!ctx() || tdr_pf_count(ctx(), &n) != 0 || n <= 0) return {};
+    const int num_samples = (int)std::min<int64_t>(1000, n);
+    std::vector<double> s((size_t)num_samples * 4);
+    if (!ok(tdr_pf_gmm_samples(ctx(), num_samples, s.data()))) s.clear();
+    return s;
+  }
+  // particle_filter.cpp:151-158: particle count of the next resampling from the GMM covariances (top-left 2x2 blocks of
+  // row-major 4x4 matrices): sum of sqrt(l0) * sqrt(l1) over the clusters, bounded below by 3/4 of the last count + 10
+  static int adaptiveCount(const std::vector<std::array<float, 16>>& covs, int last_num_particles, int max_num_particles) {
+    int num = 0;
+    for (const auto& cv : covs) {
+      const float a = cv[0], b = cv[1], c = cv[4], d = cv[5];
+      const float tr = a + d, det = a * d - b * c, disc = tr * tr - 4 * det;
+      float e0, e1;
+      if (disc >= 0) { const float sq = std::sqrt(disc); e0 = (tr - sq) / 2; e1 = (tr + sq) / 2; } else { e0 = e1 = tr / 2; }
+      num += static_cast<int>(std::sqrt(e0) * std::sqrt(e1));
+    }
+    return std::min(std::max(num, 3 * last_num_particles / 4 + 10), max_num_particles);
   }
   // particle_filter.cpp:94-189.  top_down_geo is accepted and ignored, as in the reference's cost (F10).
   void update(std::vector<ArrayXXf>& top_down_scan, std::vector<ArrayXXf>& /*top_down_geo*/, float res) {
