@@ -68,6 +68,47 @@ def _single(n_total, u, M):
     return wn, arg, idx, st[idx], ld[idx]
 
 
+def test_split_layout_roundtrip():
+    st, ld = synth.particles_tracking(10, (50.0, 60.0), 0.3, seed=1)
+    st["have_init"][::3] = 0
+    w = np.arange(10, dtype=np.float32)
+    wl, sb = sharded.pack_split_numpy(st, ld, w)
+    assert wl.shape == (20,) and sb.shape == (70,)
+    st2, ld2, w2 = sharded.unpack_split_numpy(np.concatenate([wl, wl]), np.concatenate([sb, sb]), 2, 10, synth.STATE_DTYPE)
+    assert np.array_equal(st2[:10], st) and np.array_equal(st2[10:], st) and np.array_equal(ld2[10:], ld) and np.array_equal(w2[:10], w)
+
+
+def _rank_main_split(rank, world, port, n_local, u, M, q):
+    """the two-collective step of ShardedFilter.step: weights + last_dist first, the states asynchronously while the
+    global normalisation runs, joined before the resampling"""
+    os.environ.update(MASTER_ADDR="127.0.0.1", MASTER_PORT=str(port))
+    dist.init_process_group("gloo", rank=rank, world_size=world)
+    try:
+        wd = _world()
+        n_total = n_local * world
+        st_all, ld_all = synth.particles_tracking(n_total, wd["pose"], wd["heading"], seed=5)
+        st_all["have_init"][::4] = 0
+        lo, hi = sharded.shard_range(n_total, rank, world)
+        st, ld = st_all[lo:hi].copy(), ld_all[lo:hi].copy()
+        w = orc.score_all(st, wd["fp"], wd["layers"], wd["mask"], 1.0, wd["tab"], 100, 25, wd["scan"], 2.0, wd["thetas"], wd["shifts"], n_threads=1)
+        wl, sb = (torch.from_numpy(a) for a in sharded.pack_split_numpy(st, ld, w))
+        wl_all = torch.empty(world * wl.numel(), dtype=torch.float32)
+        st_all_t = torch.empty(world * sb.numel(), dtype=torch.float32)
+        dist.all_gather_into_tensor(wl_all, wl)                                   # 8 B / particle
+        work = dist.all_gather_into_tensor(st_all_t, sb, async_op=True)          # 28 B / particle, in flight ...
+        g_w = wl_all.numpy().reshape(world, 2, n_local)[:, 0, :].reshape(-1).copy()
+        g_ld = wl_all.numpy().reshape(world, 2, n_local)[:, 1, :].reshape(-1).copy()
+        wn, arg, _ = orc.normalize(g_w, g_ld)                                     # ... while every rank normalises globally
+        work.wait()
+        g_st, g_ld2, g_w2 = sharded.unpack_split_numpy(wl_all.numpy(), st_all_t.numpy(), world, n_local, synth.STATE_DTYPE)
+        assert np.array_equal(g_ld2, g_ld) and np.array_equal(g_w2.view(np.uint32), g_w.view(np.uint32))
+        i0, i1 = sharded.sample_slice(M, rank, world)
+        idx = orc.resample_fast(wn, u, M)[i0:i1]
+        q.put((rank, wn, arg, idx, g_st[idx], g_ld[idx]))
+    finally:
+        dist.destroy_process_group()
+
+
 def _rank_main(rank, world, port, n_local, u, M, q):
     os.environ.update(MASTER_ADDR="127.0.0.1", MASTER_PORT=str(port))
     dist.init_process_group("gloo", rank=rank, world_size=world)
@@ -92,14 +133,14 @@ def _rank_main(rank, world, port, n_local, u, M, q):
         dist.destroy_process_group()
 
 
-@pytest.mark.parametrize("world", [2, 3])
-def test_sharded_update_equals_single_process(world):
+@pytest.mark.parametrize("world,split", [(2, False), (3, False), (2, True), (3, True)])
+def test_sharded_update_equals_single_process(world, split):
     n_local, M = 60, 150
     u = orc.uniform_draw(9)
     ctx = mp.get_context("spawn")
     q = ctx.Queue()
     port = _free_port()
-    procs = [ctx.Process(target=_rank_main, args=(r, world, port, n_local, u, M, q)) for r in range(world)]
+    procs = [ctx.Process(target=_rank_main_split if split else _rank_main, args=(r, world, port, n_local, u, M, q)) for r in range(world)]
     for p in procs:
         p.start()
     res = sorted([q.get(timeout=240) for _ in range(world)], key=lambda t: t[0])

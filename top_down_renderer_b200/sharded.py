@@ -160,3 +160,31 @@ def unpack_blocks_numpy(gathered, world, n_local, state_dtype):
         st[name] = g[:, k, :].reshape(N)
     st["have_init"] = (g[:, 7, :].reshape(N) != 0).astype(np.uint8)
     return st, g[:, 8, :].reshape(N).copy(), g[:, 0, :].reshape(N).copy()
+
+
+# the two-collective wire format of ShardedFilter.step (k_pack_split / k_unpack_wl / k_unpack_states):
+#   wl[2][n]     = raw weight, last_dist                                  (all-gathered first: all the normalisation needs)
+#   states[7][n] = init_x, init_y, dx, dy, theta, scale, have_init as 0/1 (all-gathered behind the normalisation)
+def pack_split_numpy(states, last_dist, weights):
+    import numpy as np
+    n = len(states)
+    wl = np.empty((2, n), dtype=np.float32)
+    wl[0], wl[1] = weights, last_dist
+    st = np.empty((7, n), dtype=np.float32)
+    for k, name in enumerate(_ROWS[1:7]):
+        st[k] = states[name]
+    st[6] = (states["have_init"] != 0).astype(np.float32)
+    return wl.reshape(-1), st.reshape(-1)
+
+
+def unpack_split_numpy(wl_all, st_all, world, n_local, state_dtype):
+    """gathered pieces in rank order -> (states[N], last_dist[N], weights[N]) in global particle order"""
+    import numpy as np
+    N = world * n_local
+    wl = np.asarray(wl_all, dtype=np.float32).reshape(world, 2, n_local)
+    g = np.asarray(st_all, dtype=np.float32).reshape(world, 7, n_local)
+    st = np.zeros(N, dtype=state_dtype)
+    for k, name in enumerate(_ROWS[1:7]):
+        st[name] = g[:, k, :].reshape(N)
+    st["have_init"] = (g[:, 6, :].reshape(N) != 0).astype(np.uint8)
+    return st, wl[:, 1, :].reshape(N).copy(), wl[:, 0, :].reshape(N).copy()
