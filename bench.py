@@ -433,7 +433,7 @@ def run_grid(args, wl):
     lo, hi = sharded.shard_range(n_total, rank, world)
     centers = np.ascontiguousarray(centers_all[lo:hi])
     n_local = hi - lo
-    shifts = np.arange(int(os.environ.get("TDR_BENCH_GRID_SHIFTS", N_THETA)), dtype=np.int32)   # experiments only
+    shifts = np.arange(N_THETA, dtype=np.int32)
     S = len(shifts)
     ctx = Context(local)
     ctx.map_set_class_image(inp["img"], inp["lut"], C, 1.0)

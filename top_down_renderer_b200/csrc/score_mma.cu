@@ -105,7 +105,6 @@ struct MmaParams {
   // fused all-gather: every cost is stored into all ranks' full arrays (NVLink peer mappings) at this rank's rows
   float* cost_peers[TDR_MAX_PEERS]; int n_cost_peers; long long cost_row0;
   unsigned long long* grid_key;     // grid mode: (min cost, first global flat index) over everything this launch computes
-  int dbg_nostore;
   int identity_shifts;      // shifts[k] == k for all k and n_shifts % 4 == 0: vector stores of the cost rows
 };
 
@@ -316,7 +315,7 @@ __global__ void __launch_bounds__(128 * T * R + 64, MmaCfg<T, R, ATM, G>::kCtasP
       float best = 3.402823466e+38f;                                                         // :193-204
       int best_k = 0x7fffffff;
       uint32_t vc[16], vn[16];
-      const bool async_rows = ATM && sp.identity_shifts && (sp.costs || sp.n_cost_peers) && !sp.dbg_nostore;   // CTA-uniform
+      const bool async_rows = ATM && sp.identity_shifts && (sp.costs || sp.n_cost_peers);   // CTA-uniform
       if (async_rows) bulk_wait_read();          // the previous tile's stores have read this thread's staging row
 #pragma unroll 1
       for (int ch = 0; ch * 16 < n_theta; ch++) {
@@ -333,7 +332,7 @@ __global__ void __launch_bounds__(128 * T * R + 64, MmaCfg<T, R, ATM, G>::kCtasP
           // first strict minimum in LIST order == lexicographic minimum of (cost, list position)
           if (k >= 0 && (cst[j] < best || (cst[j] == best && k < best_k))) { best = cst[j]; best_k = k; }
         }
-        if ((sp.costs || sp.n_cost_peers) && !sp.dbg_nostore) {          // warp-uniform
+        if ((sp.costs || sp.n_cost_peers)) {          // warp-uniform
           const int n_dst = sp.n_cost_peers ? sp.n_cost_peers : 1;
           const long long grow = (sp.n_cost_peers ? sp.cost_row0 + i : i) * sp.n_shifts;
           if (ATM && sp.identity_shifts) {
@@ -637,7 +636,6 @@ int score_mma(tdr_ctx* ctx, float res, bool grid_mode, long long n_items, float 
   sp.rings = ctx->scan_op.as<uint4>(); sp.norm_op = d_norm_op; sp.n_groups = n_groups;
   sp.perm = ctx->perm.as<int>();
   sp.shifts = dev_shifts; sp.n_shifts = n_shifts;
-  if (const char* e = getenv("TDR_DEBUG_NOSTORE")) sp.dbg_nostore = atoi(e);
   if (grid_mode) {
     sp.n_work = n_items; sp.centers = ctx->grid_centers.as<float>(); sp.grid_scale = grid_scale;
     sp.costs = grid_costs_ptr(ctx);
