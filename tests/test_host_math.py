@@ -217,3 +217,34 @@ def test_eig_cache_format_and_round_trip(tmp_path):
     assert not eigcache.cache_is_valid(str(tmp_path / "nowhere"), "/maps/campus.svg", 2, 0.5)
     l2, g2, m2 = eigcache.load_cache(d, C)
     assert np.array_equal(l2, layers) and np.array_equal(g2, geo) and np.array_equal(m2, mask)
+
+
+def test_lean_lattice_coordinate_equals_the_literal_form(hm):
+    """tdr_math.cuh lattice_coord (interval test + trunc, what the tensor-core kernels run) against
+    f2i_x86(round_half_away(v)) followed by 0 <= index < n (top_down_map_polar.cpp:31-37): every float near every
+    rounding boundary of a 4000-px axis, the border values, huge / tiny / non-finite values, and 4e6 random ones"""
+    hm.hm_lattice_coord_mismatches.restype = C.c_long
+    hm.hm_lattice_coord_mismatches.argtypes = [C.POINTER(C.c_float), C.c_long, C.c_int]
+    hm.hm_lattice_coord.argtypes = [C.c_float, C.c_int]
+    for limit in (1, 2, 1000, 4000, 4001):
+        k = np.arange(-3, limit + 3, dtype=np.float64)
+        near = []
+        for off in (0.0, 0.5, -0.5):
+            c = (k + off).astype(np.float32)
+            for _ in range(3):                               # the boundary and three floats on either side of it
+                near += [c]
+                c = np.nextafter(c, np.float32(np.inf))
+            c = (k + off).astype(np.float32)
+            for _ in range(3):
+                c = np.nextafter(c, np.float32(-np.inf))
+                near += [c]
+        special = np.float32([0.0, -0.0, np.nan, np.inf, -np.inf, 1e30, -1e30, 2147483648.0, -2147483648.0, 2147483520.0,
+                              1e-38, -1e-38, 1e-45, -1e-45, 8388608.0, 16777216.0, -0.49999997, 0.49999997])
+        rng = np.random.default_rng(limit)
+        rnd = np.concatenate([rng.uniform(-10, limit + 10, 2_000_000), rng.normal(limit / 2, limit, 2_000_000)]).astype(np.float32)
+        v = np.ascontiguousarray(np.concatenate(near + [special, rnd]), dtype=np.float32)
+        assert hm.hm_lattice_coord_mismatches(v.ctypes.data_as(C.POINTER(C.c_float)), len(v), limit) == 0, limit
+    # the documented boundary cases
+    assert hm.hm_lattice_coord(-0.5, 10) == -1 and hm.hm_lattice_coord(np.nextafter(np.float32(-0.5), np.float32(0)), 10) == 0
+    assert hm.hm_lattice_coord(9.5, 10) == -1 and hm.hm_lattice_coord(np.nextafter(np.float32(9.5), np.float32(0)), 10) == 9
+    assert hm.hm_lattice_coord(0.5, 10) == 1 and hm.hm_lattice_coord(0.49999997, 10) == 0 and hm.hm_lattice_coord(float("nan"), 10) == -1

@@ -28,6 +28,18 @@ int hm_cart_bin(float x, float y, float res, int rows, int cols, int* xi, int* y
   return cart_bin(x, y, res, rows, cols, xi, yi) ? 1 : 0;
 }
 int hm_lattice_index(float tab, float scale, float res, float off) { return lattice_index(tab, scale, res, off); }
+// the lean lattice coordinate of the tensor-core kernels against the literal form, in bulk: number of disagreements
+long hm_lattice_coord_mismatches(const float* v, long n, int limit) {
+  long bad = 0;
+  const float hi = (float)limit - 0.5f;
+  for (long i = 0; i < n; i++) {
+    const int lit = f2i_x86(round_half_away(v[i]));
+    const int want = (lit >= 0 && lit < limit) ? lit : -1;
+    if (lattice_coord(v[i], hi) != want) bad++;
+  }
+  return bad;
+}
+int hm_lattice_coord(float v, int limit) { return lattice_coord(v, (float)limit - 0.5f); }
 int hm_rot_to_shift(float rot, int n_theta) { return rot_to_shift(rot, n_theta); }
 float hm_round(float x) { return round_half_away(x); }
 int hm_f2i(float x) { return f2i_x86(x); }

@@ -196,11 +196,10 @@ struct GatherGeom {
 // of the instructions (the gather threads are issue-bound): round_half_away(v) lies in [0, limit) exactly when
 // -0.5 < v < limit - 0.5 (NaN fails both), and inside that interval it is trunc(v) + (v - trunc(v) >= 0.5).
 __device__ __forceinline__ uint32_t lattice_record(float vy, float vx, const GatherGeom& g) {
-  const bool ok = vy > -0.5f && vy < g.row_hi && vx > -0.5f && vx < g.col_hi;
-  const float ty = truncf(vy), tx = truncf(vx);
-  const int r = (int)ty + (TDR_FSUB(vy, ty) >= 0.5f ? 1 : 0);
-  const int c = (int)tx + (TDR_FSUB(vx, tx) >= 0.5f ? 1 : 0);
-  const uint32_t ur = (uint32_t)r, uc = (uint32_t)c;
+  // lattice_coord (tdr_math.cuh) for both coordinates with ONE select at the end: the rounded values are formed
+  // unconditionally (garbage off the map, never used)
+  const bool ok = lattice_in(vy, g.row_hi) && lattice_in(vx, g.col_hi);
+  const uint32_t ur = (uint32_t)lattice_round(vy), uc = (uint32_t)lattice_round(vx);
   const uint32_t rec = ((ur << g.ph_log2) + (uc & ((1u << g.ph_log2) - 1u))) * (uint32_t)g.ph_cols + (uc >> g.ph_log2);
   return ok ? rec : g.zero_rec;
 }

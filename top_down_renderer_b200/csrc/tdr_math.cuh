@@ -209,6 +209,17 @@ TDR_HD int lattice_index(float tab, float scale, float res, float off) {
   return f2i_x86(round_half_away(TDR_FADD(TDR_FMUL(TDR_FMUL(tab, scale), res), off)));
 }
 
+// the same decision without the detour through x86 conversion semantics: f2i_x86(round_half_away(v)) lies in [0, n)
+// exactly when -0.5 < v < n - 0.5 (v = -0.5 rounds away to -1, v = n - 0.5 to n, NaN fails both comparisons), and inside
+// that interval it is trunc(v) + (v - trunc(v) >= 0.5).  hi = n - 0.5 (exact in fp32 for n < 2^23).  Returns -1 off the
+// range.  Proven equal to the literal form on the CPU (tests/test_host_math.py).
+TDR_HD bool lattice_in(float v, float hi) { return v > -0.5f && v < hi; }
+TDR_HD int lattice_round(float v) {                    // round_half_away(v) as an int, for v inside the interval only
+  const float t = truncf(v);
+  return (int)t + (TDR_FSUB(v, t) >= 0.5f ? 1 : 0);
+}
+TDR_HD int lattice_coord(float v, float hi) { return lattice_in(v, hi) ? lattice_round(v) : -1; }
+
 // a10 rot -> row shift   state_particle.cpp:123-128
 TDR_HD int rot_to_shift(float rot, int n_theta) {
   double v = (double)TDR_FDIV(TDR_FMUL(rot, (float)n_theta), 2.0f) / 3.14159265358979323846;
