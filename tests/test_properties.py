@@ -1,0 +1,95 @@
+"""Property tests (hypothesis) of the CPU oracle and the host-side formats — the size-independent invariants SURVEY.md
+section 4 lists: systematic resampling is monotone and clamps to the last index, the polar rasteriser conserves points,
+the shift-correlation is a row roll, the distance transform commutes with transposition, the map cache round-trips."""
+import math
+
+import numpy as np
+from hypothesis import given, settings, strategies as st
+
+from oracle import numpy_twin as twin
+from oracle import oracle as orc
+from top_down_renderer_b200 import eigcache, synth
+
+FAST = settings(max_examples=25, deadline=None)
+
+
+@FAST
+@given(st.integers(1, 400), st.integers(1, 500), st.floats(0, 0.9999), st.integers(0, 2**31 - 1))
+def test_resample_is_monotone_in_range_and_matches_the_literal_loop(n, M, u, seed):
+    rng = np.random.default_rng(seed)
+    w = rng.random(n).astype(np.float32) ** 4
+    w /= np.float32(w.sum() if w.sum() > 0 else 1)
+    idx = orc.resample_fast(w, np.float32(u), M)
+    assert len(idx) == M and (np.diff(idx) >= 0).all() and idx.min() >= 0 and idx.max() <= n - 1
+    assert np.array_equal(idx, orc.resample_literal(w, np.float32(u), M))          # the O(N*M) loop of :172-185
+    # a sample beyond the total clamps to the last particle
+    assert orc.resample_fast((w * np.float32(0.5)).astype(np.float32), np.float32(u), M)[-1] <= n - 1
+
+
+@FAST
+@given(st.integers(0, 3000), st.floats(0.25, 6.0), st.integers(0, 2**31 - 1))
+def test_polar_rasteriser_conserves_points(n, res, seed):
+    rng = np.random.default_rng(seed)
+    C_ = 3
+    pts = np.zeros((n, 8), dtype=np.float32)
+    pts[:, 0:2] = rng.normal(0, 40, (n, 2))
+    pts[:, 4] = rng.integers(0, 6, n)                                 # classes 3..5 map to -1
+    pts[rng.random(n) < 0.1, 0:2] = 0                                 # invalid returns
+    lut = synth.identity_lut(C_)
+    ang = np.float32(2 * math.pi / 100)
+    img = orc.render_polar(pts, np.float32(res), ang, 100, 25, lut, C_)
+    assert (img >= 0).all() and img.sum() <= n and img.sum() == np.rint(img).sum()
+    # every counted point is a valid, in-range, known-class one (the twin re-derives the bins independently)
+    assert np.array_equal(img, twin.render_polar(pts, np.float32(res), ang, 100, 25, lut, C_))
+
+
+@FAST
+@given(st.integers(2, 40), st.integers(1, 12), st.integers(0, 200), st.integers(0, 2**31 - 1))
+def test_shift_correlation_is_a_row_roll(n_theta, n_r, shift, seed):
+    rng = np.random.default_rng(seed)
+    C_, P = 2, n_theta * n_r
+    scan = rng.integers(0, 5, (C_, P)).astype(np.float32)
+    classes = (rng.random((C_, P)) * 50).astype(np.float32)
+    known = (rng.random(P) < 0.8).astype(np.float32)
+    cw = np.float32([1.0, 0.5])
+    s_ = shift % n_theta
+    got = orc.cost_for_shift(scan, classes, known, n_theta, n_r, cw, s_)
+    want = twin.cost_for_shift(scan, classes, known, n_theta, n_r, cw, s_)     # explicit np.roll of the scan rows
+    assert (np.isnan(got) and np.isnan(want)) or abs(got - want) <= 1e-5 * max(abs(want), 1e-6)
+
+
+@FAST
+@given(st.integers(3, 40), st.integers(3, 40), st.integers(0, 2**31 - 1))
+def test_distance_fields_commute_with_transposition(rows, cols, seed):
+    rng = np.random.default_rng(seed)
+    lay = (rng.random((2, cols, rows)) < 0.85).astype(np.float32)     # (C, cols, rows): 0 = class present
+    d, m = orc.compute_dists(lay.copy(), 1.0)
+    dt, mt = orc.compute_dists(np.ascontiguousarray(lay.transpose(0, 2, 1)), 1.0)
+    assert np.array_equal(d, dt.transpose(0, 2, 1)) and np.array_equal(m, mt.T)
+    assert d.max() <= 50 and (d[:, m != 0] == 0).all()
+
+
+@FAST
+@given(st.integers(1, 30), st.integers(1, 30), st.integers(1, 4), st.integers(0, 2**31 - 1))
+def test_map_cache_round_trips(rows, cols, C_, seed):
+    import tempfile
+    rng = np.random.default_rng(seed)
+    layers = rng.random((C_, cols, rows)).astype(np.float32) * 50
+    geo = rng.random((2, cols, rows)).astype(np.float32)
+    mask = (rng.random((cols, rows)) < 0.2).astype(np.uint8)
+    with tempfile.TemporaryDirectory() as d:
+        eigcache.save_cache(d, "m.svg", layers, geo, mask, 1.0)
+        assert eigcache.cache_is_valid(d, "m.svg", C_, 1.0)
+        l2, g2, m2 = eigcache.load_cache(d, C_)
+    assert np.array_equal(l2, layers) and np.array_equal(g2, geo) and np.array_equal(m2, mask)
+
+
+@FAST
+@given(st.integers(0, 5000), st.integers(1, 100000), st.lists(st.floats(0, 1e4), min_size=0, max_size=12))
+def test_adaptive_count_stays_inside_its_bounds(last, cap, diag):
+    covs = np.zeros((len(diag) // 2, 4, 4), np.float32)
+    for k in range(len(diag) // 2):
+        covs[k, 0, 0], covs[k, 1, 1] = diag[2 * k], diag[2 * k + 1]
+    n = orc.adaptive_count(covs, last, cap)
+    area = sum(int(math.sqrt(np.float32(diag[2 * k])) * math.sqrt(np.float32(diag[2 * k + 1]))) for k in range(len(diag) // 2))
+    assert n == min(max(area, 3 * last // 4 + 10), cap) or abs(n - min(max(area, 3 * last // 4 + 10), cap)) <= len(diag)
