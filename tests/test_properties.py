@@ -10,7 +10,9 @@ from oracle import numpy_twin as twin
 from oracle import oracle as orc
 from top_down_renderer_b200 import eigcache, synth
 
-FAST = settings(max_examples=25, deadline=None)
+# derandomize: the suite is a gate (pytest -x) — the same examples every run; explored with other seeds and 200 examples
+# per property when the tests were written
+FAST = settings(max_examples=25, deadline=None, derandomize=True, database=None)
 
 
 @FAST
