@@ -180,3 +180,41 @@ def propagate_with_z(states, tx, ty, omega, scale_freeze, pos_cov, theta_cov, z)
         st["scale"] = st["scale"].astype(f) * (z[:, 3] * sd_sc + f(1))
     mx, my = lx - dx, ly - dy
     return st, np.sqrt(mx * mx + my * my)
+
+
+def raster_polygons(polys, poly_class, map_w, map_h, resolution, num_classes, exclusive):
+    """getRasterMap + getClasses (top_down_map.cpp:328-408) for rot = 0, vectorised numpy in float32: one (rows, cols)
+    grid of sample points, the even-odd rule as a crossing COUNT per polygon (parity instead of the reference's sign
+    flips), classes combined with logical or.  Returns (C, cols, rows) like the oracle."""
+    f = np.float32
+    rows, cols = int(map_h / resolution), int(map_w / resolution)
+
+    def lin(size):
+        lo, hi = f(-resolution * (size - 1) / 2.0), f(resolution * (size - 1) / 2.0)
+        if size == 1:
+            return np.array([lo], dtype=f)
+        step = (hi - lo) / f(size - 1)
+        v = lo + np.arange(size, dtype=f) * step
+        v[-1] = hi
+        return v.astype(f)
+    py = (lin(rows) + f(map_h) / f(2))[:, None] + np.zeros((1, cols), dtype=f)       # (rows, cols)
+    px = (lin(cols) + f(map_w) / f(2))[None, :] + np.zeros((rows, 1), dtype=f)
+    inside = np.zeros((num_classes, rows, cols), dtype=bool)
+    for poly, c in zip(polys, poly_class):
+        p = np.asarray(poly, dtype=f)
+        crossings = np.zeros((rows, cols), dtype=np.int32)
+        for i in range(len(p)):
+            xi, yi = p[i]
+            xj, yj = p[i - 1]
+            straddle = (py < yi) != (py < yj)
+            with np.errstate(divide="ignore", invalid="ignore"):
+                xint = xi + ((xj - xi) * (py - yi) / (yj - yi))
+            crossings += (straddle & (px < xint)).astype(np.int32)
+        inside[c] |= (crossings % 2) == 1
+    lay = np.where(inside, f(0), f(1)).astype(f)
+    for under in exclusive:
+        for cls in exclusive:
+            if under < cls:
+                lay[under] = lay[under] + (f(1) - lay[cls])
+        lay[under] = np.minimum(lay[under], f(1))
+    return np.ascontiguousarray(lay.transpose(0, 2, 1))

@@ -401,3 +401,23 @@ def test_gmm_samples_stride_and_encoding():
     assert np.allclose(np.hypot(s[:, 2], s[:, 3]), 50.0, atol=1e-4)
     few = orc.gmm_samples(st[:7], 7)
     assert np.array_equal(few[:, 1], (st["dy_m"][:7] * st["scale"][:7] + st["init_y_px"][:7]).astype(np.float64))
+
+
+def test_raster_polygons_equals_numpy_twin():
+    """an independently structured restatement (crossing counts on a 2-D grid, logical or over polygons) gives the same
+    layers bit for bit — pins the row / column conventions and the exclusive-class pass of the C++ oracle"""
+    rng = np.random.default_rng(23)
+    polys, cls = [], []
+    for _ in range(40):
+        k = int(rng.integers(3, 10))
+        ang = np.sort(rng.uniform(0, 2 * np.pi, k))
+        rad = rng.uniform(3, 40) * rng.uniform(0.3, 1.0, k)
+        cx, cy = rng.uniform(-5, 125), rng.uniform(-5, 95)
+        p = np.stack([cx + rad * np.cos(ang), cy + rad * np.sin(ang)], axis=1).astype(np.float32)
+        polys.append(np.rint(p).astype(np.float32) if rng.random() < 0.4 else p)
+        cls.append(int(rng.integers(0, 4)))
+    for resolution in (1.0, 0.5):
+        for excl in ([], [0, 0, 0, 0, 0, 1, 2], [2, 1, 0]):
+            a = orc.raster_polygons(polys, cls, 120, 90, 0.0, resolution, 4, excl)
+            b = twin.raster_polygons(polys, cls, 120, 90, resolution, 4, excl)
+            assert a.shape == b.shape and np.array_equal(a, b), (resolution, excl)
