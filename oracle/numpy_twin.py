@@ -218,3 +218,35 @@ def raster_polygons(polys, poly_class, map_w, map_h, resolution, num_classes, ex
                 lay[under] = lay[under] + (f(1) - lay[cls])
         lay[under] = np.minimum(lay[under], f(1))
     return np.ascontiguousarray(lay.transpose(0, 2, 1))
+
+
+def active_best_rel_pos(layers, mask, resolution, tab, n_theta, n_r, preds):
+    """ActiveLocalizer::getBestRelPos (active_localizer.cpp:45-82) with np.roll for the heading rotation and float64 sums
+    of the pairwise absolute differences.  Returns ((dist, theta), best_diff)."""
+    f = np.float32
+    preds = np.asarray(preds, dtype=f).reshape(-1, 3)
+    C_ = layers.shape[0]
+    best_diff, best = 0.0, (0.0, 0.0)
+    dist = f(50)
+    while best_diff < 6000 and dist < 150:
+        theta = f(0)
+        while float(theta) < 2 * math.pi:
+            maps = []
+            for x, y, th in preds:
+                px = f(x + dist * f(math.cos(f(theta + th))))      # cosf stand-in: double cos rounded to float
+                py = f(y + dist * f(math.sin(f(theta + th))))
+                d, _ = local_map_polar(layers, mask, resolution, tab, px, py, f(1), f(2))
+                v = float(f(f(th * f(n_theta)) / f(2))) / math.pi
+                shift = int(math.floor(abs(v) + 0.5) * (1 if v >= 0 else -1)) % n_theta
+                maps.append(np.roll(d.reshape(C_, n_r, n_theta), shift, axis=2).astype(np.float64))
+            total, cnt = 0.0, 0
+            for i in range(len(maps)):
+                for j in range(i):
+                    total += np.abs(maps[i] - maps[j]).sum()
+                    cnt += C_
+            diff = total / cnt if cnt else float("nan")
+            if diff > best_diff:
+                best_diff, best = diff, (float(dist), float(theta))
+            theta = f(float(theta) + math.pi / 8)
+        dist = f(dist + 25)
+    return best, best_diff

@@ -421,3 +421,15 @@ def test_raster_polygons_equals_numpy_twin():
             a = orc.raster_polygons(polys, cls, 120, 90, 0.0, resolution, 4, excl)
             b = twin.raster_polygons(polys, cls, 120, 90, resolution, 4, excl)
             assert a.shape == b.shape and np.array_equal(a, b), (resolution, excl)
+
+
+def test_active_localizer_equals_numpy_twin(small_world):
+    """getBestRelPos against the np.roll / float64 twin: same relative position, difference within 1e-5"""
+    w = small_world
+    rng = np.random.default_rng(3)
+    rows, cols = w["layers"].shape[2], w["layers"].shape[1]
+    for n in (2, 4):
+        preds = np.stack([rng.uniform(0.2, 0.8, n) * cols, rng.uniform(0.2, 0.8, n) * rows, rng.uniform(-3, 3, n)], axis=1).astype(np.float32)
+        (d_o, t_o), best_o = orc.active_best_rel_pos(w["layers"], w["mask"], 1.0, w["tab"], 100, 25, preds)
+        (d_t, t_t), best_t = twin.active_best_rel_pos(w["layers"], w["mask"], 1.0, w["tab"], 100, 25, preds)
+        assert (d_o, t_o) == (d_t, t_t) and abs(best_o - best_t) <= 1e-5 * best_t
