@@ -250,3 +250,100 @@ def active_best_rel_pos(layers, mask, resolution, tab, n_theta, n_r, preds):
             theta = f(float(theta) + math.pi / 8)
         dist = f(dist + 25)
     return best, best_diff
+
+
+# ---- particle initialisation, restated WITHOUT libstdc++: the Mersenne twister from numpy, the two
+# distributions from their published libstdc++ algorithms (bits/random.tcc), logf / pow from glibc through ctypes
+class LibstdcxxEngine:
+    """std::mt19937(seed) plus generate_canonical<float, 24>: one 32-bit output -> float(x) / 2^32, and 1.0 (only
+    reachable through the rounding of x >= 2^32 - 128) replaced by the largest float below 1"""
+
+    def __init__(self, seed):
+        self.bg = np.random.MT19937()
+        self.bg._legacy_seeding(int(seed))            # init_genrand: the same state std::mt19937(seed) starts from
+        self.draws = 0
+
+    def canonical(self):
+        self.draws += 1
+        r = np.float32(int(self.bg.random_raw())) / np.float32(4294967296.0)
+        return np.float32(r) if r < 1 else np.nextafter(np.float32(1), np.float32(0))
+
+
+class LibstdcxxNormal:
+    """std::normal_distribution<float>(mean, stddev): Marsaglia's polar method, second value of a pair saved"""
+
+    def __init__(self, mean=0.0, stddev=1.0):
+        import ctypes
+        self.mean, self.stddev, self.saved = np.float32(mean), np.float32(stddev), None
+        self.logf = ctypes.CDLL("libm.so.6").logf
+        self.logf.restype, self.logf.argtypes = ctypes.c_float, [ctypes.c_float]
+
+    def __call__(self, eng):
+        f = np.float32
+        if self.saved is not None:
+            ret, self.saved = self.saved, None
+        else:
+            while True:
+                x = f(f(2) * eng.canonical() - 1.0)
+                y = f(f(2) * eng.canonical() - 1.0)
+                r2 = f(f(x * x) + f(y * y))
+                if not (r2 > 1.0 or r2 == 0.0):
+                    break
+            mult = np.sqrt(f(f(f(-2) * f(self.logf(float(r2)))) / r2))
+            self.saved = f(x * mult)
+            ret = f(y * mult)
+        return f(f(ret * self.stddev) + self.mean)
+
+
+def init_particles(seed, layers, resolution, map_center, max_n, init_pos_px=(-1.0, -1.0), init_pos_px_cov=-1.0,
+                   init_pos_m=(math.inf, math.inf), init_pos_deg_theta=math.inf, init_pos_deg_cov=10.0, fixed_scale=-1.0):
+    """ParticleFilter::initializeParticles (particle_filter.cpp:19-84) with StateParticle's constructor
+    (state_particle.cpp:3-49) on distance layers (C, cols, rows).  Returns (list of (init_x, init_y, theta, scale,
+    have_init), engine outputs consumed)."""
+    f = np.float32
+    C, cols, rows = layers.shape
+    eng = LibstdcxxEngine(seed)
+    px, py, pcov = f(init_pos_px[0]), f(init_pos_px[1]), f(init_pos_px_cov)
+
+    def on_road(x, y):                                 # getClassesAtPoint(Vector2i(x, y)) contains class 1
+        cx, cy = int(f(int(x)) / f(resolution)), int(f(int(y)) / f(resolution))
+        return 0 <= cx < cols and 0 <= cy < rows and layers[1, cx, cy] < 1
+
+    def construct():
+        normal = LibstdcxxNormal()
+        mw, mh = f(f(cols) * f(resolution)), f(f(rows) * f(resolution))
+        scale = f(math.pow(10, (float(eng.canonical()) - 0.5) * 2)) if fixed_scale < 0 else f(fixed_scale)
+        while True:
+            if px > 0:
+                x = min(max(f(f(normal(eng) * pcov) + px), f(0)), mw)
+                y = min(max(f(f(normal(eng) * pcov) + py), f(0)), mh)
+            else:
+                x = f(eng.canonical() * mw)
+                y = f(eng.canonical() * mh)
+            if on_road(x, y):
+                break
+        if init_pos_deg_theta != math.inf:
+            th = f(f(normal(eng) * f(init_pos_deg_cov)) + f(init_pos_deg_theta))
+            return (x, y, f(float(th) * (math.pi / 180)), scale, 1)
+        return (x, y, f(0), scale, 0)
+
+    num_at_scale = 10 if fixed_scale < 0 else 1
+    if fixed_scale >= 0 and init_pos_m[0] != math.inf:
+        px = f(f(f(init_pos_m[0]) * f(fixed_scale)) + f(map_center[0]))
+        py = f(f(f(init_pos_m[1]) * f(fixed_scale)) + f(map_center[1]))
+        if px < 0 or px >= cols or py < 0 or py >= rows:
+            return [], 0
+        if not any(on_road(f(px + f(dx)), f(py + f(dy))) for dx in range(-4, 5) for dy in range(-4, 5)):
+            return [], 0
+    out = []
+    for _ in range(max_n // num_at_scale):
+        proto = construct()
+        scale = f(0)
+        while scale < 1:
+            part = construct()
+            if fixed_scale < 0:
+                part = proto[:3] + (f(math.pow(10.0, float(scale))), proto[4])
+            out.append(part)
+            construct()
+            scale = f(float(scale) + 1.0 / num_at_scale)
+    return out, eng.draws

@@ -8,6 +8,7 @@ reference legs may import this module.
 from __future__ import annotations
 
 import ctypes as C
+import math
 import os
 import subprocess
 
@@ -255,8 +256,10 @@ def resample_fast(w, shift, M, want_prefix=False):
     return (idx, pre) if want_prefix else idx
 
 
-def uniform_draw(seed):
-    return float(lib().orc_uniform_draw(C.c_uint32(seed)))
+def uniform_draw(seed, discard=0):
+    """the resampling offset of particle_filter.cpp:172-173 from mt19937(seed) after `discard` earlier outputs"""
+    lib().orc_uniform_draw_from.restype = C.c_float
+    return float(lib().orc_uniform_draw_from(C.c_uint32(seed), C.c_uint64(discard)))
 
 
 def mean_cov(states):
@@ -284,18 +287,20 @@ def refine_bin(xy, cls, res, cx, cy, width, height, C_):
     return out
 
 
-def propagate(states, tx, ty, omega, scale_freeze, pos_cov, theta_cov, seed):
+def propagate(states, tx, ty, omega, scale_freeze, pos_cov, theta_cov, seed, discard=None):
     """StateParticle::propagate over a particle set with ONE shared mt19937(seed), in particle order
     (state_particle.cpp:57-78, particle_filter.cpp:86-92).  Returns (new states, last_dist, z) where z[n, 4] are the
-    standard normal variates behind the draws (theta, dx, dy, scale)."""
+    standard normal variates behind the draws (theta, dx, dy, scale).  With `discard` (the engine outputs earlier calls
+    consumed) the engine resumes there and the outputs consumed here are returned as a fourth value."""
     st = np.ascontiguousarray(states.copy())
     n = len(st)
     last = np.empty(n, dtype=np.float32)
     z = np.empty((n, 4), dtype=np.float32)
-    lib().orc_propagate(st.ctypes.data_as(C.c_void_p), _p(last, c_float_p), C.c_long(n), C.c_float(tx), C.c_float(ty),
-                        C.c_float(omega), int(bool(scale_freeze)), C.c_float(pos_cov), C.c_float(theta_cov),
-                        C.c_uint32(seed), _p(z, c_float_p))
-    return st, last, z
+    draws = C.c_uint64(0)
+    lib().orc_propagate_from(st.ctypes.data_as(C.c_void_p), _p(last, c_float_p), C.c_long(n), C.c_float(tx), C.c_float(ty),
+                             C.c_float(omega), int(bool(scale_freeze)), C.c_float(pos_cov), C.c_float(theta_cov),
+                             C.c_uint32(seed), C.c_uint64(discard or 0), _p(z, c_float_p), C.byref(draws))
+    return (st, last, z) if discard is None else (st, last, z, int(draws.value))
 
 
 def raster_polygons(polys, poly_class, map_w, map_h, rot, resolution, C_, exclusive):
@@ -340,3 +345,46 @@ def adaptive_count(covs, last_num_particles, max_num_particles):
     cv = np.ascontiguousarray(covs, dtype=np.float32).reshape(-1, 16)
     lib().orc_adaptive_count.restype = C.c_int
     return int(lib().orc_adaptive_count(_p(cv, c_float_p), len(cv), int(last_num_particles), int(max_num_particles)))
+
+
+class OrcInitParams(C.Structure):
+    _fields_ = [("init_pos_px_x", C.c_float), ("init_pos_px_y", C.c_float), ("init_pos_px_cov", C.c_float),
+                ("init_pos_m_x", C.c_float), ("init_pos_m_y", C.c_float), ("init_pos_deg_theta", C.c_float),
+                ("init_pos_deg_cov", C.c_float), ("fixed_scale", C.c_float)]
+
+
+def classes_at_point(layers, resolution, px, py):
+    """TopDownMap::getClassesAtPoint(Vector2i) (top_down_map.cpp:159-170) on distance layers (C, cols, rows)"""
+    L = np.ascontiguousarray(layers, dtype=np.float32)
+    C_, cols, rows = L.shape
+    lib().orc_classes_at_point.restype = C.c_uint
+    bits = lib().orc_classes_at_point(_p(L, c_float_p), rows, cols, C_, C.c_float(resolution), int(px), int(py))
+    return [c for c in range(C_) if bits >> c & 1]
+
+
+def init_particles(seed, layers, resolution, map_center, max_n, init_pos_px=(-1.0, -1.0), init_pos_px_cov=-1.0,
+                   init_pos_m=(math.inf, math.inf), init_pos_deg_theta=math.inf, init_pos_deg_cov=10.0, fixed_scale=-1.0):
+    """ParticleFilter::initializeParticles (particle_filter.cpp:19-84) from std::mt19937(seed) on distance layers
+    (C, cols, rows).  Returns (states, scale_frozen, (init_pos_px_x, init_pos_px_y) as the filter ends up with, the number
+    of engine outputs consumed — `discard` of the calls that continue on the filter's shared engine)."""
+    L = np.ascontiguousarray(layers, dtype=np.float32)
+    C_, cols, rows = L.shape
+    ip = OrcInitParams(init_pos_px[0], init_pos_px[1], init_pos_px_cov, init_pos_m[0], init_pos_m[1], init_pos_deg_theta,
+                       init_pos_deg_cov, fixed_scale)
+    out = np.zeros(max(int(max_n), 1), dtype=STATE_DTYPE)
+    frozen = C.c_int(0)
+    px = np.zeros(2, dtype=np.float32)
+    draws = C.c_uint64(0)
+    lib().orc_init_particles.restype = C.c_long
+    n = lib().orc_init_particles(C.c_uint32(seed), _p(L, c_float_p), rows, cols, C_, C.c_float(resolution), int(map_center[0]),
+                                 int(map_center[1]), C.byref(ip), int(max_n), out.ctypes.data_as(C.c_void_p), C.byref(frozen),
+                                 _p(px, c_float_p), C.byref(draws))
+    return out[:n].copy(), bool(frozen.value), (float(px[0]), float(px[1])), int(draws.value)
+
+
+def freeze_scale(states):
+    """ParticleFilter::freezeScale (particle_filter.cpp:343-357); returns (states with the common scale, that scale)"""
+    st = np.ascontiguousarray(states).copy()
+    lib().orc_freeze_scale.restype = C.c_float
+    g = lib().orc_freeze_scale(st.ctypes.data_as(C.c_void_p), C.c_long(len(st)))
+    return st, float(g)

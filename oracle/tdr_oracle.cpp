@@ -39,6 +39,18 @@
 
 namespace {
 
+// std::mt19937 that counts its 32-bit outputs, so that a later call can resume the reference's ONE shared engine
+// (particle_filter.cpp:5) where an earlier one left it: same min / max, hence the same values out of every distribution
+struct CountingMt {
+  using result_type = std::mt19937::result_type;
+  std::mt19937 g;
+  uint64_t n = 0;
+  explicit CountingMt(uint32_t seed, uint64_t discard = 0) : g(seed) { g.discard(discard); }
+  static constexpr result_type min() { return std::mt19937::min(); }
+  static constexpr result_type max() { return std::mt19937::max(); }
+  result_type operator()() { ++n; return g(); }
+};
+
 // x86-64 cvttss2si semantics: NaN / out-of-range -> INT_MIN ("integer indefinite").
 // The reference relies on this implicitly (float -> int assignments).
 inline int f2i_x86(float v) {
@@ -629,6 +641,12 @@ ORC_API float orc_uniform_draw(uint32_t seed) {
   std::uniform_real_distribution<float> shift_dist(0., 1.);
   return shift_dist(gen);
 }
+// the same draw from the shared engine after `discard` earlier outputs
+ORC_API float orc_uniform_draw_from(uint32_t seed, uint64_t discard) {
+  CountingMt gen(seed, discard);
+  std::uniform_real_distribution<float> shift_dist(0., 1.);
+  return shift_dist(gen);
+}
 
 // -----------------------------------------------------------------------------
 // a13  pose   src/state_particle.cpp:98-102, src/particle_filter.cpp:191-236
@@ -701,9 +719,17 @@ ORC_API void orc_refine_bin(const float* xy, const int* cls, long n, float res, 
 // z_out (may be NULL): the STANDARD normal variate behind every draw, 4 per particle (theta, dx, dy, scale; scale
 // = 0 when frozen), i.e. (draw - mean) / stddev as libstdc++ computes it before `* stddev + mean` — recovered by
 // running a second engine in lock step through N(0,1) objects, which consume the identical uniforms.
+// orc_propagate_from: the engine is std::mt19937(seed) after `discard` outputs (what earlier calls on the shared engine
+// consumed); draws_out (may be NULL) receives the outputs this call consumed.
+ORC_API void orc_propagate_from(OrcState* st, float* last_dist, long n, float tx, float ty, float omega, int scale_freeze,
+                                float pos_cov, float theta_cov, uint32_t seed, uint64_t discard, float* z_out, uint64_t* draws_out);
 ORC_API void orc_propagate(OrcState* st, float* last_dist, long n, float tx, float ty, float omega, int scale_freeze,
                            float pos_cov, float theta_cov, uint32_t seed, float* z_out) {
-  std::mt19937 gen(seed), gen_z(seed);
+  orc_propagate_from(st, last_dist, n, tx, ty, omega, scale_freeze, pos_cov, theta_cov, seed, 0, z_out, nullptr);
+}
+ORC_API void orc_propagate_from(OrcState* st, float* last_dist, long n, float tx, float ty, float omega, int scale_freeze,
+                                float pos_cov, float theta_cov, uint32_t seed, uint64_t discard, float* z_out, uint64_t* draws_out) {
+  CountingMt gen(seed, discard), gen_z(seed, discard);
   for (long i = 0; i < n; i++) {
     OrcState& s = st[i];
     const float c = std::cos(s.theta), sn = std::sin(s.theta);
@@ -728,6 +754,7 @@ ORC_API void orc_propagate(OrcState* st, float* last_dist, long n, float tx, flo
     const float z0 = zt(gen_z), z1 = zd(gen_z), z2 = zd(gen_z), z3 = scale_freeze ? 0.f : zs(gen_z);
     if (z_out) { z_out[4 * i] = z0; z_out[4 * i + 1] = z1; z_out[4 * i + 2] = z2; z_out[4 * i + 3] = z3; }
   }
+  if (draws_out) *draws_out = gen.n;
 }
 
 // -----------------------------------------------------------------------------
@@ -878,6 +905,108 @@ ORC_API int orc_adaptive_count(const float* covs, int n_cov, int last_num_partic
     num += static_cast<int>(std::sqrt(e0) * std::sqrt(e1));                 // :155 area of the covariance ellipse
   }
   return std::min(std::max(num, 3 * last_num_particles / 4 + 10), max_num_particles);   // :157
+}
+
+// -----------------------------------------------------------------------------
+// SURVEY 8f rank 4  particle initialisation   src/particle_filter.cpp:19-84 (initializeParticles),
+// src/state_particle.cpp:3-49 (the StateParticle constructor's rejection sampling), src/top_down_map.cpp:159-170
+// (getClassesAtPoint), and the small host-side pieces next to it: freezeScale (:343-357), the map-centre shift of
+// ParticleFilter::updateMap (:325-333)
+// -----------------------------------------------------------------------------
+struct OrcInitParams {      // the FilterParams fields the constructors read (state_particle.h:19-38)
+  float init_pos_px_x, init_pos_px_y, init_pos_px_cov;
+  float init_pos_m_x, init_pos_m_y, init_pos_deg_theta, init_pos_deg_cov;
+  float fixed_scale;
+};
+
+// TopDownMap::getClassesAtPoint(Vector2i) :159-170 on the DISTANCE layers (class present <=> layer < 1); returns a bit set
+ORC_API unsigned orc_classes_at_point(const float* layers, int rows, int cols, int C, float resolution, int px, int py) {
+  const int cx = f2i_x86((float)px / resolution), cy = f2i_x86((float)py / resolution);   // cast<float>() / res, cast<int>()
+  unsigned bits = 0;
+  for (int cls = 0; cls < C; cls++)
+    if (cx < cols && cy < rows && cx >= 0 && cy >= 0 && layers[(size_t)cls * rows * cols + (size_t)cx * rows + cy] < 1) bits |= 1u << cls;
+  return bits;
+}
+
+namespace {
+// StateParticle::StateParticle(gen, map, params, init = true)   state_particle.cpp:3-49
+OrcState construct_particle(CountingMt& gen, const float* layers, int rows, int cols, int C, float resolution, const OrcInitParams& p) {
+  std::uniform_real_distribution<float> uniform_dist(0., 1.);                  // :7
+  std::normal_distribution<float> normal_dist(0., 1.);                         // :8
+  const float map_w = (float)cols * resolution, map_h = (float)rows * resolution;   // :11 size() = (cols, rows)
+  OrcState s{};
+  if (p.fixed_scale < 0) s.scale = (float)std::pow(10, (uniform_dist(gen) - 0.5) * 2);   // :14-15
+  else s.scale = p.fixed_scale;
+  while (true) {                                                               // :20-32
+    if (p.init_pos_px_x > 0) {
+      s.init_x_px = std::clamp<float>(normal_dist(gen) * p.init_pos_px_cov + p.init_pos_px_x, 0, map_w);
+      s.init_y_px = std::clamp<float>(normal_dist(gen) * p.init_pos_px_cov + p.init_pos_px_y, 0, map_h);
+    } else {
+      s.init_x_px = uniform_dist(gen) * map_w;
+      s.init_y_px = uniform_dist(gen) * map_h;
+    }
+    // Eigen::Vector2i(float, float): the coordinates are truncated
+    if (orc_classes_at_point(layers, rows, cols, C, resolution, f2i_x86(s.init_x_px), f2i_x86(s.init_y_px)) & 2u) break;   // class 1 = road
+  }
+  if (p.init_pos_deg_theta != std::numeric_limits<float>::infinity()) {        // :34-42
+    s.theta = normal_dist(gen) * p.init_pos_deg_cov + p.init_pos_deg_theta;
+    s.theta *= M_PI / 180;                                                     // float *= double
+    s.have_init = 1;
+  } else {
+    s.theta = 0;
+    s.have_init = 0;
+  }
+  return s;
+}
+}  // namespace
+
+// ParticleFilter::initializeParticles :19-84.  Returns the number of particles written to `out` (capacity >= max_n):
+// 0 when the metric initial position lies off the map or has no road within 4 px (:31-53).  px_out (may be NULL): the
+// init_pos_px_x / y the filter ends up with (overwritten from the metric position at :28-29).  Every loop pass
+// constructs THREE particles from the shared engine — proto_part per outer pass, `particle` and the new_particles_
+// twin per inner pass — and with a free scale the first of ten copies of proto_part's state survives.
+ORC_API long orc_init_particles(uint32_t seed, const float* layers, int rows, int cols, int C, float resolution, int map_center_x,
+                                int map_center_y, const OrcInitParams* params, int max_n, OrcState* out, int* scale_frozen_out,
+                                float* px_out, uint64_t* draws_out) {
+  CountingMt gen(seed);
+  if (draws_out) *draws_out = 0;
+  OrcInitParams p = *params;
+  size_t num_at_scale = 1;
+  bool scale_frozen = false;
+  if (p.fixed_scale < 0) num_at_scale = 10; else scale_frozen = true;          // :20-25
+  if (scale_frozen_out) *scale_frozen_out = scale_frozen;
+  if (scale_frozen && p.init_pos_m_x != std::numeric_limits<float>::infinity()) {   // :27-54
+    p.init_pos_px_x = (p.init_pos_m_x * p.fixed_scale) + map_center_x;
+    p.init_pos_px_y = (p.init_pos_m_y * p.fixed_scale) + map_center_y;
+    if (px_out) { px_out[0] = p.init_pos_px_x; px_out[1] = p.init_pos_px_y; }
+    if (p.init_pos_px_x < 0 || p.init_pos_px_x >= cols || p.init_pos_px_y < 0 || p.init_pos_px_y >= rows) return 0;
+    bool good_init = false;
+    for (int dx = -4; dx <= 4; dx++)
+      for (int dy = -4; dy <= 4; dy++)
+        if (orc_classes_at_point(layers, rows, cols, C, resolution, f2i_x86(p.init_pos_px_x + dx), f2i_x86(p.init_pos_px_y + dy)) & 2u)
+          good_init = true;
+    if (!good_init) return 0;
+  } else if (px_out) { px_out[0] = p.init_pos_px_x; px_out[1] = p.init_pos_px_y; }
+  long n = 0;
+  for (int i = 0; (size_t)i < (size_t)max_n / num_at_scale; i++) {             // :58 (int < size_t comparison)
+    const OrcState proto = construct_particle(gen, layers, rows, cols, C, resolution, p);
+    for (float scale = 0; scale < 1; scale += 1. / num_at_scale) {             // :60 float += double
+      OrcState part = construct_particle(gen, layers, rows, cols, C, resolution, p);
+      if (p.fixed_scale < 0) { part = proto; part.scale = std::pow(10., scale); }   // :62-65
+      out[n++] = part;
+      (void)construct_particle(gen, layers, rows, cols, C, resolution, p);     // :69 the new_particles_ twin
+    }
+  }
+  if (draws_out) *draws_out = gen.n;                                           // engine outputs consumed (to resume it later)
+  return n;
+}
+
+// ParticleFilter::freezeScale :343-357: geometric mean through a float accumulator and a double pow per particle
+ORC_API float orc_freeze_scale(OrcState* st, long n) {
+  float geo_mean = 1;
+  for (long i = 0; i < n; i++) geo_mean *= std::pow(st[i].scale, 1. / (size_t)n);
+  for (long i = 0; i < n; i++) st[i].scale = geo_mean;
+  return geo_mean;
 }
 
 ORC_API int orc_abi_version() { return 1; }

@@ -4,6 +4,7 @@
 // can check them against the oracle.
 #include <fstream>
 #include <iostream>
+#include <limits>
 
 #include "../../top_down_renderer_b200/host/tdr_host.hpp"
 
@@ -53,6 +54,7 @@ int main(int argc, char** argv) {
   FilterParams fp; fp.regularization = 0.7f; fp.pos_cov = 0.15f; fp.theta_cov = 0.004f; fp.fixed_scale = 2.0f;
   fp.init_pos_px_x = fmeta[1]; fp.init_pos_px_y = fmeta[2]; fp.init_pos_px_cov = fmeta[3];
   fp.init_pos_deg_theta = fmeta[4]; fp.init_pos_deg_cov = fmeta[5];
+  fp.init_pos_m_x = fp.init_pos_m_y = std::numeric_limits<float>::infinity();   // "unset", as the node passes it (top_down_render.cpp:214-222)
   fp.class_weights.assign(C, 1.f);
   ParticleFilter filter(N, &map, fp, (uint32_t)seed);
   Vector2f trans; trans.x = 0.4f; trans.y = 0.05f;
@@ -81,6 +83,36 @@ int main(int argc, char** argv) {
   Vector2f gc; gc.x = W * 0.5f; gc.y = H * 0.5f;
   map.getLocalGeoMap(gc, 2.0f, geo_local);
   wr(dir + "geo_local0.f32", geo_local[0].data(), (size_t)n_theta * n_r);
+  // ---- the rest of the ParticleFilter interface (particle_filter.h:22-41); the first filter is not touched again ----
+  const float sc_fixed = filter.scale();                                       // fixed scale: the parameter
+  // (a) ParticleFilter::updateMap: a new aerial map whose centre moved by (+3, -2) px shifts every init position
+  Vector2i c2; c2.x = W / 2 + 3; c2.y = H / 2 - 2;
+  ParticleFilter shifted(64, &map, fp, (uint32_t)seed + 1);
+  shifted.updateMap(img.data(), H, W, W, Vector2i{W / 2, H / 2});               // first map message: delta from (0, 0)
+  wr(dir + "shift_before.bin", shifted.states().data(), shifted.states().size());
+  shifted.updateMap(img.data(), H, W, W, c2);
+  wr(dir + "shift_after.bin", shifted.states().data(), shifted.states().size());
+  // (b) free scale: ten scales per prototype, scale() = -1 until freezeScale locks the geometric mean
+  FilterParams ff = fp; ff.fixed_scale = -1; ff.init_pos_px_x = ff.init_pos_px_y = -1;
+  ff.init_pos_deg_theta = std::numeric_limits<float>::infinity();
+  ParticleFilter free_scale(120, &map, ff, (uint32_t)seed + 2);
+  const float sc_free = free_scale.scale();
+  wr(dir + "free_before.bin", free_scale.states().data(), free_scale.states().size());
+  Vector2f t2; t2.x = 0.3f; t2.y = -0.1f;
+  free_scale.propagate(t2, -0.02f);                                            // scale jitter: four variates per particle
+  wr(dir + "free_propagated.bin", free_scale.states().data(), free_scale.states().size());
+  free_scale.freezeScale();
+  wr(dir + "free_frozen.bin", free_scale.states().data(), free_scale.states().size());
+  const float sc_frozen = free_scale.scale();
+  // (c) a metric initial position relative to the map centre (particle_filter.cpp:27-54), on the road and off the map
+  FilterParams fm = fp; fm.init_pos_px_x = fm.init_pos_px_y = -1;
+  fm.init_pos_m_x = (fmeta[1] - c2.x) / fp.fixed_scale; fm.init_pos_m_y = (fmeta[2] - c2.y) / fp.fixed_scale;
+  ParticleFilter metric(48, &map, fm, (uint32_t)seed + 3);
+  wr(dir + "metric_states.bin", metric.states().data(), metric.states().size());
+  FilterParams fo = fm; fo.init_pos_m_x = 1e6f;
+  ParticleFilter off_map(48, &map, fo, (uint32_t)seed + 4);
+  const float misc[5] = {sc_fixed, sc_free, sc_frozen, (float)metric.numParticles(), (float)off_map.numParticles()};
+  wr(dir + "misc.f32", misc, 5);
   std::cout << "host_demo ok: " << filter.numParticles() << " particles, mean (" << mean[0] << ", " << mean[1] << ", " << mean[2] << ")\n";
   return 0;
 }

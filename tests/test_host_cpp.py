@@ -1,6 +1,9 @@
 """The C++ host mirror of the reference's class interfaces (top_down_renderer_b200/host/tdr_host.hpp):
-it compiles and links against the C ABI on the CPU box, and on a GPU one scan step driven through
-ScanRendererPolar / TopDownMapPolar / ParticleFilter agrees with the oracle."""
+it compiles and links against the C ABI on the CPU box (and refuses to run there), and on a GPU one scan step driven
+through ScanRendererPolar / TopDownMapPolar / ParticleFilter agrees with the oracle.  The same demo linked against a
+CPU stand-in of the C ABI that answers every call with the oracle (tests/cpp/tdr_cpu_standin.cpp, test code only) puts
+the mirror's HOST logic — RNG streams, map-centre shift, freezeScale, cache files — under the CPU suite and proves the
+checks below on a run the oracle produced."""
 import math
 import os
 import subprocess
@@ -26,6 +29,20 @@ def build_demo():
     return DEMO
 
 
+DEMO_CPU = os.path.join(ROOT, "tests", "cpp", "host_demo_cpu")
+
+
+def build_demo_cpu():
+    """host_demo.cpp + the CPU stand-in of the C ABI + liboracle.so: no CUDA anywhere in this binary"""
+    so = orc.build()
+    srcs = [os.path.join(ROOT, "tests", "cpp", f) for f in ("host_demo.cpp", "tdr_cpu_standin.cpp")]
+    deps = srcs + [os.path.join(ROOT, "top_down_renderer_b200", "host", "tdr_host.hpp"), os.path.join(ROOT, "include", "tdr.h"), so]
+    if not os.path.exists(DEMO_CPU) or os.path.getmtime(DEMO_CPU) < max(os.path.getmtime(f) for f in deps):
+        subprocess.check_call(["g++", "-O2", "-std=c++17", "-Wall", "-o", DEMO_CPU] + srcs +
+                              ["-L", os.path.dirname(so), "-l:" + os.path.basename(so), "-Wl,-rpath," + os.path.dirname(so), "-pthread"])
+    return DEMO_CPU
+
+
 def write_inputs(d, N=800, seed=5):
     C, H, W = 4, 400, 480
     cm = synth.make_class_map(H, W, C, seed=seed)
@@ -49,6 +66,147 @@ def test_host_mirror_compiles_and_refuses_to_run_without_gpu(tmp_path):
     assert r.returncode == 3 and "no CPU fallback" in r.stderr
 
 
+def rd(d, name, dtype):
+    return np.fromfile(os.path.join(d, name), dtype=dtype)
+
+
+def same_bits(a, b):
+    return a.shape == b.shape and np.array_equal(a.view(np.uint32), b.view(np.uint32))
+
+
+def check_demo_outputs(d, cm, img, pts, N, seed, device):
+    """what host_demo wrote against the oracle.  device=True: the run came from libtdr_b200 (weights within 1e-5,
+    propagate bit-exact against the numpy twin that forms cos / sin like the kernel); False: from the CPU stand-in, where
+    every number is the oracle's own and everything is bit-exact."""
+    from oracle import numpy_twin as twin
+    from top_down_renderer_b200 import eigcache
+    C, H, W = 4, cm.shape[0], cm.shape[1]
+    lut = synth.identity_lut(C)
+    ang = np.float32(2 * math.pi / 100)
+    fmeta = rd(d, "meta.f32", np.float32)
+    # class images: bit-exact
+    scan_o = orc.render_polar(pts, 2.0, ang, 100, 25, lut, C)
+    scan = np.stack([rd(d, f"scan_{c}.f32", np.float32).reshape(25, 100) for c in range(C)])
+    assert np.array_equal(scan, scan_o)
+    layers, mask = orc.compute_dists(orc.class_image_to_layers(img, lut, C, 1.0), 1.0)
+    tab = orc.polar_table(100, 25, ang, 1.0)
+
+    # ---- initializeParticles + propagate: the reference's own RNG calls on ONE engine (particle_filter.cpp:19-92) ----
+    init_kw = dict(init_pos_px=(float(fmeta[1]), float(fmeta[2])), init_pos_px_cov=float(fmeta[3]), init_pos_deg_theta=float(fmeta[4]),
+                   init_pos_deg_cov=float(fmeta[5]), fixed_scale=2.0)
+    init, frozen, _, used = orc.init_particles(seed, layers, 1.0, (W // 2, H // 2), N, **init_kw)
+    assert len(init) == N and frozen and (init["have_init"] == 1).all() and (init["scale"] == 2.0).all()
+    want, last_o, z, used_p = orc.propagate(init, 0.4, 0.05, 0.01, True, 0.15, 0.004, seed, discard=used)
+    st = rd(d, "states_before.bin", synth.STATE_DTYPE)
+    ld = rd(d, "last_dist.f32", np.float32)
+    assert len(st) == N
+    for k in ("init_x_px", "init_y_px", "scale"):                 # untouched by propagate: the rejection sampler's output
+        assert same_bits(st[k], init[k]), k
+    assert np.array_equal(st["have_init"], init["have_init"])
+    ref, last_r = (twin.propagate_with_z(init, 0.4, 0.05, 0.01, True, 0.15, 0.004, z) if device else (want, last_o))
+    for k in ("dx_m", "dy_m", "theta"):
+        assert same_bits(st[k], ref[k]), k
+    assert same_bits(ld, last_r)
+    assert np.abs(st["dx_m"] - want["dx_m"]).max() <= 1e-6 and np.abs(st["dy_m"] - want["dy_m"]).max() <= 1e-6
+    # getClassesAtPoint tests the DISTANCE layer (< 1, top_down_map.cpp:166), and unknown pixels have every layer
+    # zeroed (:317), so the reference also accepts unknown pixels as "on the road" — mirrored, not fixed
+    at = cm[st["init_y_px"].astype(int), st["init_x_px"].astype(int)]
+    assert np.isin(at, [synth.ROAD, synth.UNKNOWN]).all() and (at == synth.ROAD).mean() > 0.5
+    assert (ld > 0).all()
+    # the ONE uniform of update (:172-173) is the engine's next output
+    u = float(rd(d, "u.f32", np.float32)[0])
+    assert u == orc.uniform_draw(seed, discard=used + used_p)
+
+    # ---- update: weights within 1e-5 of the oracle's on the same particle set, resampled states consistent ----
+    thetas, shifts = orc.search_list(100)
+    fp = orc.make_params(C, regularization=0.7, map_width=W, map_height=H)
+    w = orc.score_all(st.copy(), fp, layers, mask, 1.0, tab, 100, 25, scan_o, 2.0, thetas, shifts)
+    wn, arg, _ = orc.normalize(w, ld)
+    got = rd(d, "weights_norm.f32", np.float32)
+    assert np.max(np.abs(got - wn) / wn) <= 1e-5
+    if not device:
+        assert same_bits(got, wn)
+    after = rd(d, "states_after.bin", synth.STATE_DTYPE)
+    idx = orc.resample_fast(got, u, len(st))                 # stage-wise: the run's own normalised weights
+    assert np.array_equal(after, st[idx])
+    mean = rd(d, "mean.f32", np.float32)
+    wm, _ = orc.mean_cov(after)
+    assert abs(mean[0] - wm[0]) <= 0.002 and abs(mean[1] - wm[1]) <= 0.002 and abs(mean[2] - wm[2]) <= math.radians(0.01)
+    ml = rd(d, "ml.f32", np.float32)
+    s_ml = st[int(np.argmax(got))]                           # maxCoeff: the first maximum of the run's own weights
+    want_ml = np.float32([s_ml["dx_m"] * s_ml["scale"] + s_ml["init_x_px"], s_ml["dy_m"] * s_ml["scale"] + s_ml["init_y_px"],
+                          s_ml["theta"], s_ml["scale"]])
+    assert np.abs(ml - want_ml).max() <= 1e-3
+
+    # ---- the map cache the C++ mirror wrote in the reference's .eig format (and then ran the filter from): read back
+    # with the independent Python reader — distance fields and mask to the bit, geo layers like the oracle's ----
+    assert eigcache.cache_is_valid(d, "demo_map", C, 1.0) and not eigcache.cache_is_valid(d, "demo_map", C + 1, 1.0)
+    c_layers, c_geo, c_mask = eigcache.load_cache(d, C)
+    assert same_bits(c_layers, layers) and np.array_equal(c_mask, mask)
+    geo_o = orc.geo_raster(orc.class_image_to_layers(img, lut, C, 1.0))
+    geo_d, _ = orc.compute_dists(geo_o, 1.0)
+    assert same_bits(c_geo, geo_d)
+
+    # ---- ActiveLocalizer::getBestRelPos and getLocalGeoMap through the mirror classes ----
+    preds = np.float32([[W * 0.3, H * 0.4, 0.2], [W * 0.6, H * 0.5, -1.1], [W * 0.5, H * 0.7, 2.4]])
+    rel_o, _ = orc.active_best_rel_pos(layers, mask, 1.0, tab.reshape(-1), 100, 25, preds)
+    rel = rd(d, "active_rel.f32", np.float32)
+    assert (float(rel[0]), float(rel[1])) == rel_o and rel_o[0] >= 50
+    g0 = rd(d, "geo_local0.f32", np.float32)
+    want_g, _ = orc.local_map_polar(geo_d, np.zeros_like(mask), 1.0, tab, np.float32(W * 0.5), np.float32(H * 0.5), 1.0, 2.0)
+    assert same_bits(g0, want_g[0])
+
+    # ---- the rest of the ParticleFilter interface: pure host logic over the resident states ----
+    sc_fixed, sc_free, sc_frozen, n_metric, n_off = (float(v) for v in rd(d, "misc.f32", np.float32))
+    assert sc_fixed == 2.0 and sc_free == -1.0                                  # scale(): particle_filter.cpp:358-366
+    # (a) updateMap: every init position moves by the map-centre delta (:325-333) — (W/2, H/2) from the initial (0, 0)
+    # on the first map message, then (+3, -2); float += int
+    sh0, _, _, _ = orc.init_particles(seed + 1, layers, 1.0, (W // 2, H // 2), 64, **init_kw)
+    b, a = rd(d, "shift_before.bin", synth.STATE_DTYPE), rd(d, "shift_after.bin", synth.STATE_DTYPE)
+    f = np.float32
+    assert same_bits(b["init_x_px"], sh0["init_x_px"] + f(W // 2)) and same_bits(b["init_y_px"], sh0["init_y_px"] + f(H // 2))
+    assert same_bits(a["init_x_px"], b["init_x_px"] + f(3)) and same_bits(a["init_y_px"], b["init_y_px"] + f(-2))
+    for k in ("dx_m", "dy_m", "theta", "scale"):
+        assert same_bits(a[k], sh0[k]), k
+    # (b) free scale: 12 prototypes x 10 scales 10^(0, 0.1, ...), no heading; propagate jitters the scale; freezeScale
+    # locks the geometric mean (float accumulator over double pow, :343-357)
+    fr0, frozen_f, _, used_f = orc.init_particles(seed + 2, layers, 1.0, (W // 2 + 3, H // 2 - 2), 120, fixed_scale=-1.0)
+    fb = rd(d, "free_before.bin", synth.STATE_DTYPE)
+    assert not frozen_f and len(fr0) == 120 and np.array_equal(fb, fr0)
+    assert (fb["have_init"] == 0).all() and np.allclose(fb["scale"][:10], 10.0 ** (np.arange(10) / 10), rtol=1e-6)
+    assert (fb["init_x_px"].reshape(12, 10) == fb["init_x_px"].reshape(12, 10)[:, :1]).all()   # ten scales per prototype
+    fw, _, zf, _ = orc.propagate(fr0, 0.3, -0.1, -0.02, False, 0.15, 0.004, seed + 2, discard=used_f)
+    fpg = rd(d, "free_propagated.bin", synth.STATE_DTYPE)
+    fref = twin.propagate_with_z(fr0, 0.3, -0.1, -0.02, False, 0.15, 0.004, zf)[0] if device else fw
+    for k in ("dx_m", "dy_m", "theta", "scale"):
+        assert same_bits(fpg[k], fref[k]), k
+    assert not np.array_equal(fpg["scale"], fr0["scale"])
+    fz, g = orc.freeze_scale(fpg)
+    ffz = rd(d, "free_frozen.bin", synth.STATE_DTYPE)
+    assert np.array_equal(ffz, fz) and sc_frozen == g and abs(g - np.exp(np.log(fpg["scale"].astype(np.float64)).mean())) < 1e-4 * g
+    # (c) a metric initial position relative to the map centre (:27-54); off the map the filter stays empty
+    mc = (W // 2 + 3, H // 2 - 2)
+    m_xy = ((fmeta[1] - f(mc[0])) / f(2.0), (fmeta[2] - f(mc[1])) / f(2.0))
+    kw = dict(init_kw); kw["init_pos_px"] = (-1.0, -1.0)
+    ms, _, px, _ = orc.init_particles(seed + 3, layers, 1.0, mc, 48, init_pos_m=(float(m_xy[0]), float(m_xy[1])), **kw)
+    got_m = rd(d, "metric_states.bin", synth.STATE_DTYPE)
+    assert n_metric == 48 and np.array_equal(got_m, ms) and abs(px[0] - fmeta[1]) < 1e-3 and abs(px[1] - fmeta[2]) < 1e-3
+    assert np.hypot(got_m["init_x_px"] - fmeta[1], got_m["init_y_px"] - fmeta[2]).max() < 6 * fmeta[3]
+    assert n_off == 0
+
+
+def test_host_mirror_logic_on_the_cpu_standin(tmp_path):
+    """every class of the host mirror driven end to end with the oracle answering the C ABI: the mirror's own code (RNG
+    call order, state bookkeeping, file formats) must reproduce the oracle's restatement of the reference bit for bit"""
+    demo = build_demo_cpu()
+    d = str(tmp_path)
+    cm, img, pts = write_inputs(d)
+    r = subprocess.run([demo, d], capture_output=True, text=True, timeout=300)
+    assert r.returncode == 0, r.stdout + r.stderr
+    assert "No map received for input loc" in r.stderr            # the off-map filter said why it stayed empty
+    check_demo_outputs(d, cm, img, pts, 800, 5, device=False)
+
+
 @pytest.mark.gpu
 def test_host_mirror_step_matches_oracle(tmp_path):
     demo = build_demo()
@@ -56,52 +214,4 @@ def test_host_mirror_step_matches_oracle(tmp_path):
     cm, img, pts = write_inputs(d)
     r = subprocess.run([demo, d], capture_output=True, text=True, timeout=120)
     assert r.returncode == 0, r.stdout + r.stderr
-    C, H, W = 4, cm.shape[0], cm.shape[1]
-    lut = synth.identity_lut(C)
-    ang = np.float32(2 * math.pi / 100)
-    # class images: bit-exact
-    scan_o = orc.render_polar(pts, 2.0, ang, 100, 25, lut, C)
-    scan = np.stack([np.fromfile(os.path.join(d, f"scan_{c}.f32"), dtype=np.float32).reshape(25, 100) for c in range(C)])
-    assert np.array_equal(scan, scan_o)
-    # particles: initialised on road pixels (state_particle.cpp:20-32), heading known
-    st = np.fromfile(os.path.join(d, "states_before.bin"), dtype=synth.STATE_DTYPE)
-    ld = np.fromfile(os.path.join(d, "last_dist.f32"), dtype=np.float32)
-    assert len(st) == 800 and (st["have_init"] == 1).all() and (st["scale"] == 2.0).all()
-    # getClassesAtPoint tests the DISTANCE layer (< 1, top_down_map.cpp:166), and unknown pixels have every layer
-    # zeroed (:317), so the reference also accepts unknown pixels as "on the road" — mirrored, not fixed
-    at = cm[st["init_y_px"].astype(int), st["init_x_px"].astype(int)]
-    assert np.isin(at, [synth.ROAD, synth.UNKNOWN]).all() and (at == synth.ROAD).mean() > 0.5
-    assert (ld > 0).all()
-    # update: weights within 1e-5 of the oracle's on the same particle set, resampled states consistent
-    layers, mask = orc.compute_dists(orc.class_image_to_layers(img, lut, C, 1.0), 1.0)
-    tab = orc.polar_table(100, 25, ang, 1.0)
-    thetas, shifts = orc.search_list(100)
-    fp = orc.make_params(C, regularization=0.7, map_width=W, map_height=H)
-    w = orc.score_all(st.copy(), fp, layers, mask, 1.0, tab, 100, 25, scan_o, 2.0, thetas, shifts)
-    wn, arg, _ = orc.normalize(w, ld)
-    got = np.fromfile(os.path.join(d, "weights_norm.f32"), dtype=np.float32)
-    assert np.max(np.abs(got - wn) / wn) <= 1e-5
-    # the map cache the C++ mirror wrote in the reference's .eig format (and then ran the filter from): read back with
-    # the independent Python reader — distance fields and mask to the bit, geo layers like the oracle's
-    from top_down_renderer_b200 import eigcache
-    assert eigcache.cache_is_valid(d, "demo_map", C, 1.0) and not eigcache.cache_is_valid(d, "demo_map", C + 1, 1.0)
-    c_layers, c_geo, c_mask = eigcache.load_cache(d, C)
-    assert np.array_equal(c_layers.view(np.uint32), layers.view(np.uint32)) and np.array_equal(c_mask, mask)
-    geo_o = orc.geo_raster(orc.class_image_to_layers(img, lut, C, 1.0))
-    geo_d, _ = orc.compute_dists(geo_o, 1.0)
-    assert np.array_equal(c_geo.view(np.uint32), geo_d.view(np.uint32))
-    u = float(np.fromfile(os.path.join(d, "u.f32"), dtype=np.float32)[0])
-    after = np.fromfile(os.path.join(d, "states_after.bin"), dtype=synth.STATE_DTYPE)
-    idx = orc.resample_fast(got, u, len(st))                 # stage-wise: the device's own normalised weights
-    assert np.array_equal(after, st[idx])
-    # ActiveLocalizer::getBestRelPos and getLocalGeoMap through the mirror classes
-    preds = np.float32([[W * 0.3, H * 0.4, 0.2], [W * 0.6, H * 0.5, -1.1], [W * 0.5, H * 0.7, 2.4]])
-    rel_o, _ = orc.active_best_rel_pos(layers, mask, 1.0, tab.reshape(-1), 100, 25, preds)
-    rel = np.fromfile(os.path.join(d, "active_rel.f32"), dtype=np.float32)
-    assert (float(rel[0]), float(rel[1])) == rel_o and rel_o[0] >= 50
-    g0 = np.fromfile(os.path.join(d, "geo_local0.f32"), dtype=np.float32)
-    want_g, _ = orc.local_map_polar(geo_d, np.zeros_like(mask), 1.0, tab, np.float32(W * 0.5), np.float32(H * 0.5), 1.0, 2.0)
-    assert np.array_equal(g0.view(np.uint32), want_g[0].view(np.uint32))
-    mean = np.fromfile(os.path.join(d, "mean.f32"), dtype=np.float32)
-    wm, _ = orc.mean_cov(after)
-    assert abs(mean[0] - wm[0]) <= 0.002 and abs(mean[1] - wm[1]) <= 0.002 and abs(mean[2] - wm[2]) <= math.radians(0.01)
+    check_demo_outputs(d, cm, img, pts, 800, 5, device=True)

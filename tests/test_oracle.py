@@ -433,3 +433,65 @@ def test_active_localizer_equals_numpy_twin(small_world):
         (d_o, t_o), best_o = orc.active_best_rel_pos(w["layers"], w["mask"], 1.0, w["tab"], 100, 25, preds)
         (d_t, t_t), best_t = twin.active_best_rel_pos(w["layers"], w["mask"], 1.0, w["tab"], 100, 25, preds)
         assert (d_o, t_o) == (d_t, t_t) and abs(best_o - best_t) <= 1e-5 * best_t
+
+
+# ---- particle initialisation (rejection sampling on the shared engine), freezeScale -------------------
+def _states_of(parts):
+    st = np.zeros(len(parts), dtype=synth.STATE_DTYPE)
+    for i, (x, y, th, sc, hi) in enumerate(parts):
+        st[i]["init_x_px"], st[i]["init_y_px"], st[i]["theta"], st[i]["scale"], st[i]["have_init"] = x, y, th, sc, hi
+    return st
+
+
+@pytest.mark.parametrize("case", ["uniform_free_scale", "gaussian_fixed_scale", "metric_position"])
+def test_init_particles_equals_libstdcxx_free_twin(small_world, case):
+    """the C++ restatement (libstdc++'s own engine and distributions, the reference's calls) against a twin that has no
+    libstdc++ in it — numpy's Mersenne twister, generate_canonical and the polar method written out: same states to the
+    bit, same number of engine outputs consumed (the rejection loop runs the same number of times)"""
+    layers = small_world["layers"]
+    cols, rows = layers.shape[1], layers.shape[2]
+    road = np.argwhere((layers[1] < 1) & (small_world["mask"] == 0))
+    cx, cy = (float(v) + 0.5 for v in road[len(road) // 2])
+    mc = (cols // 2, rows // 2)
+    kw = {"uniform_free_scale": dict(fixed_scale=-1.0),
+          "gaussian_fixed_scale": dict(fixed_scale=2.0, init_pos_px=(cx, cy), init_pos_px_cov=7.5, init_pos_deg_theta=-140.0, init_pos_deg_cov=12.0),
+          "metric_position": dict(fixed_scale=2.0, init_pos_m=((cx - mc[0]) / 2.0, (cy - mc[1]) / 2.0), init_pos_px_cov=4.0)}[case]
+    n = 60 if case == "uniform_free_scale" else 45
+    got, frozen, px, used = orc.init_particles(99, layers, 1.0, mc, n, **kw)
+    parts, used_t = twin.init_particles(99, layers, 1.0, mc, n, **kw)
+    assert len(got) == n and frozen == (case != "uniform_free_scale")
+    assert np.array_equal(got, _states_of(parts)) and used == used_t
+    assert used >= 3 * n * (2 if case != "uniform_free_scale" else 3) / (10 if case == "uniform_free_scale" else 1)
+    # every particle sits on a pixel the reference accepts: class 1 present in the DISTANCE layer (road or unknown)
+    assert all(1 in orc.classes_at_point(layers, 1.0, int(s["init_x_px"]), int(s["init_y_px"])) for s in got)
+    if case == "metric_position":
+        assert abs(px[0] - cx) < 1e-3 and abs(px[1] - cy) < 1e-3
+    if case == "uniform_free_scale":
+        assert np.allclose(got["scale"][:10], 10.0 ** (np.arange(10) / 10), rtol=1e-6) and (got["have_init"] == 0).all()
+    # the engine resumes where initialisation left it: update's uniform is output `used` of the same stream
+    eng = twin.LibstdcxxEngine(99)
+    for _ in range(used):
+        eng.canonical()
+    assert orc.uniform_draw(99, discard=used) == float(eng.canonical())
+
+
+def test_init_particles_metric_position_off_map_or_off_road_leaves_the_filter_empty(small_world):
+    layers = small_world["layers"]
+    cols, rows = layers.shape[1], layers.shape[2]
+    st, frozen, px, used = orc.init_particles(1, layers, 1.0, (cols // 2, rows // 2), 20, fixed_scale=2.0, init_pos_m=(1e5, 0.0))
+    assert len(st) == 0 and frozen and used == 0 and px[0] > cols
+    bare = np.ones_like(layers)                       # no class anywhere within 4 px of the requested position
+    st, _, _, used = orc.init_particles(1, bare, 1.0, (cols // 2, rows // 2), 20, fixed_scale=2.0, init_pos_m=(0.0, 0.0))
+    assert len(st) == 0 and used == 0
+    assert twin.init_particles(1, bare, 1.0, (cols // 2, rows // 2), 20, fixed_scale=2.0, init_pos_m=(0.0, 0.0)) == ([], 0)
+
+
+def test_freeze_scale_known_answer():
+    st = np.zeros(4, dtype=synth.STATE_DTYPE)
+    st["scale"] = [1.0, 2.0, 4.0, 8.0]
+    out, g = orc.freeze_scale(st)
+    assert abs(g - 8.0 ** 0.5) < 1e-6 and (out["scale"] == np.float32(g)).all()
+    f = np.float32(1)
+    for s in st["scale"]:
+        f = np.float32(float(f) * math.pow(float(s), 1.0 / 4))      # float accumulator, double pow
+    assert np.float32(g) == f

@@ -57,7 +57,7 @@ using State = tdr_state;   // state_particle.h:9-17, identical layout
 struct FilterParams {
   float pos_cov = 0.3f, theta_cov = 0.0314f, regularization = 0.15f;
   float init_pos_px_x = -1, init_pos_px_y = -1, init_pos_px_cov = -1;
-  float init_pos_m_x = -1, init_pos_m_y = -1, init_pos_deg_theta = -1, init_pos_deg_cov = -1;
+  float init_pos_m_x = -1, init_pos_m_y = -1, init_pos_deg_theta = -1, init_pos_deg_cov = -1;   // the node passes +inf for "unset" (top_down_render.cpp:214-231)
   bool force_on_map = false;
   float fixed_scale = -1, scale_log_min = -0.1f, scale_log_max = 1;
   std::vector<float> class_weights;
@@ -123,13 +123,16 @@ class TopDownMapPolar {
     rows_ = r; cols_ = c;
     layers_.resize((size_t)k * r * c); mask_.resize((size_t)r * c);
     ok(tdr_map_get_layers(ctx(), layers_.data(), mask_.data()));           // host mirror for getClassesAtPoint
-    // have_map_ unless layer 1 is entirely zero (the isZero(0) quirk, :150)
-    have_map_ = true;
-    if (k > 1) {
-      bool all_zero = true;
-      for (size_t i = 0; i < (size_t)r * c && all_zero; i++) all_zero = layers_[(size_t)r * c + i] == 0.f;
-      have_map_ = !all_zero;
-    }
+    // have_map_ is set (and stays set) unless the BINARY layer 1 is entirely zero, i.e. every cell is road — the
+    // isZero(0) test of :150 runs before computeDists; cells sample the image as loadCompressedRasterMap does (:137-138)
+    bool all_road = k > 1;
+    for (int xi = 0; xi < c && all_road; xi++)
+      for (int yi = 0; yi < r && all_road; yi++) {
+        const int ir = std::max<int>((int)((float)rows - (float)yi * params_.resolution - 1), 0);
+        const int ic = std::min<int>((int)((float)xi * params_.resolution), cols - 1);
+        all_road = lut[img[(size_t)ir * stride + ic]] == 1;
+      }
+    if (!all_road) have_map_ = true;
     ok(tdr_map_set_polar_table(ctx(), tab_.data(), n_theta_, n_r_));
   }
   // ---- the map cache, top_down_map.cpp:226-286 with write_binary / read_binary of top_down_map.h:29-50: same files, same
@@ -191,6 +194,10 @@ class TopDownMapPolar {
     for (int cls = 0; cls < params_.num_classes; cls++)
       if (cx < cols_ && cy < rows_ && cx >= 0 && cy >= 0 && layers_[(size_t)cls * rows_ * cols_ + (size_t)cx * rows_ + cy] < 1)
         classes.push_back(cls);
+  }
+  // top_down_map.cpp:172-175 (float point: divided by the resolution here AND again in the integer overload)
+  void getClassesAtPoint(const Vector2f& center, std::vector<int>& classes) const {
+    getClassesAtPoint(Vector2i{(int)(center.x / params_.resolution), (int)(center.y / params_.resolution)}, classes);
   }
   // top_down_map_polar.cpp:21-53
   void getLocalMap(Vector2f center, float scale, float res, std::vector<ArrayXXf>& dists, ArrayXXc& mask) {
@@ -343,8 +350,36 @@ class ParticleFilter {
   void maxLikelihood(float state[4]) { if (ctx()) ok(tdr_pf_pose(ctx(), nullptr, nullptr, state, nullptr)); }
   void computeCov(float cov[16]) { float m[4]; if (ctx()) ok(tdr_pf_pose(ctx(), nullptr, nullptr, m, cov)); }
   int numParticles() const { return num_particles_; }
-  float scale() { pull(); return states_.empty() ? 1.f : states_[0].scale; }
+  // particle_filter.cpp:358-366
+  float scale() {
+    if (params_.fixed_scale > 0) return params_.fixed_scale;
+    if (scale_frozen_) { pull(); return states_.empty() ? -1.f : states_[0].scale; }
+    return -1;
+  }
   bool isScaleFrozen() const { return scale_frozen_; }
+  // particle_filter.cpp:343-357: lock every particle's scale to the geometric mean (float accumulator, double pow)
+  void freezeScale() {
+    if (scale_frozen_) return;
+    pull();
+    float geo_mean = 1;
+    for (const State& s : states_) geo_mean *= std::pow(s.scale, 1. / states_.size());
+    for (State& s : states_) s.scale = geo_mean;
+    scale_frozen_ = true;
+    push();
+  }
+  // particle_filter.cpp:320-341: new aerial map -> distance fields on the device, every particle's init position
+  // shifted by the map-centre delta; particles are initialised if there were none yet
+  void updateMap(const uint8_t* img, int rows, int cols, int stride, const Vector2i& map_center) {
+    map_->updateMap(img, rows, cols, stride, map_center);
+    const int dx = map_center.x - last_map_center_.x, dy = map_center.y - last_map_center_.y;
+    if (num_particles_ > 0 && (dx != 0 || dy != 0)) {
+      pull();
+      for (State& s : states_) { s.init_x_px += dx; s.init_y_px += dy; }
+      push();
+    }
+    last_map_center_ = map_center;
+    if (num_particles_ == 0 && map_->haveMap()) initializeParticles();   // the reference does not test haveMap here and spins in the road search on a road-less map
+  }
   // host views (the reference's visualize / GMM thread read the particles on the host)
   const std::vector<State>& states() { pull(); return states_; }
   const std::vector<float>& lastDist() { pull(); return last_dist_; }
@@ -388,6 +423,28 @@ class ParticleFilter {
   void initializeParticles() {
     size_t num_at_scale = 1;
     if (params_.fixed_scale < 0) num_at_scale = 10; else scale_frozen_ = true;
+    // :27-54: a metric initial position (relative to the map centre) overrides the pixel one; the filter stays empty
+    // when that position is off the map or has no road within 4 px
+    if (scale_frozen_ && params_.init_pos_m_x != std::numeric_limits<float>::infinity()) {
+      const Vector2i mc = map_->mapCenter(), sz = map_->size();
+      params_.init_pos_px_x = (params_.init_pos_m_x * params_.fixed_scale) + mc.x;
+      params_.init_pos_px_y = (params_.init_pos_m_y * params_.fixed_scale) + mc.y;
+      if (params_.init_pos_px_x < 0 || params_.init_pos_px_x >= sz.x || params_.init_pos_px_y < 0 || params_.init_pos_px_y >= sz.y) {
+        fprintf(stderr, "[XView] No map received for input loc\n");
+        return;
+      }
+      bool good_init = false;
+      std::vector<int> cls_vec;
+      for (int dx = -4; dx <= 4 && !good_init; dx++)
+        for (int dy = -4; dy <= 4 && !good_init; dy++) {
+          map_->getClassesAtPoint(Vector2i{(int)(params_.init_pos_px_x + dx), (int)(params_.init_pos_px_y + dy)}, cls_vec);
+          good_init = std::find(cls_vec.begin(), cls_vec.end(), 1) != cls_vec.end();
+        }
+      if (!good_init) {
+        fprintf(stderr, "[XView] No road in map at init location\n");
+        return;
+      }
+    }
     for (int i = 0; i < max_num_particles_ / (int)num_at_scale; i++) {
       State proto = randomState();
       for (float scale = 0; scale < 1; scale += 1. / num_at_scale) {
@@ -432,6 +489,7 @@ class ParticleFilter {
   FilterParams params_;
   int max_num_particles_ = 0, num_particles_ = 0;
   bool scale_frozen_ = false, host_dirty_ = false;
+  Vector2i last_map_center_;
   float last_u_ = 0.f;
   std::vector<State> states_;
   std::vector<float> last_dist_, stage_, z_;
