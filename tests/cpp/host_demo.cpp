@@ -113,6 +113,42 @@ int main(int argc, char** argv) {
   ParticleFilter off_map(48, &map, fo, (uint32_t)seed + 4);
   const float misc[5] = {sc_fixed, sc_free, sc_frozen, (float)metric.numParticles(), (float)off_map.numParticles()};
   wr(dir + "misc.f32", misc, 5);
+  // ---- the vector-map constructor path and the raster cache (top_down_map.cpp:22-31, :197-224): polygons -> binary class
+  // maps -> distance fields on the device; class<i>.png written, then a second map object starts from those files alone.
+  // (one device context per process: from here on the device holds THIS map)
+  {
+    auto pv = rd<float>(dir + "polys.f32");
+    auto ps = rd<int32_t>(dir + "poly_start.i32");
+    auto pc = rd<int32_t>(dir + "poly_class.i32");
+    auto vm = rd<int32_t>(dir + "vec_meta.i32");                                 // svg width, height, then the exclusive classes
+    std::vector<std::vector<std::vector<Vector2f>>> poly(C);
+    for (size_t k = 0; k < pc.size(); k++) {
+      std::vector<Vector2f> path;
+      for (int i = ps[k]; i < ps[k + 1]; i++) { Vector2f v; v.x = pv[2 * i]; v.y = pv[2 * i + 1]; path.push_back(v); }
+      poly[pc[k]].push_back(path);
+    }
+    std::vector<int> excl(vm.begin() + 2, vm.end());
+    TopDownMapPolar vmap(mp);
+    vmap.samplePtsPolar(n_theta, n_r, (float)(2 * M_PI / n_theta));
+    vmap.setVectorMap(poly, Vector2i{vm[0], vm[1]}, excl);
+    if (!vmap.haveMap()) return 7;
+    vmap.saveRasterizedMaps(dir + "vec_raster_cache");
+    std::vector<ArrayXXf> loc(C, ArrayXXf(n_theta, n_r));
+    ArrayXXc lmask(n_theta, n_r);
+    Vector2f vc; vc.x = vm[0] * 0.45f; vc.y = vm[1] * 0.55f;
+    vmap.getLocalMap(vc, 1.5f, 2.0f, loc, lmask);
+    for (int c = 0; c < C; c++) wr(dir + "vec_local" + std::to_string(c) + ".f32", loc[c].data(), (size_t)n_theta * n_r);
+    std::vector<int> at; vmap.getClassesAtPoint(vc, at);
+    std::vector<int32_t> at32(at.begin(), at.end()); at32.push_back(-1);
+    wr(dir + "vec_classes_at.i32", at32.data(), at32.size());
+    TopDownMapPolar rmap(mp);
+    rmap.samplePtsPolar(n_theta, n_r, (float)(2 * M_PI / n_theta));
+    if (rmap.loadRasterizedMaps(dir + "no_such_cache")) return 8;
+    if (!rmap.loadRasterizedMaps(dir + "vec_raster_cache") || !rmap.haveMap()) return 9;
+    rmap.getLocalMap(vc, 1.5f, 2.0f, loc, lmask);
+    for (int c = 0; c < C; c++) wr(dir + "ras_local" + std::to_string(c) + ".f32", loc[c].data(), (size_t)n_theta * n_r);
+    wr(dir + "ras_mask.u8", lmask.data(), (size_t)n_theta * n_r);
+  }
   std::cout << "host_demo ok: " << filter.numParticles() << " particles, mean (" << mean[0] << ", " << mean[1] << ", " << mean[2] << ")\n";
   return 0;
 }

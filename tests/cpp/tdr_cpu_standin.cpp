@@ -44,6 +44,8 @@ void orc_ml_cov(const OrcState* st, long n, long argmax, float ml[4], float cov[
 void orc_active_best_rel_pos(const float* layers, const uint8_t* mask, int rows, int cols, int C, float resolution, const float* tab,
                              int n_theta, int n_r, const float* preds, int n, float rel[2], float* best_diff_out);
 void orc_gmm_samples(const OrcState* st, long n, int num_samples, double* samples);
+void orc_raster_polygons(const float* verts, const int* poly_start, const int* poly_class, int n_poly, int map_w, int map_h, float rot,
+                         float resolution, int C, const int* exclusive, int n_excl, float* layers);
 }
 static_assert(sizeof(OrcState) == sizeof(tdr_state), "State layouts differ");
 
@@ -89,6 +91,28 @@ int tdr_map_set_class_image(tdr_ctx* c, const uint8_t* img, int h, int w, int st
   orc_compute_dists(c->layers.data(), c->rows, c->cols, C, res, c->mask.data());
   c->have_geo = false;
   return TDR_OK;
+}
+static int dists_from_seeds(tdr_ctx* c) {
+  c->layers = c->seeds;
+  c->mask.assign((size_t)c->rows * c->cols, 0);
+  orc_compute_dists(c->layers.data(), c->rows, c->cols, c->C, c->resolution, c->mask.data());
+  c->have_geo = false;
+  return TDR_OK;
+}
+int tdr_map_set_binary_layers(tdr_ctx* c, const float* layers, int rows, int cols, int C, float res) {
+  REQ(layers && rows > 0 && cols > 0 && C > 0 && C <= TDR_MAX_CLASSES, TDR_EINVAL, "bad layers");
+  c->rows = rows; c->cols = cols; c->C = C; c->resolution = res;
+  c->seeds.assign(layers, layers + (size_t)C * rows * cols);
+  return dists_from_seeds(c);
+}
+int tdr_map_set_polygons(tdr_ctx* c, const float* verts, const int32_t* start, const int32_t* cls, int n_poly, int map_w, int map_h,
+                         float rot, int C, float res, const int32_t* excl, int n_excl, float* layers_out) {
+  REQ(verts && start && cls && C > 0 && C <= TDR_MAX_CLASSES, TDR_EINVAL, "bad polygons");
+  c->rows = (int)((float)map_h / res); c->cols = (int)((float)map_w / res); c->C = C; c->resolution = res;
+  c->seeds.assign((size_t)C * c->rows * c->cols, 0.f);
+  orc_raster_polygons(verts, start, cls, n_poly, map_w, map_h, rot, res, C, excl, n_excl, c->seeds.data());
+  if (layers_out) std::copy(c->seeds.begin(), c->seeds.end(), layers_out);
+  return dists_from_seeds(c);
 }
 int tdr_map_set_dist_layers(tdr_ctx* c, const float* layers, const uint8_t* mask, int rows, int cols, int C, float res) {
   REQ(layers && mask && rows > 0 && cols > 0, TDR_EINVAL, "bad layers");

@@ -22,10 +22,10 @@ DEMO = os.path.join(ROOT, "tests", "cpp", "host_demo")
 def build_demo():
     tdr.build()
     src = os.path.join(ROOT, "tests", "cpp", "host_demo.cpp")
-    hdr = os.path.join(ROOT, "top_down_renderer_b200", "host", "tdr_host.hpp")
-    if not os.path.exists(DEMO) or os.path.getmtime(DEMO) < max(os.path.getmtime(src), os.path.getmtime(hdr)):
+    hdrs = [os.path.join(ROOT, "top_down_renderer_b200", "host", f) for f in ("tdr_host.hpp", "png_gray.hpp")]
+    if not os.path.exists(DEMO) or os.path.getmtime(DEMO) < max(os.path.getmtime(f) for f in [src] + hdrs):
         subprocess.check_call(["g++", "-O2", "-std=c++17", "-Wall", "-o", DEMO, src, "-L", os.path.join(ROOT, "top_down_renderer_b200"),
-                               "-l:libtdr_b200.so", "-Wl,-rpath," + os.path.join(ROOT, "top_down_renderer_b200")])
+                               "-l:libtdr_b200.so", "-Wl,-rpath," + os.path.join(ROOT, "top_down_renderer_b200"), "-lz"])
     return DEMO
 
 
@@ -36,10 +36,10 @@ def build_demo_cpu():
     """host_demo.cpp + the CPU stand-in of the C ABI + liboracle.so: no CUDA anywhere in this binary"""
     so = orc.build()
     srcs = [os.path.join(ROOT, "tests", "cpp", f) for f in ("host_demo.cpp", "tdr_cpu_standin.cpp")]
-    deps = srcs + [os.path.join(ROOT, "top_down_renderer_b200", "host", "tdr_host.hpp"), os.path.join(ROOT, "include", "tdr.h"), so]
+    deps = srcs + [os.path.join(ROOT, "top_down_renderer_b200", "host", f) for f in ("tdr_host.hpp", "png_gray.hpp")] + [os.path.join(ROOT, "include", "tdr.h"), so]
     if not os.path.exists(DEMO_CPU) or os.path.getmtime(DEMO_CPU) < max(os.path.getmtime(f) for f in deps):
         subprocess.check_call(["g++", "-O2", "-std=c++17", "-Wall", "-o", DEMO_CPU] + srcs +
-                              ["-L", os.path.dirname(so), "-l:" + os.path.basename(so), "-Wl,-rpath," + os.path.dirname(so), "-pthread"])
+                              ["-L", os.path.dirname(so), "-l:" + os.path.basename(so), "-Wl,-rpath," + os.path.dirname(so), "-pthread", "-lz"])
     return DEMO_CPU
 
 
@@ -53,7 +53,27 @@ def write_inputs(d, N=800, seed=5):
     np.array([2.0, pose[0], pose[1], 6.0, math.degrees(heading), 3.0], dtype=np.float32).tofile(os.path.join(d, "meta.f32"))
     img.tofile(os.path.join(d, "class_image.u8"))
     pts.tofile(os.path.join(d, "points.f32"))
+    polys, cls = demo_polygons()
+    np.concatenate(polys).astype(np.float32).tofile(os.path.join(d, "polys.f32"))
+    np.cumsum([0] + [len(q) for q in polys]).astype(np.int32).tofile(os.path.join(d, "poly_start.i32"))
+    np.array(cls, dtype=np.int32).tofile(os.path.join(d, "poly_class.i32"))
+    np.array([VEC_W, VEC_H] + VEC_EXCLUSIVE, dtype=np.int32).tofile(os.path.join(d, "vec_meta.i32"))
     return cm, img, pts
+
+
+VEC_W, VEC_H, VEC_EXCLUSIVE = 230, 170, [0, 1]
+
+
+def demo_polygons():
+    """a small vector map in class order (setVectorMap hands the polygons over class by class): a background, a concave
+    road, an axis-aligned building, overlapping vegetation, one polygon partly off the map"""
+    rng = np.random.default_rng(12)
+    polys = [np.float32([[-5, -5], [240, -5], [240, 180], [-5, 180]]),                                   # class 0 everywhere
+             np.float32([[20.3, 30.1], [200.7, 35.2], [205.1, 60.8], [120.5, 55.5], [110.2, 140.9], [80.8, 139.3], [85.4, 52.6], [18.9, 58.2]]),
+             np.float32([[150.25, 90.25], [190.75, 90.25], [190.75, 130.75], [150.25, 130.75]]),
+             np.float32([[60, 100], [100, 70], [140, 110], [95, 160]]) + rng.uniform(-0.4, 0.4, (4, 2)).astype(np.float32),
+             np.float32([[200, 120], [260, 125], [250, 200], [190, 190]])]
+    return polys, [0, 1, 2, 3, 3]
 
 
 def test_host_mirror_compiles_and_refuses_to_run_without_gpu(tmp_path):
@@ -193,6 +213,28 @@ def check_demo_outputs(d, cm, img, pts, N, seed, device):
     assert n_metric == 48 and np.array_equal(got_m, ms) and abs(px[0] - fmeta[1]) < 1e-3 and abs(px[1] - fmeta[2]) < 1e-3
     assert np.hypot(got_m["init_x_px"] - fmeta[1], got_m["init_y_px"] - fmeta[2]).max() < 6 * fmeta[3]
     assert n_off == 0
+
+    # ---- vector map -> raster cache -> a second map from the PNG files alone (top_down_map.cpp:22-31, :197-224) ----
+    from top_down_renderer_b200 import rastercache
+    polys, cls = demo_polygons()
+    binl = orc.raster_polygons(polys, cls, VEC_W, VEC_H, 0.0, 1.0, C, VEC_EXCLUSIVE)
+    assert all((binl[c] == 0).any() and (binl[c] == 1).any() for c in range(C))
+    cache = os.path.join(d, "vec_raster_cache")
+    assert np.array_equal(rastercache.load_rasterized_maps(cache, C), binl)      # the C++ writer's files, the Python reader
+    try:
+        import cv2
+        top = cv2.imread(os.path.join(cache, "class2.png"), cv2.IMREAD_GRAYSCALE)
+        assert np.array_equal(top, rastercache.layer_to_image(binl[2]))           # ... and OpenCV's
+    except ImportError:
+        pass
+    vl, vmask = orc.compute_dists(binl, 1.0)
+    want_l, want_m = orc.local_map_polar(vl, vmask, 1.0, tab, np.float32(VEC_W * np.float32(0.45)), np.float32(VEC_H * np.float32(0.55)), 1.5, 2.0)
+    vec = np.stack([rd(d, f"vec_local{c}.f32", np.float32) for c in range(C)])
+    ras = np.stack([rd(d, f"ras_local{c}.f32", np.float32) for c in range(C)])
+    assert same_bits(vec, want_l.reshape(C, -1)) and same_bits(ras, vec)
+    assert np.array_equal(rd(d, "ras_mask.u8", np.uint8), want_m.reshape(-1))
+    at = rd(d, "vec_classes_at.i32", np.int32)
+    assert at[-1] == -1 and list(at[:-1]) == orc.classes_at_point(vl, 1.0, int(VEC_W * np.float32(0.45)), int(VEC_H * np.float32(0.55)))
 
 
 def test_host_mirror_logic_on_the_cpu_standin(tmp_path):

@@ -219,6 +219,86 @@ def test_eig_cache_format_and_round_trip(tmp_path):
     assert np.array_equal(l2, layers) and np.array_equal(g2, geo) and np.array_equal(m2, mask)
 
 
+# ---- the reference's raster cache (top_down_map.cpp:197-224): class<i>.png, 8-bit gray, flipped vertically
+def test_raster_cache_png_codec_against_opencv(tmp_path):
+    """the PNG files are the third-party part (cv::imwrite / cv::imread): what OpenCV writes this codec reads to the
+    byte, what this codec writes OpenCV reads to the byte — for binary maps and for arbitrary gray images, whose scan
+    lines make libpng pick every filter type"""
+    import struct
+    import zlib
+    cv2 = pytest.importorskip("cv2")
+    from top_down_renderer_b200 import rastercache as rc
+    rng = np.random.default_rng(8)
+    smooth = (np.add.outer(np.arange(97), np.arange(131)) % 256).astype(np.uint8)
+    images = {"binary": (rng.random((60, 83)) < 0.4).astype(np.uint8) * 255, "noise": rng.integers(0, 256, (41, 67), dtype=np.uint8),
+              "smooth": smooth, "one_pixel": np.uint8([[200]]), "blocks": np.kron(rng.integers(0, 256, (9, 11), dtype=np.uint8), np.ones((8, 8), np.uint8))}
+    seen = set()
+    for name, img in images.items():
+        p_cv, p_own = str(tmp_path / f"{name}_cv.png"), str(tmp_path / f"{name}_own.png")
+        assert cv2.imwrite(p_cv, img)
+        assert np.array_equal(rc.read_png_gray(p_cv), img), name
+        rc.write_png_gray(p_own, img)
+        assert np.array_equal(cv2.imread(p_own, cv2.IMREAD_GRAYSCALE), img), name
+        assert np.array_equal(rc.read_png_gray(p_own), img), name
+        # which scan-line filters did libpng use?  (re-inflate the IDAT stream and look at the filter bytes)
+        data, pos, idat = open(p_cv, "rb").read(), 8, b""
+        while pos < len(data):
+            n, tag = struct.unpack(">I4s", data[pos:pos + 8])
+            if tag == b"IDAT":
+                idat += data[pos + 8:pos + 8 + n]
+            pos += 12 + n
+        seen |= set(np.frombuffer(zlib.decompress(idat), dtype=np.uint8).reshape(img.shape[0], img.shape[1] + 1)[:, 0].tolist())
+    assert 1 in seen, seen                                            # OpenCV's default: the Sub filter
+    # the other filter types, from an encoder written out here (cv2 confirms the files are valid PNGs of the image)
+    img = images["blocks"]
+    h, w = img.shape
+    for ft in (1, 2, 3, 4):
+        raw = np.zeros((h, w + 1), dtype=np.uint8)
+        raw[:, 0] = ft
+        for y in range(h):
+            for x in range(w):
+                a = int(img[y, x - 1]) if x else 0
+                b = int(img[y - 1, x]) if y else 0
+                c = int(img[y - 1, x - 1]) if x and y else 0
+                pa, pb, pc = abs(b - c), abs(a - c), abs(a + b - 2 * c)
+                pred = {1: a, 2: b, 3: (a + b) >> 1, 4: a if pa <= pb and pa <= pc else (b if pb <= pc else c)}[ft]
+                raw[y, x + 1] = (int(img[y, x]) - pred) & 255
+        path = str(tmp_path / f"filter{ft}.png")
+        with open(path, "wb") as f:
+            f.write(rc._SIG + rc._chunk(b"IHDR", struct.pack(">IIBBBBB", w, h, 8, 0, 0, 0, 0)))
+            comp = zlib.compress(raw.tobytes())
+            f.write(rc._chunk(b"IDAT", comp[:100]) + rc._chunk(b"IDAT", comp[100:]) + rc._chunk(b"IEND", b""))   # split IDAT
+        assert np.array_equal(cv2.imread(path, cv2.IMREAD_GRAYSCALE), img), ft
+        assert np.array_equal(rc.read_png_gray(path), img), ft
+    cv2.imwrite(str(tmp_path / "rgb.png"), np.zeros((4, 4, 3), np.uint8))
+    with pytest.raises(ValueError):
+        rc.read_png_gray(str(tmp_path / "rgb.png"))
+    data = bytearray(open(str(tmp_path / "noise_own.png"), "rb").read())
+    data[60] ^= 1                                                     # a flipped bit inside IDAT: the CRC catches it
+    open(str(tmp_path / "bad.png"), "wb").write(bytes(data))
+    with pytest.raises(ValueError):
+        rc.read_png_gray(str(tmp_path / "bad.png"))
+
+
+def test_raster_cache_round_trip_and_orientation(tmp_path):
+    cv2 = pytest.importorskip("cv2")
+    from top_down_renderer_b200 import rastercache as rc
+    rng = np.random.default_rng(4)
+    C, cols, rows = 3, 37, 22
+    layers = (rng.random((C, cols, rows)) < 0.7).astype(np.float32)            # binary class maps, (cols, rows) = col-major rows x cols
+    d = str(tmp_path / "campus_raster_cache")
+    rc.save_rasterized_maps(d, layers)
+    # the file looks like the input map: map row 0 (y = 0, the bottom) is the LAST image line, white = outside the class
+    img = cv2.imread(f"{d}/class1.png", cv2.IMREAD_GRAYSCALE)
+    assert img.shape == (rows, cols) and set(np.unique(img)) <= {0, 255}
+    assert img[rows - 1, 5] == 255 * layers[1, 5, 0] and img[0, 7] == 255 * layers[1, 7, rows - 1]
+    got = rc.load_rasterized_maps(d, C)
+    assert got.dtype == np.float32 and np.array_equal(got, layers)            # 255 * float(1/255) == 1.0f
+    # the literal OpenCV chain of loadRasterizedMaps on the same file: flip, convertTo(CV_32FC1, 1./255)
+    want = (cv2.flip(img, 0).astype(np.float32) * np.float32(1.0 / 255)).T
+    assert np.array_equal(got[1], want)
+
+
 def test_lean_lattice_coordinate_equals_the_literal_form(hm):
     """tdr_math.cuh lattice_coord (interval test + trunc, what the tensor-core kernels run) against
     f2i_x86(round_half_away(v)) followed by 0 <= index < n (top_down_map_polar.cpp:31-37): every float near every

@@ -12,6 +12,7 @@
 //   ParticleFilter      include/top_down_render/particle_filter.h:22-41
 #pragma once
 #include <math.h>
+#include <sys/stat.h>
 #include <algorithm>
 #include <array>
 #include <cmath>
@@ -25,6 +26,7 @@
 #include <vector>
 
 #include "../../include/tdr.h"
+#include "png_gray.hpp"
 
 namespace tdrhost {
 
@@ -187,6 +189,60 @@ class TopDownMapPolar {
     ok(tdr_map_set_polar_table(ctx(), tab_.data(), n_theta_, n_r_));
     return true;
   }
+  // ---- the vector-map constructor path (top_down_map.cpp:22-31 with getRasterMap :391-408): the polygons of every flattened
+  // class as loadSvg leaves them (y already flipped, :89) -> binary class maps (kept for saveRasterizedMaps) -> distance
+  // fields, all on the device; exclusive_classes as Params holds them (top_down_render.cpp:177-181)
+  void setVectorMap(const std::vector<std::vector<std::vector<Vector2f>>>& poly, const Vector2i& map_size,
+                    const std::vector<int>& exclusive_classes) {
+    if (poly.size() < 1 || !ctx()) return;                                  // :394
+    std::vector<float> verts; std::vector<int32_t> start(1, 0), cls;
+    for (size_t c = 0; c < poly.size(); c++)
+      for (const auto& path : poly[c]) {
+        for (const Vector2f& v : path) { verts.push_back(v.x); verts.push_back(v.y); }
+        start.push_back((int32_t)(verts.size() / 2)); cls.push_back((int32_t)c);
+      }
+    const int r = (int)((float)map_size.y / params_.resolution), c = (int)((float)map_size.x / params_.resolution);   // :399-400
+    binary_.assign((size_t)params_.num_classes * r * c, 0.f);
+    std::vector<int32_t> excl(exclusive_classes.begin(), exclusive_classes.end());
+    if (!ok(tdr_map_set_polygons(ctx(), verts.data(), start.data(), cls.data(), (int)cls.size(), map_size.x, map_size.y, 0.f,
+                                 params_.num_classes, params_.resolution, excl.data(), (int)excl.size(), binary_.data()))) return;
+    adoptDeviceMap();
+  }
+  // saveRasterizedMaps :197-211: class<i>.png = the binary class map x 255 (saturate_cast<uchar>), flipped vertically
+  void saveRasterizedMaps(const std::string& path) const {
+    if (binary_.empty()) return;
+    ::mkdir(path.c_str(), S_IRWXU);
+    std::vector<uint8_t> img((size_t)rows_ * cols_);
+    for (int cls = 0; cls < params_.num_classes; cls++) {
+      const float* m = binary_.data() + (size_t)cls * rows_ * cols_;
+      for (int r = 0; r < rows_; r++)
+        for (int c = 0; c < cols_; c++) {
+          const float v = std::nearbyint(m[(size_t)c * rows_ + r] * 255.f);
+          img[(size_t)(rows_ - 1 - r) * cols_ + c] = (uint8_t)std::min(std::max(v, 0.f), 255.f);
+        }
+      png::write_gray(path + "/class" + std::to_string(cls) + ".png", img.data(), cols_, rows_);
+    }
+  }
+  // loadRasterizedMaps :213-224 and what the constructor does next (:47-60): flip back, scale by float(1/255), distance
+  // fields on the device.  false when a file is missing or is not an 8-bit gray PNG (the reference crashes there).
+  bool loadRasterizedMaps(const std::string& path) {
+    if (!ctx()) return false;
+    std::vector<float> all;
+    int r = 0, c = 0;
+    for (int cls = 0; cls < params_.num_classes; cls++) {
+      std::vector<uint8_t> img; int w = 0, h = 0;
+      if (!png::read_gray(path + "/class" + std::to_string(cls) + ".png", img, w, h) || (cls > 0 && (w != c || h != r))) return false;
+      r = h; c = w;
+      const size_t at = all.size();
+      all.resize(at + (size_t)r * c);
+      for (int y = 0; y < r; y++)
+        for (int x = 0; x < c; x++) all[at + (size_t)x * r + y] = (float)img[(size_t)(r - 1 - y) * c + x] * (float)(1. / 255);
+    }
+    if (!ok(tdr_map_set_binary_layers(ctx(), all.data(), r, c, params_.num_classes, params_.resolution))) return false;
+    binary_.swap(all);
+    adoptDeviceMap();
+    return true;
+  }
   // top_down_map.cpp:159-170 (integer point)
   void getClassesAtPoint(const Vector2i& center_ind, std::vector<int>& classes) const {
     classes.clear();
@@ -241,7 +297,16 @@ class TopDownMapPolar {
   int nR() const { return n_r_; }
 
  private:
-  // write_binary / read_binary (top_down_map.h:29-50): Eigen::Index rows, cols, then column-major scalars
+  // after a constructor-path load: host copies of the distance fields for getClassesAtPoint, have_map_ (:62), table
+  void adoptDeviceMap() {
+    int r = 0, c = 0, k = 0; float res = 1;
+    tdr_map_info(ctx(), &r, &c, &k, &res);
+    rows_ = r; cols_ = c;
+    layers_.resize((size_t)k * r * c); mask_.resize((size_t)r * c);
+    ok(tdr_map_get_layers(ctx(), layers_.data(), mask_.data()));
+    have_map_ = true;
+    ok(tdr_map_set_polar_table(ctx(), tab_.data(), n_theta_, n_r_));
+  }
   void write_eig(const std::string& name, const void* data, size_t scalar_bytes) const {
     std::ofstream out(name, std::ios::out | std::ios::binary | std::ios::trunc);
     const int64_t rows = rows_, cols = cols_;
@@ -263,7 +328,7 @@ class TopDownMapPolar {
   bool have_map_ = false;
   Vector2i map_center_;
   int rows_ = 0, cols_ = 0, n_theta_ = 0, n_r_ = 0;
-  std::vector<float> layers_, tab_, stage_;
+  std::vector<float> layers_, tab_, stage_, binary_;
   std::vector<uint8_t> mask_;
 };
 
