@@ -51,6 +51,22 @@ int main(int argc, char** argv) {
   renderer.renderSemanticTopDown(pts, fmeta[0], (float)(2 * M_PI / n_theta), top_down);
   for (int c = 0; c < C; c++) wr(dir + "scan_" + std::to_string(c) + ".f32", top_down[c].data(), (size_t)n_theta * n_r);
 
+  // the Cartesian twins through the base classes (non-virtual name hiding, as in the reference): the refine_map-style
+  // raster of the scan and the node's debug view of the map around the start pose (top_down_render.cpp:315)
+  {
+    ScanRenderer& cart = renderer;
+    std::vector<ArrayXXf> cart_imgs(C, ArrayXXf(48, 64));
+    cart.renderSemanticTopDown(pts, 1.5f, cart_imgs);
+    for (int c = 0; c < C; c++) wr(dir + "cart_scan_" + std::to_string(c) + ".f32", cart_imgs[c].data(), (size_t)48 * 64);
+    TopDownMap* base = &map;
+    std::vector<ArrayXXf> cart_local(C, ArrayXXf(30, 40));
+    ArrayXXc cart_mask(30, 40);
+    Vector2f cc; cc.x = fmeta[1]; cc.y = fmeta[2];
+    base->getLocalMap(cc, 0.3f, 2.5f, cart_local, cart_mask);
+    for (int c = 0; c < C; c++) wr(dir + "cart_local_" + std::to_string(c) + ".f32", cart_local[c].data(), (size_t)30 * 40);
+    wr(dir + "cart_mask.u8", cart_mask.data(), (size_t)30 * 40);
+  }
+
   FilterParams fp; fp.regularization = 0.7f; fp.pos_cov = 0.15f; fp.theta_cov = 0.004f; fp.fixed_scale = 2.0f;
   fp.init_pos_px_x = fmeta[1]; fp.init_pos_px_y = fmeta[2]; fp.init_pos_px_cov = fmeta[3];
   fp.init_pos_deg_theta = fmeta[4]; fp.init_pos_deg_cov = fmeta[5];

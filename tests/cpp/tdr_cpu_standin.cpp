@@ -26,6 +26,10 @@ struct OrcFilterParams {
 };
 void orc_render_polar(const uint8_t* pts, int stride, int intensity_off, long n, float res, float ang_res, int n_theta, int n_r,
                       const int* lut, int n_lut, int C, float* imgs);
+void orc_render_cart(const uint8_t* pts, int stride, int intensity_off, long n, float res, int rows, int cols, const int* lut, int n_lut,
+                     int C, float* imgs);
+void orc_local_map_cart(const float* layers, const uint8_t* mask, int rows, int cols, int C, float resolution, float cx, float cy,
+                        float rot, float res, int out_rows, int out_cols, float* dists, uint8_t* mask_out);
 void orc_map_dims(int h_img, int w_img, float res, int* rows, int* cols);
 void orc_class_image_to_layers(const uint8_t* img, int h_img, int w_img, int stride, const int* lut, int n_lut, int C, float res,
                                float* layers);
@@ -159,6 +163,11 @@ int tdr_map_local_polar(tdr_ctx* c, const float* xy, int n, float scale, float r
                         xy[2 * i + 1], scale, res, dists + (size_t)i * c->C * P, mask + (size_t)i * P);
   return TDR_OK;
 }
+int tdr_map_local_cart(tdr_ctx* c, float cx, float cy, float rot, float res, int rows, int cols, float* dists, uint8_t* mask) {
+  REQ(c->rows > 0, TDR_ESTATE, "no map");
+  orc_local_map_cart(c->layers.data(), c->mask.data(), c->rows, c->cols, c->C, c->resolution, cx, cy, rot, res, rows, cols, dists, mask);
+  return TDR_OK;
+}
 int tdr_map_local_geo_polar(tdr_ctx* c, const float* xy, int n, float scale, float res, float* geo) {
   REQ(c->rows > 0 && !c->tab.empty(), TDR_ESTATE, "no map / table");
   ensure_geo(c);
@@ -189,6 +198,11 @@ int tdr_scan_render_polar(tdr_ctx* c, float res, float ang_res, int n_theta, int
   orc_render_polar(c->pts.data(), c->pts_stride, c->pts_off, c->n_pts, res, ang_res, n_theta, n_r, c->lut.data(), c->n_lut, c->scan_C,
                    c->scan.data());
   if (imgs) std::copy(c->scan.begin(), c->scan.end(), imgs);
+  return TDR_OK;
+}
+int tdr_scan_render_cart(tdr_ctx* c, float res, int rows, int cols, float* imgs) {
+  REQ(!c->lut.empty() && imgs, TDR_ESTATE, "no lut");
+  orc_render_cart(c->pts.data(), c->pts_stride, c->pts_off, c->n_pts, res, rows, cols, c->lut.data(), c->n_lut, c->scan_C, imgs);
   return TDR_OK;
 }
 int tdr_scan_set_polar_images(tdr_ctx* c, const float* imgs, int n_theta, int n_r, int C) {

@@ -110,6 +110,12 @@ def check_demo_outputs(d, cm, img, pts, N, seed, device):
     assert np.array_equal(scan, scan_o)
     layers, mask = orc.compute_dists(orc.class_image_to_layers(img, lut, C, 1.0), 1.0)
     tab = orc.polar_table(100, 25, ang, 1.0)
+    # the Cartesian twins through the base classes: bit-exact
+    cart = np.stack([rd(d, f"cart_scan_{c}.f32", np.float32) for c in range(C)])
+    assert np.array_equal(cart, orc.render_cart(pts, 1.5, 48, 64, lut, C).reshape(C, -1)) and cart.sum() > 1000
+    want_c, want_cm = orc.local_map_cart(layers, mask, 1.0, float(fmeta[1]), float(fmeta[2]), 0.3, 2.5, 30, 40)
+    got_c = np.stack([rd(d, f"cart_local_{c}.f32", np.float32) for c in range(C)])
+    assert same_bits(got_c, want_c.reshape(C, -1)) and np.array_equal(rd(d, "cart_mask.u8", np.uint8), want_cm.reshape(-1))
 
     # ---- initializeParticles + propagate: the reference's own RNG calls on ONE engine (particle_filter.cpp:19-92) ----
     init_kw = dict(init_pos_px=(float(fmeta[1]), float(fmeta[2])), init_pos_px_cov=float(fmeta[3]), init_pos_deg_theta=float(fmeta[4]),

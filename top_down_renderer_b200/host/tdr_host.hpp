@@ -7,8 +7,11 @@
 // behind the C ABI on the device; what stays here is what the reference also keeps on the host: particle
 // initialisation and propagation (libstdc++ RNG), the polar offset table and the theta-search list.
 //
+//   ScanRenderer        include/top_down_render/scan_renderer.h:14-23
 //   ScanRendererPolar   include/top_down_render/scan_renderer_polar.h:15-22
-//   TopDownMapPolar     include/top_down_render/top_down_map_polar.h:6-22 (+ top_down_map.h:52-101)
+//   TopDownMap          include/top_down_render/top_down_map.h:52-101
+//   TopDownMapPolar     include/top_down_render/top_down_map_polar.h:6-22
+//   ActiveLocalizer     include/top_down_render/active_localizer.h:7-16
 //   ParticleFilter      include/top_down_render/particle_filter.h:22-41
 #pragma once
 #include <math.h>
@@ -82,9 +85,34 @@ inline bool ok(int rc) {
   return rc == TDR_OK;
 }
 
-class ScanRendererPolar {
+// scan_renderer.h:14-23
+class ScanRenderer {
  public:
-  explicit ScanRendererPolar(const std::vector<int>& flatten_lut) : flatten_lut_(flatten_lut) {}
+  explicit ScanRenderer(const std::vector<int>& flatten_lut) : flatten_lut_(flatten_lut) {}
+  // scan_renderer.cpp:55-78.  imgs: pre-sized (rows x cols) images; their size defines the raster, centred on the sensor.
+  void renderSemanticTopDown(const std::vector<PointXYZI>& cloud, float res, std::vector<ArrayXXf>& imgs) {
+    if (imgs.size() < 1 || !ctx()) return;                                  // :57
+    int max_cls = -1;
+    for (int v : flatten_lut_) max_cls = std::max(max_cls, v);
+    if ((int)imgs.size() < max_cls + 1) return;                             // the reference indexes imgs[lut] unchecked
+    const int C = (int)imgs.size(), rows = imgs[0].rows(), cols = imgs[0].cols();
+    if (!ok(tdr_scan_set_lut(ctx(), flatten_lut_.data(), (int)flatten_lut_.size(), C))) return;
+    if (!ok(tdr_scan_set_points(ctx(), cloud.data(), sizeof(PointXYZI), 16, (int64_t)cloud.size()))) return;
+    stage_.resize((size_t)C * rows * cols);
+    if (!ok(tdr_scan_render_cart(ctx(), res, rows, cols, stage_.data()))) return;
+    for (int c = 0; c < C; c++)
+      std::copy(stage_.begin() + (size_t)c * rows * cols, stage_.begin() + (size_t)(c + 1) * rows * cols, imgs[c].d.begin());
+  }
+
+ protected:
+  std::vector<int> flatten_lut_;
+  std::vector<float> stage_;
+};
+
+// scan_renderer_polar.h:15-22: the 4-argument overload hides the Cartesian one, as in the reference
+class ScanRendererPolar : public ScanRenderer {
+ public:
+  explicit ScanRendererPolar(const std::vector<int>& flatten_lut) : ScanRenderer(flatten_lut) {}
   // scan_renderer_polar.cpp:83-109.  imgs: C pre-sized (n_theta x n_r) images; their size defines the raster.
   void renderSemanticTopDown(const std::vector<PointXYZI>& cloud, float res, float ang_res, std::vector<ArrayXXf>& imgs) {
     int max_cls = -1;
@@ -98,20 +126,18 @@ class ScanRendererPolar {
     for (int c = 0; c < C; c++)
       std::copy(stage_.begin() + (size_t)c * n_theta * n_r, stage_.begin() + (size_t)(c + 1) * n_theta * n_r, imgs[c].d.begin());
   }
-
- private:
-  std::vector<int> flatten_lut_;
-  std::vector<float> stage_;
 };
 
-class TopDownMapPolar {
+// top_down_map.h:52-101.  TopDownMapPolar derives from it and HIDES getLocalMap / getLocalGeoMap with the polar versions
+// of the same signatures (non-virtual, as in the reference): through a TopDownMap* the Cartesian ones are called.
+class TopDownMap {
  public:
   struct Params {                       // top_down_map.h:54-62 (the dynamic-map fields)
     std::vector<int> flatten_lut;
     int num_classes = 0;
     float resolution = 1;
   };
-  explicit TopDownMapPolar(const Params& params) : params_(params) { samplePtsPolar(100, 50, (float)(2 * M_PI / 100)); }
+  explicit TopDownMap(const Params& params) : params_(params) {}
 
   // top_down_map.cpp:146-157: class-index image (row-major, row 0 = top) -> layers -> distance fields
   void updateMap(const uint8_t* img, int rows, int cols, int stride, const Vector2i& map_center) {
@@ -135,7 +161,7 @@ class TopDownMapPolar {
         all_road = lut[img[(size_t)ir * stride + ic]] == 1;
       }
     if (!all_road) have_map_ = true;
-    ok(tdr_map_set_polar_table(ctx(), tab_.data(), n_theta_, n_r_));
+    if (!tab_.empty()) ok(tdr_map_set_polar_table(ctx(), tab_.data(), n_theta_, n_r_));
   }
   // ---- the map cache, top_down_map.cpp:226-286 with write_binary / read_binary of top_down_map.h:29-50: same files, same
   // bytes (Eigen::Index = int64 rows, cols, then column-major scalars), in `dir` instead of $HOME/.ros/xview_cache
@@ -186,7 +212,7 @@ class TopDownMapPolar {
     }
     if (!ok(tdr_map_set_geo_dist_layers(ctx(), geo.data()))) return false;
     have_map_ = true;
-    ok(tdr_map_set_polar_table(ctx(), tab_.data(), n_theta_, n_r_));
+    if (!tab_.empty()) ok(tdr_map_set_polar_table(ctx(), tab_.data(), n_theta_, n_r_));
     return true;
   }
   // ---- the vector-map constructor path (top_down_map.cpp:22-31 with getRasterMap :391-408): the polygons of every flattened
@@ -255,6 +281,62 @@ class TopDownMapPolar {
   void getClassesAtPoint(const Vector2f& center, std::vector<int>& classes) const {
     getClassesAtPoint(Vector2i{(int)(center.x / params_.resolution), (int)(center.y / params_.resolution)}, classes);
   }
+  // TopDownMap::getLocalMap (Cartesian, top_down_map.cpp:429-459): a rotated rows x cols lattice around `center`; the
+  // size of the caller's images defines the lattice.  Only the node's debug view calls it (top_down_render.cpp:315).
+  void getLocalMap(Vector2f center, float rot, float res, std::vector<ArrayXXf>& dists, ArrayXXc& mask) {
+    if (dists.size() < 1 || !ctx()) return;                                // :432
+    const int r = dists[0].rows(), c = dists[0].cols();
+    stage_.resize((size_t)params_.num_classes * r * c);
+    if (!ok(tdr_map_local_cart(ctx(), center.x, center.y, rot, res, r, c, stage_.data(), mask.data()))) return;
+    for (int k = 0; k < params_.num_classes && k < (int)dists.size(); k++)
+      std::copy(stage_.begin() + (size_t)k * r * c, stage_.begin() + (size_t)(k + 1) * r * c, dists[k].d.begin());
+  }
+  Vector2i size() const { return Vector2i{cols_, rows_}; }
+  Vector2i mapCenter() const { return map_center_; }
+  int numClasses() const { return params_.num_classes; }
+  float resolution() const { return params_.resolution; }
+  bool haveMap() const { return have_map_; }
+
+ protected:
+  // after a constructor-path load: host copies of the distance fields for getClassesAtPoint, have_map_ (:62), table
+  void adoptDeviceMap() {
+    int r = 0, c = 0, k = 0; float res = 1;
+    tdr_map_info(ctx(), &r, &c, &k, &res);
+    rows_ = r; cols_ = c;
+    layers_.resize((size_t)k * r * c); mask_.resize((size_t)r * c);
+    ok(tdr_map_get_layers(ctx(), layers_.data(), mask_.data()));
+    have_map_ = true;
+    if (!tab_.empty()) ok(tdr_map_set_polar_table(ctx(), tab_.data(), n_theta_, n_r_));
+  }
+  void write_eig(const std::string& name, const void* data, size_t scalar_bytes) const {
+    std::ofstream out(name, std::ios::out | std::ios::binary | std::ios::trunc);
+    const int64_t rows = rows_, cols = cols_;
+    out.write(reinterpret_cast<const char*>(&rows), 8);
+    out.write(reinterpret_cast<const char*>(&cols), 8);
+    out.write(reinterpret_cast<const char*>(data), (std::streamsize)((size_t)rows * cols * scalar_bytes));
+  }
+  static bool read_eig(const std::string& name, size_t scalar_bytes, std::vector<char>& data, int64_t& rows, int64_t& cols) {
+    std::ifstream in(name, std::ios::in | std::ios::binary);
+    if (!in) return false;
+    in.read(reinterpret_cast<char*>(&rows), 8);
+    in.read(reinterpret_cast<char*>(&cols), 8);
+    if (!in || rows <= 0 || cols <= 0 || rows * cols > (int64_t)1 << 32) return false;
+    data.resize((size_t)rows * cols * scalar_bytes);
+    in.read(data.data(), (std::streamsize)data.size());
+    return (bool)in;
+  }
+  Params params_;
+  bool have_map_ = false;
+  Vector2i map_center_;
+  int rows_ = 0, cols_ = 0, n_theta_ = 0, n_r_ = 0;
+  std::vector<float> layers_, tab_, stage_, binary_;
+  std::vector<uint8_t> mask_;
+};
+
+// top_down_map_polar.h:6-22
+class TopDownMapPolar : public TopDownMap {
+ public:
+  explicit TopDownMapPolar(const Params& params) : TopDownMap(params) { samplePtsPolar(100, 50, (float)(2 * M_PI / 100)); }
   // top_down_map_polar.cpp:21-53
   void getLocalMap(Vector2f center, float scale, float res, std::vector<ArrayXXf>& dists, ArrayXXc& mask) {
     if ((int)dists.size() < params_.num_classes || !ctx()) return;         // :25
@@ -288,48 +370,8 @@ class TopDownMapPolar {
     }
     if (have_map_ && ctx()) ok(tdr_map_set_polar_table(ctx(), tab_.data(), n_theta, n_r));
   }
-  Vector2i size() const { return Vector2i{cols_, rows_}; }
-  Vector2i mapCenter() const { return map_center_; }
-  int numClasses() const { return params_.num_classes; }
-  float resolution() const { return params_.resolution; }
-  bool haveMap() const { return have_map_; }
   int nTheta() const { return n_theta_; }
   int nR() const { return n_r_; }
-
- private:
-  // after a constructor-path load: host copies of the distance fields for getClassesAtPoint, have_map_ (:62), table
-  void adoptDeviceMap() {
-    int r = 0, c = 0, k = 0; float res = 1;
-    tdr_map_info(ctx(), &r, &c, &k, &res);
-    rows_ = r; cols_ = c;
-    layers_.resize((size_t)k * r * c); mask_.resize((size_t)r * c);
-    ok(tdr_map_get_layers(ctx(), layers_.data(), mask_.data()));
-    have_map_ = true;
-    ok(tdr_map_set_polar_table(ctx(), tab_.data(), n_theta_, n_r_));
-  }
-  void write_eig(const std::string& name, const void* data, size_t scalar_bytes) const {
-    std::ofstream out(name, std::ios::out | std::ios::binary | std::ios::trunc);
-    const int64_t rows = rows_, cols = cols_;
-    out.write(reinterpret_cast<const char*>(&rows), 8);
-    out.write(reinterpret_cast<const char*>(&cols), 8);
-    out.write(reinterpret_cast<const char*>(data), (std::streamsize)((size_t)rows * cols * scalar_bytes));
-  }
-  static bool read_eig(const std::string& name, size_t scalar_bytes, std::vector<char>& data, int64_t& rows, int64_t& cols) {
-    std::ifstream in(name, std::ios::in | std::ios::binary);
-    if (!in) return false;
-    in.read(reinterpret_cast<char*>(&rows), 8);
-    in.read(reinterpret_cast<char*>(&cols), 8);
-    if (!in || rows <= 0 || cols <= 0 || rows * cols > (int64_t)1 << 32) return false;
-    data.resize((size_t)rows * cols * scalar_bytes);
-    in.read(data.data(), (std::streamsize)data.size());
-    return (bool)in;
-  }
-  Params params_;
-  bool have_map_ = false;
-  Vector2i map_center_;
-  int rows_ = 0, cols_ = 0, n_theta_ = 0, n_r_ = 0;
-  std::vector<float> layers_, tab_, stage_, binary_;
-  std::vector<uint8_t> mask_;
 };
 
 // active_localizer.h:7-16 / active_localizer.cpp:45-82: the whole candidate search is one call
