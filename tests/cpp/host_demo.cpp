@@ -127,8 +127,23 @@ int main(int argc, char** argv) {
   wr(dir + "metric_states.bin", metric.states().data(), metric.states().size());
   FilterParams fo = fm; fo.init_pos_m_x = 1e6f;
   ParticleFilter off_map(48, &map, fo, (uint32_t)seed + 4);
-  const float misc[5] = {sc_fixed, sc_free, sc_frozen, (float)metric.numParticles(), (float)off_map.numParticles()};
-  wr(dir + "misc.f32", misc, 5);
+  // (d) the mixture the GMM thread fits drives the particle count of every update (particle_filter.cpp:151-158): with one
+  // 10 x 12 px cluster 300 particles shrink to 3/4 + 10 per update; the EM input matrix comes straight off the device
+  ParticleFilter adaptive(300, &map, fp, (uint32_t)seed + 5);
+  adaptive.propagate(trans, 0.01f);
+  auto gs = adaptive.gmmSamples();
+  wr(dir + "gmm_samples.f64", gs.data(), gs.size());
+  wr(dir + "gmm_states.bin", adaptive.states().data(), adaptive.states().size());
+  std::vector<Vector3f> gm(1);
+  std::vector<ParticleFilter::Matrix3f> gcov(1, ParticleFilter::Matrix3f{100, 0, 0, 0, 144, 0, 0, 0, 1});
+  adaptive.setGMM(gm, gcov);
+  adaptive.update(top_down, geo, fmeta[0]);
+  const int n_adapt1 = adaptive.numParticles(), n_states1 = (int)adaptive.states().size();
+  adaptive.update(top_down, geo, fmeta[0]);
+  const int n_adapt2 = adaptive.numParticles(), n_states2 = (int)adaptive.states().size();
+  const float misc[9] = {sc_fixed, sc_free, sc_frozen, (float)metric.numParticles(), (float)off_map.numParticles(),
+                         (float)n_adapt1, (float)n_states1, (float)n_adapt2, (float)n_states2};
+  wr(dir + "misc.f32", misc, 9);
   // ---- the vector-map constructor path and the raster cache (top_down_map.cpp:22-31, :197-224): polygons -> binary class
   // maps -> distance fields on the device; class<i>.png written, then a second map object starts from those files alone.
   // (one device context per process: from here on the device holds THIS map)

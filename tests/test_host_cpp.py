@@ -183,7 +183,7 @@ def check_demo_outputs(d, cm, img, pts, N, seed, device):
     assert same_bits(g0, want_g[0])
 
     # ---- the rest of the ParticleFilter interface: pure host logic over the resident states ----
-    sc_fixed, sc_free, sc_frozen, n_metric, n_off = (float(v) for v in rd(d, "misc.f32", np.float32))
+    sc_fixed, sc_free, sc_frozen, n_metric, n_off, n_ad1, n_st1, n_ad2, n_st2 = (float(v) for v in rd(d, "misc.f32", np.float32))
     assert sc_fixed == 2.0 and sc_free == -1.0                                  # scale(): particle_filter.cpp:358-366
     # (a) updateMap: every init position moves by the map-centre delta (:325-333) — (W/2, H/2) from the initial (0, 0)
     # on the first map message, then (+3, -2); float += int
@@ -219,6 +219,15 @@ def check_demo_outputs(d, cm, img, pts, N, seed, device):
     assert n_metric == 48 and np.array_equal(got_m, ms) and abs(px[0] - fmeta[1]) < 1e-3 and abs(px[1] - fmeta[2]) < 1e-3
     assert np.hypot(got_m["init_x_px"] - fmeta[1], got_m["init_y_px"] - fmeta[2]).max() < 6 * fmeta[3]
     assert n_off == 0
+    # (d) the GMM drives the particle count (:151-158); the EM input matrix (:262-272) off the device
+    cov = np.zeros((1, 4, 4), np.float32)
+    cov[0, 0, 0], cov[0, 1, 1] = 100.0, 144.0
+    assert n_ad1 == n_st1 == orc.adaptive_count(cov, 300, 300) == 235 and n_ad2 == n_st2 == orc.adaptive_count(cov, 235, 300) == 186
+    gst = rd(d, "gmm_states.bin", synth.STATE_DTYPE)
+    gsm = rd(d, "gmm_samples.f64", np.float64).reshape(-1, 4)
+    want_g = orc.gmm_samples(gst, 300)
+    assert len(gst) == 300 and gsm.shape == (300, 4) and np.array_equal(gsm[:, :2], want_g[:, :2])
+    assert np.abs(gsm[:, 2:] - want_g[:, 2:]).max() <= (0.0 if not device else 1e-5)
 
     # ---- vector map -> raster cache -> a second map from the PNG files alone (top_down_map.cpp:22-31, :197-224) ----
     from top_down_renderer_b200 import rastercache

@@ -427,12 +427,13 @@ class ParticleFilter {
     if (!ok(tdr_pf_gmm_samples(ctx(), num_samples, s.data()))) s.clear();
     return s;
   }
-  // particle_filter.cpp:151-158: particle count of the next resampling from the GMM covariances (top-left 2x2 blocks of
-  // row-major 4x4 matrices): sum of sqrt(l0) * sqrt(l1) over the clusters, bounded below by 3/4 of the last count + 10
-  static int adaptiveCount(const std::vector<std::array<float, 16>>& covs, int last_num_particles, int max_num_particles) {
+  // particle_filter.cpp:151-158: particle count of the next resampling from the GMM covariances (the top-left 2x2 block of
+  // every row-major 3x3 Matrix3f): sum of sqrt(l0) * sqrt(l1) over the clusters, bounded below by 3/4 of the last count + 10
+  using Matrix3f = std::array<float, 9>;
+  static int adaptiveCount(const std::vector<Matrix3f>& covs, int last_num_particles, int max_num_particles) {
     int num = 0;
     for (const auto& cv : covs) {
-      const float a = cv[0], b = cv[1], c = cv[4], d = cv[5];
+      const float a = cv[0], b = cv[1], c = cv[3], d = cv[4];
       const float tr = a + d, det = a * d - b * c, disc = tr * tr - 4 * det;
       float e0, e1;
       if (disc >= 0) { const float sq = std::sqrt(disc); e0 = (tr - sq) / 2; e1 = (tr + sq) / 2; } else { e0 = e1 = tr / 2; }
@@ -440,6 +441,11 @@ class ParticleFilter {
     }
     return std::min(std::max(num, 3 * last_num_particles / 4 + 10), max_num_particles);
   }
+  // particle_filter.cpp:238-243.  The mixture itself is fitted by OpenCV's cv::ml::EM in the reference's GMM thread
+  // (:252-318) on the matrix gmmSamples() returns; the adapter keeps that thread and hands the result over with setGMM.
+  // Until a mixture has been set, update() keeps the particle count (the reference fits one before the first update).
+  void setGMM(const std::vector<Vector3f>& means, const std::vector<Matrix3f>& covs) { means_ = means; covs_ = covs; }
+  void getGMM(std::vector<Vector3f>& means, std::vector<Matrix3f>& covs) const { means = means_; covs = covs_; }
   // particle_filter.cpp:94-189.  top_down_geo is accepted and ignored, as in the reference's cost (F10).
   void update(std::vector<ArrayXXf>& top_down_scan, std::vector<ArrayXXf>& /*top_down_geo*/, float res) {
     if (num_particles_ == 0 || !ctx()) return;                             // :96-99
@@ -448,6 +454,7 @@ class ParticleFilter {
     for (int c = 0; c < C; c++) std::copy(top_down_scan[c].d.begin(), top_down_scan[c].d.end(), stage_.begin() + (size_t)c * n_theta * n_r);
     if (!ok(tdr_scan_set_polar_images(ctx(), stage_.data(), n_theta, n_r, C))) return;
     std::uniform_real_distribution<float> dist(0., 1.);
+    if (!covs_.empty()) num_particles_ = adaptiveCount(covs_, num_particles_, max_num_particles_);   // :151-158
     const float u = last_u_ = dist(gen_);                                  // the ONE draw of :172-173
     if (!ok(tdr_pf_update(ctx(), res, u, num_particles_))) return;
     host_dirty_ = true;
@@ -600,6 +607,8 @@ class ParticleFilter {
   float last_u_ = 0.f;
   std::vector<State> states_;
   std::vector<float> last_dist_, stage_, z_;
+  std::vector<Vector3f> means_;
+  std::vector<Matrix3f> covs_;
 };
 
 }  // namespace tdrhost
