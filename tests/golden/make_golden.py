@@ -111,10 +111,37 @@ def widen_mini():
                         poly_layers=layers.astype(np.uint8), **out)
 
 
+INIT_CASES = {"free": dict(fixed_scale=-1.0),
+              "pixel": dict(fixed_scale=2.0, init_pos_px=(101.5, 88.25), init_pos_px_cov=9.0, init_pos_deg_theta=75.0, init_pos_deg_cov=8.0),
+              "metric": dict(fixed_scale=2.0, init_pos_m=(-9.25, 4.125), init_pos_px_cov=5.0)}
+
+
+def init_mini():
+    """particle initialisation on the shared engine (particle_filter.cpp:19-84): states per case + engine outputs used"""
+    Cn, H, W = 4, 180, 240
+    cm = synth.make_class_map(H, W, Cn, seed=31)
+    img, lut = synth.to_cv_image(cm), synth.identity_lut(Cn)
+    layers, _ = orc.compute_dists(orc.class_image_to_layers(img, lut, Cn, 1.0), 1.0)
+    out = {}
+    road = np.argwhere(cm == synth.ROAD)                                   # (y, x) rows of the class map
+    y0, x0 = (int(v) for v in road[np.argmin(np.hypot(road[:, 0] - H * 0.4, road[:, 1] - W * 0.6))])
+    cases = {k: dict(v) for k, v in INIT_CASES.items()}
+    cases["metric"]["init_pos_m"] = ((x0 - W // 2) / 2.0, (y0 - H // 2) / 2.0)
+    cases["pixel"]["init_pos_px"] = (x0 + 0.5, y0 + 0.25)
+    out["metric_m"], out["pixel_px_in"] = np.float32(cases["metric"]["init_pos_m"]), np.float32(cases["pixel"]["init_pos_px"])
+    for name, kw in cases.items():
+        st, frozen, px, used = orc.init_particles(2024, layers, 1.0, (W // 2, H // 2), 70, **kw)
+        assert len(st) == 70, name
+        out[f"{name}_states"], out[f"{name}_used"], out[f"{name}_px"] = st, np.int64(used), np.float32(px)
+        out[f"{name}_u"] = np.float32(orc.uniform_draw(2024, discard=used))
+    np.savez_compressed(os.path.join(HERE, "init_mini.npz"), img=img, lut=lut, num_classes=Cn, **out)
+
+
 if __name__ == "__main__":
     edt_cv2()
     cfg1_mini()
     widen_mini()
+    init_mini()
     for f in sorted(os.listdir(HERE)):
         if f.endswith(".npz"):
             print(f, os.path.getsize(os.path.join(HERE, f)))

@@ -495,3 +495,27 @@ def test_freeze_scale_known_answer():
     for s in st["scale"]:
         f = np.float32(float(f) * math.pow(float(s), 1.0 / 4))      # float accumulator, double pow
     assert np.float32(g) == f
+
+
+def test_init_mini_fixture_reproduces():
+    """tests/golden/init_mini.npz (make_golden.py): three initialisations on the shared engine.  Uniform positions involve
+    no transcendental (bit-exact); Gaussian ones go through glibc's logf (2 ulp between machines); the number of engine
+    outputs consumed — how often the rejection loop ran — and the uniform that follows are exact."""
+    g = np.load(os.path.join(GOLD, "init_mini.npz"))
+    Cn = int(g["num_classes"])
+    layers, _ = orc.compute_dists(orc.class_image_to_layers(g["img"], g["lut"], Cn, 1.0), 1.0)
+    H, W = g["img"].shape
+    from tests.golden.make_golden import INIT_CASES
+    for name, kw in INIT_CASES.items():
+        kw = dict(kw)
+        if name == "metric":
+            kw["init_pos_m"] = tuple(float(v) for v in g["metric_m"])
+        if name == "pixel":
+            kw["init_pos_px"] = tuple(float(v) for v in g["pixel_px_in"])
+        st, frozen, px, used = orc.init_particles(2024, layers, 1.0, (W // 2, H // 2), 70, **kw)
+        want = g[f"{name}_states"]
+        assert len(st) == len(want) == 70 and used == int(g[f"{name}_used"]), name
+        for k in ("init_x_px", "init_y_px", "theta", "scale"):
+            assert _ulps(st[k], want[k]).max() <= (0 if name == "free" and k != "scale" else 2), (name, k)
+        assert np.array_equal(st["have_init"], want["have_init"]) and not st["dx_m"].any() and not st["dy_m"].any()
+        assert np.allclose(px, g[f"{name}_px"]) and orc.uniform_draw(2024, discard=used) == float(g[f"{name}_u"])
