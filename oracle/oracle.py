@@ -262,6 +262,12 @@ def uniform_draw(seed, discard=0):
     return float(lib().orc_uniform_draw_from(C.c_uint32(seed), C.c_uint64(discard)))
 
 
+def engine_peek(seed, discard):
+    """raw 32-bit output number `discard` of std::mt19937(seed)"""
+    lib().orc_engine_peek.restype = C.c_uint32
+    return int(lib().orc_engine_peek(C.c_uint32(seed), C.c_uint64(discard)))
+
+
 def mean_cov(states):
     mean = np.zeros(4, dtype=np.float32)
     cov = np.zeros(16, dtype=np.float32)

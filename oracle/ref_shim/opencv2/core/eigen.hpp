@@ -1,0 +1,3 @@
+// STAND-IN (test infrastructure only), see opencv2/core/core.hpp
+#pragma once
+#include <opencv2/core/core.hpp>

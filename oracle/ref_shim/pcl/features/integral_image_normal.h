@@ -1,0 +1,3 @@
+// STAND-IN (test infrastructure only), see pcl/point_types.h
+#pragma once
+#include <pcl/point_types.h>

@@ -6,15 +6,20 @@
 // file.  Only tests/, __graft_entry__.smoke() and bench.py's cpu_baseline /
 // --impl reference legs use it, and only as the checker / CPU baseline.
 //
-// PARITY UNPINNED: the reference (KumarRobotics/top_down_renderer) ships no
-// tests, golden vectors or fixtures, and it cannot be compiled in this image
-// (every header needs ROS, Eigen, OpenCV C++, PCL, TBB — none installed, no
-// network).  This restatement is therefore pinned only by
-//   * cv2.distanceTransform / cv2.threshold (the real third-party routine the
-//     reference calls, top_down_map.cpp:312,315) — tests/test_oracle_edt.py,
-//   * glibc 2.39 libm (atan2f/sqrtf/roundf — the reference's own libm calls),
-//   * libstdc++ <random> (the reference's own RNG),
-//   * a deliberately naive numpy twin (oracle/numpy_twin.py) and hand KATs.
+// WHAT PINS IT.  The reference (KumarRobotics/top_down_renderer) ships no tests, golden vectors or fixtures, and it
+// cannot be built as shipped in this image (every header needs ROS, Eigen, OpenCV C++, PCL — none installed, no
+// network).  Two kinds of pins exist:
+//   * PINNED AGAINST THE REFERENCE'S OWN SOURCE (oracle/_ref, tests/test_ref_build.py): six of its translation units
+//     (scan_renderer.cpp, scan_renderer_polar.cpp, top_down_map_polar.cpp, state_particle.cpp, particle_filter.cpp,
+//     active_localizer.cpp) compile unmodified against stand-in headers (oracle/ref_shim/) and run beside this file:
+//     rows a1, a2, a7, a9-a13, propagate, initializeParticles, freezeScale, updateMap, getBestRelPos agree bit for bit
+//     except where a value passes through an Eigen reduction (weights: 1e-6 relative; the stand-in sums sequentially).
+//   * PARITY UNPINNED by the reference for src/top_down_map.cpp (rows a3-a6, a8 and the vector-map path: OpenCV / Eigen
+//     expression templates, not compilable here).  Those rows are pinned only by
+//       - cv2.distanceTransform / cv2.threshold (the real third-party routine the reference calls,
+//         top_down_map.cpp:312,315) and cv2.imwrite / imread for the raster cache — tests/test_oracle.py,
+//       - glibc 2.39 libm (atan2f/sqrtf/roundf — the reference's own libm calls),
+//       - a deliberately naive numpy twin (oracle/numpy_twin.py) and hand KATs.
 // Build contract being restated: g++ -O2, no -march (x86-64 baseline, SSE2
 // 4-float Eigen packets, no FMA, no SSE3 hadd), -ffp-contract=off, Eigen
 // 3.3/3.4 reduction orders where an order must be chosen.
@@ -640,6 +645,12 @@ ORC_API float orc_uniform_draw(uint32_t seed) {
   std::mt19937 gen(seed);
   std::uniform_real_distribution<float> shift_dist(0., 1.);
   return shift_dist(gen);
+}
+// raw output number `discard` of std::mt19937(seed): where a shared engine stands after `discard` outputs were consumed
+ORC_API uint32_t orc_engine_peek(uint32_t seed, uint64_t discard) {
+  std::mt19937 gen(seed);
+  gen.discard(discard);
+  return (uint32_t)gen();
 }
 // the same draw from the shared engine after `discard` earlier outputs
 ORC_API float orc_uniform_draw_from(uint32_t seed, uint64_t discard) {

@@ -1,0 +1,234 @@
+"""The oracle against the REFERENCE'S OWN SOURCE.  Six translation units of the reference (scan_renderer.cpp,
+scan_renderer_polar.cpp, top_down_map_polar.cpp, state_particle.cpp, particle_filter.cpp, active_localizer.cpp) are
+compiled unmodified from /root/reference/src against stand-in headers for the libraries this image lacks
+(oracle/ref_shim/, see its README.md) into oracle/_ref/libtdr_ref.so; these tests run the reference's classes beside the
+oracle on the same inputs and the same seeded engine.
+
+What comes out bit for bit: class images, polar gathers, particle initialisation, propagate, resampled states, pose —
+everything whose arithmetic is the reference's own statements plus libm / libstdc++.  What is held to a tolerance:
+values that pass through an Eigen reduction (.sum()), because the stand-in reduces sequentially while Eigen (and the
+oracle, which restates Eigen's SSE2 order) associates differently — 1e-6 relative, ten times tighter than the contract.
+CPU only; skipped where neither /root/reference nor a prebuilt oracle/_ref exists."""
+import math
+
+import numpy as np
+import pytest
+
+from oracle import oracle as orc
+from oracle import refbuild as ref
+from top_down_renderer_b200 import synth
+
+pytestmark = pytest.mark.skipif(not ref.available(), reason="no /root/reference and no prebuilt oracle/_ref")
+ANG = np.float32(2 * math.pi / 100)
+C_ = 4
+
+
+def same_bits(a, b):
+    return a.shape == b.shape and np.array_equal(a.view(np.uint32), b.view(np.uint32))
+
+
+@pytest.fixture(scope="module")
+def world():
+    cm = synth.make_class_map(260, 300, C_, seed=21)
+    img, lut = synth.to_cv_image(cm), synth.identity_lut(C_)
+    seeds = orc.class_image_to_layers(img, lut, C_, 1.0)
+    layers, mask = orc.compute_dists(seeds, 1.0)
+    geo, _ = orc.compute_dists(orc.geo_raster(seeds), 1.0)
+    pose, heading = synth.default_pose(cm, seed=21)
+    pts = synth.make_scan(cm, pose, heading, seed=21, n_rings=32, n_az=256)
+    tab = orc.polar_table(100, 25, ANG, 1.0)
+    H, W = cm.shape
+    m = ref.Map(layers, mask, 1.0, tab, 100, 25, geo=geo, center=(W // 2, H // 2))
+    thetas, shifts = orc.search_list(100)
+    return dict(cm=cm, lut=lut, layers=layers, mask=mask, geo=geo, pose=pose, heading=heading, pts=pts, tab=tab, H=H, W=W, map=m,
+                thetas=thetas, shifts=shifts, scan=orc.render_polar(pts, 1.5, ANG, 100, 25, lut, C_))
+
+
+# ---- a1 / a2: ScanRendererPolar / ScanRenderer::renderSemanticTopDown ----------------------------------------------
+@pytest.mark.parametrize("res", [0.5, 1.5, 4.0])
+def test_class_images_equal_the_reference_renderers(world, res):
+    pts = world["pts"].copy()
+    pts[::17, :2] = 0                                           # dropped returns: x == 0 && y == 0 is skipped
+    pts[5::23, 4] = 7                                           # a class the lut maps to -1
+    lut = np.full(256, -1, dtype=np.int32)                      # every intensity the scan holds must index the lut: the
+    lut[:C_] = np.arange(C_)                                    # reference reads flatten_lut_[pt_class] unchecked (:103-104)
+    got = ref.render_polar(pts, res, ANG, 100, 25, lut, C_)
+    assert np.array_equal(got, orc.render_polar(pts, res, ANG, 100, 25, lut, C_)) and got.sum() > 1000
+    cart = ref.render_cart(pts, res, 48, 64, lut, C_)
+    assert np.array_equal(cart, orc.render_cart(pts, res, 48, 64, lut, C_).reshape(cart.shape)) and cart.sum() > 100
+
+
+# ---- a7: TopDownMapPolar::getLocalMap / getLocalGeoMap ----------------------------------------------------------------
+def test_polar_gather_equals_the_reference(world):
+    w = world
+    rng = np.random.default_rng(1)
+    centres = [(150.3, 120.8), (2.0, 3.0), (299.6, 259.4), (-40.0, 100.0), (-5000.0, -5000.0), (149.5, 130.5)]
+    centres += [tuple(rng.uniform(-20, 320, 2)) for _ in range(10)]
+    for k, (cx, cy) in enumerate(centres):
+        scale, res = (2.0, 1.5) if k % 2 else (1.3, 4.0)
+        d, m = w["map"].local_map_polar(cx, cy, scale, res)
+        do, mo = orc.local_map_polar(w["layers"], w["mask"], 1.0, w["tab"], cx, cy, scale, res)
+        assert same_bits(d, do.reshape(d.shape)) and np.array_equal(m, mo.reshape(m.shape)), (cx, cy)
+        g = w["map"].local_geo_polar(cx, cy, scale, res)
+        go, _ = orc.local_map_polar(w["geo"], np.zeros_like(w["mask"]), 1.0, w["tab"], cx, cy, scale, res)
+        assert same_bits(g, go.reshape(g.shape))
+
+
+def _tracking_kwargs(w):
+    return dict(fixed_scale=2.0, init_pos_px=(float(w["pose"][0]), float(w["pose"][1])), init_pos_px_cov=6.0,
+                init_pos_deg_theta=math.degrees(w["heading"]), init_pos_deg_cov=3.0)
+
+
+# ---- the whole filter step on ONE shared engine: initializeParticles -> propagate -> update -> pose ------------------
+def test_filter_step_equals_the_reference(world):
+    w = world
+    W, H, seed, N = w["W"], w["H"], 77, 500
+    kw = _tracking_kwargs(w)
+    f = ref.Filter(w["map"], N, seed, regularization=0.7, pos_cov=0.15, theta_cov=0.004, **kw)
+    # initializeParticles (particle_filter.cpp:19-84, state_particle.cpp:3-49): states and engine position
+    st0, _, _ = f.get()
+    so, frozen, px, used = orc.init_particles(seed, w["layers"], 1.0, (W // 2, H // 2), N, **kw)
+    assert len(st0) == N and np.array_equal(st0, so) and f.scale_frozen() == frozen and f.scale() == 2.0
+    assert f.engine_peek() == orc.engine_peek(seed, used)
+    # propagate (:86-92, state_particle.cpp:57-78)
+    f.propagate(0.4, 0.05, 0.01)
+    st1, ld1, _ = f.get()
+    want, last_o, _, used_p = orc.propagate(so, 0.4, 0.05, 0.01, True, 0.15, 0.004, seed, discard=used)
+    assert np.array_equal(st1, want) and same_bits(ld1, last_o) and (ld1 > 0).all()
+    assert f.engine_peek() == orc.engine_peek(seed, used + used_p)
+    # the mixture the count of the next resampling comes from (:151-158); fitted on this thread from the propagated set
+    samples, _, covs = f.gmm()
+    assert np.array_equal(samples, orc.gmm_samples(st1, min(1000, N)))         # the EM input matrix (:262-272)
+    cov4 = np.zeros((1, 4, 4), np.float32)
+    cov4[0, :3, :3] = covs[0]
+    M = orc.adaptive_count(cov4, N, N)
+    # update (:94-189): raw weights, normalised weights, resampled states
+    f.update(w["scan"], 1.5)
+    scored, ld_s, raw = f.get(scored_set=True)
+    assert same_bits(ld_s, ld1)
+    fp = orc.make_params(C_, regularization=0.7, map_width=W, map_height=H)
+    st_o = st1.copy()
+    raw_o = orc.score_all(st_o, fp, w["layers"], w["mask"], 1.0, w["tab"], 100, 25, w["scan"], 1.5, w["thetas"], w["shifts"])
+    assert not np.isnan(raw).any() and np.max(np.abs(raw - raw_o) / raw_o) <= 1e-6
+    assert np.array_equal(scored, st_o)                                         # theta / have_init as the reference left them
+    wn = f.weights()
+    wn_o, arg_o, _ = orc.normalize(raw.copy(), ld_s)                            # stage-wise: the reference's own raw weights
+    assert np.max(np.abs(wn - wn_o) / wn_o) <= 1e-6 and int(np.argmax(wn)) == arg_o
+    cur, _, _ = f.get()
+    assert f.num_particles() == len(cur) == M and M < N
+    u = orc.uniform_draw(seed, discard=used + used_p)                           # the ONE draw of :172-173, next on the engine
+    assert np.array_equal(cur, scored[orc.resample_fast(wn, u, M)])             # indices: bit-exact on the reference's weights
+    assert np.array_equal(orc.resample_fast(wn, u, M), orc.resample_literal(wn, u, M))
+    assert f.engine_peek() == orc.engine_peek(seed, used + used_p + 1)
+    # pose (:191-236)
+    mean, cov, ml, cov_ml = f.pose()
+    mo, co = orc.mean_cov(cur)
+    assert same_bits(mean, mo) and same_bits(cov.reshape(-1), co.reshape(-1))
+    mlo, _ = orc.ml_cov(scored, int(np.argmax(wn)))
+    assert same_bits(ml, mlo)
+    both = np.concatenate([scored[int(np.argmax(wn)):][:1], cur])               # computeCov: the current set about the ML pose
+    _, cmo = orc.ml_cov(both, 0)
+    assert np.allclose(cov_ml.reshape(-1) * (len(cur) - 1), cmo.reshape(-1) * len(cur), rtol=1e-5, atol=1e-5)
+
+
+# ---- global localisation: free scale, no heading -> the 40-candidate theta search, the scale gate, NaN weights ----------
+def test_theta_search_and_gates_equal_the_reference(world):
+    w = world
+    W, H, seed, N = w["W"], w["H"], 5, 400
+    f = ref.Filter(w["map"], N, seed, regularization=0.7, fixed_scale=-1.0, scale_log_min=-0.1, scale_log_max=0.65, force_on_map=True)
+    st0, _, _ = f.get()
+    so, frozen, _, used = orc.init_particles(seed, w["layers"], 1.0, (W // 2, H // 2), N, fixed_scale=-1.0)
+    assert np.array_equal(st0, so) and not frozen and f.scale() == -1.0 and (st0["have_init"] == 0).all()
+    # push a few particles off the map (force_on_map gate) and onto unknown ground before the update
+    st0["dx_m"][:7] = 1e4
+    f.set(st0)
+    f.propagate(0.2, 0.0, 0.0)                                                  # scale jitter on: four draws per particle
+    st1, ld1, _ = f.get()
+    want, last_o, _, used_p = orc.propagate(st0, 0.2, 0.0, 0.0, False, 0.3, 0.0314, seed, discard=used)
+    assert np.array_equal(st1, want) and same_bits(ld1, last_o)
+    f.update(w["scan"], 1.5)
+    scored, ld_s, raw = f.get(scored_set=True)
+    fp = orc.make_params(C_, regularization=0.7, fixed_scale=-1.0, force_on_map=True, map_width=W, map_height=H)
+    fp.scale_log_min, fp.scale_log_max = -0.1, 0.65
+    st_o = st1.copy()
+    raw_o = orc.score_all(st_o, fp, w["layers"], w["mask"], 1.0, w["tab"], 100, 25, w["scan"], 1.5, w["thetas"], w["shifts"])
+    assert np.array_equal(np.isnan(raw), np.isnan(raw_o)) and np.array_equal(raw == 0, raw_o == 0)
+    assert (raw[:7] == 0).all() and (raw == 0).sum() > 7                        # off the map; scale outside 10^[-0.1, 0.65]
+    ok = ~np.isnan(raw) & (raw != 0)
+    assert ok.sum() > 100 and np.max(np.abs(raw[ok] - raw_o[ok]) / raw_o[ok]) <= 1e-6
+    # the heading each particle chose: the first strict minimum over 40 candidates; a different summation order can only
+    # flip near-ties
+    searched = ok | np.isnan(raw)
+    assert (scored["have_init"][searched] == 1).all() and (scored["have_init"][raw == 0] == 0).all()
+    assert (scored["theta"][searched] == st_o["theta"][searched]).mean() >= 0.99
+    wn = f.weights()
+    wn_o, _, _ = orc.normalize(raw.copy(), ld_s)
+    assert np.allclose(wn, wn_o, rtol=1e-6, atol=0) and not np.isnan(wn).any()
+    # freezeScale (:343-357) on the resampled set
+    cur, _, _ = f.get()
+    f.freeze_scale()
+    froz, _, _ = f.get()
+    fo, g = orc.freeze_scale(cur)
+    assert np.array_equal(froz, fo) and f.scale_frozen() and f.scale() == np.float32(g)
+
+
+def test_nan_weights_take_the_mean_minus_lower_deviation(world):
+    """particles whose polar footprint is mostly unknown get NaN (state_particle.cpp:117-120) and the normalisation
+    replaces it by mean - bottom_stddev (particle_filter.cpp:107-134): the reference's loops against the oracle's"""
+    w = world
+    W, H, seed, N = w["W"], w["H"], 9, 300
+    kw = _tracking_kwargs(w)
+    f = ref.Filter(w["map"], N, seed, regularization=0.7, **kw)
+    st, _, _ = f.get()
+    st["init_x_px"][::5] = -150.0                                               # footprints hanging off the map edge
+    st["init_y_px"][1::7] = H + 120.0
+    ld = np.random.default_rng(3).uniform(0, 0.4, N).astype(np.float32)
+    f.set(st, ld)
+    f.update(w["scan"], 1.5)
+    scored, ld_s, raw = f.get(scored_set=True)
+    assert same_bits(ld_s, ld) and 20 < np.isnan(raw).sum() < N - 50
+    fp = orc.make_params(C_, regularization=0.7, map_width=W, map_height=H)
+    raw_o = orc.score_all(st.copy(), fp, w["layers"], w["mask"], 1.0, w["tab"], 100, 25, w["scan"], 1.5, w["thetas"], w["shifts"])
+    assert np.array_equal(np.isnan(raw), np.isnan(raw_o))
+    wn = f.weights()
+    wn_o, arg_o, stats = orc.normalize(raw.copy(), ld_s)
+    assert stats[5] == 0 and not np.isnan(wn).any() and np.max(np.abs(wn - wn_o) / wn_o) <= 1e-6
+
+
+# ---- ParticleFilter::updateMap, the metric initial position ------------------------------------------------------------
+def test_map_centre_shift_and_metric_initial_position(world):
+    w = world
+    W, H = w["W"], w["H"]
+    kw = _tracking_kwargs(w)
+    f = ref.Filter(w["map"], 64, 3, **kw)
+    a, _, _ = f.get()
+    f.update_map((W // 2 + 3, H // 2 - 2))                                      # last_map_center_ starts at (0, 0) (:12)
+    b, _, _ = f.get()
+    fl = np.float32
+    assert same_bits(b["init_x_px"], a["init_x_px"] + fl(W // 2 + 3)) and same_bits(b["init_y_px"], a["init_y_px"] + fl(H // 2 - 2))
+    f.update_map((W // 2, H // 2))
+    c, _, _ = f.get()
+    assert same_bits(c["init_x_px"], b["init_x_px"] + fl(-3)) and same_bits(c["init_y_px"], b["init_y_px"] + fl(2))
+    # metric position relative to the map centre (:27-54)
+    m_xy = ((float(w["pose"][0]) - W // 2) / 2.0, (float(w["pose"][1]) - H // 2) / 2.0)
+    kw2 = dict(kw, init_pos_px=(-1.0, -1.0), init_pos_m=m_xy)
+    g = ref.Filter(w["map"], 48, 11, **kw2)
+    got, _, _ = g.get()
+    so, _, px, used = orc.init_particles(11, w["layers"], 1.0, (W // 2, H // 2), 48, **kw2)
+    assert len(got) == 48 and np.array_equal(got, so) and g.init_px() == px and g.engine_peek() == orc.engine_peek(11, used)
+    off = ref.Filter(w["map"], 48, 12, **dict(kw2, init_pos_m=(1e5, 0.0)))
+    assert off.count() == 0 and off.num_particles() == 0
+    assert len(orc.init_particles(12, w["layers"], 1.0, (W // 2, H // 2), 48, **dict(kw2, init_pos_m=(1e5, 0.0)))[0]) == 0
+    off.update(w["scan"], 1.5)                                                  # no particles: returns at once (:96-99)
+    assert off.count() == 0
+
+
+# ---- ActiveLocalizer::getBestRelPos ------------------------------------------------------------------------------------
+def test_active_localizer_equals_the_reference(world):
+    w = world
+    rng = np.random.default_rng(3)
+    for n in (1, 2, 4):
+        preds = np.stack([rng.uniform(0.2, 0.8, n) * w["W"], rng.uniform(0.2, 0.8, n) * w["H"], rng.uniform(-3, 3, n)], axis=1).astype(np.float32)
+        rel = w["map"].active_best_rel_pos(preds)
+        rel_o, _ = orc.active_best_rel_pos(w["layers"], w["mask"], 1.0, w["tab"], 100, 25, preds)
+        assert rel == rel_o, (n, rel, rel_o)
