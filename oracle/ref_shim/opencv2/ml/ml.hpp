@@ -13,7 +13,8 @@ class EM {
   void setCovarianceMatrixType(int) {}
   void setClustersNumber(int) {}
   bool trainEM(const Mat& samples, Mat& likelihoods, Mat& labels) {
-    last_samples_ = samples;                      // exposed to the harness: the matrix computeGMM built
+    last_samples_ = Mat(samples.rows, samples.cols, CV_64F);   // a copy for the harness: the matrix computeGMM built
+    std::memcpy(last_samples_.data, samples.data, samples.total() * 8);
     const int n = samples.rows, k = samples.cols;
     means_ = Mat(1, k, CV_64F); cov_ = Mat(k, k, CV_64F);
     for (int i = 0; i < n; i++) for (int j = 0; j < k; j++) means_.at<double>(0, j) += samples.at<double>(i, j) / n;

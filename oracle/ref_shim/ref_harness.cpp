@@ -1,6 +1,6 @@
 // ref_harness.cpp — TEST INFRASTRUCTURE ONLY: a C interface over the reference's OWN classes, built from the reference's
-// unmodified sources (scan_renderer.cpp, scan_renderer_polar.cpp, top_down_map_polar.cpp, state_particle.cpp,
-// particle_filter.cpp, active_localizer.cpp under /root/reference/src) against the stand-in headers of this directory.
+// unmodified sources (scan_renderer.cpp, scan_renderer_polar.cpp, top_down_map.cpp, top_down_map_polar.cpp,
+// state_particle.cpp, particle_filter.cpp, active_localizer.cpp under /root/reference/src) against the stand-in headers of this directory.
 // tests/test_ref_build.py drives it beside the oracle.  See README.md here for what this does and does not pin.
 #include "top_down_render/scan_renderer_polar.h"
 #include "top_down_render/particle_filter.h"
@@ -74,6 +74,89 @@ REF_API void ref_active_best_rel_pos(void* map, const float* preds, int n, float
   for (int i = 0; i < n; i++) p.push_back(Eigen::Vector3f(preds[3 * i], preds[3 * i + 1], preds[3 * i + 2]));
   Eigen::Vector2f best = al.getBestRelPos(p);
   rel[0] = best[0]; rel[1] = best[1];
+}
+
+// ---- a3 - a6, a8, the vector map and the caches: src/top_down_map.cpp itself -------------------------------------------
+static TopDownMap::Params make_params(int C, float resolution, const int* lut, int n_lut) {
+  TopDownMap::Params p;
+  p.num_classes = C; p.resolution = resolution;
+  if (lut) p.flatten_lut.assign(lut, lut + n_lut);
+  return p;
+}
+// the dynamic-map path: TopDownMapPolar(params) then updateMap(image, centre) (top_down_render.cpp:81, :591)
+REF_API void* ref_map_from_class_image(const uint8_t* img, int h, int w, int stride, const int* lut, int n_lut, int C, float resolution,
+                                       int center_x, int center_y) {
+  auto* m = new TopDownMapPolar(make_params(C, resolution, lut, n_lut));
+  std::vector<uint8_t> packed((size_t)h * w);
+  for (int r = 0; r < h; r++) std::memcpy(&packed[(size_t)r * w], img + (size_t)r * stride, (size_t)w);
+  m->updateMap(cv::Mat(h, w, CV_8UC1, packed.data()), Eigen::Vector2i(center_x, center_y));
+  return m;
+}
+// the static-map constructor (top_down_map.cpp:9-64): cache hit -> loadCachedMaps; `.svg` -> loadSvg (nanosvg, vendored in
+// the reference), getRasterMap, saveRasterizedMaps; a directory -> loadRasterizedMaps; then geo maps, computeDists,
+// saveCachedMaps.  home: what $HOME is set to for the cache directory.  class_colors: packed fill colour per class index.
+REF_API void* ref_map_from_path(const char* home, const char* map_path, const int* lut, int n_lut, int C, float resolution,
+                                const uint32_t* class_colors, const int* exclusive, int n_excl) {
+  setenv("HOME", home, 1);
+  TopDownMap::Params p = make_params(C, resolution, lut, n_lut);
+  p.map_path = map_path;
+  p.color_lut.packed.assign(class_colors, class_colors + n_lut);
+  p.exclusive_classes.assign(exclusive, exclusive + n_excl);
+  return new TopDownMapPolar(p);
+}
+REF_API void ref_map_info(void* map, int* rows, int* cols, int* C, int* have_map, int* center_xy) {
+  auto* m = static_cast<TopDownMapPolar*>(map);
+  *rows = m->class_maps_.empty() ? 0 : (int)m->class_maps_[0].rows();
+  *cols = m->class_maps_.empty() ? 0 : (int)m->class_maps_[0].cols();
+  *C = (int)m->class_maps_.size(); *have_map = m->haveMap() ? 1 : 0;
+  center_xy[0] = m->mapCenter()[0]; center_xy[1] = m->mapCenter()[1];
+}
+REF_API void ref_map_get(void* map, float* layers, uint8_t* mask, float* geo) {
+  auto* m = static_cast<TopDownMapPolar*>(map);
+  if (layers) copy_out(m->class_maps_, layers);
+  if (mask) std::memcpy(mask, m->class_mask_.data(), (size_t)m->class_mask_.size());
+  if (geo && m->geo_maps_.size() == 2) copy_out(m->geo_maps_, geo);
+}
+// what the static constructor does after loading (:47-58), for a map that came through updateMap: geo maps + their distances
+REF_API void ref_map_build_geo(void* map) {
+  auto* m = static_cast<TopDownMapPolar*>(map);
+  // updateMap leaves class_maps_ as DISTANCE fields; getGeoRasterMap wants the binary maps, which the caller re-installs
+  m->geo_maps_.clear();
+  for (size_t i = 0; i < 2; i++) m->geo_maps_.push_back(Eigen::ArrayXXf(m->class_maps_[0].rows(), m->class_maps_[0].cols()));
+  m->getGeoRasterMap(m->geo_maps_);
+  Eigen::ArrayXXc tmp;
+  m->computeDists(m->geo_maps_, tmp);
+}
+REF_API void ref_map_set_class_maps(void* map, const float* layers, int rows, int cols, int C) {
+  static_cast<TopDownMapPolar*>(map)->class_maps_ = make_imgs(C, rows, cols, layers);
+}
+REF_API void ref_map_polar_table(void* map, int n_theta, int n_r, float ang_res, float* tab) {
+  auto* m = static_cast<TopDownMapPolar*>(map);
+  m->samplePtsPolar(Eigen::Vector2i(n_theta, n_r), ang_res);
+  std::memcpy(tab, m->ang_sample_pts_.data(), (size_t)2 * n_theta * n_r * 4);
+}
+REF_API void ref_map_set_polar_table(void* map, const float* tab, int n_theta, int n_r) {
+  auto* m = static_cast<TopDownMapPolar*>(map);
+  m->ang_sample_pts_ = Eigen::Array2Xf(2, n_theta * n_r);
+  std::memcpy(m->ang_sample_pts_.data(), tab, (size_t)2 * n_theta * n_r * 4);
+}
+REF_API unsigned ref_map_classes_at(void* map, int as_float, float x, float y) {
+  auto* m = static_cast<TopDownMapPolar*>(map);
+  std::vector<int> cls;
+  if (as_float) m->TopDownMap::getClassesAtPoint(Eigen::Vector2f(x, y), cls);
+  else m->TopDownMap::getClassesAtPoint(Eigen::Vector2i((int)x, (int)y), cls);
+  unsigned bits = 0;
+  for (int c : cls) bits |= 1u << c;
+  return bits;
+}
+// a8: the Cartesian TopDownMap::getLocalMap (hidden by the polar overloads: called through the base class)
+REF_API void ref_map_local_cart(void* map, float cx, float cy, float rot, float res, int rows, int cols, float* dists, uint8_t* mask) {
+  auto* m = static_cast<TopDownMapPolar*>(map);
+  auto v = make_imgs(m->numClasses(), rows, cols);
+  Eigen::ArrayXXc k(rows, cols);
+  static_cast<TopDownMap*>(m)->getLocalMap(Eigen::Vector2f(cx, cy), rot, res, v, k);
+  copy_out(v, dists);
+  std::memcpy(mask, k.data(), (size_t)rows * cols);
 }
 
 // ---- a9 - a13 and the rows around them: ParticleFilter ------------------------------------------------------------------
@@ -156,8 +239,10 @@ REF_API void ref_filter_pose(void* fv, float mean[4], float cov_mean[16], float 
 REF_API void ref_filter_freeze_scale(void* fv) { static_cast<ParticleFilter*>(fv)->freezeScale(); }
 REF_API float ref_filter_scale(void* fv) { return static_cast<ParticleFilter*>(fv)->scale(); }
 REF_API int ref_filter_scale_frozen(void* fv) { return static_cast<ParticleFilter*>(fv)->isScaleFrozen() ? 1 : 0; }
-REF_API void ref_filter_update_map(void* fv, int center_x, int center_y) {
-  static_cast<ParticleFilter*>(fv)->updateMap(cv::Mat(), Eigen::Vector2i(center_x, center_y));
+// ParticleFilter::updateMap (:320-341) with a class-index image; the filter's map must carry a flatten_lut
+REF_API void ref_filter_update_map(void* fv, const uint8_t* img, int h, int w, int center_x, int center_y) {
+  std::vector<uint8_t> copy(img, img + (size_t)h * w);
+  static_cast<ParticleFilter*>(fv)->updateMap(cv::Mat(h, w, CV_8UC1, copy.data()), Eigen::Vector2i(center_x, center_y));
 }
 REF_API void ref_filter_init_px(void* fv, float px[2]) {
   auto* f = static_cast<ParticleFilter*>(fv);

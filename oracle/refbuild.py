@@ -1,6 +1,6 @@
-"""TEST INFRASTRUCTURE ONLY — `oracle/_ref/libtdr_ref.so`: six translation units of the reference compiled UNMODIFIED
-from /root/reference/src (scan_renderer.cpp, scan_renderer_polar.cpp, top_down_map_polar.cpp, state_particle.cpp,
-particle_filter.cpp, active_localizer.cpp) against the stand-in headers in oracle/ref_shim/ (the reference's real
+"""TEST INFRASTRUCTURE ONLY — `oracle/_ref/libtdr_ref.so`: seven translation units of the reference compiled UNMODIFIED
+from /root/reference/src (scan_renderer.cpp, scan_renderer_polar.cpp, top_down_map.cpp, top_down_map_polar.cpp,
+state_particle.cpp, particle_filter.cpp, active_localizer.cpp) against the stand-in headers in oracle/ref_shim/ (the reference's real
 dependencies — ROS, Eigen, OpenCV, PCL — are not installed), behind the C interface of oracle/ref_shim/ref_harness.cpp.
 oracle/ref_shim/README.md says what that pins and what it cannot.  The library is built only where /root/reference
 exists (this container); the prebuilt file travels to the GPU box.  Nothing outside tests/ loads it."""
@@ -18,7 +18,7 @@ from .oracle import STATE_DTYPE
 _HERE = os.path.dirname(os.path.abspath(__file__))
 SO = os.path.join(_HERE, "_ref", "libtdr_ref.so")
 REFERENCE = "/root/reference"
-UNITS = ["scan_renderer", "scan_renderer_polar", "top_down_map_polar", "state_particle", "particle_filter", "active_localizer"]
+UNITS = ["scan_renderer", "scan_renderer_polar", "top_down_map", "top_down_map_polar", "state_particle", "particle_filter", "active_localizer"]
 
 
 def available() -> bool:
@@ -52,6 +52,9 @@ def lib():
     if _lib is None:
         _lib = C.CDLL(build())
         _lib.ref_map_create.restype = C.c_void_p
+        _lib.ref_map_from_class_image.restype = C.c_void_p
+        _lib.ref_map_from_path.restype = C.c_void_p
+        _lib.ref_map_classes_at.restype = C.c_uint
         _lib.ref_filter_create.restype = C.c_void_p
         for name in ("ref_filter_count", "ref_filter_get", "ref_filter_weights"):
             getattr(_lib, name).restype = C.c_long
@@ -86,7 +89,80 @@ def render_cart(pts, res, rows, cols, lut, num_classes):
 
 
 class Map:
-    """TopDownMapPolar with the oracle's distance fields / mask / offset table installed (inputs of this build)"""
+    """TopDownMapPolar.  Map(...) installs given distance fields / mask / offset table (inputs); Map.from_class_image and
+    Map.from_path run the reference's own map code (top_down_map.cpp) on an image / a map file."""
+
+    @classmethod
+    def _wrap(cls, handle, n_theta, n_r):
+        self = cls.__new__(cls)
+        self.h = C.c_void_p(handle)
+        self.n_theta, self.n_r = n_theta, n_r
+        self.rows, self.cols, self.C, _, _ = self.info()
+        return self
+
+    @classmethod
+    def from_class_image(cls, img, lut, num_classes, resolution, center=(0, 0), n_theta=100, n_r=25):
+        """TopDownMapPolar(params) + updateMap(image, centre): loadCompressedRasterMap + computeDists (:116-157, :289-326)"""
+        img = np.ascontiguousarray(img, dtype=np.uint8)
+        lut = np.ascontiguousarray(lut, dtype=np.int32)
+        h = lib().ref_map_from_class_image(_p(img, _u8p), img.shape[0], img.shape[1], img.shape[1], _p(lut, _i32p), len(lut),
+                                           int(num_classes), C.c_float(resolution), int(center[0]), int(center[1]))
+        return cls._wrap(h, n_theta, n_r)
+
+    @classmethod
+    def from_path(cls, home, map_path, lut, num_classes, resolution, class_colors, exclusive=(), n_theta=100, n_r=25):
+        """the static-map constructor (:9-64) with $HOME = home for ~/.ros/xview_cache"""
+        lut = np.ascontiguousarray(lut, dtype=np.int32)
+        col = np.ascontiguousarray(class_colors, dtype=np.uint32)
+        ex = np.ascontiguousarray(exclusive, dtype=np.int32)
+        assert len(col) == len(lut)
+        h = lib().ref_map_from_path(home.encode(), map_path.encode(), _p(lut, _i32p), len(lut), int(num_classes), C.c_float(resolution),
+                                    col.ctypes.data_as(C.POINTER(C.c_uint32)), _p(ex, _i32p), len(ex))
+        return cls._wrap(h, n_theta, n_r)
+
+    def info(self):
+        r, c, k, have = C.c_int(0), C.c_int(0), C.c_int(0), C.c_int(0)
+        ctr = (C.c_int * 2)()
+        lib().ref_map_info(self.h, C.byref(r), C.byref(c), C.byref(k), C.byref(have), ctr)
+        return r.value, c.value, k.value, bool(have.value), (ctr[0], ctr[1])
+
+    def get(self, want_geo=False):
+        """-> (class_maps_ (C, cols, rows), class_mask_ (cols, rows)[, geo_maps_ (2, cols, rows)])"""
+        rows, cols, k, _, _ = self.info()
+        layers, mask = np.zeros((k, cols, rows), dtype=np.float32), np.zeros((cols, rows), dtype=np.uint8)
+        geo = np.zeros((2, cols, rows), dtype=np.float32) if want_geo else None
+        lib().ref_map_get(self.h, _p(layers, _f32p), _p(mask, _u8p), _p(geo, _f32p) if want_geo else None)
+        return (layers, mask, geo) if want_geo else (layers, mask)
+
+    def build_geo_from_binary(self, binary_layers):
+        """getGeoRasterMap + computeDists (:410-427, :47-58) on the given binary class maps; the distance fields are put back"""
+        dist, _ = self.get()
+        b = np.ascontiguousarray(binary_layers, dtype=np.float32)
+        lib().ref_map_set_class_maps(self.h, _p(b, _f32p), self.rows, self.cols, self.C)
+        lib().ref_map_build_geo(self.h)
+        lib().ref_map_set_class_maps(self.h, _p(dist, _f32p), self.rows, self.cols, self.C)
+        return self.get(want_geo=True)[2]
+
+    def polar_table(self, n_theta, n_r, ang_res):
+        """samplePtsPolar (top_down_map_polar.cpp:7-19) through samplePts (top_down_map.cpp:367-389)"""
+        tab = np.zeros(2 * n_theta * n_r, dtype=np.float32)
+        lib().ref_map_polar_table(self.h, n_theta, n_r, C.c_float(ang_res), _p(tab, _f32p))
+        self.n_theta, self.n_r = n_theta, n_r
+        return tab.reshape(-1, 2)
+
+    def set_polar_table(self, tab, n_theta, n_r):
+        t = np.ascontiguousarray(tab, dtype=np.float32).reshape(-1)
+        lib().ref_map_set_polar_table(self.h, _p(t, _f32p), n_theta, n_r)
+        self.n_theta, self.n_r = n_theta, n_r
+
+    def classes_at(self, x, y, as_float=False):
+        bits = lib().ref_map_classes_at(self.h, int(as_float), C.c_float(x), C.c_float(y))
+        return [c for c in range(self.C) if bits >> c & 1]
+
+    def local_map_cart(self, cx, cy, rot, res, rows, cols):
+        d, m = np.zeros((self.C, cols, rows), dtype=np.float32), np.zeros((cols, rows), dtype=np.uint8)
+        lib().ref_map_local_cart(self.h, C.c_float(cx), C.c_float(cy), C.c_float(rot), C.c_float(res), rows, cols, _p(d, _f32p), _p(m, _u8p))
+        return d, m
 
     def __init__(self, layers, mask, resolution, tab, n_theta, n_r, geo=None, center=(0, 0)):
         layers = np.ascontiguousarray(layers, dtype=np.float32)
@@ -178,8 +254,9 @@ class Filter:
     def scale_frozen(self):
         return bool(lib().ref_filter_scale_frozen(self.h))
 
-    def update_map(self, center):
-        lib().ref_filter_update_map(self.h, int(center[0]), int(center[1]))
+    def update_map(self, img, center):
+        img = np.ascontiguousarray(img, dtype=np.uint8)
+        lib().ref_filter_update_map(self.h, _p(img, _u8p), img.shape[0], img.shape[1], int(center[0]), int(center[1]))
 
     def init_px(self):
         px = np.zeros(2, dtype=np.float32)

@@ -9,17 +9,18 @@
 // WHAT PINS IT.  The reference (KumarRobotics/top_down_renderer) ships no tests, golden vectors or fixtures, and it
 // cannot be built as shipped in this image (every header needs ROS, Eigen, OpenCV C++, PCL — none installed, no
 // network).  Two kinds of pins exist:
-//   * PINNED AGAINST THE REFERENCE'S OWN SOURCE (oracle/_ref, tests/test_ref_build.py): six of its translation units
-//     (scan_renderer.cpp, scan_renderer_polar.cpp, top_down_map_polar.cpp, state_particle.cpp, particle_filter.cpp,
-//     active_localizer.cpp) compile unmodified against stand-in headers (oracle/ref_shim/) and run beside this file:
-//     rows a1, a2, a7, a9-a13, propagate, initializeParticles, freezeScale, updateMap, getBestRelPos agree bit for bit
-//     except where a value passes through an Eigen reduction (weights: 1e-6 relative; the stand-in sums sequentially).
-//   * PARITY UNPINNED by the reference for src/top_down_map.cpp (rows a3-a6, a8 and the vector-map path: OpenCV / Eigen
-//     expression templates, not compilable here).  Those rows are pinned only by
-//       - cv2.distanceTransform / cv2.threshold (the real third-party routine the reference calls,
-//         top_down_map.cpp:312,315) and cv2.imwrite / imread for the raster cache — tests/test_oracle.py,
+//   * PINNED AGAINST THE REFERENCE'S OWN SOURCE (oracle/_ref, tests/test_ref_build.py): the seven translation units of
+//     the hot path (scan_renderer.cpp, scan_renderer_polar.cpp, top_down_map.cpp, top_down_map_polar.cpp,
+//     state_particle.cpp, particle_filter.cpp, active_localizer.cpp) compile unmodified against stand-in headers
+//     (oracle/ref_shim/) and run beside this file: every row of SURVEY 8a and the widened rows agree bit for bit, except
+//     where a value passes through an Eigen reduction (weights: 1e-6 relative; the stand-in sums sequentially).
+//   * NOT PINNED BY THAT BUILD — whatever is decided inside the absent third-party libraries — and pinned instead by
+//       - cv2.distanceTransform / cv2.threshold (the real routine the reference calls, top_down_map.cpp:312,315) and
+//         cv2.imwrite / imread for the raster cache — tests/test_oracle.py, tests/test_host_math.py,
 //       - glibc 2.39 libm (atan2f/sqrtf/roundf — the reference's own libm calls),
-//       - a deliberately naive numpy twin (oracle/numpy_twin.py) and hand KATs.
+//       - a deliberately naive numpy twin (oracle/numpy_twin.py) and hand KATs;
+//     Eigen's SIMD reduction order, its packet cos/sin and the assertion-free meaning of samplePts' shape-mismatched
+//     assignment are restated from Eigen's published sources and stay unpinned.
 // Build contract being restated: g++ -O2, no -march (x86-64 baseline, SSE2
 // 4-float Eigen packets, no FMA, no SSE3 hadd), -ffp-contract=off, Eigen
 // 3.3/3.4 reduction orders where an order must be chosen.

@@ -40,7 +40,7 @@ def world():
     H, W = cm.shape
     m = ref.Map(layers, mask, 1.0, tab, 100, 25, geo=geo, center=(W // 2, H // 2))
     thetas, shifts = orc.search_list(100)
-    return dict(cm=cm, lut=lut, layers=layers, mask=mask, geo=geo, pose=pose, heading=heading, pts=pts, tab=tab, H=H, W=W, map=m,
+    return dict(cm=cm, img=img, seeds=seeds, lut=lut, layers=layers, mask=mask, geo=geo, pose=pose, heading=heading, pts=pts, tab=tab, H=H, W=W, map=m,
                 thetas=thetas, shifts=shifts, scan=orc.render_polar(pts, 1.5, ANG, 100, 25, lut, C_))
 
 
@@ -200,13 +200,17 @@ def test_map_centre_shift_and_metric_initial_position(world):
     w = world
     W, H = w["W"], w["H"]
     kw = _tracking_kwargs(w)
-    f = ref.Filter(w["map"], 64, 3, **kw)
+    own = ref.Map.from_class_image(w["img"], w["lut"], C_, 1.0, center=(W // 2, H // 2))     # updateMap replaces the layers
+    own.set_polar_table(w["tab"], 100, 25)
+    f = ref.Filter(own, 64, 3, **kw)
     a, _, _ = f.get()
-    f.update_map((W // 2 + 3, H // 2 - 2))                                      # last_map_center_ starts at (0, 0) (:12)
+    assert np.array_equal(a, orc.init_particles(3, w["layers"], 1.0, (W // 2, H // 2), 64, **kw)[0])
+    f.update_map(w["img"], (W // 2 + 3, H // 2 - 2))                            # last_map_center_ starts at (0, 0) (:12)
     b, _, _ = f.get()
     fl = np.float32
     assert same_bits(b["init_x_px"], a["init_x_px"] + fl(W // 2 + 3)) and same_bits(b["init_y_px"], a["init_y_px"] + fl(H // 2 - 2))
-    f.update_map((W // 2, H // 2))
+    assert own.info()[4] == (W // 2 + 3, H // 2 - 2)
+    f.update_map(w["img"], (W // 2, H // 2))
     c, _, _ = f.get()
     assert same_bits(c["init_x_px"], b["init_x_px"] + fl(-3)) and same_bits(c["init_y_px"], b["init_y_px"] + fl(2))
     # metric position relative to the map centre (:27-54)
@@ -232,3 +236,130 @@ def test_active_localizer_equals_the_reference(world):
         rel = w["map"].active_best_rel_pos(preds)
         rel_o, _ = orc.active_best_rel_pos(w["layers"], w["mask"], 1.0, w["tab"], 100, 25, preds)
         assert rel == rel_o, (n, rel, rel_o)
+
+
+# ---- src/top_down_map.cpp itself: a3 - a6, a8, the vector map, both caches -----------------------------------------------
+@pytest.mark.parametrize("resolution", [1.0, 0.5, 2.0])
+def test_distance_fields_equal_the_reference_map_code(world, resolution):
+    """TopDownMap::updateMap = loadCompressedRasterMap + computeDists from the reference's source; cv::distanceTransform
+    itself is the stand-in's exact transform (OpenCV's values, pinned by cv2 elsewhere) — what is checked here is
+    everything AROUND it: the flipped / scaled sampling of the image, the lut, the unknown mask built from uint8 sums,
+    the 8-bit conversion, x resolution, truncation at 50, zeroing under the mask"""
+    w = world
+    m = ref.Map.from_class_image(w["img"], w["lut"], C_, resolution, center=(7, -3))
+    layers, mask = m.get()
+    seeds = orc.class_image_to_layers(w["img"], w["lut"], C_, resolution)
+    lo, mo = orc.compute_dists(seeds, resolution)
+    assert layers.shape == lo.shape and same_bits(layers, lo) and np.array_equal(mask, mo)
+    rows, cols, k, have, centre = m.info()
+    assert (rows, cols) == orc.map_dims(w["H"], w["W"], resolution) and k == C_ and have and centre == (7, -3)
+    # getGeoRasterMap + computeDists (:410-427, :47-58)
+    geo = m.build_geo_from_binary(seeds)
+    go, _ = orc.compute_dists(orc.geo_raster(seeds), resolution)
+    assert same_bits(geo, go)
+    # getClassesAtPoint, both overloads (:159-175; the float one divides by the resolution twice)
+    rng = np.random.default_rng(2)
+    for _ in range(200):
+        x, y = (float(v) for v in rng.uniform(-10, max(w["W"], w["H"]) + 10, 2))
+        assert m.classes_at(x, y) == orc.classes_at_point(lo, resolution, int(x), int(y))
+        assert m.classes_at(x, y, as_float=True) == orc.classes_at_point(lo, resolution, int(np.float32(x) / np.float32(resolution)),
+                                                                         int(np.float32(y) / np.float32(resolution)))
+
+
+def test_map_without_a_non_road_cell_is_not_a_map(world):
+    """the isZero(0) test of updateMap (:150) runs on the BINARY layer 1: all road -> have_map_ stays false"""
+    img = np.full((40, 50), 1, dtype=np.uint8)
+    assert not ref.Map.from_class_image(img, world["lut"], C_, 1.0).info()[3]
+    img[3, 4] = 2
+    assert ref.Map.from_class_image(img, world["lut"], C_, 1.0).info()[3]
+
+
+def test_polar_table_and_cartesian_gather_through_sample_pts(world):
+    """samplePts (:367-389) assigns a replicated LinSpaced row to strided maps of another shape — defined only with
+    Eigen's assertions off; the stand-in implements the reading the oracle restates (destination (i, j) <- row[j mod n]),
+    so this checks the code AROUND that reading: strides, rotation, centre offsets, the polar post-processing, rounding"""
+    w = world
+    for (nt, nr) in ((100, 25), (100, 50), (36, 7)):
+        ang = np.float32(2 * math.pi / nt)
+        for resolution in (1.0, 0.5):
+            m = ref.Map.from_class_image(w["img"], w["lut"], C_, resolution)
+            assert same_bits(m.polar_table(nt, nr, ang), orc.polar_table(nt, nr, ang, resolution).reshape(-1, 2))
+    m = ref.Map.from_class_image(w["img"], w["lut"], C_, 1.0)
+    for (cx, cy, rot, res, rows, cols) in [(150.0, 130.0, 0.0, 1.0, 50, 50), (20.3, 250.1, 0.7, 2.0, 40, 31), (217.8, 99.2, -2.1, 0.5, 33, 64)]:
+        d, k = m.local_map_cart(cx, cy, rot, res, rows, cols)
+        do, ko = orc.local_map_cart(w["layers"], w["mask"], 1.0, cx, cy, rot, res, rows, cols)
+        assert same_bits(d, do.reshape(d.shape)) and np.array_equal(k, ko.reshape(k.shape)), (cx, cy, rot)
+
+
+SVG_W, SVG_H = 230, 170
+SVG_SHAPES = [("#101010", [(-5, -5), (240, -5), (240, 180), (-5, 180)]),                                        # class 0: background
+              ("#2040c0", [(20.25, 30.5), (200.75, 35.25), (205.0, 60.75), (120.5, 55.5), (110.25, 140.75), (80.75, 139.25), (85.5, 52.5), (18.75, 58.25)]),
+              ("#c04020", [(150.25, 90.25), (190.75, 90.25), (190.75, 130.75), (150.25, 130.75)]),
+              ("#20c040", [(60.25, 100.5), (100.5, 70.25), (140.75, 110.5), (95.25, 160.75)]),
+              ("#20c040", [(200.5, 120.25), (260.0, 125.5), (250.25, 200.0), (190.5, 190.25)])]
+SVG_CLASS_HEX = ["#101010", "#2040c0", "#c04020", "#20c040"]
+
+
+def _write_svg(path):
+    body = "".join(f'<polygon fill="{col}" points="{" ".join(f"{x},{y}" for x, y in pts)}"/>\n' for col, pts in SVG_SHAPES)
+    with open(path, "w") as f:
+        f.write(f'<svg xmlns="http://www.w3.org/2000/svg" width="{SVG_W}" height="{SVG_H}">\n{body}</svg>\n')
+
+
+def _packed(hexcol):                                          # what loadSvg compares with nanosvg's 0xBBGGRR (:80-86)
+    r, g, b = int(hexcol[1:3], 16), int(hexcol[3:5], 16), int(hexcol[5:7], 16)
+    return b << 16 | g << 8 | r
+
+
+def test_static_map_constructor_svg_raster_cache_and_eig_cache(tmp_path):
+    """the reference's static-map constructor (:9-64) end to end on an svg file: nanosvg (vendored in the reference) ->
+    loadSvg -> getRasterMap / samplePts / getClasses -> saveRasterizedMaps -> geo maps -> computeDists -> saveCachedMaps;
+    then again from the .eig cache, and once more from the raster cache directory — against the oracle's polygon
+    rasteriser and this repository's readers of both cache formats"""
+    from top_down_renderer_b200 import eigcache, rastercache
+    home = tmp_path / "home"
+    (home / ".ros").mkdir(parents=True)
+    svg = str(tmp_path / "campus.svg")
+    _write_svg(svg)
+    lut = np.arange(C_, dtype=np.int32)
+    colors = [_packed(c) for c in SVG_CLASS_HEX]
+    excl = [0, 1]
+    m = ref.Map.from_path(str(home), svg, lut, C_, 1.0, colors, exclusive=excl)
+    layers, mask, geo = m.get(want_geo=True)
+    # the oracle on the same polygons (y flipped as loadSvg does, :89), in class order
+    cls_of = {c: i for i, c in enumerate(SVG_CLASS_HEX)}
+    polys = [np.float32([(x, SVG_H - y) for x, y in pts]) for _, pts in SVG_SHAPES]
+    pcls = [cls_of[col] for col, _ in SVG_SHAPES]
+    order = sorted(range(len(polys)), key=lambda i: pcls[i])
+    binl = orc.raster_polygons([polys[i] for i in order], [pcls[i] for i in order], SVG_W, SVG_H, 0.0, 1.0, C_, excl)
+    lo, mo = orc.compute_dists(binl, 1.0)
+    assert layers.shape == (C_, SVG_W, SVG_H) and same_bits(layers, lo) and np.array_equal(mask, mo)
+    go, _ = orc.compute_dists(orc.geo_raster(binl), 1.0)
+    assert same_bits(geo, go)
+    assert all((binl[c] == 0).any() and (binl[c] == 1).any() for c in range(C_))
+    # the raster cache the reference wrote (cv::imwrite through the stand-in's PNG codec): this repository's reader
+    cache = str(tmp_path / "campus_raster_cache")
+    assert np.array_equal(rastercache.load_rasterized_maps(cache, C_), binl)
+    # the .eig cache it wrote: metadata + distance fields, geo, mask — this repository's reader
+    xc = str(home / ".ros" / "xview_cache")
+    assert eigcache.cache_is_valid(xc, svg, C_, 1.0)
+    c_layers, c_geo, c_mask = eigcache.load_cache(xc, C_)
+    assert same_bits(c_layers, lo) and same_bits(c_geo, go) and np.array_equal(c_mask, mo)
+    # second construction: a cache hit (loadCacheMetaData + loadCachedMaps); a cache written by THIS repository loads too
+    again = ref.Map.from_path(str(home), svg, lut, C_, 1.0, colors, exclusive=excl)
+    l2, m2, g2 = again.get(want_geo=True)
+    assert same_bits(l2, lo) and same_bits(g2, go) and np.array_equal(m2, mo) and again.info()[3]
+    home2 = tmp_path / "home2"
+    (home2 / ".ros" / "xview_cache").mkdir(parents=True)
+    eigcache.save_cache(str(home2 / ".ros" / "xview_cache"), "some/other/map.svg", lo, go, mo, 1.0)
+    ours = ref.Map.from_path(str(home2), "some/other/map.svg", lut, C_, 1.0, colors, exclusive=excl)
+    l3, m3, g3 = ours.get(want_geo=True)
+    assert same_bits(l3, lo) and same_bits(g3, go) and np.array_equal(m3, mo)
+    # third: the raster cache directory as the map path (loadRasterizedMaps :213-224), written by THIS repository
+    home3 = tmp_path / "home3"
+    (home3 / ".ros").mkdir(parents=True)
+    own_cache = str(tmp_path / "own_raster_cache")
+    rastercache.save_rasterized_maps(own_cache, binl)
+    ras = ref.Map.from_path(str(home3), own_cache, lut, C_, 1.0, colors, exclusive=excl)
+    l4, m4 = ras.get()
+    assert same_bits(l4, lo) and np.array_equal(m4, mo)
