@@ -15,7 +15,9 @@ GPU), the map / scan are replicated, and ONE all-gather of (weights + states) pe
 normalise + order-exact prefix done redundantly on every rank (bit-exact indices independent of N).
 
 Rank 0 prints ONE JSON line (see the driver contract).  `--impl reference` times the CPU restatement of
-the reference (oracle/, all host threads) on bounded samples of the same workload instead.
+the reference (oracle/, all host threads) on bounded samples of the same workload instead.  The partial build of
+the reference's own sources (oracle/_ref) is a correctness pin only: against stand-in Eigen headers and on one
+thread it is 4x slower per thread than the restatement, which therefore is the conservative CPU arm (kind "port").
 """
 from __future__ import annotations
 
