@@ -107,3 +107,64 @@ def test_filter_step_equals_the_reference_build(rw):
     r_mean, _, _, _ = f.pose()
     assert abs(mean[0] - r_mean[0]) <= 0.002 and abs(mean[1] - r_mean[1]) <= 0.002
     assert abs(mean[2] - r_mean[2]) <= math.radians(0.01) and mean[3] == r_mean[3]
+
+
+def test_ref_mini_fixture_through_the_c_abi():
+    """tests/golden/ref_mini.npz — arrays computed by the reference's own classes (tests/golden/make_ref_golden.py) — against
+    the CUDA path; needs neither the reference nor its build on the GPU box"""
+    import os
+    from top_down_renderer_b200.core import Context
+    g = np.load(os.path.join(os.path.dirname(os.path.abspath(__file__)), "golden", "ref_mini.npz"))
+    Cn, res, ang = int(g["num_classes"]), float(g["res"]), g["ang_res"]
+    N = len(g["propagated"])
+    thetas, shifts = orc.search_list(N_THETA)
+    c = Context(0)
+    try:
+        c.map_set_class_image(g["img"], g["lut"], Cn, 1.0)
+        layers, mask = c.map_get_layers()
+        assert np.array_equal(layers.view(np.uint32), g["layers"].view(np.uint32)) and np.array_equal(mask, g["mask"])      # a3, a4
+        c.map_set_polar_table(g["tab"], N_THETA, N_R)
+        c.scan_set_lut(g["lut"], Cn)
+        c.scan_set_points(g["pts"])
+        assert np.array_equal(c.scan_render_polar(res, ang, N_THETA, N_R), g["scan"])                                       # a1
+        assert np.array_equal(c.scan_render_cart(res, 40, 56), g["cart"])                                                   # a2
+        d, m = c.map_local_polar(g["centres"], 2.0, res)                                                                    # a7
+        for i in range(len(g["centres"])):
+            assert np.array_equal(np.asarray(m[i]).reshape(-1), g["local_m"][i].reshape(-1)), i
+            assert np.array_equal(np.asarray(d[i]).reshape(-1).view(np.uint32), g["local_d"][i].reshape(-1).view(np.uint32)), i
+        c.pf_set_params(Cn, regularization=0.7)
+        c.pf_set_search(thetas, shifts)
+        c.scan_set_polar_images(g["scan"])
+        c.pf_set_states(g["propagated"], g["last_dist"])
+        w = c.pf_score(res)                                                                                                 # a9, a10
+        assert rel_err(w, g["raw"]).max() <= 1.1e-5          # 1e-5 to Eigen's order + the reference build's sequential sums (1e-6)
+        c.pf_set_states(g["scored"], g["last_dist"])
+        c.pf_set_weights(g["raw"])
+        c.pf_normalize()                                                                                                    # a11
+        assert rel_err(c.pf_get_weights(N), g["weights_norm"]).max() <= 1e-6
+        # a12: the uniform is the engine output the reference consumed next: generate_canonical<float, 24> of it
+        u = np.float32(int(g["engine_peek"][1])) / np.float32(4294967296.0)
+        assert u < 1
+        M = len(g["resampled"])
+        c.pf_set_states(g["scored"], g["last_dist"])
+        c.pf_set_weights(g["weights_norm"])
+        c.pf_resample(float(u), M)
+        new = c.pf_get_states()
+        assert len(new) == M
+        for k in ("init_x_px", "init_y_px", "dx_m", "dy_m", "theta", "scale", "have_init"):
+            assert np.array_equal(new[k], g["resampled"][k]), k
+        mean, _, _, _ = c.pf_pose(want_ml=False)                                                                            # a13
+        assert abs(mean[0] - g["mean"][0]) <= 0.002 and abs(mean[1] - g["mean"][1]) <= 0.002
+        assert abs(mean[2] - g["mean"][2]) <= math.radians(0.01)
+        # the search set: force_on_map / NaN / all-NaN search (weight 1 / (FLT_MAX + reg), a denormal)
+        c.pf_set_params(Cn, regularization=0.7, force_on_map=True)
+        c.pf_set_states(g["search_in"], g["search_last_dist"])
+        sw = c.pf_score(res)
+        r = g["search_raw"]
+        assert np.array_equal(np.isnan(sw), np.isnan(r)) and np.array_equal(sw == 0, r == 0)
+        assert rel_err(sw, r).max() <= 1.1e-5
+        got = c.pf_get_states()
+        assert np.array_equal(got["have_init"], g["search_scored"]["have_init"])
+        assert (got["theta"] == g["search_scored"]["theta"]).mean() >= 0.95       # near-ties between candidates may flip with the summation order
+    finally:
+        c.close()

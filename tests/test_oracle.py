@@ -3,6 +3,7 @@
 twin, hand-computed known answers, and domain properties."""
 import math
 import os
+import sys
 import zlib
 
 import numpy as np
@@ -519,3 +520,67 @@ def test_init_mini_fixture_reproduces():
             assert _ulps(st[k], want[k]).max() <= (0 if name == "free" and k != "scale" else 2), (name, k)
         assert np.array_equal(st["have_init"], want["have_init"]) and not st["dx_m"].any() and not st["dy_m"].any()
         assert np.allclose(px, g[f"{name}_px"]) and orc.uniform_draw(2024, discard=used) == float(g[f"{name}_u"])
+
+
+# ---- the committed fixture computed by the REFERENCE'S OWN SOURCE (tests/golden/make_ref_golden.py, oracle/_ref) --------
+def test_ref_mini_fixture_from_the_reference_build():
+    """every array of tests/golden/ref_mini.npz was produced by the reference's classes compiled from /root/reference/src
+    (oracle/ref_shim/README.md).  The oracle reproduces it: bit for bit everywhere except the weights, which pass through
+    Eigen reductions that build sums sequentially (1e-6 relative).  Unlike tests/test_ref_build.py this needs neither the
+    reference nor its build, so it also runs wherever only the repository travels."""
+    g = np.load(os.path.join(GOLD, "ref_mini.npz"))
+    Cn, res, ang = int(g["num_classes"]), float(g["res"]), g["ang_res"]
+    img, lut, pts = g["img"], g["lut"], g["pts"]
+    H, W = img.shape
+    bits = lambda a, b: a.shape == b.shape and np.array_equal(a.view(np.uint32), b.view(np.uint32))   # noqa: E731
+    layers, mask = orc.compute_dists(orc.class_image_to_layers(img, lut, Cn, 1.0), 1.0)
+    assert bits(layers, g["layers"]) and np.array_equal(mask, g["mask"])                      # a3, a4
+    tab = orc.polar_table(100, 25, ang, 1.0)
+    assert bits(tab.reshape(-1), g["tab"].reshape(-1))                                         # a6 (libm cos / sin on both sides)
+    scan = orc.render_polar(pts, res, ang, 100, 25, lut, Cn)
+    assert np.array_equal(scan, g["scan"])                                                     # a1
+    assert np.array_equal(orc.render_cart(pts, res, 40, 56, lut, Cn).reshape(g["cart"].shape), g["cart"])   # a2
+    for c, d_ref, m_ref in zip(g["centres"], g["local_d"], g["local_m"]):                      # a7
+        d, m = orc.local_map_polar(layers, mask, 1.0, tab, c[0], c[1], 2.0, res)
+        assert bits(d.reshape(d_ref.shape), d_ref) and np.array_equal(m.reshape(m_ref.shape), m_ref)
+    # initializeParticles -> propagate -> update on one engine
+    sys.path.insert(0, GOLD)
+    from make_ref_golden import FILTER, KW, MOTION, N, SEED
+    kw = dict(KW, init_pos_px=tuple(float(v) for v in g["init_px"]), init_pos_deg_theta=float(g["init_theta_deg"]))
+    st0, frozen, _, used = orc.init_particles(SEED, layers, 1.0, (W // 2, H // 2), N, **kw)
+    assert np.array_equal(st0, g["init_states"]) and frozen and orc.engine_peek(SEED, used) == int(g["engine_peek"][0])
+    st1, ld1, _, used_p = orc.propagate(st0, *MOTION, True, FILTER["pos_cov"], FILTER["theta_cov"], SEED, discard=used)
+    assert np.array_equal(st1, g["propagated"]) and bits(ld1, g["last_dist"]) and orc.engine_peek(SEED, used + used_p) == int(g["engine_peek"][1])
+    assert np.array_equal(orc.gmm_samples(st1, N), g["gmm_samples"])
+    thetas, shifts = orc.search_list(100)
+    fp = orc.make_params(Cn, regularization=FILTER["regularization"], map_width=W, map_height=H)
+    st_o = st1.copy()
+    raw = orc.score_all(st_o, fp, layers, mask, 1.0, tab, 100, 25, scan, res, thetas, shifts)
+    assert np.max(np.abs(raw - g["raw"]) / g["raw"]) <= 1e-6 and np.array_equal(st_o, g["scored"])          # a9, a10
+    wn, arg, _ = orc.normalize(g["raw"].copy(), ld1)                                           # a11 on the reference's raw weights
+    assert np.max(np.abs(wn - g["weights_norm"]) / g["weights_norm"]) <= 1e-6
+    cov4 = np.zeros((1, 4, 4), np.float32)
+    cov4[0, :3, :3] = g["gmm_cov"]
+    M = orc.adaptive_count(cov4, N, N)
+    assert M == len(g["resampled"])
+    u = orc.uniform_draw(SEED, discard=used + used_p)
+    idx = orc.resample_fast(g["weights_norm"], u, M)                                           # a12 on the reference's weights
+    assert np.array_equal(g["scored"][idx], g["resampled"]) and np.array_equal(idx, orc.resample_literal(g["weights_norm"], u, M))
+    assert orc.engine_peek(SEED, used + used_p + 1) == int(g["engine_peek"][2])
+    mean, cov = orc.mean_cov(g["resampled"])                                                   # a13
+    assert bits(mean, g["mean"]) and bits(cov.reshape(-1), g["cov"].reshape(-1))
+    ml, _ = orc.ml_cov(g["scored"], int(np.argmax(g["weights_norm"])))
+    assert bits(ml, g["ml"])
+    # the search set: gates (weight 0), a NaN heading-known particle, the all-NaN search (1 / (FLT_MAX + reg), a denormal)
+    fp2 = orc.make_params(Cn, regularization=0.7, force_on_map=True, map_width=W, map_height=H)
+    s_o = g["search_in"].copy()
+    s_raw = orc.score_all(s_o, fp2, layers, mask, 1.0, tab, 100, 25, scan, res, thetas, shifts)
+    r = g["search_raw"]
+    assert np.array_equal(np.isnan(s_raw), np.isnan(r)) and np.isnan(r).sum() == 4 and np.array_equal(s_raw == 0, r == 0) and (r == 0).sum() == 18
+    tiny = r < 1e-30
+    assert (tiny & (r > 0)).sum() >= 3 and np.array_equal(s_raw[tiny & (r > 0)], r[tiny & (r > 0)])
+    ok = ~np.isnan(r) & ~tiny
+    assert np.max(np.abs(s_raw[ok] - r[ok]) / r[ok]) <= 1e-6
+    assert np.array_equal(s_o["have_init"], g["search_scored"]["have_init"]) and (s_o["theta"] == g["search_scored"]["theta"]).mean() >= 0.98
+    s_wn, _, _ = orc.normalize(r.copy(), g["search_last_dist"])
+    assert np.allclose(s_wn, g["search_weights_norm"], rtol=1e-6, atol=1e-12) and not np.isnan(g["search_weights_norm"]).any()
