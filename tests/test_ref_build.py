@@ -363,3 +363,84 @@ def test_static_map_constructor_svg_raster_cache_and_eig_cache(tmp_path):
     ras = ref.Map.from_path(str(home3), own_cache, lut, C_, 1.0, colors, exclusive=excl)
     l4, m4 = ras.get()
     assert same_bits(l4, lo) and np.array_equal(m4, mo)
+
+
+# ---- ties and specials: where two implementations of the same loop usually part ways -----------------------------------
+def test_class_images_at_bin_boundaries_and_special_coordinates(world):
+    """points on the rounding boundaries of the angular / radial / Cartesian bins (+- a few ulp), NaN and infinite
+    coordinates, the (0, 0) return: the reference's float -> int conversions (x86 cvttss2si: NaN / overflow -> INT_MIN)
+    against the oracle's restatement of them"""
+    rng = np.random.default_rng(5)
+    n = 60000
+    pts = np.zeros((n, 8), dtype=np.float32)
+    k = rng.integers(-51, 52, n)
+    th = (k + 0.5) * float(ANG) + rng.normal(0, 2e-6, n)
+    kr = rng.integers(0, 27, n)
+    r = (kr + 0.5) * 4.0 + rng.normal(0, 2e-5, n)
+    pts[:, 0] = (r * np.sin(th)).astype(np.float32)
+    pts[:, 1] = (r * np.cos(th)).astype(np.float32)
+    half = n // 2                                                 # second half: Cartesian cell boundaries
+    pts[half:, 0] = ((rng.integers(-40, 40, n - half) + 0.5) * 1.5 + rng.normal(0, 1e-6, n - half)).astype(np.float32)
+    pts[half:, 1] = ((rng.integers(-30, 30, n - half) + 0.5) * 1.5 + rng.normal(0, 1e-6, n - half)).astype(np.float32)
+    pts[:, 4] = rng.integers(0, C_ + 2, n).astype(np.float32)    # classes 4, 5 map to -1
+    pts[:10, 0] = np.nan
+    pts[10:20, 1] = np.inf
+    pts[20:30, 0] = -np.inf
+    pts[30:40, 0:2] = 0
+    pts[40:50, 0] = 3e38
+    lut = np.full(256, -1, dtype=np.int32)
+    lut[:C_] = np.arange(C_)
+    for res in (4.0, 1.5):
+        a, b = ref.render_polar(pts, res, ANG, 100, 25, lut, C_), orc.render_polar(pts, res, ANG, 100, 25, lut, C_)
+        assert np.array_equal(a, b) and a.sum() > 10000
+        a, b = ref.render_cart(pts, res, 61, 81, lut, C_), orc.render_cart(pts, res, 61, 81, lut, C_)
+        assert np.array_equal(a, b.reshape(a.shape)) and a.sum() > 10000
+
+
+def test_polar_gather_at_pixel_boundaries(world):
+    """centres and scales that put many lattice points exactly on x.5 pixel boundaries (round half away from zero), on the
+    map border and just outside it"""
+    w = world
+    for cx, cy, scale, res in [(0.0, 0.0, 1.0, 1.0), (100.5, 80.5, 1.0, 0.5), (299.5, 259.5, 2.0, 0.25), (-0.5, -0.5, 1.0, 1.0),
+                               (150.0, 130.0, 0.5, 1.0), (w["W"] - 0.5, 10.0, 1.0, 2.0), (1e6, 1e6, 2.0, 4.0), (float("nan"), 5.0, 2.0, 4.0)]:
+        d, m = w["map"].local_map_polar(cx, cy, scale, res)
+        do, mo = orc.local_map_polar(w["layers"], w["mask"], 1.0, w["tab"], cx, cy, scale, res)
+        assert same_bits(d, do.reshape(d.shape)) and np.array_equal(m, mo.reshape(m.shape)), (cx, cy, scale, res)
+
+
+@pytest.mark.parametrize("seed,N,motion", [(101, 64, (0.0, 0.0, 0.0)), (202, 333, (1.5, -0.7, 0.2)), (303, 1000, (0.05, 0.0, -0.01))])
+def test_filter_steps_over_seeds_sizes_and_motions(world, seed, N, motion):
+    """two consecutive propagate + update steps (the second on the resampled, adaptively sized set), several seeds"""
+    w = world
+    W, H = w["W"], w["H"]
+    kw = _tracking_kwargs(w)
+    f = ref.Filter(w["map"], N, seed, regularization=0.7, pos_cov=0.3, theta_cov=0.0314, **kw)
+    st, frozen, _, used = orc.init_particles(seed, w["layers"], 1.0, (W // 2, H // 2), N, **kw)
+    fp = orc.make_params(C_, regularization=0.7, map_width=W, map_height=H)
+    for step in range(2):
+        f.propagate(*motion)
+        st, ld, _, used_p = orc.propagate(st, *motion, True, 0.3, 0.0314, seed, discard=used)
+        used += used_p
+        got, got_ld, _ = f.get()
+        assert np.array_equal(got, st) and same_bits(got_ld, ld), step
+        _, _, covs = f.gmm()
+        cov4 = np.zeros((1, 4, 4), np.float32)
+        cov4[0, :3, :3] = covs[0]
+        M = orc.adaptive_count(cov4, len(st), N)
+        f.update(w["scan"], 1.5)
+        scored, _, raw = f.get(scored_set=True)
+        st_o = st.copy()
+        raw_o = orc.score_all(st_o, fp, w["layers"], w["mask"], 1.0, w["tab"], 100, 25, w["scan"], 1.5, w["thetas"], w["shifts"])
+        assert np.array_equal(np.isnan(raw), np.isnan(raw_o)) and np.allclose(raw, raw_o, rtol=1e-6, atol=0, equal_nan=True)
+        wn = f.weights()
+        wn_o, _, _ = orc.normalize(raw.copy(), ld)
+        assert np.allclose(wn, wn_o, rtol=1e-6, atol=0)
+        u = orc.uniform_draw(seed, discard=used)
+        used += 1
+        cur, _, _ = f.get()
+        assert len(cur) == M == f.num_particles()
+        st = scored[orc.resample_fast(wn, u, M)]
+        assert np.array_equal(cur, st) and f.engine_peek() == orc.engine_peek(seed, used), step
+    mean, cov, _, _ = f.pose()
+    mo, co = orc.mean_cov(st)
+    assert same_bits(mean, mo) and same_bits(cov.reshape(-1), co.reshape(-1))
