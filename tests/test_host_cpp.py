@@ -262,6 +262,25 @@ def test_host_mirror_logic_on_the_cpu_standin(tmp_path):
     assert r.returncode == 0, r.stdout + r.stderr
     assert "No map received for input loc" in r.stderr            # the off-map filter said why it stayed empty
     check_demo_outputs(d, cm, img, pts, 800, 5, device=False)
+    # ... and the reference's OWN ParticleFilter (oracle/_ref: its sources compiled against stand-in headers) seeded alike:
+    # the mirror's initialisation + propagate reproduce it bit for bit
+    from oracle import refbuild as ref
+    if ref.available():
+        fmeta = rd(d, "meta.f32", np.float32)
+        H, W = cm.shape
+        rmap = ref.Map.from_class_image(img, synth.identity_lut(4), 4, 1.0, center=(W // 2, H // 2))
+        rmap.set_polar_table(orc.polar_table(100, 25, np.float32(2 * math.pi / 100), 1.0), 100, 25)
+        f = ref.Filter(rmap, 800, 5, regularization=0.7, pos_cov=0.15, theta_cov=0.004, fixed_scale=2.0,
+                       init_pos_px=(float(fmeta[1]), float(fmeta[2])), init_pos_px_cov=float(fmeta[3]),
+                       init_pos_deg_theta=float(fmeta[4]), init_pos_deg_cov=float(fmeta[5]))
+        f.propagate(0.4, 0.05, 0.01)
+        r_st, r_ld, _ = f.get()
+        assert np.array_equal(r_st, rd(d, "states_before.bin", synth.STATE_DTYPE)) and same_bits(r_ld, rd(d, "last_dist.f32", np.float32))
+        # its update draws the same uniform next
+        f.update(orc.render_polar(pts, 2.0, np.float32(2 * math.pi / 100), 100, 25, synth.identity_lut(4), 4), 2.0)
+        _, _, r_raw = f.get(scored_set=True)
+        r_wn = f.weights()
+        assert np.allclose(rd(d, "weights_norm.f32", np.float32), r_wn, rtol=1e-6, atol=0)
 
 
 @pytest.mark.gpu
