@@ -1,7 +1,7 @@
 """ctypes front-end for oracle/tdr_oracle.cpp (TEST INFRASTRUCTURE ONLY).
 
 The oracle is the CPU restatement of the reference hot path; see the header of
-tdr_oracle.cpp for what pins it ("parity unpinned" by the reference itself).
+tdr_oracle.cpp for what pins it (the reference's own sources built in oracle/_ref, cv2, libm / libstdc++, twins).
 Only tests/, __graft_entry__.smoke() and bench.py's cpu_baseline / --impl
 reference legs may import this module.
 """
