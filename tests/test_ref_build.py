@@ -444,3 +444,51 @@ def test_filter_steps_over_seeds_sizes_and_motions(world, seed, N, motion):
     mean, cov, _, _ = f.pose()
     mo, co = orc.mean_cov(st)
     assert same_bits(mean, mo) and same_bits(cov.reshape(-1), co.reshape(-1))
+
+
+@pytest.mark.parametrize("num_classes,resolution,res,weights", [(6, 1.0, 4.0, [1.0, 0.5, 2.0, 1.5, 0.25, 3.0]), (4, 0.5, 1.5, [1.0, 1.0, 1.0, 1.0]),
+                                                                  (5, 2.0, 0.5, [0.0, 1.0, 4.0, 0.1, 1.0])])
+def test_weights_over_class_counts_resolutions_headings(num_classes, resolution, res, weights):
+    """computeWeight / getCostForRot with a known heading (state_particle.cpp:112-219): class weights, map resolutions other
+    than 1, radial bin sizes, headings far outside [0, 2 pi) (the while-loops that normalise the row shift), free scale
+    with its gate — injected states, the reference's weights against the oracle's"""
+    rng = np.random.default_rng(num_classes)
+    cm = synth.make_class_map(220, 260, num_classes, seed=40 + num_classes)
+    img, lut = synth.to_cv_image(cm), synth.identity_lut(num_classes)
+    layers, mask = orc.compute_dists(orc.class_image_to_layers(img, lut, num_classes, resolution), resolution)
+    pose, heading = synth.default_pose(cm, seed=3)
+    pts = synth.make_scan(cm, pose, heading, seed=3, n_rings=16, n_az=256)
+    scan = orc.render_polar(pts, res, ANG, 100, 25, lut, num_classes)
+    tab = orc.polar_table(100, 25, ANG, resolution)
+    m = ref.Map.from_class_image(img, lut, num_classes, resolution)
+    assert same_bits(m.get()[0], layers)
+    assert same_bits(m.polar_table(100, 25, ANG), tab.reshape(-1, 2))
+    N = 300
+    f = ref.Filter(m, N, 8, regularization=0.15, fixed_scale=-1.0, scale_log_min=-0.2, scale_log_max=0.5, class_weights=weights)
+    assert f.count() == N
+    st = np.zeros(N, dtype=synth.STATE_DTYPE)
+    st["init_x_px"] = rng.uniform(-20, cm.shape[1] + 20, N)
+    st["init_y_px"] = rng.uniform(-20, cm.shape[0] + 20, N)
+    st["dx_m"], st["dy_m"] = rng.normal(0, 3, N), rng.normal(0, 3, N)
+    st["theta"] = rng.uniform(-25, 25, N)                           # many turns either way
+    st["theta"][:8] = [0.0, -0.0, 2 * math.pi, -2 * math.pi, math.pi / 100, -math.pi / 100, 199 * math.pi / 100, 1e3]
+    st["scale"] = 10.0 ** rng.uniform(-0.4, 0.7, N)                 # some outside 10^[-0.2, 0.5]: gated to 0
+    st["have_init"] = 1
+    ld = rng.uniform(0, 0.4, N).astype(np.float32)
+    f.set(st, ld)
+    f.update(scan, res)
+    scored, _, raw = f.get(scored_set=True)
+    H, W = cm.shape
+    fp = orc.make_params(num_classes, regularization=0.15, class_weights=weights, fixed_scale=-1.0, scale_log_min=-0.2, scale_log_max=0.5,
+                         map_width=(W / resolution) * resolution, map_height=(H / resolution) * resolution)
+    thetas, shifts = orc.search_list(100)
+    st_o = st.copy()
+    raw_o = orc.score_all(st_o, fp, layers, mask, resolution, tab, 100, 25, scan, res, thetas, shifts)
+    assert np.array_equal(np.isnan(raw), np.isnan(raw_o)) and np.array_equal(raw == 0, raw_o == 0) and (raw == 0).sum() > 10
+    assert (~np.isnan(raw) & (raw != 0)).sum() > 40
+    assert np.allclose(raw, raw_o, rtol=1e-6, atol=0, equal_nan=True)
+    assert np.array_equal(scored, st_o)                              # a known heading is left alone
+    for t in st["theta"][:40]:                                       # the row shift itself (:123-128)
+        assert 0 <= orc.rot_to_shift(float(t), 100) < 100
+    wn, wn_o = f.weights(), orc.normalize(raw.copy(), ld)[0]
+    assert np.allclose(wn, wn_o, rtol=1e-6, atol=0)
