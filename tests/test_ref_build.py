@@ -492,3 +492,41 @@ def test_weights_over_class_counts_resolutions_headings(num_classes, resolution,
         assert 0 <= orc.rot_to_shift(float(t), 100) < 100
     wn, wn_o = f.weights(), orc.normalize(raw.copy(), ld)[0]
     assert np.allclose(wn, wn_o, rtol=1e-6, atol=0)
+
+
+@pytest.mark.parametrize("seed,resolution", [(1, 1.0), (2, 1.0), (3, 0.5)])
+def test_random_svg_polygons_with_vertices_on_sample_points(tmp_path, seed, resolution):
+    """getRasterMap / getClasses (top_down_map.cpp:328-408) on random concave polygons whose vertices lie on quarter pixels —
+    a quarter of them exactly ON sample points (x.5) and many edges horizontal or vertical: the ties of the even-odd
+    rule's `<` comparisons and the divisions by zero of horizontal edges, the reference's expression against the oracle's"""
+    rng = np.random.default_rng(seed)
+    Wm, Hm = 120, 90
+    shapes = []
+    for _ in range(14):
+        k = int(rng.integers(3, 9))
+        cx, cy = rng.uniform(-10, Wm + 10), rng.uniform(-10, Hm + 10)
+        a = np.sort(rng.uniform(0, 2 * np.pi, k))
+        rad = rng.uniform(4, 45) * rng.uniform(0.3, 1.0, k)
+        p = np.stack([cx + rad * np.cos(a), cy + rad * np.sin(a)], axis=1)
+        p = np.round(p * 4) / 4                                    # quarter pixels: exact in the svg text and in fp32
+        if rng.random() < 0.5:
+            p = np.floor(p) + 0.5                                  # on the sample lattice
+        shapes.append((int(rng.integers(0, C_)), p))
+    svg = str(tmp_path / "random.svg")
+    with open(svg, "w") as f:
+        f.write(f'<svg xmlns="http://www.w3.org/2000/svg" width="{Wm}" height="{Hm}">\n')
+        for c, p in shapes:
+            f.write(f'<polygon fill="{SVG_CLASS_HEX[c]}" points="{" ".join(f"{x:.2f},{y:.2f}" for x, y in p)}"/>\n')
+        f.write("</svg>\n")
+    home = tmp_path / "home"
+    (home / ".ros").mkdir(parents=True)
+    excl = [0, 1, 2]
+    m = ref.Map.from_path(str(home), svg, np.arange(C_, dtype=np.int32), C_, resolution, [_packed(c) for c in SVG_CLASS_HEX], exclusive=excl)
+    layers, mask = m.get()
+    order = sorted(range(len(shapes)), key=lambda i: shapes[i][0])
+    polys = [np.float32([(x, Hm - y) for x, y in shapes[i][1]]) for i in order]
+    binl = orc.raster_polygons(polys, [shapes[i][0] for i in order], Wm, Hm, 0.0, resolution, C_, excl)
+    lo, mo = orc.compute_dists(binl, resolution)
+    assert layers.shape == lo.shape and same_bits(layers, lo) and np.array_equal(mask, mo)
+    from top_down_renderer_b200 import rastercache
+    assert np.array_equal(rastercache.load_rasterized_maps(str(tmp_path / "random_raster_cache"), C_), binl)
