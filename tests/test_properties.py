@@ -95,3 +95,46 @@ def test_adaptive_count_stays_inside_its_bounds(last, cap, diag):
     n = orc.adaptive_count(covs, last, cap)
     area = sum(int(math.sqrt(np.float32(diag[2 * k])) * math.sqrt(np.float32(diag[2 * k + 1]))) for k in range(len(diag) // 2))
     assert n == min(max(area, 3 * last // 4 + 10), cap) or abs(n - min(max(area, 3 * last // 4 + 10), cap)) <= len(diag)
+
+
+# ---- the oracle against the reference's own source (oracle/_ref) on hypothesis-drawn inputs ------------------------------
+@FAST
+@given(st.integers(0, 2000), st.floats(0.25, 6.0), st.sampled_from([(100, 25), (36, 9), (7, 3)]), st.integers(0, 2**31 - 1))
+def test_renderers_equal_the_reference_source_on_random_clouds(n, res, shape, seed):
+    from oracle import refbuild as ref
+    if not ref.available():
+        return
+    rng = np.random.default_rng(seed)
+    n_theta, n_r = shape
+    ang = np.float32(2 * math.pi / n_theta)
+    pts = np.zeros((n, 8), dtype=np.float32)
+    pts[:, 0:2] = rng.normal(0, rng.choice([0.5, 8.0, 60.0]), (n, 2))
+    pts[:, 4] = rng.integers(0, 6, n)
+    pts[rng.random(n) < 0.1, 0:2] = 0
+    lut = np.full(256, -1, dtype=np.int32)
+    lut[:4] = [2, 0, -1, 1]                                            # a permuting lut with a hole
+    assert np.array_equal(ref.render_polar(pts, res, ang, n_theta, n_r, lut, 3), orc.render_polar(pts, res, ang, n_theta, n_r, lut, 3))
+    rows, cols = int(rng.integers(1, 40)), int(rng.integers(1, 40))
+    a = ref.render_cart(pts, res, rows, cols, lut, 3)
+    assert np.array_equal(a, orc.render_cart(pts, res, rows, cols, lut, 3).reshape(a.shape))
+
+
+@FAST
+@given(st.integers(4, 40), st.integers(4, 40), st.sampled_from([1.0, 0.5, 2.0, 1.3]), st.floats(0.0, 1.0), st.integers(0, 2**31 - 1))
+def test_distance_fields_equal_the_reference_source_on_random_images(h, w, resolution, unknown, seed):
+    from oracle import refbuild as ref
+    if not ref.available():
+        return
+    rng = np.random.default_rng(seed)
+    img = rng.integers(0, 4, (h, w)).astype(np.uint8)
+    img[rng.random((h, w)) < unknown * 0.5] = 200                      # unknown pixels (lut -> -1)
+    if rng.random() < 0.2:
+        img[:] = rng.integers(0, 4)                                    # a single class everywhere: the other layers have no seed
+    lut = synth.identity_lut(4)
+    rows, cols = orc.map_dims(h, w, resolution)
+    if rows < 1 or cols < 1:
+        return
+    m = ref.Map.from_class_image(img, lut, 4, resolution)
+    layers, mask = m.get()
+    lo, mo = orc.compute_dists(orc.class_image_to_layers(img, lut, 4, resolution), resolution)
+    assert layers.shape == lo.shape and np.array_equal(layers.view(np.uint32), lo.view(np.uint32)) and np.array_equal(mask, mo)
