@@ -271,3 +271,44 @@ class Filter:
         means, covs = np.zeros((8, 3), dtype=np.float32), np.zeros((8, 3, 3), dtype=np.float32)
         n = int(lib().ref_filter_gmm(self.h, _p(samples, _f64p), 1000, _p(means, _f32p), _p(covs, _f32p), 8))
         return samples[:n], means[:1], covs[:1]
+
+
+# ---- the ADAPTERS (top_down_renderer_b200/adapters/*.cpp): bodies over the C ABI for the reference's unchanged class
+# declarations, behind the same C interface (oracle/ref_shim/adapter_harness.cpp)
+def adapters_so(kind: str) -> str:
+    assert kind in ("cpu", "gpu")
+    return os.path.join(_HERE, "_ref", f"libtdr_adapters_{kind}.so")
+
+
+def adapters_available(kind: str) -> bool:
+    return os.path.exists(adapters_so(kind)) or os.path.isdir(os.path.join(REFERENCE, "include"))
+
+
+_adp = {}
+
+
+def adapters(kind: str):
+    """kind "cpu": linked with the CPU stand-in of the C ABI (the oracle answers); "gpu": with libtdr_b200.so"""
+    if kind not in _adp:
+        if os.path.isdir(os.path.join(REFERENCE, "include")):
+            subprocess.check_call(["make", "-C", _HERE, "-s", "_ref/" + os.path.basename(adapters_so(kind))])
+        _adp[kind] = C.CDLL(adapters_so(kind))
+    return _adp[kind]
+
+
+def adapter_render_polar(kind, pts, res, ang_res, n_theta, n_r, lut, num_classes):
+    pts = np.ascontiguousarray(pts, dtype=np.float32)
+    lut = np.ascontiguousarray(lut, dtype=np.int32)
+    out = np.zeros((num_classes, n_r, n_theta), dtype=np.float32)
+    adapters(kind).adp_render_polar(_p(pts, _f32p), C.c_long(len(pts)), C.c_float(res), C.c_float(ang_res), n_theta, n_r, _p(lut, _i32p),
+                                    len(lut), num_classes, _p(out, _f32p))
+    return out
+
+
+def adapter_render_cart(kind, pts, res, rows, cols, lut, num_classes):
+    pts = np.ascontiguousarray(pts, dtype=np.float32)
+    lut = np.ascontiguousarray(lut, dtype=np.int32)
+    out = np.zeros((num_classes, cols, rows), dtype=np.float32)
+    adapters(kind).adp_render_cart(_p(pts, _f32p), C.c_long(len(pts)), C.c_float(res), rows, cols, _p(lut, _i32p), len(lut), num_classes,
+                                   _p(out, _f32p))
+    return out

@@ -1,0 +1,77 @@
+// adapters/scan_renderer.cpp — the bodies that REPLACE src/scan_renderer.cpp and src/scan_renderer_polar.cpp of the
+// reference: the class declarations come from the reference's own, unchanged headers
+// (include/top_down_render/scan_renderer.h:14-23, scan_renderer_polar.h:15-22); every member with arithmetic calls the
+// C ABI of libtdr_b200 (include/tdr.h).  Compile inside the reference's catkin package in place of the two files, or —
+// in this repository, where ROS / Eigen / PCL are absent — against the stand-in headers of oracle/ref_shim
+// (`make -C oracle _adapters`), which is how tests/test_adapters.py links and runs it.
+//
+// renderGeometricTopDown (scan_renderer.cpp:7-53, scan_renderer_polar.cpp:6-81) keeps the reference's host body: its only
+// call is commented out (top_down_render.cpp:540) and the cost function ignores the geometric images; it is
+// not redefined here, so a package build keeps those two functions from the original files.
+#include <cstddef>
+#include <cstdio>
+#include <cstdlib>
+#include <cstring>
+#include <vector>
+
+#include "top_down_render/scan_renderer_polar.h"
+
+#include "tdr.h"
+
+namespace {
+// one device context per process, like the single ROS spinner thread that owns every call (SURVEY 8b "Threading")
+tdr_ctx* tdr() {
+  static tdr_ctx* ctx = nullptr;
+  if (!ctx) {
+    const char* dev = getenv("TDR_DEVICE");
+    if (tdr_create(&ctx, dev ? atoi(dev) : 0) != TDR_OK) {
+      ROS_ERROR("[XView] libtdr_b200: %s", tdr_last_error());
+      fprintf(stderr, "[XView] libtdr_b200: %s\n", tdr_last_error());
+      ctx = nullptr;
+    }
+  }
+  return ctx;
+}
+bool ok(int rc) {
+  if (rc != TDR_OK) fprintf(stderr, "[XView] libtdr_b200: %s\n", tdr_last_error());   // the reference's methods are void: log, carry on
+  return rc == TDR_OK;
+}
+// scan upload shared by both renderers: pcl::PointXYZI is 32 bytes with the intensity at byte 16
+bool upload(const Eigen::VectorXi& lut, const pcl::PointCloud<pcl::PointXYZI>::ConstPtr& cloud, int num_images) {
+  static_assert(sizeof(pcl::PointXYZI) == 32, "pcl::PointXYZI layout");
+  if (!tdr()) return false;
+  if (!ok(tdr_scan_set_lut(tdr(), lut.data(), (int)lut.size(), num_images))) return false;
+  return ok(tdr_scan_set_points(tdr(), cloud->points.data(), (int)sizeof(pcl::PointXYZI), (int)offsetof(pcl::PointXYZI, intensity),
+                                (int64_t)cloud->height * cloud->width));
+}
+void scatter(const std::vector<float>& stage, std::vector<Eigen::ArrayXXf>& imgs) {
+  size_t at = 0;
+  for (auto& img : imgs) { std::memcpy(img.data(), stage.data() + at, (size_t)img.size() * sizeof(float)); at += (size_t)img.size(); }
+}
+}  // namespace
+
+ScanRenderer::ScanRenderer(const Eigen::VectorXi& flatten_lut) { flatten_lut_ = flatten_lut; }   // scan_renderer.cpp:3-5
+
+// replaces scan_renderer.cpp:55-78
+void ScanRenderer::renderSemanticTopDown(const pcl::PointCloud<pcl::PointXYZI>::ConstPtr& cloud, float res,
+                                         std::vector<Eigen::ArrayXXf>& imgs) {
+  if (imgs.size() < 1) return;                                                           // :57
+  const int rows = (int)imgs[0].rows(), cols = (int)imgs[0].cols();
+  if (!upload(flatten_lut_, cloud, (int)imgs.size())) return;
+  std::vector<float> stage(imgs.size() * (size_t)rows * cols);
+  if (!ok(tdr_scan_render_cart(tdr(), res, rows, cols, stage.data()))) return;
+  scatter(stage, imgs);
+}
+
+ScanRendererPolar::ScanRendererPolar(const Eigen::VectorXi& flatten_lut) : ScanRenderer(flatten_lut) {}   // scan_renderer_polar.cpp:3-4
+
+// replaces scan_renderer_polar.cpp:83-109; the class images also stay resident on the device for ParticleFilter::update
+void ScanRendererPolar::renderSemanticTopDown(const pcl::PointCloud<pcl::PointXYZI>::ConstPtr& cloud, float res, float ang_res,
+                                              std::vector<Eigen::ArrayXXf>& imgs) {
+  if (imgs.size() < 1) return;                                                           // :85
+  const int n_theta = (int)imgs[0].rows(), n_r = (int)imgs[0].cols();
+  if (!upload(flatten_lut_, cloud, (int)imgs.size())) return;
+  std::vector<float> stage(imgs.size() * (size_t)n_theta * n_r);
+  if (!ok(tdr_scan_render_polar(tdr(), res, ang_res, n_theta, n_r, stage.data()))) return;
+  scatter(stage, imgs);
+}
