@@ -29,15 +29,17 @@ struct Scalar { double v[4]; Scalar(double a = 0, double b = 0, double c = 0, do
 inline size_t elem_size(int type) { return type == CV_8UC1 ? 1 : type == CV_32FC1 ? 4 : 8; }
 class Mat {
  public:
+  static size_t elem_size_of(int type) { return elem_size(type); }
   int rows = 0, cols = 0, type_ = CV_8UC1;
   uint8_t* data = nullptr;
+  size_t step = 0;                                                       // bytes per row (always dense here)
   std::shared_ptr<std::vector<uint8_t>> own;
   Mat() {}
   Mat(int r, int c, int type) { create(r, c, type); }
-  Mat(int r, int c, int type, void* external) : rows(r), cols(c), type_(type), data(static_cast<uint8_t*>(external)) {}
+  Mat(int r, int c, int type, void* external) : rows(r), cols(c), type_(type), data(static_cast<uint8_t*>(external)), step((size_t)c * elem_size_of(type)) {}
   void create(int r, int c, int type) {
     if (data && rows == r && cols == c && type_ == type) return;       // like cv::Mat::create: keeps a fitting buffer
-    rows = r; cols = c; type_ = type;
+    rows = r; cols = c; type_ = type; step = (size_t)c * elem_size_of(type);
     own = std::make_shared<std::vector<uint8_t>>((size_t)r * c * elem_size(type), 0);
     data = own->data();
   }

@@ -47,19 +47,30 @@ _lib = None
 _f32p, _u8p, _i32p, _f64p = C.POINTER(C.c_float), C.POINTER(C.c_uint8), C.POINTER(C.c_int), C.POINTER(C.c_double)
 
 
-def lib():
-    global _lib
-    if _lib is None:
-        _lib = C.CDLL(build())
-        _lib.ref_map_create.restype = C.c_void_p
-        _lib.ref_map_from_class_image.restype = C.c_void_p
-        _lib.ref_map_from_path.restype = C.c_void_p
-        _lib.ref_map_classes_at.restype = C.c_uint
-        _lib.ref_filter_create.restype = C.c_void_p
+def _prepare(lb, with_filter=True):
+    lb.ref_map_create.restype = C.c_void_p
+    lb.ref_map_from_class_image.restype = C.c_void_p
+    lb.ref_map_from_path.restype = C.c_void_p
+    lb.ref_map_classes_at.restype = C.c_uint
+    if with_filter:
+        lb.ref_filter_create.restype = C.c_void_p
         for name in ("ref_filter_count", "ref_filter_get", "ref_filter_weights"):
-            getattr(_lib, name).restype = C.c_long
-        _lib.ref_filter_scale.restype = C.c_float
-        _lib.ref_filter_engine_peek.restype = C.c_uint32
+            getattr(lb, name).restype = C.c_long
+        lb.ref_filter_scale.restype = C.c_float
+        lb.ref_filter_engine_peek.restype = C.c_uint32
+    return lb
+
+
+_forced = None
+
+
+def lib():
+    """the reference build — or, inside `with using_adapters(kind):`, the adapters behind the same C interface"""
+    global _lib
+    if _forced is not None:
+        return _forced
+    if _lib is None:
+        _lib = _prepare(C.CDLL(build()))
     return _lib
 
 
@@ -296,19 +307,17 @@ def adapters(kind: str):
     return _adp[kind]
 
 
-def adapter_render_polar(kind, pts, res, ang_res, n_theta, n_r, lut, num_classes):
-    pts = np.ascontiguousarray(pts, dtype=np.float32)
-    lut = np.ascontiguousarray(lut, dtype=np.int32)
-    out = np.zeros((num_classes, n_r, n_theta), dtype=np.float32)
-    adapters(kind).adp_render_polar(_p(pts, _f32p), C.c_long(len(pts)), C.c_float(res), C.c_float(ang_res), n_theta, n_r, _p(lut, _i32p),
-                                    len(lut), num_classes, _p(out, _f32p))
-    return out
+import contextlib  # noqa: E402
 
 
-def adapter_render_cart(kind, pts, res, rows, cols, lut, num_classes):
-    pts = np.ascontiguousarray(pts, dtype=np.float32)
-    lut = np.ascontiguousarray(lut, dtype=np.int32)
-    out = np.zeros((num_classes, cols, rows), dtype=np.float32)
-    adapters(kind).adp_render_cart(_p(pts, _f32p), C.c_long(len(pts)), C.c_float(res), rows, cols, _p(lut, _i32p), len(lut), num_classes,
-                                   _p(out, _f32p))
-    return out
+@contextlib.contextmanager
+def using_adapters(kind: str):
+    """inside the block render_polar / render_cart / Map run the ADAPTERS (adapters/*.cpp over the C ABI: "cpu" = the CPU
+    stand-in answers, "gpu" = libtdr_b200) through the very harness that drives the reference's own bodies"""
+    global _forced
+    prev = _forced
+    _forced = _prepare(adapters(kind), with_filter=False)
+    try:
+        yield
+    finally:
+        _forced = prev

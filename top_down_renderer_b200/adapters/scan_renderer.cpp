@@ -16,26 +16,12 @@
 
 #include "top_down_render/scan_renderer_polar.h"
 
-#include "tdr.h"
+#include "tdr_adapter_common.h"
+
+using tdr_adapter::ok;
+using tdr_adapter::tdr;
 
 namespace {
-// one device context per process, like the single ROS spinner thread that owns every call (SURVEY 8b "Threading")
-tdr_ctx* tdr() {
-  static tdr_ctx* ctx = nullptr;
-  if (!ctx) {
-    const char* dev = getenv("TDR_DEVICE");
-    if (tdr_create(&ctx, dev ? atoi(dev) : 0) != TDR_OK) {
-      ROS_ERROR("[XView] libtdr_b200: %s", tdr_last_error());
-      fprintf(stderr, "[XView] libtdr_b200: %s\n", tdr_last_error());
-      ctx = nullptr;
-    }
-  }
-  return ctx;
-}
-bool ok(int rc) {
-  if (rc != TDR_OK) fprintf(stderr, "[XView] libtdr_b200: %s\n", tdr_last_error());   // the reference's methods are void: log, carry on
-  return rc == TDR_OK;
-}
 // scan upload shared by both renderers: pcl::PointXYZI is 32 bytes with the intensity at byte 16
 bool upload(const Eigen::VectorXi& lut, const pcl::PointCloud<pcl::PointXYZI>::ConstPtr& cloud, int num_images) {
   static_assert(sizeof(pcl::PointXYZI) == 32, "pcl::PointXYZI layout");
