@@ -4,12 +4,8 @@
 // tests/test_ref_build.py drives it beside the oracle.  See README.md here for what this does and does not pin.
 #include "top_down_render/scan_renderer_polar.h"
 // TDR_ADAPTER_BUILD: the same harness over the ADAPTERS (top_down_renderer_b200/adapters/*.cpp) instead of the reference's own
-// bodies — the classes the adapters cover so far (scan renderers, TopDownMap / TopDownMapPolar); see `make -C oracle _adapters`
-#ifdef TDR_ADAPTER_BUILD
-#include "top_down_render/top_down_map_polar.h"
-#else
+// bodies (active_localizer.cpp stays the reference's, on top of the adapter map); see `make -C oracle _adapters`
 #include "top_down_render/particle_filter.h"
-#endif
 
 #define REF_API extern "C" __attribute__((visibility("default")))
 
@@ -74,7 +70,6 @@ REF_API void ref_map_local_geo_polar(void* map, float cx, float cy, float scale,
   static_cast<TopDownMapPolar*>(map)->getLocalGeoMap(Eigen::Vector2f(cx, cy), scale, res, v);
   copy_out(v, geo);
 }
-#ifndef TDR_ADAPTER_BUILD
 REF_API void ref_active_best_rel_pos(void* map, const float* preds, int n, float rel[2]) {
   ActiveLocalizer al(static_cast<TopDownMapPolar*>(map));
   std::vector<Eigen::Vector3f> p;
@@ -82,8 +77,6 @@ REF_API void ref_active_best_rel_pos(void* map, const float* preds, int n, float
   Eigen::Vector2f best = al.getBestRelPos(p);
   rel[0] = best[0]; rel[1] = best[1];
 }
-
-#endif
 
 // ---- a3 - a6, a8, the vector map and the caches: src/top_down_map.cpp itself -------------------------------------------
 static TopDownMap::Params make_params(int C, float resolution, const int* lut, int n_lut) {
@@ -170,7 +163,6 @@ REF_API void ref_map_local_cart(void* map, float cx, float cy, float rot, float 
   std::memcpy(mask, k.data(), (size_t)rows * cols);
 }
 
-#ifndef TDR_ADAPTER_BUILD
 // ---- a9 - a13 and the rows around them: ParticleFilter ------------------------------------------------------------------
 struct RefFilterParams {      // FilterParams, state_particle.h:19-38
   float pos_cov, theta_cov, regularization;
@@ -276,4 +268,3 @@ REF_API int ref_filter_gmm(void* fv, double* samples, int cap_rows, float* means
   }
   return s.rows;
 }
-#endif  // !TDR_ADAPTER_BUILD

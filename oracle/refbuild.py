@@ -316,7 +316,7 @@ def using_adapters(kind: str):
     stand-in answers, "gpu" = libtdr_b200) through the very harness that drives the reference's own bodies"""
     global _forced
     prev = _forced
-    _forced = _prepare(adapters(kind), with_filter=False)
+    _forced = _prepare(adapters(kind))
     try:
         yield
     finally:

@@ -262,9 +262,9 @@ int tdr_pf_gmm_samples(tdr_ctx* c, int num, double* out) {
   orc_gmm_samples(c->states.data(), (long)c->states.size(), num, out);
   return TDR_OK;
 }
-// ParticleFilter::update (particle_filter.cpp:94-189): score, normalise, systematic resampling to M particles
-int tdr_pf_update(tdr_ctx* c, float res, float u, int64_t M) {
-  REQ(c->rows > 0 && !c->tab.empty() && !c->scan.empty() && !c->states.empty() && !c->thetas.empty(), TDR_ESTATE, "update before setup");
+// ParticleFilter::update (particle_filter.cpp:94-189) in its three stages, and in one call
+int tdr_pf_score(tdr_ctx* c, float res, float* weights_out) {
+  REQ(c->rows > 0 && !c->tab.empty() && !c->scan.empty() && !c->states.empty() && !c->thetas.empty(), TDR_ESTATE, "score before setup");
   const long n = (long)c->states.size();
   OrcFilterParams fp{};
   fp.regularization = c->fp.regularization; fp.force_on_map = c->fp.force_on_map; fp.fixed_scale = c->fp.fixed_scale;
@@ -275,14 +275,31 @@ int tdr_pf_update(tdr_ctx* c, float res, float u, int64_t M) {
   const int nt = (int)std::max(1u, std::min(8u, std::thread::hardware_concurrency()));
   orc_score_all(c->states.data(), n, &fp, c->layers.data(), c->mask.data(), nullptr, c->rows, c->cols, c->resolution, c->tab.data(),
                 c->n_theta, c->n_r, c->scan.data(), res, c->thetas.data(), c->shifts.data(), (int)c->thetas.size(), c->weights.data(), nt);
-  const long arg = orc_normalize(c->weights.data(), c->last_dist.data(), n, nullptr);
+  if (weights_out) std::copy(c->weights.begin(), c->weights.end(), weights_out);
+  return TDR_OK;
+}
+int tdr_pf_set_weights(tdr_ctx* c, const float* w, int64_t n) { c->weights.assign(w, w + n); return TDR_OK; }
+int tdr_pf_normalize(tdr_ctx* c, int64_t* argmax_out, float* stats) {
+  REQ(c->weights.size() == c->states.size() && !c->states.empty(), TDR_ESTATE, "weights and particles differ");
+  const long arg = orc_normalize(c->weights.data(), c->last_dist.data(), (long)c->states.size(), stats);
   c->ml_state = c->states[arg]; c->have_ml = true;
+  if (argmax_out) *argmax_out = arg;
+  return TDR_OK;
+}
+int tdr_pf_resample(tdr_ctx* c, float u, int64_t M, int32_t* idx_out) {
+  REQ(c->weights.size() == c->states.size() && !c->states.empty() && M > 0, TDR_ESTATE, "resample before normalise");
   std::vector<int> idx((size_t)M);
-  orc_resample_fast(c->weights.data(), n, u, (int)M, idx.data(), nullptr);
+  orc_resample_fast(c->weights.data(), (long)c->states.size(), u, (int)M, idx.data(), nullptr);
   std::vector<OrcState> ns((size_t)M); std::vector<float> nl((size_t)M);
   for (int64_t i = 0; i < M; i++) { ns[i] = c->states[idx[i]]; nl[i] = c->last_dist[idx[i]]; }
   c->states.swap(ns); c->last_dist.swap(nl);
+  if (idx_out) std::copy(idx.begin(), idx.end(), idx_out);
   return TDR_OK;
+}
+int tdr_pf_update(tdr_ctx* c, float res, float u, int64_t M) {
+  if (int e = tdr_pf_score(c, res, nullptr)) return e;
+  if (int e = tdr_pf_normalize(c, nullptr, nullptr)) return e;
+  return tdr_pf_resample(c, u, M, nullptr);
 }
 int tdr_pf_pose(tdr_ctx* c, float mean[4], float cov_mean[16], float ml[4], float cov_ml[16]) {
   REQ(!c->states.empty(), TDR_ESTATE, "no particles");

@@ -147,3 +147,90 @@ def test_scan_renderer_adapters_on_the_device():
 def test_map_adapters_on_the_device(tmp_path):
     _gpu_adapters()
     _check_map("gpu", tmp_path)
+
+
+# ---- ParticleFilter / StateParticle through the adapters -------------------------------------------------------------------
+REF_BUILD_TESTS = ["test_filter_step_equals_the_reference", "test_theta_search_and_gates_equal_the_reference",
+                   "test_nan_weights_take_the_mean_minus_lower_deviation", "test_map_centre_shift_and_metric_initial_position",
+                   "test_active_localizer_equals_the_reference", "test_polar_gather_equals_the_reference"]
+
+
+@pytest.mark.skipif(not ref.adapters_available("cpu"), reason="no /root/reference and no prebuilt adapters")
+def test_filter_adapters_pass_the_reference_builds_own_tests_on_the_cpu_standin():
+    """the tests that hold the REFERENCE's own ParticleFilter / TopDownMapPolar / ActiveLocalizer against the oracle
+    (tests/test_ref_build.py), run unchanged on the adapter classes: same harness, same assertions — initialisation,
+    propagate and the engine position bit for bit, weights, adaptive count, resampled states, pose, gates, NaN handling,
+    freezeScale, the map-centre shift, the metric initial position, getBestRelPos"""
+    import tests.test_ref_build as t
+    with ref.using_adapters("cpu"):
+        world = t.world._get_wrapped_function()()
+        for name in REF_BUILD_TESTS:
+            getattr(t, name)(world)
+        for args in [(101, 64, (0.0, 0.0, 0.0)), (202, 333, (1.5, -0.7, 0.2))]:
+            t.test_filter_steps_over_seeds_sizes_and_motions(world, *args)
+
+
+def _check_filter_on_device(kind):
+    """the adapter ParticleFilter with the DEVICE behind the C ABI: host-side parts (initialisation, RNG stream, adaptive
+    count, mirror bookkeeping) bit for bit, device stages to the bars of tests/test_gpu_parity.py"""
+    from oracle import numpy_twin as twin
+    from tests.common import make_world, N_R, N_THETA, rel_err
+    wd = make_world(h=300, w=400, C=4, seed=11, res=2.0)
+    seed, N = 23, 400
+    kw = dict(fixed_scale=2.0, init_pos_px=(float(wd.pose[0]), float(wd.pose[1])), init_pos_px_cov=8.0,
+              init_pos_deg_theta=math.degrees(wd.heading), init_pos_deg_cov=4.0)
+    with ref.using_adapters(kind):
+        m = ref.Map.from_class_image(wd.img, wd.lut, wd.C, 1.0, center=(wd.w // 2, wd.h // 2))
+        m.polar_table(N_THETA, N_R, np.float32(2 * math.pi / N_THETA))
+        layers, mask = m.get()
+        assert np.array_equal(layers.view(np.uint32), wd.layers.view(np.uint32)) and np.array_equal(mask, wd.mask)
+        f = ref.Filter(m, N, seed, regularization=0.7, pos_cov=0.15, theta_cov=0.004, **kw)
+        st0, _, _ = f.get()
+        so, frozen, _, used = orc.init_particles(seed, wd.layers, 1.0, (wd.w // 2, wd.h // 2), N, **kw)
+        assert np.array_equal(st0, so) and f.scale_frozen() == frozen and f.engine_peek() == orc.engine_peek(seed, used)
+        f.propagate(0.4, 0.05, 0.01)
+        st1, ld1, _ = f.get()
+        want, last_o, z, used_p = orc.propagate(so, 0.4, 0.05, 0.01, True, 0.15, 0.004, seed, discard=used)
+        tw, last_t = twin.propagate_with_z(so, 0.4, 0.05, 0.01, True, 0.15, 0.004, z)
+        assert f.engine_peek() == orc.engine_peek(seed, used + used_p)                       # the same variates were drawn
+        for k in ("dx_m", "dy_m", "theta"):
+            assert np.abs(st1[k] - want[k]).max() <= 1e-6, k                                 # 1 ulp of cosf / sinf at most
+            assert np.array_equal(st1[k], tw[k]) or np.array_equal(st1[k], want[k]), k       # the kernel's form or glibc's
+        for k in ("init_x_px", "init_y_px", "scale", "have_init"):
+            assert np.array_equal(st1[k], so[k]), k
+        assert np.abs(ld1 - last_o).max() <= 1e-6
+        _, _, covs = f.gmm()
+        cov4 = np.zeros((1, 4, 4), np.float32)
+        cov4[0, :3, :3] = covs[0]
+        M = orc.adaptive_count(cov4, N, N)
+        f.update(wd.scan, wd.res)
+        scored, ld_s, raw = f.get(scored_set=True)
+        st_o = st1.copy()
+        raw_o = orc.score_all(st_o, wd.fp, wd.layers, wd.mask, 1.0, wd.tab, N_THETA, N_R, wd.scan, wd.res, wd.thetas, wd.shifts)
+        assert rel_err(raw, raw_o).max() <= 1e-5                                             # a9, a10
+        wn = f.weights()
+        wn_o, _, _ = orc.normalize(raw.copy(), ld_s)                                         # a11, stage-wise on the device's raw weights
+        assert rel_err(wn, wn_o).max() <= 1e-6
+        cur, _, _ = f.get()
+        assert len(cur) == M == f.num_particles()
+        u = orc.uniform_draw(seed, discard=used + used_p)
+        idx = orc.resample_fast(wn, u, M)                                                    # a12, stage-wise on the device's weights
+        for k in ("init_x_px", "init_y_px", "dx_m", "dy_m", "theta", "scale", "have_init"):
+            assert np.array_equal(cur[k], scored[k][idx]), k
+        assert f.engine_peek() == orc.engine_peek(seed, used + used_p + 1)
+        mean, cov, ml, _ = f.pose()                                                          # a13
+        mo, _ = orc.mean_cov(cur)
+        assert abs(mean[0] - mo[0]) <= 0.002 and abs(mean[1] - mo[1]) <= 0.002 and abs(mean[2] - mo[2]) <= math.radians(0.01)
+        mlo, _ = orc.ml_cov(scored, int(np.argmax(wn)))
+        assert np.array_equal(ml, mlo)                                                       # the ML particle is a host object
+
+
+@pytest.mark.skipif(not ref.adapters_available("cpu"), reason="no /root/reference and no prebuilt adapters")
+def test_filter_adapter_device_checks_hold_on_the_cpu_standin():
+    _check_filter_on_device("cpu")                      # the GPU test's own assertions, proven where they can run today
+
+
+@pytest.mark.gpu
+def test_filter_adapters_on_the_device():
+    _gpu_adapters()
+    _check_filter_on_device("gpu")

@@ -1,4 +1,4 @@
-// adapters/scan_renderer.cpp — the bodies that REPLACE src/scan_renderer.cpp and src/scan_renderer_polar.cpp of the
+// adapters/scan_renderer_adapter.cpp — the bodies that REPLACE src/scan_renderer.cpp and src/scan_renderer_polar.cpp of the
 // reference: the class declarations come from the reference's own, unchanged headers
 // (include/top_down_render/scan_renderer.h:14-23, scan_renderer_polar.h:15-22); every member with arithmetic calls the
 // C ABI of libtdr_b200 (include/tdr.h).  Compile inside the reference's catkin package in place of the two files, or —

@@ -1,4 +1,4 @@
-// adapters/top_down_map.cpp — the bodies that REPLACE src/top_down_map.cpp and src/top_down_map_polar.cpp of the reference.
+// adapters/top_down_map_adapter.cpp — the bodies that REPLACE src/top_down_map.cpp and src/top_down_map_polar.cpp of the reference.
 // The class declarations are the reference's own, unchanged (include/top_down_render/top_down_map.h:52-101,
 // top_down_map_polar.h:6-22); rasterising the vector map, the distance fields and every gather run on the device through
 // the C ABI (include/tdr.h).  What stays host code is what is file / glue work in the reference too: the svg parse
