@@ -22,13 +22,20 @@ def _have_gpu():
 
 # run last: the GPU tests whose newest checks were written in a session without GPU access (proven there on the CPU
 # stand-in / a dry run only), so that with `-x` a surprise in them cannot hide the long-standing parity tests
-_LAST = ("tests/test_host_cpp.py::test_host_mirror_step_matches_oracle", "tests/test_gpu_vs_reference.py",
+_LAST = ("tests/test_gpu_vs_reference.py", "tests/test_host_cpp.py::test_host_mirror_step_matches_oracle",
          "tests/test_adapters.py::test_scan_renderer_adapters_on_the_device", "tests/test_adapters.py::test_map_adapters_on_the_device",
          "tests/test_adapters.py::test_filter_adapters_on_the_device")
 
 
+def _rank(item):
+    for k, prefix in enumerate(_LAST):
+        if item.nodeid.startswith(prefix):
+            return k + 1
+    return 0
+
+
 def pytest_collection_modifyitems(config, items):
-    items.sort(key=lambda it: any(it.nodeid.startswith(p) for p in _LAST))      # stable: everything else keeps its order
+    items.sort(key=_rank)                                                      # stable: everything else keeps its order
     if _have_gpu():
         return
     skip = pytest.mark.skip(reason="no CUDA device in this container")
