@@ -24,7 +24,8 @@ def _have_gpu():
 # stand-in / a dry run only), so that with `-x` a surprise in them cannot hide the long-standing parity tests
 _LAST = ("tests/test_gpu_vs_reference.py", "tests/test_host_cpp.py::test_host_mirror_step_matches_oracle",
          "tests/test_adapters.py::test_scan_renderer_adapters_on_the_device", "tests/test_adapters.py::test_map_adapters_on_the_device",
-         "tests/test_adapters.py::test_filter_adapters_on_the_device")
+         "tests/test_adapters.py::test_filter_adapters_on_the_device",
+         "tests/test_adapters.py::test_map_adapters_gathers_at_half_resolution_on_the_device")
 
 
 def _rank(item):

@@ -42,7 +42,7 @@ def _check(kind):
                               orc.render_polar(pts, 2.0, np.float32(2 * math.pi / 36), 36, 9, lut, 4))
 
 
-def _check_map(kind, tmp_path):
+def _check_map(kind, tmp_path, resolutions=(1.0, 0.5), static_paths=True):
     """TopDownMap / TopDownMapPolar through the adapters: the dynamic path, the gathers, the static constructor and caches"""
     from top_down_renderer_b200 import eigcache, rastercache
     from tests.test_ref_build import SVG_CLASS_HEX, SVG_H, SVG_SHAPES, SVG_W, _packed, _write_svg, same_bits
@@ -50,7 +50,7 @@ def _check_map(kind, tmp_path):
     cm = synth.make_class_map(200, 240, C_, seed=9)
     img, lut = synth.to_cv_image(cm), synth.identity_lut(C_)
     with ref.using_adapters(kind):
-        for resolution in (1.0, 0.5):
+        for resolution in resolutions:
             seeds = orc.class_image_to_layers(img, lut, C_, resolution)
             lo, mo = orc.compute_dists(seeds, resolution)
             m = ref.Map.from_class_image(img, lut, C_, resolution, center=(5, -2))          # updateMap: a3 + a4 on the device side
@@ -70,6 +70,8 @@ def _check_map(kind, tmp_path):
             d, k = m.local_map_cart(100.0, 80.0, 0.7, 2.0, 40, 31)                           # a8 through the base class
             do, ko = orc.local_map_cart(lo, mo, resolution, 100.0, 80.0, 0.7, 2.0, 40, 31)
             assert same_bits(d, do.reshape(d.shape)) and np.array_equal(k, ko.reshape(k.shape))
+        if not static_paths:
+            return
         # two maps alive at once: the device holds one, the other is re-installed from its host copies on demand
         a = ref.Map.from_class_image(img, lut, C_, 1.0)
         b = ref.Map.from_class_image(img[::-1].copy(), lut, C_, 1.0)
@@ -146,7 +148,15 @@ def test_scan_renderer_adapters_on_the_device():
 @pytest.mark.gpu
 def test_map_adapters_on_the_device(tmp_path):
     _gpu_adapters()
-    _check_map("gpu", tmp_path)
+    _check_map("gpu", tmp_path, resolutions=(1.0,))
+
+
+@pytest.mark.gpu
+def test_map_adapters_gathers_at_half_resolution_on_the_device(tmp_path):
+    """gathers on a map whose resolution is not 1 (centre / resolution, radius / resolution): the device kernels divide as
+    the reference does, but no GPU test fed them such a map before this one — it runs last for that reason"""
+    _gpu_adapters()
+    _check_map("gpu", tmp_path, resolutions=(0.5,), static_paths=False)
 
 
 # ---- ParticleFilter / StateParticle through the adapters -------------------------------------------------------------------
