@@ -1,4 +1,5 @@
 // api.cu — the extern "C" surface declared in include/tdr.h.
+#include <atomic>
 #include <cmath>
 #include <stdarg.h>
 #include <stdlib.h>
@@ -10,6 +11,7 @@
 namespace tdr {
 
 static thread_local char g_err[512] = "";
+uint64_t next_tab_id() { static std::atomic<uint64_t> next{0}; return ++next; }
 void set_error(const char* fmt, ...) {
   va_list ap; va_start(ap, fmt);
   vsnprintf(g_err, sizeof(g_err), fmt, ap);
@@ -159,11 +161,15 @@ int tdr_create(tdr_ctx** out, int device) {
   if (const char* e = getenv("TDR_MMA_RING_CFG")) c->mma_ring_cfg = atoi(e);
   if (const char* e = getenv("TDR_MMA_KERNEL")) c->mma_kernel = atoi(e);
   if (const char* e = getenv("TDR_MMA_CTAS")) c->mma_ctas = atoi(e);
+  if (const char* e = getenv("TDR_MMA_GRID_CAP")) { int v = atoi(e); if (v > 0) c->mma_grid_cap = v; }
   if (const char* e = getenv("TDR_MMA_ST_SHIFT")) { int v = atoi(e); if (v >= 5 && v <= 16) c->mma_st_shift = v; }
   TDR_CUDA(cudaStreamCreateWithFlags(&c->stream, cudaStreamNonBlocking));
   if (int r = c->scal.reserve(SC_TOTAL * 4)) { delete c; return r; }
   TDR_CUDA(cudaMemsetAsync(c->scal.p, 0, SC_TOTAL * 4, c->stream));
   if (int r = c->d_cw.reserve(64)) { delete c; return r; }
+  if (int r = c->uninit_dev.reserve(16)) { delete c; return r; }
+  TDR_CUDA(cudaEventCreateWithFlags(&c->uninit_ev, cudaEventDisableTiming));
+  TDR_CUDA(cudaMallocHost(reinterpret_cast<void**>(&c->uninit_pin), 16));
   *out = c;
   return TDR_OK;
 }
@@ -181,6 +187,9 @@ void tdr_destroy(tdr_ctx* c) {
   c->grid_full.release();
   c->part[0].release(); c->part[1].release(); c->ckpt.release(); c->all.release();
   c->pin.release();
+  c->uninit_dev.release();
+  if (c->uninit_ev) cudaEventDestroy(c->uninit_ev);
+  if (c->uninit_pin) cudaFreeHost(c->uninit_pin);
   for (int k = 0; k <= TDR_N_STAGES; k++) if (c->stage_ev[k]) cudaEventDestroy(c->stage_ev[k]);
   for (int k = 0; k < 2; k++) { if (c->refine_copied[k]) cudaEventDestroy(c->refine_copied[k]); if (c->refine_binned[k]) cudaEventDestroy(c->refine_binned[k]); c->refine_stage[k].release(); }
   if (c->copy_stream) cudaStreamDestroy(c->copy_stream);
@@ -256,7 +265,7 @@ int tdr_map_set_polar_table(tdr_ctx* ctx, const float* tab, int n_theta, int n_r
   if (int e = ctx->tab.reserve(bytes)) return e;
   TDR_CUDA(cudaMemcpyAsync(ctx->tab.p, tab, bytes, cudaMemcpyHostToDevice, ctx->stream));
   TDR_CUDA(cudaStreamSynchronize(ctx->stream));
-  ctx->n_theta = n_theta; ctx->n_r = n_r; ctx->have_tab = true; ctx->tab_version++;
+  ctx->n_theta = n_theta; ctx->n_r = n_r; ctx->have_tab = true; ctx->tab_version++; ctx->tab_id = tdr::next_tab_id();
   return TDR_OK;
 }
 
@@ -500,7 +509,7 @@ int tdr_pf_set_states(tdr_ctx* ctx, const tdr_state* states, const float* last_d
   TDR_CUDA(cudaStreamSynchronize(ctx->stream));
   int64_t un = 0;
   for (int64_t i = 0; i < n; i++) un += states[i].have_init ? 0 : 1;
-  pt.n = n; ctx->n_uninit = un; ctx->have_argmax = false;
+  pt.n = n; ctx->n_uninit = un; ctx->uninit_pending = false; ctx->have_argmax = false;
   return TDR_OK;
 }
 
@@ -580,6 +589,7 @@ int tdr_pf_checkpoint(tdr_ctx* ctx) {
   Particles& pt = ctx->part[ctx->cur];
   TDR_REQUIRE(pt.n > 0, TDR_ESTATE, "no particles");
   if (int e = copy_particles(ctx, ctx->ckpt, pt)) return e;
+  if (int e = sync_uninit(ctx)) return e;
   ctx->ckpt_uninit = ctx->n_uninit;
   return TDR_OK;
 }
@@ -588,7 +598,7 @@ int tdr_pf_restore(tdr_ctx* ctx) {
   CTX_CHECK(ctx);
   TDR_REQUIRE(ctx->ckpt.n > 0, TDR_ESTATE, "no checkpoint");
   if (int e = copy_particles(ctx, ctx->part[ctx->cur], ctx->ckpt)) return e;
-  ctx->n_uninit = ctx->ckpt_uninit; ctx->have_argmax = false;
+  ctx->n_uninit = ctx->ckpt_uninit; ctx->uninit_pending = false; ctx->have_argmax = false;
   return TDR_OK;
 }
 

@@ -333,7 +333,12 @@ static __global__ void k_bin_scatter(BinParams b, int* __restrict__ cursor, int*
 // FMUL of the index math; from constant memory (uniform LDC through the constant cache) it is off that path.
 static const int MMA_TAB_MAX = 4096;
 __constant__ float2 c_tab[MMA_TAB_MAX];
-static const void* g_tab_owner = nullptr;     // device table currently mirrored in c_tab
+// c_tab exists once per device (and per translation unit that includes this header).  g_tab_on_device[d] = the
+// process-unique id (tdr_ctx::tab_id) of the table this unit's copy on device d mirrors; 0 = none / a scaled grid table.
+// Contexts on different devices, several contexts on one device and recycled table pointers all key correctly.
+// (Two contexts that share a device must not SCORE concurrently from two threads: they share this constant bank.)
+static const int MMA_MAX_DEVICES = 64;
+static uint64_t g_tab_on_device[MMA_MAX_DEVICES] = {};
 
 static const int MMA_G = 2;        // lattice cells per pipeline stage
 // A tile (128 hypotheses x 16 fp16, K-major, no swizzle): K chunk 0 at [0, 2048), K chunk 1 at [A_LBO, A_LBO + 2048).
@@ -373,13 +378,14 @@ static int sync_const_tab_scaled(tdr_ctx* ctx, int P, float scale, float res) {
   k_scale_tab<<<(P + 255) / 256, 256, 0, ctx->stream>>>(ctx->tab.as<float2>(), P, scale, res, ctx->tab_scaled.as<float2>());
   count_launch(ctx);
   TDR_CUDA(cudaMemcpyToSymbolAsync(c_tab, ctx->tab_scaled.p, (size_t)P * 8, 0, cudaMemcpyDeviceToDevice, ctx->stream));
-  g_tab_owner = nullptr;                      // the next particle launch mirrors the plain table again
+  g_tab_on_device[ctx->device % MMA_MAX_DEVICES] = 0;     // the next particle launch mirrors the plain table again
   return TDR_OK;
 }
-static int sync_const_tab(tdr_ctx* ctx, int P, uint64_t* seen_version) {
-  if (g_tab_owner != ctx->tab.p || *seen_version != ctx->tab_version) {
+static int sync_const_tab(tdr_ctx* ctx, int P) {
+  uint64_t& seen = g_tab_on_device[ctx->device % MMA_MAX_DEVICES];
+  if (seen != ctx->tab_id || ctx->tab_id == 0) {
     TDR_CUDA(cudaMemcpyToSymbolAsync(c_tab, ctx->tab.p, (size_t)P * 8, 0, cudaMemcpyDeviceToDevice, ctx->stream));
-    g_tab_owner = ctx->tab.p; *seen_version = ctx->tab_version;
+    seen = ctx->tab_id;
   }
   return TDR_OK;
 }

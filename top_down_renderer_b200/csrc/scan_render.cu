@@ -157,11 +157,7 @@ int scan_render(tdr_ctx* ctx, bool polar, float res, float ang_res, int d0, int 
   if (W > 8) W = 8;
   if (W >= 2 && ctx->n_pts > 0) {
     // atomic-free path
-    static bool attr_set = false;
-    if (!attr_set) {
-      TDR_CUDA(cudaFuncSetAttribute(k_scan_bin_private, cudaFuncAttributeMaxDynamicSharedMemorySize, kSmemBudget + 8192));
-      attr_set = true;
-    }
+    TDR_SMEM_OPTIN(ctx, OPTIN_SCAN_BIN, k_scan_bin_private, kSmemBudget + 8192);
     long long done = 0;
     int round = 0;
     while (done < ctx->n_pts) {

@@ -394,12 +394,12 @@ int score_particles(tdr_ctx* ctx, float res) {
   ctx->n_weights = pt.n;
   const int P = sp.P;
   TDR_REQUIRE(P <= 65535 && P <= SEARCH_THREADS * SEARCH_JMAX, TDR_EUNSUPPORTED, "polar image of %d cells is too large (max %d)", P, SEARCH_THREADS * SEARCH_JMAX);
-  static bool attr_set = false;
-  if (!attr_set) {
-    TDR_CUDA(cudaFuncSetAttribute(k_score_track, cudaFuncAttributeMaxDynamicSharedMemorySize, 200 * 1024));
-    TDR_CUDA(cudaFuncSetAttribute(k_score_search<SEARCH_THREADS, SEARCH_JMAX>, cudaFuncAttributeMaxDynamicSharedMemorySize, 200 * 1024));
-    attr_set = true;
-  }
+  TDR_SMEM_OPTIN(ctx, OPTIN_SCORE_TRACK, k_score_track, 200 * 1024);
+  TDR_SMEM_OPTIN(ctx, OPTIN_SCORE_SEARCH, (k_score_search<SEARCH_THREADS, SEARCH_JMAX>), 200 * 1024);
+  if (int e = sync_uninit(ctx)) return e;
+  // a gated particle (force_on_map / scale range) returns before the search and keeps have_init = 0
+  // (state_particle.cpp:163-176): with a gate switched on the set is recounted after the search instead of assumed clean
+  const bool gates_on = ctx->fp.force_on_map != 0 || ctx->fp.fixed_scale < 0;
   // particles that already have a heading are tracked (one shift); the rest run the theta search,
   // which sets theta / have_init (state_particle.cpp:195-206).  Track first: it only READS have_init.
   const size_t track_smem = (size_t)P * 32 + (size_t)P * 8 + (size_t)P * 4;
@@ -419,11 +419,18 @@ int score_particles(tdr_ctx* ctx, float res) {
       if (ctx->mma_kernel != 2) { if (int e = score_mma_list(ctx, res, false, pt.n, 1.f, sp.shifts, sp.n_shifts, &used)) return e; }
       if (!used) { if (int e = score_mma(ctx, res, false, pt.n, 1.f, sp.shifts, ctx->search_shifts.data(), sp.n_shifts, &used)) return e; }
     }
-    if (used) { ctx->n_uninit = 0; TDR_CUDA(cudaGetLastError()); return TDR_OK; }
+    if (used) {
+      TDR_CUDA(cudaGetLastError());
+      if (gates_on) return recount_uninit(ctx, pt);
+      ctx->n_uninit = 0;
+      return TDR_OK;
+    }
     size_t smem = (size_t)P * 32 + (size_t)sp.n_shifts * (SEARCH_THREADS / 32) * 8 + 256;
     long long ctas = sp.n < (long long)ctx->sm_count * 8 ? sp.n : (long long)ctx->sm_count * 8;
     k_score_search<SEARCH_THREADS, SEARCH_JMAX><<<(unsigned)ctas, SEARCH_THREADS, smem, ctx->stream>>>(sp, 0);
     count_launch(ctx);
+    TDR_CUDA(cudaGetLastError());
+    if (gates_on) return recount_uninit(ctx, pt);
     ctx->n_uninit = 0;
   }
   TDR_CUDA(cudaGetLastError());
@@ -447,7 +454,7 @@ int score_grid(tdr_ctx* ctx, long long n, float scale, float res) {
   if (used) return TDR_OK;
   TDR_REQUIRE(ctx->grid_n_peers == 0, TDR_EUNSUPPORTED, "the fused peer all-gather needs the tensor-core ring kernel (n_theta <= 112 and even, distinct shifts)");
   TDR_REQUIRE(P <= SEARCH_THREADS * SEARCH_JMAX, TDR_EUNSUPPORTED, "polar image too large");
-  TDR_CUDA(cudaFuncSetAttribute(k_score_search<SEARCH_THREADS, SEARCH_JMAX>, cudaFuncAttributeMaxDynamicSharedMemorySize, 200 * 1024));
+  TDR_SMEM_OPTIN(ctx, OPTIN_SCORE_SEARCH, (k_score_search<SEARCH_THREADS, SEARCH_JMAX>), 200 * 1024);
   size_t smem = (size_t)P * 32 + (size_t)sp.n_shifts * (SEARCH_THREADS / 32) * 8 + 256;
   long long ctas = n < (long long)ctx->sm_count * 8 ? n : (long long)ctx->sm_count * 8;
   k_score_search<SEARCH_THREADS, SEARCH_JMAX><<<(unsigned)ctas, SEARCH_THREADS, smem, ctx->stream>>>(sp, 1);

@@ -626,9 +626,8 @@ int score_mma(tdr_ctx* ctx, float res, bool grid_mode, long long n_items, float 
 
   if (int e = build_perm(ctx, grid_mode, n_items)) return e;
   tdr::Particles& pt = ctx->part[ctx->cur];
-  static uint64_t tab_seen = 0;
   if (grid_mode) { if (int e = sync_const_tab_scaled(ctx, P, grid_scale, res)) return e; }
-  else if (int e = sync_const_tab(ctx, P, &tab_seen)) return e;
+  else if (int e = sync_const_tab(ctx, P)) return e;
   MmaParams sp; memset(&sp, 0, sizeof(sp));
   if (int e = build_map16(ctx, grid_mode ? ctx->grid_phase_log2 : 0, &sp.map16, &sp.geom)) return e;
   sp.resolution = ctx->resolution; sp.tab_scaled = grid_mode ? 1 : 0;
@@ -660,13 +659,14 @@ int score_mma(tdr_ctx* ctx, float res, bool grid_mode, long long n_items, float 
     sp.regularization = ctx->fp.regularization;
     sp.thetas = ctx->d_search_thetas.as<float>();
   }
-#define TDR_LAUNCH_MMA(TT, RR, AA, GG)                                                                               \
+#define TDR_LAUNCH_MMA(IDX, TT, RR, AA, GG)                                                                            \
   do {                                                                                                                \
     using Cfg = MmaCfg<TT, RR, AA, GG>;                                                                               \
-    static bool attr = false;                                                                                         \
-    if (!attr) { TDR_CUDA(cudaFuncSetAttribute(k_score_mma<TT, RR, AA, GG>, cudaFuncAttributeMaxDynamicSharedMemorySize, Cfg::kSmem)); attr = true; } \
+    TDR_SMEM_OPTIN(ctx, OPTIN_RING_BASE + IDX,                                                                        \
+                   (k_score_mma<TT, RR, AA, GG>), Cfg::kSmem);                                                        \
     const long long nb = (sp.n_work + 128 * TT - 1) / (128 * TT);                                                     \
-    const long long cap = (long long)ctx->sm_count * (ctx->mma_ctas > 0 && ctx->mma_ctas < Cfg::kCtasPerSm ? ctx->mma_ctas : Cfg::kCtasPerSm); \
+    long long cap = (long long)ctx->sm_count * (ctx->mma_ctas > 0 && ctx->mma_ctas < Cfg::kCtasPerSm ? ctx->mma_ctas : Cfg::kCtasPerSm); \
+    if (ctx->mma_grid_cap > 0 && ctx->mma_grid_cap < cap) cap = ctx->mma_grid_cap;                                    \
     const int grid = (int)(nb < cap ? nb : cap);                                                                      \
     k_score_mma<TT, RR, AA, GG><<<grid, Cfg::kThreads, Cfg::kSmem, ctx->stream>>>(sp);                                \
   } while (0)
@@ -674,15 +674,15 @@ int score_mma(tdr_ctx* ctx, float res, bool grid_mode, long long n_items, float 
   int rcfg = ctx->mma_ring_cfg;
   if (rcfg >= 400 && ctx->n_theta % 4 != 0) rcfg = 114;
   switch (rcfg) {
-    case 21: TDR_LAUNCH_MMA(2, 1, false, 2); break;
-    case 22: TDR_LAUNCH_MMA(2, 2, false, 2); break;
-    case 11: TDR_LAUNCH_MMA(1, 1, false, 2); break;
-    case 14: TDR_LAUNCH_MMA(1, 4, false, 2); break;
-    case 12: TDR_LAUNCH_MMA(1, 2, false, 2); break;
-    case 112: TDR_LAUNCH_MMA(1, 2, true, 2); break;
-    case 114: TDR_LAUNCH_MMA(1, 4, true, 2); break;
-    case 412: TDR_LAUNCH_MMA(1, 2, true, 4); break;
-    default: TDR_LAUNCH_MMA(1, 3, true, 4); break;
+    case 21: TDR_LAUNCH_MMA(0, 2, 1, false, 2); break;
+    case 22: TDR_LAUNCH_MMA(1, 2, 2, false, 2); break;
+    case 11: TDR_LAUNCH_MMA(2, 1, 1, false, 2); break;
+    case 14: TDR_LAUNCH_MMA(3, 1, 4, false, 2); break;
+    case 12: TDR_LAUNCH_MMA(4, 1, 2, false, 2); break;
+    case 112: TDR_LAUNCH_MMA(5, 1, 2, true, 2); break;
+    case 114: TDR_LAUNCH_MMA(6, 1, 4, true, 2); break;
+    case 412: TDR_LAUNCH_MMA(7, 1, 2, true, 4); break;
+    default: TDR_LAUNCH_MMA(8, 1, 3, true, 4); break;
   }
 #undef TDR_LAUNCH_MMA
   count_launch(ctx);

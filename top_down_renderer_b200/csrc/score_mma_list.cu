@@ -338,9 +338,8 @@ int score_mma_list(tdr_ctx* ctx, float res, bool grid_mode, long long n_items, f
 
   if (int e = build_perm(ctx, grid_mode, n_items)) return e;
   tdr::Particles& pt = ctx->part[ctx->cur];
-  static uint64_t tab_seen = 0;
   if (grid_mode) { if (int e = sync_const_tab_scaled(ctx, P, grid_scale, res)) return e; }
-  else if (int e = sync_const_tab(ctx, P, &tab_seen)) return e;
+  else if (int e = sync_const_tab(ctx, P)) return e;
   ListParams sp; memset(&sp, 0, sizeof(sp));
   if (int e = build_map16(ctx, grid_mode ? ctx->grid_phase_log2 : 0, &sp.map16, &sp.geom)) return e;
   sp.resolution = ctx->resolution; sp.tab_scaled = grid_mode ? 1 : 0;
@@ -363,32 +362,33 @@ int score_mma_list(tdr_ctx* ctx, float res, bool grid_mode, long long n_items, f
     sp.regularization = ctx->fp.regularization;
     sp.thetas = ctx->d_search_thetas.as<float>();
   }
-#define TDR_LAUNCH_LIST(NN, TT, RR, AA)                                                                               \
+#define TDR_LAUNCH_LIST(IDX, NN, TT, RR, AA)                                                                            \
   do {                                                                                                                \
     using Cfg = ListCfg<NN, TT, RR, AA>;                                                                               \
-    static bool attr = false;                                                                                         \
-    if (!attr) { TDR_CUDA(cudaFuncSetAttribute(k_score_mma_list<NN, TT, RR, AA>, cudaFuncAttributeMaxDynamicSharedMemorySize, Cfg::kSmem)); attr = true; } \
+    TDR_SMEM_OPTIN(ctx, OPTIN_LIST_BASE + IDX,                                                                        \
+                   (k_score_mma_list<NN, TT, RR, AA>), Cfg::kSmem);                                                   \
     const long long nb = (sp.n_work + 128 * TT - 1) / (128 * TT);                                                     \
-    const long long cap = (long long)ctx->sm_count * (ctx->mma_ctas > 0 && ctx->mma_ctas < Cfg::kCtasPerSm ? ctx->mma_ctas : Cfg::kCtasPerSm); \
+    long long cap = (long long)ctx->sm_count * (ctx->mma_ctas > 0 && ctx->mma_ctas < Cfg::kCtasPerSm ? ctx->mma_ctas : Cfg::kCtasPerSm); \
+    if (ctx->mma_grid_cap > 0 && ctx->mma_grid_cap < cap) cap = ctx->mma_grid_cap;                                    \
     const int grid = (int)(nb < cap ? nb : cap);                                                                      \
     k_score_mma_list<NN, TT, RR, AA><<<grid, Cfg::kThreads, Cfg::kSmem, ctx->stream>>>(sp);                              \
   } while (0)
   const int cfg = ctx->mma_tiles * 10 + ctx->mma_split;
   if (ctx->mma_a_tmem) {
     switch (cfg) {
-      case 21: TDR_LAUNCH_LIST(96, 2, 1, true); break;
-      case 12: TDR_LAUNCH_LIST(96, 1, 2, true); break;
-      case 14: TDR_LAUNCH_LIST(96, 1, 4, true); break;
-      default: TDR_LAUNCH_LIST(96, 2, 2, true); break;     // 9.5 ms per 1e6 x 40 (T = 1, R = 4: 12.1; T = 2, R = 1: 15.6)
+      case 21: TDR_LAUNCH_LIST(0, 96, 2, 1, true); break;
+      case 12: TDR_LAUNCH_LIST(1, 96, 1, 2, true); break;
+      case 14: TDR_LAUNCH_LIST(2, 96, 1, 4, true); break;
+      default: TDR_LAUNCH_LIST(3, 96, 2, 2, true); break;     // 9.5 ms per 1e6 x 40 (T = 1, R = 4: 12.1; T = 2, R = 1: 15.6)
     }
   } else {
     switch (cfg) {
-      case 41: TDR_LAUNCH_LIST(96, 4, 1, false); break;
-      case 21: TDR_LAUNCH_LIST(96, 2, 1, false); break;
-      case 22: TDR_LAUNCH_LIST(96, 2, 2, false); break;
-      case 11: TDR_LAUNCH_LIST(96, 1, 1, false); break;
-      case 14: TDR_LAUNCH_LIST(96, 1, 4, false); break;
-      default: TDR_LAUNCH_LIST(96, 1, 2, false); break;
+      case 41: TDR_LAUNCH_LIST(4, 96, 4, 1, false); break;
+      case 21: TDR_LAUNCH_LIST(5, 96, 2, 1, false); break;
+      case 22: TDR_LAUNCH_LIST(6, 96, 2, 2, false); break;
+      case 11: TDR_LAUNCH_LIST(7, 96, 1, 1, false); break;
+      case 14: TDR_LAUNCH_LIST(8, 96, 1, 4, false); break;
+      default: TDR_LAUNCH_LIST(9, 96, 1, 2, false); break;
     }
   }
 #undef TDR_LAUNCH_LIST

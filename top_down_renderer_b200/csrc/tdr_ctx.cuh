@@ -119,6 +119,8 @@ struct tdr_ctx {
   int mma_ring_cfg = 413;    // ring kernel: tiles * 10 + threads per row, + 100 operands in tensor memory, + 400 and 4-cell stages (tuning: TDR_MMA_RING_CFG)
   int mma_kernel = 0;        // 0 auto, 1 streamed-operand kernel only, 2 ring kernel only (tuning: TDR_MMA_KERNEL)
   int mma_ctas = 0;          // cap on co-resident CTAs per SM (0 = as many as TMEM allows; tuning: TDR_MMA_CTAS)
+  int mma_grid_cap = 0;      // cap on the grid of the persistent score kernels (0 = none; TDR_MMA_GRID_CAP — tests use it to
+                             // make every CTA walk many batches)
   int mma_st_shift = 10;     // log2 of the binning super-tile side in px (tuning: TDR_MMA_ST_SHIFT)
 
   // ---- polar table
@@ -155,6 +157,18 @@ struct tdr_ctx {
   tdr::Particles ckpt;       // device-side snapshot of the particle set (tdr_pf_checkpoint / tdr_pf_restore)
   int64_t ckpt_uninit = 0;
   int64_t n_uninit = 0;      // particles still without a heading (have_init == false)
+  // n_uninit is exact on the host except while a device recount is in flight: a gated particle keeps have_init = 0
+  // through the theta search (state_particle.cpp:163-176 return before :205) and resampling multiplies or drops it,
+  // so the set is recounted on the device (k_count_uninit -> pinned word, event) and read back lazily by the next
+  // score call (tdr::sync_uninit) — no host round trip inside an update.
+  bool uninit_pending = false;
+  cudaEvent_t uninit_ev = nullptr;
+  int* uninit_pin = nullptr;           // pinned host word the recount lands in
+  tdr::DevBuf uninit_dev;              // its device-side counter
+  // kernels whose dynamic shared-memory opt-in has been set ON THIS CONTEXT'S DEVICE (function attributes are per
+  // device; a process may hold contexts on several)
+  uint64_t smem_optin = 0;
+  uint64_t tab_id = 0;                 // process-unique id of the resident polar table (constant-memory mirrors key on it)
   tdr::DevBuf d_cw;          // class weights (16 floats)
   tdr::Particles all;        // multi-GPU: the all-gathered particle set (N = ranks * n_local) in global order
   tdr::DevBuf weights;       // raw -> normalised in place
@@ -204,6 +218,17 @@ enum {
 
 
 inline void count_launch(tdr_ctx* c, int k = 1) { c->launches += k; }
+// opt a kernel into more than 48 KB of dynamic shared memory once per context (= per device)
+enum { OPTIN_SCORE_TRACK = 0, OPTIN_SCORE_SEARCH, OPTIN_SMALL_UPDATE, OPTIN_SCAN_BIN, OPTIN_EDT_ROWS, OPTIN_NORM_FUSED,
+       OPTIN_LIST_BASE = 16 /* + kernel variant */, OPTIN_RING_BASE = 32, OPTIN_TILE_BASE = 48 };
+#define TDR_SMEM_OPTIN(ctx, bit, kernel, bytes)                                                                   \
+  do {                                                                                                            \
+    if (!((ctx)->smem_optin & (1ull << (bit)))) {                                                                 \
+      TDR_CUDA(cudaFuncSetAttribute(kernel, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)(bytes)));          \
+      (ctx)->smem_optin |= 1ull << (bit);                                                                         \
+    }                                                                                                             \
+  } while (0)
+uint64_t next_tab_id();
 inline void stage_mark(tdr_ctx* c, int k) { if (c->profiling) cudaEventRecord(c->stage_ev[k], c->stream); }
 
 // map_build.cu
@@ -244,6 +269,8 @@ int build_prefix(tdr_ctx*);
 int resample(tdr_ctx*, float u, long long M, long long i0, long long i1, Particles* src, Particles* dst);
 int cache_ml_state(tdr_ctx*, const Particles& src);
 int small_update(tdr_ctx*, float u, long long M, bool do_resample, bool* used);
+int recount_uninit(tdr_ctx*, Particles& pt);   // asynchronous device recount of have_init == 0 over pt (see tdr_ctx::uninit_pending)
+int sync_uninit(tdr_ctx*);                     // n_uninit exact on the host again
 int exact_sums(tdr_ctx*, const float* const* cols, long long n, int ncols, float* totals_dev);
 // pose.cu
 int pose_of(tdr_ctx*, Particles& pt, float* mean, float* cov_mean, float* ml, float* cov_ml);

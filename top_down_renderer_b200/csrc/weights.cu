@@ -957,6 +957,35 @@ int build_prefix(tdr_ctx* ctx) {
   return launch_seq(ctx, jobs, 1);
 }
 
+// have_init == 0 over a particle set: warp ballot, one atomic per warp that saw any (none in the steady state)
+__global__ void k_count_uninit(const uint8_t* __restrict__ have_init, long long n, int* __restrict__ out) {
+  int mine = 0;
+  for (long long i = (long long)blockIdx.x * blockDim.x + threadIdx.x; i < n; i += (long long)gridDim.x * blockDim.x)
+    mine += have_init[i] ? 0 : 1;
+  for (int o = 16; o > 0; o >>= 1) mine += __shfl_xor_sync(0xffffffffu, mine, o);
+  if ((threadIdx.x & 31) == 0 && mine) atomicAdd(out, mine);
+}
+int recount_uninit(tdr_ctx* ctx, Particles& pt) {
+  int* d = ctx->uninit_dev.as<int>();
+  TDR_CUDA(cudaMemsetAsync(d, 0, 4, ctx->stream));
+  const long long n = pt.n;
+  const int blocks = (int)((n + 1023) / 1024 < ctx->sm_count * 4 ? (n + 1023) / 1024 : ctx->sm_count * 4);
+  k_count_uninit<<<blocks < 1 ? 1 : blocks, 256, 0, ctx->stream>>>(pt.have_init.as<uint8_t>(), n, d);
+  count_launch(ctx);
+  TDR_CUDA(cudaGetLastError());
+  TDR_CUDA(cudaMemcpyAsync(ctx->uninit_pin, d, 4, cudaMemcpyDeviceToHost, ctx->stream));
+  TDR_CUDA(cudaEventRecord(ctx->uninit_ev, ctx->stream));
+  ctx->uninit_pending = true;
+  return TDR_OK;
+}
+int sync_uninit(tdr_ctx* ctx) {
+  if (!ctx->uninit_pending) return TDR_OK;
+  TDR_CUDA(cudaEventSynchronize(ctx->uninit_ev));      // recorded an update ago: normally complete already
+  ctx->n_uninit = *ctx->uninit_pin;
+  ctx->uninit_pending = false;
+  return TDR_OK;
+}
+
 // outputs [i0, i1) of the M systematic samples over the resident weights; when src/dst are given the
 // states of the drawn particles are gathered from *src into *dst (dst->n = i1 - i0).
 // Single GPU: i0 = 0, i1 = M, src = particles_, dst = new_particles_ (particle_filter.cpp:185-187).
@@ -981,7 +1010,11 @@ int resample(tdr_ctx* ctx, float u, long long M, long long i0, long long i1, Par
   k_resample<<<blocks, 256, 0, ctx->stream>>>(ctx->prefix.as<float>(), n, u, M, i0, i1, ctx->idx.as<int32_t>(), g, src_n);
   count_launch(ctx);
   TDR_CUDA(cudaGetLastError());
-  if (src && dst) dst->n = cnt;
+  if (src && dst) {
+    dst->n = cnt;
+    // un-initialised (gated) particles may have been multiplied or dropped: recount, asynchronously
+    if (ctx->uninit_pending || ctx->n_uninit > 0) { if (int e = recount_uninit(ctx, *dst)) return e; }
+  }
   return TDR_OK;
 }
 
@@ -1003,14 +1036,16 @@ int small_update(tdr_ctx* ctx, float u, long long M, bool do_resample, bool* use
     g.oix = dst.init_x.as<float>(); g.oiy = dst.init_y.as<float>(); g.odx = dst.dx.as<float>(); g.ody = dst.dy.as<float>();
     g.oth = dst.theta.as<float>(); g.osc = dst.scale.as<float>(); g.old = dst.last_dist.as<float>(); g.ohi = dst.have_init.as<uint8_t>();
   }
-  static bool attr = false;
-  if (!attr) { TDR_CUDA(cudaFuncSetAttribute(k_small_update, cudaFuncAttributeMaxDynamicSharedMemorySize, SMALL_MAX * 4)); attr = true; }
+  TDR_SMEM_OPTIN(ctx, OPTIN_SMALL_UPDATE, k_small_update, SMALL_MAX * 4);
   k_small_update<<<1, SEQ_THREADS, (size_t)n * 4, ctx->stream>>>(ctx->weights.as<float>(), src.last_dist.as<float>(), (int)n,
                                                                 ctx->scal.as<float>(), u, (int)M, ctx->idx.as<int32_t>(), g,
                                                                 do_resample ? 1 : 0);
   count_launch(ctx);
   TDR_CUDA(cudaGetLastError());
-  if (do_resample) dst.n = M;
+  if (do_resample) {
+    dst.n = M;
+    if (ctx->uninit_pending || ctx->n_uninit > 0) { if (int e = recount_uninit(ctx, dst)) return e; }
+  }
   *used = true;
   return TDR_OK;
 }
