@@ -467,8 +467,11 @@ def test_checkpoint_restore_and_stage_timers(world):
 
 
 # ---- tcgen05 gather-GEMM score path (score_mma.cu): same bars as the CUDA-core kernels ---------------------------
-@pytest.fixture()
-def mma_ctx(world):
+@pytest.fixture(params=["fp16", "u8"])
+def mma_ctx(world, request, monkeypatch):
+    """the tensor-core score path with either operand format: fp16 hi/lo records (score_mma_list.cu / score_mma.cu) or
+    the 16-byte integer records where they apply (score_mma_i8.cu: particle searches of <= 40 shifts)"""
+    monkeypatch.setenv("TDR_MMA_I8", "0" if request.param == "fp16" else "1")
     c = make_ctx(world)
     c.set_score_impl(2)
     yield c

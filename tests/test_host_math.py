@@ -306,6 +306,8 @@ def test_lean_lattice_coordinate_equals_the_literal_form(hm):
     hm.hm_lattice_coord_mismatches.restype = C.c_long
     hm.hm_lattice_coord_mismatches.argtypes = [C.POINTER(C.c_float), C.c_long, C.c_int]
     hm.hm_lattice_coord.argtypes = [C.c_float, C.c_int]
+    hm.hm_lattice_fixed_mismatches.restype = C.c_long
+    hm.hm_lattice_fixed_mismatches.argtypes = [C.POINTER(C.c_float), C.c_long, C.c_int]
     for limit in (1, 2, 1000, 4000, 4001):
         k = np.arange(-3, limit + 3, dtype=np.float64)
         near = []
@@ -324,6 +326,8 @@ def test_lean_lattice_coordinate_equals_the_literal_form(hm):
         rnd = np.concatenate([rng.uniform(-10, limit + 10, 2_000_000), rng.normal(limit / 2, limit, 2_000_000)]).astype(np.float32)
         v = np.ascontiguousarray(np.concatenate(near + [special, rnd]), dtype=np.float32)
         assert hm.hm_lattice_coord_mismatches(v.ctypes.data_as(C.POINTER(C.c_float)), len(v), limit) == 0, limit
+        # and the fixed-point form of the integer-record kernel (coordinates pre-multiplied by 4096)
+        assert hm.hm_lattice_fixed_mismatches(v.ctypes.data_as(C.POINTER(C.c_float)), len(v), limit) == 0, limit
     # the documented boundary cases
     assert hm.hm_lattice_coord(-0.5, 10) == -1 and hm.hm_lattice_coord(np.nextafter(np.float32(-0.5), np.float32(0)), 10) == 0
     assert hm.hm_lattice_coord(9.5, 10) == -1 and hm.hm_lattice_coord(np.nextafter(np.float32(9.5), np.float32(0)), 10) == 9

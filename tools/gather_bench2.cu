@@ -20,25 +20,22 @@ __device__ __forceinline__ uint32_t smem_u32(const void* p) { return (uint32_t)_
 //      0: aligned groups of `share` consecutive lanes      1: lanes l, l + 32/share, ... (strided)      2: random pairing
 //    within the line every lane takes its own REC-byte slot (distinct sectors where REC >= 32).
 template <int REC>
-__device__ __forceinline__ uint32_t rec_offset(int share, int how, uint32_t warp, uint32_t lane, uint32_t it) {
-  const uint32_t n_lines = (32u << 20) / 128u;
-  const uint32_t per_line = 128 / REC;
-  uint32_t grp, slot;
-  if (how == 0) { grp = lane / share; slot = lane % share; }
-  else if (how == 1) { const uint32_t ng = 32 / share; grp = lane % ng; slot = lane / ng; }
-  else { const uint32_t perm = (lane * 13u + 5u * it) & 31u; grp = perm / share; slot = perm % share; }
-  const uint32_t line = hash32(warp * 131u + it * 7919u + grp * 977u) % n_lines;
-  return line * 128u + (slot % per_line) * REC;
-}
-
-template <int REC>
 __global__ void __launch_bounds__(512) k_ldg(const unsigned char* __restrict__ base, int share, int how, int iters,
                                              uint32_t* __restrict__ sink) {
   const uint32_t gid = blockIdx.x * blockDim.x + threadIdx.x, lane = threadIdx.x & 31, warp = gid >> 5;
+  const uint32_t n_lines = (32u << 20) / 128u, per_line = 128 / REC;
+  // lane -> (group, slot) once (the loop must stay load-bound, not ALU-bound)
+  uint32_t grp, slot;
+  if (how == 0) { grp = lane / share; slot = lane % share; }
+  else if (how == 1) { const uint32_t ng = 32 / share; grp = lane % ng; slot = lane / ng; }
+  else { const uint32_t perm = (lane * 13u) & 31u; grp = perm / share; slot = perm % share; }
+  const uint32_t slot_off = (slot % per_line) * REC;
+  uint32_t q = hash32(warp * 131u + grp * 977u + 1u);          // same stream for every lane of a group
   uint32_t acc = 0;
 #pragma unroll 4
   for (int it = 0; it < iters; it++) {
-    const unsigned char* p = base + rec_offset<REC>(share, how, warp, lane, it);
+    q = q * 1664525u + 1013904223u;
+    const unsigned char* p = base + (size_t)(__umulhi(q, n_lines) * 128u + (REC >= 32 ? ((q >> 3) & 3u) * 32u * (share == 1) : 0u) + slot_off);
     if (REC == 32) {
       uint32_t v0, v1, v2, v3, v4, v5, v6, v7;
       asm volatile("ld.global.nc.v8.b32 {%0,%1,%2,%3,%4,%5,%6,%7}, [%8];"
@@ -62,7 +59,7 @@ __global__ void __launch_bounds__(512) k_ldg(const unsigned char* __restrict__ b
 //    iteration (spread = how far apart the 8 lanes of a quarter warp may be, in records: small = spatially sorted
 //    particles).  refill: warp 0's elected lane keeps issuing cp.async.bulk of CHUNK bytes into a second buffer.
 template <int REC>
-__global__ void __launch_bounds__(512) k_lds(const unsigned char* __restrict__ gsrc, int region_bytes, int spread, int iters, int refill,
+__global__ void __launch_bounds__(544) k_lds(const unsigned char* __restrict__ gsrc, int region_bytes, int spread, int iters, int refill,
                                              int swz, uint32_t* __restrict__ sink) {
   extern __shared__ __align__(128) unsigned char smem[];
   __shared__ __align__(8) uint64_t bars[4];
@@ -201,6 +198,7 @@ int main() {
         CK(cudaMemset(sink, 0, 64));                                                                                    \
         cudaEventRecord(e0);                                                                                            \
         k_lds<REC><<<sms, 544, region + 4 * 8192>>>(d, region, spread, iters * 4, refill, SWZ, sink);                    \
+        CK(cudaGetLastError());                                                                                         \
         cudaEventRecord(e1);                                                                                            \
         CK(cudaDeviceSynchronize());                                                                                    \
         const float ms = time_ms(e0, e1);                                                                               \

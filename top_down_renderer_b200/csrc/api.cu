@@ -161,6 +161,9 @@ int tdr_create(tdr_ctx** out, int device) {
   if (const char* e = getenv("TDR_MMA_RING_CFG")) c->mma_ring_cfg = atoi(e);
   if (const char* e = getenv("TDR_MMA_KERNEL")) c->mma_kernel = atoi(e);
   if (const char* e = getenv("TDR_MMA_CTAS")) c->mma_ctas = atoi(e);
+  if (const char* e = getenv("TDR_MMA_I8")) { int v = atoi(e); if (v >= 0 && v <= 2) c->mma_i8 = v; }
+  if (const char* e = getenv("TDR_MMA_I8_CFG")) c->mma_i8_cfg = atoi(e);
+  if (const char* e = getenv("TDR_MMA_SORT")) { int v = atoi(e); if (v >= 0 && v <= 1) c->mma_sort = v; }
   if (const char* e = getenv("TDR_MMA_GRID_CAP")) { int v = atoi(e); if (v > 0) c->mma_grid_cap = v; }
   if (const char* e = getenv("TDR_MMA_ST_SHIFT")) { int v = atoi(e); if (v >= 5 && v <= 16) c->mma_st_shift = v; }
   TDR_CUDA(cudaStreamCreateWithFlags(&c->stream, cudaStreamNonBlocking));
@@ -170,6 +173,9 @@ int tdr_create(tdr_ctx** out, int device) {
   if (int r = c->uninit_dev.reserve(16)) { delete c; return r; }
   TDR_CUDA(cudaEventCreateWithFlags(&c->uninit_ev, cudaEventDisableTiming));
   TDR_CUDA(cudaMallocHost(reinterpret_cast<void**>(&c->uninit_pin), 16));
+  TDR_CUDA(cudaEventCreateWithFlags(&c->scan_max_ev, cudaEventDisableTiming));
+  TDR_CUDA(cudaMallocHost(reinterpret_cast<void**>(&c->scan_max_pin), 16));
+  *c->scan_max_pin = 0;
   *out = c;
   return TDR_OK;
 }
@@ -190,6 +196,9 @@ void tdr_destroy(tdr_ctx* c) {
   c->uninit_dev.release();
   if (c->uninit_ev) cudaEventDestroy(c->uninit_ev);
   if (c->uninit_pin) cudaFreeHost(c->uninit_pin);
+  c->map8.release();
+  if (c->scan_max_ev) cudaEventDestroy(c->scan_max_ev);
+  if (c->scan_max_pin) cudaFreeHost(c->scan_max_pin);
   for (int k = 0; k <= TDR_N_STAGES; k++) if (c->stage_ev[k]) cudaEventDestroy(c->stage_ev[k]);
   for (int k = 0; k < 2; k++) { if (c->refine_copied[k]) cudaEventDestroy(c->refine_copied[k]); if (c->refine_binned[k]) cudaEventDestroy(c->refine_binned[k]); c->refine_stage[k].release(); }
   if (c->copy_stream) cudaStreamDestroy(c->copy_stream);
@@ -476,7 +485,7 @@ int tdr_pf_set_params(tdr_ctx* ctx, const tdr_filter_params* p) {
   ctx->fp = *p;
   TDR_CUDA(cudaMemcpyAsync(ctx->d_cw.p, ctx->fp.class_weights, 64, cudaMemcpyHostToDevice, ctx->stream));
   TDR_CUDA(cudaStreamSynchronize(ctx->stream));
-  ctx->have_params = true; ctx->map16_valid = false; ctx->map16g_log2 = -1;   // class weights are folded into the fp16 map copy
+  ctx->have_params = true; ctx->map16_valid = false; ctx->map8_valid = false; ctx->map16g_log2 = -1;   // class weights are folded into the fp16 map copy
   return TDR_OK;
 }
 
@@ -923,8 +932,13 @@ int tdr_grid_best_key(tdr_ctx* ctx, uint64_t* key) {
   CTX_CHECK(ctx);
   TDR_REQUIRE(key, TDR_EINVAL, "null argument");
   TDR_REQUIRE(ctx->grid_key_valid, TDR_ESTATE, "the last grid did not run on the tensor-core kernel: use tdr_grid_best");
+  int bailed = 0;
   TDR_CUDA(cudaMemcpyAsync(key, ctx->grid_key.p, 8, cudaMemcpyDeviceToHost, ctx->stream));
+  TDR_CUDA(cudaMemcpyAsync(&bailed, ctx->scal.as<float>() + SC_MMA_BAILED, 4, cudaMemcpyDeviceToHost, ctx->stream));
   TDR_CUDA(cudaStreamSynchronize(ctx->stream));
+  // the fp16 exactness of the scan counts is checked on the device; this read-back is where the host learns about it
+  TDR_REQUIRE(!bailed, TDR_ESTATE, "scan counts above 2048: the tensor-core kernel left this grid to the CUDA cores%s",
+              ctx->grid_n_peers ? " and the fused peer all-gather did not run" : " (use tdr_grid_best)");
   return TDR_OK;
 }
 int tdr_grid_key_decode(uint64_t key, float* best_cost, int64_t* best_index) {

@@ -39,6 +39,17 @@ long hm_lattice_coord_mismatches(const float* v, long n, int limit) {
   }
   return bad;
 }
+// the fixed-point form of the integer-record kernel (score_mma_i8.cu), fed with v * 4096 (exact)
+long hm_lattice_fixed_mismatches(const float* v, long n, int limit) {
+  long bad = 0;
+  for (long i = 0; i < n; i++) {
+    if (v[i] != v[i]) continue;                 // NaN centres are switched off by the caller
+    const int lit = f2i_x86(round_half_away(v[i]));
+    const int want = (lit >= 0 && lit < limit) ? lit : -1;
+    if (lattice_fixed(v[i] * 4096.0f, 4096u * (uint32_t)limit - 1u) != want) bad++;
+  }
+  return bad;
+}
 int hm_lattice_coord(float v, int limit) { return lattice_coord(v, (float)limit - 0.5f); }
 int hm_rot_to_shift(float rot, int n_theta) { return rot_to_shift(rot, n_theta); }
 float hm_round(float x) { return round_half_away(x); }

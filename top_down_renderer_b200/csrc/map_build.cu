@@ -232,7 +232,7 @@ static int map_alloc(tdr_ctx* ctx, int rows, int cols, int C, float resolution) 
   if (int e = ctx->map_px.reserve(L * sizeof(MapPixel))) return e;
   if (int e = ctx->seedbits.reserve(L)) return e;
   ctx->rows = rows; ctx->cols = cols; ctx->C = C; ctx->resolution = resolution;
-  ctx->map16_valid = false; ctx->map16g_log2 = -1; ctx->perm_grid_n = -1; ctx->geo_valid = false;
+  ctx->map16_valid = false; ctx->map8_valid = false; ctx->map16g_log2 = -1; ctx->perm_grid_n = -1; ctx->geo_valid = false;
   return TDR_OK;
 }
 

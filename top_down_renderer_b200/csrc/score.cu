@@ -34,6 +34,8 @@ struct ScoreParams {
   float* weights;
   // grid mode
   const float* centers; float grid_scale; float* costs;
+  // launched BEHIND a tensor-core kernel: run only if that one bailed out (scan counts above 2048, decided on the device)
+  const int* only_if_bailed;
 };
 
 __device__ __forceinline__ float4 ldg4(const void* p) { return __ldg(reinterpret_cast<const float4*>(p)); }
@@ -147,6 +149,7 @@ template <int THREADS, int JMAX>
 __global__ void __launch_bounds__(THREADS) k_score_search(ScoreParams sp, int grid_mode) {
   extern __shared__ __align__(16) unsigned char smem[];
   constexpr int WARPS = THREADS / 32;
+  if (sp.only_if_bailed && *sp.only_if_bailed == 0) return;
   float* s_scan = reinterpret_cast<float*>(smem);
   float* s_part = s_scan + (size_t)sp.P * 8;               // [n_shifts][WARPS][2]
   float* s_kc = s_part + (size_t)sp.n_shifts * WARPS * 2;   // [WARPS]
@@ -377,7 +380,7 @@ static int fill_params(tdr_ctx* ctx, float res, ScoreParams* sp) {
   sp->regularization = ctx->fp.regularization;
   sp->thetas = ctx->d_search_thetas.as<float>(); sp->shifts = ctx->d_search_shifts.as<int32_t>();
   sp->n_shifts = (int)ctx->search_shifts.size();
-  sp->centers = nullptr; sp->grid_scale = 1.f; sp->costs = nullptr;
+  sp->centers = nullptr; sp->grid_scale = 1.f; sp->costs = nullptr; sp->only_if_bailed = nullptr;
   return TDR_OK;
 }
 
@@ -416,17 +419,16 @@ int score_particles(tdr_ctx* ctx, float res) {
     bool used = false;
     if (ctx->score_impl == 2 || (ctx->score_impl == 0 && ctx->n_uninit >= 4096)) {
       // short candidate lists: streamed-operand kernel (two pipelines per SM); long ones: all-shifts ring kernel
-      if (ctx->mma_kernel != 2) { if (int e = score_mma_list(ctx, res, false, pt.n, 1.f, sp.shifts, sp.n_shifts, &used)) return e; }
+      // integer 16-byte records where their error bound and the count range allow (score_mma_i8.cu)
+      if (ctx->mma_kernel == 0 || ctx->mma_kernel == 3) { if (int e = score_mma_i8(ctx, res, sp.shifts, sp.n_shifts, &used)) return e; }
+      if (!used && ctx->mma_kernel != 2) { if (int e = score_mma_list(ctx, res, false, pt.n, 1.f, sp.shifts, sp.n_shifts, &used)) return e; }
       if (!used) { if (int e = score_mma(ctx, res, false, pt.n, 1.f, sp.shifts, ctx->search_shifts.data(), sp.n_shifts, &used)) return e; }
     }
-    if (used) {
-      TDR_CUDA(cudaGetLastError());
-      if (gates_on) return recount_uninit(ctx, pt);
-      ctx->n_uninit = 0;
-      return TDR_OK;
-    }
-    size_t smem = (size_t)P * 32 + (size_t)sp.n_shifts * (SEARCH_THREADS / 32) * 8 + 256;
-    long long ctas = sp.n < (long long)ctx->sm_count * 8 ? sp.n : (long long)ctx->sm_count * 8;
+    const size_t smem = (size_t)P * 32 + (size_t)sp.n_shifts * (SEARCH_THREADS / 32) * 8 + 256;
+    const long long ctas = sp.n < (long long)ctx->sm_count * 8 ? sp.n : (long long)ctx->sm_count * 8;
+    // behind a tensor-core launch the CUDA-core kernel runs guarded: it leaves at once unless that kernel found scan
+    // counts above 2048 (not exact in fp16) ON THE DEVICE and left the search to this one — no host round trip
+    if (used) sp.only_if_bailed = reinterpret_cast<const int*>(ctx->scal.as<float>() + SC_MMA_BAILED);
     k_score_search<SEARCH_THREADS, SEARCH_JMAX><<<(unsigned)ctas, SEARCH_THREADS, smem, ctx->stream>>>(sp, 0);
     count_launch(ctx);
     TDR_CUDA(cudaGetLastError());
@@ -451,7 +453,11 @@ int score_grid(tdr_ctx* ctx, long long n, float scale, float res) {
     if (!used) { if (int e = score_mma(ctx, res, true, n, scale, sp.shifts, ctx->grid_shifts_host.data(), sp.n_shifts, &used)) return e; }
     if (!used && ctx->mma_kernel != 1 && !ctx->grid_n_peers) { if (int e = score_mma_list(ctx, res, true, n, scale, sp.shifts, sp.n_shifts, &used)) return e; }
   }
-  if (used) return TDR_OK;
+  // the tensor-core kernels check the fp16 exactness of the scan counts on the device; behind one of them the CUDA-core
+  // kernel is launched guarded (runs only if that one bailed out).  The fused peer all-gather has no such fallback:
+  // tdr_grid_best_key reports a bail-out there.
+  if (used && (ctx->grid_n_peers || P > SEARCH_THREADS * SEARCH_JMAX)) return TDR_OK;
+  if (used) sp.only_if_bailed = reinterpret_cast<const int*>(ctx->scal.as<float>() + SC_MMA_BAILED);
   TDR_REQUIRE(ctx->grid_n_peers == 0, TDR_EUNSUPPORTED, "the fused peer all-gather needs the tensor-core ring kernel (n_theta <= 112 and even, distinct shifts)");
   TDR_REQUIRE(P <= SEARCH_THREADS * SEARCH_JMAX, TDR_EUNSUPPORTED, "polar image too large");
   TDR_SMEM_OPTIN(ctx, OPTIN_SCORE_SEARCH, (k_score_search<SEARCH_THREADS, SEARCH_JMAX>), 200 * 1024);

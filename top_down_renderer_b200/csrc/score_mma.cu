@@ -106,12 +106,20 @@ struct MmaParams {
   float* cost_peers[TDR_MAX_PEERS]; int n_cost_peers; long long cost_row0;
   unsigned long long* grid_key;     // grid mode: (min cost, first global flat index) over everything this launch computes
   int identity_shifts;      // shifts[k] == k for all k and n_shifts % 4 == 0: vector stores of the cost rows
+  const int* maxcount; int* bailed;     // device-side fp16 exactness precondition, see score_mma_list.cu
 };
 
 static const int MAX_RING_ROWS = 2 * RING_N;                  // n_theta <= RING_N
 static const int RING_SLOT_BYTES = 2 * MAX_RING_ROWS * 16;    // 2 K chunks
 static const int NB2 = 4, B2_BYTES = 2 * RING_N * 16;         // tot-block slots (one block per 16 cells)
-static const int NA2 = 3, A2_TILE = 4096;                     // known-flag operand buffers (128 rows x 16 cells)
+// known-flag operand buffers (128 rows x 16 cells), one per 16-cell group in flight.  A gather thread may run kStages
+// stages ahead of the stage the MMA warp has retired, and the last group of a batch is SHORT (P / G stages is not a
+// multiple of the stages per group), so kStages + 1 consecutive stages can touch FOUR groups: the tail of one, the
+// short one, a whole one of the next batch and the head of the one after.  With three buffers that fourth group
+// overwrote the flags of the first before its normalisation MMA had read them (round 1: run-to-run differences of
+// ~7e-5 in ~0.1 % of the grid costs whenever the long grid epilogue let the other thread sets run ahead —
+// tools/determinism.py).  Needs kStages <= 2 x stages per group (asserted in MmaCfg).
+static const int NA2 = 4, A2_TILE = 4096;
 static const int CELLS_PER_GROUP = 16;
 static const int OUT_STRIDE = RING_N;              // floats per staged cost row (16-byte multiple, >= n_theta)
 // T = 128-hypothesis tiles per CTA; R = gather threads per hypothesis row (the R threads of a row take turns
@@ -119,7 +127,7 @@ static const int OUT_STRIDE = RING_N;              // floats per staged cost row
 // footprint — that are in flight together)
 // ATM (T = 1 only) = the gathered records and the known-flag operand live in TENSOR MEMORY (tcgen05.st; the MMA takes A
 // from there): no operand stores through the L1 data pipe and no operand reads by the tensor core out of shared
-// memory.  TMEM columns: [0, 224) accumulators | [224, 248) NA2 flag groups | [248, 504) 16 stages x 2 cells x 8.
+// memory.  TMEM columns: [0, 224) accumulators | [224, 256) NA2 flag groups | [256, 512) 16 stages x 2 cells x 8.
 // G = lattice cells per pipeline stage (2, or 4 on the tensor-memory path): the per-stage handshake of the single
 // MMA-issuing warp (~90 instructions) is what bounds this kernel once the operands are off the L1 pipe, so a stage
 // carries as many cells as the registers of the gather threads allow.
@@ -143,12 +151,17 @@ template <int T, int R, bool ATM, int G> struct MmaCfg {
   static const int kStages = ATM ? ((512 - kACol) / kACols > 16 ? 16 : (512 - kACol) / kACols) : kStagesSm;
   static const int kSmem = kStages * kStageBytes + kFixed;
   static_assert(!ATM || T == 1, "the tensor-memory operand path holds one tile per CTA");
+  static_assert(kStages <= 2 * (CELLS_PER_GROUP / G), "NA2 = 4 flag buffers cover at most 2 x stages-per-group stages in flight");
   static_assert(G == 2 || (ATM && G == 4), "4-cell stages exist on the tensor-memory path only");
 };
 
 template <int T, int R, bool ATM, int G>
 __global__ void __launch_bounds__(128 * T * R + 64, MmaCfg<T, R, ATM, G>::kCtasPerSm) k_score_mma(MmaParams sp) {
   using Cfg = MmaCfg<T, R, ATM, G>;
+  if (*sp.maxcount > MMA_MAX_EXACT_COUNT) {          // grid-uniform, before anything is allocated
+    if (blockIdx.x == 0 && threadIdx.x == 0) *sp.bailed = 1;
+    return;
+  }
   constexpr int STAGES_PER_GROUP = CELLS_PER_GROUP / G;
   constexpr int GW = 4 * T * R;        // gather warps
   constexpr int NS = Cfg::kStages;
@@ -609,7 +622,7 @@ int score_mma(tdr_ctx* ctx, float res, bool grid_mode, long long n_items, float 
   if (int e = ctx->scan_op.reserve(ring_total + (size_t)n_groups * B2_BYTES)) return e;
   uint4* d_norm_op = reinterpret_cast<uint4*>(ctx->scan_op.as<unsigned char>() + ring_total);
   int* d_max = reinterpret_cast<int*>(ctx->scal.as<float>() + SC_MMA_MAXCOUNT);
-  TDR_CUDA(cudaMemsetAsync(d_max, 0, 4, ctx->stream));
+  TDR_CUDA(cudaMemsetAsync(d_max, 0, 8, ctx->stream));     // max count, "tensor-core kernel bailed out" flag
   {
     const int total = ctx->n_r * ring_rows;
     k_build_rings<<<(total + 255) / 256, 256, 0, ctx->stream>>>(ctx->scan_img.as<float>(), ctx->C, ctx->n_theta, ctx->n_r,
@@ -619,10 +632,8 @@ int score_mma(tdr_ctx* ctx, float res, bool grid_mode, long long n_items, float 
     count_launch(ctx, 2);
     TDR_CUDA(cudaGetLastError());
   }
-  int h_max = 0;
-  TDR_CUDA(cudaMemcpyAsync(&h_max, d_max, 4, cudaMemcpyDeviceToHost, ctx->stream));
-  TDR_CUDA(cudaStreamSynchronize(ctx->stream));
-  if (h_max > 2048) return TDR_OK;              // counts not exact in fp16: CUDA-core path
+  // counts above 2048 are not exact in fp16: checked ON THE DEVICE (sp.maxcount), the caller launches the guarded
+  // CUDA-core kernel behind this one
 
   if (int e = build_perm(ctx, grid_mode, n_items)) return e;
   tdr::Particles& pt = ctx->part[ctx->cur];
@@ -635,6 +646,7 @@ int score_mma(tdr_ctx* ctx, float res, bool grid_mode, long long n_items, float 
   sp.rings = ctx->scan_op.as<uint4>(); sp.norm_op = d_norm_op; sp.n_groups = n_groups;
   sp.perm = ctx->perm.as<int>();
   sp.shifts = dev_shifts; sp.n_shifts = n_shifts;
+  sp.maxcount = d_max; sp.bailed = d_max + 1;
   if (grid_mode) {
     sp.n_work = n_items; sp.centers = ctx->grid_centers.as<float>(); sp.grid_scale = grid_scale;
     sp.costs = grid_costs_ptr(ctx);

@@ -1,0 +1,478 @@
+// score_mma_i8.cu — a7/a9/a10, the 40-shift theta search, as an INTEGER tcgen05 gather-GEMM on 16-byte map records.
+//
+// Reference: TopDownMapPolar::getLocalMap (src/top_down_map_polar.cpp:21-53), StateParticle::getCostForRot
+// (src/state_particle.cpp:112-155), StateParticle::computeWeight (:157-219).
+//
+// Why a second operand format (profiles/r02_gather_microbench.txt, profiles/r02_list_counters.md): the
+// fp16 hi/lo kernel (score_mma_list.cu) reads one 32-byte record per (hypothesis, cell) and is bound by L1 wavefronts —
+// 24.9 per warp load measured, one per distinct 128-byte line inside a half warp (x ~1.2 for partly used lines), at
+// most one per clock and SM.  A 128-byte line of that layout holds 4 pixels.  Here a pixel is 16 bytes:
+//     bytes 2c, 2c+1 : hi / lo byte of v_c = round(w_c * dist_c / q), q = 50 max(w) / 65535      (c < 7)
+//     byte  14       : known (0 / 1)                      byte 15: 0
+// so a line holds 8 pixels of a map row and neighbouring hypotheses share lines twice as often; one 128-bit load per
+// (hypothesis, cell) — 1.9 records / clk / SM measured for warps whose lanes lie within 8 x 8 px (tools/tex_bench.cu),
+// against 1.5 for 256-bit loads of pixel pairs and 1.0 for the 32-byte records.  The kernel was ISSUE-bound on its
+// gather threads (78 instructions per record, profiles/r02_i8_ncu.md), so the index arithmetic is fixed point
+// (tdr_math.cuh lattice_fixed) on a table pre-multiplied by scale * res * 4096 in constant memory — which needs ONE
+// scale for all hypotheses of a launch (FilterParams::fixed_scale; checked on the device).
+// Two cells make one K = 32 step of tcgen05.mma.kind::i8 (u8 x u8 -> s32, exact):
+//     A[m, 16 j + b]  = byte b of the record of hypothesis m at cell 2k + j                       (tensor memory)
+//     B rows n = s        : u8 class counts of the shifted scan cell at the hi bytes    -> Xhi[s]      (s < S <= 40)
+//            n = 40 + s   : the same counts at the lo bytes                              -> Xlo[s]
+//            n = 80 + s   : the class-summed count at the known byte                     -> norm[s]
+//            n = 120      : 1 at the known byte                                          -> number of known cells
+//     cost[s] = 0.01 q (256 Xhi[s] + Xlo[s]) / norm[s]
+// Integer sums are exact; the only error is the 16-bit quantisation of w_c * dist_c: |d cost| <= 0.01 q / 2, i.e. a
+// relative weight error <= 0.005 q / regularization.  The host takes this path only where that bound is below 9e-6
+// (regularization >= 0.42 max(w): the launch file's 0.7 qualifies, the code default 0.15 does not) and the scan
+// counts fit a byte (checked on the device; the guarded CUDA-core launch behind the kernel takes over otherwise).
+#include "mma_common.cuh"
+
+namespace tdr {
+
+static const int I8_N = 128;              // accumulator columns per tile
+static const int I8_S_MAX = 40;           // candidate shifts: 3 S + 1 <= 128 with the blocks on multiples of 8 columns
+static const int I8_MAX_COUNT = 255;
+
+__device__ __forceinline__ void umma_i8_ts(uint32_t d_tmem, uint32_t a_tmem, uint64_t bdesc, uint32_t idesc, uint32_t accumulate) {
+  asm volatile(
+      "{\n\t"
+      ".reg .pred p;\n\t"
+      "setp.ne.b32 p, %4, 0;\n\t"
+      "tcgen05.mma.cta_group::1.kind::i8 [%0], [%1], %2, %3, p;\n\t"
+      "}" ::"r"(d_tmem), "r"(a_tmem), "l"(bdesc), "r"(idesc), "r"(accumulate)
+      : "memory");
+}
+__device__ __forceinline__ void tmem_ld8(uint32_t taddr, uint32_t* v) {
+  asm volatile("tcgen05.ld.sync.aligned.32x32b.x8.b32 {%0, %1, %2, %3, %4, %5, %6, %7}, [%8];"
+               : "=r"(v[0]), "=r"(v[1]), "=r"(v[2]), "=r"(v[3]), "=r"(v[4]), "=r"(v[5]), "=r"(v[6]), "=r"(v[7])
+               : "r"(taddr));
+}
+
+// ------------------------------------------------------------------------------------------------
+// the 16-byte map copy
+// ------------------------------------------------------------------------------------------------
+// row-major, `pitch` records per map row; one all-zero record past the map is what cells off the map read
+struct Geom8 {
+  uint32_t pitch, zero_rec;
+  uint32_t lim_y, lim_x;           // 4096 rows - 1, 4096 cols - 1 (lattice_fixed)
+};
+
+static __global__ void k_build_map8(const MapPixel* __restrict__ map, size_t n, int C, const float* __restrict__ cw,
+                                    float inv_q, uint4* __restrict__ out) {
+  const size_t i = (size_t)blockIdx.x * blockDim.x + threadIdx.x;
+  if (i >= n) return;
+  const float4* src = reinterpret_cast<const float4*>(map + i);
+  const float4 a = src[0], b = src[1];
+  const float v[8] = {a.x, a.y, a.z, a.w, b.x, b.y, b.z, b.w};
+  uint32_t w[4] = {0u, 0u, 0u, 0u};
+#pragma unroll
+  for (int k = 0; k < 7; k++) {
+    uint32_t q = 0;
+    if (k < C) {
+      float x = TDR_FMUL(TDR_FMUL(cw[k], v[k]), inv_q);
+      x = fminf(fmaxf(x, 0.f), 65535.f);
+      q = __float2uint_rn(x);
+    }
+    // bytes 2k (hi), 2k + 1 (lo)
+    w[k >> 1] |= ((q >> 8) | ((q & 0xffu) << 8)) << ((k & 1) * 16);
+  }
+  if (v[7] != 0.f) w[3] |= 1u << 16;            // byte 14: known
+  out[i] = make_uint4(w[0], w[1], w[2], w[3]);
+}
+
+// one scale for every hypothesis of the launch?  (min, max) of the scale bits over the particles still to be searched
+static __global__ void k_scale_range(const float* __restrict__ scale, const uint8_t* __restrict__ have_init, long long n,
+                                     uint32_t* __restrict__ range /* [min, max] of the (positive) float bits */) {
+  uint32_t lo = 0xffffffffu, hi = 0u;
+  for (long long i = (long long)blockIdx.x * blockDim.x + threadIdx.x; i < n; i += (long long)gridDim.x * blockDim.x)
+    if (!have_init[i]) { const uint32_t b = __float_as_uint(scale[i]); lo = min(lo, b); hi = max(hi, b); }
+  for (int o = 16; o > 0; o >>= 1) { lo = min(lo, __shfl_xor_sync(0xffffffffu, lo, o)); hi = max(hi, __shfl_xor_sync(0xffffffffu, hi, o)); }
+  if ((threadIdx.x & 31) == 0 && lo <= hi) { atomicMin(range, lo); atomicMax(range + 1, hi); }
+}
+// table of lattice offsets for that scale: ((tab * scale) * res) * 4096, padding cells far off every map
+static __global__ void k_scale_tab4096(const float2* __restrict__ tab, int P, int P_pad, const uint32_t* __restrict__ range, float res,
+                                       float2* __restrict__ out, int* __restrict__ bailed) {
+  const int p = blockIdx.x * blockDim.x + threadIdx.x;
+  if (p == 0 && range[0] != range[1]) *bailed = 1;           // mixed scales (or negative / NaN bits): not this kernel's case
+  if (p >= P_pad) return;
+  const float scale = __uint_as_float(range[0]);
+  out[p] = p < P ? make_float2(TDR_FMUL(TDR_FMUL(TDR_FMUL(tab[p].x, scale), res), 4096.f), TDR_FMUL(TDR_FMUL(TDR_FMUL(tab[p].y, scale), res), 4096.f))
+                 : make_float2(1e30f, 1e30f);
+}
+
+// scan operand, per stage k (cells 2k, 2k + 1): [kc = 2][n = N][16 B] (K-major canonical layout, LBO = N*16, SBO = 128);
+// chunk kc holds the 16 K slots of cell 2k + kc.  One thread per (stage, n).
+static __global__ void k_build_scan_operand_i8(const float* __restrict__ img, int C, int n_theta, int P, int n_stages,
+                                               const int32_t* __restrict__ shifts, int S, uint4* __restrict__ out,
+                                               int* __restrict__ maxcount) {
+  const long long id = (long long)blockIdx.x * blockDim.x + threadIdx.x;
+  if (id >= (long long)n_stages * I8_N) return;
+  const int k = (int)(id / I8_N), n = (int)(id - (long long)k * I8_N);
+  uint4* stage = out + (size_t)k * I8_N * 2;
+#pragma unroll
+  for (int j = 0; j < 2; j++) {
+    const int p = 2 * k + j;
+    uint32_t w[4] = {0u, 0u, 0u, 0u};
+    const int s = n % I8_S_MAX, kind = n / I8_S_MAX;                     // row blocks of I8_S_MAX: 0 hi, 1 lo, 2 norm; then the probe
+    if (p < P && (n == 3 * I8_S_MAX || (kind < 3 && s < S))) {
+      if (n == 3 * I8_S_MAX) w[3] = 1u << 16;                           // probe row: counts the known cells
+      else {
+        const int r = p / n_theta, th = p - r * n_theta;
+        int t2 = th + shifts[s];
+        t2 %= n_theta; if (t2 < 0) t2 += n_theta;
+        const int cell = r * n_theta + t2;                              // scan row (theta + shift) pairs with map row theta
+        float tot = 0.f;
+        for (int c = 0; c < C; c++) {
+          const float v = img[(size_t)c * P + cell];
+          tot += v;
+          const uint32_t u = (uint32_t)fminf(fmaxf(v, 0.f), 255.f);
+          if (kind == 0) w[c >> 1] |= u << ((c & 1) * 16);              // byte 2c
+          else if (kind == 1) w[c >> 1] |= u << ((c & 1) * 16 + 8);     // byte 2c + 1
+        }
+        if (kind == 2) {
+          w[3] = (uint32_t)fminf(fmaxf(tot, 0.f), 255.f) << 16;         // byte 14
+          if (s == 0) atomicMax(maxcount, (int)fminf(tot, 1e9f));       // shift[0] is a bijection of the cells: global max
+        }
+      }
+    }
+    stage[j * I8_N + n] = make_uint4(w[0], w[1], w[2], w[3]);
+  }
+}
+
+struct I8Params {
+  const uint4* map8; Geom8 geom; float resolution;
+  int n_stages; int P;
+  const uint4* bop;
+  const int* perm; long long n_work;
+  const float *init_x, *init_y, *dx, *dy; float* theta; const float* scale; uint8_t* have_init; float* weights;
+  int force_on_map; float map_w, map_h; int scale_gate; double scale_lo, scale_hi; float regularization;
+  const float* thetas; int n_shifts;
+  float q001;                       // 0.01 * q: accumulator units -> cost
+  const int* maxcount; int* bailed; // device-side preconditions: scan counts fit a byte, one scale for all hypotheses
+};
+
+// T = 128-hypothesis tiles per CTA, R = gather threads per hypothesis row (they take turns stage by stage),
+// F = stages every gather thread keeps in flight (2 cells = two 128-bit loads each)
+template <int T, int R, int F> struct I8Cfg {
+  static const int kThreads = 128 * T * R + 64;
+  static const int kBBytes = I8_N * 32;                    // scan operand of one stage (2 cells)
+  static const int kACols = T * 8;                         // TMEM columns of one stage of A
+  static const int kStagesMax = (512 - T * I8_N) / kACols;
+  static const int kStages = kStagesMax > 16 ? 16 : kStagesMax;
+  static const int kSmem = kStages * kBBytes + 512;        // + barriers (2 * kStages + 1) and the TMEM base word
+  static_assert(kStages >= R * F, "every stage a thread has in flight needs its own slot");
+};
+
+template <int T, int R, int F>
+__global__ void __launch_bounds__(128 * T * R + 64, 1) k_score_mma_i8(I8Params sp) {
+  using Cfg = I8Cfg<T, R, F>;
+  constexpr int N = I8_N;
+  constexpr int GW = 4 * T * R;        // gather warps
+  constexpr int NS = Cfg::kStages;
+  if (*sp.maxcount > I8_MAX_COUNT || *sp.bailed) {   // grid-uniform, before anything is allocated
+    if (blockIdx.x == 0 && threadIdx.x == 0) *sp.bailed = 1;
+    return;
+  }
+  extern __shared__ __align__(128) unsigned char smem[];
+  unsigned char* sB = smem;                                                   // [NS][kc 2][N][16 B]
+  uint64_t* bars = reinterpret_cast<uint64_t*>(smem + (size_t)NS * Cfg::kBBytes);   // full[NS] empty[NS] accum
+  uint32_t* s_tmem = reinterpret_cast<uint32_t*>(bars + 2 * NS + 1);
+  const int tid = threadIdx.x, warp = tid >> 5, lane = tid & 31;
+  const uint32_t bar_full = smem_u32(bars), bar_empty = smem_u32(bars + NS), bar_accum = smem_u32(bars + 2 * NS);
+
+  if (warp == GW + 1) tmem_alloc(smem_u32(s_tmem), 512);
+  if (tid == 0) {
+    for (int s = 0; s < NS; s++) { mbar_init(bar_full + 8 * s, 4 * T + 1); mbar_init(bar_empty + 8 * s, 1); }
+    mbar_init(bar_accum, 1);
+    fence_barrier_init();
+  }
+  tc_fence_before();
+  __syncthreads();
+  tc_fence_after();
+  const uint32_t tmem_base = *s_tmem;
+
+  const long long per_batch = 128 * T;
+  const long long n_batches = (sp.n_work + per_batch - 1) / per_batch;
+  const int K_ITERS = sp.n_stages;
+  uint32_t local_batch = 0;
+
+  if (warp < GW) {
+    // =========================== gather + epilogue ===========================
+    const int sub = warp / (4 * T);                      // which of the R threads of a row this is
+    const int t = (warp % (4 * T)) >> 2;
+    const uint4* map8 = sp.map8;
+    uint32_t it = 0;                                      // pipeline iteration of the batch's first stage (same sequence in every role)
+    const uint32_t tcol0 = tmem_base + ((uint32_t)((warp & 3) * 32) << 16) + (uint32_t)(T * N + t * 8);
+    for (long long batch = blockIdx.x; batch < n_batches; batch += gridDim.x, local_batch++) {
+      const long long slot = batch * per_batch + (tid % (128 * T));
+      long long i = -1;
+      if (slot < sp.n_work) i = sp.perm ? (long long)sp.perm[slot] : slot;
+      float cx = 0.f, cy = 0.f;
+      bool active = false, gated = false;
+      if (i >= 0) {
+        const float sc = sp.scale[i];
+        cx = TDR_FADD(TDR_FMUL(sp.dx[i], sc), sp.init_x[i]);
+        cy = TDR_FADD(TDR_FMUL(sp.dy[i], sc), sp.init_y[i]);
+        if (sp.force_on_map && (cx < 0.f || cy < 0.f || cx > sp.map_w || cy > sp.map_h)) gated = true;      // :163-168
+        if (sp.scale_gate && ((double)sc < sp.scale_lo || (double)sc > sp.scale_hi)) gated = true;          // :169-176
+        active = !gated;
+      }
+      // centre / resolution, times 4096 (exact); a NaN centre or an idle row reads the zero record everywhere
+      const float oy = TDR_FMUL(TDR_FDIV(cy, sp.resolution), 4096.f), ox = TDR_FMUL(TDR_FDIV(cx, sp.resolution), 4096.f);
+      if (!(oy == oy) || !(ox == ox)) active = false;
+      const uint32_t lim_y = active ? sp.geom.lim_y : 0u, lim_x = sp.geom.lim_x;
+      // slot / parity of THIS thread's next store: iteration it + sub, then + R per stage
+      uint32_t st = (it + (uint32_t)sub) % NS, ph = ((it + (uint32_t)sub) / NS) & 1u;
+
+      // one 128-bit load per cell: the 16-byte record of this hypothesis' lattice pixel (top_down_map_polar.cpp:28-37)
+      auto load_stage = [&](int k, uint4 (&rec)[2]) {
+#pragma unroll
+        for (int g = 0; g < 2; g++) {
+          const float2 tb = c_tab[2 * k + g];              // ((tab * scale) * res) * 4096; padding cells: far off the map
+          const uint32_t ty = (uint32_t)__float2int_rz(TDR_FADD(tb.x, oy)) + 2047u;
+          const uint32_t tx = (uint32_t)__float2int_rz(TDR_FADD(tb.y, ox)) + 2047u;
+          uint32_t r = ((ty + 1u) >> 12) * sp.geom.pitch + ((tx + 1u) >> 12);
+          if (!(ty < lim_y && tx < lim_x)) r = sp.geom.zero_rec;
+          rec[g] = __ldg(map8 + r);
+        }
+      };
+      auto store_stage = [&](const uint4 (&rec)[2]) {
+        mbar_wait(bar_empty + 8 * st, ph ^ 1u);
+        // row m of the A tile = TMEM lane m (this warp's quarter), 8 columns = 32 K slots: cell 2k | cell 2k + 1
+        tmem_st8(tcol0 + st * Cfg::kACols, rec[0], rec[1]);
+        tmem_wait_st();
+        tc_fence_before();
+        __syncwarp();
+        if (lane == 0) mbar_arrive(bar_full + 8 * st);
+        st += R; if (st >= NS) { st -= NS; ph ^= 1u; }
+      };
+
+      // software pipeline of depth F over this thread's stages sub, sub + R, ...: F - 1 loads ahead of every store
+      uint4 buf[F][2];
+      const int J = (K_ITERS - sub + R - 1) / R;         // this thread's stages
+#pragma unroll
+      for (int f = 0; f < F - 1; f++) if (f < J) load_stage(sub + f * R, buf[f]);
+#pragma unroll 1
+      for (int j = 0; j < J; j += F) {
+#pragma unroll
+        for (int f = 0; f < F; f++) {
+          const int jj = j + f;
+          if (jj + F - 1 < J) load_stage(sub + (jj + F - 1) * R, buf[(f + F - 1) % F]);
+          if (jj < J) store_stage(buf[f]);
+        }
+      }
+      it += (uint32_t)K_ITERS;
+      if (sub != 0) continue;                            // the first thread of each row owns the epilogue
+
+      // ---- epilogue: this thread's accumulator row (s32)
+      mbar_wait(bar_accum, local_batch & 1u);
+      tc_fence_after();
+      const uint32_t trow = tmem_base + ((uint32_t)((warp & 3) * 32) << 16) + (uint32_t)(t * N);
+      const int S = sp.n_shifts;
+      const uint32_t kraw = tmem_ld1(trow + (uint32_t)(3 * I8_S_MAX));
+      tmem_wait_ld();
+      const bool unknown = (double)TDR_FDIV((float)(int)kraw, (float)sp.P) < 0.5;                // :117-120
+      float best = 3.402823466e+38f, best_theta = 0.f;                                           // :193-204
+      uint32_t vh[8], vl[8], vn[8];
+#pragma unroll 1
+      for (int ch = 0; ch * 8 < S; ch++) {
+        tmem_ld8(trow + (uint32_t)(ch * 8), vh);
+        tmem_ld8(trow + (uint32_t)(I8_S_MAX + ch * 8), vl);
+        tmem_ld8(trow + (uint32_t)(2 * I8_S_MAX + ch * 8), vn);
+        tmem_wait_ld();
+#pragma unroll
+        for (int j = 0; j < 8; j++) {
+          const int s = ch * 8 + j;
+          if (s < S) {
+            const float num = fmaf((float)(int)vh[j], 256.f, (float)(int)vl[j]);
+            const float cost = unknown ? __int_as_float(0x7fc00000) : TDR_FDIV(TDR_FMUL(num, sp.q001), (float)(int)vn[j]);   // :137,154
+            if (cost < best) { best = cost; best_theta = sp.thetas[s]; }
+          }
+        }
+      }
+      if (i >= 0) {
+        if (gated) sp.weights[i] = 0.f;
+        else {
+          sp.theta[i] = best_theta;
+          sp.have_init[i] = 1;
+          sp.weights[i] = (float)(1.0 / (double)TDR_FADD(best, sp.regularization));             // :212
+        }
+      }
+      tc_fence_before();           // TMEM reads are done before the next batch's first full-barrier arrive
+    }
+  } else if (warp == GW) {
+    // =========================== scan-operand loader ===========================
+    const bool leader = elect_one();
+    const uint32_t sB_u = smem_u32(sB);
+    uint32_t st = 0, ph = 0;
+    for (long long batch = blockIdx.x; batch < n_batches; batch += gridDim.x) {
+      const unsigned char* src = reinterpret_cast<const unsigned char*>(sp.bop);
+      for (int k = 0; k < K_ITERS; k++, src += Cfg::kBBytes) {
+        mbar_wait(bar_empty + 8 * st, ph ^ 1u);
+        if (leader) {
+          mbar_expect_tx(bar_full + 8 * st, Cfg::kBBytes);
+          bulk_g2s(sB_u + st * Cfg::kBBytes, src, Cfg::kBBytes, bar_full + 8 * st);
+        }
+        __syncwarp();
+        if (++st == NS) { st = 0; ph ^= 1u; }
+      }
+    }
+  } else {
+    // =========================== MMA issuer ===========================
+    // instruction descriptor: D = s32, A = B = u8, both K-major, N, M = 128 (K = 32)
+    const bool leader = elect_one();
+    const uint32_t idesc = (2u << 4) | ((uint32_t)(N >> 3) << 17) | ((uint32_t)(128 >> 4) << 24);
+    const uint32_t sB_u = smem_u32(sB);
+    uint32_t st = 0, ph = 0;
+    for (long long batch = blockIdx.x; batch < n_batches; batch += gridDim.x) {
+      for (int k = 0; k < K_ITERS; k++) {
+        mbar_wait(bar_full + 8 * st, ph);
+        tc_fence_after();
+        if (leader) {
+          const uint64_t bdesc = umma_desc(sB_u + st * Cfg::kBBytes, N * 16, 128);
+#pragma unroll
+          for (int tt = 0; tt < T; tt++)
+            umma_i8_ts(tmem_base + (uint32_t)(tt * N), tmem_base + (uint32_t)(T * N + tt * 8) + st * Cfg::kACols, bdesc, idesc, k > 0 ? 1u : 0u);
+          umma_commit(bar_empty + 8 * st);        // implies tcgen05.fence::before_thread_sync
+          if (k == K_ITERS - 1) umma_commit(bar_accum);
+        }
+        __syncwarp();
+        if (++st == NS) { st = 0; ph ^= 1u; }
+      }
+    }
+  }
+  tc_fence_before();
+  __syncthreads();
+  if (warp == GW + 1) tmem_dealloc(tmem_base, 512);
+}
+
+// ------------------------------------------------------------------------------------------------
+// host side
+// ------------------------------------------------------------------------------------------------
+// worst-case relative weight error of the 16-bit records: 0.005 q / regularization, q = 50 max(w) / 65535
+static bool i8_usable(tdr_ctx* ctx, int n_shifts, float* q_out) {
+  if (ctx->score_impl == 1 || ctx->mma_i8 == 0) return false;
+  if (n_shifts < 1 || n_shifts > I8_S_MAX || ctx->C > 7) return false;
+  float wmax = 0.f;
+  for (int c = 0; c < ctx->C; c++) {
+    const float w = ctx->fp.class_weights[c];
+    if (!(w >= 0.f) || w > 1e4f) return false;
+    if (w > wmax) wmax = w;
+  }
+  if (!(wmax > 0.f) || !(ctx->fp.regularization > 0.f)) return false;
+  const float q = 50.f * wmax / 65535.f;
+  *q_out = q;
+  if (ctx->mma_i8 == 2) return true;                       // forced (tests of the kernel itself)
+  return 0.005 * (double)q / (double)ctx->fp.regularization <= 9e-6;
+}
+
+static int build_map8(tdr_ctx* ctx, float q, const uint4** out, Geom8* geom) {
+  const size_t n_rec = (size_t)ctx->rows * ctx->cols;
+  TDR_REQUIRE(n_rec < (1ull << 31) && ctx->rows < (1 << 19) && ctx->cols < (1 << 19), TDR_EUNSUPPORTED,
+              "map too large for the 16-byte copy (%zu records)", n_rec);
+  geom->pitch = (uint32_t)ctx->cols; geom->zero_rec = (uint32_t)n_rec;
+  geom->lim_y = 4096u * (uint32_t)ctx->rows - 1u; geom->lim_x = 4096u * (uint32_t)ctx->cols - 1u;
+  if (!ctx->map8_valid || ctx->map8_q != q) {
+    if (int e = ctx->map8.reserve((n_rec + 1) * 16)) return e;
+    TDR_CUDA(cudaMemsetAsync(ctx->map8.as<unsigned char>() + n_rec * 16, 0, 16, ctx->stream));      // the all-zero record
+    k_build_map8<<<(unsigned)((n_rec + 255) / 256), 256, 0, ctx->stream>>>(ctx->map_px.as<MapPixel>(), n_rec, ctx->C, ctx->d_cw.as<float>(),
+                                                                            1.f / q, ctx->map8.as<uint4>());
+    count_launch(ctx);
+    TDR_CUDA(cudaGetLastError());
+    ctx->map8_valid = true; ctx->map8_q = q;
+  }
+  *out = ctx->map8.as<uint4>();
+  return TDR_OK;
+}
+
+// returns TDR_OK and sets *used = true when the integer tensor-core path was launched (it may still leave the work to
+// the guarded CUDA-core launch behind it: scan counts above 255, decided on the device)
+int score_mma_i8(tdr_ctx* ctx, float res, const int32_t* dev_shifts, int n_shifts, bool* used) {
+  *used = false;
+  float q = 0.f;
+  if (!i8_usable(ctx, n_shifts, &q)) return TDR_OK;
+  const int P = ctx->n_theta * ctx->n_r;
+  if (P + 3 > MMA_TAB_MAX) return TDR_OK;
+  // the previous scan's maximum count predicts whether this one fits a byte (the device check decides)
+  if (ctx->scan_max_pending && cudaEventQuery(ctx->scan_max_ev) == cudaSuccess) { ctx->scan_max_seen = *ctx->scan_max_pin; ctx->scan_max_pending = false; }
+  if (ctx->mma_i8 != 2 && ctx->scan_max_seen > I8_MAX_COUNT) return TDR_OK;
+  const int n_stages = ((P + 1) / 2 + 1) / 2 * 2;            // even number of stages keeps the 2x unroll simple
+  if (int e = ctx->scan_op.reserve((size_t)n_stages * I8_N * 32)) return e;
+  int* d_max = reinterpret_cast<int*>(ctx->scal.as<float>() + SC_MMA_MAXCOUNT);
+  TDR_CUDA(cudaMemsetAsync(d_max, 0, 8, ctx->stream));       // max count, "tensor-core kernel bailed out" flag
+  {
+    const long long total = (long long)n_stages * I8_N;
+    k_build_scan_operand_i8<<<(unsigned)((total + 255) / 256), 256, 0, ctx->stream>>>(ctx->scan_img.as<float>(), ctx->C, ctx->n_theta, P,
+                                                                                       n_stages, dev_shifts, n_shifts, ctx->scan_op.as<uint4>(), d_max);
+    count_launch(ctx);
+    TDR_CUDA(cudaGetLastError());
+    TDR_CUDA(cudaMemcpyAsync(ctx->scan_max_pin, d_max, 4, cudaMemcpyDeviceToHost, ctx->stream));
+    TDR_CUDA(cudaEventRecord(ctx->scan_max_ev, ctx->stream));
+    ctx->scan_max_pending = true;
+  }
+  if (int e = build_perm(ctx, false, ctx->part[ctx->cur].n, ctx->mma_sort == 1)) return e;
+  tdr::Particles& pt = ctx->part[ctx->cur];
+  // the lattice offsets for this launch's scale and radial resolution, x 4096, into constant memory; the scale comes
+  // from the particles themselves (one value for all of them, else the kernel leaves the search to the CUDA cores)
+  {
+    uint32_t* d_range = reinterpret_cast<uint32_t*>(ctx->scal.as<float>() + SC_MMA_SCALE_RANGE);
+    const uint32_t init_range[2] = {0xffffffffu, 0u};
+    TDR_CUDA(cudaMemcpyAsync(d_range, init_range, 8, cudaMemcpyHostToDevice, ctx->stream));
+    const int blocks = (int)((pt.n + 1023) / 1024 < ctx->sm_count * 4 ? (pt.n + 1023) / 1024 : ctx->sm_count * 4);
+    k_scale_range<<<blocks < 1 ? 1 : blocks, 256, 0, ctx->stream>>>(pt.scale.as<float>(), pt.have_init.as<uint8_t>(), pt.n, d_range);
+    if (int e = ctx->tab_scaled.reserve((size_t)n_stages * 2 * 8)) return e;
+    k_scale_tab4096<<<(n_stages * 2 + 255) / 256, 256, 0, ctx->stream>>>(ctx->tab.as<float2>(), P, n_stages * 2, d_range, res,
+                                                                          ctx->tab_scaled.as<float2>(), d_max + 1);
+    count_launch(ctx, 2);
+    TDR_CUDA(cudaGetLastError());
+    TDR_CUDA(cudaMemcpyToSymbolAsync(c_tab, ctx->tab_scaled.p, (size_t)n_stages * 2 * 8, 0, cudaMemcpyDeviceToDevice, ctx->stream));
+    g_tab_on_device[ctx->device % MMA_MAX_DEVICES] = 0;
+  }
+  I8Params sp; memset(&sp, 0, sizeof(sp));
+  if (int e = build_map8(ctx, q, &sp.map8, &sp.geom)) return e;
+  sp.resolution = ctx->resolution; sp.P = P; sp.n_stages = n_stages;
+  sp.bop = ctx->scan_op.as<uint4>();
+  sp.perm = ctx->perm.as<int>();
+  sp.n_shifts = n_shifts;
+  sp.q001 = 0.01f * q;
+  sp.maxcount = d_max; sp.bailed = d_max + 1;
+  sp.n_work = ctx->n_uninit;
+  sp.init_x = pt.init_x.as<float>(); sp.init_y = pt.init_y.as<float>(); sp.dx = pt.dx.as<float>(); sp.dy = pt.dy.as<float>();
+  sp.theta = pt.theta.as<float>(); sp.scale = pt.scale.as<float>(); sp.have_init = pt.have_init.as<uint8_t>();
+  sp.weights = ctx->weights.as<float>();
+  sp.force_on_map = ctx->fp.force_on_map;
+  sp.map_w = (float)ctx->cols * ctx->resolution; sp.map_h = (float)ctx->rows * ctx->resolution;
+  sp.scale_gate = ctx->fp.fixed_scale < 0 ? 1 : 0;
+  sp.scale_lo = pow(10.0, (double)ctx->fp.scale_log_min); sp.scale_hi = pow(10.0, (double)ctx->fp.scale_log_max);
+  sp.regularization = ctx->fp.regularization;
+  sp.thetas = ctx->d_search_thetas.as<float>();
+#define TDR_LAUNCH_I8(IDX, TT, RR, FF)                                                                                \
+  do {                                                                                                                \
+    using Cfg = I8Cfg<TT, RR, FF>;                                                                                    \
+    TDR_SMEM_OPTIN(ctx, OPTIN_TILE_BASE + IDX, (k_score_mma_i8<TT, RR, FF>), Cfg::kSmem);                             \
+    const long long nb = (sp.n_work + 128 * TT - 1) / (128 * TT);                                                     \
+    long long cap = ctx->sm_count;                                                                                    \
+    if (ctx->mma_grid_cap > 0 && ctx->mma_grid_cap < cap) cap = ctx->mma_grid_cap;                                    \
+    const int grid = (int)(nb < cap ? nb : cap);                                                                      \
+    k_score_mma_i8<TT, RR, FF><<<grid, Cfg::kThreads, Cfg::kSmem, ctx->stream>>>(sp);                                 \
+  } while (0)
+  switch (ctx->mma_i8_cfg) {                     // tiles * 100 + threads per row * 10 + stages in flight (TDR_MMA_I8_CFG)
+    case 212: TDR_LAUNCH_I8(0, 2, 1, 2); break;
+    case 214: TDR_LAUNCH_I8(1, 2, 1, 4); break;
+    case 222: TDR_LAUNCH_I8(2, 2, 2, 2); break;
+    case 223: TDR_LAUNCH_I8(3, 2, 2, 3); break;
+    case 233: TDR_LAUNCH_I8(5, 2, 3, 3); break;
+    case 142: TDR_LAUNCH_I8(6, 1, 4, 2); break;
+    case 144: TDR_LAUNCH_I8(7, 1, 4, 4); break;
+    case 224: TDR_LAUNCH_I8(8, 2, 2, 4); break;
+    default: TDR_LAUNCH_I8(4, 2, 3, 2); break;
+  }
+#undef TDR_LAUNCH_I8
+  count_launch(ctx);
+  TDR_CUDA(cudaGetLastError());
+  *used = true;
+  return TDR_OK;
+}
+
+}  // namespace tdr

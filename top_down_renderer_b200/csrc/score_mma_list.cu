@@ -67,6 +67,9 @@ struct ListParams {
   const float* thetas; int n_shifts;
   // grid mode
   const float* centers; float grid_scale; float* costs;
+  // device-side precondition: fp16 holds integer counts exactly up to 2048.  Above that the kernel leaves at once and
+  // the guarded CUDA-core launch that follows does the work (no host round trip to decide)
+  const int* maxcount; int* bailed;
 };
 
 
@@ -98,6 +101,10 @@ __global__ void __launch_bounds__(128 * T * R + 64, ListCfg<N, T, R, ATM>::kCtas
   constexpr int GW = 4 * T * R;        // gather warps
   constexpr int NS = Cfg::kStages;
   constexpr int S_PAD = N / 2;
+  if (*sp.maxcount > MMA_MAX_EXACT_COUNT) {          // grid-uniform, before anything is allocated
+    if (blockIdx.x == 0 && threadIdx.x == 0) *sp.bailed = 1;
+    return;
+  }
   extern __shared__ __align__(128) unsigned char smem[];
   unsigned char* sA = smem;                                  // [NS][G][T] tiles of A_TILE bytes
   unsigned char* sB = smem + (size_t)NS * Cfg::kABytes;       // [NS][G][kc 2][N][16 B]
@@ -322,7 +329,7 @@ int score_mma_list(tdr_ctx* ctx, float res, bool grid_mode, long long n_items, f
   // ---- scan operand (+ max count check: fp16 integers are exact up to 2048)
   if (int e = ctx->scan_op.reserve((size_t)P_pad * N * 32)) return e;
   int* d_max = reinterpret_cast<int*>(ctx->scal.as<float>() + SC_MMA_MAXCOUNT);
-  TDR_CUDA(cudaMemsetAsync(d_max, 0, 4, ctx->stream));
+  TDR_CUDA(cudaMemsetAsync(d_max, 0, 8, ctx->stream));     // max count, "tensor-core kernel bailed out" flag
   {
     long long total = (long long)P_pad * N;
     k_build_scan_operand<<<(unsigned)((total + 255) / 256), 256, 0, ctx->stream>>>(
@@ -330,11 +337,14 @@ int score_mma_list(tdr_ctx* ctx, float res, bool grid_mode, long long n_items, f
         ctx->scan_op.as<uint4>(), d_max);
     count_launch(ctx);
     TDR_CUDA(cudaGetLastError());
+    if (!grid_mode) {          // feeds the operand-format predictor of score_mma_i8.cu
+      TDR_CUDA(cudaMemcpyAsync(ctx->scan_max_pin, d_max, 4, cudaMemcpyDeviceToHost, ctx->stream));
+      TDR_CUDA(cudaEventRecord(ctx->scan_max_ev, ctx->stream));
+      ctx->scan_max_pending = true;
+    }
   }
-  int h_max = 0;
-  TDR_CUDA(cudaMemcpyAsync(&h_max, d_max, 4, cudaMemcpyDeviceToHost, ctx->stream));
-  TDR_CUDA(cudaStreamSynchronize(ctx->stream));
-  if (h_max > 2048) return TDR_OK;              // counts not exact in fp16: CUDA-core path
+  // counts above 2048 are not exact in fp16: checked ON THE DEVICE (sp.maxcount), the caller launches the guarded
+  // CUDA-core kernel behind this one
 
   if (int e = build_perm(ctx, grid_mode, n_items)) return e;
   tdr::Particles& pt = ctx->part[ctx->cur];
@@ -347,6 +357,7 @@ int score_mma_list(tdr_ctx* ctx, float res, bool grid_mode, long long n_items, f
   sp.bop = ctx->scan_op.as<uint4>();
   sp.perm = ctx->perm.as<int>();
   sp.n_shifts = n_shifts;
+  sp.maxcount = d_max; sp.bailed = d_max + 1;
   if (grid_mode) {
     sp.n_work = n_items; sp.centers = ctx->grid_centers.as<float>(); sp.grid_scale = grid_scale;
     sp.costs = ctx->grid_costs.as<float>();

@@ -117,8 +117,23 @@ struct tdr_ctx {
   int mma_split = 2;         // gather threads per hypothesis row (tuning: TDR_MMA_SPLIT)
   int mma_a_tmem = 1;        // list kernel: gathered records to tensor memory instead of shared (tuning: TDR_MMA_A_TMEM)
   int mma_ring_cfg = 413;    // ring kernel: tiles * 10 + threads per row, + 100 operands in tensor memory, + 400 and 4-cell stages (tuning: TDR_MMA_RING_CFG)
-  int mma_kernel = 0;        // 0 auto, 1 streamed-operand kernel only, 2 ring kernel only (tuning: TDR_MMA_KERNEL)
+  int mma_kernel = 0;        // 0 auto (integer kernel, else streamed-operand, else ring), 1 streamed-operand fp16 kernel only,
+                             // 2 ring kernel only, 3 integer kernel first (= auto) (tuning: TDR_MMA_KERNEL)
   int mma_ctas = 0;          // cap on co-resident CTAs per SM (0 = as many as TMEM allows; tuning: TDR_MMA_CTAS)
+  int mma_i8 = 1;            // integer 16-byte-record theta search (score_mma_i8.cu): 0 off, 1 where its error bound holds,
+                             // 2 always (tests of the kernel itself; TDR_MMA_I8)
+  int mma_i8_cfg = 232;      // integer kernel: tiles * 100 + gather threads per row * 10 + stages in flight per thread (TDR_MMA_I8_CFG)
+  int mma_sort = 0;          // integer kernel, hypothesis order inside a super-tile: 0 = pixel row, 4-px segment (its records are
+                             // row-major); 1 = Morton over 2 x 2-px cells (TDR_MMA_SORT)
+  tdr::DevBuf map8;          // rows*cols x 16 B: u16 fixed-point class distances (hi / lo bytes) + known, 4 x 2-px blocks
+  bool map8_valid = false;
+  float map8_q = 0.f;        // its quantum
+  // the previous scan's largest class-summed count, read back lazily: predicts which operand format the next scan fits
+  // (u8 <= 255, fp16 <= 2048); the kernels re-check on the device
+  int scan_max_seen = 0;
+  bool scan_max_pending = false;
+  cudaEvent_t scan_max_ev = nullptr;
+  int* scan_max_pin = nullptr;
   int mma_grid_cap = 0;      // cap on the grid of the persistent score kernels (0 = none; TDR_MMA_GRID_CAP — tests use it to
                              // make every CTA walk many batches)
   int mma_st_shift = 10;     // log2 of the binning super-tile side in px (tuning: TDR_MMA_ST_SHIFT)
@@ -210,6 +225,8 @@ enum {
   SC_SUM = 0, SC_NVALID, SC_MEAN, SC_BS, SC_NUNDER, SC_FALLBACK,     // stats (6 floats, ABI order)
   SC_S1, SC_S2, SC_REP, SC_ARGMAX /*int*/, SC_ARGVAL, SC_BSRAW /* sequential sum of lower squared deviations */,
   SC_MMA_MAXCOUNT = 12,     // int: max class-summed scan count (fp16 exactness check of the tensor-core path)
+  SC_MMA_SCALE_RANGE = 14,  // 2 x uint32: min / max scale bits over the particles of an integer-kernel launch
+  SC_MMA_BAILED = 13,       // int: the tensor-core kernel found counts above 2048 and left the work to the CUDA cores
   SC_CHAIN = 16,            // 8 chain totals
   SC_DBL = 32,              // doubles from here (8-byte aligned): sumsq, count_valid, count_under ...
   SC_POSE = 64,             // pose scalars
@@ -263,6 +280,8 @@ int score_mma(tdr_ctx*, float res, bool grid_mode, long long n_items, float grid
 // score_mma_list.cu
 int score_mma_list(tdr_ctx*, float res, bool grid_mode, long long n_items, float grid_scale, const int32_t* dev_shifts,
                    int n_shifts, bool* used);
+// score_mma_i8.cu
+int score_mma_i8(tdr_ctx*, float res, const int32_t* dev_shifts, int n_shifts, bool* used);
 // weights.cu
 int normalize(tdr_ctx*, bool lazy_stddev = false);   // lazy: skip the lower-half deviation when no weight is NaN (stats[3] undefined then)
 int build_prefix(tdr_ctx*);

@@ -220,6 +220,27 @@ TDR_HD int lattice_round(float v) {                    // round_half_away(v) as 
 }
 TDR_HD int lattice_coord(float v, float hi) { return lattice_in(v, hi) ? lattice_round(v) : -1; }
 
+// The same decision once more, in fixed point, for a coordinate that arrives pre-multiplied by 4096 (exact: scaling both
+// addends of tab*scale*res + centre by a power of two commutes with the rounding of their sum).  With t = trunc(v4096) +
+// 2047, -0.5 < v < n - 0.5 holds exactly when 0 <= t <= 4096 n - 2, and then round_half_away(v) = (t + 1) >> 12:
+// FADD, F2I, IADD, ISETP, IADD, SHF per coordinate (score_mma_i8.cu is issue-bound on its gather threads).  The
+// conversion saturates (cvt.rzi.s32.f32): huge and infinite values wrap past the limit and are off the map like in the
+// reference; NaN converts to 0 — callers mark a hypothesis with a NaN centre inactive themselves.  n < 2^19.
+TDR_HD int f2i_sat(float v) {
+#if defined(__CUDA_ARCH__)
+  return __float2int_rz(v);
+#else
+  if (v != v) return 0;
+  if (v >= 2147483648.0f) return INT_MAX;
+  if (v <= -2147483648.0f) return INT_MIN;
+  return (int)v;
+#endif
+}
+TDR_HD int lattice_fixed(float v4096, uint32_t lim /* 4096 n - 1 */) {
+  const uint32_t t = (uint32_t)f2i_sat(v4096) + 2047u;
+  return t < lim ? (int)((t + 1u) >> 12) : -1;
+}
+
 // a10 rot -> row shift   state_particle.cpp:123-128
 TDR_HD int rot_to_shift(float rot, int n_theta) {
   double v = (double)TDR_FDIV(TDR_FMUL(rot, (float)n_theta), 2.0f) / 3.14159265358979323846;
