@@ -163,6 +163,8 @@ int tdr_create(tdr_ctx** out, int device) {
   if (const char* e = getenv("TDR_MMA_CTAS")) c->mma_ctas = atoi(e);
   if (const char* e = getenv("TDR_MMA_I8")) { int v = atoi(e); if (v >= 0 && v <= 2) c->mma_i8 = v; }
   if (const char* e = getenv("TDR_MMA_I8_CFG")) c->mma_i8_cfg = atoi(e);
+  if (const char* e = getenv("TDR_MMA_TEX")) c->mma_tex = atoi(e) ? 1 : 0;
+  if (const char* e = getenv("TDR_MMA_SKIP_RINGS")) c->mma_skip_rings = atoi(e) ? 1 : 0;
   if (const char* e = getenv("TDR_MMA_SORT")) { int v = atoi(e); if (v >= 0 && v <= 1) c->mma_sort = v; }
   if (const char* e = getenv("TDR_MMA_GRID_CAP")) { int v = atoi(e); if (v > 0) c->mma_grid_cap = v; }
   if (const char* e = getenv("TDR_MMA_ST_SHIFT")) { int v = atoi(e); if (v >= 5 && v <= 16) c->mma_st_shift = v; }
@@ -196,6 +198,7 @@ void tdr_destroy(tdr_ctx* c) {
   c->uninit_dev.release();
   if (c->uninit_ev) cudaEventDestroy(c->uninit_ev);
   if (c->uninit_pin) cudaFreeHost(c->uninit_pin);
+  if (c->map8_tex) cudaDestroyTextureObject((cudaTextureObject_t)c->map8_tex);
   c->map8.release();
   if (c->scan_max_ev) cudaEventDestroy(c->scan_max_ev);
   if (c->scan_max_pin) cudaFreeHost(c->scan_max_pin);

@@ -33,6 +33,7 @@ namespace tdr {
 static const int I8_N = 128;              // accumulator columns per tile
 static const int I8_S_MAX = 40;           // candidate shifts: 3 S + 1 <= 128 with the blocks on multiples of 8 columns
 static const int I8_MAX_COUNT = 255;
+static const int PLAN_HDR = 4;            // ints in front of the cell lists of a scan plan (k_plan_cells)
 
 __device__ __forceinline__ void umma_i8_ts(uint32_t d_tmem, uint32_t a_tmem, uint64_t bdesc, uint32_t idesc, uint32_t accumulate) {
   asm volatile(
@@ -42,6 +43,12 @@ __device__ __forceinline__ void umma_i8_ts(uint32_t d_tmem, uint32_t a_tmem, uin
       "tcgen05.mma.cta_group::1.kind::i8 [%0], [%1], %2, %3, p;\n\t"
       "}" ::"r"(d_tmem), "r"(a_tmem), "l"(bdesc), "r"(idesc), "r"(accumulate)
       : "memory");
+}
+// unfiltered texel fetch with integer coordinates; outside the texture the border colour (zeros) comes back
+__device__ __forceinline__ uint4 tex_fetch(unsigned long long tex, int x, int y) {
+  uint4 v;
+  asm("tex.2d.v4.u32.s32 {%0, %1, %2, %3}, [%4, {%5, %6}];" : "=r"(v.x), "=r"(v.y), "=r"(v.z), "=r"(v.w) : "l"(tex), "r"(x), "r"(y));
+  return v;
 }
 __device__ __forceinline__ void tmem_ld8(uint32_t taddr, uint32_t* v) {
   asm volatile("tcgen05.ld.sync.aligned.32x32b.x8.b32 {%0, %1, %2, %3, %4, %5, %6, %7}, [%8];"
@@ -90,32 +97,99 @@ static __global__ void k_scale_range(const float* __restrict__ scale, const uint
   for (int o = 16; o > 0; o >>= 1) { lo = min(lo, __shfl_xor_sync(0xffffffffu, lo, o)); hi = max(hi, __shfl_xor_sync(0xffffffffu, hi, o)); }
   if ((threadIdx.x & 31) == 0 && lo <= hi) { atomicMin(range, lo); atomicMax(range + 1, hi); }
 }
-// table of lattice offsets for that scale: ((tab * scale) * res) * 4096, padding cells far off every map
-static __global__ void k_scale_tab4096(const float2* __restrict__ tab, int P, int P_pad, const uint32_t* __restrict__ range, float res,
-                                       float2* __restrict__ out, int* __restrict__ bailed) {
-  const int p = blockIdx.x * blockDim.x + threadIdx.x;
-  if (p == 0 && range[0] != range[1]) *bailed = 1;           // mixed scales (or negative / NaN bits): not this kernel's case
-  if (p >= P_pad) return;
+// table of lattice offsets for that scale, ((tab * scale) * res) * 4096, in PLAN order: the gathered cells (padding: far
+// off every map), then from entry 2 x stages on the skipped ones
+static __global__ void k_scale_tab4096(const float2* __restrict__ tab, int P, const int* __restrict__ plan, const uint32_t* __restrict__ range,
+                                       float res, float2* __restrict__ out, int* __restrict__ bailed) {
+  const int j = blockIdx.x * blockDim.x + threadIdx.x;
+  const int P_cap = (P + 3) & ~3;
+  if (j == 0 && range[0] != range[1]) *bailed = 1;           // mixed scales (or negative / NaN bits): not this kernel's case
+  const int n_gather = 2 * plan[2];
+  if (j >= n_gather + plan[1]) return;
   const float scale = __uint_as_float(range[0]);
-  out[p] = p < P ? make_float2(TDR_FMUL(TDR_FMUL(TDR_FMUL(tab[p].x, scale), res), 4096.f), TDR_FMUL(TDR_FMUL(TDR_FMUL(tab[p].y, scale), res), 4096.f))
-                 : make_float2(1e30f, 1e30f);
+  const int p = j < n_gather ? plan[PLAN_HDR + j] : plan[PLAN_HDR + P_cap + (j - n_gather)];
+  out[j] = p >= 0 ? make_float2(TDR_FMUL(TDR_FMUL(TDR_FMUL(tab[p].x, scale), res), 4096.f), TDR_FMUL(TDR_FMUL(TDR_FMUL(tab[p].y, scale), res), 4096.f))
+                  : make_float2(1e30f, 1e30f);
 }
 
-// scan operand, per stage k (cells 2k, 2k + 1): [kc = 2][n = N][16 B] (K-major canonical layout, LBO = N*16, SBO = 128);
-// chunk kc holds the 16 K slots of cell 2k + kc.  One thread per (stage, n).
-static __global__ void k_build_scan_operand_i8(const float* __restrict__ img, int C, int n_theta, int P, int n_stages,
+// Which lattice cells does this scan need?  A lattice cell (theta, r) meets the scan cells (theta + s, r) of the S
+// candidate shifts; if none of them holds a single return in any class, the cell contributes nothing to any cost or
+// normalisation and is not gathered at all (top_down_map_polar.cpp:21-53 per cell is the dominant cost) — whole rings
+// beyond the sensor's range, and most of the sparse outer ones.  Only the "mostly unknown" test
+// (state_particle.cpp:117-120) still needs the known flags of the skipped cells: the kernel's epilogue counts them
+// exactly, and only for the hypotheses whose answer the gathered cells leave open.
+// plan: [0] gathered cells  [1] skipped cells  [2] stages (2 cells each, >= 1)  [3] unused | gathered[P_cap] | skipped[P_cap]
+static __global__ void __launch_bounds__(1024) k_plan_cells(const float* __restrict__ img, int C, int n_theta, int n_r,
+                                                            const int32_t* __restrict__ shifts, int S, int skip_on, int* __restrict__ plan) {
+  __shared__ float s_tot[MMA_TAB_MAX];
+  __shared__ int s_w[32];
+  __shared__ int s_shift[TDR_MAX_SHIFTS];
+  const int P = n_theta * n_r, P_cap = (P + 3) & ~3;
+  for (int p = threadIdx.x; p < P; p += blockDim.x) {
+    float t = 0.f;
+    for (int c = 0; c < C; c++) t += img[(size_t)c * P + p];
+    s_tot[p] = t;
+  }
+  for (int k = threadIdx.x; k < S; k += blockDim.x) { int v = shifts[k] % n_theta; s_shift[k] = v < 0 ? v + n_theta : v; }
+  __syncthreads();
+  // this thread's cells: 4 consecutive ones (P <= 4096)
+  int live[4], n_live = 0;
+#pragma unroll
+  for (int q = 0; q < 4; q++) {
+    const int p = threadIdx.x * 4 + q;
+    live[q] = 0;
+    if (p < P) {
+      if (!skip_on) live[q] = 1;
+      else {
+        const int r = p / n_theta, th = p - r * n_theta;
+        for (int k = 0; k < S && !live[q]; k++) {
+          int t2 = th + s_shift[k]; if (t2 >= n_theta) t2 -= n_theta;
+          if (s_tot[r * n_theta + t2] != 0.f) live[q] = 1;              // counts are >= 0: a zero sum means every class is 0
+        }
+      }
+      n_live += live[q];
+    }
+  }
+  int total;
+  int pos = block_excl_scan(n_live, s_w, &total);
+  int* act = plan + PLAN_HDR;
+  int* skp = act + P_cap;
+#pragma unroll
+  for (int q = 0; q < 4; q++) {
+    const int p = threadIdx.x * 4 + q;
+    if (p < P) {
+      if (live[q]) act[pos++] = p;
+    }
+  }
+  // skipped cells: the same scan on the complement
+  int n_dead = 0;
+#pragma unroll
+  for (int q = 0; q < 4; q++) { const int p = threadIdx.x * 4 + q; if (p < P && !live[q]) n_dead++; }
+  int total_dead;
+  int dpos = block_excl_scan(n_dead, s_w, &total_dead);
+#pragma unroll
+  for (int q = 0; q < 4; q++) { const int p = threadIdx.x * 4 + q; if (p < P && !live[q]) skp[dpos++] = p; }
+  for (int j = total + threadIdx.x; j < P_cap; j += blockDim.x) act[j] = -1;            // padding of the last stage
+  if (threadIdx.x == 0) { plan[0] = total; plan[1] = total_dead; plan[2] = total > 0 ? (total + 1) / 2 : 1; plan[3] = 0; }
+}
+
+// scan operand, per stage k (cells act[2k], act[2k + 1]): [kc = 2][n = N][16 B] (K-major canonical layout, LBO = N*16,
+// SBO = 128); chunk kc holds the 16 K slots of the stage's cell kc.  One thread per (stage, n).
+static __global__ void k_build_scan_operand_i8(const float* __restrict__ img, int C, int n_theta, int P, const int* __restrict__ plan,
                                                const int32_t* __restrict__ shifts, int S, uint4* __restrict__ out,
                                                int* __restrict__ maxcount) {
   const long long id = (long long)blockIdx.x * blockDim.x + threadIdx.x;
+  const int n_stages = plan[2];
   if (id >= (long long)n_stages * I8_N) return;
   const int k = (int)(id / I8_N), n = (int)(id - (long long)k * I8_N);
+  const int* act = plan + PLAN_HDR;
   uint4* stage = out + (size_t)k * I8_N * 2;
 #pragma unroll
   for (int j = 0; j < 2; j++) {
-    const int p = 2 * k + j;
+    const int p = act[2 * k + j];
     uint32_t w[4] = {0u, 0u, 0u, 0u};
     const int s = n % I8_S_MAX, kind = n / I8_S_MAX;                     // row blocks of I8_S_MAX: 0 hi, 1 lo, 2 norm; then the probe
-    if (p < P && (n == 3 * I8_S_MAX || (kind < 3 && s < S))) {
+    if (p >= 0 && (n == 3 * I8_S_MAX || (kind < 3 && s < S))) {
       if (n == 3 * I8_S_MAX) w[3] = 1u << 16;                           // probe row: counts the known cells
       else {
         const int r = p / n_theta, th = p - r * n_theta;
@@ -132,7 +206,7 @@ static __global__ void k_build_scan_operand_i8(const float* __restrict__ img, in
         }
         if (kind == 2) {
           w[3] = (uint32_t)fminf(fmaxf(tot, 0.f), 255.f) << 16;         // byte 14
-          if (s == 0) atomicMax(maxcount, (int)fminf(tot, 1e9f));       // shift[0] is a bijection of the cells: global max
+          if (s == 0) atomicMax(maxcount, (int)fminf(tot, 1e9f));       // every non-empty scan cell X is met at shift 0 by the gathered cell X - shift[0]: the max over all counts in play
         }
       }
     }
@@ -142,12 +216,14 @@ static __global__ void k_build_scan_operand_i8(const float* __restrict__ img, in
 
 struct I8Params {
   const uint4* map8; Geom8 geom; float resolution;
-  int n_stages; int P;
+  const int* plan; int P, P_cap;      // the scan plan (k_plan_cells)
+  const float2* tab_g;                // the constant table's global twin (divergent indices: the epilogue's lookups): [0] gathered cells [1] skipped cells [2] stages
   const uint4* bop;
   const int* perm; long long n_work;
   const float *init_x, *init_y, *dx, *dy; float* theta; const float* scale; uint8_t* have_init; float* weights;
   int force_on_map; float map_w, map_h; int scale_gate; double scale_lo, scale_hi; float regularization;
   const float* thetas; int n_shifts;
+  unsigned long long tex;           // the same records as a pitch-linear 2-D texture (border = zero record); 0: not used
   float q001;                       // 0.01 * q: accumulator units -> cost
   const int* maxcount; int* bailed; // device-side preconditions: scan counts fit a byte, one scale for all hypotheses
 };
@@ -164,7 +240,10 @@ template <int T, int R, int F> struct I8Cfg {
   static_assert(kStages >= R * F, "every stage a thread has in flight needs its own slot");
 };
 
-template <int T, int R, int F>
+// TEX: the second cell of every stage comes through the texture pipe instead of the LSU — the kernel is bound by L1
+// data-pipe wavefronts of its 128-bit loads (84 % busy, profiles/r02_i8_ncu.md) and the two front ends together deliver
+// more records per clock than either alone (2.27 against 1.9, tools/tex_bench.cu)
+template <int T, int R, int F, bool TEX>
 __global__ void __launch_bounds__(128 * T * R + 64, 1) k_score_mma_i8(I8Params sp) {
   using Cfg = I8Cfg<T, R, F>;
   constexpr int N = I8_N;
@@ -194,7 +273,7 @@ __global__ void __launch_bounds__(128 * T * R + 64, 1) k_score_mma_i8(I8Params s
 
   const long long per_batch = 128 * T;
   const long long n_batches = (sp.n_work + per_batch - 1) / per_batch;
-  const int K_ITERS = sp.n_stages;
+  const int K_ITERS = sp.plan[2];
   uint32_t local_batch = 0;
 
   if (warp < GW) {
@@ -232,9 +311,13 @@ __global__ void __launch_bounds__(128 * T * R + 64, 1) k_score_mma_i8(I8Params s
           const float2 tb = c_tab[2 * k + g];              // ((tab * scale) * res) * 4096; padding cells: far off the map
           const uint32_t ty = (uint32_t)__float2int_rz(TDR_FADD(tb.x, oy)) + 2047u;
           const uint32_t tx = (uint32_t)__float2int_rz(TDR_FADD(tb.y, ox)) + 2047u;
-          uint32_t r = ((ty + 1u) >> 12) * sp.geom.pitch + ((tx + 1u) >> 12);
-          if (!(ty < lim_y && tx < lim_x)) r = sp.geom.zero_rec;
-          rec[g] = __ldg(map8 + r);
+          const bool ok = ty < lim_y && tx < lim_x;
+          if (TEX && g == 1) rec[g] = tex_fetch(sp.tex, ok ? (int)((tx + 1u) >> 12) : -1, (int)((ty + 1u) >> 12));
+          else {
+            uint32_t r = ((ty + 1u) >> 12) * sp.geom.pitch + ((tx + 1u) >> 12);
+            if (!ok) r = sp.geom.zero_rec;
+            rec[g] = __ldg(map8 + r);
+          }
         }
       };
       auto store_stage = [&](const uint4 (&rec)[2]) {
@@ -272,7 +355,28 @@ __global__ void __launch_bounds__(128 * T * R + 64, 1) k_score_mma_i8(I8Params s
       const int S = sp.n_shifts;
       const uint32_t kraw = tmem_ld1(trow + (uint32_t)(3 * I8_S_MAX));
       tmem_wait_ld();
-      const bool unknown = (double)TDR_FDIV((float)(int)kraw, (float)sp.P) < 0.5;                // :117-120
+      // known cells: the gathered ones were counted by the probe row; the cells of the skipped (empty) rings only matter
+      // when they can still tip the "less than half known" test, and are looked up one by one then
+      int known = (int)kraw;
+      const int n_skip = sp.plan[1];
+      const bool open_q = i >= 0 && !gated && n_skip > 0 && 2 * known < sp.P && 2 * (known + n_skip) >= sp.P;
+      // the warp settles its open rows one after the other, 32 skipped cells at a time (6 % of cfg3's particles)
+      unsigned need = __ballot_sync(0xffffffffu, open_q);
+      while (need) {
+        const int src = __ffs(need) - 1;
+        need &= need - 1;
+        const float soy = __shfl_sync(0xffffffffu, oy, src), sox = __shfl_sync(0xffffffffu, ox, src);
+        int cnt = 0;
+        for (int m = lane; m < n_skip; m += 32) {
+          const float2 tb = sp.tab_g[2 * K_ITERS + m];
+          const uint32_t ty = (uint32_t)__float2int_rz(TDR_FADD(tb.x, soy)) + 2047u;
+          const uint32_t tx = (uint32_t)__float2int_rz(TDR_FADD(tb.y, sox)) + 2047u;
+          if (ty < sp.geom.lim_y && tx < lim_x) cnt += (int)((__ldg(map8 + (((ty + 1u) >> 12) * sp.geom.pitch + ((tx + 1u) >> 12))).w >> 16) & 1u);
+        }
+        for (int o = 16; o > 0; o >>= 1) cnt += __shfl_xor_sync(0xffffffffu, cnt, o);
+        if (lane == src) known += cnt;
+      }
+      const bool unknown = (double)TDR_FDIV((float)known, (float)sp.P) < 0.5;                    // :117-120
       float best = 3.402823466e+38f, best_theta = 0.f;                                           // :193-204
       uint32_t vh[8], vl[8], vn[8];
 #pragma unroll 1
@@ -381,6 +485,20 @@ static int build_map8(tdr_ctx* ctx, float q, const uint4** out, Geom8* geom) {
     count_launch(ctx);
     TDR_CUDA(cudaGetLastError());
     ctx->map8_valid = true; ctx->map8_q = q;
+    // the same buffer as a pitch-linear 2-D texture of uint4 texels; outside it reads the border colour = the zero record
+    if (ctx->map8_tex) { cudaDestroyTextureObject((cudaTextureObject_t)ctx->map8_tex); ctx->map8_tex = 0; }
+    if (ctx->mma_tex && ((size_t)ctx->cols * 16) % 32 == 0) {
+      cudaResourceDesc rd; memset(&rd, 0, sizeof(rd));
+      rd.resType = cudaResourceTypePitch2D;
+      rd.res.pitch2D.devPtr = ctx->map8.p; rd.res.pitch2D.desc = cudaCreateChannelDesc<uint4>();
+      rd.res.pitch2D.width = (size_t)ctx->cols; rd.res.pitch2D.height = (size_t)ctx->rows; rd.res.pitch2D.pitchInBytes = (size_t)ctx->cols * 16;
+      cudaTextureDesc td; memset(&td, 0, sizeof(td));
+      td.addressMode[0] = td.addressMode[1] = cudaAddressModeBorder; td.filterMode = cudaFilterModePoint;
+      td.readMode = cudaReadModeElementType; td.normalizedCoords = 0;
+      cudaTextureObject_t t = 0;
+      if (cudaCreateTextureObject(&t, &rd, &td, nullptr) == cudaSuccess) ctx->map8_tex = (unsigned long long)t;
+      else (void)cudaGetLastError();                  // size beyond the linear-texture limits: loads only
+    }
   }
   *out = ctx->map8.as<uint4>();
   return TDR_OK;
@@ -393,19 +511,22 @@ int score_mma_i8(tdr_ctx* ctx, float res, const int32_t* dev_shifts, int n_shift
   float q = 0.f;
   if (!i8_usable(ctx, n_shifts, &q)) return TDR_OK;
   const int P = ctx->n_theta * ctx->n_r;
-  if (P + 3 > MMA_TAB_MAX) return TDR_OK;
+  if (((P + 3) & ~3) + 4 > MMA_TAB_MAX) return TDR_OK;         // gathered (+ padding) and skipped cells share the constant table
   // the previous scan's maximum count predicts whether this one fits a byte (the device check decides)
   if (ctx->scan_max_pending && cudaEventQuery(ctx->scan_max_ev) == cudaSuccess) { ctx->scan_max_seen = *ctx->scan_max_pin; ctx->scan_max_pending = false; }
   if (ctx->mma_i8 != 2 && ctx->scan_max_seen > I8_MAX_COUNT) return TDR_OK;
-  const int n_stages = ((P + 1) / 2 + 1) / 2 * 2;            // even number of stages keeps the 2x unroll simple
-  if (int e = ctx->scan_op.reserve((size_t)n_stages * I8_N * 32)) return e;
+  const int P_cap = (P + 3) & ~3, max_stages = P_cap / 2;
+  if (int e = ctx->scan_op.reserve((size_t)max_stages * I8_N * 32 + (size_t)(PLAN_HDR + 2 * P_cap) * 4)) return e;
+  int* d_plan = reinterpret_cast<int*>(ctx->scan_op.as<unsigned char>() + (size_t)max_stages * I8_N * 32);
   int* d_max = reinterpret_cast<int*>(ctx->scal.as<float>() + SC_MMA_MAXCOUNT);
   TDR_CUDA(cudaMemsetAsync(d_max, 0, 8, ctx->stream));       // max count, "tensor-core kernel bailed out" flag
   {
-    const long long total = (long long)n_stages * I8_N;
+    k_plan_cells<<<1, 1024, 0, ctx->stream>>>(ctx->scan_img.as<float>(), ctx->C, ctx->n_theta, ctx->n_r, dev_shifts, n_shifts,
+                                              ctx->mma_skip_rings, d_plan);
+    const long long total = (long long)max_stages * I8_N;
     k_build_scan_operand_i8<<<(unsigned)((total + 255) / 256), 256, 0, ctx->stream>>>(ctx->scan_img.as<float>(), ctx->C, ctx->n_theta, P,
-                                                                                       n_stages, dev_shifts, n_shifts, ctx->scan_op.as<uint4>(), d_max);
-    count_launch(ctx);
+                                                                                       d_plan, dev_shifts, n_shifts, ctx->scan_op.as<uint4>(), d_max);
+    count_launch(ctx, 2);
     TDR_CUDA(cudaGetLastError());
     TDR_CUDA(cudaMemcpyAsync(ctx->scan_max_pin, d_max, 4, cudaMemcpyDeviceToHost, ctx->stream));
     TDR_CUDA(cudaEventRecord(ctx->scan_max_ev, ctx->stream));
@@ -421,21 +542,23 @@ int score_mma_i8(tdr_ctx* ctx, float res, const int32_t* dev_shifts, int n_shift
     TDR_CUDA(cudaMemcpyAsync(d_range, init_range, 8, cudaMemcpyHostToDevice, ctx->stream));
     const int blocks = (int)((pt.n + 1023) / 1024 < ctx->sm_count * 4 ? (pt.n + 1023) / 1024 : ctx->sm_count * 4);
     k_scale_range<<<blocks < 1 ? 1 : blocks, 256, 0, ctx->stream>>>(pt.scale.as<float>(), pt.have_init.as<uint8_t>(), pt.n, d_range);
-    if (int e = ctx->tab_scaled.reserve((size_t)n_stages * 2 * 8)) return e;
-    k_scale_tab4096<<<(n_stages * 2 + 255) / 256, 256, 0, ctx->stream>>>(ctx->tab.as<float2>(), P, n_stages * 2, d_range, res,
-                                                                          ctx->tab_scaled.as<float2>(), d_max + 1);
+    if (int e = ctx->tab_scaled.reserve((size_t)(P_cap + 4) * 8)) return e;
+    k_scale_tab4096<<<(P_cap + 4 + 255) / 256, 256, 0, ctx->stream>>>(ctx->tab.as<float2>(), P, d_plan, d_range, res,
+                                                                       ctx->tab_scaled.as<float2>(), d_max + 1);
     count_launch(ctx, 2);
     TDR_CUDA(cudaGetLastError());
-    TDR_CUDA(cudaMemcpyToSymbolAsync(c_tab, ctx->tab_scaled.p, (size_t)n_stages * 2 * 8, 0, cudaMemcpyDeviceToDevice, ctx->stream));
+    TDR_CUDA(cudaMemcpyToSymbolAsync(c_tab, ctx->tab_scaled.p, (size_t)(P_cap + 4) * 8, 0, cudaMemcpyDeviceToDevice, ctx->stream));
     g_tab_on_device[ctx->device % MMA_MAX_DEVICES] = 0;
   }
   I8Params sp; memset(&sp, 0, sizeof(sp));
   if (int e = build_map8(ctx, q, &sp.map8, &sp.geom)) return e;
-  sp.resolution = ctx->resolution; sp.P = P; sp.n_stages = n_stages;
+  sp.resolution = ctx->resolution; sp.P = P; sp.P_cap = P_cap; sp.plan = d_plan;
   sp.bop = ctx->scan_op.as<uint4>();
   sp.perm = ctx->perm.as<int>();
   sp.n_shifts = n_shifts;
   sp.q001 = 0.01f * q;
+  sp.tab_g = ctx->tab_scaled.as<float2>();
+  sp.tex = ctx->map8_tex;
   sp.maxcount = d_max; sp.bailed = d_max + 1;
   sp.n_work = ctx->n_uninit;
   sp.init_x = pt.init_x.as<float>(); sp.init_y = pt.init_y.as<float>(); sp.dx = pt.dx.as<float>(); sp.dy = pt.dy.as<float>();
@@ -450,23 +573,24 @@ int score_mma_i8(tdr_ctx* ctx, float res, const int32_t* dev_shifts, int n_shift
 #define TDR_LAUNCH_I8(IDX, TT, RR, FF)                                                                                \
   do {                                                                                                                \
     using Cfg = I8Cfg<TT, RR, FF>;                                                                                    \
-    TDR_SMEM_OPTIN(ctx, OPTIN_TILE_BASE + IDX, (k_score_mma_i8<TT, RR, FF>), Cfg::kSmem);                             \
+    if (sp.tex) TDR_SMEM_OPTIN(ctx, OPTIN_TILE_BASE + IDX, (k_score_mma_i8<TT, RR, FF, true>), Cfg::kSmem);           \
+    else TDR_SMEM_OPTIN(ctx, OPTIN_TILE_BASE + 8 + (IDX % 8), (k_score_mma_i8<TT, RR, FF, false>), Cfg::kSmem);       \
     const long long nb = (sp.n_work + 128 * TT - 1) / (128 * TT);                                                     \
     long long cap = ctx->sm_count;                                                                                    \
     if (ctx->mma_grid_cap > 0 && ctx->mma_grid_cap < cap) cap = ctx->mma_grid_cap;                                    \
     const int grid = (int)(nb < cap ? nb : cap);                                                                      \
-    k_score_mma_i8<TT, RR, FF><<<grid, Cfg::kThreads, Cfg::kSmem, ctx->stream>>>(sp);                                 \
+    if (sp.tex) k_score_mma_i8<TT, RR, FF, true><<<grid, Cfg::kThreads, Cfg::kSmem, ctx->stream>>>(sp);               \
+    else k_score_mma_i8<TT, RR, FF, false><<<grid, Cfg::kThreads, Cfg::kSmem, ctx->stream>>>(sp);                     \
   } while (0)
   switch (ctx->mma_i8_cfg) {                     // tiles * 100 + threads per row * 10 + stages in flight (TDR_MMA_I8_CFG)
     case 212: TDR_LAUNCH_I8(0, 2, 1, 2); break;
-    case 214: TDR_LAUNCH_I8(1, 2, 1, 4); break;
-    case 222: TDR_LAUNCH_I8(2, 2, 2, 2); break;
-    case 223: TDR_LAUNCH_I8(3, 2, 2, 3); break;
-    case 233: TDR_LAUNCH_I8(5, 2, 3, 3); break;
-    case 142: TDR_LAUNCH_I8(6, 1, 4, 2); break;
-    case 144: TDR_LAUNCH_I8(7, 1, 4, 4); break;
-    case 224: TDR_LAUNCH_I8(8, 2, 2, 4); break;
-    default: TDR_LAUNCH_I8(4, 2, 3, 2); break;
+    case 222: TDR_LAUNCH_I8(1, 2, 2, 2); break;
+    case 223: TDR_LAUNCH_I8(2, 2, 2, 3); break;
+    case 224: TDR_LAUNCH_I8(3, 2, 2, 4); break;
+    case 233: TDR_LAUNCH_I8(4, 2, 3, 3); break;
+    case 142: TDR_LAUNCH_I8(5, 1, 4, 2); break;
+    case 231: TDR_LAUNCH_I8(6, 2, 3, 1); break;
+    default: TDR_LAUNCH_I8(7, 2, 3, 2); break;
   }
 #undef TDR_LAUNCH_I8
   count_launch(ctx);

@@ -122,6 +122,9 @@ struct tdr_ctx {
   int mma_ctas = 0;          // cap on co-resident CTAs per SM (0 = as many as TMEM allows; tuning: TDR_MMA_CTAS)
   int mma_i8 = 1;            // integer 16-byte-record theta search (score_mma_i8.cu): 0 off, 1 where its error bound holds,
                              // 2 always (tests of the kernel itself; TDR_MMA_I8)
+  int mma_tex = 0;           // integer kernel: every second cell through the texture pipe (TDR_MMA_TEX; measured slower: 5.35 against 4.89 ms)
+  unsigned long long map8_tex = 0;     // cudaTextureObject_t over map8 (pitch-linear, border addressing)
+  int mma_skip_rings = 1;    // integer kernel: do not gather lattice cells that meet no scan return under any candidate shift (TDR_MMA_SKIP_RINGS)
   int mma_i8_cfg = 232;      // integer kernel: tiles * 100 + gather threads per row * 10 + stages in flight per thread (TDR_MMA_I8_CFG)
   int mma_sort = 0;          // integer kernel, hypothesis order inside a super-tile: 0 = pixel row, 4-px segment (its records are
                              // row-major); 1 = Morton over 2 x 2-px cells (TDR_MMA_SORT)
