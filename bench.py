@@ -224,6 +224,81 @@ def setup_ctx(wl, inp, device):
     return ctx
 
 
+def init_dist():
+    """(rank, world, local) of this process; joins the NCCL group once when launched under torchrun"""
+    import torch
+    import torch.distributed as dist
+    rank = int(os.environ.get("RANK", "0"))
+    world = int(os.environ.get("WORLD_SIZE", "1"))
+    local = int(os.environ.get("LOCAL_RANK", "0"))
+    if not torch.cuda.is_available():
+        raise SystemExit("bench.py: no CUDA device — the product path has no CPU fallback "
+                         "(use --impl reference for the CPU arm)")
+    torch.cuda.set_device(local)
+    if world > 1 and not dist.is_initialized():
+        os.environ.setdefault("MASTER_ADDR", "127.0.0.1")
+        dist.init_process_group("nccl", device_id=torch.device("cuda", local))
+    return rank, world, local
+
+
+def states_digest(states):
+    """order-sensitive digest of a resampled particle set (the 28-byte State records, padding zeroed)"""
+    import hashlib
+    a = np.ascontiguousarray(states).copy()
+    a["pad"] = 0
+    return hashlib.blake2b(a.tobytes(), digest_size=8).hexdigest()
+
+
+def verify_update(ctx, wl, inp, arm, u, n_sample=4096):
+    """Outside every timed region: one update of the benchmarked configuration, stage by stage through the C ABI,
+    against the oracle — class images bit-exact, a sample of raw weights within 1e-5 (a heading that differs must be a
+    tie to within 1e-5), normalised weights and ALL resampled indices bit-exact given the device's own raw weights."""
+    orc = arm.orc
+    n, C, res = wl["n"], wl["C"], wl["res"]
+    out = {"sample_particles": int(min(n_sample, n))}
+    ctx.pf_restore()
+    scan = ctx.scan_render_polar(res, float(ANG_RES), N_THETA, N_R, want=True)
+    scan_o = orc.render_polar(inp["pts"], res, ANG_RES, N_THETA, N_R, inp["lut"], C)
+    out["class_images_bit_exact"] = bool(np.array_equal(scan, scan_o))
+    w = ctx.pf_score(res)
+    st_g = ctx.pf_get_states()
+    pick = np.sort(np.random.default_rng(SEED).choice(n, out["sample_particles"], replace=False))
+    st_o = inp["st"][pick].copy()
+    w_o = orc.score_all(st_o, arm.fp, arm.layers, arm.mask, 1.0, arm.tab, N_THETA, N_R, scan_o, res, arm.thetas, arm.shifts,
+                        n_threads=arm.cores)
+    both_nan = np.isnan(w[pick]) & np.isnan(w_o)
+    err = np.abs(w[pick].astype(np.float64) - w_o) / np.maximum(np.abs(w_o.astype(np.float64)), 1e-300)
+    err[both_nan] = 0
+    err[np.isnan(w[pick]) ^ np.isnan(w_o)] = np.inf
+    out["weights_max_rel_err"] = float(err.max())
+    diff = np.flatnonzero(st_g["theta"][pick] != st_o["theta"])
+    out["headings_differing"] = int(diff.size)
+    gap = 0.0
+    if diff.size:
+        src = inp["st"][pick][diff]
+        cen = np.stack([(src["dx_m"] * src["scale"]).astype(np.float32) + src["init_x_px"],
+                        (src["dy_m"] * src["scale"]).astype(np.float32) + src["init_y_px"]], axis=1).astype(np.float32)
+        costs = orc.cost_grid(cen, 2.0, arm.fp, arm.layers, arm.mask, 1.0, arm.tab, N_THETA, N_R, scan_o, res, arm.shifts,
+                              n_threads=arm.cores)
+        th = np.asarray(arm.thetas, dtype=np.float32)
+        kg = [int(np.flatnonzero(th == t)[0]) for t in st_g["theta"][pick][diff]]
+        ko = [int(np.flatnonzero(th == t)[0]) for t in st_o["theta"][diff]]
+        cg = costs[np.arange(diff.size), kg].astype(np.float64)
+        co = costs[np.arange(diff.size), ko].astype(np.float64)
+        gap = float(np.max(np.abs(cg - co) / np.maximum(np.abs(co), 1e-300)))
+    out["heading_ties_max_gap"] = gap
+    ctx.pf_normalize()
+    wn = ctx.pf_get_weights(n)
+    wn_o, _, _ = orc.normalize(w, inp["ld"])
+    out["normalised_bit_exact"] = bool(np.array_equal(wn.view(np.uint32), wn_o.view(np.uint32)))
+    idx = ctx.pf_resample(u, n)
+    out["indices_bit_exact"] = bool(np.array_equal(idx, orc.resample_fast(wn, u, n)))
+    ctx.pf_restore()
+    out["verified"] = bool(out["class_images_bit_exact"] and out["weights_max_rel_err"] <= 1e-5 and gap <= 1e-5 and
+                           out["normalised_bit_exact"] and out["indices_bit_exact"])
+    return out
+
+
 def more_warmup(t0, world, local, need_s=1.5):
     """True while the clock sampler has not yet seen need_s seconds of load (decided collectively: every rank
     must run the same number of steps)."""
@@ -238,21 +313,17 @@ def more_warmup(t0, world, local, need_s=1.5):
     return more > 0
 
 
-def run_gpu(args, wl):
+def measure_particles(args, wl, workload_name, rank, world, local, steps, warmup, with_cpu, with_verify):
+    """one particle-filter workload (cfg3 global / cfg2 tracking) on `world` ranks; returns rank 0's record"""
     import torch
     import torch.distributed as dist
-    rank = int(os.environ.get("RANK", "0"))
-    world = int(os.environ.get("WORLD_SIZE", "1"))
-    local = int(os.environ.get("LOCAL_RANK", "0"))
-    if not torch.cuda.is_available():
-        raise SystemExit("bench.py: no CUDA device — the product path has no CPU fallback "
-                         "(use --impl reference for the CPU arm)")
-    torch.cuda.set_device(local)
-    if world > 1:
-        os.environ.setdefault("MASTER_ADDR", "127.0.0.1")
-        dist.init_process_group("nccl", device_id=torch.device("cuda", local))
     from top_down_renderer_b200 import sharded
 
+    class _A:
+        pass
+    a_ = _A()
+    a_.steps, a_.warmup, a_.workload, a_.no_cpu = steps, warmup, workload_name, not with_cpu
+    args = a_
     inp = make_inputs(wl, rank)
     ctx = setup_ctx(wl, inp, local)
     ctx.profile_enable(True)
@@ -263,6 +334,15 @@ def run_gpu(args, wl):
     u = float(np.random.default_rng(SEED).random(dtype=np.float32))
     pts_pinned = torch.from_numpy(inp["pts"]).pin_memory()
     flush = torch.empty(256 << 20, dtype=torch.uint8, device=f"cuda:{local}")
+    arm, verification = None, None
+    if rank == 0 and (with_verify or (with_cpu and world == 1)):
+        arm = CpuArm(wl, inp)
+    if with_verify:
+        ctx.scan_set_points_ptr(pts_pinned.data_ptr(), 32, 16, pts_pinned.shape[0])
+        if rank == 0:
+            verification = verify_update(ctx, wl, inp, arm, u)
+        if world > 1:
+            dist.barrier()
 
     def one_step():
         if flt is not None:
@@ -346,16 +426,43 @@ def run_gpu(args, wl):
         e2e_total = float(t.item())
     e2e_value = scores_per_step * args.steps / e2e_total
 
+    # ---- N > 1: the sharded update reproduces the single-GPU states bit for bit (the design's claim) — one more
+    # update from the checkpoint on every rank, digests of the resampled shards against rank 0 running ALL particles
+    shard_check = None
+    if world > 1 and with_verify:
+        with torch.cuda.stream(stream):
+            ctx.pf_restore()
+            one_step()
+        torch.cuda.synchronize()
+        mine = states_digest(ctx.pf_get_states())
+        digests = [None] * world
+        dist.all_gather_object(digests, mine)
+        if rank == 0:
+            from top_down_renderer_b200 import synth
+            parts = [synth.particles_global(n, inp["cm"], seed=SEED + 101 * r) if wl["shifts"] > 1 else
+                     synth.particles_tracking(n, inp["pose"], inp["heading"], seed=SEED + 101 * r) for r in range(world)]
+            big = dict(inp, st=np.concatenate([p_[0] for p_ in parts]), ld=np.concatenate([p_[1] for p_ in parts]))
+            ref = setup_ctx(dict(wl, n=n * world), big, local)
+            ref.scan_set_points(inp["pts"])
+            ref.step(res, float(ANG_RES), N_THETA, N_R, u, M * world)
+            ref.sync()
+            st_ref = ref.pf_get_states()
+            ref.close()
+            want = [states_digest(st_ref[r * M:(r + 1) * M]) for r in range(world)]
+            shard_check = {"ranks": world, "states_equal_single_gpu": bool(want == digests), "digests": digests}
+        dist.barrier()
+
     out = None
     if rank == 0:
         peak, peak_src = peaks()
         score_ms = float(stage[:, 1].mean())
         achieved = n * b_score(C) / (score_ms * 1e-3) / 1e9
-        traffic = None
+        traffic, traffic_src = None, None
         try:
             with open(os.path.join(ROOT, "profiles", "score_kernel_traffic.json")) as f:
                 t_ = json.load(f).get(args.workload, {})
                 traffic = int(t_["captured_dram_bytes"] * n / t_["captured_particles"])      # per launch of n particles
+                traffic_src = t_.get("source", "profiles/ ncu --set full capture of this kernel, scaled by particles; NOT measured in this run")
         except Exception:
             pass
         out = {"metric": "particle_scores_per_sec", "value": value, "unit": "scores/s", "n_gpus": world,
@@ -375,13 +482,17 @@ def run_gpu(args, wl):
                        "p50_ms": 1e3 * float(np.median(e2e_t)), "timer": "host wall clock around set_points+step+pose"},
                "gpu_launches": int(launches),
                "wall_s_timed_region": t_wall,
-               "roofline": {"bound": "hbm", "kernel": "k_score_mma_list (tcgen05 gather-GEMM, operands in tensor memory)" if wl["shifts"] > 1 else "k_score_track",
+               "roofline": {"bound": "hbm", "kernel": "k_score_mma_i8 (tcgen05 kind::i8 gather-GEMM on 16-byte records, operands in tensor memory)" if wl["shifts"] > 1 else "k_score_track",
                             "achieved": achieved, "peak": peak, "unit": "GB/s", "frac": achieved / peak,
-                            "traffic": traffic, "peak_source": peak_src,
+                            "traffic": traffic, "traffic_source": traffic_src, "peak_source": peak_src,
                             "algorithmic_bytes_per_launch": n * b_score(C), "kernel_ms": score_ms}}
+        if verification is not None:
+            out["verified"] = verification["verified"]
+            out["verification"] = verification
+        if shard_check is not None:
+            out["multi_gpu_check"] = shard_check
     # ---- CPU baseline (rank 0, N = 1 only): bounded sample of the same workload on the host cores
     if rank == 0 and world == 1 and not args.no_cpu:
-        arm = CpuArm(wl, inp)
         n_s = min(n, 32768 if wl["shifts"] > 1 else n)
         arm.step(0, min(n_s, 2048))
         reps = 1 if wl["shifts"] > 1 else 20
@@ -393,12 +504,10 @@ def run_gpu(args, wl):
                                          f"{arm.cores} std::threads"}
     elif rank == 0:
         out["cpu_baseline"] = None
-    if rank == 0:
-        emit(out)
     ctx.close()
     if world > 1:
         dist.barrier()
-        dist.destroy_process_group()
+    return out
 
 
 def grid_traffic(n_local):
@@ -411,22 +520,19 @@ def grid_traffic(n_local):
         return None
 
 
-def run_grid(args, wl):
+def measure_grid(wl, rank, world, local, steps, warmup, grid_collective, with_verify):
     """cfg4: exhaustive (x, y, theta) grid, STRONG scaling: the lattice of centres is split over the ranks; one
-    all-gather of the costs ("weight all-gather") per step, then the arg-min on every rank."""
+    all-gather of the costs ("weight all-gather") per step, then the arg-min on every rank.  world = 1 with rank 0 of a
+    larger job = the single-GPU reference of the same run.  Returns rank 0's record."""
     import torch
     import torch.distributed as dist
     from top_down_renderer_b200 import hostmath, sharded, synth
     from top_down_renderer_b200.core import Context
-    rank = int(os.environ.get("RANK", "0"))
-    world = int(os.environ.get("WORLD_SIZE", "1"))
-    local = int(os.environ.get("LOCAL_RANK", "0"))
-    if not torch.cuda.is_available():
-        raise SystemExit("bench.py: no CUDA device — the product path has no CPU fallback")
-    torch.cuda.set_device(local)
-    if world > 1:
-        os.environ.setdefault("MASTER_ADDR", "127.0.0.1")
-        dist.init_process_group("nccl", device_id=torch.device("cuda", local))
+
+    class _A:
+        pass
+    args = _A()
+    args.steps, args.warmup, args.grid_collective = steps, warmup, grid_collective
     side, C, res = wl["side"], wl["C"], wl["res"]
     inp = make_inputs(dict(wl, n=16, shifts=1), rank)
     centers_all = synth.grid_centers(side, side, 4)                       # 1000 x 1000 centres
@@ -533,6 +639,22 @@ def run_grid(args, wl):
         t = torch.tensor([total_ms, e2e_total], device=dev, dtype=torch.float64)
         dist.all_reduce(t, op=dist.ReduceOp.MAX)
         total_ms, e2e_total = float(t[0].item()), float(t[1].item())
+    verification = None
+    if with_verify and rank == 0:
+        # a sample of this rank's cost rows against the oracle (outside the timed region)
+        arm = CpuArm(wl, inp)
+        rows = np.sort(np.random.default_rng(SEED).choice(n_local, 1024, replace=False))
+        got = np.stack([ctx.copy_from_device(full_ptr + 4 * (lo + int(r)) * S, S) for r in rows])
+        scan_o = arm.orc.render_polar(inp["pts"], res, ANG_RES, N_THETA, N_R, inp["lut"], C)
+        want = arm.orc.cost_grid(centers[rows], 2.0, arm.fp, arm.layers, arm.mask, 1.0, arm.tab, N_THETA, N_R, scan_o, res, shifts,
+                                 n_threads=arm.cores)
+        both = np.isnan(got) & np.isnan(want)
+        err = np.abs(got.astype(np.float64) - want) / np.maximum(np.abs(want.astype(np.float64)), 1e-300)
+        err[both] = 0
+        err[np.isnan(got) ^ np.isnan(want)] = np.inf
+        verification = {"sample_centres": int(len(rows)), "costs_max_rel_err": float(err.max()),
+                        "verified": bool(err.max() <= 1e-5)}
+    out = None
     if rank == 0:
         peak, peak_src = peaks()
         scores = n_total * S
@@ -556,17 +678,20 @@ def run_grid(args, wl):
                "gpu_launches": int(launches),
                "roofline": {"bound": "hbm", "kernel": "k_score_mma (tcgen05 gather-GEMM, sliding scan ring, operands in tensor memory)",
                             "achieved": achieved, "peak": peak, "unit": "GB/s", "frac": achieved / peak,
-                            "traffic": grid_traffic(n_local), "peak_source": peak_src,
+                            "traffic": grid_traffic(n_local), "traffic_source": "profiles/ ncu --set full capture, scaled; NOT measured in this run",
+                            "peak_source": peak_src,
                             "algorithmic_bytes_per_launch": n_local * b_score(C), "kernel_ms": k_ms},
                "cpu_baseline": None}
-        emit(out)
+        if verification is not None:
+            out["verified"] = verification["verified"]
+            out["verification"] = verification
     if fused:
         dist.barrier()
         gather.close()
     ctx.close()
     if world > 1:
         dist.barrier()
-        dist.destroy_process_group()
+    return out
 
 
 _REAL_STDOUT = None
@@ -719,6 +844,8 @@ def main():
     ap.add_argument("--no-cpu", action="store_true", help="skip the cpu_baseline leg")
     ap.add_argument("--grid-collective", default="fused", choices=["fused", "nccl"],
                     help="grid workload, N > 1: all-gather fused into the score kernel over peer memory, or NCCL")
+    ap.add_argument("--no-sub", action="store_true", help="default workload only: skip the cfg2 / cfg4 sub-records")
+    ap.add_argument("--no-verify", action="store_true", help="skip the oracle check of the benchmarked configuration")
     args = ap.parse_args()
     args.warmup = max(args.warmup, 0)
     wl = dict(WORKLOADS[args.workload])
@@ -726,12 +853,50 @@ def main():
         wl["n"] = args.particles
     if args.impl == "reference":
         run_reference(args, wl)
-    elif wl.get("refine"):
+        return
+    if wl.get("refine"):
         run_refine(args, wl)
-    elif wl.get("grid"):
-        run_grid(args, wl)
+        return
+    import torch.distributed as dist
+    rank, world, local = init_dist()
+    verify = not args.no_verify
+    if wl.get("grid"):
+        out = measure_grid(wl, rank, world, local, args.steps, args.warmup, args.grid_collective, verify)
     else:
-        run_gpu(args, wl)
+        out = measure_particles(args, wl, args.workload, rank, world, local, args.steps, args.warmup, not args.no_cpu, verify)
+        if args.workload == "global" and not args.no_sub and not args.particles:
+            # the other two configurations BASELINE.json's metric names, as sub-records of the same line:
+            # cfg2 = p50 update latency of 10k tracked particles on ONE GPU (rank 0; the others wait),
+            # cfg4 = the 1e8-hypothesis exhaustive grid, strong scaling over all ranks (+ rank 0 alone as the 1-GPU reference)
+            trk = None
+            if rank == 0:
+                t = measure_particles(args, dict(WORKLOADS["tracking"]), "tracking", 0, 1, local, 200, 10, False, verify)
+                trk = {"workload": t["config"]["workload"], "p50_update_ms": t["p50_update_ms"], "ms_per_step": t["ms_per_step"],
+                       "stage_ms": t["stage_ms"], "e2e_p50_ms": t["e2e"]["p50_ms"], "value": t["value"], "unit": t["unit"],
+                       "steps": 200, "verified": t.get("verified"), "verification": t.get("verification"),
+                       "roofline_frac": t["roofline"]["frac"]}
+            if world > 1:
+                dist.barrier()
+            g = measure_grid(dict(WORKLOADS["grid"]), rank, world, local, 10, 3, args.grid_collective, verify)
+            g1 = None
+            if world > 1:
+                if rank == 0:
+                    g1 = measure_grid(dict(WORKLOADS["grid"]), 0, 1, local, 10, 3, args.grid_collective, False)
+                dist.barrier()
+            if rank == 0:
+                out["tracking"] = trk
+                out["grid"] = {"workload": g["config"]["workload"], "value": g["value"], "unit": g["unit"], "ms_per_step": g["ms_per_step"],
+                               "scaling": "strong", "n_gpus": world, "steps": 10, "score_kernel_ms": g["stage_ms"]["score"],
+                               "e2e_ms_per_step": g["e2e"]["ms_per_step"], "best": g["best"], "verified": g.get("verified"),
+                               "verification": g.get("verification"), "roofline_frac": g["roofline"]["frac"],
+                               "vs_1gpu": (g["value"] / g1["value"]) if g1 else 1.0,
+                               "ms_per_step_1gpu": g1["ms_per_step"] if g1 else g["ms_per_step"],
+                               "collective": g["config"]["parallelism"]}
+    if rank == 0 and out is not None:
+        emit(out)
+    if world > 1:
+        dist.barrier()
+        dist.destroy_process_group()
 
 
 if __name__ == "__main__":
