@@ -59,14 +59,21 @@ __device__ __forceinline__ void tmem_ld8(uint32_t taddr, uint32_t* v) {
 // ------------------------------------------------------------------------------------------------
 // the 16-byte map copy
 // ------------------------------------------------------------------------------------------------
-// row-major, `pitch` records per map row; one all-zero record past the map is what cells off the map read
+// Two layouts: row-major (`pitch` records per map row: a 128-byte line = 8 px of one row) or 4 x 2-px blocks (a line =
+// 4 px of two adjacent rows, `pitch` blocks per block row) — with hypotheses in Morton order the compact 2-D clusters of
+// a warp touch fewer lines of the blocked layout (12.1 against 14.6 simulated on cfg3).  One all-zero record past the
+// map is what cells off the map read.
 struct Geom8 {
   uint32_t pitch, zero_rec;
   uint32_t lim_y, lim_x;           // 4096 rows - 1, 4096 cols - 1 (lattice_fixed)
 };
+template <bool BLK> __host__ __device__ __forceinline__ uint32_t map8_index(uint32_t r, uint32_t c, uint32_t pitch) {
+  if (!BLK) return r * pitch + c;
+  return (((r >> 1) * pitch + (c >> 2)) << 3) | ((r & 1u) << 2) | (c & 3u);
+}
 
-static __global__ void k_build_map8(const MapPixel* __restrict__ map, size_t n, int C, const float* __restrict__ cw,
-                                    float inv_q, uint4* __restrict__ out) {
+static __global__ void k_build_map8(const MapPixel* __restrict__ map, size_t n, int cols, int C, const float* __restrict__ cw,
+                                    float inv_q, int blocked, uint32_t pitch, uint4* __restrict__ out) {
   const size_t i = (size_t)blockIdx.x * blockDim.x + threadIdx.x;
   if (i >= n) return;
   const float4* src = reinterpret_cast<const float4*>(map + i);
@@ -85,7 +92,8 @@ static __global__ void k_build_map8(const MapPixel* __restrict__ map, size_t n, 
     w[k >> 1] |= ((q >> 8) | ((q & 0xffu) << 8)) << ((k & 1) * 16);
   }
   if (v[7] != 0.f) w[3] |= 1u << 16;            // byte 14: known
-  out[i] = make_uint4(w[0], w[1], w[2], w[3]);
+  const uint32_t r = (uint32_t)(i / cols), c = (uint32_t)(i % cols);
+  out[blocked ? map8_index<true>(r, c, pitch) : i] = make_uint4(w[0], w[1], w[2], w[3]);
 }
 
 // one scale for every hypothesis of the launch?  (min, max) of the scale bits over the particles still to be searched
@@ -234,7 +242,9 @@ template <int T, int R, int F> struct I8Cfg {
   static const int kThreads = 128 * T * R + 64;
   static const int kBBytes = I8_N * 32;                    // scan operand of one stage (2 cells)
   static const int kACols = T * 8;                         // TMEM columns of one stage of A
-  static const int kStagesMax = (512 - T * I8_N) / kACols;
+  static const int kCtasPerSm = T == 1 ? 2 : 1;            // one tile per CTA leaves room for two CTAs (two pipelines) per SM
+  static const int kTmemCols = 512 / kCtasPerSm;
+  static const int kStagesMax = (kTmemCols - T * I8_N) / kACols;
   static const int kStages = kStagesMax > 16 ? 16 : kStagesMax;
   static const int kSmem = kStages * kBBytes + 512;        // + barriers (2 * kStages + 1) and the TMEM base word
   static_assert(kStages >= R * F, "every stage a thread has in flight needs its own slot");
@@ -243,8 +253,8 @@ template <int T, int R, int F> struct I8Cfg {
 // TEX: the second cell of every stage comes through the texture pipe instead of the LSU — the kernel is bound by L1
 // data-pipe wavefronts of its 128-bit loads (84 % busy, profiles/r02_i8_ncu.md) and the two front ends together deliver
 // more records per clock than either alone (2.27 against 1.9, tools/tex_bench.cu)
-template <int T, int R, int F, bool TEX>
-__global__ void __launch_bounds__(128 * T * R + 64, 1) k_score_mma_i8(I8Params sp) {
+template <int T, int R, int F, bool TEX, bool BLK>
+__global__ void __launch_bounds__(128 * T * R + 64, I8Cfg<T, R, F>::kCtasPerSm) k_score_mma_i8(I8Params sp) {
   using Cfg = I8Cfg<T, R, F>;
   constexpr int N = I8_N;
   constexpr int GW = 4 * T * R;        // gather warps
@@ -260,7 +270,7 @@ __global__ void __launch_bounds__(128 * T * R + 64, 1) k_score_mma_i8(I8Params s
   const int tid = threadIdx.x, warp = tid >> 5, lane = tid & 31;
   const uint32_t bar_full = smem_u32(bars), bar_empty = smem_u32(bars + NS), bar_accum = smem_u32(bars + 2 * NS);
 
-  if (warp == GW + 1) tmem_alloc(smem_u32(s_tmem), 512);
+  if (warp == GW + 1) tmem_alloc(smem_u32(s_tmem), Cfg::kTmemCols);
   if (tid == 0) {
     for (int s = 0; s < NS; s++) { mbar_init(bar_full + 8 * s, 4 * T + 1); mbar_init(bar_empty + 8 * s, 1); }
     mbar_init(bar_accum, 1);
@@ -314,7 +324,7 @@ __global__ void __launch_bounds__(128 * T * R + 64, 1) k_score_mma_i8(I8Params s
           const bool ok = ty < lim_y && tx < lim_x;
           if (TEX && g == 1) rec[g] = tex_fetch(sp.tex, ok ? (int)((tx + 1u) >> 12) : -1, (int)((ty + 1u) >> 12));
           else {
-            uint32_t r = ((ty + 1u) >> 12) * sp.geom.pitch + ((tx + 1u) >> 12);
+            uint32_t r = map8_index<BLK>((ty + 1u) >> 12, (tx + 1u) >> 12, sp.geom.pitch);
             if (!ok) r = sp.geom.zero_rec;
             rec[g] = __ldg(map8 + r);
           }
@@ -371,7 +381,7 @@ __global__ void __launch_bounds__(128 * T * R + 64, 1) k_score_mma_i8(I8Params s
           const float2 tb = sp.tab_g[2 * K_ITERS + m];
           const uint32_t ty = (uint32_t)__float2int_rz(TDR_FADD(tb.x, soy)) + 2047u;
           const uint32_t tx = (uint32_t)__float2int_rz(TDR_FADD(tb.y, sox)) + 2047u;
-          if (ty < sp.geom.lim_y && tx < lim_x) cnt += (int)((__ldg(map8 + (((ty + 1u) >> 12) * sp.geom.pitch + ((tx + 1u) >> 12))).w >> 16) & 1u);
+          if (ty < sp.geom.lim_y && tx < lim_x) cnt += (int)((__ldg(map8 + map8_index<BLK>((ty + 1u) >> 12, (tx + 1u) >> 12, sp.geom.pitch)).w >> 16) & 1u);
         }
         for (int o = 16; o > 0; o >>= 1) cnt += __shfl_xor_sync(0xffffffffu, cnt, o);
         if (lane == src) known += cnt;
@@ -448,7 +458,7 @@ __global__ void __launch_bounds__(128 * T * R + 64, 1) k_score_mma_i8(I8Params s
   }
   tc_fence_before();
   __syncthreads();
-  if (warp == GW + 1) tmem_dealloc(tmem_base, 512);
+  if (warp == GW + 1) tmem_dealloc(tmem_base, Cfg::kTmemCols);
 }
 
 // ------------------------------------------------------------------------------------------------
@@ -471,23 +481,26 @@ static bool i8_usable(tdr_ctx* ctx, int n_shifts, float* q_out) {
   return 0.005 * (double)q / (double)ctx->fp.regularization <= 9e-6;
 }
 
-static int build_map8(tdr_ctx* ctx, float q, const uint4** out, Geom8* geom) {
-  const size_t n_rec = (size_t)ctx->rows * ctx->cols;
+static int build_map8(tdr_ctx* ctx, float q, bool blocked, const uint4** out, Geom8* geom) {
+  const uint32_t bx = ((uint32_t)ctx->cols + 3u) / 4u, by = ((uint32_t)ctx->rows + 1u) / 2u;
+  const size_t n_px = (size_t)ctx->rows * ctx->cols;
+  const size_t n_rec = blocked ? (size_t)bx * by * 8 : n_px;
   TDR_REQUIRE(n_rec < (1ull << 31) && ctx->rows < (1 << 19) && ctx->cols < (1 << 19), TDR_EUNSUPPORTED,
               "map too large for the 16-byte copy (%zu records)", n_rec);
-  geom->pitch = (uint32_t)ctx->cols; geom->zero_rec = (uint32_t)n_rec;
+  geom->pitch = blocked ? bx : (uint32_t)ctx->cols; geom->zero_rec = (uint32_t)n_rec;
   geom->lim_y = 4096u * (uint32_t)ctx->rows - 1u; geom->lim_x = 4096u * (uint32_t)ctx->cols - 1u;
-  if (!ctx->map8_valid || ctx->map8_q != q) {
+  if (!ctx->map8_valid || ctx->map8_q != q || ctx->map8_blocked != (blocked ? 1 : 0)) {
     if (int e = ctx->map8.reserve((n_rec + 1) * 16)) return e;
-    TDR_CUDA(cudaMemsetAsync(ctx->map8.as<unsigned char>() + n_rec * 16, 0, 16, ctx->stream));      // the all-zero record
-    k_build_map8<<<(unsigned)((n_rec + 255) / 256), 256, 0, ctx->stream>>>(ctx->map_px.as<MapPixel>(), n_rec, ctx->C, ctx->d_cw.as<float>(),
-                                                                            1.f / q, ctx->map8.as<uint4>());
+    if (blocked) TDR_CUDA(cudaMemsetAsync(ctx->map8.p, 0, (n_rec + 1) * 16, ctx->stream));           // padding pixels of the edge blocks
+    else TDR_CUDA(cudaMemsetAsync(ctx->map8.as<unsigned char>() + n_rec * 16, 0, 16, ctx->stream));   // the all-zero record
+    k_build_map8<<<(unsigned)((n_px + 255) / 256), 256, 0, ctx->stream>>>(ctx->map_px.as<MapPixel>(), n_px, ctx->cols, ctx->C,
+                                                                           ctx->d_cw.as<float>(), 1.f / q, blocked ? 1 : 0, geom->pitch, ctx->map8.as<uint4>());
     count_launch(ctx);
     TDR_CUDA(cudaGetLastError());
-    ctx->map8_valid = true; ctx->map8_q = q;
+    ctx->map8_valid = true; ctx->map8_q = q; ctx->map8_blocked = blocked ? 1 : 0;
     // the same buffer as a pitch-linear 2-D texture of uint4 texels; outside it reads the border colour = the zero record
     if (ctx->map8_tex) { cudaDestroyTextureObject((cudaTextureObject_t)ctx->map8_tex); ctx->map8_tex = 0; }
-    if (ctx->mma_tex && ((size_t)ctx->cols * 16) % 32 == 0) {
+    if (ctx->mma_tex && !blocked && ((size_t)ctx->cols * 16) % 32 == 0) {
       cudaResourceDesc rd; memset(&rd, 0, sizeof(rd));
       rd.resType = cudaResourceTypePitch2D;
       rd.res.pitch2D.devPtr = ctx->map8.p; rd.res.pitch2D.desc = cudaCreateChannelDesc<uint4>();
@@ -551,7 +564,8 @@ int score_mma_i8(tdr_ctx* ctx, float res, const int32_t* dev_shifts, int n_shift
     g_tab_on_device[ctx->device % MMA_MAX_DEVICES] = 0;
   }
   I8Params sp; memset(&sp, 0, sizeof(sp));
-  if (int e = build_map8(ctx, q, &sp.map8, &sp.geom)) return e;
+  const bool blocked = ctx->mma_sort == 1;              // Morton order goes with the 4 x 2-px block layout
+  if (int e = build_map8(ctx, q, blocked, &sp.map8, &sp.geom)) return e;
   sp.resolution = ctx->resolution; sp.P = P; sp.P_cap = P_cap; sp.plan = d_plan;
   sp.bop = ctx->scan_op.as<uint4>();
   sp.perm = ctx->perm.as<int>();
@@ -570,29 +584,39 @@ int score_mma_i8(tdr_ctx* ctx, float res, const int32_t* dev_shifts, int n_shift
   sp.scale_lo = pow(10.0, (double)ctx->fp.scale_log_min); sp.scale_hi = pow(10.0, (double)ctx->fp.scale_log_max);
   sp.regularization = ctx->fp.regularization;
   sp.thetas = ctx->d_search_thetas.as<float>();
+#define I8_OPTIN(BIT, KERNEL)                                                                                         \
+  do {                                                                                                                \
+    if (!(ctx->smem_optin_i8 & (1ull << (BIT)))) {                                                                    \
+      TDR_CUDA(cudaFuncSetAttribute(KERNEL, cudaFuncAttributeMaxDynamicSharedMemorySize, Cfg::kSmem));                \
+      ctx->smem_optin_i8 |= 1ull << (BIT);                                                                            \
+    }                                                                                                                 \
+  } while (0)
 #define TDR_LAUNCH_I8(IDX, TT, RR, FF)                                                                                \
   do {                                                                                                                \
     using Cfg = I8Cfg<TT, RR, FF>;                                                                                    \
-    if (sp.tex) TDR_SMEM_OPTIN(ctx, OPTIN_TILE_BASE + IDX, (k_score_mma_i8<TT, RR, FF, true>), Cfg::kSmem);           \
-    else TDR_SMEM_OPTIN(ctx, OPTIN_TILE_BASE + 8 + (IDX % 8), (k_score_mma_i8<TT, RR, FF, false>), Cfg::kSmem);       \
+    if (sp.tex) I8_OPTIN(IDX, (k_score_mma_i8<TT, RR, FF, true, false>));                                             \
+    else if (blocked) I8_OPTIN(16 + IDX, (k_score_mma_i8<TT, RR, FF, false, true>));                                  \
+    else I8_OPTIN(32 + IDX, (k_score_mma_i8<TT, RR, FF, false, false>));                                              \
     const long long nb = (sp.n_work + 128 * TT - 1) / (128 * TT);                                                     \
-    long long cap = ctx->sm_count;                                                                                    \
+    long long cap = (long long)ctx->sm_count * Cfg::kCtasPerSm;                                                       \
     if (ctx->mma_grid_cap > 0 && ctx->mma_grid_cap < cap) cap = ctx->mma_grid_cap;                                    \
     const int grid = (int)(nb < cap ? nb : cap);                                                                      \
-    if (sp.tex) k_score_mma_i8<TT, RR, FF, true><<<grid, Cfg::kThreads, Cfg::kSmem, ctx->stream>>>(sp);               \
-    else k_score_mma_i8<TT, RR, FF, false><<<grid, Cfg::kThreads, Cfg::kSmem, ctx->stream>>>(sp);                     \
+    if (sp.tex) k_score_mma_i8<TT, RR, FF, true, false><<<grid, Cfg::kThreads, Cfg::kSmem, ctx->stream>>>(sp);        \
+    else if (blocked) k_score_mma_i8<TT, RR, FF, false, true><<<grid, Cfg::kThreads, Cfg::kSmem, ctx->stream>>>(sp);  \
+    else k_score_mma_i8<TT, RR, FF, false, false><<<grid, Cfg::kThreads, Cfg::kSmem, ctx->stream>>>(sp);              \
   } while (0)
   switch (ctx->mma_i8_cfg) {                     // tiles * 100 + threads per row * 10 + stages in flight (TDR_MMA_I8_CFG)
-    case 212: TDR_LAUNCH_I8(0, 2, 1, 2); break;
+    case 131: TDR_LAUNCH_I8(0, 1, 3, 1); break;
     case 222: TDR_LAUNCH_I8(1, 2, 2, 2); break;
     case 223: TDR_LAUNCH_I8(2, 2, 2, 3); break;
     case 224: TDR_LAUNCH_I8(3, 2, 2, 4); break;
     case 233: TDR_LAUNCH_I8(4, 2, 3, 3); break;
-    case 142: TDR_LAUNCH_I8(5, 1, 4, 2); break;
+    case 141: TDR_LAUNCH_I8(5, 1, 4, 1); break;
     case 231: TDR_LAUNCH_I8(6, 2, 3, 1); break;
     default: TDR_LAUNCH_I8(7, 2, 3, 2); break;
   }
 #undef TDR_LAUNCH_I8
+#undef I8_OPTIN
   count_launch(ctx);
   TDR_CUDA(cudaGetLastError());
   *used = true;

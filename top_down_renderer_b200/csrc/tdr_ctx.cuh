@@ -125,12 +125,13 @@ struct tdr_ctx {
   int mma_tex = 0;           // integer kernel: every second cell through the texture pipe (TDR_MMA_TEX; measured slower: 5.35 against 4.89 ms)
   unsigned long long map8_tex = 0;     // cudaTextureObject_t over map8 (pitch-linear, border addressing)
   int mma_skip_rings = 1;    // integer kernel: do not gather lattice cells that meet no scan return under any candidate shift (TDR_MMA_SKIP_RINGS)
-  int mma_i8_cfg = 232;      // integer kernel: tiles * 100 + gather threads per row * 10 + stages in flight per thread (TDR_MMA_I8_CFG)
+  int mma_i8_cfg = 141;      // integer kernel: tiles * 100 + gather threads per row * 10 + stages in flight per thread (TDR_MMA_I8_CFG)
   int mma_sort = 0;          // integer kernel, hypothesis order inside a super-tile: 0 = pixel row, 4-px segment (its records are
                              // row-major); 1 = Morton over 2 x 2-px cells (TDR_MMA_SORT)
   tdr::DevBuf map8;          // rows*cols x 16 B: u16 fixed-point class distances (hi / lo bytes) + known, 4 x 2-px blocks
   bool map8_valid = false;
   float map8_q = 0.f;        // its quantum
+  int map8_blocked = -1;     // its layout: 0 row-major, 1 blocks of 4 x 2 px
   // the previous scan's largest class-summed count, read back lazily: predicts which operand format the next scan fits
   // (u8 <= 255, fp16 <= 2048); the kernels re-check on the device
   int scan_max_seen = 0;
@@ -186,6 +187,7 @@ struct tdr_ctx {
   // kernels whose dynamic shared-memory opt-in has been set ON THIS CONTEXT'S DEVICE (function attributes are per
   // device; a process may hold contexts on several)
   uint64_t smem_optin = 0;
+  uint64_t smem_optin_i8 = 0;          // the same for the variants of the integer score kernel
   uint64_t tab_id = 0;                 // process-unique id of the resident polar table (constant-memory mirrors key on it)
   tdr::DevBuf d_cw;          // class weights (16 floats)
   tdr::Particles all;        // multi-GPU: the all-gathered particle set (N = ranks * n_local) in global order
