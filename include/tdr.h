@@ -145,6 +145,16 @@ int tdr_scan_set_lut(tdr_ctx* ctx, const int32_t* lut, int n_lut, int num_classe
 int tdr_scan_render_polar(tdr_ctx* ctx, float res, float ang_res, int n_theta, int n_r, float* imgs);
 /* a2: ScanRenderer::renderSemanticTopDown (scan_renderer.cpp:55-78); C col-major rows x cols */
 int tdr_scan_render_cart(tdr_ctx* ctx, float res, int rows, int cols, float* imgs);
+/* SURVEY 8f rank 2 — the geometric renderers over the resident points taken as an ORGANISED cloud (width columns x
+ * height rows, point (col, row) at row * width + col, visited column by column like cloud->at(idx, idy)):
+ * ScanRendererPolar::renderGeometricTopDown (scan_renderer_polar.cpp:6-81): angular bins, each sorted by descending
+ * planar range, walked with the slope rule (> 1: obstacle cell in imgs[1]; < 0.3 and not behind an obstacle: imgs[0]
+ * filled from the previous range bin to this one); and ScanRenderer::renderGeometricTopDown (scan_renderer.cpp:7-53):
+ * the same rule along every vertical scan line, flat steps drawn as line segments.  imgs: 2 column-major images
+ * (n_theta x n_r / rows x cols).  Points of exactly equal range keep their visiting order (std::sort leaves it open).
+ * An angular bin may hold at most 8192 points (TDR_EUNSUPPORTED beyond). */
+int tdr_scan_render_geometric_polar(tdr_ctx* ctx, int width, int height, float res, float ang_res, int n_theta, int n_r, float* imgs);
+int tdr_scan_render_geometric_cart(tdr_ctx* ctx, int width, int height, float res, int rows, int cols, float* imgs);
 /* BASELINE cfg5 (refine_map-style batch rasterisation): MapRefiner::loadSemOccGrid's binning rule
  * (src/refine_map.cpp:76-94) over n points (x, y) with class indices: ind = floor(pt/res) + (int)(centre/res), one
  * uint8 counter per (class, y, x), wrapping mod 256 like the reference's "+= 1".  maps_out: C x height x width. */

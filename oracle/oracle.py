@@ -104,6 +104,27 @@ def render_cart(pts, res, rows, cols, lut, C_, intensity_off=16):
     return out
 
 
+def render_geometric_polar(pts, width, height, res, ang_res, n_theta, n_r):
+    """ScanRendererPolar::renderGeometricTopDown (scan_renderer_polar.cpp:6-81) over an organised cloud
+    (pts[row * width + col]); returns (2, n_r, n_theta): [0] flat ground fill, [1] obstacle steps."""
+    pts = np.ascontiguousarray(pts, dtype=np.float32)
+    assert pts.shape[0] == width * height
+    out = np.empty((2, n_r, n_theta), dtype=np.float32)
+    lib().orc_render_geometric_polar(_p(pts, c_u8_p), C.c_int(pts.strides[0]), width, height, C.c_float(res), C.c_float(ang_res),
+                                     n_theta, n_r, _p(out, c_float_p))
+    return out
+
+
+def render_geometric_cart(pts, width, height, res, rows, cols):
+    """ScanRenderer::renderGeometricTopDown (scan_renderer.cpp:7-53); returns (2, cols, rows)"""
+    pts = np.ascontiguousarray(pts, dtype=np.float32)
+    assert pts.shape[0] == width * height
+    out = np.empty((2, cols, rows), dtype=np.float32)
+    lib().orc_render_geometric_cart(_p(pts, c_u8_p), C.c_int(pts.strides[0]), width, height, C.c_float(res), rows, cols,
+                                    _p(out, c_float_p))
+    return out
+
+
 # ---- a3 / a4 / a5 ----------------------------------------------------------------------------
 def map_dims(h_img, w_img, res):
     r, c = C.c_int(), C.c_int()

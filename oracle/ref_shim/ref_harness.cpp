@@ -41,6 +41,27 @@ REF_API void ref_render_cart(const float* pts, long n, float res, int rows, int 
   copy_out(v, imgs);
 }
 
+// ---- f2: the reference's geometric renderers on an organised cloud (width columns x height rows)
+static pcl::PointCloud<pcl::PointXYZI>::ConstPtr make_cloud_wh(const float* aos, int width, int height) {
+  auto c = std::make_shared<pcl::PointCloud<pcl::PointXYZI>>();
+  c->points.resize((size_t)width * height);
+  std::memcpy(c->points.data(), aos, (size_t)width * height * 32);
+  c->width = (uint32_t)width; c->height = (uint32_t)height;
+  return c;
+}
+REF_API void ref_render_geometric_polar(const float* pts, int width, int height, float res, float ang_res, int n_theta, int n_r, float* imgs) {
+  ScanRendererPolar r(make_lut(nullptr, 0));
+  auto v = make_imgs(2, n_theta, n_r);
+  r.renderGeometricTopDown(make_cloud_wh(pts, width, height), res, ang_res, v);
+  copy_out(v, imgs);
+}
+REF_API void ref_render_geometric_cart(const float* pts, int width, int height, float res, int rows, int cols, float* imgs) {
+  ScanRenderer r(make_lut(nullptr, 0));
+  auto v = make_imgs(2, rows, cols);
+  r.renderGeometricTopDown(make_cloud_wh(pts, width, height), res, v);
+  copy_out(v, imgs);
+}
+
 // ---- a7: TopDownMapPolar on installed layers ---------------------------------------------------------------------------
 REF_API void* ref_map_create(const float* layers, const uint8_t* mask, const float* geo, int rows, int cols, int C, float resolution,
                              const float* tab, int n_theta, int n_r, int center_x, int center_y) {

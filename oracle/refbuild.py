@@ -89,6 +89,22 @@ def render_polar(pts, res, ang_res, n_theta, n_r, lut, num_classes):
     return out
 
 
+def render_geometric_polar(pts, width, height, res, ang_res, n_theta, n_r):
+    """ScanRendererPolar::renderGeometricTopDown (scan_renderer_polar.cpp:6-81) -> (2, n_r, n_theta)"""
+    pts = np.ascontiguousarray(pts, dtype=np.float32)
+    out = np.zeros((2, n_r, n_theta), dtype=np.float32)
+    lib().ref_render_geometric_polar(_p(pts, _f32p), width, height, C.c_float(res), C.c_float(ang_res), n_theta, n_r, _p(out, _f32p))
+    return out
+
+
+def render_geometric_cart(pts, width, height, res, rows, cols):
+    """ScanRenderer::renderGeometricTopDown (scan_renderer.cpp:7-53) -> (2, cols, rows)"""
+    pts = np.ascontiguousarray(pts, dtype=np.float32)
+    out = np.zeros((2, cols, rows), dtype=np.float32)
+    lib().ref_render_geometric_cart(_p(pts, _f32p), width, height, C.c_float(res), rows, cols, _p(out, _f32p))
+    return out
+
+
 def render_cart(pts, res, rows, cols, lut, num_classes):
     """ScanRenderer::renderSemanticTopDown (scan_renderer.cpp:55-78) -> (C, cols, rows)"""
     pts = np.ascontiguousarray(pts, dtype=np.float32)

@@ -185,6 +185,103 @@ ORC_API void orc_render_cart(const uint8_t* pts, int stride, int intensity_off, 
 }
 
 // -----------------------------------------------------------------------------
+// f2  ScanRendererPolar::renderGeometricTopDown   src/scan_renderer_polar.cpp:6-81
+// The cloud is ORGANISED (width columns x height rows, point (col, row) at row * width + col) and walked column by
+// column (:27-28).  Points go to angular bins in that order (theta index clamped, :36-37), every bin is sorted by
+// descending planar range (std::sort, :50-52 — the order of exactly equal ranges is whatever introsort leaves; here the
+// same std::sort on the same sequence), then walked with the slope rule: a step steeper than 1 marks an obstacle cell in
+// imgs[1], a step flatter than 0.3 that does not follow an obstacle fills imgs[0] from the previous range bin up to this
+// one.  imgs: 2 images n_theta x n_r column-major.
+ORC_API void orc_render_geometric_polar(const uint8_t* pts, int stride, int width, int height, float res, float ang_res,
+                                        int n_theta, int n_r, float* imgs) {
+  std::memset(imgs, 0, sizeof(float) * 2 * (size_t)n_theta * n_r);                 // :12-14
+  struct P4 { float x, y, z, r; };
+  std::vector<std::vector<P4>> bins((size_t)n_theta);                             // :18-22
+  for (int idx = 0; idx < width; idx++) {                                          // :27
+    for (int idy = 0; idy < height; idy++) {                                       // :28
+      float x, y, z;
+      const uint8_t* q = pts + ((size_t)idy * width + idx) * stride;
+      std::memcpy(&x, q, 4); std::memcpy(&y, q + 4, 4); std::memcpy(&z, q + 8, 4);
+      if (x == 0 && y == 0) continue;                                              // :30
+      float theta = atan2(x, y);                                                   // :32
+      float r = sqrt(x * x + y * y);                                               // :33
+      float t = std::round(theta / ang_res) + n_theta / 2;                         // :36-37, clamp<float>
+      if (t != t) continue;                                                        // NaN: the reference indexes out of bounds
+      t = (t < 0.f) ? 0.f : (((float)(n_theta - 1) < t) ? (float)(n_theta - 1) : t);
+      bins[(size_t)(int)t].push_back(P4{x, y, z, r});                             // :39
+    }
+  }
+  for (int theta_ind = 0; theta_ind < n_theta; theta_ind++) {                      // :47
+    auto& bin = bins[(size_t)theta_ind];
+    std::sort(bin.begin(), bin.end(), [](P4& a, P4& b) { return a.r > b.r; });    // :50-52
+    float lx = 0, ly = 0, lz = 0;                                                  // :55
+    bool last_high_grad = false;
+    int last_r_ind = 0;
+    for (const P4& pt : bin) {                                                     // :58
+      const float dx = pt.x - lx, dy = pt.y - ly;
+      float s2 = 0.f; s2 = s2 + dx * dx; s2 = s2 + dy * dy;                        // head<2>().norm(): sequential sum of squares
+      const float dist = std::sqrt(s2);                                            // :59
+      const float slope = abs(pt.z - lz) / dist;                                   // :60 (float abs: <math.h>)
+      const int r_ind = f2i_x86(std::round(pt.r / res));                           // :61
+      if (slope > 1) {                                                             // :63
+        if (r_ind >= 0 && r_ind < n_r) imgs[(size_t)n_theta * n_r + (size_t)r_ind * n_theta + theta_ind] += 1;   // :64-66
+        last_high_grad = true;
+      } else if (slope < 0.3 && last_high_grad == false) {                         // :68 (double 0.3)
+        for (int i = last_r_ind; i <= r_ind; i += 1)                               // :69
+          if (i < n_r && i >= 0) imgs[(size_t)i * n_theta + theta_ind] += 1;       // :70-72 (i >= 0 always: ranges are >= 0)
+      } else {
+        last_high_grad = false;                                                    // :75
+      }
+      lx = pt.x; ly = pt.y; lz = pt.z;                                             // :77
+      last_r_ind = r_ind;
+    }
+  }
+}
+
+// f2  ScanRenderer::renderGeometricTopDown   src/scan_renderer.cpp:7-53
+// One pass per vertical scan line (column of the organised cloud); obstacle steps mark imgs[1], flat steps draw the
+// segment from the previous cell to this one into imgs[0] (float parameter i += 1. / |diff| with the INTEGER norm of
+// the index difference, :38-39).  imgs: 2 images rows x cols column-major, (y_ind, x_ind) at x_ind * rows + y_ind.
+ORC_API void orc_render_geometric_cart(const uint8_t* pts, int stride, int width, int height, float res, int rows, int cols,
+                                       float* imgs) {
+  std::memset(imgs, 0, sizeof(float) * 2 * (size_t)rows * cols);
+  const int sx = cols, sy = rows;                                                  // img_size = (cols, rows)  :10
+  for (int idx = 0; idx < width; idx++) {                                          // :16
+    float lx = 0, ly = 0, lz = 0;
+    int last_x = sx / 2, last_y = sy / 2;                                          // :19
+    bool last_high_grad = false;
+    for (int idy = 0; idy < height; idy++) {                                       // :23
+      float x, y, z;
+      const uint8_t* q = pts + ((size_t)idy * width + idx) * stride;
+      std::memcpy(&x, q, 4); std::memcpy(&y, q + 4, 4); std::memcpy(&z, q + 8, 4);
+      if (x == 0 && y == 0) continue;                                              // :26
+      const int x_ind = f2i_x86(std::round(x / res) + sx / 2);                     // :27
+      const int y_ind = f2i_x86(std::round(y / res) + sy / 2);                     // :28
+      const float dx = x - lx, dy = y - ly;
+      float s2 = 0.f; s2 = s2 + dx * dx; s2 = s2 + dy * dy;
+      const float dist = std::sqrt(s2);                                            // :30
+      const float slope = abs(z - lz) / dist;                                      // :31
+      if (slope > 1) {
+        if (x_ind >= 0 && x_ind < sx && y_ind >= 0 && y_ind < sy) imgs[(size_t)rows * cols + (size_t)x_ind * rows + y_ind] += 1;   // :33-35
+        last_high_grad = true;
+      } else if (slope < 0.3 && last_high_grad == false) {
+        const int ddx = x_ind - last_x, ddy = y_ind - last_y;                      // :38
+        const int nrm = (int)std::sqrt((double)((long long)ddx * ddx + (long long)ddy * ddy));   // Vector2i::norm(): integer
+        for (float i = 0; i < 1; i += 1. / nrm) {                                  // :39 (float += double)
+          const int ix = f2i_x86(round((float)last_x + i * (float)ddx));           // :40
+          const int iy = f2i_x86(round((float)last_y + i * (float)ddy));
+          if (ix >= 0 && ix < sx && iy >= 0 && iy < sy) imgs[(size_t)ix * rows + iy] += 1;   // :41-44
+        }
+      } else {
+        last_high_grad = false;
+      }
+      lx = x; ly = y; lz = z;                                                      // :49
+      last_x = x_ind; last_y = y_ind;
+    }
+  }
+}
+
+// -----------------------------------------------------------------------------
 // a3  TopDownMap::loadCompressedRasterMap   src/top_down_map.cpp:116-144
 // img: row-major uint8 (cv::Mat) h_img x w_img with row stride `stride`.
 // layers: C layers rows x cols column-major, rows=(int)(h_img/res), cols=(int)(w_img/res).

@@ -26,6 +26,8 @@ struct OrcFilterParams {
 };
 void orc_render_polar(const uint8_t* pts, int stride, int intensity_off, long n, float res, float ang_res, int n_theta, int n_r,
                       const int* lut, int n_lut, int C, float* imgs);
+void orc_render_geometric_polar(const uint8_t* pts, int stride, int width, int height, float res, float ang_res, int n_theta, int n_r, float* imgs);
+void orc_render_geometric_cart(const uint8_t* pts, int stride, int width, int height, float res, int rows, int cols, float* imgs);
 void orc_render_cart(const uint8_t* pts, int stride, int intensity_off, long n, float res, int rows, int cols, const int* lut, int n_lut,
                      int C, float* imgs);
 void orc_local_map_cart(const float* layers, const uint8_t* mask, int rows, int cols, int C, float resolution, float cx, float cy,
@@ -203,6 +205,16 @@ int tdr_scan_render_polar(tdr_ctx* c, float res, float ang_res, int n_theta, int
 int tdr_scan_render_cart(tdr_ctx* c, float res, int rows, int cols, float* imgs) {
   REQ(!c->lut.empty() && imgs, TDR_ESTATE, "no lut");
   orc_render_cart(c->pts.data(), c->pts_stride, c->pts_off, c->n_pts, res, rows, cols, c->lut.data(), c->n_lut, c->scan_C, imgs);
+  return TDR_OK;
+}
+int tdr_scan_render_geometric_polar(tdr_ctx* c, int width, int height, float res, float ang_res, int n_theta, int n_r, float* imgs) {
+  REQ((long)width * height == c->n_pts && imgs, TDR_EINVAL, "organised cloud expected");
+  orc_render_geometric_polar(c->pts.data(), c->pts_stride, width, height, res, ang_res, n_theta, n_r, imgs);
+  return TDR_OK;
+}
+int tdr_scan_render_geometric_cart(tdr_ctx* c, int width, int height, float res, int rows, int cols, float* imgs) {
+  REQ((long)width * height == c->n_pts && imgs, TDR_EINVAL, "organised cloud expected");
+  orc_render_geometric_cart(c->pts.data(), c->pts_stride, width, height, res, rows, cols, imgs);
   return TDR_OK;
 }
 int tdr_scan_set_polar_images(tdr_ctx* c, const float* imgs, int n_theta, int n_r, int C) {

@@ -40,6 +40,15 @@ def _check(kind):
         # other raster shapes: the size of the caller's images defines the raster
         assert np.array_equal(ref.render_polar(pts, 2.0, np.float32(2 * math.pi / 36), 36, 9, lut, 4),
                               orc.render_polar(pts, 2.0, np.float32(2 * math.pi / 36), 36, 9, lut, 4))
+        # the geometric renderers (scan_renderer_polar.cpp:6-81, scan_renderer.cpp:7-53) over the organised 256 x 32 cloud
+        gp = pts.copy()
+        rng = np.random.default_rng(4)
+        gp[:, 2] = -2.0 + rng.normal(0, 0.4, len(gp)).astype(np.float32) * (rng.random(len(gp)) < 0.3)
+        for res in (4.0, 1.0):
+            geo = ref.render_geometric_polar(gp, 256, 32, res, ANG, 100, 25)
+            assert np.array_equal(geo, orc.render_geometric_polar(gp, 256, 32, res, ANG, 100, 25)) and geo[0].sum() > 50 and geo[1].sum() > 50
+            gc = ref.render_geometric_cart(gp, 256, 32, res, 96, 80)
+            assert np.array_equal(gc, orc.render_geometric_cart(gp, 256, 32, res, 96, 80)) and gc[0].sum() > 50
 
 
 def _check_map(kind, tmp_path, resolutions=(1.0, 0.5), static_paths=True):

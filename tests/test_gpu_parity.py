@@ -111,6 +111,25 @@ def test_cartesian_class_images_bit_exact(world, ctx):
         assert np.array_equal(got, want), (rows, cols, res)
 
 
+@pytest.mark.parametrize("res", [4.0, 1.0])
+def test_geometric_renderers_bit_exact(world, ctx, res):
+    """f2: renderGeometricTopDown on the device (per angular bin: compaction in visiting order, sort by range, slope walk;
+    per scan line: slope walk + line drawing) against the oracle, which equals the reference build (test_ref_build.py)"""
+    pts = world.pts.copy()
+    rng = np.random.default_rng(12)
+    pts[:, 2] = -2.0 + rng.normal(0, 0.4, len(pts)).astype(np.float32) * (rng.random(len(pts)) < 0.3)
+    ctx.scan_set_points(pts)
+    got = ctx.scan_render_geometric_polar(1024, 64, res, ANG_RES, N_THETA, N_R)
+    want = orc.render_geometric_polar(pts, 1024, 64, res, ANG_RES, N_THETA, N_R)
+    assert want[0].sum() > 100 and want[1].sum() > 100
+    assert np.array_equal(got, want)
+    got = ctx.scan_render_geometric_cart(1024, 64, res, 150, 170)
+    want = orc.render_geometric_cart(pts, 1024, 64, res, 150, 170)
+    assert want[0].sum() > 100 and np.array_equal(got, want)
+    got = ctx.scan_render_geometric_polar(64, 1024, res, ANG_RES, N_THETA, N_R)
+    assert np.array_equal(got, orc.render_geometric_polar(pts, 64, 1024, res, ANG_RES, N_THETA, N_R))
+
+
 def test_empty_scan(world, ctx):
     pts = np.zeros((0, 8), dtype=np.float32)
     ctx.scan_set_points(pts)

@@ -59,6 +59,23 @@ def test_class_images_equal_the_reference_renderers(world, res):
 
 
 # ---- a7: TopDownMapPolar::getLocalMap / getLocalGeoMap ----------------------------------------------------------------
+@pytest.mark.parametrize("res", [4.0, 1.0, 0.37])
+def test_geometric_renderers_equal_the_reference(world, res):
+    """f2: ScanRendererPolar / ScanRenderer::renderGeometricTopDown (scan_renderer_polar.cpp:6-81, scan_renderer.cpp:7-53)
+    compiled from the reference's own sources against the oracle's restatement: an organised 1024 x 64 cloud with rough
+    ground (so that both slope branches, the fill loop and the line drawing are exercised), bit-identical images"""
+    pts = synth.make_scan(world["cm"], world["pose"], world["heading"], seed=21)      # 64 rings x 1024 azimuths
+    rng = np.random.default_rng(12)
+    pts[:, 2] = -2.0 + rng.normal(0, 0.4, len(pts)).astype(np.float32) * (rng.random(len(pts)) < 0.3)
+    a, b = orc.render_geometric_polar(pts, 1024, 64, res, ANG, 100, 25), ref.render_geometric_polar(pts, 1024, 64, res, ANG, 100, 25)
+    assert np.array_equal(a, b) and a[0].sum() > 100 and a[1].sum() > 100
+    a, b = orc.render_geometric_cart(pts, 1024, 64, res, 150, 170), ref.render_geometric_cart(pts, 1024, 64, res, 150, 170)
+    assert np.array_equal(a, b) and a[0].sum() > 100 and a[1].sum() > 100
+    # a transposed organisation (64 columns of 1024 points) visits the points in another order
+    a, b = orc.render_geometric_polar(pts, 64, 1024, res, ANG, 100, 25), ref.render_geometric_polar(pts, 64, 1024, res, ANG, 100, 25)
+    assert np.array_equal(a, b)
+
+
 def test_polar_gather_equals_the_reference(world):
     w = world
     rng = np.random.default_rng(1)

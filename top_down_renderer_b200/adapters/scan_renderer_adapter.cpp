@@ -5,9 +5,9 @@
 // in this repository, where ROS / Eigen / PCL are absent — against the stand-in headers of oracle/ref_shim
 // (`make -C oracle _adapters`), which is how tests/test_adapters.py links and runs it.
 //
-// renderGeometricTopDown (scan_renderer.cpp:7-53, scan_renderer_polar.cpp:6-81) keeps the reference's host body: its only
-// call is commented out (top_down_render.cpp:540) and the cost function ignores the geometric images; it is
-// not redefined here, so a package build keeps those two functions from the original files.
+// renderGeometricTopDown (scan_renderer.cpp:7-53, scan_renderer_polar.cpp:6-81) runs on the device too
+// (tdr_scan_render_geometric_polar / _cart): per angular bin a sort by range and the slope walk, per scan line the
+// slope walk with line drawing.  Its only call in the node is commented out (top_down_render.cpp:540).
 #include <cstddef>
 #include <cstdio>
 #include <cstdlib>
@@ -27,6 +27,12 @@ bool upload(const Eigen::VectorXi& lut, const pcl::PointCloud<pcl::PointXYZI>::C
   static_assert(sizeof(pcl::PointXYZI) == 32, "pcl::PointXYZI layout");
   if (!tdr()) return false;
   if (!ok(tdr_scan_set_lut(tdr(), lut.data(), (int)lut.size(), num_images))) return false;
+  return ok(tdr_scan_set_points(tdr(), cloud->points.data(), (int)sizeof(pcl::PointXYZI), (int)offsetof(pcl::PointXYZI, intensity),
+                                (int64_t)cloud->height * cloud->width));
+}
+// the geometric renderers need the points only (no class lut)
+bool upload_points(const pcl::PointCloud<pcl::PointXYZI>::ConstPtr& cloud) {
+  if (!tdr()) return false;
   return ok(tdr_scan_set_points(tdr(), cloud->points.data(), (int)sizeof(pcl::PointXYZI), (int)offsetof(pcl::PointXYZI, intensity),
                                 (int64_t)cloud->height * cloud->width));
 }
@@ -60,4 +66,32 @@ void ScanRendererPolar::renderSemanticTopDown(const pcl::PointCloud<pcl::PointXY
   std::vector<float> stage(imgs.size() * (size_t)n_theta * n_r);
   if (!ok(tdr_scan_render_polar(tdr(), res, ang_res, n_theta, n_r, stage.data()))) return;
   scatter(stage, imgs);
+}
+
+// replaces scan_renderer.cpp:7-53
+void ScanRenderer::renderGeometricTopDown(const pcl::PointCloud<pcl::PointXYZI>::ConstPtr& cloud, float res,
+                                          std::vector<Eigen::ArrayXXf>& imgs) {
+  if (imgs.size() < 2) return;                                                           // :9
+  const int rows = (int)imgs[0].rows(), cols = (int)imgs[0].cols();
+  if (!upload_points(cloud)) return;
+  std::vector<float> stage(2 * (size_t)rows * cols);
+  if (!ok(tdr_scan_render_geometric_cart(tdr(), (int)cloud->width, (int)cloud->height, res, rows, cols, stage.data()))) return;
+  for (size_t i = 2; i < imgs.size(); i++) imgs[i].setZero();                            // :12-14 zero every image
+  std::vector<Eigen::ArrayXXf> two(imgs.begin(), imgs.begin() + 2);
+  scatter(stage, two);
+  imgs[0] = two[0]; imgs[1] = two[1];
+}
+
+// replaces scan_renderer_polar.cpp:6-81
+void ScanRendererPolar::renderGeometricTopDown(const pcl::PointCloud<pcl::PointXYZI>::ConstPtr& cloud, float res, float ang_res,
+                                               std::vector<Eigen::ArrayXXf>& imgs) {
+  if (imgs.size() < 2) return;                                                           // :8
+  const int n_theta = (int)imgs[0].rows(), n_r = (int)imgs[0].cols();
+  if (!upload_points(cloud)) return;
+  std::vector<float> stage(2 * (size_t)n_theta * n_r);
+  if (!ok(tdr_scan_render_geometric_polar(tdr(), (int)cloud->width, (int)cloud->height, res, ang_res, n_theta, n_r, stage.data()))) return;
+  for (size_t i = 2; i < imgs.size(); i++) imgs[i].setZero();
+  std::vector<Eigen::ArrayXXf> two(imgs.begin(), imgs.begin() + 2);
+  scatter(stage, two);
+  imgs[0] = two[0]; imgs[1] = two[1];
 }

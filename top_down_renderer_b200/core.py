@@ -200,6 +200,18 @@ class Context:
         check(self._lib.tdr_scan_render_cart(self._h, C.c_float(res), int(rows), int(cols), _pf(out)))
         return out
 
+    def scan_render_geometric_polar(self, width, height, res, ang_res, n_theta, n_r):
+        """ScanRendererPolar::renderGeometricTopDown over the resident points as a width x height organised cloud"""
+        out = np.empty((2, n_r, n_theta), dtype=np.float32)
+        check(self._lib.tdr_scan_render_geometric_polar(self._h, int(width), int(height), C.c_float(res), C.c_float(ang_res),
+                                                        int(n_theta), int(n_r), _pf(out)))
+        return out
+
+    def scan_render_geometric_cart(self, width, height, res, rows, cols):
+        out = np.empty((2, cols, rows), dtype=np.float32)
+        check(self._lib.tdr_scan_render_geometric_cart(self._h, int(width), int(height), C.c_float(res), int(rows), int(cols), _pf(out)))
+        return out
+
     def refine_bin(self, xy, cls, res, cx, cy, width, height, num_classes):
         xy = np.ascontiguousarray(xy, dtype=np.float32).reshape(-1, 2)
         cls = np.ascontiguousarray(cls, dtype=np.int32)

@@ -451,6 +451,28 @@ int tdr_scan_render_cart(tdr_ctx* ctx, float res, int rows, int cols, float* img
   return TDR_OK;
 }
 
+int tdr_scan_render_geometric_polar(tdr_ctx* ctx, int width, int height, float res, float ang_res, int n_theta, int n_r, float* imgs) {
+  CTX_CHECK(ctx);
+  TDR_REQUIRE(imgs && n_theta > 0 && n_r > 0 && n_r <= 1024, TDR_EINVAL, "bad geometric image shape");
+  const size_t bytes = (size_t)2 * n_theta * n_r * 4;
+  if (int e = ctx->scratch2.reserve(bytes)) return e;
+  if (int e = scan_render_geometric(ctx, true, res, ang_res, n_theta, n_r, width, height, ctx->scratch2.as<float>())) return e;
+  TDR_CUDA(cudaMemcpyAsync(imgs, ctx->scratch2.p, bytes, cudaMemcpyDeviceToHost, ctx->stream));
+  TDR_CUDA(cudaStreamSynchronize(ctx->stream));
+  return TDR_OK;
+}
+
+int tdr_scan_render_geometric_cart(tdr_ctx* ctx, int width, int height, float res, int rows, int cols, float* imgs) {
+  CTX_CHECK(ctx);
+  TDR_REQUIRE(imgs && rows > 0 && cols > 0, TDR_EINVAL, "bad geometric image shape");
+  const size_t bytes = (size_t)2 * rows * cols * 4;
+  if (int e = ctx->scratch2.reserve(bytes)) return e;
+  if (int e = scan_render_geometric(ctx, false, res, 0.f, rows, cols, width, height, ctx->scratch2.as<float>())) return e;
+  TDR_CUDA(cudaMemcpyAsync(imgs, ctx->scratch2.p, bytes, cudaMemcpyDeviceToHost, ctx->stream));
+  TDR_CUDA(cudaStreamSynchronize(ctx->stream));
+  return TDR_OK;
+}
+
 int tdr_refine_bin(tdr_ctx* ctx, const float* xy, const int32_t* cls, int64_t n, float res, float center_x, float center_y,
                    int width, int height, int num_classes, uint8_t* maps_out) {
   CTX_CHECK(ctx);

@@ -289,6 +289,174 @@ int refine_bin(tdr_ctx* ctx, const float* xy, const int32_t* cls, long long n, f
   return refine_counts(ctx, maps_out);
 }
 
+// ------------------------------------------------------------------------------------------------
+// f2: the geometric renderers (scan_renderer_polar.cpp:6-81, scan_renderer.cpp:7-53) — the last reference function of
+// SURVEY section 8 without a kernel.  The cloud is organised: `width` columns x `height` rows, point (col, row) at
+// row * width + col, visited column by column.
+// ------------------------------------------------------------------------------------------------
+static const int GEO_CAP = 8192;             // points one angular bin can hold (shared memory: keys + xyz)
+
+// Polar: one CTA per angular bin.  (1) the bin's points in visiting order (block-wide compaction), (2) bitonic sort
+// by descending range — equal ranges keep the visiting order, where std::sort (:50-52) leaves their order open —
+// (3) one thread walks the sorted points with the slope rule (:58-78): the walk is a dependent chain by construction.
+__global__ void __launch_bounds__(1024) k_geo_polar(const uint8_t* __restrict__ pts, int stride, int width, int height, float res,
+                                                    float ang_res, int n_theta, int n_r, float* __restrict__ out,
+                                                    int* __restrict__ overflow) {
+  extern __shared__ __align__(16) unsigned char smem[];
+  unsigned long long* keys = reinterpret_cast<unsigned long long*>(smem);          // [GEO_CAP]
+  float* xyz = reinterpret_cast<float*>(keys + GEO_CAP);                           // [GEO_CAP][3]
+  float* row = xyz + 3 * GEO_CAP;                                                   // [2][n_r]
+  __shared__ int s_warp[32];
+  __shared__ int s_count;
+  const int bin = blockIdx.x, tid = threadIdx.x, lane = tid & 31, warp = tid >> 5;
+  if (tid == 0) s_count = 0;
+  for (int q = tid; q < 2 * n_r; q += blockDim.x) row[q] = 0.f;
+  __syncthreads();
+  const long long n = (long long)width * height;
+  for (long long base = 0; base < n; base += blockDim.x) {
+    const long long o = base + tid;                     // visiting order: o = col * height + row
+    bool mine = false;
+    float x = 0.f, y = 0.f, z = 0.f, r = 0.f;
+    if (o < n) {
+      const int col = (int)(o / height), rw = (int)(o - (long long)col * height);
+      const uint8_t* p = pts + ((size_t)rw * width + col) * stride;
+      x = *reinterpret_cast<const float*>(p); y = *reinterpret_cast<const float*>(p + 4); z = *reinterpret_cast<const float*>(p + 8);
+      if (!(x == 0.f && y == 0.f)) {                                                       // :30
+        const float theta = fdlibm_atan2f(x, y);                                           // :32 atan2(pt.x, pt.y)
+        r = TDR_FSQRT(TDR_FADD(TDR_FMUL(x, x), TDR_FMUL(y, y)));                           // :33
+        float t = TDR_FADD(round_half_away(TDR_FDIV(theta, ang_res)), (float)(n_theta / 2));   // :36-37
+        if (t == t) {
+          t = (t < 0.f) ? 0.f : (((float)(n_theta - 1) < t) ? (float)(n_theta - 1) : t);   // std::clamp<float>
+          mine = (int)t == bin;
+        }
+      }
+    }
+    // ordered append: positions by a block-wide exclusive count
+    const unsigned bal = __ballot_sync(0xffffffffu, mine);
+    if (lane == 0) s_warp[warp] = __popc(bal);
+    __syncthreads();
+    int before = s_count;
+    for (int w = 0; w < warp; w++) before += s_warp[w];
+    const int pos = before + __popc(bal & ((1u << lane) - 1u));
+    if (mine) {
+      if (pos < GEO_CAP) {
+        keys[pos] = ((unsigned long long)(~__float_as_uint(r)) << 32) | (unsigned)pos;      // r >= 0: bits order like values
+        xyz[3 * pos] = x; xyz[3 * pos + 1] = y; xyz[3 * pos + 2] = z;
+      } else atomicExch(overflow, 1);
+    }
+    __syncthreads();
+    if (tid == 0) { int t = 0; for (int w = 0; w < (int)(blockDim.x >> 5); w++) t += s_warp[w]; s_count += t; }
+    __syncthreads();
+  }
+  const int count = s_count < GEO_CAP ? s_count : GEO_CAP;
+  int m = 1; while (m < count) m <<= 1;
+  for (int q = count + tid; q < m; q += blockDim.x) keys[q] = ~0ull;                        // padding sorts last
+  __syncthreads();
+  for (int k = 2; k <= m; k <<= 1)
+    for (int j = k >> 1; j > 0; j >>= 1) {
+      for (int q = tid; q < m; q += blockDim.x) {
+        const int l = q ^ j;
+        if (l > q) {
+          const unsigned long long a = keys[q], b = keys[l];
+          const bool up = (q & k) == 0;
+          if ((a > b) == up) { keys[q] = b; keys[l] = a; }
+        }
+      }
+      __syncthreads();
+    }
+  if (tid == 0) {
+    float lx = 0.f, ly = 0.f, lz = 0.f;                                                     // :55
+    bool last_high = false;
+    int last_r = 0;
+    for (int q = 0; q < count; q++) {
+      const unsigned long long key = keys[q];
+      const int src = (int)(key & 0xffffffffu);
+      const float r = __uint_as_float(~(unsigned)(key >> 32));
+      const float x = xyz[3 * src], y = xyz[3 * src + 1], z = xyz[3 * src + 2];
+      const float dx = TDR_FSUB(x, lx), dy = TDR_FSUB(y, ly);
+      const float dist = TDR_FSQRT(TDR_FADD(TDR_FADD(0.f, TDR_FMUL(dx, dx)), TDR_FMUL(dy, dy)));   // :59
+      const float slope = TDR_FDIV(fabsf(TDR_FSUB(z, lz)), dist);                           // :60
+      const int r_ind = f2i_x86(round_half_away(TDR_FDIV(r, res)));                         // :61
+      if (slope > 1.f) {                                                                    // :63
+        if (r_ind >= 0 && r_ind < n_r) row[n_r + r_ind] += 1.f;
+        last_high = true;
+      } else if ((double)slope < 0.3 && !last_high) {                                       // :68
+        for (int i = last_r; i <= r_ind; i++) if (i >= 0 && i < n_r) row[i] += 1.f;         // :69-73
+      } else last_high = false;
+      lx = x; ly = y; lz = z; last_r = r_ind;
+    }
+  }
+  __syncthreads();
+  for (int q = tid; q < 2 * n_r; q += blockDim.x) {
+    const int img = q / n_r, r = q - img * n_r;
+    out[((size_t)img * n_r + r) * n_theta + bin] = row[q];                                  // img(theta, r) at r * n_theta + theta
+  }
+}
+
+// Cartesian: one thread per vertical scan line (column), integer counters (exact, order-independent)
+__global__ void k_geo_cart(const uint8_t* __restrict__ pts, int stride, int width, int height, float res, int rows, int cols,
+                           int32_t* __restrict__ cnt) {
+  const int idx = blockIdx.x * blockDim.x + threadIdx.x;
+  if (idx >= width) return;
+  const int sx = cols, sy = rows;
+  float lx = 0.f, ly = 0.f, lz = 0.f;
+  int last_x = sx / 2, last_y = sy / 2;                                                     // :19
+  bool last_high = false;
+  for (int idy = 0; idy < height; idy++) {
+    const uint8_t* p = pts + ((size_t)idy * width + idx) * stride;
+    const float x = *reinterpret_cast<const float*>(p), y = *reinterpret_cast<const float*>(p + 4), z = *reinterpret_cast<const float*>(p + 8);
+    if (x == 0.f && y == 0.f) continue;                                                     // :26
+    const int x_ind = f2i_x86(TDR_FADD(round_half_away(TDR_FDIV(x, res)), (float)(sx / 2)));    // :27
+    const int y_ind = f2i_x86(TDR_FADD(round_half_away(TDR_FDIV(y, res)), (float)(sy / 2)));    // :28
+    const float dx = TDR_FSUB(x, lx), dy = TDR_FSUB(y, ly);
+    const float dist = TDR_FSQRT(TDR_FADD(TDR_FADD(0.f, TDR_FMUL(dx, dx)), TDR_FMUL(dy, dy)));     // :30
+    const float slope = TDR_FDIV(fabsf(TDR_FSUB(z, lz)), dist);                             // :31
+    if (slope > 1.f) {
+      if (x_ind >= 0 && x_ind < sx && y_ind >= 0 && y_ind < sy) atomicAdd(cnt + (size_t)rows * cols + (size_t)x_ind * rows + y_ind, 1);
+      last_high = true;
+    } else if ((double)slope < 0.3 && !last_high) {
+      const int ddx = x_ind - last_x, ddy = y_ind - last_y;                                 // :38
+      const int nrm = (int)sqrt((double)((long long)ddx * ddx + (long long)ddy * ddy));     // Vector2i::norm(): integer
+      const double step = 1.0 / (double)nrm;                                                // inf when the cell did not change
+      for (float i = 0.f; i < 1.f; i = (float)((double)i + step)) {                         // :39
+        const int ix = f2i_x86(round_half_away(TDR_FADD((float)last_x, TDR_FMUL(i, (float)ddx))));   // :40
+        const int iy = f2i_x86(round_half_away(TDR_FADD((float)last_y, TDR_FMUL(i, (float)ddy))));
+        if (ix >= 0 && ix < sx && iy >= 0 && iy < sy) atomicAdd(cnt + (size_t)ix * rows + iy, 1);
+      }
+    } else last_high = false;
+    lx = x; ly = y; lz = z; last_x = x_ind; last_y = y_ind;
+  }
+}
+
+// polar: d0 = n_theta, d1 = n_r; cart: d0 = rows, d1 = cols.  dev_out: 2 images, column-major.
+int scan_render_geometric(tdr_ctx* ctx, bool polar, float res, float ang_res, int d0, int d1, int width, int height, float* dev_out) {
+  TDR_REQUIRE(ctx->n_pts > 0 && (long long)width * height == ctx->n_pts, TDR_EINVAL,
+              "organised cloud of %d x %d points expected, %lld resident", width, height, (long long)ctx->n_pts);
+  const uint8_t* pts = ctx->pts.as<uint8_t>();
+  if (polar) {
+    const size_t smem = (size_t)GEO_CAP * (8 + 12) + (size_t)2 * d1 * 4;
+    TDR_SMEM_OPTIN(ctx, OPTIN_GEO_POLAR, k_geo_polar, smem);
+    int* d_over = reinterpret_cast<int*>(ctx->scal.as<float>() + SC_MMA_MAXCOUNT);
+    TDR_CUDA(cudaMemsetAsync(d_over, 0, 4, ctx->stream));
+    k_geo_polar<<<d0, 1024, smem, ctx->stream>>>(pts, ctx->pts_stride, width, height, res, ang_res, d0, d1, dev_out, d_over);
+    count_launch(ctx);
+    TDR_CUDA(cudaGetLastError());
+    int over = 0;
+    TDR_CUDA(cudaMemcpyAsync(&over, d_over, 4, cudaMemcpyDeviceToHost, ctx->stream));
+    TDR_CUDA(cudaStreamSynchronize(ctx->stream));
+    TDR_REQUIRE(!over, TDR_EUNSUPPORTED, "an angular bin holds more than %d points", GEO_CAP);
+    return TDR_OK;
+  }
+  const size_t cells = (size_t)2 * d0 * d1;
+  if (int e = ctx->hist.reserve(cells * 4)) return e;
+  TDR_CUDA(cudaMemsetAsync(ctx->hist.p, 0, cells * 4, ctx->stream));
+  k_geo_cart<<<(width + 127) / 128, 128, 0, ctx->stream>>>(pts, ctx->pts_stride, width, height, res, d0, d1, ctx->hist.as<int32_t>());
+  k_hist_to_float<<<(unsigned)((cells + 255) / 256), 256, 0, ctx->stream>>>(ctx->hist.as<int32_t>(), (int)cells, dev_out);
+  count_launch(ctx, 2);
+  TDR_CUDA(cudaGetLastError());
+  return TDR_OK;
+}
+
 int scan_pack(tdr_ctx* ctx) {
   TDR_REQUIRE(ctx->have_scan && ctx->have_params, TDR_ESTATE, "scan images / filter params missing");
   int P = ctx->scan_theta * ctx->scan_r;

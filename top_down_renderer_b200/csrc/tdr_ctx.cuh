@@ -241,7 +241,7 @@ enum {
 
 inline void count_launch(tdr_ctx* c, int k = 1) { c->launches += k; }
 // opt a kernel into more than 48 KB of dynamic shared memory once per context (= per device)
-enum { OPTIN_SCORE_TRACK = 0, OPTIN_SCORE_SEARCH, OPTIN_SMALL_UPDATE, OPTIN_SCAN_BIN, OPTIN_EDT_ROWS, OPTIN_NORM_FUSED,
+enum { OPTIN_SCORE_TRACK = 0, OPTIN_SCORE_SEARCH, OPTIN_SMALL_UPDATE, OPTIN_SCAN_BIN, OPTIN_EDT_ROWS, OPTIN_NORM_FUSED, OPTIN_GEO_POLAR,
        OPTIN_LIST_BASE = 16 /* + kernel variant */, OPTIN_RING_BASE = 32, OPTIN_TILE_BASE = 48 };
 #define TDR_SMEM_OPTIN(ctx, bit, kernel, bytes)                                                                   \
   do {                                                                                                            \
@@ -268,6 +268,7 @@ int map_set_polygons(tdr_ctx*, const float* verts, const int32_t* poly_start, co
 // scan_render.cu
 int scan_render(tdr_ctx*, bool polar, float res, float ang_res, int d0, int d1, float* dev_img_out);
 int scan_pack(tdr_ctx*);
+int scan_render_geometric(tdr_ctx*, bool polar, float res, float ang_res, int d0, int d1, int width, int height, float* dev_out);
 int refine_begin(tdr_ctx*, float res, float cx, float cy, int width, int height, int C);
 int refine_add(tdr_ctx*, const float* xy, const int32_t* cls, long long n, bool on_device);
 int refine_counts(tdr_ctx*, uint8_t* maps_out);
