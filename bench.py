@@ -697,6 +697,23 @@ def measure_grid(wl, rank, world, local, steps, warmup, grid_collective, with_ve
 _REAL_STDOUT = None
 
 
+def class_api_record():
+    """the same update through the reference's OWN class interface (ParticleFilter::propagate / update / pose members on the
+    adapters, tools/class_api_bench.py) — a separate process: the adapters own their device context"""
+    so = os.path.join(ROOT, "oracle", "_ref", "libtdr_adapters_gpu.so")
+    if not os.path.exists(so):
+        return {"unavailable": "oracle/_ref/libtdr_adapters_gpu.so is not built (needs /root/reference at build time)"}
+    try:
+        r = subprocess.run([sys.executable, os.path.join(ROOT, "tools", "class_api_bench.py"), "1000000", "5", "both"],
+                           capture_output=True, text=True, timeout=300)
+        line = [ln for ln in r.stdout.splitlines() if ln.startswith("{")]
+        if r.returncode != 0 or not line:
+            return {"unavailable": "tools/class_api_bench.py failed: " + (r.stderr.strip().splitlines() or ["?"])[-1][:200]}
+        return json.loads(line[-1])
+    except Exception as e:                                      # a missing adapter build must not cost the headline line
+        return {"unavailable": f"{type(e).__name__}: {e}"[:200]}
+
+
 def run_refine(args, wl):
     """cfg5 (a composition): refine_map's binning rule over a batch of recorded scans, then the
     distance fields of the binned class maps.  One step = the WHOLE batch: zero the counters, bin every chunk, rebuild
@@ -892,6 +909,8 @@ def main():
                                "vs_1gpu": (g["value"] / g1["value"]) if g1 else 1.0,
                                "ms_per_step_1gpu": g1["ms_per_step"] if g1 else g["ms_per_step"],
                                "collective": g["config"]["parallelism"]}
+    if rank == 0 and out is not None and args.workload == "global" and not args.no_sub and not args.particles:
+        out["e2e_class_api"] = class_api_record()
     if rank == 0 and out is not None:
         emit(out)
     if world > 1:

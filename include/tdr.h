@@ -182,6 +182,14 @@ int tdr_pf_set_search(tdr_ctx* ctx, const float* thetas, const int32_t* shifts, 
 int tdr_pf_set_states(tdr_ctx* ctx, const tdr_state* states, const float* last_dist, int64_t n);
 int tdr_pf_get_states(tdr_ctx* ctx, tdr_state* states, int64_t n);
 int tdr_pf_count(tdr_ctx* ctx, int64_t* n);
+/* For a host mirror that is refreshed LAZILY (the adapter behind ParticleFilter, SURVEY section 7 H7: the node's own
+ * propagate / update calls move no particle data; visualize, the GMM thread or a harness pull it when they read):
+ * the set the last resampling read from — the particles that were scored, what new_particles_ holds after
+ * ParticleFilter::update's swap (particle_filter.cpp:187) — and the raw weights of the last scoring
+ * (StateParticle::weight()), kept in a device-side copy once tdr_pf_keep_raw_weights is on. */
+int tdr_pf_get_prev_states(tdr_ctx* ctx, tdr_state* states, float* last_dist, int64_t n);
+int tdr_pf_keep_raw_weights(tdr_ctx* ctx, int on);
+int tdr_pf_get_raw_weights(tdr_ctx* ctx, float* weights, int64_t n);
 /* device-side snapshot / roll-back of the resident particle set (asynchronous, D2D).  No reference
  * counterpart: lets a supervisor (or bench.py) replay an update from the same prior without a
  * 28 B/particle H2D. */

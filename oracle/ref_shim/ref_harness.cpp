@@ -215,10 +215,24 @@ REF_API void* ref_filter_create(void* map, int N, const RefFilterParams* rp, uin
   if (initialize) f->initializeParticles();
   return f;
 }
-REF_API long ref_filter_count(void* fv) { return (long)static_cast<ParticleFilter*>(fv)->particles_.size(); }
+// the adapters keep particles_ / new_particles_ / weights_ as a LAZY mirror of the device set: visualize is the reader
+// that refreshes it (adapters/particle_filter_adapter.cpp); the reference's own classes need nothing
+#ifdef TDR_ADAPTER_BUILD
+extern "C" void tdr_adapter_mark_host_ahead(const void* filter);
+#endif
+static void sync_mirror(ParticleFilter* f) {
+#ifdef TDR_ADAPTER_BUILD
+  cv::Mat none;
+  f->visualize(none);
+#else
+  (void)f;
+#endif
+}
+REF_API long ref_filter_count(void* fv) { sync_mirror(static_cast<ParticleFilter*>(fv)); return (long)static_cast<ParticleFilter*>(fv)->particles_.size(); }
 REF_API int ref_filter_num_particles(void* fv) { return static_cast<ParticleFilter*>(fv)->numParticles(); }
 // which: 0 = particles_ (the current set), 1 = new_particles_ (after an update: the set that was scored)
 REF_API long ref_filter_get(void* fv, int which, State* st, float* last_dist, float* raw_weight, long cap) {
+  sync_mirror(static_cast<ParticleFilter*>(fv));
   auto* f = static_cast<ParticleFilter*>(fv);
   std::lock_guard<std::mutex> g(f->particle_lock_);
   auto& v = which ? f->new_particles_ : f->particles_;
@@ -231,14 +245,19 @@ REF_API long ref_filter_get(void* fv, int which, State* st, float* last_dist, fl
   return (long)v.size();
 }
 REF_API void ref_filter_set(void* fv, const State* st, const float* last_dist, long n) {
+  sync_mirror(static_cast<ParticleFilter*>(fv));
   auto* f = static_cast<ParticleFilter*>(fv);
   std::lock_guard<std::mutex> g(f->particle_lock_);
   for (long i = 0; i < n && i < (long)f->particles_.size(); i++) {
     f->particles_[i]->setState(st[i]);
     if (last_dist) f->particles_[i]->last_dist_ = last_dist[i];
   }
+#ifdef TDR_ADAPTER_BUILD
+  tdr_adapter_mark_host_ahead(f);
+#endif
 }
 REF_API long ref_filter_weights(void* fv, float* w, long cap) {
+  sync_mirror(static_cast<ParticleFilter*>(fv));
   auto* f = static_cast<ParticleFilter*>(fv);
   long n = std::min<long>(cap, (long)f->weights_.size());
   for (long i = 0; i < n; i++) w[i] = f->weights_[i];

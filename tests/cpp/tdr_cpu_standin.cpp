@@ -62,7 +62,9 @@ struct tdr_ctx {
   std::vector<uint8_t> mask, pts;
   std::vector<int> lut, shifts;
   int pts_stride = 0, pts_off = 0; long n_pts = 0;
-  std::vector<OrcState> states;
+  std::vector<OrcState> states, prev_states;
+  std::vector<float> prev_last_dist, raw;
+  bool keep_raw = false;
   OrcState ml_state{};
   bool have_ml = false, have_geo = false;
   tdr_filter_params fp{};
@@ -269,6 +271,10 @@ int tdr_pf_propagate(tdr_ctx* c, float tx, float ty, float omega, int freeze, fl
   }
   return TDR_OK;
 }
+int tdr_pf_propagate_rng(tdr_ctx*, float, float, float, int, float, float, uint64_t, uint64_t, float*) {
+  g_err = "the CPU stand-in has no device RNG (TDR_ADAPTER_DEVICE_RNG needs the real library)";
+  return TDR_EUNSUPPORTED;
+}
 int tdr_pf_gmm_samples(tdr_ctx* c, int num, double* out) {
   REQ(!c->states.empty() && num > 0, TDR_ESTATE, "no particles");
   orc_gmm_samples(c->states.data(), (long)c->states.size(), num, out);
@@ -287,6 +293,7 @@ int tdr_pf_score(tdr_ctx* c, float res, float* weights_out) {
   const int nt = (int)std::max(1u, std::min(8u, std::thread::hardware_concurrency()));
   orc_score_all(c->states.data(), n, &fp, c->layers.data(), c->mask.data(), nullptr, c->rows, c->cols, c->resolution, c->tab.data(),
                 c->n_theta, c->n_r, c->scan.data(), res, c->thetas.data(), c->shifts.data(), (int)c->thetas.size(), c->weights.data(), nt);
+  if (c->keep_raw) c->raw = c->weights;
   if (weights_out) std::copy(c->weights.begin(), c->weights.end(), weights_out);
   return TDR_OK;
 }
@@ -305,7 +312,20 @@ int tdr_pf_resample(tdr_ctx* c, float u, int64_t M, int32_t* idx_out) {
   std::vector<OrcState> ns((size_t)M); std::vector<float> nl((size_t)M);
   for (int64_t i = 0; i < M; i++) { ns[i] = c->states[idx[i]]; nl[i] = c->last_dist[idx[i]]; }
   c->states.swap(ns); c->last_dist.swap(nl);
+  c->prev_states.swap(ns); c->prev_last_dist.swap(nl);          // the set the resampling read from
   if (idx_out) std::copy(idx.begin(), idx.end(), idx_out);
+  return TDR_OK;
+}
+int tdr_pf_get_prev_states(tdr_ctx* c, tdr_state* st, float* ld, int64_t n) {
+  REQ(st && n > 0 && n <= (int64_t)c->prev_states.size(), TDR_EINVAL, "bad state count");
+  std::memcpy(st, c->prev_states.data(), (size_t)n * sizeof(tdr_state));
+  if (ld) std::copy(c->prev_last_dist.begin(), c->prev_last_dist.begin() + n, ld);
+  return TDR_OK;
+}
+int tdr_pf_keep_raw_weights(tdr_ctx* c, int on) { c->keep_raw = on != 0; return TDR_OK; }
+int tdr_pf_get_raw_weights(tdr_ctx* c, float* w, int64_t n) {
+  REQ(w && n > 0 && n <= (int64_t)c->raw.size(), TDR_EINVAL, "bad raw weight count");
+  std::copy(c->raw.begin(), c->raw.begin() + n, w);
   return TDR_OK;
 }
 int tdr_pf_update(tdr_ctx* c, float res, float u, int64_t M) {

@@ -330,3 +330,31 @@ def test_theta_search_is_repeatable(world6):
     c.close()
     for r in out[1:]:
         assert np.array_equal(out[0].view(np.uint32), r.view(np.uint32))
+
+
+@pytest.mark.parametrize("impl", [0, 2])
+def test_large_tracked_set_through_the_ring_kernel(world6, impl):
+    """100 000 particles WITH a heading: from 65 536 up the tracked set goes through the tensor-core ring kernel (every
+    particle keeps the column of its own heading) instead of one warp per particle; same weights as the oracle, the
+    headings untouched, gated and mostly-unknown particles as in state_particle.cpp:163-176 / :117-120."""
+    wd = world6
+    n = 100_000
+    st, ld = synth.particles_global(n, wd.class_map, seed=41)
+    rng = np.random.default_rng(41)
+    st["theta"] = rng.uniform(-7.0, 7.0, n).astype(np.float32)
+    st["have_init"] = 1
+    st["init_x_px"][:50] = -800                       # off the map: every cell unknown -> NaN cost -> NaN weight
+    st["init_y_px"][50:80] = 1e9
+    c = make_ctx(wd)
+    c.set_score_impl(impl)
+    c.scan_set_polar_images(wd.scan)
+    c.pf_set_states(st, ld)
+    got = c.pf_score(4.0)
+    st_g = c.pf_get_states()
+    c.close()
+    st_o = st.copy()
+    want = orc.score_all(st_o, wd.fp, wd.layers, wd.mask, 1.0, wd.tab, N_THETA, N_R, wd.scan, 4.0, wd.thetas, wd.shifts)
+    e = rel_err(got, want)
+    assert np.isfinite(e).all() and e.max() <= WEIGHT_RTOL, e.max()
+    assert np.isnan(got[:50]).all()
+    assert np.array_equal(st_g["theta"], st["theta"]) and (st_g["have_init"] == 1).all()

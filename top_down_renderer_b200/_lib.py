@@ -63,7 +63,7 @@ SYMBOLS = [
     "tdr_map_info", "tdr_map_get_geo_layers", "tdr_map_set_polar_table", "tdr_map_local_polar", "tdr_map_local_cart", "tdr_map_local_geo_polar", "tdr_map_set_geo_dist_layers", "tdr_active_best_rel_pos",
     "tdr_scan_set_points", "tdr_scan_set_lut", "tdr_scan_render_polar", "tdr_scan_render_cart", "tdr_scan_render_geometric_polar", "tdr_scan_render_geometric_cart",
     "tdr_scan_set_polar_images", "tdr_refine_bin", "tdr_refine_begin", "tdr_refine_add", "tdr_refine_add_dev", "tdr_refine_counts", "tdr_refine_rebuild_map", "tdr_pf_set_params", "tdr_pf_set_search", "tdr_pf_set_states", "tdr_pf_get_states",
-    "tdr_pf_count", "tdr_pf_checkpoint", "tdr_pf_restore", "tdr_pf_score", "tdr_pf_set_weights", "tdr_pf_get_weights", "tdr_pf_normalize", "tdr_pf_resample", "tdr_pf_normalize_resample",
+    "tdr_pf_count", "tdr_pf_get_prev_states", "tdr_pf_keep_raw_weights", "tdr_pf_get_raw_weights", "tdr_pf_checkpoint", "tdr_pf_restore", "tdr_pf_score", "tdr_pf_set_weights", "tdr_pf_get_weights", "tdr_pf_normalize", "tdr_pf_resample", "tdr_pf_normalize_resample",
     "tdr_pf_pose", "tdr_pf_update", "tdr_step", "tdr_grid_costs", "tdr_grid_best", "tdr_grid_set_costs_buffer", "tdr_grid_best_dev", "tdr_grid_best_key", "tdr_grid_key_decode", "tdr_grid_peer_alloc", "tdr_grid_peer_open",
     "tdr_grid_peer_set", "tdr_grid_peer_clear", "tdr_dev_ptr",
     "tdr_pf_propagate", "tdr_pf_propagate_dev", "tdr_pf_propagate_rng", "tdr_pf_get_last_dist", "tdr_pf_gmm_samples",

@@ -5,14 +5,17 @@
 // rejection sampling of the StateParticle constructor, the standard-normal variates of propagate, the single uniform of
 // update — so a run with the same seed consumes the engine exactly as the reference does.
 //
-// particles_ / new_particles_ / weights_ — the members the header declares — are kept as host mirrors of the device set
-// (states, last_dist, raw weight per particle; normalised weights), which is what visualize, the GMM thread and the harness
-// read.  The headers give ParticleFilter no access to StateParticle's private fields, so the reference's own call structure
-// carries the results back: update() scores the WHOLE set on the device, then calls computeWeight on every particle, whose
-// body here takes that particle's raw weight / heading from the staged result; propagate() likewise.  A production build
-// would refresh lazily (28 B per particle and step over PCIe); tdr_host.hpp shows that variant.  visualize (:367-421,
-// drawing only) keeps the reference's body.
+// particles_ / new_particles_ / weights_ — the members the header declares — are a host MIRROR of the device set, refreshed
+// LAZILY: the node's per-scan calls, propagate and update, move no particle data over PCIe (16 B of
+// standard variates per particle go up for propagate, or nothing with TDR_ADAPTER_DEVICE_RNG=1); the pose members read
+// the device; visualize, the map shift, freezeScale and a test harness pull the states when they read them
+// (tdr_adapter_sync_mirror).  The headers give ParticleFilter no access to StateParticle's private fields (weight_,
+// last_dist_), so the refresh goes through StateParticle's own members: their bodies here take one particle's share of a
+// staged result, in particle order.  What the adapter needs beyond the declared members (is the mirror behind the device?
+// which arg-max?) lives in a side table keyed by the filter — the class declaration stays the reference's.
 #include <cstring>
+#include <map>
+#include <mutex>
 #include <vector>
 
 #include "top_down_render/particle_filter.h"
@@ -79,26 +82,49 @@ float StateParticle::lastDist() const { return last_dist_; }
 // propagate (:57-78) and computeWeight / getCostForRot (:112-219) run for the WHOLE set on the device (ParticleFilter below);
 // these two members hand one particle its share of the staged result, in particle order
 namespace {
-std::vector<tdr_state> g_stage_states;
-std::vector<float> g_stage_last_dist, g_stage_weight;
-size_t g_cursor = 0;
+// per thread: the spinner thread and the GMM thread never share a staging area (and both hold particle_lock_ anyway)
+struct Stage {
+  std::vector<tdr_state> states;
+  std::vector<float> last_dist, weight;
+  size_t cursor = 0;
+};
+thread_local Stage g_stage;
 }  // namespace
 void StateParticle::propagate(Eigen::Vector2f&, float, bool) {
-  const tdr_state& t = g_stage_states[g_cursor];
-  state_.dx_m = t.dx_m; state_.dy_m = t.dy_m; state_.theta = t.theta; state_.scale = t.scale;
-  last_dist_ = g_stage_last_dist[g_cursor++];
+  const tdr_state& t = g_stage.states[g_stage.cursor];
+  state_.init_x_px = t.init_x_px; state_.init_y_px = t.init_y_px;
+  state_.dx_m = t.dx_m; state_.dy_m = t.dy_m; state_.theta = t.theta; state_.scale = t.scale; state_.have_init = t.have_init != 0;
+  last_dist_ = g_stage.last_dist[g_stage.cursor++];
 }
 void StateParticle::computeWeight(std::vector<Eigen::ArrayXXf>&, std::vector<Eigen::ArrayXXf>&, float) {
-  const tdr_state& t = g_stage_states[g_cursor];
+  const tdr_state& t = g_stage.states[g_stage.cursor];
   state_.theta = t.theta;                                                     // the heading search's choice (:195-206)
   state_.have_init = t.have_init != 0;
-  weight_ = g_stage_weight[g_cursor++];
+  weight_ = g_stage.weight[g_stage.cursor++];
 }
 
 // ============================ ParticleFilter (particle_filter.cpp) ==========================================================
 namespace {
-// the device holds one particle set: the filter that used it last
-const void* g_owner = nullptr;
+// what the adapter knows about a filter beyond its declared members
+struct Side {
+  enum Where { IN_SYNC, HOST_AHEAD, DEVICE_AFTER_PROPAGATE, DEVICE_AFTER_UPDATE } where = HOST_AHEAD;
+  int64_t argmax = 0;                 // arg-max of the last normalisation (max_likelihood_particle_ = scored set [argmax])
+  bool have_params = false;
+  tdr_filter_params params{};         // what the device holds
+  size_t scored = 0;                  // size of the set the last update scored
+  // the four pose members of one scan (top_down_render.cpp:423-431 calls them back to back) share ONE device pass
+  bool have_pose = false;
+  float mean[4], cov_mean[16], ml[4], cov_ml[16];
+  bool have_seed = false;             // TDR_ADAPTER_DEVICE_RNG: Philox key (from the shared engine, once) and step counter
+  uint64_t rng_seed = 0, steps = 0;
+};
+// heap objects that are never destroyed: the detached GMM thread may still run while the process exits
+std::mutex& g_side_lock = *new std::mutex;
+std::map<const ParticleFilter*, Side>& g_side = *new std::map<const ParticleFilter*, Side>;
+// the device holds ONE particle set: the filter that used it last
+ParticleFilter* g_owner = nullptr;
+Side& side_of(const ParticleFilter* f) { std::lock_guard<std::mutex> g(g_side_lock); return g_side[f]; }
+bool device_rng() { static const bool on = [] { const char* e = getenv("TDR_ADAPTER_DEVICE_RNG"); return e && atoi(e) != 0; }(); return on; }
 
 std::vector<tdr_state> states_of(const std::vector<std::shared_ptr<StateParticle>>& v, std::vector<float>& last_dist) {
   std::vector<tdr_state> st(v.size());
@@ -127,14 +153,14 @@ ParticleFilter::ParticleFilter(int N, TopDownMapPolar* map, FilterParams& params
   if (map_->haveMap()) initializeParticles();
 }
 
-// the filter's parameters, the heading candidates (state_particle.cpp:197, :123-128) and the host set -> device
-static bool upload_filter(ParticleFilter* f, const FilterParams& p, TopDownMapPolar* map, const std::vector<std::shared_ptr<StateParticle>>& particles) {
-  if (!tdr() || particles.empty()) return false;
+// the filter's parameters and the heading candidates (state_particle.cpp:197, :123-128) -> device, when they changed
+static bool upload_params(Side& sd, const FilterParams& p, TopDownMapPolar* map) {
   tdr_filter_params fp;
   std::memset(&fp, 0, sizeof(fp));
   fp.regularization = p.regularization; fp.force_on_map = p.force_on_map ? 1 : 0; fp.fixed_scale = p.fixed_scale;
   fp.scale_log_min = p.scale_log_min; fp.scale_log_max = p.scale_log_max; fp.num_classes = map->numClasses();
   for (int c = 0; c < fp.num_classes && c < 16; c++) fp.class_weights[c] = c < (int)p.class_weights.size() ? p.class_weights[c] : 1.f;
+  if (sd.have_params && std::memcmp(&fp, &sd.params, sizeof(fp)) == 0) return true;      // the fp16 / u8 map copies stay valid
   if (!ok(tdr_pf_set_params(tdr(), &fp))) return false;
   std::vector<float> thetas;
   std::vector<int32_t> shifts;
@@ -147,15 +173,88 @@ static bool upload_filter(ParticleFilter* f, const FilterParams& p, TopDownMapPo
     shifts.push_back(shift);
   }
   if (!ok(tdr_pf_set_search(tdr(), thetas.data(), shifts.data(), (int)thetas.size()))) return false;
+  if (!ok(tdr_pf_keep_raw_weights(tdr(), 1))) return false;                  // StateParticle::weight() of a refreshed mirror
+  sd.params = fp; sd.have_params = true;
+  return true;
+}
+
+// device set -> host mirror of ONE filter (its private members, handed in by a member function), if the device is ahead.
+// After an update the reference's vectors read: particles_ = the resampled set, new_particles_ = the set that was scored
+// (raw weight, searched heading), weights_ = the normalised weights, max_likelihood_particle_ = scored set [arg-max].
+static bool pull_mirror(Side& sd, std::mt19937* gen, TopDownMapPolar* map, FilterParams* params,
+                        std::vector<std::shared_ptr<StateParticle>>& particles, std::vector<std::shared_ptr<StateParticle>>& new_particles,
+                        Eigen::VectorXf& weights, std::shared_ptr<StateParticle>& ml_particle) {
+  if (sd.where != Side::DEVICE_AFTER_PROPAGATE && sd.where != Side::DEVICE_AFTER_UPDATE) return true;
+  if (!tdr()) return false;
+  int64_t n = 0;
+  if (!ok(tdr_pf_count(tdr(), &n)) || n <= 0) return false;
+  Eigen::Vector2f no_trans(0, 0);
+  std::vector<Eigen::ArrayXXf> none;
+  Stage& sg = g_stage;
+  if (sd.where == Side::DEVICE_AFTER_UPDATE) {
+    // the scored set first: states as the search left them, last_dist, raw weights -> new_particles_
+    const int64_t m = (int64_t)sd.scored;
+    sg.states.resize((size_t)m); sg.last_dist.resize((size_t)m); sg.weight.resize((size_t)m);
+    if (!ok(tdr_pf_get_prev_states(tdr(), sg.states.data(), sg.last_dist.data(), m)) || !ok(tdr_pf_get_raw_weights(tdr(), sg.weight.data(), m))) return false;
+    if (new_particles.size() > (size_t)m) new_particles.resize((size_t)m);
+    while (new_particles.size() < (size_t)m) new_particles.push_back(std::make_shared<StateParticle>(gen, map, params, false));
+    sg.cursor = 0;
+    for (auto& p : new_particles) p->propagate(no_trans, 0.f, true);          // every State field + last_dist_
+    sg.cursor = 0;
+    for (auto& p : new_particles) p->computeWeight(none, none, 0.f);          // weight_ (and heading / have_init again)
+    weights = Eigen::VectorXf(m);
+    if (!ok(tdr_pf_get_weights(tdr(), weights.data(), m))) return false;
+    ml_particle = new_particles[(size_t)sd.argmax];
+  }
+  sg.states.resize((size_t)n); sg.last_dist.resize((size_t)n);
+  if (!ok(tdr_pf_get_states(tdr(), sg.states.data(), n)) || !ok(tdr_pf_get_last_dist(tdr(), sg.last_dist.data(), n))) return false;
+  if (particles.size() > (size_t)n) particles.resize((size_t)n);
+  while (particles.size() < (size_t)n) particles.push_back(std::make_shared<StateParticle>(gen, map, params, false));
+  sg.cursor = 0;
+  for (auto& p : particles) p->propagate(no_trans, 0.f, true);
+  sd.where = Side::IN_SYNC;
+  return true;
+}
+
+// host mirror -> device, when the mirror is ahead (initialisation, map shift, freezeScale, a harness edit) or the context
+// last served another filter
+static bool push_mirror(ParticleFilter* f, Side& sd, const FilterParams& p, TopDownMapPolar* map,
+                        const std::vector<std::shared_ptr<StateParticle>>& particles) {
+  if (!tdr() || particles.empty()) return false;
+  if (!upload_params(sd, p, map)) return false;
+  if (g_owner == f && sd.where != Side::HOST_AHEAD) return true;
   std::vector<float> last_dist;
   std::vector<tdr_state> st = states_of(particles, last_dist);
   if (!ok(tdr_pf_set_states(tdr(), st.data(), last_dist.data(), (int64_t)st.size()))) return false;
   g_owner = f;
+  sd.where = Side::IN_SYNC; sd.have_pose = false;
   return true;
+}
+
+// Before a filter touches the device: if the context last served ANOTHER filter whose mirror is behind the device, that
+// filter's mirror is refreshed first.  A macro because only code inside a ParticleFilter member may reach another
+// ParticleFilter's private members, and the class declaration is not ours to extend.
+#define take_device()                                                                                                   \
+  do {                                                                                                                  \
+    if (g_owner && g_owner != this) {                                                                                   \
+      ParticleFilter* o_ = g_owner;                                                                                     \
+      Side& so_ = side_of(o_);                                                                                          \
+      pull_mirror(so_, o_->gen_, o_->map_, &o_->params_, o_->particles_, o_->new_particles_, o_->weights_, o_->max_likelihood_particle_); \
+      so_.where = Side::HOST_AHEAD;                                                                                     \
+      g_owner = nullptr;                                                                                                \
+    }                                                                                                                   \
+  } while (0)
+
+// for code that edits a filter's particles_ behind the class's back (the test harness does, through its private-access
+// build): the next propagate / update uploads the mirror again
+extern "C" void tdr_adapter_mark_host_ahead(const void* filter) {
+  Side& sd = side_of(static_cast<const ParticleFilter*>(filter));
+  sd.where = Side::HOST_AHEAD; sd.have_pose = false;
 }
 
 // :19-84 — the same three constructions per particle from the shared engine; then the set goes to the device
 void ParticleFilter::initializeParticles() {
+  tdr_adapter::Guard dev_guard;
   size_t num_at_scale = 1;
   if (params_.fixed_scale < 0) num_at_scale = 10; else scale_frozen_ = true;
   if (scale_frozen_ && params_.init_pos_m_x != std::numeric_limits<float>::infinity()) {
@@ -187,52 +286,49 @@ void ParticleFilter::initializeParticles() {
   max_likelihood_particle_ = particles_[0];
   num_particles_ = particles_.size();
   weights_ = Eigen::Matrix<float, 1, Eigen::Dynamic>::Ones(num_particles_) / num_particles_;
-  upload_filter(this, params_, map_, particles_);
+  { Side& sd = side_of(this); sd.where = Side::HOST_AHEAD; take_device(); push_mirror(this, sd, params_, map_, particles_); }
   computeGMM();
   gmm_thread_ = new std::thread(std::bind(&ParticleFilter::gmmThread, this));
 }
 
-// the device set is this filter's, with the host mirror's current values (another filter may have used the context since)
-static bool ensure_on_device(ParticleFilter* f, const FilterParams& p, TopDownMapPolar* map, const std::vector<std::shared_ptr<StateParticle>>& particles) {
-  return g_owner == f || upload_filter(f, p, map, particles);
-}
-// the device set after a bulk call -> the staging area the per-particle members read from
-static bool stage_device_set(size_t expect, const float* raw_weights) {
-  int64_t n = 0;
-  if (!ok(tdr_pf_count(tdr(), &n)) || n != (int64_t)expect) return false;
-  g_stage_states.resize((size_t)n); g_stage_last_dist.resize((size_t)n);
-  if (!ok(tdr_pf_get_states(tdr(), g_stage_states.data(), n)) || !ok(tdr_pf_get_last_dist(tdr(), g_stage_last_dist.data(), n))) return false;
-  if (raw_weights) g_stage_weight.assign(raw_weights, raw_weights + n);
-  g_cursor = 0;
-  return true;
-}
-
-// :86-92 with StateParticle::propagate (:57-78): the reference's RNG calls in particle order, as STANDARD variates (the
-// uniforms consumed do not depend on the standard deviation); the device applies `z * stddev + mean` and the motion
+// :86-92 with StateParticle::propagate (:57-78).  The reference's RNG calls in particle order, as STANDARD variates (the
+// uniforms consumed do not depend on the standard deviation): the device applies `z * stddev + mean` and the motion, and
+// the shared engine ends where the reference's would.  TDR_ADAPTER_DEVICE_RNG=1 draws on the device instead (no host
+// loop over the particles at all; the engine is then not advanced by propagate).  No state comes back.
 void ParticleFilter::propagate(Eigen::Vector2f& trans, float omega) {
+  tdr_adapter::Guard dev_guard;
   std::lock_guard<std::mutex> guard(particle_lock_);
   if (particles_.empty()) return;
-  // host values first: ParticleFilter::updateMap / freezeScale / a harness may have edited the mirror
-  upload_filter(this, params_, map_, particles_);
-  std::vector<float> z(4 * particles_.size(), 0.f);
-  for (size_t i = 0; i < particles_.size(); i++) {
-    std::normal_distribution<float> disp_dist{0, 1}, theta_dist{0, 1};
-    z[4 * i] = theta_dist(*gen_);
-    z[4 * i + 1] = disp_dist(*gen_);
-    z[4 * i + 2] = disp_dist(*gen_);
-    if (!scale_frozen_) { std::normal_distribution<float> scale_dist{0, 1}; z[4 * i + 3] = scale_dist(*gen_); }
+  Side& sd = side_of(this);
+  take_device();
+  if (!push_mirror(this, sd, params_, map_, particles_)) return;
+  const size_t n = particles_.size();
+  if (device_rng()) {
+    if (!sd.have_seed) { sd.rng_seed = ((uint64_t)(*gen_)() << 32) | (uint64_t)(*gen_)(); sd.have_seed = true; }   // two engine outputs, once
+    if (!ok(tdr_pf_propagate_rng(tdr(), trans[0], trans[1], omega, scale_frozen_ ? 1 : 0, params_.pos_cov, params_.theta_cov,
+                                 sd.rng_seed, ++sd.steps, nullptr))) return;
+  } else {
+    std::vector<float> z(4 * n, 0.f);
+    for (size_t i = 0; i < n; i++) {
+      std::normal_distribution<float> disp_dist{0, 1}, theta_dist{0, 1};
+      z[4 * i] = theta_dist(*gen_);
+      z[4 * i + 1] = disp_dist(*gen_);
+      z[4 * i + 2] = disp_dist(*gen_);
+      if (!scale_frozen_) { std::normal_distribution<float> scale_dist{0, 1}; z[4 * i + 3] = scale_dist(*gen_); }
+    }
+    if (!ok(tdr_pf_propagate(tdr(), trans[0], trans[1], omega, scale_frozen_ ? 1 : 0, params_.pos_cov, params_.theta_cov, z.data(), (int64_t)n))) return;
   }
-  if (!ok(tdr_pf_propagate(tdr(), trans[0], trans[1], omega, scale_frozen_ ? 1 : 0, params_.pos_cov, params_.theta_cov, z.data(),
-                           (int64_t)particles_.size()))) return;
-  if (!stage_device_set(particles_.size(), nullptr)) return;
-  for (auto& p : particles_) p->propagate(trans, omega, scale_frozen_);      // the reference's loop; each particle takes its result
+  sd.where = Side::DEVICE_AFTER_PROPAGATE; sd.have_pose = false;
 }
 
-// :94-189
+// :94-189 on the resident set: score, normalise, the adaptive particle count, ONE uniform from the shared engine, resample
 void ParticleFilter::update(std::vector<Eigen::ArrayXXf>& top_down_scan, std::vector<Eigen::ArrayXXf>& /*top_down_geo*/, float res) {
+  tdr_adapter::Guard dev_guard;
   if (num_particles_ == 0) return;
   std::lock_guard<std::mutex> guard(particle_lock_);
-  if (!upload_filter(this, params_, map_, particles_)) return;
+  Side& sd = side_of(this);
+  take_device();
+  if (!push_mirror(this, sd, params_, map_, particles_)) return;
   // the map (and its polar table) must be the one this filter scores against
   std::vector<Eigen::ArrayXXf> probe(map_->numClasses(), Eigen::ArrayXXf(top_down_scan[0].rows(), top_down_scan[0].cols()));
   Eigen::ArrayXXc probe_mask(top_down_scan[0].rows(), top_down_scan[0].cols());
@@ -240,17 +336,11 @@ void ParticleFilter::update(std::vector<Eigen::ArrayXXf>& top_down_scan, std::ve
   std::vector<float> scan;
   for (const auto& img : top_down_scan) scan.insert(scan.end(), img.data(), img.data() + img.size());
   if (!ok(tdr_scan_set_polar_images(tdr(), scan.data(), (int)top_down_scan[0].rows(), (int)top_down_scan[0].cols(), (int)top_down_scan.size()))) return;
-  const size_t n = particles_.size();
-  std::vector<float> raw(n);
-  if (!ok(tdr_pf_score(tdr(), res, raw.data()))) return;                     // a9, a10 for the whole set
-  if (!stage_device_set(n, raw.data())) return;
-  std::vector<Eigen::ArrayXXf> no_geo;
-  for (auto& p : particles_) p->computeWeight(top_down_scan, no_geo, res);   // the reference's loop (:104-105); each takes its weight
+  int64_t n = 0;
+  if (!ok(tdr_pf_count(tdr(), &n))) return;
+  if (!ok(tdr_pf_score(tdr(), res, nullptr))) return;                        // a9, a10 for the whole set; the weights stay on the device
   int64_t arg = 0;
   if (!ok(tdr_pf_normalize(tdr(), &arg, nullptr))) return;                   // a11
-  weights_ = Eigen::VectorXf(n);
-  if (!ok(tdr_pf_get_weights(tdr(), weights_.data(), (int64_t)n))) return;
-  max_likelihood_particle_ = particles_[arg];
   int last_num_particles = num_particles_;                                   // :151-158
   num_particles_ = 0;
   for (const auto& cov : covs_) {
@@ -258,39 +348,76 @@ void ParticleFilter::update(std::vector<Eigen::ArrayXXf>& top_down_scan, std::ve
     num_particles_ += static_cast<int>(sqrt(eig[0].real()) * sqrt(eig[1].real()));
   }
   num_particles_ = std::min(std::max(num_particles_, 3 * last_num_particles / 4 + 10), max_num_particles_);
-  if ((size_t)num_particles_ < new_particles_.size()) new_particles_.resize(num_particles_);
-  while (new_particles_.size() < (size_t)num_particles_) new_particles_.push_back(std::make_shared<StateParticle>(gen_, map_, &params_, false));
   std::uniform_real_distribution<float> shift_dist(0., 1.);
   float shift = shift_dist(*gen_);                                           // the ONE draw of :172-173
-  std::vector<int32_t> idx((size_t)num_particles_);
-  if (!ok(tdr_pf_resample(tdr(), shift, num_particles_, idx.data()))) return;   // a12: indices from the device
-  for (int i = 0; i < num_particles_; i++) new_particles_[i]->setState(particles_[idx[i]]->state());   // :185, the mirror follows
-  particles_.swap(new_particles_);
+  if (!ok(tdr_pf_resample(tdr(), shift, num_particles_, nullptr))) return;   // a12 + the state gather (:185) on the device
+  sd.argmax = arg; sd.scored = (size_t)n;
+  sd.where = Side::DEVICE_AFTER_UPDATE; sd.have_pose = false;
 }
 
-// :191-236 — the sums run on the device; the ML particle is a host object, as in the reference
+// :191-236 — the sums run on the device, the max-likelihood state too (the arg-max of the last normalisation); the four
+// members of one scan share one device pass (Side::have_pose)
+static bool device_pose(Side& sd, bool with_ml) {
+  if (sd.have_pose) return true;
+  if (!ok(tdr_pf_pose(tdr(), sd.mean, sd.cov_mean, with_ml ? sd.ml : nullptr, with_ml ? sd.cov_ml : nullptr))) return false;
+  sd.have_pose = with_ml;
+  return true;
+}
 void ParticleFilter::meanLikelihood(Eigen::Vector4f& mean_state) {
+  tdr_adapter::Guard dev_guard;
   mean_state = Eigen::Vector4f::Zero();
-  if (particles_.empty() || !ensure_on_device(this, params_, map_, particles_)) return;
-  ok(tdr_pf_pose(tdr(), mean_state.data(), nullptr, nullptr, nullptr));
+  std::lock_guard<std::mutex> guard(particle_lock_);
+  Side& sd = side_of(this);
+  take_device();
+  if (particles_.empty() || !push_mirror(this, sd, params_, map_, particles_)) return;
+  if (device_pose(sd, sd.where == Side::DEVICE_AFTER_UPDATE)) std::memcpy(mean_state.data(), sd.mean, sizeof(sd.mean));
 }
 void ParticleFilter::computeMeanCov(Eigen::Matrix4f& cov) {
+  tdr_adapter::Guard dev_guard;
   cov.setZero();
-  if (num_particles_ < 1 || !ensure_on_device(this, params_, map_, particles_)) return;
-  float mean[4];
-  ok(tdr_pf_pose(tdr(), mean, cov.data(), nullptr, nullptr));
+  std::lock_guard<std::mutex> guard(particle_lock_);
+  Side& sd = side_of(this);
+  take_device();
+  if (num_particles_ < 1 || !push_mirror(this, sd, params_, map_, particles_)) return;
+  if (device_pose(sd, sd.where == Side::DEVICE_AFTER_UPDATE)) std::memcpy(cov.data(), sd.cov_mean, sizeof(sd.cov_mean));
 }
-void ParticleFilter::maxLikelihood(Eigen::Vector4f& state) { state = max_likelihood_particle_->mlState(); }
+void ParticleFilter::maxLikelihood(Eigen::Vector4f& state) {
+  tdr_adapter::Guard dev_guard;
+  std::lock_guard<std::mutex> guard(particle_lock_);
+  Side& sd = side_of(this);
+  if (sd.where == Side::DEVICE_AFTER_UPDATE && g_owner == this) { if (device_pose(sd, true)) std::memcpy(state.data(), sd.ml, sizeof(sd.ml)); return; }
+  state = max_likelihood_particle_->mlState();
+}
 void ParticleFilter::computeCov(Eigen::Matrix4f& cov) {
+  tdr_adapter::Guard dev_guard;
   cov.setZero();
+  std::lock_guard<std::mutex> guard(particle_lock_);
+  Side& sd = side_of(this);
+  if (sd.where == Side::DEVICE_AFTER_UPDATE && g_owner == this) { if (device_pose(sd, true)) std::memcpy(cov.data(), sd.cov_ml, sizeof(sd.cov_ml)); return; }
   Eigen::Vector4f ml = max_likelihood_particle_->mlState();
-  for (const auto& particle : particles_) {                                  // N x 16 flops on the host mirror; off the hot path
+  for (const auto& particle : particles_) {                                  // the mirror is current: the reference's loop
     Eigen::Vector4f state = particle->mlState() - ml;
     while (state[2] > M_PI) state[2] -= 2 * M_PI;
     while (state[2] < -M_PI) state[2] += 2 * M_PI;
     cov += state * state.transpose();
   }
   cov /= particles_.size() - 1;
+}
+
+// :367-421 — the drawing walks every particle of the host mirror: this is where a node that visualises pays the 28 B per
+// particle; a harness calls it (with any image) to read a current mirror.  The drawing itself needs OpenCV's imgproc.
+void ParticleFilter::visualize(cv::Mat& img) {
+  tdr_adapter::Guard dev_guard;
+  {
+    std::lock_guard<std::mutex> guard(particle_lock_);
+    Side& sd = side_of(this);
+    if (g_owner == this) pull_mirror(sd, gen_, map_, &params_, particles_, new_particles_, weights_, max_likelihood_particle_);
+  }
+#ifdef TDR_ADAPTER_DRAW
+  tdr_adapter_draw(img, particles_, means_, covs_, gmm_lock_, max_likelihood_particle_);   // the reference's drawing code, unchanged
+#else
+  (void)img;
+#endif
 }
 
 void ParticleFilter::getGMM(std::vector<Eigen::Vector3f>& means, std::vector<Eigen::Matrix3f>& covs) {
@@ -309,7 +436,10 @@ void ParticleFilter::gmmThread() {
 void ParticleFilter::computeGMM() {
   cv::Mat samples;
   {
+    tdr_adapter::Guard dev_guard;
     std::lock_guard<std::mutex> guard(particle_lock_);
+    // once a second the GMM thread reads a strided sample of the set: the mirror is refreshed here if the device is ahead
+    if (g_owner == this) pull_mirror(side_of(this), gen_, map_, &params_, particles_, new_particles_, weights_, max_likelihood_particle_);
     const size_t n = particles_.size();
     num_gaussians_ = std::min(static_cast<int>(n / 20) + 1, num_gaussians_);
     const int num_samples = std::min(1000, static_cast<int>(n));
@@ -353,7 +483,10 @@ void ParticleFilter::updateMap(const cv::Mat& map, const Eigen::Vector2i& map_ce
   map_->updateMap(map, map_center);
   Eigen::Vector2i delta = map_center - last_map_center_;
   {
+    tdr_adapter::Guard dev_guard;
     std::lock_guard<std::mutex> guard(particle_lock_);
+    Side& sd = side_of(this);
+    if (g_owner == this) pull_mirror(sd, gen_, map_, &params_, particles_, new_particles_, weights_, max_likelihood_particle_);
     for (auto& particle : particles_) {
       State s = particle->state();
       s.init_x_px += delta[0];
@@ -361,7 +494,7 @@ void ParticleFilter::updateMap(const cv::Mat& map, const Eigen::Vector2i& map_ce
       particle->setState(s);
       particle->updateSize();
     }
-    g_owner = nullptr;                                                       // the mirror is ahead of the device
+    sd.where = Side::HOST_AHEAD; sd.have_pose = false;                       // the mirror is ahead of the device
   }
   last_map_center_ = map_center;
   if (num_particles_ == 0) initializeParticles();
@@ -369,16 +502,20 @@ void ParticleFilter::updateMap(const cv::Mat& map, const Eigen::Vector2i& map_ce
 // :343-357
 void ParticleFilter::freezeScale() {
   if (scale_frozen_) return;
+  tdr_adapter::Guard dev_guard;
+  std::lock_guard<std::mutex> guard(particle_lock_);
+  Side& sd = side_of(this);
+  if (g_owner == this) pull_mirror(sd, gen_, map_, &params_, particles_, new_particles_, weights_, max_likelihood_particle_);
   float geo_mean = 1;
   for (const auto& p : particles_) geo_mean *= std::pow(p->state().scale, 1. / particles_.size());
   for (auto& p : particles_) p->setScale(geo_mean);
   scale_frozen_ = true;
-  g_owner = nullptr;
+  sd.where = Side::HOST_AHEAD; sd.have_pose = false;
 }
 // :358-366
 float ParticleFilter::scale() const {
   if (params_.fixed_scale > 0) return params_.fixed_scale;
-  if (scale_frozen_) return particles_[0]->state().scale;
+  if (scale_frozen_) return particles_[0]->state().scale;                    // frozen: every particle holds it, the device changes it no more
   return -1;
 }
 int ParticleFilter::numParticles() const { return num_particles_; }

@@ -47,6 +47,7 @@ ScanRenderer::ScanRenderer(const Eigen::VectorXi& flatten_lut) { flatten_lut_ = 
 // replaces scan_renderer.cpp:55-78
 void ScanRenderer::renderSemanticTopDown(const pcl::PointCloud<pcl::PointXYZI>::ConstPtr& cloud, float res,
                                          std::vector<Eigen::ArrayXXf>& imgs) {
+  tdr_adapter::Guard dev_guard;
   if (imgs.size() < 1) return;                                                           // :57
   const int rows = (int)imgs[0].rows(), cols = (int)imgs[0].cols();
   if (!upload(flatten_lut_, cloud, (int)imgs.size())) return;
@@ -60,6 +61,7 @@ ScanRendererPolar::ScanRendererPolar(const Eigen::VectorXi& flatten_lut) : ScanR
 // replaces scan_renderer_polar.cpp:83-109; the class images also stay resident on the device for ParticleFilter::update
 void ScanRendererPolar::renderSemanticTopDown(const pcl::PointCloud<pcl::PointXYZI>::ConstPtr& cloud, float res, float ang_res,
                                               std::vector<Eigen::ArrayXXf>& imgs) {
+  tdr_adapter::Guard dev_guard;
   if (imgs.size() < 1) return;                                                           // :85
   const int n_theta = (int)imgs[0].rows(), n_r = (int)imgs[0].cols();
   if (!upload(flatten_lut_, cloud, (int)imgs.size())) return;
@@ -71,6 +73,7 @@ void ScanRendererPolar::renderSemanticTopDown(const pcl::PointCloud<pcl::PointXY
 // replaces scan_renderer.cpp:7-53
 void ScanRenderer::renderGeometricTopDown(const pcl::PointCloud<pcl::PointXYZI>::ConstPtr& cloud, float res,
                                           std::vector<Eigen::ArrayXXf>& imgs) {
+  tdr_adapter::Guard dev_guard;
   if (imgs.size() < 2) return;                                                           // :9
   const int rows = (int)imgs[0].rows(), cols = (int)imgs[0].cols();
   if (!upload_points(cloud)) return;
@@ -85,6 +88,7 @@ void ScanRenderer::renderGeometricTopDown(const pcl::PointCloud<pcl::PointXYZI>:
 // replaces scan_renderer_polar.cpp:6-81
 void ScanRendererPolar::renderGeometricTopDown(const pcl::PointCloud<pcl::PointXYZI>::ConstPtr& cloud, float res, float ang_res,
                                                std::vector<Eigen::ArrayXXf>& imgs) {
+  tdr_adapter::Guard dev_guard;
   if (imgs.size() < 2) return;                                                           // :8
   const int n_theta = (int)imgs[0].rows(), n_r = (int)imgs[0].cols();
   if (!upload_points(cloud)) return;

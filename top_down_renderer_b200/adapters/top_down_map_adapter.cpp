@@ -107,6 +107,7 @@ Eigen::Vector2i TopDownMap::loadSvg(const std::string& svg_path, std::vector<std
 
 // replaces :391-408 together with samplePts (:367-389) and getClasses (:328-365): tdr_map_set_polygons
 void TopDownMap::getRasterMap(const Eigen::Vector2i& map_size, float rot, float res, std::vector<std::vector<std::vector<Eigen::Vector2f>>>& poly) {
+  tdr_adapter::Guard dev_guard;
   if (poly.size() < 1 || !tdr()) return;
   std::vector<float> verts;
   std::vector<int32_t> start(1, 0), cls;
@@ -129,6 +130,7 @@ void TopDownMap::getRasterMap(const Eigen::Vector2i& map_size, float rot, float 
 // distance fields exactly as the reference leaves them.  class_maps_ -> upload the seeds; geo_maps_ -> the device derives
 // the pair from the class seeds it already holds.
 void TopDownMap::computeDists(std::vector<Eigen::ArrayXXf>& classes, Eigen::ArrayXXc& mask) {
+  tdr_adapter::Guard dev_guard;
   if (!tdr() || class_maps_.empty()) return;
   const int rows = (int)class_maps_[0].rows(), cols = (int)class_maps_[0].cols();
   if (&classes == &class_maps_) {
@@ -193,6 +195,7 @@ void TopDownMap::saveRasterizedMaps(const std::string& path) {
 }
 // replaces :213-224
 void TopDownMap::loadRasterizedMaps(const std::string& map_path) {
+  tdr_adapter::Guard dev_guard;
   for (size_t i = 0; i < (size_t)params_.num_classes; i++) {
     cv::Mat img = cv::imread(map_path + "/class" + std::to_string(i) + ".png", cv::IMREAD_GRAYSCALE);
     if (img.empty()) { class_maps_.clear(); return; }
@@ -216,6 +219,7 @@ bool TopDownMap::loadCacheMetaData(const std::string& map_path) {
 }
 // replaces :244-261: the reference's own read_binary template (top_down_map.h:40-50), then the fields go to the device as they are
 void TopDownMap::loadCachedMaps() {
+  tdr_adapter::Guard dev_guard;
   for (int cls = 0; cls < params_.num_classes; cls++) {
     Eigen::ArrayXXf m;
     std::string name = cache_dir() + "class_map" + std::to_string(cls) + ".eig";
@@ -291,6 +295,7 @@ void scatter(const std::vector<float>& stage, std::vector<Eigen::ArrayXXf>& dist
 
 // replaces :429-459 (a8)
 void TopDownMap::getLocalMap(Eigen::Vector2f center, float rot, float res, std::vector<Eigen::ArrayXXf>& dists, Eigen::ArrayXXc& mask) {
+  tdr_adapter::Guard dev_guard;
   if (dists.size() < 1 || !make_resident(this, class_maps_, class_mask_, geo_maps_, params_.num_classes, params_.resolution)) return;
   const int rows = (int)dists[0].rows(), cols = (int)dists[0].cols();
   std::vector<float> stage((size_t)params_.num_classes * rows * cols);
@@ -303,6 +308,7 @@ TopDownMapPolar::TopDownMapPolar(const Params& params) : TopDownMap(params) { sa
 
 // :7-19 (with samplePts at rot = 0): offset p = (row p % n_theta, column p / n_theta) -> (cos, sin)(angle) * radius
 void TopDownMapPolar::samplePtsPolar(Eigen::Vector2i shape, float ang_res) {
+  tdr_adapter::Guard dev_guard;
   const int n_theta = shape[0], n_r = shape[1];
   ang_sample_pts_ = Eigen::Array2Xf(2, n_theta * n_r);
   for (int p = 0; p < n_theta * n_r; p++) {
@@ -329,6 +335,7 @@ bool table_resident(const Eigen::Array2Xf& tab, int n_theta, int n_r) {
 
 // replaces :21-53 (a7)
 void TopDownMapPolar::getLocalMap(Eigen::Vector2f center, float scale, float res, std::vector<Eigen::ArrayXXf>& dists, Eigen::ArrayXXc& mask) {
+  tdr_adapter::Guard dev_guard;
   if (dists.size() < 1 || !make_resident(this, class_maps_, class_mask_, geo_maps_, params_.num_classes, params_.resolution)) return;
   if (!table_resident(ang_sample_pts_, (int)dists[0].rows(), (int)dists[0].cols())) return;
   const float c[2] = {center[0], center[1]};
@@ -338,6 +345,7 @@ void TopDownMapPolar::getLocalMap(Eigen::Vector2f center, float scale, float res
 }
 // replaces :55-76
 void TopDownMapPolar::getLocalGeoMap(Eigen::Vector2f center, float scale, float res, std::vector<Eigen::ArrayXXf>& dists) {
+  tdr_adapter::Guard dev_guard;
   if (dists.size() < 1 || !make_resident(this, class_maps_, class_mask_, geo_maps_, params_.num_classes, params_.resolution)) return;
   if (!table_resident(ang_sample_pts_, (int)dists[0].rows(), (int)dists[0].cols())) return;
   const float c[2] = {center[0], center[1]};
@@ -346,8 +354,10 @@ void TopDownMapPolar::getLocalGeoMap(Eigen::Vector2f center, float scale, float 
   scatter(stage, dists, 2);
 }
 void TopDownMapPolar::getLocalMap(Eigen::Vector2f center, float res, std::vector<Eigen::ArrayXXf>& dists, Eigen::ArrayXXc& mask) {
+  tdr_adapter::Guard dev_guard;
   getLocalMap(center, 1, res, dists, mask);                                  // :78-82
 }
 void TopDownMapPolar::getLocalGeoMap(Eigen::Vector2f center, float res, std::vector<Eigen::ArrayXXf>& dists) {
+  tdr_adapter::Guard dev_guard;
   getLocalGeoMap(center, 1, res, dists);                                     // :84-87
 }

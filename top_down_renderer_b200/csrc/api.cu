@@ -196,6 +196,7 @@ void tdr_destroy(tdr_ctx* c) {
   c->part[0].release(); c->part[1].release(); c->ckpt.release(); c->all.release();
   c->pin.release();
   c->uninit_dev.release();
+  c->raw_weights.release();
   if (c->uninit_ev) cudaEventDestroy(c->uninit_ev);
   if (c->uninit_pin) cudaFreeHost(c->uninit_pin);
   if (c->map8_tex) cudaDestroyTextureObject((cudaTextureObject_t)c->map8_tex);
@@ -607,6 +608,39 @@ int tdr_pf_get_last_dist(tdr_ctx* ctx, float* last_dist, int64_t n) {
   return TDR_OK;
 }
 
+// the set the last resampling READ from (particles that were scored): the other half of the ping-pong pair.  What a
+// lazily refreshed host mirror shows as new_particles_ after ParticleFilter::update's swap (particle_filter.cpp:187).
+int tdr_pf_get_prev_states(tdr_ctx* ctx, tdr_state* states, float* last_dist, int64_t n) {
+  CTX_CHECK(ctx);
+  Particles& pt = ctx->part[ctx->cur ^ 1];
+  TDR_REQUIRE(states && n > 0 && n <= pt.n, TDR_EINVAL, "bad state count %lld (the previous set holds %lld)", (long long)n, (long long)pt.n);
+  if (int e = ctx->scratch.reserve((size_t)n * 28)) return e;
+  k_soa_to_aos<<<grid_for(ctx, n), 256, 0, ctx->stream>>>(soa_of(pt), n, ctx->scratch.as<uint32_t>());
+  count_launch(ctx);
+  TDR_CUDA(cudaGetLastError());
+  TDR_CUDA(cudaMemcpyAsync(states, ctx->scratch.p, (size_t)n * 28, cudaMemcpyDeviceToHost, ctx->stream));
+  if (last_dist) TDR_CUDA(cudaMemcpyAsync(last_dist, pt.last_dist.p, (size_t)n * 4, cudaMemcpyDeviceToHost, ctx->stream));
+  TDR_CUDA(cudaStreamSynchronize(ctx->stream));
+  return TDR_OK;
+}
+// raw weights (StateParticle::weight(), before particle_filter.cpp:107-147 rewrites the vector) survive the normalisation
+// in a device-side copy when asked for: 4 B / particle device-to-device per update instead of a D2H inside it
+int tdr_pf_keep_raw_weights(tdr_ctx* ctx, int on) { CTX_CHECK(ctx); ctx->keep_raw = on != 0; return TDR_OK; }
+int tdr_pf_get_raw_weights(tdr_ctx* ctx, float* weights, int64_t n) {
+  CTX_CHECK(ctx);
+  TDR_REQUIRE(weights && n > 0 && n <= ctx->n_raw, TDR_EINVAL, "bad raw weight count %lld (kept: %lld)", (long long)n, (long long)ctx->n_raw);
+  TDR_CUDA(cudaMemcpyAsync(weights, ctx->raw_weights.p, (size_t)n * 4, cudaMemcpyDeviceToHost, ctx->stream));
+  TDR_CUDA(cudaStreamSynchronize(ctx->stream));
+  return TDR_OK;
+}
+static int snapshot_raw(tdr_ctx* ctx) {
+  if (!ctx->keep_raw) return TDR_OK;
+  if (int e = ctx->raw_weights.reserve((size_t)ctx->n_weights * 4)) return e;
+  TDR_CUDA(cudaMemcpyAsync(ctx->raw_weights.p, ctx->weights.p, (size_t)ctx->n_weights * 4, cudaMemcpyDeviceToDevice, ctx->stream));
+  ctx->n_raw = ctx->n_weights;
+  return TDR_OK;
+}
+
 static int copy_particles(tdr_ctx* ctx, Particles& dst, Particles& src) {
   if (int e = dst.reserve(src.n)) return e;
   DevBuf* d[] = {&dst.init_x, &dst.init_y, &dst.dx, &dst.dy, &dst.theta, &dst.scale, &dst.last_dist};
@@ -650,6 +684,7 @@ int tdr_pf_score(tdr_ctx* ctx, float res, float* weights_out) {
   stage_mark(ctx, TDR_STAGE_SCORE);
   if (int e = score_particles(ctx, res)) return e;
   ctx->ld_override = nullptr;
+  if (int e = snapshot_raw(ctx)) return e;
   if (weights_out) return copy_out_floats(ctx, weights_out, ctx->weights.p, ctx->n_weights);
   return TDR_OK;
 }
@@ -755,6 +790,7 @@ static int update_resident(tdr_ctx* ctx, float res, float u, int64_t M) {
   stage_mark(ctx, TDR_STAGE_SCORE);
   if (int e = score_particles(ctx, res)) return e;
   ctx->ld_override = nullptr;
+  if (int e = snapshot_raw(ctx)) return e;
   stage_mark(ctx, TDR_STAGE_NORMALIZE);
   if (int e = normalize_resample(ctx, u, M)) return e;
   stage_mark(ctx, TDR_N_STAGES);

@@ -243,6 +243,7 @@ struct BinParams {
   const float *init_x, *init_y, *dx, *dy, *scale; const uint8_t* have_init;   // particle mode
   const float* centers;                                                       // grid mode
   long long n; float resolution; int rows, cols, st_shift, seg_shift, super_x, per_super, n_bins, morton;
+  int select_init;          // particle mode: bin the particles WITH a heading (tracking) instead of those without (search)
 };
 __device__ __forceinline__ uint32_t spread_bits16(uint32_t v) {      // abcd -> 0a0b0c0d
   v &= 0xffffu;
@@ -253,7 +254,7 @@ __device__ __forceinline__ int bin_of(const BinParams& b, long long i) {
   float x, y;
   if (b.centers) { x = b.centers[2 * i]; y = b.centers[2 * i + 1]; }
   else {
-    if (b.have_init[i]) return -1;                // tracked by k_score_track
+    if ((b.have_init[i] != 0) != (b.select_init != 0)) return -1;     // the other kind of particle: another launch
     float s = b.scale[i];
     x = TDR_FADD(TDR_FMUL(b.dx[i], s), b.init_x[i]); y = TDR_FADD(TDR_FMUL(b.dy[i], s), b.init_y[i]);
   }
@@ -400,7 +401,7 @@ static int sync_const_tab(tdr_ctx* ctx, int P) {
 }
 
 // spatial binning of the hypotheses -> ctx->perm (counting sort by super-tile, pixel row, column segment)
-static int build_perm(tdr_ctx* ctx, bool grid_mode, long long n_items, bool morton = false) {
+static int build_perm(tdr_ctx* ctx, bool grid_mode, long long n_items, bool morton = false, bool select_init = false) {
   if (grid_mode && ctx->perm_grid_n == n_items) return TDR_OK;       // resident centres, same map: the order still holds
   ctx->perm_grid_n = -1;
   tdr::Particles& pt = ctx->part[ctx->cur];
@@ -419,6 +420,7 @@ static int build_perm(tdr_ctx* ctx, bool grid_mode, long long n_items, bool mort
   bp.super_x = (ctx->cols >> bp.st_shift) + 1;
   bp.seg_shift = ctx->mma_seg_shift;
   bp.morton = morton ? 1 : 0;
+  bp.select_init = select_init ? 1 : 0;
   if (morton) bp.seg_shift = 2;                   // (S/2)^2 Morton cells = S * (S >> 2) bins: the same count
   if (morton && bp.st_shift > 16) bp.st_shift = 16;
   bp.per_super = (1 << bp.st_shift) * ((1 << bp.st_shift) >> bp.seg_shift);

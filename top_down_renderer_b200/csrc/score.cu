@@ -69,6 +69,7 @@ __device__ __forceinline__ void ldg256f(const void* p, float4& a, float4& b) {
 
 __global__ void __launch_bounds__(512, 2) k_score_track(ScoreParams sp) {
   extern __shared__ __align__(16) unsigned char smem[];
+  if (sp.only_if_bailed && *sp.only_if_bailed == 0) return;      // launched behind the tensor-core kernel, which did the work
   float* s_scan = reinterpret_cast<float*>(smem);
   float2* s_tab = reinterpret_cast<float2*>(s_scan + (size_t)sp.P * 8);
   ushort2* s_cell = reinterpret_cast<ushort2*>(s_tab + sp.P);
@@ -407,10 +408,21 @@ int score_particles(tdr_ctx* ctx, float res) {
   // which sets theta / have_init (state_particle.cpp:195-206).  Track first: it only READS have_init.
   const size_t track_smem = (size_t)P * 32 + (size_t)P * 8 + (size_t)P * 4;
   if (ctx->n_uninit < pt.n) {
+    // LARGE tracked sets go through the tensor-core ring kernel as well: it computes all n_theta shifts per particle in
+    // spatially sorted tiles and each particle keeps the column of its own heading — 62.7 ms -> ~9 ms for 1e6 tracked
+    // particles (k_score_track walks the particles in resampling order, one warp each, and is DRAM-latency-bound there:
+    // profiles/r02_tracking_1m.txt).  Small sets (cfg2: 1e4) stay on k_score_track.
+    bool tracked_by_mma = false;
+    const long long n_init = pt.n - ctx->n_uninit;
+    if (sp.n_shifts > 0 && (ctx->score_impl == 2 || (ctx->score_impl == 0 && n_init >= 65536))) {
+      if (int e = score_mma(ctx, res, false, pt.n, 1.f, sp.shifts, ctx->search_shifts.data(), sp.n_shifts, &tracked_by_mma, true)) return e;
+    }
+    ScoreParams st = sp;
+    if (tracked_by_mma) st.only_if_bailed = reinterpret_cast<const int*>(ctx->scal.as<float>() + SC_MMA_BAILED);   // guarded fallback
     const long long warps = pt.n;
     long long ctas = (warps + 15) / 16;
     if (ctas > (long long)ctx->sm_count * 2) ctas = (long long)ctx->sm_count * 2;
-    k_score_track<<<(unsigned)ctas, 512, track_smem, ctx->stream>>>(sp);
+    k_score_track<<<(unsigned)ctas, 512, track_smem, ctx->stream>>>(st);
     count_launch(ctx);
   }
   if (ctx->n_uninit > 0) {

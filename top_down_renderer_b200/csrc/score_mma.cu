@@ -107,6 +107,7 @@ struct MmaParams {
   unsigned long long* grid_key;     // grid mode: (min cost, first global flat index) over everything this launch computes
   int identity_shifts;      // shifts[k] == k for all k and n_shifts % 4 == 0: vector stores of the cost rows
   const int* maxcount; int* bailed;     // device-side fp16 exactness precondition, see score_mma_list.cu
+  int track_mode;           // particle mode: every particle takes the cost at ITS OWN heading's shift (rot_to_shift), no search
 };
 
 static const int MAX_RING_ROWS = 2 * RING_N;                  // n_theta <= RING_N
@@ -327,6 +328,9 @@ __global__ void __launch_bounds__(128 * T * R + 64, MmaCfg<T, R, ATM, G>::kCtasP
       const uint32_t trow = tmem_base + ((uint32_t)((warp & 3) * 32) << 16) + (uint32_t)(t * ACC);
       float best = 3.402823466e+38f;                                                         // :193-204
       int best_k = 0x7fffffff;
+      // tracking: the one column of this particle's heading (state_particle.cpp:207-210); NaN stays NaN there
+      const int my_shift = (sp.track_mode && i >= 0) ? rot_to_shift(sp.theta[i], n_theta) : -1;
+      float my_cost = 0.f;
       uint32_t vc[16], vn[16];
       const bool async_rows = ATM && sp.identity_shifts && (sp.costs || sp.n_cost_peers);   // CTA-uniform
       if (async_rows) bulk_wait_read();          // the previous tile's stores have read this thread's staging row
@@ -344,6 +348,7 @@ __global__ void __launch_bounds__(128 * T * R + 64, MmaCfg<T, R, ATM, G>::kCtasP
                            : TDR_FDIV(TDR_FMUL(__uint_as_float(vc[j]), 0.01f), __uint_as_float(vn[j]));   // :137,154
           // first strict minimum in LIST order == lexicographic minimum of (cost, list position)
           if (k >= 0 && (cst[j] < best || (cst[j] == best && k < best_k))) { best = cst[j]; best_k = k; }
+          if (s == my_shift) my_cost = cst[j];
         }
         if ((sp.costs || sp.n_cost_peers)) {          // warp-uniform
           const int n_dst = sp.n_cost_peers ? sp.n_cost_peers : 1;
@@ -415,7 +420,9 @@ __global__ void __launch_bounds__(128 * T * R + 64, MmaCfg<T, R, ATM, G>::kCtasP
         for (int o = 16; o > 0; o >>= 1) { const unsigned long long t = __shfl_xor_sync(0xffffffffu, key, o); if (t < key) key = t; }
         if (lane == 0 && key != ~0ull) atomicMin(sp.grid_key, key);
       }
-      if (i >= 0 && !sp.centers) {
+      if (i >= 0 && !sp.centers && sp.track_mode) {
+        sp.weights[i] = gated ? 0.f : (float)(1.0 / (double)TDR_FADD(my_cost, sp.regularization));   // :212
+      } else if (i >= 0 && !sp.centers) {
         if (gated) sp.weights[i] = 0.f;
         else {
           sp.theta[i] = best_k == 0x7fffffff ? 0.f : sp.thetas[best_k];
@@ -611,7 +618,7 @@ static bool mma_usable(tdr_ctx* ctx, const int32_t* host_shifts, int n_shifts) {
 
 // returns TDR_OK and sets *used = true when the tensor-core path ran; *used = false -> caller falls back
 int score_mma(tdr_ctx* ctx, float res, bool grid_mode, long long n_items, float grid_scale, const int32_t* dev_shifts,
-              const int32_t* host_shifts, int n_shifts, bool* used) {
+              const int32_t* host_shifts, int n_shifts, bool* used, bool track) {
   *used = false;
   if (!mma_usable(ctx, host_shifts, n_shifts)) return TDR_OK;
   const int P = ctx->n_theta * ctx->n_r;
@@ -635,7 +642,7 @@ int score_mma(tdr_ctx* ctx, float res, bool grid_mode, long long n_items, float 
   // counts above 2048 are not exact in fp16: checked ON THE DEVICE (sp.maxcount), the caller launches the guarded
   // CUDA-core kernel behind this one
 
-  if (int e = build_perm(ctx, grid_mode, n_items)) return e;
+  if (int e = build_perm(ctx, grid_mode, n_items, false, track)) return e;
   tdr::Particles& pt = ctx->part[ctx->cur];
   if (grid_mode) { if (int e = sync_const_tab_scaled(ctx, P, grid_scale, res)) return e; }
   else if (int e = sync_const_tab(ctx, P)) return e;
@@ -660,7 +667,8 @@ int score_mma(tdr_ctx* ctx, float res, bool grid_mode, long long n_items, float 
     for (int k = 0; k < n_shifts; k++) if (host_shifts[k] != k) sp.identity_shifts = 0;
     for (int d = 0; d < ctx->grid_n_peers; d++) sp.cost_peers[d] = ctx->grid_peers[d];
   } else {
-    sp.n_work = ctx->n_uninit;
+    sp.n_work = track ? pt.n - ctx->n_uninit : ctx->n_uninit;
+    sp.track_mode = track ? 1 : 0;
     sp.init_x = pt.init_x.as<float>(); sp.init_y = pt.init_y.as<float>(); sp.dx = pt.dx.as<float>(); sp.dy = pt.dy.as<float>();
     sp.theta = pt.theta.as<float>(); sp.scale = pt.scale.as<float>(); sp.have_init = pt.have_init.as<uint8_t>();
     sp.weights = ctx->weights.as<float>();

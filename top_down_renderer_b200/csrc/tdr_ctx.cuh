@@ -192,6 +192,9 @@ struct tdr_ctx {
   tdr::DevBuf d_cw;          // class weights (16 floats)
   tdr::Particles all;        // multi-GPU: the all-gathered particle set (N = ranks * n_local) in global order
   tdr::DevBuf weights;       // raw -> normalised in place
+  tdr::DevBuf raw_weights;   // copy of the raw weights of the last scoring (tdr_pf_keep_raw_weights)
+  bool keep_raw = false;
+  int64_t n_raw = 0;
   int64_t n_weights = 0;
   const float* ld_override = nullptr;  // device last_dist aligned with an all-gathered weight vector (multi-GPU)
   tdr::DevBuf prefix;        // running max of the order-exact prefix
@@ -282,7 +285,7 @@ int local_polar(tdr_ctx*, const float* dev_centers, int n, float scale, float re
 int local_cart(tdr_ctx*, float cx, float cy, float rot, float res, int out_rows, int out_cols, float* dev_dists, uint8_t* dev_mask);
 // score_mma.cu
 int score_mma(tdr_ctx*, float res, bool grid_mode, long long n_items, float grid_scale, const int32_t* dev_shifts,
-              const int32_t* host_shifts, int n_shifts, bool* used);
+              const int32_t* host_shifts, int n_shifts, bool* used, bool track = false);
 // score_mma_list.cu
 int score_mma_list(tdr_ctx*, float res, bool grid_mode, long long n_items, float grid_scale, const int32_t* dev_shifts,
                    int n_shifts, bool* used);
