@@ -323,14 +323,21 @@ def measure_particles(args, wl, workload_name, rank, world, local, steps, warmup
         pass
     a_ = _A()
     a_.steps, a_.warmup, a_.workload, a_.no_cpu = steps, warmup, workload_name, not with_cpu
+    a_.shard_impl = getattr(args, "shard_impl", "library")
     args = a_
     inp = make_inputs(wl, rank)
     ctx = setup_ctx(wl, inp, local)
     ctx.profile_enable(True)
     stream = torch.cuda.ExternalStream(ctx.stream, device=local)
-    flt = sharded.ShardedFilter(ctx, stream, rank, world) if world > 1 else None
+    shard_impl = getattr(args, "shard_impl", "library")
     n, C, res = wl["n"], wl["C"], wl["res"]
     M = n                                   # resample back to the same particle count (per GPU)
+    flt = None
+    if world > 1:
+        # "library": NCCL + peer-mapped state slots below the C ABI (csrc/shard.cu); "torch": the round-1 harness over
+        # torch.distributed with the states all-gathered to every rank
+        flt = (sharded.LibraryShardedFilter(ctx, rank, world, n) if shard_impl == "library"
+               else sharded.ShardedFilter(ctx, stream, rank, world))
     u = float(np.random.default_rng(SEED).random(dtype=np.float32))
     pts_pinned = torch.from_numpy(inp["pts"]).pin_memory()
     flush = torch.empty(256 << 20, dtype=torch.uint8, device=f"cuda:{local}")
@@ -471,7 +478,8 @@ def measure_particles(args, wl, workload_name, rank, world, local, steps, warmup
                "config": {"workload": wl["desc"], "particles_per_gpu": n, "shifts_per_particle": wl["shifts"],
                           "map_px": [wl["side"], wl["side"]], "classes": C, "polar_image": [N_THETA, N_R],
                           "res_m_per_bin": res, "parallelism": f"particle shards x{world}, map replicated"
-                          + (", 1 all-gather(weights+states)/step" if world > 1 else ""),
+                          + ((", ncclAllGather of 8 B/particle inside libtdr_b200 + resampled states read from the owner's peer-mapped slot"
+                              if args.shard_impl == "library" else ", all-gather(weights) + all-gather(states) via torch.distributed") if world > 1 else ""),
                           "l2": "flushed (256 MiB write) and particle set rolled back between steps, outside the timed events"},
                "clocks": clocks,
                "p50_update_ms": float(np.median(step_ms)),
@@ -504,6 +512,8 @@ def measure_particles(args, wl, workload_name, rank, world, local, steps, warmup
                                          f"{arm.cores} std::threads"}
     elif rank == 0:
         out["cpu_baseline"] = None
+    if flt is not None and hasattr(flt, "close"):
+        flt.close()
     ctx.close()
     if world > 1:
         dist.barrier()
@@ -861,6 +871,8 @@ def main():
     ap.add_argument("--no-cpu", action="store_true", help="skip the cpu_baseline leg")
     ap.add_argument("--grid-collective", default="fused", choices=["fused", "nccl"],
                     help="grid workload, N > 1: all-gather fused into the score kernel over peer memory, or NCCL")
+    ap.add_argument("--shard-impl", default="library", choices=["library", "torch"],
+                    help="particle workloads, N > 1: the sharded filter inside the library (tdr_shard_*) or the torch.distributed harness")
     ap.add_argument("--no-sub", action="store_true", help="default workload only: skip the cfg2 / cfg4 sub-records")
     ap.add_argument("--no-verify", action="store_true", help="skip the oracle check of the benchmarked configuration")
     args = ap.parse_args()

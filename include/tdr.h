@@ -309,6 +309,23 @@ int tdr_pf_resample_gathered(tdr_ctx* ctx, const void* dev_states_all, int n_ran
                              int64_t i0, int64_t i1);
 int tdr_pf_pose_gathered(tdr_ctx* ctx, const void* dev_all, int n_ranks, int64_t n_local, float mean[4],
                          float cov_mean[16], float ml[4], float cov_ml[16]);
+/* ---- the same, below the ABI: the sharded filter as library calls (one process per GPU, NCCL resolved at run time
+ * from libnccl.so.2 — a C++ node needs nothing but this library and NCCL).  Rank 0 creates a communicator id
+ * (tdr_shard_unique_id) and distributes its 128 bytes by whatever means the host has (MPI, a file, torch.distributed);
+ * every rank calls tdr_shard_init with the same id — it also allocates this rank's two state EXPORT slots and maps every
+ * peer's through CUDA IPC.  tdr_shard_step = tdr_step on the concatenated particle set: rasterise + score the local
+ * shard, ONE ncclAllGather of (raw weight, last_dist) = 8 B per particle, normalisation of all N weights in global order
+ * on every rank (weights, indices and states do not depend on the number of ranks), then this rank's slice of the M
+ * systematic samples with the drawn particles' states read straight out of the owning rank's export slot over NVLink
+ * (28 B per OUTPUT particle instead of an all-gather of every state to every rank).  M must be a multiple of the number
+ * of ranks (equal shards).  tdr_shard_pose = tdr_pf_pose over the whole resampled set (all-gathers 16 B per particle).
+ * tdr_shard_finalize (also run by tdr_destroy) destroys the communicator and unmaps the peers. */
+#define TDR_NCCL_ID_BYTES 128
+int tdr_shard_unique_id(uint8_t id[TDR_NCCL_ID_BYTES]);
+int tdr_shard_init(tdr_ctx* ctx, int rank, int world, const uint8_t id[TDR_NCCL_ID_BYTES], int64_t particles_per_rank);
+int tdr_shard_step(tdr_ctx* ctx, float res, float ang_res, int n_theta, int n_r, float u, int64_t M_total);
+int tdr_shard_pose(tdr_ctx* ctx, float mean[4], float cov_mean[16], float ml[4], float cov_ml[16]);
+void tdr_shard_finalize(tdr_ctx* ctx);
 /* replace the resident weights by an externally gathered vector living on the device
  * (all-gather output), n floats */
 int tdr_pf_set_weights_dev(tdr_ctx* ctx, const void* dev_weights, int64_t n);

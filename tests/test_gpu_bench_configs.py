@@ -358,3 +358,22 @@ def test_large_tracked_set_through_the_ring_kernel(world6, impl):
     assert np.isfinite(e).all() and e.max() <= WEIGHT_RTOL, e.max()
     assert np.isnan(got[:50]).all()
     assert np.array_equal(st_g["theta"], st["theta"]) and (st_g["have_init"] == 1).all()
+
+
+@pytest.mark.gpu
+@pytest.mark.parametrize("workload,particles", [("global", 20000), ("tracking", 20000)])
+def test_library_sharded_filter_equals_one_gpu(workload, particles):
+    """csrc/shard.cu (NCCL + peer-mapped state slots below the C ABI) on two GPUs: states, indices and pose of four
+    consecutive scans equal ONE GPU running the concatenated particle set, bit for bit.  Needs two devices."""
+    import subprocess
+    import sys
+    import torch
+    if torch.cuda.device_count() < 2:
+        pytest.skip("needs two GPUs")
+    import socket
+    s = socket.socket(); s.bind(("127.0.0.1", 0)); port = s.getsockname()[1]; s.close()
+    root = os.path.dirname(os.path.dirname(os.path.abspath(__file__)))
+    r = subprocess.run([sys.executable, "-m", "torch.distributed.run", "--nnodes=1", "--nproc-per-node", "2", "--master-addr", "127.0.0.1",
+                        "--master-port", str(port), os.path.join(root, "tools", "shard_check.py"), "--workload", workload,
+                        "--particles", str(particles)], capture_output=True, text=True, timeout=600)
+    assert r.returncode == 0, r.stdout[-2000:] + r.stderr[-2000:]

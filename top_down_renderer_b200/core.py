@@ -371,6 +371,31 @@ class Context:
                                              _pf(cov), _pf(ml) if want_ml else None, _pf(cov_ml) if want_ml else None))
         return mean, cov.reshape(4, 4), ml, cov_ml.reshape(4, 4)
 
+    # ---- the sharded filter below the ABI (csrc/shard.cu): NCCL + peer-mapped state slots inside the library
+    @staticmethod
+    def shard_unique_id() -> bytes:
+        buf = (C.c_uint8 * 128)()
+        check(_lib.load().tdr_shard_unique_id(buf))
+        return bytes(buf)
+
+    def shard_init(self, rank, world, unique_id: bytes, particles_per_rank):
+        buf = (C.c_uint8 * 128).from_buffer_copy(unique_id)
+        check(self._lib.tdr_shard_init(self._h, int(rank), int(world), buf, C.c_int64(particles_per_rank)))
+
+    def shard_step(self, res, ang_res, n_theta, n_r, u, M_total):
+        check(self._lib.tdr_shard_step(self._h, C.c_float(res), C.c_float(ang_res), int(n_theta), int(n_r), C.c_float(u), C.c_int64(M_total)))
+
+    def shard_pose(self, want_ml=True):
+        mean = np.zeros(4, dtype=np.float32)
+        cov = np.zeros(16, dtype=np.float32)
+        ml = np.zeros(4, dtype=np.float32)
+        cov_ml = np.zeros(16, dtype=np.float32)
+        check(self._lib.tdr_shard_pose(self._h, _pf(mean), _pf(cov), _pf(ml) if want_ml else None, _pf(cov_ml) if want_ml else None))
+        return mean, cov.reshape(4, 4), ml, cov_ml.reshape(4, 4)
+
+    def shard_finalize(self):
+        self._lib.tdr_shard_finalize(self._h)
+
     # ---- grid
     def grid_costs(self, centers_xy, scale, res, shifts, want=True):
         centers = np.ascontiguousarray(centers_xy, dtype=np.float32).reshape(-1, 2)

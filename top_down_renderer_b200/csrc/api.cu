@@ -185,6 +185,7 @@ int tdr_create(tdr_ctx** out, int device) {
 void tdr_destroy(tdr_ctx* c) {
   if (!c) return;
   cudaSetDevice(c->device);
+  tdr_shard_finalize(c);
   if (c->stream) { cudaStreamSynchronize(c->stream); }
   tdr::DevBuf* bufs[] = {&c->map_px, &c->seedbits, &c->edt_g, &c->scratch, &c->scratch2, &c->tab, &c->pts, &c->lut,
                          &c->scan_img, &c->scan_pack, &c->hist, &c->d_search_thetas, &c->d_search_shifts, &c->weights,

@@ -186,6 +186,7 @@ struct tdr_ctx {
   tdr::DevBuf uninit_dev;              // its device-side counter
   // kernels whose dynamic shared-memory opt-in has been set ON THIS CONTEXT'S DEVICE (function attributes are per
   // device; a process may hold contexts on several)
+  void* shard = nullptr;               // tdr::Shard (shard.cu): NCCL communicator, peer-mapped export slots
   uint64_t smem_optin = 0;
   uint64_t smem_optin_i8 = 0;          // the same for the variants of the integer score kernel
   uint64_t tab_id = 0;                 // process-unique id of the resident polar table (constant-memory mirrors key on it)

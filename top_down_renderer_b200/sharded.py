@@ -60,6 +60,7 @@ class ShardedFilter:
         import torch.distributed as dist
         torch, ctx = self.torch, self.ctx
         n_local = ctx.pf_count()
+        assert M_total % self.world == 0, "equal shards: the particle count must be a multiple of the number of ranks"
         i0, i1 = sample_slice(M_total, self.rank, self.world)
         if getattr(self, "_split_n", None) != n_local:
             dev = torch.device("cuda", ctx.device)
@@ -96,6 +97,30 @@ class ShardedFilter:
         with self.torch.cuda.stream(self.stream):
             self._all_gather(n_local, False)
             return ctx.pf_pose_gathered(self.recv.data_ptr(), self.world, n_local, want_ml)
+
+
+class LibraryShardedFilter:
+    """The same update with everything below the C ABI (csrc/shard.cu: tdr_shard_*): the library owns the NCCL
+    communicator (created from an id that rank 0 makes and torch.distributed merely carries to the other ranks) and the
+    peer-mapped state slots.  Per scan: ONE all-gather of 8 B per particle; resampled states are read from the owning
+    rank over NVLink.  What a C++ node would call; this class is the harness over it."""
+
+    def __init__(self, ctx, rank: int, world: int, particles_per_rank: int, group=None):
+        import torch.distributed as dist
+        self.ctx, self.rank, self.world = ctx, rank, world
+        box = [ctx.shard_unique_id() if rank == 0 else None]
+        dist.broadcast_object_list(box, src=0, group=group)
+        ctx.shard_init(rank, world, box[0], particles_per_rank)
+
+    def step(self, res, ang_res, n_theta, n_r, u, M_total):
+        assert M_total % self.world == 0, "equal shards: the particle count must be a multiple of the number of ranks"
+        self.ctx.shard_step(res, ang_res, n_theta, n_r, u, M_total)
+
+    def pose(self, want_ml=True):
+        return self.ctx.shard_pose(want_ml)
+
+    def close(self):
+        self.ctx.shard_finalize()
 
 
 class FusedGridGather:
