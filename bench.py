@@ -560,7 +560,7 @@ def measure_grid(wl, rank, world, local, steps, warmup, grid_collective, with_ve
     ctx.pf_set_params(C, regularization=0.7)
     stream = torch.cuda.ExternalStream(ctx.stream, device=local)
     dev = f"cuda:{local}"
-    fused = world > 1 and args.grid_collective == "fused"
+    fused = world > 1 and args.grid_collective in ("fused", "fused-nccl")
     tiny = torch.zeros(1, device=dev)
     if fused:
         gather = sharded.FusedGridGather(ctx, rank, world, n_total, S)     # peers map each other's full arrays
@@ -585,9 +585,13 @@ def measure_grid(wl, rank, world, local, steps, warmup, grid_collective, with_ve
         with torch.cuda.stream(stream):
             ctx.scan_render_polar(res, float(ANG_RES), N_THETA, N_R, want=False)
             ctx.grid_run_resident(n_local, 2.0, res, shifts)
-            if fused:
-                # ONE collective: MIN all-reduce of the packed (cost, global flat index) key the kernel folded — it is
-                # also the barrier after which every rank's array holds every cost (peer stores of all ranks done)
+            if fused and args.grid_collective == "fused":
+                # the cross-rank step inside the library: MIN of the packed (cost, global flat index) key + barrier, by
+                # system-scope atomics on a mailbox behind every rank's peer-mapped array; after it every rank's array
+                # holds every cost (peer stores of all ranks done).  Returns the reduced key (synchronises).
+                out = ctx.grid_key_decode(ctx.grid_peer_exchange())
+            elif fused:
+                # "fused-nccl": the same with ONE NCCL collective, a MIN all-reduce of the key, as barrier + reduction
                 dist.all_reduce(key_t, op=dist.ReduceOp.MIN)
                 out = ctx.grid_key_decode(int(key_t.item()))               # D2H of the key: synchronises
             elif world > 1:
@@ -595,7 +599,7 @@ def measure_grid(wl, rank, world, local, steps, warmup, grid_collective, with_ve
                 out = ctx.grid_best_dev(full_ptr, full_numel)              # D2H of (cost, index): synchronises
             else:
                 out = ctx.grid_key_decode(ctx.grid_best_key())             # folded by the score kernel; D2H synchronises
-            if not checked[0]:                                             # first (warm-up) step: same answer as a re-scan
+            if not checked[0] and not os.environ.get("TDR_GRID_SELF_ONLY"):   # first (warm-up) step: same answer as a re-scan
                 checked[0] = True
                 ref = ctx.grid_best_dev(full_ptr, full_numel)
                 assert ref == out, (ref, out)
@@ -676,7 +680,10 @@ def measure_grid(wl, rank, world, local, steps, warmup, grid_collective, with_ve
                "config": {"workload": wl["desc"], "centres_total": n_total, "centres_per_gpu": n_local, "shifts": S,
                           "map_px": [side, side], "classes": C, "polar_image": [N_THETA, N_R], "res_m_per_bin": res,
                           "parallelism": f"centre shards x{world}, map replicated"
-                          + ((", weight all-gather fused into the score kernel (NVLink peer stores) + 1 barrier all-reduce/step"
+                          + (((", weight all-gather fused into the score kernel (NVLink peer stores) + arg-min/barrier by "
+                               "system-scope atomics on peer mailboxes (tdr_grid_peer_exchange), no NCCL in the step"
+                               if args.grid_collective == "fused" else
+                               ", weight all-gather fused into the score kernel (NVLink peer stores) + 1 NCCL MIN all-reduce/step")
                               if fused else ", 1 NCCL all-gather(costs)/step") if world > 1 else ""),
                           "l2": "flushed (256 MiB write) between steps, outside the timed events"},
                "clocks": clocks, "best": {"cost": best[0], "flat_index": best[1]},
@@ -869,7 +876,7 @@ def main():
     ap.add_argument("--workload", default="global", choices=sorted(WORKLOADS))
     ap.add_argument("--particles", type=int, default=0, help="override particles per GPU")
     ap.add_argument("--no-cpu", action="store_true", help="skip the cpu_baseline leg")
-    ap.add_argument("--grid-collective", default="fused", choices=["fused", "nccl"],
+    ap.add_argument("--grid-collective", default="fused", choices=["fused", "fused-nccl", "nccl"],
                     help="grid workload, N > 1: all-gather fused into the score kernel over peer memory, or NCCL")
     ap.add_argument("--shard-impl", default="library", choices=["library", "torch"],
                     help="particle workloads, N > 1: the sharded filter inside the library (tdr_shard_*) or the torch.distributed harness")

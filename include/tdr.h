@@ -280,6 +280,14 @@ int tdr_grid_peer_alloc(tdr_ctx* ctx, int64_t n_floats, void** dev_ptr, uint8_t 
 int tdr_grid_peer_open(tdr_ctx* ctx, const uint8_t handle[TDR_IPC_HANDLE_BYTES], void** dev_ptr);
 int tdr_grid_peer_set(tdr_ctx* ctx, void* const* peer_ptrs, int n_peers, int64_t row_offset);
 int tdr_grid_peer_clear(tdr_ctx* ctx);   /* forgets the registration and closes the opened mappings */
+/* The cross-rank step of the fused grid WITHOUT a collective library: every rank calls it once per grid, behind
+ * tdr_grid_costs / tdr_grid_run_resident.  A one-warp kernel MINs this rank's packed (cost, global flat index) key into a
+ * mailbox behind every rank's full array and counts itself in there (system-scope atomics over NVLink), then waits until
+ * all ranks have counted themselves in its own mailbox: *key is the global arg-min (tdr_grid_key_decode) and every peer's
+ * cost stores into this rank's array have landed.  Replaces the NCCL MIN all-reduce + read-back of the key (same result;
+ * ~0.1 ms less per grid at 8 GPUs).  All ranks must call it the same number of times; a peer that never arrives makes it
+ * fail with TDR_ESTATE after ~3 s instead of hanging. */
+int tdr_grid_peer_exchange(tdr_ctx* ctx, uint64_t* key);
 /* device pointers of resident buffers for collectives issued by the host layer (NCCL through
  * torch.distributed): weights (n floats) / grid costs (n*n_shifts floats) */
 int tdr_dev_ptr(tdr_ctx* ctx, int which, void** ptr, int64_t* n_elems);
@@ -320,6 +328,10 @@ int tdr_pf_pose_gathered(tdr_ctx* ctx, const void* dev_all, int n_ranks, int64_t
  * (28 B per OUTPUT particle instead of an all-gather of every state to every rank).  M must be a multiple of the number
  * of ranks (equal shards).  tdr_shard_pose = tdr_pf_pose over the whole resampled set (all-gathers 16 B per particle).
  * tdr_shard_finalize (also run by tdr_destroy) destroys the communicator and unmaps the peers. */
+/* host-side sharding (the tdr_pf_*_gathered calls below): tell the context how many ranks share the particle set, so that the
+ * choice between scoring kernels goes by the GLOBAL particle count and the weights do not depend on the number of ranks
+ * (tdr_shard_init does this itself) */
+int tdr_pf_set_shard_count(tdr_ctx* ctx, int n_ranks);
 #define TDR_NCCL_ID_BYTES 128
 int tdr_shard_unique_id(uint8_t id[TDR_NCCL_ID_BYTES]);
 int tdr_shard_init(tdr_ctx* ctx, int rank, int world, const uint8_t id[TDR_NCCL_ID_BYTES], int64_t particles_per_rank);

@@ -67,7 +67,7 @@ SYMBOLS = [
     "tdr_pf_pose", "tdr_pf_update", "tdr_step", "tdr_grid_costs", "tdr_grid_best", "tdr_grid_set_costs_buffer", "tdr_grid_best_dev", "tdr_grid_best_key", "tdr_grid_key_decode", "tdr_grid_peer_alloc", "tdr_grid_peer_open",
     "tdr_grid_peer_set", "tdr_grid_peer_clear", "tdr_dev_ptr",
     "tdr_pf_propagate", "tdr_pf_propagate_dev", "tdr_pf_propagate_rng", "tdr_pf_get_last_dist", "tdr_pf_gmm_samples",
-    "tdr_pf_set_weights_dev", "tdr_pf_export_shard", "tdr_pf_update_gathered", "tdr_pf_export_split", "tdr_pf_normalize_gathered", "tdr_pf_resample_gathered", "tdr_pf_pose_gathered", "tdr_shard_unique_id", "tdr_shard_init", "tdr_shard_step", "tdr_shard_pose", "tdr_shard_finalize",
+    "tdr_pf_set_weights_dev", "tdr_pf_export_shard", "tdr_pf_update_gathered", "tdr_pf_export_split", "tdr_pf_normalize_gathered", "tdr_pf_resample_gathered", "tdr_pf_pose_gathered", "tdr_grid_peer_exchange", "tdr_pf_set_shard_count", "tdr_shard_unique_id", "tdr_shard_init", "tdr_shard_step", "tdr_shard_pose", "tdr_shard_finalize",
 ]
 
 

@@ -372,6 +372,9 @@ class Context:
         return mean, cov.reshape(4, 4), ml, cov_ml.reshape(4, 4)
 
     # ---- the sharded filter below the ABI (csrc/shard.cu): NCCL + peer-mapped state slots inside the library
+    def pf_set_shard_count(self, n_ranks):
+        check(self._lib.tdr_pf_set_shard_count(self._h, int(n_ranks)))
+
     @staticmethod
     def shard_unique_id() -> bytes:
         buf = (C.c_uint8 * 128)()
@@ -438,6 +441,12 @@ class Context:
 
     def grid_peer_clear(self):
         check(self._lib.tdr_grid_peer_clear(self._h))
+
+    def grid_peer_exchange(self) -> int:
+        """arg-min reduction + barrier of the fused grid over peer memory (no collective library); the packed key"""
+        k = C.c_uint64()
+        check(self._lib.tdr_grid_peer_exchange(self._h, C.byref(k)))
+        return int(k.value)
 
     def copy_from_device(self, dev_ptr, n_floats):
         """debug / test helper: D2H of n floats from a raw device pointer (synchronises the context stream first)"""

@@ -178,6 +178,9 @@ int tdr_create(tdr_ctx** out, int device) {
   TDR_CUDA(cudaEventCreateWithFlags(&c->scan_max_ev, cudaEventDisableTiming));
   TDR_CUDA(cudaMallocHost(reinterpret_cast<void**>(&c->scan_max_pin), 16));
   *c->scan_max_pin = 0;
+  TDR_CUDA(cudaMallocHost(reinterpret_cast<void**>(&c->grid_key_pin), 32));
+  memset(c->grid_key_pin, 0, 32);
+  if (const char* e = getenv("TDR_GRID_SELF_ONLY")) c->grid_self_only = atoi(e) != 0;
   *out = c;
   return TDR_OK;
 }
@@ -204,6 +207,7 @@ void tdr_destroy(tdr_ctx* c) {
   c->map8.release();
   if (c->scan_max_ev) cudaEventDestroy(c->scan_max_ev);
   if (c->scan_max_pin) cudaFreeHost(c->scan_max_pin);
+  if (c->grid_key_pin) cudaFreeHost(c->grid_key_pin);
   for (int k = 0; k <= TDR_N_STAGES; k++) if (c->stage_ev[k]) cudaEventDestroy(c->stage_ev[k]);
   for (int k = 0; k < 2; k++) { if (c->refine_copied[k]) cudaEventDestroy(c->refine_copied[k]); if (c->refine_binned[k]) cudaEventDestroy(c->refine_binned[k]); c->refine_stage[k].release(); }
   if (c->copy_stream) cudaStreamDestroy(c->copy_stream);
@@ -879,6 +883,11 @@ int tdr_pf_export_split(tdr_ctx* ctx, void* dev_wl, void* dev_states) {
   TDR_CUDA(cudaGetLastError());
   return TDR_OK;
 }
+int tdr_pf_set_shard_count(tdr_ctx* ctx, int n_ranks) {
+  TDR_REQUIRE(ctx && n_ranks >= 1 && n_ranks <= TDR_MAX_PEERS, TDR_EINVAL, "bad rank count");
+  ctx->count_scale = n_ranks;
+  return TDR_OK;
+}
 int tdr_pf_normalize_gathered(tdr_ctx* ctx, const void* dev_wl_all, int n_ranks, int64_t n_local) {
   CTX_CHECK(ctx);
   const int64_t N = (int64_t)n_ranks * n_local;
@@ -1013,11 +1022,87 @@ int tdr_grid_key_decode(uint64_t key, float* best_cost, int64_t* best_index) {
   return TDR_OK;
 }
 
+// ---- the cross-rank step of the fused grid: arg-min reduction + barrier over peer memory, no NCCL -------------------
+// Behind every rank's full cost array sits a mailbox its peers have mapped with the array: two slots of
+// (key: u64, arrivals: u32).  Exchange e uses slot e & 1.  Every rank atomically MINs its own (cost, flat index) key into
+// the slot of EVERY rank (its own included) and then bumps that rank's arrival counter, both with system-scope atomics
+// over NVLink; it then spins until its own counter shows all ranks.  At that point its slot holds the global minimum and —
+// because each rank publishes from a kernel launched behind its score kernel, after a system-scope fence — every peer's
+// cost stores into this rank's array have landed.  Counters never reset (target = ranks x uses of the slot); a key slot
+// is reset by its owner right after reading it, which is safe because no peer can start exchange e + 2 before this rank
+// has arrived in exchange e + 1.
+static const size_t GRID_MAILBOX_BYTES = 256;
+static size_t mailbox_offset(int64_t n_floats) { return (((size_t)n_floats * 4) + 255) / 256 * 256; }
+struct GridBoxes { unsigned char* box[TDR_MAX_PEERS]; };
+__global__ void k_grid_exchange(GridBoxes peers, int n_peers, unsigned char* own, int slot, unsigned int target,
+                                unsigned long long* local_key, unsigned long long* pin, int* timed_out) {
+  const int d = threadIdx.x;
+  const unsigned long long mine = *local_key;
+  if (d < n_peers) {
+    unsigned long long* key = reinterpret_cast<unsigned long long*>(peers.box[d]) + slot;
+    unsigned int* arrive = reinterpret_cast<unsigned int*>(peers.box[d] + 16) + slot;
+    atomicMin_system(key, mine);
+    __threadfence_system();
+    atomicAdd_system(arrive, 1u);
+  }
+  __syncwarp();
+  if (d == 0) {
+    volatile unsigned int* arrive = reinterpret_cast<volatile unsigned int*>(own + 16) + slot;
+    const long long t0 = clock64();
+    bool ok = true;
+    while (*arrive < target) {
+      if (clock64() - t0 > 6000000000ll) { ok = false; break; }       // ~3 s: a peer never arrived
+      __nanosleep(200);
+    }
+    __threadfence_system();
+    unsigned long long* key = reinterpret_cast<unsigned long long*>(own) + slot;
+    const unsigned long long best = ok ? *reinterpret_cast<volatile unsigned long long*>(key) : ~0ull;
+    *key = ~0ull;                                                     // ready for exchange e + 2
+    __threadfence_system();
+    *local_key = best;
+    *pin = best;
+    *timed_out = ok ? 0 : 1;
+  }
+}
+
+int tdr_grid_peer_exchange(tdr_ctx* ctx, uint64_t* key) {
+  CTX_CHECK(ctx);
+  TDR_REQUIRE(key, TDR_EINVAL, "null argument");
+  TDR_REQUIRE(ctx->grid_n_peers >= 1 && ctx->grid_full.p && ctx->grid_full_floats > 0, TDR_ESTATE, "no peer arrays registered");
+  TDR_REQUIRE(ctx->grid_key_valid, TDR_ESTATE, "the last grid did not run on the tensor-core kernel");
+  const size_t box = mailbox_offset(ctx->grid_full_floats);
+  GridBoxes peers;
+  for (int d = 0; d < TDR_MAX_PEERS; d++)
+    peers.box[d] = d < ctx->grid_n_peers ? reinterpret_cast<unsigned char*>(ctx->grid_peers[d]) + box : nullptr;
+  const int slot = (int)(ctx->grid_epoch & 1);
+  const unsigned int target = (unsigned int)(ctx->grid_n_peers * (ctx->grid_epoch / 2 + 1));
+  ctx->grid_epoch++;
+  int* flags = reinterpret_cast<int*>(ctx->grid_key_pin + 1);
+  k_grid_exchange<<<1, 32, 0, ctx->stream>>>(peers, ctx->grid_n_peers, ctx->grid_full.as<unsigned char>() + box, slot, target,
+                                             ctx->grid_key.as<unsigned long long>(), ctx->grid_key_pin, flags);
+  count_launch(ctx);
+  TDR_CUDA(cudaGetLastError());
+  TDR_CUDA(cudaMemcpyAsync(flags + 1, ctx->scal.as<float>() + SC_MMA_BAILED, 4, cudaMemcpyDeviceToHost, ctx->stream));
+  TDR_CUDA(cudaStreamSynchronize(ctx->stream));
+  TDR_REQUIRE(!flags[0], TDR_ESTATE, "grid exchange: a peer did not arrive within 3 s");
+  TDR_REQUIRE(!flags[1], TDR_ESTATE, "scan counts above 2048: the fused peer all-gather did not run");
+  *key = *ctx->grid_key_pin;
+  return TDR_OK;
+}
+
 int tdr_grid_peer_alloc(tdr_ctx* ctx, int64_t n_floats, void** dev_ptr, uint8_t handle[TDR_IPC_HANDLE_BYTES]) {
   CTX_CHECK(ctx);
   static_assert(sizeof(cudaIpcMemHandle_t) == TDR_IPC_HANDLE_BYTES, "IPC handle size");
   TDR_REQUIRE(n_floats > 0 && dev_ptr && handle, TDR_EINVAL, "bad arguments");
-  if (int e = ctx->grid_full.reserve((size_t)n_floats * 4)) return e;
+  const size_t box = mailbox_offset(n_floats);
+  if (int e = ctx->grid_full.reserve(box + GRID_MAILBOX_BYTES)) return e;
+  ctx->grid_full_floats = n_floats; ctx->grid_epoch = 0;
+  // mailbox: two (key, arrivals) slots; keys start at "no result", arrival counters at 0 and only ever grow
+  unsigned long long init[GRID_MAILBOX_BYTES / 8];
+  memset(init, 0, sizeof(init));
+  init[0] = init[1] = ~0ull;
+  TDR_CUDA(cudaMemcpyAsync(ctx->grid_full.as<unsigned char>() + box, init, sizeof(init), cudaMemcpyHostToDevice, ctx->stream));
+  TDR_CUDA(cudaStreamSynchronize(ctx->stream));
   cudaIpcMemHandle_t h;
   TDR_CUDA(cudaIpcGetMemHandle(&h, ctx->grid_full.p));
   memcpy(handle, &h, TDR_IPC_HANDLE_BYTES);
@@ -1045,7 +1130,7 @@ int tdr_grid_peer_clear(tdr_ctx* ctx) {
   CTX_CHECK(ctx);
   cudaStreamSynchronize(ctx->stream);
   for (void* p : ctx->grid_opened) cudaIpcCloseMemHandle(p);
-  ctx->grid_opened.clear(); ctx->grid_n_peers = 0;
+  ctx->grid_opened.clear(); ctx->grid_n_peers = 0; ctx->grid_epoch = 0;
   return TDR_OK;
 }
 

@@ -414,7 +414,7 @@ int score_particles(tdr_ctx* ctx, float res) {
     // profiles/r02_tracking_1m.txt).  Small sets (cfg2: 1e4) stay on k_score_track.
     bool tracked_by_mma = false;
     const long long n_init = pt.n - ctx->n_uninit;
-    if (sp.n_shifts > 0 && (ctx->score_impl == 2 || (ctx->score_impl == 0 && n_init >= 65536))) {
+    if (sp.n_shifts > 0 && (ctx->score_impl == 2 || (ctx->score_impl == 0 && n_init * ctx->count_scale >= 65536))) {
       if (int e = score_mma(ctx, res, false, pt.n, 1.f, sp.shifts, ctx->search_shifts.data(), sp.n_shifts, &tracked_by_mma, true)) return e;
     }
     ScoreParams st = sp;
@@ -429,7 +429,7 @@ int score_particles(tdr_ctx* ctx, float res) {
     TDR_REQUIRE(sp.n_shifts > 0, TDR_ESTATE, "theta-search list not set (tdr_pf_set_search)");
     // large searches go to the tensor cores (score_mma.cu); small ones stay on the CUDA cores
     bool used = false;
-    if (ctx->score_impl == 2 || (ctx->score_impl == 0 && ctx->n_uninit >= 4096)) {
+    if (ctx->score_impl == 2 || (ctx->score_impl == 0 && (long long)ctx->n_uninit * ctx->count_scale >= 4096)) {
       // short candidate lists: streamed-operand kernel (two pipelines per SM); long ones: all-shifts ring kernel
       // integer 16-byte records where their error bound and the count range allow (score_mma_i8.cu)
       if (ctx->mma_kernel == 0 || ctx->mma_kernel == 3) { if (int e = score_mma_i8(ctx, res, sp.shifts, sp.n_shifts, &used)) return e; }

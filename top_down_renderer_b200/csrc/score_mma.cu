@@ -666,6 +666,7 @@ int score_mma(tdr_ctx* ctx, float res, bool grid_mode, long long n_items, float 
     sp.identity_shifts = (n_shifts % 4 == 0) ? 1 : 0;
     for (int k = 0; k < n_shifts; k++) if (host_shifts[k] != k) sp.identity_shifts = 0;
     for (int d = 0; d < ctx->grid_n_peers; d++) sp.cost_peers[d] = ctx->grid_peers[d];
+    if (ctx->grid_n_peers && ctx->grid_self_only) { sp.n_cost_peers = 1; sp.cost_peers[0] = ctx->grid_full.as<float>(); }   // diagnostic: no NVLink stores
   } else {
     sp.n_work = track ? pt.n - ctx->n_uninit : ctx->n_uninit;
     sp.track_mode = track ? 1 : 0;

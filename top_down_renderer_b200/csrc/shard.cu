@@ -196,6 +196,7 @@ void tdr_shard_finalize(tdr_ctx* ctx) {
   sh->exp[0].release(); sh->exp[1].release(); sh->wl.release(); sh->wl_all.release(); sh->cols.release(); sh->cols_all.release();
   delete sh;
   ctx->shard = nullptr;
+  ctx->count_scale = 1;
 }
 
 int tdr_shard_init(tdr_ctx* ctx, int rank, int world, const uint8_t id[TDR_NCCL_ID_BYTES], int64_t particles_per_rank) {
@@ -208,6 +209,7 @@ int tdr_shard_init(tdr_ctx* ctx, int rank, int world, const uint8_t id[TDR_NCCL_
   Shard* sh = new Shard();
   ctx->shard = sh;
   sh->rank = rank; sh->world = world; sh->cap = particles_per_rank;
+  ctx->count_scale = world;
   ncclUniqueId u;
   memcpy(&u, id, sizeof(u));
   TDR_NCCL(api, api->CommInitRank(&sh->comm, world, u, rank));

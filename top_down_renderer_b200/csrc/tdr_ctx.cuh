@@ -186,6 +186,8 @@ struct tdr_ctx {
   tdr::DevBuf uninit_dev;              // its device-side counter
   // kernels whose dynamic shared-memory opt-in has been set ON THIS CONTEXT'S DEVICE (function attributes are per
   // device; a process may hold contexts on several)
+  int count_scale = 1;                  // ranks sharing the particle set: kernel choices go by the GLOBAL count, so that
+                                        // weights (hence resampled indices) do not depend on the number of ranks
   void* shard = nullptr;               // tdr::Shard (shard.cu): NCCL communicator, peer-mapped export slots
   uint64_t smem_optin = 0;
   uint64_t smem_optin_i8 = 0;          // the same for the variants of the integer score kernel
@@ -222,7 +224,11 @@ struct tdr_ctx {
   float* grid_peers[TDR_MAX_PEERS] = {};
   int grid_n_peers = 0;
   int64_t grid_peer_row0 = 0;
-  tdr::DevBuf grid_full;                 // this rank's full array (IPC-exported)
+  tdr::DevBuf grid_full;                 // this rank's full array (IPC-exported), followed by the exchange mailbox
+  int64_t grid_full_floats = 0;          // floats of the cost array proper: the mailbox sits at the next 256-byte boundary
+  uint64_t grid_epoch = 0;               // exchanges done (all ranks in lock step): picks the mailbox slot
+  unsigned long long* grid_key_pin = nullptr;   // pinned host word the exchange kernel writes the reduced key to
+  bool grid_self_only = false;           // TDR_GRID_SELF_ONLY=1: store costs to the own array only (diagnostic)
   std::vector<void*> grid_opened;        // mappings to close
   float* grid_costs_ext = nullptr;       // caller-provided device buffer for the costs (tdr_grid_set_costs_buffer)
   int64_t grid_costs_ext_cap = 0;

@@ -25,7 +25,7 @@ struct SeqJob {
   const unsigned long long* skip_if; unsigned long long skip_val;
 };
 __device__ __forceinline__ bool seq_skipped(const SeqJob& job) { return job.skip_if && *job.skip_if == job.skip_val; }
-#define TDR_MAX_JOBS 8
+#define TDR_MAX_JOBS 9
 struct SeqJobs { SeqJob j[TDR_MAX_JOBS]; };
 
 static const int SEQ_THREADS = 1024;
@@ -605,14 +605,17 @@ __global__ void k_under(const float* __restrict__ w, long long n, const float* _
   if ((threadIdx.x & 31) == 0 && c) atomicAdd(nunder, c);
 }
 
-__global__ void k_stats(float* scal, const unsigned long long* nunder) {
-  int nu = (int)*nunder;
+// u64: [1] = num_valid, [2] = num_under, [4] <- "k_fill_nan will change a weight" (a NaN to replace, or the all-ones
+// fallback): the sums over the filled weights that normalize() started speculatively on the raw ones are redone
+__global__ void k_stats(float* scal, unsigned long long* u64, unsigned long long n) {
+  int nu = (int)u64[2];
   float bs = scal[SC_BSRAW];
   bs = TDR_FSQRT(TDR_FDIV(bs, (float)nu));                       // :126
   scal[SC_BS] = bs; scal[SC_NUNDER] = (float)nu;
   bool fallback = (scal[SC_SUM] == 0.f) || (nu < 1);             // :129
   scal[SC_FALLBACK] = fallback ? 1.f : 0.f;
   scal[SC_REP] = TDR_FSUB(scal[SC_MEAN], bs);                    // :133
+  u64[4] = (fallback || u64[1] != n) ? 1ull : 0ull;
 }
 
 __global__ void k_fill_nan(float* __restrict__ w, long long n, const float* __restrict__ scal) {
@@ -880,15 +883,24 @@ static int launch_seq(tdr_ctx* ctx, const SeqJobs& jobs, int njobs) {
 }
 
 // Eigen linear-vectorised sum of x[0..n) into scal[slot]
-static int eigen_sum(tdr_ctx* ctx, const float* x, long long n, int slot) {
+// the 8 interleaved chains of Eigen's packet sum as jobs [at, at + 8)
+static void eigen_chain_jobs(SeqJobs& jobs, int at, const float* x, long long n, float* scal, int skip_nan) {
+  const long long aS2 = (n / 8) * 8;
+  for (int k = 0; k < 8; k++) {
+    SeqJob& j = jobs.j[at + k];
+    j.x = x; j.start = k; j.stride = 8; j.count = aS2 / 8;
+    j.runmax_out = nullptr; j.total_out = scal + SC_CHAIN + k; j.skip_nan = skip_nan;
+  }
+}
+// skip_if_zero: the chain totals in scal[SC_CHAIN..] are already those of x (computed speculatively) unless this device
+// word is non-zero
+static int eigen_sum(tdr_ctx* ctx, const float* x, long long n, int slot, const unsigned long long* skip_if_zero = nullptr) {
   float* scal = ctx->scal.as<float>();
   const long long aS2 = (n / 8) * 8;
   if (aS2 >= 8) {
     SeqJobs jobs; memset(&jobs, 0, sizeof(jobs));
-    for (int k = 0; k < 8; k++) {
-      jobs.j[k].x = x; jobs.j[k].start = k; jobs.j[k].stride = 8; jobs.j[k].count = aS2 / 8;
-      jobs.j[k].runmax_out = nullptr; jobs.j[k].total_out = scal + SC_CHAIN + k; jobs.j[k].skip_nan = 0;
-    }
+    eigen_chain_jobs(jobs, 0, x, n, scal, 0);
+    if (skip_if_zero) for (int k = 0; k < 8; k++) { jobs.j[k].skip_if = skip_if_zero; jobs.j[k].skip_val = 0ull; }
     if (int e = launch_seq(ctx, jobs, 8)) return e;
   }
   k_eigen_sum_finish<<<1, 1, 0, ctx->stream>>>(x, n, scal + SC_CHAIN, scal + slot);
@@ -913,7 +925,14 @@ int normalize(tdr_ctx* ctx, bool lazy_stddev) {
   SeqJobs jobs; memset(&jobs, 0, sizeof(jobs));
   jobs.j[0].x = w; jobs.j[0].start = 0; jobs.j[0].stride = 1; jobs.j[0].count = n; jobs.j[0].runmax_out = nullptr;
   jobs.j[0].total_out = scal + SC_SUM; jobs.j[0].skip_nan = 1;
-  if (int e = launch_seq(ctx, jobs, 1)) return e;
+  // In the steady state no weight is NaN and the all-ones fallback (:129) does not fire, so k_fill_nan changes nothing
+  // and the sum AFTER it (:135) runs over the same numbers as this one: its 8 Eigen chains ride along in the same
+  // launches (their walks in parallel CTAs) instead of costing a second dependent pass.  k_stats decides on the device
+  // whether that was right (u64[4]); if not, eigen_sum below recomputes them.
+  const bool spec = n >= 8 && n >= SQ_MIN_COUNT;
+  if (spec) eigen_chain_jobs(jobs, 1, w, n, scal, 1);
+  if (int e = launch_seq(ctx, jobs, spec ? 9 : 1)) return e;
+  if (spec) memset(&jobs.j[1], 0, 8 * sizeof(SeqJob));
   k_count_valid<<<blocks, 256, 0, ctx->stream>>>(w, n, u64 + 1);
   k_mean<<<1, 1, 0, ctx->stream>>>(scal, u64 + 1);
   k_under<<<blocks, 256, 0, ctx->stream>>>(w, n, scal, u64 + 2);
@@ -922,10 +941,10 @@ int normalize(tdr_ctx* ctx, bool lazy_stddev) {
   if (lazy_stddev) { jobs.j[0].skip_if = u64 + 1; jobs.j[0].skip_val = (unsigned long long)n; }     // num_valid == n: no NaN to replace
   if (int e = launch_seq(ctx, jobs, 1)) return e;
   jobs.j[0].skip_if = nullptr;
-  k_stats<<<1, 1, 0, ctx->stream>>>(scal, u64 + 2);
+  k_stats<<<1, 1, 0, ctx->stream>>>(scal, u64, (unsigned long long)n);
   k_fill_nan<<<blocks, 256, 0, ctx->stream>>>(w, n, scal);
   count_launch(ctx, 5);
-  if (int e = eigen_sum(ctx, w, n, SC_S1)) return e;
+  if (int e = eigen_sum(ctx, w, n, SC_S1, spec ? u64 + 4 : nullptr)) return e;
   k_regularize<<<blocks, 256, 0, ctx->stream>>>(w, ld, n, scal);
   count_launch(ctx);
   if (int e = eigen_sum(ctx, w, n, SC_S2)) return e;

@@ -40,6 +40,8 @@ class ShardedFilter:
         import torch
         self.torch, self.ctx, self.stream, self.rank, self.world, self.group = torch, ctx, stream, rank, world, group
         self.send = self.recv = None
+        if hasattr(ctx, "pf_set_shard_count"):
+            ctx.pf_set_shard_count(world)      # kernel choices by the global particle count: results independent of `world`
 
     def _buffers(self, n_local):
         torch = self.torch
