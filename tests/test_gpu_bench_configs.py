@@ -377,3 +377,33 @@ def test_library_sharded_filter_equals_one_gpu(workload, particles):
                         "--master-port", str(port), os.path.join(root, "tools", "shard_check.py"), "--workload", workload,
                         "--particles", str(particles)], capture_output=True, text=True, timeout=600)
     assert r.returncode == 0, r.stdout[-2000:] + r.stderr[-2000:]
+
+
+@pytest.mark.gpu
+@pytest.mark.parametrize("h,w,C,resolution", [(37, 53, 3, 1.0), (130, 1031, 7, 1.0), (65, 2055, 6, 0.5), (90, 9, 2, 0.3), (64, 1024, 5, 2.0)])
+def test_packed_edt_row_pass_odd_shapes(h, w, C, resolution):
+    """k_edt_rows_dpx (16-bit packed add-min, 1024-pixel row tiles) on shapes that exercise its edges: rows shorter than a
+    tile, one pixel past a tile, widths that are no multiple of 8, seven classes, windows of 27 / 52 / 102 / 169 px —
+    bit-exact against the oracle's EDT, and identical to the scalar tap scan it replaces."""
+    from top_down_renderer_b200.core import Context
+    img = synth.to_cv_image(synth.make_class_map(h, w, C, seed=11))
+    lut = synth.identity_lut(C)
+    want, want_mask = orc.compute_dists(orc.class_image_to_layers(img, lut, C, resolution), resolution)
+    c = Context(0)
+    c.map_set_class_image(img, lut, C, resolution)
+    layers, mask = c.map_get_layers()
+    geo = c.map_get_geo_layers()
+    c.close()
+    assert np.array_equal(mask, want_mask)
+    assert np.array_equal(layers.view(np.uint32), want.view(np.uint32))
+    os.environ["TDR_EDT_IMPL"] = "1"
+    try:
+        c = Context(0)
+        c.map_set_class_image(img, lut, C, resolution)
+        l1, m1 = c.map_get_layers()
+        g1 = c.map_get_geo_layers()
+        c.close()
+    finally:
+        del os.environ["TDR_EDT_IMPL"]
+    assert np.array_equal(l1.view(np.uint32), layers.view(np.uint32)) and np.array_equal(m1, mask)
+    assert np.array_equal(np.asarray(g1).view(np.uint32), np.asarray(geo).view(np.uint32))

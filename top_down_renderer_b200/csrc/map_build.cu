@@ -159,6 +159,108 @@ __global__ void k_edt_horizontal(const uint8_t* __restrict__ seed, const uint8_t
   }
 }
 
+// ------------------------------------------------------------------------------------------------
+// Pass H, packed: the same minimum  d2_c(y, x) = min_dx dx^2 + g_c(y, x + dx)^2  as k_edt_horizontal, evaluated with the
+// DPX instruction VIADDMNMX.U16x2 (__viaddmin_u16x2: min(a + b, c) on two 16-bit lanes): ONE instruction covers two
+// taps, against ~6 for the scalar tap (load, test, multiply-add, compare, select) — that kernel was instruction-bound at
+// 3.6 % of its HBM roofline.  A CTA owns EDT_XT pixels of one row: for every class the squared column distances g^2 of
+// the tile and its +-R halo go to shared memory as 16-bit words (0x7fff = no seed: every sum with it stays above any
+// capped distance and below 2^16); a thread owns 8 adjacent pixels and walks the 2R + 8 taps they share, eight taps
+// per 128-bit shared load.  The squared offsets come from one table E[j] = ((j - R - 7)^2, (j - R - 6)^2), read with
+// warp-uniform addresses (broadcast).  No early exit, no branches: every pixel costs the same ~65 instructions per class.
+// Taps beyond the truncation window only add candidates >= capcode, which the final min(d2, capcode) removes, so the
+// result equals the windowed scan bit for bit (tests/test_gpu_parity.py EDT cases, the cv2 fixture, the reference build).
+// Needs (R + 7)^2 <= 0x7fff, i.e. windows up to 174 px (resolution >= 0.29 m/px); finer maps keep k_edt_horizontal.
+static const int EDT_XT_THREADS = 128, EDT_XT = EDT_XT_THREADS * 8;
+template <bool TO_MAP>
+__global__ void __launch_bounds__(EDT_XT_THREADS) k_edt_rows_dpx(const uint8_t* __restrict__ seed, const uint8_t* __restrict__ g,
+                                                                 int rows, int cols, int C, int R, uint32_t capcode,
+                                                                 float resolution, MapPixel* __restrict__ map_px,
+                                                                 float* __restrict__ planar) {
+  extern __shared__ __align__(16) unsigned char edt_smem[];
+  const int span = EDT_XT + 2 * R + 8;                          // 16-bit words per class (multiple of 8)
+  const int n_e = 2 * R + 24;                                   // table entries (multiple of 8)
+  uint32_t* s_e = reinterpret_cast<uint32_t*>(edt_smem);
+  uint16_t* s_g2 = reinterpret_cast<uint16_t*>(edt_smem + (size_t)n_e * 4);
+  const int y = blockIdx.y, x0 = blockIdx.x * EDT_XT, tid = threadIdx.x;
+  const size_t L = (size_t)rows * cols;
+  for (int j = tid; j < n_e; j += EDT_XT_THREADS) {
+    const int d = j - R - 7;
+    s_e[j] = (uint32_t)(d * d) | ((uint32_t)((d + 1) * (d + 1)) << 16);
+  }
+  for (int c = 0; c < C; c++) {
+    const uint8_t* gr = g + (size_t)c * L + (size_t)y * cols;
+    uint16_t* dst = s_g2 + (size_t)c * span;
+    for (int j = tid; j < span; j += EDT_XT_THREADS) {
+      const int x = x0 - R + j;
+      uint32_t v = 255u;
+      if (x >= 0 && x < cols) v = gr[x];
+      dst[j] = v == 255u ? (uint16_t)0x7fff : (uint16_t)(v * v);
+    }
+  }
+  __syncthreads();
+  const int xb = x0 + 8 * tid;                                   // this thread's pixels xb .. xb + 7
+  if (xb >= cols) return;
+  uint32_t unk = 0;
+#pragma unroll
+  for (int p = 0; p < 8; p++) if (xb + p < cols && (seed[(size_t)y * cols + xb + p] & 0x80u)) unk |= 1u << p;
+  uint32_t d2p[8][4];                                            // [pixel][class pair] two capped d2 per word
+#pragma unroll
+  for (int p = 0; p < 8; p++) { d2p[p][0] = d2p[p][1] = d2p[p][2] = d2p[p][3] = 0; }
+  const int n_blocks = (2 * R + 8) / 8;
+#pragma unroll
+  for (int c = 0; c < 7; c++) {
+    if (c < C) {
+      uint32_t best[8];
+#pragma unroll
+      for (int p = 0; p < 8; p++) best[p] = 0x7fff7fffu;
+      const uint4* src = reinterpret_cast<const uint4*>(s_g2 + (size_t)c * span + 8 * tid);
+      const uint4* et = reinterpret_cast<const uint4*>(s_e);
+#pragma unroll 1
+      for (int b = 0; b < n_blocks; b++) {
+        const uint4 gv = src[b];                                 // taps 8b .. 8b + 7 of this thread's window
+        const uint4 e0 = et[2 * b], e1 = et[2 * b + 1], e2 = et[2 * b + 2], e3 = et[2 * b + 3];
+        const uint32_t e[16] = {e0.x, e0.y, e0.z, e0.w, e1.x, e1.y, e1.z, e1.w, e2.x, e2.y, e2.z, e2.w, e3.x, e3.y, e3.z, e3.w};
+        const uint32_t gq[4] = {gv.x, gv.y, gv.z, gv.w};
+#pragma unroll
+        for (int q = 0; q < 4; q++)
+#pragma unroll
+          for (int p = 0; p < 8; p++) best[p] = __viaddmin_u16x2(gq[q], e[2 * q + 7 - p], best[p]);   // taps 8b+2q, +1 against pixel p
+      }
+      // (visiting the blocks from the centre outwards and stopping once no unvisited column can improve any of the eight
+      // minima was measured SLOWER, 0.71 vs 0.51 ms at 4000^2 x 6: the test costs more than the taps it saves)
+#pragma unroll
+      for (int p = 0; p < 8; p++) {
+        uint32_t d2 = min(best[p] & 0xffffu, best[p] >> 16);
+        d2 = d2 < capcode ? d2 : capcode;
+        d2p[p][c >> 1] |= d2 << (16 * (c & 1));
+      }
+    }
+  }
+#pragma unroll
+  for (int p = 0; p < 8; p++) {
+    const int x = xb + p;
+    if (x >= cols) break;
+    const bool unknown = (unk >> p) & 1u;
+    float out[8];
+#pragma unroll
+    for (int c = 0; c < 8; c++) out[c] = 0.f;
+#pragma unroll
+    for (int c = 0; c < 7; c++)
+      if (c < C) out[c] = unknown ? 0.f : dist_value((d2p[p][c >> 1] >> (16 * (c & 1))) & 0xffffu, resolution);   // top_down_map.cpp:312-317
+    if (TO_MAP) {
+      out[7] = unknown ? 0.f : 1.f;
+      float4* dst = reinterpret_cast<float4*>(map_px + (size_t)y * cols + x);
+      dst[0] = make_float4(out[0], out[1], out[2], out[3]);
+      dst[1] = make_float4(out[4], out[5], out[6], out[7]);
+    } else {
+#pragma unroll
+      for (int c = 0; c < 7; c++)
+        if (c < C) planar[(size_t)c * L + (size_t)x * rows + y] = out[c];
+    }
+  }
+}
+
 // cached distance layers (col-major) + mask -> MapPixel
 __global__ void k_dist_layers_to_map(const float* __restrict__ layers, const uint8_t* __restrict__ mask, int rows,
                                      int cols, int C, MapPixel* __restrict__ map_px) {
@@ -212,6 +314,22 @@ static int run_edt(tdr_ctx* ctx, const uint8_t* seed, int rows, int cols, int C,
   uint8_t* d_seg = d_g + ((L * (size_t)C + 255) / 256) * 256;
   dim3 vgrd((cols + 127) / 128, (rows + EDT_BAND - 1) / EDT_BAND);
   k_edt_vsweep<<<vgrd, 128, 0, ctx->stream>>>(seed, rows, cols, C, rcap, d_g, d_seg, segs);
+  // the packed row pass (16-bit lanes) wherever its window fits; TDR_EDT_IMPL=1 forces the scalar tap scan
+  const int R = (rcap + 3) / 4 * 4;
+  if ((R + 7) * (R + 7) <= 0x7fff && capcode <= 0x7fffu && ctx->edt_impl != 1) {
+    const size_t smem = (size_t)(2 * R + 24) * 4 + (size_t)C * (EDT_XT + 2 * R + 8) * 2;      // <= 21 KB (C <= 7, R <= 176)
+    dim3 rgrd((cols + EDT_XT - 1) / EDT_XT, rows);
+    if (to_map) {
+      k_edt_rows_dpx<true><<<rgrd, EDT_XT_THREADS, smem, ctx->stream>>>(seed, d_g, rows, cols, C, R, capcode, resolution,
+                                                                       ctx->map_px.as<MapPixel>(), nullptr);
+    } else {
+      k_edt_rows_dpx<false><<<rgrd, EDT_XT_THREADS, smem, ctx->stream>>>(seed, d_g, rows, cols, C, R, capcode, resolution, nullptr,
+                                                                              planar_out);
+    }
+    count_launch(ctx, 2);
+    TDR_CUDA(cudaGetLastError());
+    return TDR_OK;
+  }
   dim3 blk(32, 8), grd((cols + 31) / 32, (rows + 7) / 8);
   if (to_map)
     k_edt_horizontal<true><<<grd, blk, 0, ctx->stream>>>(seed, d_g, d_seg, segs, rows, cols, C, rcap, capcode,
