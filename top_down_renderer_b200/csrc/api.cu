@@ -181,6 +181,7 @@ int tdr_create(tdr_ctx** out, int device) {
   TDR_CUDA(cudaMallocHost(reinterpret_cast<void**>(&c->grid_key_pin), 32));
   memset(c->grid_key_pin, 0, 32);
   if (const char* e = getenv("TDR_EDT_IMPL")) c->edt_impl = atoi(e);
+  if (const char* e = getenv("TDR_EDT_BAND")) { int v = atoi(e); if (v >= 16 && v <= 1024) c->edt_band = v; }
   if (const char* e = getenv("TDR_GRID_SELF_ONLY")) c->grid_self_only = atoi(e) != 0;
   if (const char* e = getenv("TDR_GRID_STORE_HINT")) c->grid_store_hint = atoi(e) ? 1 : 0;
   *out = c;

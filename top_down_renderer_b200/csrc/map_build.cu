@@ -63,16 +63,16 @@ __global__ void k_geo_seeds(const uint8_t* __restrict__ seed, size_t n, int C, u
   gseed[i] = obstacle ? 2 : 1;
 }
 
-// pass V as two column sweeps per band of EDT_BAND rows (thread = column x band): a counter per class holds the
+// pass V as two column sweeps per band of `band` rows (thread = column x band): a counter per class holds the
 // distance to the last seed seen, so the cost does not depend on how rare a class is (a window scan per pixel only
 // stops when EVERY class has been found).  Down sweep writes the partial result, up sweep takes the minimum.
 // The band starts rcap rows early so that its counters are exact where they are used.  segmin[c][y][x/32] = min of
 // the final g over a 32-pixel segment lets pass H skip classes that have no seed anywhere near.
-static const int EDT_BAND = 128;
+// (segmin == nullptr: not wanted — the packed row pass does not use it.)
 __global__ void __launch_bounds__(128) k_edt_vsweep(const uint8_t* __restrict__ seed, int rows, int cols, int C, int rcap,
-                                                    uint8_t* __restrict__ g, uint8_t* __restrict__ segmin, int segs) {
+                                                    uint8_t* __restrict__ g, uint8_t* __restrict__ segmin, int segs, int band) {
   const int x = blockIdx.x * blockDim.x + threadIdx.x;
-  const int y_lo = blockIdx.y * EDT_BAND, y_hi = min(rows, y_lo + EDT_BAND) - 1;
+  const int y_lo = blockIdx.y * band, y_hi = min(rows, y_lo + band) - 1;
   const bool live = x < cols;
   const int xc = live ? x : cols - 1;
   const size_t L = (size_t)rows * cols;
@@ -102,8 +102,10 @@ __global__ void __launch_bounds__(128) k_edt_vsweep(const uint8_t* __restrict__ 
           if (v > (uint32_t)rcap) v = 255u;              // beyond the truncation window: "no seed"
           g[at] = (uint8_t)v;
         }
-        const uint32_t m = __reduce_min_sync(0xffffffffu, v);
-        if ((threadIdx.x & 31) == 0 && x < cols) segmin[((size_t)c * rows + y) * segs + (x >> 5)] = (uint8_t)m;
+        if (segmin) {                                    // kernel-uniform
+          const uint32_t m = __reduce_min_sync(0xffffffffu, v);
+          if ((threadIdx.x & 31) == 0 && x < cols) segmin[((size_t)c * rows + y) * segs + (x >> 5)] = (uint8_t)m;
+        }
       }
     }
   }
@@ -312,11 +314,13 @@ static int run_edt(tdr_ctx* ctx, const uint8_t* seed, int rows, int cols, int C,
   if (int e = ctx->edt_g.reserve(L * (size_t)C + seg_bytes + 256)) return e;
   uint8_t* d_g = ctx->edt_g.as<uint8_t>();
   uint8_t* d_seg = d_g + ((L * (size_t)C + 255) / 256) * 256;
-  dim3 vgrd((cols + 127) / 128, (rows + EDT_BAND - 1) / EDT_BAND);
-  k_edt_vsweep<<<vgrd, 128, 0, ctx->stream>>>(seed, rows, cols, C, rcap, d_g, d_seg, segs);
   // the packed row pass (16-bit lanes) wherever its window fits; TDR_EDT_IMPL=1 forces the scalar tap scan
   const int R = (rcap + 3) / 4 * 4;
-  if ((R + 7) * (R + 7) <= 0x7fff && capcode <= 0x7fffu && ctx->edt_impl != 1) {
+  const bool packed = (R + 7) * (R + 7) <= 0x7fff && capcode <= 0x7fffu && ctx->edt_impl != 1;
+  const int band = ctx->edt_band > 0 ? ctx->edt_band : 64;      // 128: 0.39 ms, 64: 0.36, 32: 0.35, 256: 0.67 at 4000^2 x 6
+  dim3 vgrd((cols + 127) / 128, (rows + band - 1) / band);
+  k_edt_vsweep<<<vgrd, 128, 0, ctx->stream>>>(seed, rows, cols, C, rcap, d_g, packed ? nullptr : d_seg, segs, band);
+  if (packed) {
     const size_t smem = (size_t)(2 * R + 24) * 4 + (size_t)C * (EDT_XT + 2 * R + 8) * 2;      // <= 21 KB (C <= 7, R <= 176)
     dim3 rgrd((cols + EDT_XT - 1) / EDT_XT, rows);
     if (to_map) {

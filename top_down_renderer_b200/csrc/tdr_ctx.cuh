@@ -228,6 +228,7 @@ struct tdr_ctx {
   int64_t grid_full_floats = 0;          // floats of the cost array proper: the mailbox sits at the next 256-byte boundary
   uint64_t grid_epoch = 0;               // exchanges done (all ranks in lock step): picks the mailbox slot
   unsigned long long* grid_key_pin = nullptr;   // pinned host word the exchange kernel writes the reduced key to
+  int edt_band = 0;                      // TDR_EDT_BAND: rows per column-sweep thread (default 64)
   int edt_impl = 0;                      // TDR_EDT_IMPL=1: scalar tap scan instead of the packed (DPX) row pass
   int grid_store_hint = 0;               // TDR_GRID_STORE_HINT=1: L2 evict-first policy on the cost stores
   bool grid_self_only = false;           // TDR_GRID_SELF_ONLY=1: store costs to the own array only (diagnostic)
