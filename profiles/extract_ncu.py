@@ -25,7 +25,19 @@ WANT = ["gpu__time_duration.sum", "dram__bytes_read.sum", "dram__bytes_write.sum
         "smsp__average_warps_issue_stalled_math_pipe_throttle_per_issue_active.ratio", "smsp__average_warps_issue_stalled_sleeping_per_issue_active.ratio",
         "smsp__average_warps_issue_stalled_dispatch_stall_per_issue_active.ratio", "smsp__average_warps_issue_stalled_not_selected_per_issue_active.ratio",
         "smsp__average_warps_issue_stalled_selected_per_issue_active.ratio", "smsp__average_warps_issue_stalled_drain_per_issue_active.ratio",
-        "smsp__average_warps_issue_stalled_imc_miss_per_issue_active.ratio", "smsp__average_warps_issue_stalled_tex_throttle_per_issue_active.ratio"]
+        "smsp__average_warps_issue_stalled_imc_miss_per_issue_active.ratio", "smsp__average_warps_issue_stalled_tex_throttle_per_issue_active.ratio",
+        # round 2: the L1 data pipe (what bounds the 16-byte-record gather), requests vs wavefronts vs sectors, integer tensor pipe
+        "l1tex__data_pipe_lsu_wavefronts.sum", "l1tex__data_pipe_lsu_wavefronts.sum.pct_of_peak_sustained_elapsed",
+        "l1tex__data_pipe_lsu_wavefronts_mem_lgds.sum", "l1tex__data_pipe_lsu_wavefronts_mem_shared.sum",
+        "l1tex__t_requests_pipe_lsu_mem_global_op_ld.sum", "l1tex__t_sectors_pipe_lsu_mem_global_op_ld.sum",
+        "l1tex__t_sectors_pipe_lsu_mem_global_op_ld_lookup_hit.sum", "l1tex__t_sectors_pipe_lsu_mem_global_op_st.sum",
+        "l1tex__data_pipe_tc_wavefronts_mem_shared.sum.pct_of_peak_sustained_elapsed",
+        "sm__pipe_tensor_cycles_active_realtime.avg.pct_of_peak_sustained_elapsed",
+        "sm__inst_executed.sum", "sm__inst_executed_pipe_lsu.sum", "sm__inst_executed_pipe_uniform.sum", "sm__inst_executed_pipe_alu.sum",
+        "sm__inst_executed_pipe_fma.sum", "smsp__inst_executed.avg.per_cycle_active", "sm__warps_active.avg.per_cycle_active",
+        "launch__occupancy_limit_registers", "launch__occupancy_limit_shared_mem", "launch__waves_per_multiprocessor",
+        "launch__shared_mem_per_block_dynamic", "lts__t_sectors_srcunit_tex_op_read.sum", "lts__t_sectors_srcunit_tex_op_read_lookup_hit.sum",
+        "lts__t_sectors_srcunit_tex_op_read_lookup_miss.sum"]
 
 
 def main(path):
@@ -36,8 +48,9 @@ def main(path):
         name = vals[hdr.index("Kernel Name")] if "Kernel Name" in hdr else "?"
         print(f"# kernel,{name.split('(')[0]}")
         for w in WANT:
-            if w in hdr:
-                i = hdr.index(w)
+            hits = [i for i, h in enumerate(hdr) if h == w or h.endswith("." + w)]     # some sections prefix the metric name
+            if hits:
+                i = hits[0]
                 print(f"{w},{units[i]},{vals[i]}")
 
 

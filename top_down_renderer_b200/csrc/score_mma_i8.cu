@@ -3,7 +3,7 @@
 // Reference: TopDownMapPolar::getLocalMap (src/top_down_map_polar.cpp:21-53), StateParticle::getCostForRot
 // (src/state_particle.cpp:112-155), StateParticle::computeWeight (:157-219).
 //
-// Why a second operand format (profiles/r02_gather_microbench.txt, profiles/r02_list_counters.md): the
+// Why a second operand format (profiles/r02_gather_microbench.txt, profiles/r02_score_list_wavefront_counters.csv): the
 // fp16 hi/lo kernel (score_mma_list.cu) reads one 32-byte record per (hypothesis, cell) and is bound by L1 wavefronts —
 // 24.9 per warp load measured, one per distinct 128-byte line inside a half warp (x ~1.2 for partly used lines), at
 // most one per clock and SM.  A 128-byte line of that layout holds 4 pixels.  Here a pixel is 16 bytes:
@@ -12,7 +12,7 @@
 // so a line holds 8 pixels of a map row and neighbouring hypotheses share lines twice as often; one 128-bit load per
 // (hypothesis, cell) — 1.9 records / clk / SM measured for warps whose lanes lie within 8 x 8 px (tools/tex_bench.cu),
 // against 1.5 for 256-bit loads of pixel pairs and 1.0 for the 32-byte records.  The kernel was ISSUE-bound on its
-// gather threads (78 instructions per record, profiles/r02_i8_ncu.md), so the index arithmetic is fixed point
+// gather threads (78 instructions per record, profiles/r02_SUMMARY.md), so the index arithmetic is fixed point
 // (tdr_math.cuh lattice_fixed) on a table pre-multiplied by scale * res * 4096 in constant memory — which needs ONE
 // scale for all hypotheses of a launch (FilterParams::fixed_scale; checked on the device).
 // Two cells make one K = 32 step of tcgen05.mma.kind::i8 (u8 x u8 -> s32, exact):
@@ -251,7 +251,7 @@ template <int T, int R, int F> struct I8Cfg {
 };
 
 // TEX: the second cell of every stage comes through the texture pipe instead of the LSU — the kernel is bound by L1
-// data-pipe wavefronts of its 128-bit loads (84 % busy, profiles/r02_i8_ncu.md) and the two front ends together deliver
+// data-pipe wavefronts of its 128-bit loads (84 % busy, profiles/r02_SUMMARY.md) and the two front ends together deliver
 // more records per clock than either alone (2.27 against 1.9, tools/tex_bench.cu)
 template <int T, int R, int F, bool TEX, bool BLK>
 __global__ void __launch_bounds__(128 * T * R + 64, I8Cfg<T, R, F>::kCtasPerSm) k_score_mma_i8(I8Params sp) {
