@@ -204,6 +204,7 @@ void tdr_destroy(tdr_ctx* c) {
   c->pin.release();
   c->uninit_dev.release();
   c->raw_weights.release();
+  c->ident_shifts.release();
   if (c->uninit_ev) cudaEventDestroy(c->uninit_ev);
   if (c->uninit_pin) cudaFreeHost(c->uninit_pin);
   if (c->map8_tex) cudaDestroyTextureObject((cudaTextureObject_t)c->map8_tex);

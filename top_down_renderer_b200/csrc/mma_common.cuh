@@ -255,6 +255,7 @@ struct BinParams {
   const float* centers;                                                       // grid mode
   long long n; float resolution; int rows, cols, st_shift, seg_shift, super_x, per_super, n_bins, morton;
   int select_init;          // particle mode: bin the particles WITH a heading (tracking) instead of those without (search)
+  const float* theta; int n_theta, shift_lo, shift_hi;   // shift_hi > 0: only particles whose heading maps to a row shift in [lo, hi)
 };
 __device__ __forceinline__ uint32_t spread_bits16(uint32_t v) {      // abcd -> 0a0b0c0d
   v &= 0xffffu;
@@ -266,6 +267,7 @@ __device__ __forceinline__ int bin_of(const BinParams& b, long long i) {
   if (b.centers) { x = b.centers[2 * i]; y = b.centers[2 * i + 1]; }
   else {
     if ((b.have_init[i] != 0) != (b.select_init != 0)) return -1;     // the other kind of particle: another launch
+    if (b.shift_hi > 0) { const int sh = rot_to_shift(b.theta[i], b.n_theta); if (sh < b.shift_lo || sh >= b.shift_hi) return -1; }
     float s = b.scale[i];
     x = TDR_FADD(TDR_FMUL(b.dx[i], s), b.init_x[i]); y = TDR_FADD(TDR_FMUL(b.dy[i], s), b.init_y[i]);
   }
@@ -412,7 +414,10 @@ static int sync_const_tab(tdr_ctx* ctx, int P) {
 }
 
 // spatial binning of the hypotheses -> ctx->perm (counting sort by super-tile, pixel row, column segment)
-static int build_perm(tdr_ctx* ctx, bool grid_mode, long long n_items, bool morton = false, bool select_init = false) {
+// shift_hi > 0 (tracking in passes): only the particles whose heading lies in that window of row shifts are listed; their
+// number is not known on the host — *count_dev (if given) receives the device word that holds it once the scatter ran
+static int build_perm(tdr_ctx* ctx, bool grid_mode, long long n_items, bool morton = false, bool select_init = false,
+                      int shift_lo = 0, int shift_hi = 0, const int** count_dev = nullptr) {
   if (grid_mode && ctx->perm_grid_n == n_items) return TDR_OK;       // resident centres, same map: the order still holds
   ctx->perm_grid_n = -1;
   tdr::Particles& pt = ctx->part[ctx->cur];
@@ -432,6 +437,7 @@ static int build_perm(tdr_ctx* ctx, bool grid_mode, long long n_items, bool mort
   bp.seg_shift = ctx->mma_seg_shift;
   bp.morton = morton ? 1 : 0;
   bp.select_init = select_init ? 1 : 0;
+  bp.theta = pt.theta.as<float>(); bp.n_theta = ctx->n_theta; bp.shift_lo = shift_lo; bp.shift_hi = shift_hi;
   if (morton) bp.seg_shift = 2;                   // (S/2)^2 Morton cells = S * (S >> 2) bins: the same count
   if (morton && bp.st_shift > 16) bp.st_shift = 16;
   bp.per_super = (1 << bp.st_shift) * ((1 << bp.st_shift) >> bp.seg_shift);
@@ -455,6 +461,7 @@ static int build_perm(tdr_ctx* ctx, bool grid_mode, long long n_items, bool mort
   count_launch(ctx, 5);
   TDR_CUDA(cudaGetLastError());
   if (grid_mode) ctx->perm_grid_n = n_items;
+  if (count_dev) *count_dev = d_counts + (bp.n_bins - 1);       // the last bin's cursor ends at the number of listed items
   return TDR_OK;
 }
 

@@ -415,7 +415,9 @@ int score_particles(tdr_ctx* ctx, float res) {
     bool tracked_by_mma = false;
     const long long n_init = pt.n - ctx->n_uninit;
     if (sp.n_shifts > 0 && (ctx->score_impl == 2 || (ctx->score_impl == 0 && n_init * ctx->count_scale >= 65536))) {
-      if (int e = score_mma(ctx, res, false, pt.n, 1.f, sp.shifts, ctx->search_shifts.data(), sp.n_shifts, &tracked_by_mma, true)) return e;
+      // the integer kernel in passes of 40 row shifts first (every particle gathered once); else the fp16 ring kernel
+      if (ctx->mma_kernel == 0 || ctx->mma_kernel == 3) { if (int e = score_mma_i8_track(ctx, res, &tracked_by_mma)) return e; }
+      if (!tracked_by_mma) { if (int e = score_mma(ctx, res, false, pt.n, 1.f, sp.shifts, ctx->search_shifts.data(), sp.n_shifts, &tracked_by_mma, true)) return e; }
     }
     ScoreParams st = sp;
     if (tracked_by_mma) st.only_if_bailed = reinterpret_cast<const int*>(ctx->scal.as<float>() + SC_MMA_BAILED);   // guarded fallback

@@ -98,10 +98,10 @@ static __global__ void k_build_map8(const MapPixel* __restrict__ map, size_t n, 
 
 // one scale for every hypothesis of the launch?  (min, max) of the scale bits over the particles still to be searched
 static __global__ void k_scale_range(const float* __restrict__ scale, const uint8_t* __restrict__ have_init, long long n,
-                                     uint32_t* __restrict__ range /* [min, max] of the (positive) float bits */) {
+                                     uint32_t* __restrict__ range /* [min, max] of the (positive) float bits */, int want_init) {
   uint32_t lo = 0xffffffffu, hi = 0u;
   for (long long i = (long long)blockIdx.x * blockDim.x + threadIdx.x; i < n; i += (long long)gridDim.x * blockDim.x)
-    if (!have_init[i]) { const uint32_t b = __float_as_uint(scale[i]); lo = min(lo, b); hi = max(hi, b); }
+    if ((have_init[i] != 0) == (want_init != 0)) { const uint32_t b = __float_as_uint(scale[i]); lo = min(lo, b); hi = max(hi, b); }
   for (int o = 16; o > 0; o >>= 1) { lo = min(lo, __shfl_xor_sync(0xffffffffu, lo, o)); hi = max(hi, __shfl_xor_sync(0xffffffffu, hi, o)); }
   if ((threadIdx.x & 31) == 0 && lo <= hi) { atomicMin(range, lo); atomicMax(range + 1, hi); }
 }
@@ -228,6 +228,8 @@ struct I8Params {
   const float2* tab_g;                // the constant table's global twin (divergent indices: the epilogue's lookups): [0] gathered cells [1] skipped cells [2] stages
   const uint4* bop;
   const int* perm; long long n_work;
+  const int* n_work_dev;              // != nullptr: the number of listed hypotheses lives on the device (tracking passes)
+  int track, track_lo, n_theta;       // track: every particle keeps the cost of ITS heading's row shift, list position shift - track_lo
   const float *init_x, *init_y, *dx, *dy; float* theta; const float* scale; uint8_t* have_init; float* weights;
   int force_on_map; float map_w, map_h; int scale_gate; double scale_lo, scale_hi; float regularization;
   const float* thetas; int n_shifts;
@@ -282,7 +284,8 @@ __global__ void __launch_bounds__(128 * T * R + 64, I8Cfg<T, R, F>::kCtasPerSm) 
   const uint32_t tmem_base = *s_tmem;
 
   const long long per_batch = 128 * T;
-  const long long n_batches = (sp.n_work + per_batch - 1) / per_batch;
+  const long long n_work = sp.n_work_dev ? (long long)*sp.n_work_dev : sp.n_work;
+  const long long n_batches = (n_work + per_batch - 1) / per_batch;
   const int K_ITERS = sp.plan[2];
   uint32_t local_batch = 0;
 
@@ -296,7 +299,7 @@ __global__ void __launch_bounds__(128 * T * R + 64, I8Cfg<T, R, F>::kCtasPerSm) 
     for (long long batch = blockIdx.x; batch < n_batches; batch += gridDim.x, local_batch++) {
       const long long slot = batch * per_batch + (tid % (128 * T));
       long long i = -1;
-      if (slot < sp.n_work) i = sp.perm ? (long long)sp.perm[slot] : slot;
+      if (slot < n_work) i = sp.perm ? (long long)sp.perm[slot] : slot;
       float cx = 0.f, cy = 0.f;
       bool active = false, gated = false;
       if (i >= 0) {
@@ -388,6 +391,9 @@ __global__ void __launch_bounds__(128 * T * R + 64, I8Cfg<T, R, F>::kCtasPerSm) 
       }
       const bool unknown = (double)TDR_FDIV((float)known, (float)sp.P) < 0.5;                    // :117-120
       float best = 3.402823466e+38f, best_theta = 0.f;                                           // :193-204
+      // tracking: the one column of this particle's heading (state_particle.cpp:207-210); NaN stays NaN there
+      const int my_col = (sp.track && i >= 0) ? rot_to_shift(sp.theta[i], sp.n_theta) - sp.track_lo : -1;
+      float my_cost = 0.f;
       uint32_t vh[8], vl[8], vn[8];
 #pragma unroll 1
       for (int ch = 0; ch * 8 < S; ch++) {
@@ -401,11 +407,14 @@ __global__ void __launch_bounds__(128 * T * R + 64, I8Cfg<T, R, F>::kCtasPerSm) 
           if (s < S) {
             const float num = fmaf((float)(int)vh[j], 256.f, (float)(int)vl[j]);
             const float cost = unknown ? __int_as_float(0x7fc00000) : TDR_FDIV(TDR_FMUL(num, sp.q001), (float)(int)vn[j]);   // :137,154
-            if (cost < best) { best = cost; best_theta = sp.thetas[s]; }
+            if (sp.track) { if (s == my_col) my_cost = cost; }
+            else if (cost < best) { best = cost; best_theta = sp.thetas[s]; }
           }
         }
       }
-      if (i >= 0) {
+      if (i >= 0 && sp.track) {
+        sp.weights[i] = gated ? 0.f : (float)(1.0 / (double)TDR_FADD(my_cost, sp.regularization));   // :212
+      } else if (i >= 0) {
         if (gated) sp.weights[i] = 0.f;
         else {
           sp.theta[i] = best_theta;
@@ -519,20 +528,27 @@ static int build_map8(tdr_ctx* ctx, float q, bool blocked, const uint4** out, Ge
 
 // returns TDR_OK and sets *used = true when the integer tensor-core path was launched (it may still leave the work to
 // the guarded CUDA-core launch behind it: scan counts above 255, decided on the device)
-int score_mma_i8(tdr_ctx* ctx, float res, const int32_t* dev_shifts, int n_shifts, bool* used) {
+// One launch of the integer kernel.  Search (track_pass < 0): the particles without a heading against the candidate
+// list.  Tracking pass p >= 0: the particles whose heading maps to a row shift in [shift_lo, shift_lo + n_shifts), against
+// exactly those shifts (dev_shifts = shift_lo, shift_lo + 1, ...); each keeps the column of its own shift.
+static int launch_i8(tdr_ctx* ctx, float res, const int32_t* dev_shifts, int n_shifts, int track_pass, int shift_lo, bool* used) {
   *used = false;
+  const bool track = track_pass >= 0;
   float q = 0.f;
   if (!i8_usable(ctx, n_shifts, &q)) return TDR_OK;
   const int P = ctx->n_theta * ctx->n_r;
   if (((P + 3) & ~3) + 4 > MMA_TAB_MAX) return TDR_OK;         // gathered (+ padding) and skipped cells share the constant table
   // the previous scan's maximum count predicts whether this one fits a byte (the device check decides)
-  if (ctx->scan_max_pending && cudaEventQuery(ctx->scan_max_ev) == cudaSuccess) { ctx->scan_max_seen = *ctx->scan_max_pin; ctx->scan_max_pending = false; }
-  if (ctx->mma_i8 != 2 && ctx->scan_max_seen > I8_MAX_COUNT) return TDR_OK;
+  // (later tracking passes do not look again: the passes stand or fall together, the device guard is the same for all)
+  if (track_pass <= 0) {
+    if (ctx->scan_max_pending && cudaEventQuery(ctx->scan_max_ev) == cudaSuccess) { ctx->scan_max_seen = *ctx->scan_max_pin; ctx->scan_max_pending = false; }
+    if (ctx->mma_i8 != 2 && ctx->scan_max_seen > I8_MAX_COUNT) return TDR_OK;
+  }
   const int P_cap = (P + 3) & ~3, max_stages = P_cap / 2;
   if (int e = ctx->scan_op.reserve((size_t)max_stages * I8_N * 32 + (size_t)(PLAN_HDR + 2 * P_cap) * 4)) return e;
   int* d_plan = reinterpret_cast<int*>(ctx->scan_op.as<unsigned char>() + (size_t)max_stages * I8_N * 32);
   int* d_max = reinterpret_cast<int*>(ctx->scal.as<float>() + SC_MMA_MAXCOUNT);
-  TDR_CUDA(cudaMemsetAsync(d_max, 0, 8, ctx->stream));       // max count, "tensor-core kernel bailed out" flag
+  if (track_pass <= 0) TDR_CUDA(cudaMemsetAsync(d_max, 0, 8, ctx->stream));       // max count, "tensor-core kernel bailed out" flag (one verdict for all passes)
   {
     k_plan_cells<<<1, 1024, 0, ctx->stream>>>(ctx->scan_img.as<float>(), ctx->C, ctx->n_theta, ctx->n_r, dev_shifts, n_shifts,
                                               ctx->mma_skip_rings, d_plan);
@@ -545,7 +561,9 @@ int score_mma_i8(tdr_ctx* ctx, float res, const int32_t* dev_shifts, int n_shift
     TDR_CUDA(cudaEventRecord(ctx->scan_max_ev, ctx->stream));
     ctx->scan_max_pending = true;
   }
-  if (int e = build_perm(ctx, false, ctx->part[ctx->cur].n, ctx->mma_sort == 1)) return e;
+  const int* count_dev = nullptr;
+  if (track) { if (int e = build_perm(ctx, false, ctx->part[ctx->cur].n, ctx->mma_sort == 1, true, shift_lo, shift_lo + n_shifts, &count_dev)) return e; }
+  else if (int e = build_perm(ctx, false, ctx->part[ctx->cur].n, ctx->mma_sort == 1)) return e;
   tdr::Particles& pt = ctx->part[ctx->cur];
   // the lattice offsets for this launch's scale and radial resolution, x 4096, into constant memory; the scale comes
   // from the particles themselves (one value for all of them, else the kernel leaves the search to the CUDA cores)
@@ -554,7 +572,7 @@ int score_mma_i8(tdr_ctx* ctx, float res, const int32_t* dev_shifts, int n_shift
     const uint32_t init_range[2] = {0xffffffffu, 0u};
     TDR_CUDA(cudaMemcpyAsync(d_range, init_range, 8, cudaMemcpyHostToDevice, ctx->stream));
     const int blocks = (int)((pt.n + 1023) / 1024 < ctx->sm_count * 4 ? (pt.n + 1023) / 1024 : ctx->sm_count * 4);
-    k_scale_range<<<blocks < 1 ? 1 : blocks, 256, 0, ctx->stream>>>(pt.scale.as<float>(), pt.have_init.as<uint8_t>(), pt.n, d_range);
+    k_scale_range<<<blocks < 1 ? 1 : blocks, 256, 0, ctx->stream>>>(pt.scale.as<float>(), pt.have_init.as<uint8_t>(), pt.n, d_range, track ? 1 : 0);
     if (int e = ctx->tab_scaled.reserve((size_t)(P_cap + 4) * 8)) return e;
     k_scale_tab4096<<<(P_cap + 4 + 255) / 256, 256, 0, ctx->stream>>>(ctx->tab.as<float2>(), P, d_plan, d_range, res,
                                                                        ctx->tab_scaled.as<float2>(), d_max + 1);
@@ -574,7 +592,9 @@ int score_mma_i8(tdr_ctx* ctx, float res, const int32_t* dev_shifts, int n_shift
   sp.tab_g = ctx->tab_scaled.as<float2>();
   sp.tex = ctx->map8_tex;
   sp.maxcount = d_max; sp.bailed = d_max + 1;
-  sp.n_work = ctx->n_uninit;
+  sp.n_work = track ? pt.n - ctx->n_uninit : ctx->n_uninit;      // tracking: an upper bound for the grid size; the kernel reads the real count
+  sp.n_work_dev = track ? count_dev : nullptr;
+  sp.track = track ? 1 : 0; sp.track_lo = shift_lo; sp.n_theta = ctx->n_theta;
   sp.init_x = pt.init_x.as<float>(); sp.init_y = pt.init_y.as<float>(); sp.dx = pt.dx.as<float>(); sp.dy = pt.dy.as<float>();
   sp.theta = pt.theta.as<float>(); sp.scale = pt.scale.as<float>(); sp.have_init = pt.have_init.as<uint8_t>();
   sp.weights = ctx->weights.as<float>();
@@ -619,6 +639,45 @@ int score_mma_i8(tdr_ctx* ctx, float res, const int32_t* dev_shifts, int n_shift
 #undef I8_OPTIN
   count_launch(ctx);
   TDR_CUDA(cudaGetLastError());
+  *used = true;
+  return TDR_OK;
+}
+
+int score_mma_i8(tdr_ctx* ctx, float res, const int32_t* dev_shifts, int n_shifts, bool* used) {
+  return launch_i8(ctx, res, dev_shifts, n_shifts, -1, 0, used);
+}
+
+// Tracking LARGE particle sets (steady-state global localisation: 1e6 particles that all have a heading): the heading of
+// a particle selects ONE of the n_theta row shifts, a different one per particle, so a tile of 128 particles needs a
+// whole window of shifts.  The particles are binned by their shift into windows of 40 (the operand's candidate rows)
+// and every window is one launch of the search kernel in which each particle keeps its own column: together the passes
+// gather every particle's cells once — half the time of the fp16 ring kernel's all-shift pass
+// (state_particle.cpp:207-212).  *used = false: not this kernel's case, nothing was launched.
+int score_mma_i8_track(tdr_ctx* ctx, float res, bool* used) {
+  *used = false;
+  float q = 0.f;
+  const int n_theta = ctx->n_theta;
+  if (n_theta < 1 || !i8_usable(ctx, n_theta < I8_S_MAX ? n_theta : I8_S_MAX, &q)) return TDR_OK;
+  if (ctx->ident_shifts_n != n_theta) {
+    std::vector<int32_t> h((size_t)n_theta);
+    for (int k = 0; k < n_theta; k++) h[(size_t)k] = k;
+    if (int e = ctx->ident_shifts.reserve((size_t)n_theta * 4)) return e;
+    TDR_CUDA(cudaMemcpyAsync(ctx->ident_shifts.p, h.data(), (size_t)n_theta * 4, cudaMemcpyHostToDevice, ctx->stream));
+    TDR_CUDA(cudaStreamSynchronize(ctx->stream));           // h goes out of scope; once per table
+    ctx->ident_shifts_n = n_theta;
+  }
+  int pass = 0;
+  for (int lo = 0; lo < n_theta; lo += I8_S_MAX, pass++) {
+    const int S = n_theta - lo < I8_S_MAX ? n_theta - lo : I8_S_MAX;
+    bool u = false;
+    if (int e = launch_i8(ctx, res, ctx->ident_shifts.as<int32_t>() + lo, S, pass, lo, &u)) return e;
+    if (!u) {
+      // a pass that declines after an earlier one ran would leave some particles unscored: the preconditions are the same
+      // for every pass (operand format, table size, predicted scan maximum), so only the first can decline
+      TDR_REQUIRE(pass == 0, TDR_ESTATE, "integer tracking pass %d declined after earlier passes ran", pass);
+      return TDR_OK;
+    }
+  }
   *used = true;
   return TDR_OK;
 }
