@@ -154,9 +154,18 @@ class CpuArm:
         self.thetas, self.shifts = orc.search_list(N_THETA)
         self.fp = orc.make_params(C, regularization=0.7, map_width=wl["side"], map_height=wl["side"])
         self.u = orc.uniform_draw(SEED)
+        self._bin_layers, self._geo = bl, None
 
-    def step(self, lo, n):
-        """one reference update on particles [lo, lo+n): render + score (all host threads) + normalise + resample"""
+    def geo_layers(self):
+        """distance fields of the two geometric layers (getGeoRasterMap): what the reference gathers per particle and
+        never uses (state_particle.cpp:189) — only the "literal" CPU figure pays for it"""
+        if self._geo is None:
+            self._geo, _ = self.orc.compute_dists(self.orc.geo_raster(self._bin_layers), 1.0)
+        return self._geo
+
+    def step(self, lo, n, literal=False):
+        """one reference update on particles [lo, lo+n): render + score (all host threads) + normalise + resample.
+        literal: with the unused per-particle geo gather of state_particle.cpp:189 kept"""
         orc, wl, inp = self.orc, self.wl, self.inp
         if wl.get("grid"):
             from top_down_renderer_b200 import synth
@@ -173,7 +182,7 @@ class CpuArm:
         t0 = time.perf_counter()
         scan = orc.render_polar(inp["pts"], wl["res"], ANG_RES, N_THETA, N_R, inp["lut"], wl["C"])
         w = orc.score_all(st, self.fp, self.layers, self.mask, 1.0, self.tab, N_THETA, N_R, scan, wl["res"],
-                          self.thetas, self.shifts, n_threads=self.cores)
+                          self.thetas, self.shifts, geo_layers=self.geo_layers() if literal else None, n_threads=self.cores)
         wn, _, _ = orc.normalize(w, ld)
         orc.resample_fast(wn, self.u, n)
         return time.perf_counter() - t0
@@ -510,6 +519,21 @@ def measure_particles(args, wl, workload_name, rank, world, local, steps, warmup
                                "sample": f"{reps} update(s) of {n_s} of the {n} particles (x{wl['shifts']} shifts) incl. scan render, "
                                          f"normalise, O(N) resample; oracle/tdr_oracle.cpp (g++ -O2, no -march), "
                                          f"{arm.cores} std::threads"}
+        # BASELINE.md section 5's two figures: "tidy" is the one above (the unused geo gather removed, O(N) resampler);
+        # "literal" keeps the geo gather per particle and the reference's O(N*M) resampler, the latter timed at 1e4 x 1e4
+        # and extrapolated quadratically to this workload's N = M (labelled as such)
+        arm.geo_layers()
+        tl = sum(arm.step(0, n_s, literal=True) for _ in range(reps))
+        m_lit = min(n, 10_000)
+        w_lit = np.full(m_lit, 1.0 / m_lit, dtype=np.float32)
+        t0 = time.perf_counter()
+        arm.orc.resample_literal(w_lit, arm.u, m_lit)
+        t_res = time.perf_counter() - t0
+        out["cpu_baseline"]["tidy_value"] = out["cpu_baseline"]["value"]
+        out["cpu_baseline"]["literal_value"] = n_s * wl["shifts"] * reps / tl
+        out["cpu_baseline"]["literal_resample"] = {"measured_s": t_res, "at": [m_lit, m_lit],
+                                                   "extrapolated_s_at_workload": t_res * (n / m_lit) ** 2,
+                                                   "note": "particle_filter.cpp:174-185 is O(N*M) on one thread; extrapolated, not run"}
     elif rank == 0:
         out["cpu_baseline"] = None
     if flt is not None and hasattr(flt, "close"):

@@ -5,7 +5,7 @@
  * This is the drop-in boundary: the reference's TopDownMap / TopDownMapPolar /
  * ScanRenderer / ScanRendererPolar / ParticleFilter classes keep their
  * declarations and become thin adapters over these entry points (see
- * INTEGRATION.md and top_down_renderer_b200/host/tdr_host.hpp).  Plain pointers and
+ * INTEGRATION.md and top_down_renderer_b200/adapters/).  Plain pointers and
  * sizes only; caller-owned host buffers, library-owned device buffers.
  *
  * Conventions

@@ -22,7 +22,7 @@ def _have_gpu():
 
 # run last: the GPU tests whose newest checks were written in a session without GPU access (proven there on the CPU
 # stand-in / a dry run only), so that with `-x` a surprise in them cannot hide the long-standing parity tests
-_LAST = ("tests/test_gpu_vs_reference.py", "tests/test_host_cpp.py::test_host_mirror_step_matches_oracle",
+_LAST = ("tests/test_gpu_vs_reference.py",
          "tests/test_adapters.py::test_scan_renderer_adapters_on_the_device", "tests/test_adapters.py::test_map_adapters_on_the_device",
          "tests/test_adapters.py::test_filter_adapters_on_the_device",
          "tests/test_adapters.py::test_map_adapters_gathers_at_half_resolution_on_the_device")

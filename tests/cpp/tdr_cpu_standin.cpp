@@ -1,12 +1,12 @@
-// tdr_cpu_standin.cpp — TEST INFRASTRUCTURE ONLY: the subset of the C ABI (include/tdr.h) that the C++ host mirror
-// (top_down_renderer_b200/host/tdr_host.hpp) calls, answered by the CPU oracle (oracle/tdr_oracle.cpp).
+// tdr_cpu_standin.cpp — TEST INFRASTRUCTURE ONLY: the subset of the C ABI (include/tdr.h) that the adapters
+// (top_down_renderer_b200/adapters/*.cpp) call, answered by the CPU oracle (oracle/tdr_oracle.cpp).
 //
-// It exists so that the HOST logic of the mirror classes — the RNG streams of initializeParticles / propagate /
-// update, the map-centre shift of updateMap, freezeScale, the map cache files — can be exercised by the
-// `-m "not gpu"` suite and so that the checks of the GPU test (tests/test_host_cpp.py) are themselves proven on a
-// run whose every number comes from the oracle.  It is built into tests/cpp/host_demo_cpu only; the package, the
-// product library libtdr_b200.so, bench.py and smoke() never see it, and libtdr_b200.so keeps failing with
-// TDR_ENOGPU when no device is usable.
+// It exists so that the HOST logic of the adapter classes — the RNG streams of initializeParticles / propagate /
+// update, the lazy host mirror, the map-centre shift of updateMap, freezeScale, the map cache files — can be exercised
+// by the `-m "not gpu"` suite (tests/test_adapters.py) and so that the checks of the GPU tests are themselves proven on
+// a run whose every number comes from the oracle.  It is linked into the adapters' CPU test library only (oracle/Makefile,
+// `_adapters`); the package, the product library libtdr_b200.so, bench.py and smoke() never see it, and
+// libtdr_b200.so keeps failing with TDR_ENOGPU when no device is usable.
 #include <math.h>
 #include <algorithm>
 #include <cmath>

@@ -632,6 +632,8 @@ static int launch_i8(tdr_ctx* ctx, float res, const int32_t* dev_shifts, int n_s
     case 224: TDR_LAUNCH_I8(3, 2, 2, 4); break;
     case 233: TDR_LAUNCH_I8(4, 2, 3, 3); break;
     case 141: TDR_LAUNCH_I8(5, 1, 4, 1); break;
+    case 151: TDR_LAUNCH_I8(8, 1, 5, 1); break;
+    case 161: TDR_LAUNCH_I8(9, 1, 6, 1); break;
     case 231: TDR_LAUNCH_I8(6, 2, 3, 1); break;
     default: TDR_LAUNCH_I8(7, 2, 3, 2); break;
   }
