@@ -30,8 +30,12 @@
 
 namespace tdr {
 
-static const int I8_N = 128;              // accumulator columns per tile
-static const int I8_S_MAX = 40;           // candidate shifts: 3 S + 1 <= 128 with the blocks on multiples of 8 columns
+static const int I8_S_MAX = 40;           // candidate shifts per launch
+static const int I8_NH = 96;              // rows of the scan block = accumulator columns of the hi MMA: [0, 40) class counts, [48, 88) class-summed counts, 88 the probe
+static const int I8_NL = 48;              // accumulator columns of the lo MMA (rows [0, 48) of the same block: counts, then zeros)
+static const int I8_NORM0 = 48, I8_PROBE = 88;
+static const int I8_ACC = I8_NH + I8_NL;  // accumulator columns per tile
+static const int I8_CELLS = 4;            // lattice cells per pipeline stage = per K = 32 step (8 bytes each)
 static const int I8_MAX_COUNT = 255;
 static const int PLAN_HDR = 4;            // ints in front of the cell lists of a scan plan (k_plan_cells)
 
@@ -88,10 +92,11 @@ static __global__ void k_build_map8(const MapPixel* __restrict__ map, size_t n, 
       x = fminf(fmaxf(x, 0.f), 65535.f);
       q = __float2uint_rn(x);
     }
-    // bytes 2k (hi), 2k + 1 (lo)
-    w[k >> 1] |= ((q >> 8) | ((q & 0xffu) << 8)) << ((k & 1) * 16);
+    // byte k: hi, byte 8 + k: lo
+    w[k >> 2] |= (q >> 8) << ((k & 3) * 8);
+    w[2 + (k >> 2)] |= (q & 0xffu) << ((k & 3) * 8);
   }
-  if (v[7] != 0.f) w[3] |= 1u << 16;            // byte 14: known
+  if (v[7] != 0.f) w[1] |= 1u << 24;            // byte 7: known
   const uint32_t r = (uint32_t)(i / cols), c = (uint32_t)(i % cols);
   out[blocked ? map8_index<true>(r, c, pitch) : i] = make_uint4(w[0], w[1], w[2], w[3]);
 }
@@ -112,7 +117,7 @@ static __global__ void k_scale_tab4096(const float2* __restrict__ tab, int P, co
   const int j = blockIdx.x * blockDim.x + threadIdx.x;
   const int P_cap = (P + 3) & ~3;
   if (j == 0 && range[0] != range[1]) *bailed = 1;           // mixed scales (or negative / NaN bits): not this kernel's case
-  const int n_gather = 2 * plan[2];
+  const int n_gather = I8_CELLS * plan[2];
   if (j >= n_gather + plan[1]) return;
   const float scale = __uint_as_float(range[0]);
   const int p = j < n_gather ? plan[PLAN_HDR + j] : plan[PLAN_HDR + P_cap + (j - n_gather)];
@@ -126,7 +131,7 @@ static __global__ void k_scale_tab4096(const float2* __restrict__ tab, int P, co
 // beyond the sensor's range, and most of the sparse outer ones.  Only the "mostly unknown" test
 // (state_particle.cpp:117-120) still needs the known flags of the skipped cells: the kernel's epilogue counts them
 // exactly, and only for the hypotheses whose answer the gathered cells leave open.
-// plan: [0] gathered cells  [1] skipped cells  [2] stages (2 cells each, >= 1)  [3] unused | gathered[P_cap] | skipped[P_cap]
+// plan: [0] gathered cells  [1] skipped cells  [2] stages (4 cells each, >= 1)  [3] unused | gathered[P_cap] | skipped[P_cap]
 static __global__ void __launch_bounds__(1024) k_plan_cells(const float* __restrict__ img, int C, int n_theta, int n_r,
                                                             const int32_t* __restrict__ shifts, int S, int skip_on, int* __restrict__ plan) {
   __shared__ float s_tot[MMA_TAB_MAX];
@@ -178,47 +183,51 @@ static __global__ void __launch_bounds__(1024) k_plan_cells(const float* __restr
 #pragma unroll
   for (int q = 0; q < 4; q++) { const int p = threadIdx.x * 4 + q; if (p < P && !live[q]) skp[dpos++] = p; }
   for (int j = total + threadIdx.x; j < P_cap; j += blockDim.x) act[j] = -1;            // padding of the last stage
-  if (threadIdx.x == 0) { plan[0] = total; plan[1] = total_dead; plan[2] = total > 0 ? (total + 1) / 2 : 1; plan[3] = 0; }
+  if (threadIdx.x == 0) { plan[0] = total; plan[1] = total_dead; plan[2] = total > 0 ? (total + I8_CELLS - 1) / I8_CELLS : 1; plan[3] = 0; }
 }
 
-// scan operand, per stage k (cells act[2k], act[2k + 1]): [kc = 2][n = N][16 B] (K-major canonical layout, LBO = N*16,
-// SBO = 128); chunk kc holds the 16 K slots of the stage's cell kc.  One thread per (stage, n).
+// scan operand, per stage k (cells act[4k .. 4k + 3]): [kc = 2][n = I8_NH][16 B] (K-major canonical layout, LBO = I8_NH*16,
+// SBO = 128); chunk kc holds cells 2 kc and 2 kc + 1 of the stage, 8 K slots (bytes) each — the slots of a record HALF:
+// class 0..6, then the known byte (hi half) / zero (lo half).  Row s < S: the class counts of the scan cell the lattice
+// cell meets under candidate shift s (slots 0..6); row 48 + s: their sum at slot 7; row 88: 1 at slot 7.  The hi MMA
+// multiplies all 96 rows with the hi halves (-> Xhi, norm, number of known cells), the lo MMA rows [0, 48) with the lo
+// halves (-> Xlo; rows 40..47 are zero).  One thread per (stage, n).
 static __global__ void k_build_scan_operand_i8(const float* __restrict__ img, int C, int n_theta, int P, const int* __restrict__ plan,
                                                const int32_t* __restrict__ shifts, int S, uint4* __restrict__ out,
                                                int* __restrict__ maxcount) {
   const long long id = (long long)blockIdx.x * blockDim.x + threadIdx.x;
   const int n_stages = plan[2];
-  if (id >= (long long)n_stages * I8_N) return;
-  const int k = (int)(id / I8_N), n = (int)(id - (long long)k * I8_N);
+  if (id >= (long long)n_stages * I8_NH) return;
+  const int k = (int)(id / I8_NH), n = (int)(id - (long long)k * I8_NH);
   const int* act = plan + PLAN_HDR;
-  uint4* stage = out + (size_t)k * I8_N * 2;
+  uint4* stage = out + (size_t)k * I8_NH * 2;
+  const int kind = n < I8_S_MAX ? 0 : (n >= I8_NORM0 && n < I8_NORM0 + I8_S_MAX) ? 1 : n == I8_PROBE ? 2 : 3;
+  const int s = kind == 0 ? n : n - I8_NORM0;
 #pragma unroll
-  for (int j = 0; j < 2; j++) {
-    const int p = act[2 * k + j];
+  for (int kc = 0; kc < 2; kc++) {
     uint32_t w[4] = {0u, 0u, 0u, 0u};
-    const int s = n % I8_S_MAX, kind = n / I8_S_MAX;                     // row blocks of I8_S_MAX: 0 hi, 1 lo, 2 norm; then the probe
-    if (p >= 0 && (n == 3 * I8_S_MAX || (kind < 3 && s < S))) {
-      if (n == 3 * I8_S_MAX) w[3] = 1u << 16;                           // probe row: counts the known cells
-      else {
-        const int r = p / n_theta, th = p - r * n_theta;
-        int t2 = th + shifts[s];
-        t2 %= n_theta; if (t2 < 0) t2 += n_theta;
-        const int cell = r * n_theta + t2;                              // scan row (theta + shift) pairs with map row theta
-        float tot = 0.f;
-        for (int c = 0; c < C; c++) {
-          const float v = img[(size_t)c * P + cell];
-          tot += v;
-          const uint32_t u = (uint32_t)fminf(fmaxf(v, 0.f), 255.f);
-          if (kind == 0) w[c >> 1] |= u << ((c & 1) * 16);              // byte 2c
-          else if (kind == 1) w[c >> 1] |= u << ((c & 1) * 16 + 8);     // byte 2c + 1
-        }
-        if (kind == 2) {
-          w[3] = (uint32_t)fminf(fmaxf(tot, 0.f), 255.f) << 16;         // byte 14
-          if (s == 0) atomicMax(maxcount, (int)fminf(tot, 1e9f));       // every non-empty scan cell X is met at shift 0 by the gathered cell X - shift[0]: the max over all counts in play
-        }
+#pragma unroll
+    for (int h = 0; h < 2; h++) {
+      const int p = act[I8_CELLS * k + 2 * kc + h];
+      if (p < 0 || kind == 3 || (kind < 2 && s >= S)) continue;
+      if (kind == 2) { w[2 * h + 1] = 1u << 24; continue; }             // probe row: counts the known cells
+      const int r = p / n_theta, th = p - r * n_theta;
+      int t2 = th + shifts[s];
+      t2 %= n_theta; if (t2 < 0) t2 += n_theta;
+      const int cell = r * n_theta + t2;                                // scan row (theta + shift) pairs with map row theta
+      float tot = 0.f;
+      for (int c = 0; c < C; c++) {
+        const float v = img[(size_t)c * P + cell];
+        tot += v;
+        const uint32_t u = (uint32_t)fminf(fmaxf(v, 0.f), 255.f);
+        if (kind == 0) w[2 * h + (c >> 2)] |= u << ((c & 3) * 8);       // slot c
+      }
+      if (kind == 1) {
+        w[2 * h + 1] = (uint32_t)fminf(fmaxf(tot, 0.f), 255.f) << 24;   // slot 7
+        if (s == 0) atomicMax(maxcount, (int)fminf(tot, 1e9f));         // every non-empty scan cell X is met at shift 0 by the gathered cell X - shift[0]: the max over all counts in play
       }
     }
-    stage[j * I8_N + n] = make_uint4(w[0], w[1], w[2], w[3]);
+    stage[kc * I8_NH + n] = make_uint4(w[0], w[1], w[2], w[3]);
   }
 }
 
@@ -235,6 +244,7 @@ struct I8Params {
   const float* thetas; int n_shifts;
   unsigned long long tex;           // the same records as a pitch-linear 2-D texture (border = zero record); 0: not used
   float q001;                       // 0.01 * q: accumulator units -> cost
+  int diag_half_b;                  // TDR_I8_DIAG_HALF_B=1: stream only half of every operand block — a TIMING probe, results are wrong
   const int* maxcount; int* bailed; // device-side preconditions: scan counts fit a byte, one scale for all hypotheses
 };
 
@@ -242,11 +252,11 @@ struct I8Params {
 // F = stages every gather thread keeps in flight (2 cells = two 128-bit loads each)
 template <int T, int R, int F> struct I8Cfg {
   static const int kThreads = 128 * T * R + 64;
-  static const int kBBytes = I8_N * 32;                    // scan operand of one stage (2 cells)
-  static const int kACols = T * 8;                         // TMEM columns of one stage of A
+  static const int kBBytes = I8_NH * 32;                   // scan operand of one stage (4 cells)
+  static const int kACols = T * 16;                        // TMEM columns of one stage of A: per tile 8 (hi halves of 4 cells) + 8 (lo halves)
   static const int kCtasPerSm = T == 1 ? 2 : 1;            // one tile per CTA leaves room for two CTAs (two pipelines) per SM
   static const int kTmemCols = 512 / kCtasPerSm;
-  static const int kStagesMax = (kTmemCols - T * I8_N) / kACols;
+  static const int kStagesMax = (kTmemCols - T * I8_ACC) / kACols;
   static const int kStages = kStagesMax > 16 ? 16 : kStagesMax;
   static const int kSmem = kStages * kBBytes + 512;        // + barriers (2 * kStages + 1) and the TMEM base word
   static_assert(kStages >= R * F, "every stage a thread has in flight needs its own slot");
@@ -258,7 +268,6 @@ template <int T, int R, int F> struct I8Cfg {
 template <int T, int R, int F, bool TEX, bool BLK>
 __global__ void __launch_bounds__(128 * T * R + 64, I8Cfg<T, R, F>::kCtasPerSm) k_score_mma_i8(I8Params sp) {
   using Cfg = I8Cfg<T, R, F>;
-  constexpr int N = I8_N;
   constexpr int GW = 4 * T * R;        // gather warps
   constexpr int NS = Cfg::kStages;
   if (*sp.maxcount > I8_MAX_COUNT || *sp.bailed) {   // grid-uniform, before anything is allocated
@@ -266,7 +275,7 @@ __global__ void __launch_bounds__(128 * T * R + 64, I8Cfg<T, R, F>::kCtasPerSm) 
     return;
   }
   extern __shared__ __align__(128) unsigned char smem[];
-  unsigned char* sB = smem;                                                   // [NS][kc 2][N][16 B]
+  unsigned char* sB = smem;                                                   // [NS][kc 2][I8_NH][16 B]
   uint64_t* bars = reinterpret_cast<uint64_t*>(smem + (size_t)NS * Cfg::kBBytes);   // full[NS] empty[NS] accum
   uint32_t* s_tmem = reinterpret_cast<uint32_t*>(bars + 2 * NS + 1);
   const int tid = threadIdx.x, warp = tid >> 5, lane = tid & 31;
@@ -295,7 +304,7 @@ __global__ void __launch_bounds__(128 * T * R + 64, I8Cfg<T, R, F>::kCtasPerSm) 
     const int t = (warp % (4 * T)) >> 2;
     const uint4* map8 = sp.map8;
     uint32_t it = 0;                                      // pipeline iteration of the batch's first stage (same sequence in every role)
-    const uint32_t tcol0 = tmem_base + ((uint32_t)((warp & 3) * 32) << 16) + (uint32_t)(T * N + t * 8);
+    const uint32_t tcol0 = tmem_base + ((uint32_t)((warp & 3) * 32) << 16) + (uint32_t)(T * I8_ACC + t * 16);
     for (long long batch = blockIdx.x; batch < n_batches; batch += gridDim.x, local_batch++) {
       const long long slot = batch * per_batch + (tid % (128 * T));
       long long i = -1;
@@ -318,14 +327,14 @@ __global__ void __launch_bounds__(128 * T * R + 64, I8Cfg<T, R, F>::kCtasPerSm) 
       uint32_t st = (it + (uint32_t)sub) % NS, ph = ((it + (uint32_t)sub) / NS) & 1u;
 
       // one 128-bit load per cell: the 16-byte record of this hypothesis' lattice pixel (top_down_map_polar.cpp:28-37)
-      auto load_stage = [&](int k, uint4 (&rec)[2]) {
+      auto load_stage = [&](int k, uint4 (&rec)[I8_CELLS]) {
 #pragma unroll
-        for (int g = 0; g < 2; g++) {
-          const float2 tb = c_tab[2 * k + g];              // ((tab * scale) * res) * 4096; padding cells: far off the map
+        for (int g = 0; g < I8_CELLS; g++) {
+          const float2 tb = c_tab[I8_CELLS * k + g];       // ((tab * scale) * res) * 4096; padding cells: far off the map
           const uint32_t ty = (uint32_t)__float2int_rz(TDR_FADD(tb.x, oy)) + 2047u;
           const uint32_t tx = (uint32_t)__float2int_rz(TDR_FADD(tb.y, ox)) + 2047u;
           const bool ok = ty < lim_y && tx < lim_x;
-          if (TEX && g == 1) rec[g] = tex_fetch(sp.tex, ok ? (int)((tx + 1u) >> 12) : -1, (int)((ty + 1u) >> 12));
+          if (TEX && (g & 1)) rec[g] = tex_fetch(sp.tex, ok ? (int)((tx + 1u) >> 12) : -1, (int)((ty + 1u) >> 12));
           else {
             uint32_t r = map8_index<BLK>((ty + 1u) >> 12, (tx + 1u) >> 12, sp.geom.pitch);
             if (!ok) r = sp.geom.zero_rec;
@@ -333,10 +342,12 @@ __global__ void __launch_bounds__(128 * T * R + 64, I8Cfg<T, R, F>::kCtasPerSm) 
           }
         }
       };
-      auto store_stage = [&](const uint4 (&rec)[2]) {
+      auto store_stage = [&](const uint4 (&rec)[I8_CELLS]) {
         mbar_wait(bar_empty + 8 * st, ph ^ 1u);
-        // row m of the A tile = TMEM lane m (this warp's quarter), 8 columns = 32 K slots: cell 2k | cell 2k + 1
-        tmem_st8(tcol0 + st * Cfg::kACols, rec[0], rec[1]);
+        // row m of the A tiles = TMEM lane m (this warp's quarter); 8 columns = 32 K slots = the hi halves (.x .y) of the
+        // stage's four records, the next 8 columns their lo halves (.z .w)
+        tmem_st8(tcol0 + st * Cfg::kACols, make_uint4(rec[0].x, rec[0].y, rec[1].x, rec[1].y), make_uint4(rec[2].x, rec[2].y, rec[3].x, rec[3].y));
+        tmem_st8(tcol0 + st * Cfg::kACols + 8u, make_uint4(rec[0].z, rec[0].w, rec[1].z, rec[1].w), make_uint4(rec[2].z, rec[2].w, rec[3].z, rec[3].w));
         tmem_wait_st();
         tc_fence_before();
         __syncwarp();
@@ -345,7 +356,7 @@ __global__ void __launch_bounds__(128 * T * R + 64, I8Cfg<T, R, F>::kCtasPerSm) 
       };
 
       // software pipeline of depth F over this thread's stages sub, sub + R, ...: F - 1 loads ahead of every store
-      uint4 buf[F][2];
+      uint4 buf[F][I8_CELLS];
       const int J = (K_ITERS - sub + R - 1) / R;         // this thread's stages
 #pragma unroll
       for (int f = 0; f < F - 1; f++) if (f < J) load_stage(sub + f * R, buf[f]);
@@ -364,9 +375,9 @@ __global__ void __launch_bounds__(128 * T * R + 64, I8Cfg<T, R, F>::kCtasPerSm) 
       // ---- epilogue: this thread's accumulator row (s32)
       mbar_wait(bar_accum, local_batch & 1u);
       tc_fence_after();
-      const uint32_t trow = tmem_base + ((uint32_t)((warp & 3) * 32) << 16) + (uint32_t)(t * N);
+      const uint32_t trow = tmem_base + ((uint32_t)((warp & 3) * 32) << 16) + (uint32_t)(t * I8_ACC);
       const int S = sp.n_shifts;
-      const uint32_t kraw = tmem_ld1(trow + (uint32_t)(3 * I8_S_MAX));
+      const uint32_t kraw = tmem_ld1(trow + (uint32_t)I8_PROBE);
       tmem_wait_ld();
       // known cells: the gathered ones were counted by the probe row; the cells of the skipped (empty) rings only matter
       // when they can still tip the "less than half known" test, and are looked up one by one then
@@ -381,10 +392,10 @@ __global__ void __launch_bounds__(128 * T * R + 64, I8Cfg<T, R, F>::kCtasPerSm) 
         const float soy = __shfl_sync(0xffffffffu, oy, src), sox = __shfl_sync(0xffffffffu, ox, src);
         int cnt = 0;
         for (int m = lane; m < n_skip; m += 32) {
-          const float2 tb = sp.tab_g[2 * K_ITERS + m];
+          const float2 tb = sp.tab_g[I8_CELLS * K_ITERS + m];
           const uint32_t ty = (uint32_t)__float2int_rz(TDR_FADD(tb.x, soy)) + 2047u;
           const uint32_t tx = (uint32_t)__float2int_rz(TDR_FADD(tb.y, sox)) + 2047u;
-          if (ty < sp.geom.lim_y && tx < lim_x) cnt += (int)((__ldg(map8 + map8_index<BLK>((ty + 1u) >> 12, (tx + 1u) >> 12, sp.geom.pitch)).w >> 16) & 1u);
+          if (ty < sp.geom.lim_y && tx < lim_x) cnt += (int)((__ldg(map8 + map8_index<BLK>((ty + 1u) >> 12, (tx + 1u) >> 12, sp.geom.pitch)).y >> 24) & 1u);
         }
         for (int o = 16; o > 0; o >>= 1) cnt += __shfl_xor_sync(0xffffffffu, cnt, o);
         if (lane == src) known += cnt;
@@ -398,8 +409,8 @@ __global__ void __launch_bounds__(128 * T * R + 64, I8Cfg<T, R, F>::kCtasPerSm) 
 #pragma unroll 1
       for (int ch = 0; ch * 8 < S; ch++) {
         tmem_ld8(trow + (uint32_t)(ch * 8), vh);
-        tmem_ld8(trow + (uint32_t)(I8_S_MAX + ch * 8), vl);
-        tmem_ld8(trow + (uint32_t)(2 * I8_S_MAX + ch * 8), vn);
+        tmem_ld8(trow + (uint32_t)(I8_NH + ch * 8), vl);
+        tmem_ld8(trow + (uint32_t)(I8_NORM0 + ch * 8), vn);
         tmem_wait_ld();
 #pragma unroll
         for (int j = 0; j < 8; j++) {
@@ -427,6 +438,7 @@ __global__ void __launch_bounds__(128 * T * R + 64, I8Cfg<T, R, F>::kCtasPerSm) 
   } else if (warp == GW) {
     // =========================== scan-operand loader ===========================
     const bool leader = elect_one();
+    const uint32_t b_bytes = sp.diag_half_b ? Cfg::kBBytes / 2 : Cfg::kBBytes;   // diagnostic only: half the operand (wrong results)
     const uint32_t sB_u = smem_u32(sB);
     uint32_t st = 0, ph = 0;
     for (long long batch = blockIdx.x; batch < n_batches; batch += gridDim.x) {
@@ -434,8 +446,8 @@ __global__ void __launch_bounds__(128 * T * R + 64, I8Cfg<T, R, F>::kCtasPerSm) 
       for (int k = 0; k < K_ITERS; k++, src += Cfg::kBBytes) {
         mbar_wait(bar_empty + 8 * st, ph ^ 1u);
         if (leader) {
-          mbar_expect_tx(bar_full + 8 * st, Cfg::kBBytes);
-          bulk_g2s(sB_u + st * Cfg::kBBytes, src, Cfg::kBBytes, bar_full + 8 * st);
+          mbar_expect_tx(bar_full + 8 * st, b_bytes);
+          bulk_g2s(sB_u + st * Cfg::kBBytes, src, b_bytes, bar_full + 8 * st);
         }
         __syncwarp();
         if (++st == NS) { st = 0; ph ^= 1u; }
@@ -443,9 +455,10 @@ __global__ void __launch_bounds__(128 * T * R + 64, I8Cfg<T, R, F>::kCtasPerSm) 
     }
   } else {
     // =========================== MMA issuer ===========================
-    // instruction descriptor: D = s32, A = B = u8, both K-major, N, M = 128 (K = 32)
+    // instruction descriptors: D = s32, A = B = u8, both K-major, M = 128 (K = 32); N = 96 (hi halves) and 48 (lo halves)
     const bool leader = elect_one();
-    const uint32_t idesc = (2u << 4) | ((uint32_t)(N >> 3) << 17) | ((uint32_t)(128 >> 4) << 24);
+    const uint32_t idesc_hi = (2u << 4) | ((uint32_t)(I8_NH >> 3) << 17) | ((uint32_t)(128 >> 4) << 24);
+    const uint32_t idesc_lo = (2u << 4) | ((uint32_t)(I8_NL >> 3) << 17) | ((uint32_t)(128 >> 4) << 24);
     const uint32_t sB_u = smem_u32(sB);
     uint32_t st = 0, ph = 0;
     for (long long batch = blockIdx.x; batch < n_batches; batch += gridDim.x) {
@@ -453,10 +466,13 @@ __global__ void __launch_bounds__(128 * T * R + 64, I8Cfg<T, R, F>::kCtasPerSm) 
         mbar_wait(bar_full + 8 * st, ph);
         tc_fence_after();
         if (leader) {
-          const uint64_t bdesc = umma_desc(sB_u + st * Cfg::kBBytes, N * 16, 128);
+          const uint64_t bdesc = umma_desc(sB_u + st * Cfg::kBBytes, I8_NH * 16, 128);    // the lo MMA reads rows [0, 48) of the same block
 #pragma unroll
-          for (int tt = 0; tt < T; tt++)
-            umma_i8_ts(tmem_base + (uint32_t)(tt * N), tmem_base + (uint32_t)(T * N + tt * 8) + st * Cfg::kACols, bdesc, idesc, k > 0 ? 1u : 0u);
+          for (int tt = 0; tt < T; tt++) {
+            const uint32_t a_cols = tmem_base + (uint32_t)(T * I8_ACC + tt * 16) + st * Cfg::kACols;
+            umma_i8_ts(tmem_base + (uint32_t)(tt * I8_ACC), a_cols, bdesc, idesc_hi, k > 0 ? 1u : 0u);
+            umma_i8_ts(tmem_base + (uint32_t)(tt * I8_ACC + I8_NH), a_cols + 8u, bdesc, idesc_lo, k > 0 ? 1u : 0u);
+          }
           umma_commit(bar_empty + 8 * st);        // implies tcgen05.fence::before_thread_sync
           if (k == K_ITERS - 1) umma_commit(bar_accum);
         }
@@ -544,15 +560,15 @@ static int launch_i8(tdr_ctx* ctx, float res, const int32_t* dev_shifts, int n_s
     if (ctx->scan_max_pending && cudaEventQuery(ctx->scan_max_ev) == cudaSuccess) { ctx->scan_max_seen = *ctx->scan_max_pin; ctx->scan_max_pending = false; }
     if (ctx->mma_i8 != 2 && ctx->scan_max_seen > I8_MAX_COUNT) return TDR_OK;
   }
-  const int P_cap = (P + 3) & ~3, max_stages = P_cap / 2;
-  if (int e = ctx->scan_op.reserve((size_t)max_stages * I8_N * 32 + (size_t)(PLAN_HDR + 2 * P_cap) * 4)) return e;
-  int* d_plan = reinterpret_cast<int*>(ctx->scan_op.as<unsigned char>() + (size_t)max_stages * I8_N * 32);
+  const int P_cap = (P + 3) & ~3, max_stages = P_cap / I8_CELLS;
+  if (int e = ctx->scan_op.reserve((size_t)max_stages * I8_NH * 32 + (size_t)(PLAN_HDR + 2 * P_cap) * 4)) return e;
+  int* d_plan = reinterpret_cast<int*>(ctx->scan_op.as<unsigned char>() + (size_t)max_stages * I8_NH * 32);
   int* d_max = reinterpret_cast<int*>(ctx->scal.as<float>() + SC_MMA_MAXCOUNT);
   if (track_pass <= 0) TDR_CUDA(cudaMemsetAsync(d_max, 0, 8, ctx->stream));       // max count, "tensor-core kernel bailed out" flag (one verdict for all passes)
   {
     k_plan_cells<<<1, 1024, 0, ctx->stream>>>(ctx->scan_img.as<float>(), ctx->C, ctx->n_theta, ctx->n_r, dev_shifts, n_shifts,
                                               ctx->mma_skip_rings, d_plan);
-    const long long total = (long long)max_stages * I8_N;
+    const long long total = (long long)max_stages * I8_NH;
     k_build_scan_operand_i8<<<(unsigned)((total + 255) / 256), 256, 0, ctx->stream>>>(ctx->scan_img.as<float>(), ctx->C, ctx->n_theta, P,
                                                                                        d_plan, dev_shifts, n_shifts, ctx->scan_op.as<uint4>(), d_max);
     count_launch(ctx, 2);
@@ -592,6 +608,7 @@ static int launch_i8(tdr_ctx* ctx, float res, const int32_t* dev_shifts, int n_s
   sp.tab_g = ctx->tab_scaled.as<float2>();
   sp.tex = ctx->map8_tex;
   sp.maxcount = d_max; sp.bailed = d_max + 1;
+  if (const char* e = getenv("TDR_I8_DIAG_HALF_B")) sp.diag_half_b = atoi(e) ? 1 : 0;
   sp.n_work = track ? pt.n - ctx->n_uninit : ctx->n_uninit;      // tracking: an upper bound for the grid size; the kernel reads the real count
   sp.n_work_dev = track ? count_dev : nullptr;
   sp.track = track ? 1 : 0; sp.track_lo = shift_lo; sp.n_theta = ctx->n_theta;
@@ -629,8 +646,6 @@ static int launch_i8(tdr_ctx* ctx, float res, const int32_t* dev_shifts, int n_s
     case 131: TDR_LAUNCH_I8(0, 1, 3, 1); break;
     case 222: TDR_LAUNCH_I8(1, 2, 2, 2); break;
     case 223: TDR_LAUNCH_I8(2, 2, 2, 3); break;
-    case 224: TDR_LAUNCH_I8(3, 2, 2, 4); break;
-    case 233: TDR_LAUNCH_I8(4, 2, 3, 3); break;
     case 141: TDR_LAUNCH_I8(5, 1, 4, 1); break;
     case 151: TDR_LAUNCH_I8(8, 1, 5, 1); break;
     case 161: TDR_LAUNCH_I8(9, 1, 6, 1); break;
