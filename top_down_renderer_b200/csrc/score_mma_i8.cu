@@ -648,6 +648,10 @@ static int launch_i8(tdr_ctx* ctx, float res, const int32_t* dev_shifts, int n_s
     case 223: TDR_LAUNCH_I8(2, 2, 2, 3); break;
     case 141: TDR_LAUNCH_I8(5, 1, 4, 1); break;
     case 151: TDR_LAUNCH_I8(8, 1, 5, 1); break;
+    case 132: TDR_LAUNCH_I8(3, 1, 3, 2); break;
+    case 122: TDR_LAUNCH_I8(4, 1, 2, 2); break;
+    case 123: TDR_LAUNCH_I8(10, 1, 2, 3); break;
+    case 121: TDR_LAUNCH_I8(11, 1, 2, 1); break;
     case 161: TDR_LAUNCH_I8(9, 1, 6, 1); break;
     case 231: TDR_LAUNCH_I8(6, 2, 3, 1); break;
     default: TDR_LAUNCH_I8(7, 2, 3, 2); break;
