@@ -63,6 +63,8 @@ __device__ __forceinline__ void tmem_ld8(uint32_t taddr, uint32_t* v) {
 // ------------------------------------------------------------------------------------------------
 // the 16-byte map copy
 // ------------------------------------------------------------------------------------------------
+// (Splitting the record into a hi and a lo plane of 8-byte records, 16 px per line, read with two LDG.64, was measured
+// SLOWER: 4.17 ms against 3.87 ms in Morton order, 4.8-5.6 ms in row order — profiles/r02_sweep_i8.txt.)
 // Two layouts: row-major (`pitch` records per map row: a 128-byte line = 8 px of one row) or 4 x 2-px blocks (a line =
 // 4 px of two adjacent rows, `pitch` blocks per block row) — with hypotheses in Morton order the compact 2-D clusters of
 // a warp touch fewer lines of the blocked layout (12.1 against 14.6 simulated on cfg3).  One all-zero record past the

@@ -126,8 +126,10 @@ struct tdr_ctx {
   unsigned long long map8_tex = 0;     // cudaTextureObject_t over map8 (pitch-linear, border addressing)
   int mma_skip_rings = 1;    // integer kernel: do not gather lattice cells that meet no scan return under any candidate shift (TDR_MMA_SKIP_RINGS)
   int mma_i8_cfg = 141;      // integer kernel: tiles * 100 + gather threads per row * 10 + stages in flight per thread (TDR_MMA_I8_CFG)
-  int mma_sort = 0;          // integer kernel, hypothesis order inside a super-tile: 0 = pixel row, 4-px segment (its records are
-                             // row-major); 1 = Morton over 2 x 2-px cells (TDR_MMA_SORT)
+  int mma_sort = 1;          // integer kernel, hypothesis order inside a super-tile: 0 = pixel row, 4-px segment (its records are
+                             // row-major); 1 = Morton over 2 x 2-px cells with 4 x 2-px lines (TDR_MMA_SORT).  Equal while the
+                             // kernel was balanced; 6 % faster (4.13 -> 3.87 ms) once the L1 data pipe became the bound
+                             // (profiles/r02_sweep_i8.txt)
   tdr::DevBuf map8;          // rows*cols x 16 B: u16 fixed-point class distances (hi / lo bytes) + known, 4 x 2-px blocks
   bool map8_valid = false;
   float map8_q = 0.f;        // its quantum
