@@ -502,7 +502,10 @@ def measure_particles(args, wl, workload_name, rank, world, local, steps, warmup
                "roofline": {"bound": "hbm", "kernel": "k_score_mma_i8 (tcgen05 kind::i8 gather-GEMM on 16-byte records, operands in tensor memory)" if wl["shifts"] > 1 else "k_score_track",
                             "achieved": achieved, "peak": peak, "unit": "GB/s", "frac": achieved / peak,
                             "traffic": traffic, "traffic_source": traffic_src, "peak_source": peak_src,
-                            "algorithmic_bytes_per_launch": n * b_score(C), "kernel_ms": score_ms}}
+                            "algorithmic_bytes_per_launch": n * b_score(C), "kernel_ms": score_ms,
+                            "note": ("frac > 1 is expected here: the algorithmic bytes are SURVEY 8d's figure in the reference's fp32 planar "
+                                     "format, the kernel moves 16 B per visited cell and those come out of L2 (see traffic); what bounds it is "
+                                     "the L1 data pipe, 86 % busy in profiles/r02_score_i8_ncu.csv") if wl["shifts"] > 1 else None}}
         if verification is not None:
             out["verified"] = verification["verified"]
             out["verification"] = verification
