@@ -54,3 +54,27 @@ def rel_err(a, b):
     d[np.isnan(a) ^ np.isnan(b)] = np.inf
     d[(a == b)] = 0
     return d
+
+
+def assert_heading_flips_are_ties(wd, st_before, theta_dev, theta_oracle, res, tol=1e-5, scan=None):
+    """Where the device chose another candidate heading than the oracle, the two candidates' costs (the oracle's own, for
+    that particle) must agree to `tol` relative: a flip is only legitimate as a tie broken by rounding
+    (state_particle.cpp:193-204 takes the first strict minimum).  Returns the number of flips."""
+    diff = np.flatnonzero(np.asarray(theta_dev) != np.asarray(theta_oracle))
+    if diff.size == 0:
+        return 0
+    src = st_before[diff]
+    scales = np.unique(src["scale"])
+    assert scales.size == 1, "helper written for one scale"
+    cen = np.stack([(src["dx_m"] * src["scale"]).astype(np.float32) + src["init_x_px"],
+                    (src["dy_m"] * src["scale"]).astype(np.float32) + src["init_y_px"]], axis=1).astype(np.float32)
+    costs = orc.cost_grid(cen, float(scales[0]), wd.fp, wd.layers, wd.mask, wd.resolution, wd.tab, N_THETA, N_R,
+                          wd.scan if scan is None else scan, res, wd.shifts).astype(np.float64)
+    th = np.asarray(wd.thetas, dtype=np.float32)
+    kd = np.array([int(np.flatnonzero(th == t)[0]) for t in np.asarray(theta_dev)[diff]])
+    ko = np.array([int(np.flatnonzero(th == t)[0]) for t in np.asarray(theta_oracle)[diff]])
+    cd, co = costs[np.arange(diff.size), kd], costs[np.arange(diff.size), ko]
+    gap = np.abs(cd - co) / np.maximum(np.abs(co), 1e-300)
+    gap[np.isnan(cd) & np.isnan(co)] = 0
+    assert np.all(gap <= tol), (diff[np.argmax(gap)], float(np.nanmax(gap)))
+    return int(diff.size)
