@@ -44,6 +44,12 @@ __device__ __forceinline__ double seq_elem(const SeqJob& job, long long j) {
   return 0.0;
 }
 __device__ __forceinline__ float seq_add(float S, double d) { return (float)((double)S + d); }
+// the IncPair of one addend.  Mode 0 chains (plain float weights, `strict` false) hold float values in their double
+// slots: the 32-bit form gives the same pair (tdr_math.cuh: "for a float-valued d this reduces to inc_pair") at a third
+// of the instructions of the 64-bit one — k_seq_tile_aggs is the second largest cost of a normalisation.
+__device__ __forceinline__ IncPair elem_pair(double x, int E, bool double_addends, bool* irregular) {
+  return double_addends ? inc_pair_d(x, E, true, irregular) : inc_pair((float)x, E, irregular);
+}
 
 __device__ __forceinline__ IncPair shfl_up_pair(IncPair v, int d) {
   IncPair r;
@@ -375,7 +381,7 @@ __global__ void __launch_bounds__(SQ_THREADS) k_seq_tile_aggs(SeqJobs jobs, SeqW
     IncPair agg; agg.a = agg.b = 0;
     if (E <= 127) {
 #pragma unroll
-      for (int k = 0; k < SQ_ITEMS; k++) { bool irr; agg = pair_compose(agg, inc_pair_d(x[k], E, job.mode != 0, &irr)); }
+      for (int k = 0; k < SQ_ITEMS; k++) { bool irr; agg = pair_compose(agg, elem_pair(x[k], E, job.mode != 0, &irr)); }
     }
     IncPair total;
     block_scan_pairs(agg, s_warp, &total);
@@ -421,7 +427,7 @@ __device__ float seq_resolve_tile(const double (&x)[SQ_ITEMS], bool strict, int 
     for (int k = 0; k < SQ_ITEMS; k++) {
       const int j = threadIdx.x * SQ_ITEMS + k;
       IncPair pr; pr.a = pr.b = 0;
-      if (j >= first && j < tile_len) { bool irr; pr = inc_pair_d(x[k], E, strict, &irr); }
+      if (j >= first && j < tile_len) { bool irr; pr = elem_pair(x[k], E, strict, &irr); }
       agg = pair_compose(agg, pr);
       loc[k] = agg;
     }
