@@ -7,21 +7,27 @@
 // fp16 hi/lo kernel (score_mma_list.cu) reads one 32-byte record per (hypothesis, cell) and is bound by L1 wavefronts —
 // 24.9 per warp load measured, one per distinct 128-byte line inside a half warp (x ~1.2 for partly used lines), at
 // most one per clock and SM.  A 128-byte line of that layout holds 4 pixels.  Here a pixel is 16 bytes:
-//     bytes 2c, 2c+1 : hi / lo byte of v_c = round(w_c * dist_c / q), q = 50 max(w) / 65535      (c < 7)
-//     byte  14       : known (0 / 1)                      byte 15: 0
-// so a line holds 8 pixels of a map row and neighbouring hypotheses share lines twice as often; one 128-bit load per
-// (hypothesis, cell) — 1.9 records / clk / SM measured for warps whose lanes lie within 8 x 8 px (tools/tex_bench.cu),
-// against 1.5 for 256-bit loads of pixel pairs and 1.0 for the 32-byte records.  The kernel was ISSUE-bound on its
-// gather threads (78 instructions per record, profiles/r02_SUMMARY.md), so the index arithmetic is fixed point
-// (tdr_math.cuh lattice_fixed) on a table pre-multiplied by scale * res * 4096 in constant memory — which needs ONE
-// scale for all hypotheses of a launch (FilterParams::fixed_scale; checked on the device).
-// Two cells make one K = 32 step of tcgen05.mma.kind::i8 (u8 x u8 -> s32, exact):
-//     A[m, 16 j + b]  = byte b of the record of hypothesis m at cell 2k + j                       (tensor memory)
-//     B rows n = s        : u8 class counts of the shifted scan cell at the hi bytes    -> Xhi[s]      (s < S <= 40)
-//            n = 40 + s   : the same counts at the lo bytes                              -> Xlo[s]
-//            n = 80 + s   : the class-summed count at the known byte                     -> norm[s]
-//            n = 120      : 1 at the known byte                                          -> number of known cells
+//     bytes 0..6  : hi bytes of v_c = round(w_c * dist_c / q), q = 50 max(w) / 65535   (c < 7)     byte 7 : known (0 / 1)
+//     bytes 8..14 : lo bytes of v_c                                                               byte 15: 0
+// so a line holds 8 pixels (a 4 x 2 block, or 8 px of a row) and neighbouring hypotheses share lines twice as often; one
+// 128-bit load per (hypothesis, cell) — 1.9 records / clk / SM measured for warps whose lanes lie within 8 x 8 px
+// (tools/tex_bench.cu), against 1.5 for 256-bit loads of pixel pairs and 1.0 for the 32-byte records.  The kernel was
+// ISSUE-bound on its gather threads (78 instructions per record, profiles/r02_SUMMARY.md), so the index arithmetic is
+// fixed point (tdr_math.cuh lattice_fixed) on a table pre-multiplied by scale * res * 4096 in constant memory — which
+// needs ONE scale for all hypotheses of a launch (FilterParams::fixed_scale; checked on the device).
+// FOUR cells make one K = 32 step of tcgen05.mma.kind::i8 (u8 x u8 -> s32, exact), 8 K slots per cell (class 0..6 and
+// the known / zero byte).  The hi halves of the four records are one A tile, the lo halves a second one (tensor memory),
+// and both meet the SAME scan block B of 96 rows:
+//     B rows n = s        : u8 class counts of the scan cell under candidate shift s, slots 0..6     (s < S <= 40)
+//            n = 48 + s   : their sum at slot 7
+//            n = 88       : 1 at slot 7
+//     hi MMA (N = 96, all rows)   : Xhi[s], norm[s] = sum of known x total count, number of known cells
+//     lo MMA (N = 48, rows 0..47) : Xlo[s]                                  (rows 40..47 are zero)
 //     cost[s] = 0.01 q (256 Xhi[s] + Xlo[s]) / norm[s]
+// (The first version kept a class's hi and lo byte next to each other — two cells per K step — and needed separate hi
+// and lo count rows: 128 rows x 32 B per TWO cells.  With that, almost half of the bytes reaching an SM were the scan
+// operand streamed by cp.async.bulk, and a probe that streamed half of it ran 14 % faster; sharing one block between
+// the halves of four cells cut the operand to 768 B per cell: 4.70 -> 4.13 ms, same sums, same bits.)
 // Integer sums are exact; the only error is the 16-bit quantisation of w_c * dist_c: |d cost| <= 0.01 q / 2, i.e. a
 // relative weight error <= 0.005 q / regularization.  The host takes this path only where that bound is below 9e-6
 // (regularization >= 0.42 max(w): the launch file's 0.7 qualifies, the code default 0.15 does not) and the scan
