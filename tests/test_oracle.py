@@ -584,3 +584,21 @@ def test_ref_mini_fixture_from_the_reference_build():
     assert np.array_equal(s_o["have_init"], g["search_scored"]["have_init"]) and (s_o["theta"] == g["search_scored"]["theta"]).mean() >= 0.98
     s_wn, _, _ = orc.normalize(r.copy(), g["search_last_dist"])
     assert np.allclose(s_wn, g["search_weights_norm"], rtol=1e-6, atol=1e-12) and not np.isnan(g["search_weights_norm"]).any()
+
+
+def test_heading_flip_helper_accepts_ties_and_rejects_real_flips():
+    """tests.common.assert_heading_flips_are_ties (what the GPU tests use to judge a heading that differs from the
+    oracle's): identical headings pass with zero flips, a heading moved five candidates away is rejected."""
+    from tests.common import N_R, N_THETA, assert_heading_flips_are_ties, make_world
+    from top_down_renderer_b200 import synth
+    wd = make_world(h=300, w=300)
+    st, _ = synth.particles_global(64, wd.class_map)
+    st_o = st.copy()
+    orc.score_all(st_o, wd.fp, wd.layers, wd.mask, 1.0, wd.tab, N_THETA, N_R, wd.scan, 4.0, wd.thetas, wd.shifts)
+    assert assert_heading_flips_are_ties(wd, st, st_o["theta"], st_o["theta"], 4.0) == 0
+    th = np.asarray(wd.thetas, dtype=np.float32)
+    bad = st_o["theta"].copy()
+    k = int(np.flatnonzero(th == bad[3])[0])
+    bad[3] = th[(k + 5) % len(th)]
+    with pytest.raises(AssertionError):
+        assert_heading_flips_are_ties(wd, st, bad, st_o["theta"], 4.0)
