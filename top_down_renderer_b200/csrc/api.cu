@@ -211,6 +211,9 @@ void tdr_destroy(tdr_ctx* c) {
   c->map8.release();
   if (c->scan_max_ev) cudaEventDestroy(c->scan_max_ev);
   if (c->scan_max_pin) cudaFreeHost(c->scan_max_pin);
+  if (c->prep_stream) { cudaStreamSynchronize(c->prep_stream); cudaStreamDestroy(c->prep_stream); }
+  if (c->prep_fork) cudaEventDestroy(c->prep_fork);
+  if (c->prep_done) cudaEventDestroy(c->prep_done);
   if (c->grid_key_pin) cudaFreeHost(c->grid_key_pin);
   for (int k = 0; k <= TDR_N_STAGES; k++) if (c->stage_ev[k]) cudaEventDestroy(c->stage_ev[k]);
   for (int k = 0; k < 2; k++) { if (c->refine_copied[k]) cudaEventDestroy(c->refine_copied[k]); if (c->refine_binned[k]) cudaEventDestroy(c->refine_binned[k]); c->refine_stage[k].release(); }
@@ -816,6 +819,8 @@ int tdr_pf_update(tdr_ctx* ctx, float res, float u, int64_t M) {
 int tdr_step(tdr_ctx* ctx, float res, float ang_res, int n_theta, int n_r, float u, int64_t M) {
   CTX_CHECK(ctx);
   stage_mark(ctx, TDR_STAGE_RENDER);
+  if (int e = sync_uninit(ctx)) return e;
+  if (int e = score_i8_prepare_async(ctx)) return e;      // the particle sort of a theta search starts beside the rasteriser
   if (int e = render_polar_resident(ctx, res, ang_res, n_theta, n_r)) return e;
   return update_resident(ctx, res, u, M);
 }

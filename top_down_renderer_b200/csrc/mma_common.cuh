@@ -418,6 +418,7 @@ static int sync_const_tab(tdr_ctx* ctx, int P) {
 // number is not known on the host — *count_dev (if given) receives the device word that holds it once the scatter ran
 static int build_perm(tdr_ctx* ctx, bool grid_mode, long long n_items, bool morton = false, bool select_init = false,
                       int shift_lo = 0, int shift_hi = 0, const int** count_dev = nullptr) {
+  if (int e = score_i8_prepare_join(ctx)) return e;                  // never two sorts into the same buffers at once
   if (grid_mode && ctx->perm_grid_n == n_items) return TDR_OK;       // resident centres, same map: the order still holds
   ctx->perm_grid_n = -1;
   tdr::Particles& pt = ctx->part[ctx->cur];

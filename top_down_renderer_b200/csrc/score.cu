@@ -385,7 +385,7 @@ static int fill_params(tdr_ctx* ctx, float res, ScoreParams* sp) {
   return TDR_OK;
 }
 
-int score_particles(tdr_ctx* ctx, float res) {
+static int score_particles_impl(tdr_ctx* ctx, float res) {
   ScoreParams sp;
   if (int e = fill_params(ctx, res, &sp)) return e;
   tdr::Particles& pt = ctx->part[ctx->cur];
@@ -520,6 +520,12 @@ int local_cart(tdr_ctx* ctx, float cx, float cy, float rot, float res, int out_r
   count_launch(ctx);
   TDR_CUDA(cudaGetLastError());
   return TDR_OK;
+}
+
+int score_particles(tdr_ctx* ctx, float res) {
+  const int e = score_particles_impl(ctx, res);
+  const int j = score_i8_prepare_join(ctx);        // a head start the chosen kernels did not consume ends here, used or not
+  return e ? e : j;
 }
 
 }  // namespace tdr

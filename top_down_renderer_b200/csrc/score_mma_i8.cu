@@ -552,6 +552,56 @@ static int build_map8(tdr_ctx* ctx, float q, bool blocked, const uint4** out, Ge
 
 // returns TDR_OK and sets *used = true when the integer tensor-core path was launched (it may still leave the work to
 // the guarded CUDA-core launch behind it: scan counts above 255, decided on the device)
+// (min, max) of the scale bits over the particles of a launch into the context's SC_MMA_SCALE_RANGE words
+static int scale_range(tdr_ctx* ctx, tdr::Particles& pt, bool track) {
+  uint32_t* d_range = reinterpret_cast<uint32_t*>(ctx->scal.as<float>() + SC_MMA_SCALE_RANGE);
+  static const uint32_t init_range[2] = {0xffffffffu, 0u};
+  TDR_CUDA(cudaMemcpyAsync(d_range, init_range, 8, cudaMemcpyHostToDevice, ctx->stream));
+  const int blocks = (int)((pt.n + 1023) / 1024 < ctx->sm_count * 4 ? (pt.n + 1023) / 1024 : ctx->sm_count * 4);
+  k_scale_range<<<blocks < 1 ? 1 : blocks, 256, 0, ctx->stream>>>(pt.scale.as<float>(), pt.have_init.as<uint8_t>(), pt.n, d_range, track ? 1 : 0);
+  count_launch(ctx);
+  TDR_CUDA(cudaGetLastError());
+  return TDR_OK;
+}
+
+// Head start for a theta search: everything that depends on the PARTICLES only (the spatial sort, 5 small kernels, and the
+// scale check) runs on a side stream while the main stream rasterises the scan and builds the scan-dependent operand —
+// ~0.1 ms of dependent small launches that used to sit between the rasteriser and the score kernel.  Only for sets in
+// which every particle is searched (a mixed set sorts twice into the same buffer); the decision whether the integer
+// kernel runs at all is taken later as before — a head start that is not used is simply joined.
+int score_i8_prepare_async(tdr_ctx* ctx) {
+  tdr::Particles& pt = ctx->part[ctx->cur];
+  float q = 0.f;
+  if (int e = score_i8_prepare_join(ctx)) return e;           // a head start nobody consumed (an error in between) is stale: drop it
+  if (ctx->uninit_pending || pt.n <= 0 || ctx->n_uninit != pt.n) return TDR_OK;
+  if (!(ctx->mma_kernel == 0 || ctx->mma_kernel == 3) || ctx->score_impl == 1) return TDR_OK;
+  if (ctx->score_impl == 0 && (long long)ctx->n_uninit * ctx->count_scale < 4096) return TDR_OK;
+  const int n_shifts = (int)ctx->search_shifts.size();
+  if (!i8_usable(ctx, n_shifts, &q)) return TDR_OK;
+  if (!ctx->prep_stream) {
+    TDR_CUDA(cudaStreamCreateWithFlags(&ctx->prep_stream, cudaStreamNonBlocking));
+    TDR_CUDA(cudaEventCreateWithFlags(&ctx->prep_fork, cudaEventDisableTiming));
+    TDR_CUDA(cudaEventCreateWithFlags(&ctx->prep_done, cudaEventDisableTiming));
+  }
+  TDR_CUDA(cudaEventRecord(ctx->prep_fork, ctx->stream));          // after everything that last read the sort buffers
+  TDR_CUDA(cudaStreamWaitEvent(ctx->prep_stream, ctx->prep_fork, 0));
+  cudaStream_t main_stream = ctx->stream;
+  ctx->stream = ctx->prep_stream;                                   // the helpers launch on ctx->stream
+  int e = build_perm(ctx, false, pt.n, ctx->mma_sort == 1);
+  if (!e) e = scale_range(ctx, pt, false);
+  ctx->stream = main_stream;
+  if (e) { cudaStreamSynchronize(ctx->prep_stream); return e; }
+  TDR_CUDA(cudaEventRecord(ctx->prep_done, ctx->prep_stream));
+  ctx->prep_pending = true;
+  return TDR_OK;
+}
+int score_i8_prepare_join(tdr_ctx* ctx) {
+  if (!ctx->prep_pending) return TDR_OK;
+  TDR_CUDA(cudaStreamWaitEvent(ctx->stream, ctx->prep_done, 0));
+  ctx->prep_pending = false;
+  return TDR_OK;
+}
+
 // One launch of the integer kernel.  Search (track_pass < 0): the particles without a heading against the candidate
 // list.  Tracking pass p >= 0: the particles whose heading maps to a row shift in [shift_lo, shift_lo + n_shifts), against
 // exactly those shifts (dev_shifts = shift_lo, shift_lo + 1, ...); each keeps the column of its own shift.
@@ -586,21 +636,23 @@ static int launch_i8(tdr_ctx* ctx, float res, const int32_t* dev_shifts, int n_s
     ctx->scan_max_pending = true;
   }
   const int* count_dev = nullptr;
-  if (track) { if (int e = build_perm(ctx, false, ctx->part[ctx->cur].n, ctx->mma_sort == 1, true, shift_lo, shift_lo + n_shifts, &count_dev)) return e; }
+  const bool prepared = !track && ctx->prep_pending;          // sort + scale check already under way on the side stream
+  if (prepared) { if (int e = score_i8_prepare_join(ctx)) return e; }
+  else if (track) {
+    if (int e = score_i8_prepare_join(ctx)) return e;         // (a stale head start must not race with this sort)
+    if (int e = build_perm(ctx, false, ctx->part[ctx->cur].n, ctx->mma_sort == 1, true, shift_lo, shift_lo + n_shifts, &count_dev)) return e;
+  }
   else if (int e = build_perm(ctx, false, ctx->part[ctx->cur].n, ctx->mma_sort == 1)) return e;
   tdr::Particles& pt = ctx->part[ctx->cur];
   // the lattice offsets for this launch's scale and radial resolution, x 4096, into constant memory; the scale comes
   // from the particles themselves (one value for all of them, else the kernel leaves the search to the CUDA cores)
   {
     uint32_t* d_range = reinterpret_cast<uint32_t*>(ctx->scal.as<float>() + SC_MMA_SCALE_RANGE);
-    const uint32_t init_range[2] = {0xffffffffu, 0u};
-    TDR_CUDA(cudaMemcpyAsync(d_range, init_range, 8, cudaMemcpyHostToDevice, ctx->stream));
-    const int blocks = (int)((pt.n + 1023) / 1024 < ctx->sm_count * 4 ? (pt.n + 1023) / 1024 : ctx->sm_count * 4);
-    k_scale_range<<<blocks < 1 ? 1 : blocks, 256, 0, ctx->stream>>>(pt.scale.as<float>(), pt.have_init.as<uint8_t>(), pt.n, d_range, track ? 1 : 0);
+    if (!prepared) { if (int e = scale_range(ctx, pt, track)) return e; }
     if (int e = ctx->tab_scaled.reserve((size_t)(P_cap + 4) * 8)) return e;
     k_scale_tab4096<<<(P_cap + 4 + 255) / 256, 256, 0, ctx->stream>>>(ctx->tab.as<float2>(), P, d_plan, d_range, res,
                                                                        ctx->tab_scaled.as<float2>(), d_max + 1);
-    count_launch(ctx, 2);
+    count_launch(ctx);
     TDR_CUDA(cudaGetLastError());
     TDR_CUDA(cudaMemcpyToSymbolAsync(c_tab, ctx->tab_scaled.p, (size_t)(P_cap + 4) * 8, 0, cudaMemcpyDeviceToDevice, ctx->stream));
     g_tab_on_device[ctx->device % MMA_MAX_DEVICES] = 0;

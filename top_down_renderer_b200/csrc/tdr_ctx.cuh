@@ -189,6 +189,9 @@ struct tdr_ctx {
   // kernels whose dynamic shared-memory opt-in has been set ON THIS CONTEXT'S DEVICE (function attributes are per
   // device; a process may hold contexts on several)
   tdr::DevBuf ident_shifts; int ident_shifts_n = 0;   // 0 .. n_theta - 1 on the device (tracking passes of the integer kernel)
+  // the particle-dependent preparation of a theta search (spatial sort, scale check) started on a side stream before the
+  // scan is rasterised (score_i8_prepare_async); the search launch joins it
+  cudaStream_t prep_stream = nullptr; cudaEvent_t prep_fork = nullptr, prep_done = nullptr; bool prep_pending = false;
   int count_scale = 1;                  // ranks sharing the particle set: kernel choices go by the GLOBAL count, so that
                                         // weights (hence resampled indices) do not depend on the number of ranks
   void* shard = nullptr;               // tdr::Shard (shard.cu): NCCL communicator, peer-mapped export slots
@@ -304,7 +307,9 @@ int score_mma_list(tdr_ctx*, float res, bool grid_mode, long long n_items, float
                    int n_shifts, bool* used);
 // score_mma_i8.cu
 int score_mma_i8(tdr_ctx*, float res, const int32_t* dev_shifts, int n_shifts, bool* used);
-int score_mma_i8_track(tdr_ctx*, float res, bool* used);   // large tracked sets, in passes of 40 row shifts
+int score_mma_i8_track(tdr_ctx*, float res, bool* used);
+int score_i8_prepare_async(tdr_ctx*);   // optional head start for the next theta search (pure search sets only)
+int score_i8_prepare_join(tdr_ctx*);    // no-op when nothing is pending   // large tracked sets, in passes of 40 row shifts
 // weights.cu
 int normalize(tdr_ctx*, bool lazy_stddev = false);   // lazy: skip the lower-half deviation when no weight is NaN (stats[3] undefined then)
 int build_prefix(tdr_ctx*);
