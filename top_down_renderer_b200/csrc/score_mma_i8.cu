@@ -252,7 +252,6 @@ struct I8Params {
   const float* thetas; int n_shifts;
   unsigned long long tex;           // the same records as a pitch-linear 2-D texture (border = zero record); 0: not used
   float q001;                       // 0.01 * q: accumulator units -> cost
-  int diag_half_b;                  // TDR_I8_DIAG_HALF_B=1: stream only half of every operand block — a TIMING probe, results are wrong
   const int* maxcount; int* bailed; // device-side preconditions: scan counts fit a byte, one scale for all hypotheses
 };
 
@@ -446,7 +445,6 @@ __global__ void __launch_bounds__(128 * T * R + 64, I8Cfg<T, R, F>::kCtasPerSm) 
   } else if (warp == GW) {
     // =========================== scan-operand loader ===========================
     const bool leader = elect_one();
-    const uint32_t b_bytes = sp.diag_half_b ? Cfg::kBBytes / 2 : Cfg::kBBytes;   // diagnostic only: half the operand (wrong results)
     const uint32_t sB_u = smem_u32(sB);
     uint32_t st = 0, ph = 0;
     for (long long batch = blockIdx.x; batch < n_batches; batch += gridDim.x) {
@@ -454,8 +452,8 @@ __global__ void __launch_bounds__(128 * T * R + 64, I8Cfg<T, R, F>::kCtasPerSm) 
       for (int k = 0; k < K_ITERS; k++, src += Cfg::kBBytes) {
         mbar_wait(bar_empty + 8 * st, ph ^ 1u);
         if (leader) {
-          mbar_expect_tx(bar_full + 8 * st, b_bytes);
-          bulk_g2s(sB_u + st * Cfg::kBBytes, src, b_bytes, bar_full + 8 * st);
+          mbar_expect_tx(bar_full + 8 * st, Cfg::kBBytes);
+          bulk_g2s(sB_u + st * Cfg::kBBytes, src, Cfg::kBBytes, bar_full + 8 * st);
         }
         __syncwarp();
         if (++st == NS) { st = 0; ph ^= 1u; }
@@ -668,7 +666,6 @@ static int launch_i8(tdr_ctx* ctx, float res, const int32_t* dev_shifts, int n_s
   sp.tab_g = ctx->tab_scaled.as<float2>();
   sp.tex = ctx->map8_tex;
   sp.maxcount = d_max; sp.bailed = d_max + 1;
-  if (const char* e = getenv("TDR_I8_DIAG_HALF_B")) sp.diag_half_b = atoi(e) ? 1 : 0;
   sp.n_work = track ? pt.n - ctx->n_uninit : ctx->n_uninit;      // tracking: an upper bound for the grid size; the kernel reads the real count
   sp.n_work_dev = track ? count_dev : nullptr;
   sp.track = track ? 1 : 0; sp.track_lo = shift_lo; sp.n_theta = ctx->n_theta;
