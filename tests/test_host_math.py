@@ -332,3 +332,36 @@ def test_lean_lattice_coordinate_equals_the_literal_form(hm):
     assert hm.hm_lattice_coord(-0.5, 10) == -1 and hm.hm_lattice_coord(np.nextafter(np.float32(-0.5), np.float32(0)), 10) == 0
     assert hm.hm_lattice_coord(9.5, 10) == -1 and hm.hm_lattice_coord(np.nextafter(np.float32(9.5), np.float32(0)), 10) == 9
     assert hm.hm_lattice_coord(0.5, 10) == 1 and hm.hm_lattice_coord(0.49999997, 10) == 0 and hm.hm_lattice_coord(float("nan"), 10) == -1
+
+
+def test_integer_record_format_error_bound():
+    """The 16-byte map record of csrc/score_mma_i8.cu in numpy: v_c = round(w_c dist_c / q) split into hi / lo bytes, u8 scan
+    counts, exact integer sums  ->  cost = 0.01 q (256 Xhi + Xlo) / norm.  The claims the host relies on when it picks that
+    kernel: |cost - exact cost| <= 0.005 q, hence a relative weight error <= 0.005 q / regularization, below 9e-6 whenever
+    regularization >= 0.42 max(w) — and the hi / lo split loses nothing (256 hi + lo == v)."""
+    rng = np.random.default_rng(5)
+    C, P, S = 6, 2500, 40
+    w = rng.uniform(0.2, 1.0, C)
+    wmax = float(w.max())
+    q = 50.0 * wmax / 65535.0
+    worst_cost, worst_rel = 0.0, 0.0
+    for trial in range(20):
+        dist = np.minimum(rng.exponential(15.0, (P, C)), 50.0)              # class distances, capped like the map's
+        x = w[None, :] * dist                                               # what the fp32 kernels multiply the counts with
+        v = np.clip(np.rint(x / q), 0, 65535).astype(np.int64)
+        hi, lo = v >> 8, v & 255
+        assert np.array_equal(256 * hi + lo, v) and hi.max() <= 255
+        known = (rng.random(P) > 0.1).astype(np.int64)
+        counts = rng.integers(0, 256, (S, P, C)) * (rng.random((S, P, 1)) < 0.3)   # sparse scan, counts fit a byte
+        tot = counts.sum(2)
+        xhi = (counts * (hi * known[:, None])[None]).sum((1, 2))
+        xlo = (counts * (lo * known[:, None])[None]).sum((1, 2))
+        norm = (tot * known[None]).sum(1)
+        ok = norm > 0
+        cost_int = 0.01 * q * (256.0 * xhi[ok] + xlo[ok]) / norm[ok]
+        cost_ref = 0.01 * (counts * (x * known[:, None])[None]).sum((1, 2))[ok] / norm[ok]
+        worst_cost = max(worst_cost, float(np.abs(cost_int - cost_ref).max()))
+        reg = 0.42 * wmax
+        worst_rel = max(worst_rel, float((np.abs(1 / (cost_int + reg) - 1 / (cost_ref + reg)) * (cost_ref + reg)).max()))
+    assert worst_cost <= 0.005 * q * (1 + 1e-9), (worst_cost, 0.005 * q)
+    assert worst_rel <= 9e-6, worst_rel
