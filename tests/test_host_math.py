@@ -365,3 +365,38 @@ def test_integer_record_format_error_bound():
         worst_rel = max(worst_rel, float((np.abs(1 / (cost_int + reg) - 1 / (cost_ref + reg)) * (cost_ref + reg)).max()))
     assert worst_cost <= 0.005 * q * (1 + 1e-9), (worst_cost, 0.005 * q)
     assert worst_rel <= 9e-6, worst_rel
+
+
+def test_packed_edt_row_pass_model():
+    """The arithmetic of k_edt_rows_dpx (csrc/map_build.cu) in numpy: 16-bit words g^2 with 0x7fff for "no seed", squared
+    offsets up to (R + 7)^2 added WITHOUT saturation (the DPX add wraps at 2^16 — so nothing may reach it), minimum over
+    the 2R + 8 taps a thread's eight pixels share, then min(d2, capcode).  Must equal the windowed scalar scan of
+    k_edt_horizontal for every resolution the packed pass accepts."""
+    rng = np.random.default_rng(8)
+    for resolution in (2.0, 1.0, 0.5, 0.3):
+        capcode = next(d2 for d2 in range(1 << 20) if np.float32(np.sqrt(np.float32(d2))) * np.float32(resolution) >= np.float32(50.0))
+        rcap = int(np.ceil(np.sqrt(capcode))) + 1
+        R = (rcap + 3) // 4 * 4
+        assert (R + 7) ** 2 <= 0x7fff and capcode <= 0x7fff
+        cols = 700
+        g = rng.integers(0, rcap + 1, cols)
+        g[rng.random(cols) < 0.85] = 255                                      # sparse seeds
+        g2 = np.where(g == 255, 0x7fff, g * g).astype(np.int64)
+        assert (g2.max() + (R + 7) ** 2) < (1 << 16)                          # the unsaturated 16-bit add cannot wrap
+        pad = np.full(R + 8, 0x7fff, dtype=np.int64)
+        row = np.concatenate([pad, g2, pad])
+        got = np.empty(cols, dtype=np.int64)
+        for xb in range(0, cols, 8):                                          # a thread's eight pixels and their shared taps
+            taps = row[xb + 8: xb + 8 + 2 * R + 8]                            # source columns xb - R .. xb + R + 7
+            src = np.arange(xb - R, xb + R + 8)
+            for p in range(min(8, cols - xb)):
+                d = src - (xb + p)
+                got[xb + p] = min(int((taps + d * d).min()), capcode)
+        want = np.empty(cols, dtype=np.int64)
+        for x in range(cols):
+            best = 0x3fffffff
+            for dx in range(-rcap, rcap + 1):
+                if 0 <= x + dx < cols and g[x + dx] != 255:
+                    best = min(best, dx * dx + int(g[x + dx]) ** 2)
+            want[x] = min(best, capcode)
+        assert np.array_equal(got, want), resolution
