@@ -153,3 +153,46 @@ def test_sharded_update_equals_single_process(world, split):
     assert np.array_equal(np.concatenate([r[3] for r in res]), idx)
     assert np.array_equal(np.concatenate([r[4] for r in res]), st_new)
     assert np.array_equal(np.concatenate([r[5] for r in res]), ld_new)
+
+
+def test_grid_mailbox_exchange_protocol_model():
+    """The protocol of tdr_grid_peer_exchange (csrc/api.cu: k_grid_exchange) as a state machine under random interleavings:
+    every rank MINs its key into slot e & 1 of EVERY rank's mailbox, then bumps that rank's arrival counter; it waits until
+    its own counter shows ranks x (uses of the slot), reads the minimum and resets the key slot for exchange e + 2.
+    Counters never reset.  Claim: whatever the interleaving, every rank reads the minimum over all ranks' keys of THAT
+    exchange — in particular no key of exchange e + 2 can land before the owner's reset of exchange e."""
+    import random
+    INF = 1 << 62
+    for trial in range(300):
+        rnd = random.Random(trial)
+        G, E = rnd.choice([2, 3, 4, 8]), 6
+        keys = [[rnd.randrange(1, 1 << 30) for _ in range(G)] for _ in range(E)]          # keys[e][rank]
+        box_key = [[INF, INF] for _ in range(G)]
+        box_cnt = [[0, 0] for _ in range(G)]
+        got = [[None] * G for _ in range(E)]
+
+        def rank_prog(r):
+            for e in range(E):
+                slot = e & 1
+                for d in range(G):                       # lanes of the one warp: any order between ranks, in order per lane
+                    box_key[d][slot] = min(box_key[d][slot], keys[e][r]); yield
+                    box_cnt[d][slot] += 1; yield
+                target = G * (e // 2 + 1)
+                while box_cnt[r][slot] < target:
+                    yield
+                got[e][r] = box_key[r][slot]; yield
+                box_key[r][slot] = INF; yield            # ready for exchange e + 2
+
+        progs = [rank_prog(r) for r in range(G)]
+        live = list(range(G))
+        steps = 0
+        while live:
+            r = rnd.choice(live)
+            try:
+                next(progs[r])
+            except StopIteration:
+                live.remove(r)
+            steps += 1
+            assert steps < 2_000_000, "deadlock"
+        for e in range(E):
+            assert got[e] == [min(keys[e])] * G, (trial, e, got[e], min(keys[e]))
