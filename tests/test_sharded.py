@@ -196,3 +196,38 @@ def test_grid_mailbox_exchange_protocol_model():
             assert steps < 2_000_000, "deadlock"
         for e in range(E):
             assert got[e] == [min(keys[e])] * G, (trial, e, got[e], min(keys[e]))
+
+
+def test_shard_export_slot_protocol_model():
+    """tdr_shard_step's state exchange (csrc/shard.cu) as a state machine: per scan t every rank packs its states into its
+    export slot t & 1, joins the all-gather of the weights (which completes on a rank only once EVERY rank has joined it),
+    then reads the drawn particles' states out of its peers' slot t & 1.  Claim: with two slots and no other
+    synchronisation a reader never sees a slot that its owner has already overwritten with scan t + 2."""
+    import random
+    for trial in range(300):
+        rnd = random.Random(1000 + trial)
+        G, T = rnd.choice([2, 3, 4, 8]), 7
+        slots = [[-1, -1] for _ in range(G)]            # slots[rank][k] = the scan whose states it holds
+        joined = [0] * G                                # all-gathers a rank has joined
+        bad = []
+
+        def rank_prog(r):
+            for t in range(T):
+                slots[r][t & 1] = t; yield              # k_shard_pack
+                joined[r] = t + 1; yield                # enqueue the all-gather of scan t
+                while min(joined) < t + 1:              # ... which completes only when every rank has joined it
+                    yield
+                for d in rnd.sample(range(G), G):       # k_shard_resample: peer reads, any order, not atomic as a group
+                    if slots[d][t & 1] != t:
+                        bad.append((t, r, d, slots[d][t & 1]))
+                    yield
+
+        progs = [rank_prog(r) for r in range(G)]
+        live = list(range(G))
+        while live:
+            r = rnd.choice(live)
+            try:
+                next(progs[r])
+            except StopIteration:
+                live.remove(r)
+        assert not bad, bad[:3]
