@@ -133,7 +133,7 @@ __device__ float cta_exact_chain(Elem elem, long long count, bool strict, float*
       double w = 0.0;
       if (j < chunk_len) w = elem(pos + j);
       bool irr;
-      IncPair pr = inc_pair_d(w, E, strict, &irr);
+      IncPair pr = elem_pair(w, E, strict, &irr);
       agg = pair_compose(agg, pr);
       loc[k] = agg;                       // inclusive within the thread
     }
