@@ -400,3 +400,18 @@ def test_packed_edt_row_pass_model():
                     best = min(best, dx * dx + int(g[x + dx]) ** 2)
             want[x] = min(best, capcode)
         assert np.array_equal(got, want), resolution
+
+
+def test_pair_constructions_agree_for_float_addends(hm):
+    """tdr_math.cuh: inc_pair (32-bit arithmetic) and inc_pair_d (64-bit, for double addends) must give the same
+    (increment-if-even, increment-if-odd) pair — and the same "irregular" verdict — for every float addend in every
+    binade of the running sum: weights.cu picks the cheap form for chains of plain float weights."""
+    hm.hm_pair_forms_mismatches.restype = C.c_long
+    hm.hm_pair_forms_mismatches.argtypes = [C.POINTER(C.c_float), C.c_long]
+    rng = np.random.default_rng(17)
+    bits = rng.integers(0, 1 << 32, 40000, dtype=np.uint64).astype(np.uint32)          # every kind of float, NaN / inf / negative / denormal included
+    special = np.array([0x00000000, 0x80000000, 0x00000001, 0x007fffff, 0x00800000, 0x3f800000, 0x3f800001, 0x7f7fffff, 0x7f800000,
+                        0x7fc00000, 0xff800000, 0x33800000, 0x34000000, 0x4b000000, 0x4b800000], dtype=np.uint32)
+    halves = (np.arange(1, 255, dtype=np.uint32) << 23)                                 # exact powers of two: the tie cases
+    w = np.ascontiguousarray(np.concatenate([bits, special, halves, halves | 0x00400000]).view(np.float32))
+    assert hm.hm_pair_forms_mismatches(w.ctypes.data_as(C.POINTER(C.c_float)), len(w)) == 0

@@ -159,4 +159,19 @@ int hm_pair_tree_equals_chain(const float* x, int n, int E) {
   return (n == 0) || (t[0].a == chain.a && t[0].b == chain.b);
 }
 
+// inc_pair (32-bit) against inc_pair_d (64-bit) for float-valued addends: the order-exact sums use the former for chains of
+// plain float weights and the latter where the addends are doubles; for a float they must be the same pair in every binade
+long hm_pair_forms_mismatches(const float* w, long n) {
+  long bad = 0;
+  for (long i = 0; i < n; i++) {
+    for (int E = -127; E <= 127; E++) {
+      bool i1, i2;
+      const IncPair a = inc_pair(w[i], E, &i1);
+      const IncPair b = inc_pair_d((double)w[i], E, false, &i2);
+      if (a.a != b.a || a.b != b.b || i1 != i2) bad++;
+    }
+  }
+  return bad;
+}
+
 }  // extern "C"
