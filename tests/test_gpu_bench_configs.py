@@ -421,3 +421,26 @@ def test_packed_edt_row_pass_odd_shapes(h, w, C, resolution):
         del os.environ["TDR_EDT_IMPL"]
     assert np.array_equal(l1.view(np.uint32), layers.view(np.uint32)) and np.array_equal(m1, mask)
     assert np.array_equal(np.asarray(g1).view(np.uint32), np.asarray(geo).view(np.uint32))
+
+
+@pytest.mark.gpu
+@pytest.mark.parametrize("operand", ["u8", "fp16"])
+def test_theta_search_seven_classes_odd_map(monkeypatch, operand):
+    """all seven class slots of the map records in use, and a map whose sides are no multiple of the 4 x 2-px lines of the
+    integer kernel's blocked layout (1001 x 1503): the edge blocks are padding, particles sit right at the borders"""
+    wd = make_world(h=1001, w=1503, C=7, seed=23)
+    monkeypatch.setenv("TDR_MMA_I8", "0" if operand == "fp16" else "1")
+    st, ld = synth.particles_global(20_000, wd.class_map, seed=33)
+    rng = np.random.default_rng(33)
+    edge = rng.choice(len(st), 2000, replace=False)                   # a tenth of them within a few pixels of a border
+    st["init_x_px"][edge[:500]] = rng.uniform(0, 3, 500)
+    st["init_x_px"][edge[500:1000]] = rng.uniform(wd.w - 3, wd.w, 500)
+    st["init_y_px"][edge[1000:1500]] = rng.uniform(0, 3, 500)
+    st["init_y_px"][edge[1500:]] = rng.uniform(wd.h - 3, wd.h, 500)
+    c = make_ctx(wd)
+    c.set_score_impl(2)
+    got, want, st_g, st_o = run_search(wd, st, ld, c)
+    c.close()
+    e = rel_err(got, want)
+    assert np.isfinite(e).all() and e.max() <= WEIGHT_RTOL, e.max()
+    assert_headings_tie(wd, st, st_g, st_o)
